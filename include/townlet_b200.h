@@ -1,0 +1,377 @@
+/*
+ * townlet_b200.h — C ABI of the B200-native Townlet per-tick agent hot path.
+ *
+ * The reference (tachyon-beep/townlet) is pure Python and has no FFI of its
+ * own; its seams for this path are Python protocols.  This header is the
+ * boundary a maintainer binds (ctypes / cffi) underneath those protocols:
+ *
+ *   tl_obs_build      replaces WorldObservationService.build_batch
+ *                     (src/townlet/world/observations/service.py:201-233) and
+ *                     the encoders it drives (encoders/map.py:39,151,
+ *                     encoders/features.py:43, encoders/social.py:27).
+ *   tl_decay_reward   replaces WorldState._apply_need_decay
+ *                     (src/townlet/world/grid.py:1439-1455), the faint
+ *                     predicate of LifecycleManager.evaluate
+ *                     (src/townlet/lifecycle/manager.py:39-45) and
+ *                     RewardEngine.compute (src/townlet/rewards/engine.py:34-178).
+ *   tl_tick           one launch that advances n_ticks ticks in the order of
+ *                     SimulationLoop.step (src/townlet/core/sim_loop.py:632):
+ *                     decay -> faint -> reward -> episode_tick -> observe.
+ *   tl_host_tick      the same through HOST buffers (copies inside the call).
+ *   TlTownBatch       the structure-of-arrays layout replacing AgentSnapshot
+ *                     (world/agents/snapshot.py:19-44), InteractiveObject
+ *                     (world/grid.py:121-128), the relationship / rivalry
+ *                     ledgers (world/relationships.py:40, world/rivalry.py:36)
+ *                     and the spatial index (world/spatial.py:14).
+ *
+ * Conventions: every pointer in TlTownBatch / TlObsOut / TlRewardOut and the
+ * LUT pointers of TlObsParams is caller-owned DEVICE memory for the device
+ * entry points (tl_obs_build, tl_decay_reward, tl_tick) and caller-owned HOST
+ * memory for tl_host_tick.  Nothing is allocated inside the device entry
+ * points; they are asynchronous on the given stream.  Return value 0 = ok,
+ * negative = error (text from tl_last_error(), thread-local).  There is no
+ * CPU fallback: without a CUDA device every compute entry returns TL_ERR_CUDA.
+ */
+#ifndef TOWNLET_B200_H
+#define TOWNLET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TL_ABI_VERSION 1
+
+#define TL_N_NEEDS 3          /* hunger, hygiene, energy (snapshot.py:15) */
+#define TL_MAX_EDGES 8        /* upper bound for max_edges (ledger capacity) */
+#define TL_MAX_SOCIAL_SLOTS 8 /* config/observations.py:43-44 */
+#define TL_MAX_PROFILES 8
+#define TL_N_COMPS 16         /* reward component row, see TL_COMP_* */
+#define TL_N_KPI 8            /* per-town KPI row, see TL_KPI_* */
+#define TL_N_SUMMARY 8        /* per-agent integer summary row, see TL_SUM_* */
+#define TL_N_BASE_FEATURES 33 /* service.py:92-129 */
+#define TL_MAX_CTYPES 4       /* compact object:<type> channels */
+#define TL_MAX_WINDOW 21
+
+/* error codes */
+#define TL_OK 0
+#define TL_ERR_ARG (-1)
+#define TL_ERR_CUDA (-2)
+#define TL_ERR_UNSUPPORTED (-3)
+
+/* observation variants (config ObservationVariant) */
+#define TL_VARIANT_HYBRID 0
+#define TL_VARIANT_FULL 1
+#define TL_VARIANT_COMPACT 2
+
+/* phases of tl_tick */
+#define TL_PHASE_DECAY 1u
+#define TL_PHASE_REWARD 2u
+#define TL_PHASE_OBS 4u
+#define TL_PHASE_ADVANCE 8u /* tick += 1, episode_tick = (episode_tick+1) % tpd (world/core/context.py:283-289) */
+
+/*
+ * Entity word (uint32), one per thing that occupies a tile of a town.
+ * Coordinates are relative to the town's origin chosen at ingest, so that
+ * 0 <= x < grid_w and 0 <= y < grid_h.
+ *   bits  0- 9  x
+ *   bits 10-19  y
+ *   bits 20-21  kind   0 agent occupancy (cache.py:28-31)
+ *                      1 object (cache.py:33-38 / observe.py:109-147)
+ *                      2 reserved tile (world/spatial.py:117-120)
+ *   bits 22-24  ltype  landmark code, exact match on object_type:
+ *                      0 other, 1 fridge, 2 stove, 3 bed, 4 shower
+ *   bits 25-28  ctype  1 + index into compact.object_channels, 0 = none
+ *   bit  29     lm     object is a nearest-of-type candidate
+ *   bit  30     tile   object is present in the position lookup
+ * Per town, entities are stored agents first (one per agent, agent order),
+ * then objects in insertion order, then reserved tiles.
+ */
+#define TL_ENT_X(e) ((int)((e) & 1023u))
+#define TL_ENT_Y(e) ((int)(((e) >> 10) & 1023u))
+#define TL_ENT_KIND(e) (((e) >> 20) & 3u)
+#define TL_ENT_LTYPE(e) (((e) >> 22) & 7u)
+#define TL_ENT_CTYPE(e) (((e) >> 25) & 15u)
+#define TL_ENT_LM(e) (((e) >> 29) & 1u)
+#define TL_ENT_TILE(e) (((e) >> 30) & 1u)
+#define TL_ENT_PACK(x, y, kind, ltype, ctype, lm, tile)                              \
+    (((uint32_t)(x) & 1023u) | (((uint32_t)(y) & 1023u) << 10) | ((uint32_t)(kind) << 20) | \
+     ((uint32_t)(ltype) << 22) | ((uint32_t)(ctype) << 25) | ((uint32_t)(lm) << 29) |   \
+     ((uint32_t)(tile) << 30))
+#define TL_KIND_AGENT 0u
+#define TL_KIND_OBJECT 1u
+#define TL_KIND_RESERVED 2u
+#define TL_MAX_GRID 1024
+
+/* per-agent flag word */
+#define TL_F_ON_SHIFT (1u << 0)
+#define TL_F_SHIFT_SHIFT 1 /* bits 1-3: 0 pre_shift/unknown 1 on_time 2 late 3 absent 4 post_shift */
+#define TL_F_SHIFT_MASK (7u << 1)
+#define TL_F_LAST_SUCCESS (1u << 4)
+#define TL_F_IN_QUEUE (1u << 5)
+#define TL_F_RESERVATION (1u << 6)
+#define TL_F_TERMINATED (1u << 7)
+#define TL_F_REASON_SHIFT 8 /* bits 8-9: 0 none 1 faint 2 eviction 3 other */
+#define TL_F_REASON_MASK (3u << 8)
+#define TL_F_CTX_RESET (1u << 10)
+#define TL_F_PROFILE_SHIFT 11 /* bits 11-13: 0 none, 1 balanced, 2 socialite, 3 industrious, 4 stoic */
+#define TL_F_PROFILE_MASK (7u << 11)
+#define TL_F_FAINTED (1u << 14) /* written by the fused faint predicate each tick; effective terminated = TERMINATED | FAINTED */
+
+#define TL_TERM_BLOCK_NONE INT32_MIN
+
+/* reward component row (double[TL_N_COMPS]); names follow dto/rewards.py:17-60 */
+enum {
+    TL_COMP_TOTAL = 0,
+    TL_COMP_SURVIVAL,
+    TL_COMP_NEEDS_PENALTY,
+    TL_COMP_SOCIAL_BONUS,
+    TL_COMP_SOCIAL_PENALTY,
+    TL_COMP_SOCIAL_AVOIDANCE,
+    TL_COMP_SOCIAL,
+    TL_COMP_WAGE,
+    TL_COMP_PUNCTUALITY,
+    TL_COMP_TERMINAL_PENALTY,
+    TL_COMP_CLIP_ADJUSTMENT,
+    TL_COMP_HOMEOSTASIS,
+    TL_COMP_WORK,
+    TL_COMP_GUARDRAIL_ACTIVE, /* 0.0 / 1.0 */
+    TL_COMP_CLIPPED,          /* 0.0 / 1.0 */
+    TL_COMP_RESERVED
+};
+
+/* per-town KPI row (float[TL_N_KPI]) */
+enum {
+    TL_KPI_REWARD_SUM = 0,
+    TL_KPI_REWARD_SUMSQ,
+    TL_KPI_HUNGER_MIN,
+    TL_KPI_HUNGER_MEAN,
+    TL_KPI_STARVING,   /* count(hunger <= starvation_threshold), starvation.py:132-139 */
+    TL_KPI_TERMINATED, /* count */
+    TL_KPI_LATENESS_MEAN, /* publisher.py:2671-2694 */
+    TL_KPI_WALLET_MEAN
+};
+
+/* per-agent integer summary row (int32[TL_N_SUMMARY]); host derives the
+ * float64 LocalSummary metadata from it (encoders/map.py:127-146) */
+enum {
+    TL_SUM_OTHER_AGENTS = 0,
+    TL_SUM_OBJECTS,
+    TL_SUM_RESERVED,
+    TL_SUM_NEAREST_D2, /* 0 = none */
+    TL_SUM_FILLED_SLOTS,
+    TL_SUM_RELATION_SOURCE, /* 0 empty, 1 relationships, 2 rivalry_fallback */
+    TL_SUM_RESERVED0,
+    TL_SUM_RESERVED1
+};
+
+/* base feature indices, fixed by service.py:92-129 */
+enum {
+    TL_FEAT_NEED_HUNGER = 0,
+    TL_FEAT_NEED_HYGIENE,
+    TL_FEAT_NEED_ENERGY,
+    TL_FEAT_WALLET,
+    TL_FEAT_LATENESS,
+    TL_FEAT_ON_SHIFT,
+    TL_FEAT_TIME_SIN,
+    TL_FEAT_TIME_COS,
+    TL_FEAT_ATTENDANCE,
+    TL_FEAT_WAGES_WITHHELD,
+    TL_FEAT_SHIFT_PRE, /* ..+4 */
+    TL_FEAT_SLOT_NORM = 15,
+    TL_FEAT_CTX_RESET,
+    TL_FEAT_EPISODE_PROGRESS,
+    TL_FEAT_RIVALRY_MAX,
+    TL_FEAT_RIVALRY_AVOID,
+    TL_FEAT_LAST_HASH,
+    TL_FEAT_LAST_SUCCESS,
+    TL_FEAT_LAST_DURATION,
+    TL_FEAT_RESERVATION,
+    TL_FEAT_IN_QUEUE,
+    TL_FEAT_PATH_NORTH, /* south, east, west follow */
+    TL_FEAT_AGENT_RATIO = 29,
+    TL_FEAT_OBJECT_RATIO,
+    TL_FEAT_RESERVED_RATIO,
+    TL_FEAT_NEAREST
+};
+
+/*
+ * Structure-of-arrays town batch.  T towns, N agents (town-major: the agents
+ * of town t are rows town_agent_off[t] .. town_agent_off[t+1]-1, in the
+ * reference's agent iteration order), E entities.  K = max_edges is the row
+ * stride of the tie and rivalry tables, EW = embed_words the number of
+ * uint64 words per id embedding (ceil(embed_dim / 8)).
+ */
+typedef struct TlTownBatch {
+    int32_t n_towns;
+    int32_t n_agents;
+    int32_t n_entities;
+    int32_t max_edges;   /* K <= TL_MAX_EDGES */
+    int32_t embed_words; /* EW in 1..4 */
+    int32_t grid_w;      /* tiles; every town fits in grid_w x grid_h */
+    int32_t grid_h;
+    int32_t reserved0;
+
+    /* towns */
+    const int32_t* town_agent_off; /* [T+1] */
+    const int32_t* town_ent_off;   /* [T+1] */
+    int32_t* town_tick;            /* [T] world.tick */
+
+    /* entities */
+    const uint32_t* ent; /* [E] */
+
+    /* agents: identity / geometry */
+    const int32_t* pos; /* [N] window centre snapshot.position: (x & 0xffff) | (y << 16), int16 each, town-relative */
+
+    /* agents: float64 state (grid.py / snapshot.py fields stay float64) */
+    double* needs;                /* [3][N] hunger, hygiene, energy */
+    const double* wallet;         /* [N] */
+    const double* attendance;     /* [N] attendance_ratio */
+    const double* wages_withheld; /* [N] */
+    const double* wages_paid;     /* [N] employment context wages_paid (context.py:57) */
+    const double* punctuality;    /* [N] employment context punctuality (context.py:58) */
+    double* episode_total;        /* [N] RewardEngine._episode_totals (engine.py:28) */
+    const double* social_in;      /* [3][N] social_bonus, social_penalty, avoidance (engine.py:54-63); may be NULL */
+
+    /* agents: integer state */
+    int32_t* term_block_tick;            /* [N] RewardEngine._termination_block or TL_TERM_BLOCK_NONE */
+    const int32_t* lateness;             /* [N] lateness_counter */
+    const int32_t* last_action_duration; /* [N] */
+    int32_t* episode_tick;               /* [N] */
+    const int32_t* slot;                 /* [N] embedding slot (host allocator, embedding.py:35) */
+    uint32_t* flags;                     /* [N] TL_F_* */
+    const float* last_action_hash;       /* [N] blake2s(last_action_id)[:4]/2^32 (features.py:194-200) */
+    const float* personality;            /* [3][N] extroversion, forgiveness, ambition; may be NULL */
+
+    /* relationship ties in ledger insertion order (social.py:171-186) */
+    const uint8_t* tie_count;  /* [N] */
+    const uint64_t* tie_embed; /* [N][K][EW] blake2s(other_id) digest bytes, little-endian words */
+    const double* tie_trust;   /* [N][K] */
+    const double* tie_fam;     /* [N][K] */
+    const double* tie_riv;     /* [N][K] */
+
+    /* rivalry edges as returned by rivalry_top(agent, K): already sorted (rivalry.py:101-110) */
+    const uint8_t* riv_count;  /* [N] */
+    const uint64_t* riv_embed; /* [N][K][EW] */
+    const double* riv_score;   /* [N][K] */
+} TlTownBatch;
+
+/* Observation parameters derived from SimulationConfig (config/observations.py). */
+typedef struct TlObsParams {
+    int32_t variant;          /* TL_VARIANT_* */
+    int32_t window;           /* odd; hybrid.local_window or compact.map_window */
+    int32_t n_channels;       /* 4 hybrid, 6 full, 5 + n_ctypes compact */
+    int32_t n_features;       /* F */
+    int32_t n_ctypes;         /* compact object:<type> channels, <= TL_MAX_CTYPES */
+    int32_t normalize_counts; /* compact */
+    int32_t ticks_per_day;    /* hybrid.time_ticks_per_day (also for compact/full) */
+    int32_t max_slots;        /* embedding_allocator.max_slots */
+    int32_t rivalry_max_edges;/* conflict.rivalry.max_edges */
+    int32_t top_friends;
+    int32_t top_rivals;
+    int32_t embed_dim;
+    int32_t include_aggregates;
+    int32_t landmark_base;    /* feature index of fridge_dx, or -1 */
+    int32_t personality_base; /* feature index of personality_extroversion, or -1 */
+    int32_t social_base;      /* feature index of social_slot0_d0, or -1 when the snippet is disabled */
+    int32_t path_hint_ltype;  /* 2 = stove (features.py:264) */
+    int32_t reserved0;
+    double avoid_threshold;   /* conflict.rivalry.avoid_threshold */
+    /* float32 look-up tables computed on the host with the reference's own
+     * float64 expressions, so device results are bit-identical by construction */
+    const float* time_lut;        /* [tpd][2] sin, cos (features.py:142-148) */
+    const float* progress_lut;    /* [tpd+1] clamp01(e/tpd) (features.py:180-188); index min(e, tpd) */
+    const float* slot_lut;        /* [max_slots] slot/max_slots (features.py:172-176) */
+    const float* agent_ratio_lut; /* [W*W] min(1, n/max(1,W*W-1)); index min(n, W*W-1) (map.py:127-128) */
+    const float* tile_ratio_lut;  /* [W*W+1] min(1, n/W*W); index min(n, W*W) (map.py:129-130) */
+    const float* nearest_lut;     /* [2*r*r+1] clamp01(hypot/max(1,r)) by squared distance (map.py:131-134) */
+    const float* path_lut;        /* [2][W*W] dx/|d|, dy/|d| (map.py:115-125); full variant only */
+} TlObsParams;
+
+/* Reward / decay parameters derived from config.rewards (config/rewards.py). */
+typedef struct TlRewardParams {
+    double decay_rate[TL_N_NEEDS];  /* rewards.decay_rates; 0 when the key is absent */
+    double need_weight[TL_N_NEEDS]; /* rewards.needs_weights */
+    double survival_tick;
+    double wage_rate;
+    double punctuality_bonus;
+    double faint_penalty;
+    double eviction_penalty;
+    double clip_per_tick;
+    double clip_per_episode;
+    double faint_threshold;      /* 0.03, lifecycle/manager.py:41 */
+    double starvation_threshold; /* stability.starvation.hunger_threshold */
+    double need_mult[TL_MAX_PROFILES][TL_N_NEEDS];   /* profile need multipliers (agents/models.py:61-85) */
+    double reward_bias[TL_MAX_PROFILES][3];          /* social, employment, survival */
+    int32_t block_window;        /* clip.no_positive_within_death_ticks */
+    int32_t decay_personality;   /* WorldState._personality_reward_enabled (grid.py:244) */
+    int32_t reward_personality;  /* RewardEngine._reward_scaling_enabled (engine.py:30) */
+    int32_t fuse_faint;          /* rewrite TL_F_FAINTED = (hunger <= faint_threshold) after decay; reason faint unless one is set */
+} TlRewardParams;
+
+/* Observation outputs.  Row strides are in elements; per-tick strides apply in tl_tick. */
+typedef struct TlObsOut {
+    float* map;        /* [N][C][W][W] */
+    float* features;   /* [N][F] */
+    int32_t* summary;  /* [N][TL_N_SUMMARY]; may be NULL */
+    int64_t map_tick_stride;      /* elements between consecutive ticks (0 = overwrite) */
+    int64_t features_tick_stride;
+    int64_t summary_tick_stride;
+} TlObsOut;
+
+typedef struct TlRewardOut {
+    float* reward;        /* [N] total as float32; may be NULL */
+    double* comps;        /* [N][TL_N_COMPS]; may be NULL */
+    uint8_t* terminated;  /* [N] effective terminated flag of the tick; may be NULL */
+    float* kpi;           /* [T][TL_N_KPI]; may be NULL */
+    int64_t reward_tick_stride;
+    int64_t comps_tick_stride;
+    int64_t terminated_tick_stride;
+    int64_t kpi_tick_stride;
+} TlRewardOut;
+
+typedef void* tl_stream_t; /* cudaStream_t */
+
+const char* tl_last_error(void);
+int tl_abi_version(void);
+/* sizeof of the idx-th ABI struct (0 TlTownBatch, 1 TlObsParams, 2 TlRewardParams,
+ * 3 TlObsOut, 4 TlRewardOut) so bindings can verify their layout; -1 otherwise */
+int tl_abi_struct_size(int idx);
+/* number of SMs of the current device, or a negative error */
+int tl_device_sm_count(void);
+
+/* O1-O8: observation build for every agent of the batch (no state change). */
+int tl_obs_build(const TlTownBatch* batch, const TlObsParams* obs, const TlObsOut* out, tl_stream_t stream);
+
+/* D1 + T1 + R1 + K: need decay, faint predicate, reward with guardrails, per-town KPIs. */
+int tl_decay_reward(const TlTownBatch* batch, const TlRewardParams* rew, const TlRewardOut* out,
+                    uint32_t phases, tl_stream_t stream);
+
+/* Fused tick loop: for each of n_ticks ticks run the phases of the mask in
+ * SimulationLoop.step order inside one launch.  obs / obs_out may be NULL
+ * when TL_PHASE_OBS is not requested, rew / rew_out likewise. */
+int tl_tick(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardParams* rew,
+            const TlObsOut* obs_out, const TlRewardOut* rew_out, uint32_t phases, int32_t n_ticks,
+            tl_stream_t stream);
+
+/* Number of kernels launched by this library since load (the bench reports it). */
+int64_t tl_launch_count(void);
+
+/* Host-buffer entry: every pointer (batch, LUTs, outputs) is HOST memory.
+ * Copies the batch to the context's device arena, runs tl_tick, copies the
+ * requested outputs and the mutated state back, and synchronises. */
+typedef struct TlContext TlContext;
+TlContext* tl_context_create(int device);
+void tl_context_destroy(TlContext* ctx);
+int tl_host_tick(TlContext* ctx, const TlTownBatch* host_batch, const TlObsParams* obs,
+                 const TlRewardParams* rew, const TlObsOut* host_obs_out, const TlRewardOut* host_rew_out,
+                 uint32_t phases, int32_t n_ticks);
+/* bytes moved by the last tl_host_tick call */
+int64_t tl_context_last_h2d_bytes(const TlContext* ctx);
+int64_t tl_context_last_d2h_bytes(const TlContext* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOWNLET_B200_H */

@@ -1,0 +1,116 @@
+"""ctypes wrapper of ``oracle/liboracle.so`` (townlet_oracle.c) — TEST INFRASTRUCTURE ONLY.
+
+Parity status: pinned against reference-generated golden vectors
+(tests/golden/, tests/test_oracle_golden.py).  Never imported by the product
+package ``townlet_b200``; it only borrows the package's ctypes struct
+definitions so that oracle and kernels consume the identical batch bytes.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from townlet_b200 import capi
+from townlet_b200.params import ObsSpec, RewardSpec
+from townlet_b200.soa import TownBatch
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "liboracle.so"
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    src = HERE / "townlet_oracle.c"
+    hdr = HERE.parent / "include" / "townlet_b200.h"
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        subprocess.run(["make", "-C", str(HERE), "-B", "liboracle.so"], check=True, capture_output=True)
+    return LIB
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(LIB))
+        _lib.tlo_tick.restype = C.c_int
+        _lib.tlo_tick.argtypes = [
+            C.POINTER(capi.TlTownBatch),
+            C.POINTER(capi.TlObsParams),
+            C.POINTER(capi.TlRewardParams),
+            C.POINTER(capi.TlObsOut),
+            C.POINTER(capi.TlRewardOut),
+            C.c_uint32,
+            C.c_int32,
+            C.c_int32,
+        ]
+    return _lib
+
+
+def oracle_tick(
+    batch: TownBatch,
+    obs: ObsSpec | None,
+    rew: RewardSpec | None,
+    phases: int,
+    n_ticks: int = 1,
+    n_threads: int = 1,
+    want_comps: bool = True,
+) -> dict[str, np.ndarray]:
+    """Run the oracle IN PLACE on ``batch`` (host arena); returns the output arrays.
+
+    Outputs carry a leading tick axis of length ``n_ticks``.
+    """
+    lib = load()
+    n, t = batch.n_agents, batch.n_towns
+    out: dict[str, np.ndarray] = {}
+    bs = batch.struct()
+    op = rp = None
+    oo = ro = None
+    if phases & capi.TL_PHASE_OBS or (phases & capi.TL_PHASE_ADVANCE and obs is not None):
+        assert obs is not None
+        op = obs.struct()  # the oracle ignores LUT pointers
+    if phases & capi.TL_PHASE_OBS:
+        assert obs is not None
+        out["map"] = np.full((n_ticks, n, *obs.map_shape), np.nan, dtype=np.float32)
+        out["features"] = np.full((n_ticks, n, obs.n_features), np.nan, dtype=np.float32)
+        out["summary"] = np.zeros((n_ticks, n, capi.TL_N_SUMMARY), dtype=np.int32)
+        oo = capi.TlObsOut()
+        oo.map = out["map"].ctypes.data
+        oo.features = out["features"].ctypes.data
+        oo.summary = out["summary"].ctypes.data
+        oo.map_tick_stride = n * obs.map_elems
+        oo.features_tick_stride = n * obs.n_features
+        oo.summary_tick_stride = n * capi.TL_N_SUMMARY
+    if phases & (capi.TL_PHASE_DECAY | capi.TL_PHASE_REWARD):
+        assert rew is not None
+        rp = rew.struct()
+        out["reward"] = np.zeros((n_ticks, n), dtype=np.float32)
+        out["terminated"] = np.zeros((n_ticks, n), dtype=np.uint8)
+        out["kpi"] = np.zeros((n_ticks, t, capi.TL_N_KPI), dtype=np.float32)
+        ro = capi.TlRewardOut()
+        ro.reward = out["reward"].ctypes.data
+        ro.terminated = out["terminated"].ctypes.data
+        ro.kpi = out["kpi"].ctypes.data
+        ro.reward_tick_stride = n
+        ro.terminated_tick_stride = n
+        ro.kpi_tick_stride = t * capi.TL_N_KPI
+        if want_comps:
+            out["comps"] = np.zeros((n_ticks, n, capi.TL_N_COMPS), dtype=np.float64)
+            ro.comps = out["comps"].ctypes.data
+            ro.comps_tick_stride = n * capi.TL_N_COMPS
+    status = lib.tlo_tick(
+        C.byref(bs),
+        C.byref(op) if op is not None else None,
+        C.byref(rp) if rp is not None else None,
+        C.byref(oo) if oo is not None else None,
+        C.byref(ro) if ro is not None else None,
+        phases,
+        n_ticks,
+        n_threads,
+    )
+    if status != 0:
+        raise RuntimeError(f"oracle tlo_tick failed with {status}")
+    return out

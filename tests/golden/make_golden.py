@@ -1,0 +1,618 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by RUNNING THE REFERENCE.
+
+Run in the build container (the reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py            # reference at /root/reference
+
+The script copies the reference to a writable temp dir (it writes ``logs/``
+and uses relative config paths), imports it, builds populated worlds the way
+the reference's own tests do, runs ``WorldObservationService.build_batch``
+(src/townlet/world/observations/service.py:201), ``WorldState._apply_need_decay``
+(world/grid.py:1439), ``LifecycleManager.evaluate`` (lifecycle/manager.py:32)
+and ``RewardEngine.compute`` (rewards/engine.py:34), ingests the SAME world
+states into the SoA batch and stores inputs + reference outputs.
+
+It also re-checks the reference against its own stored fixtures
+(tests/data/observations/baseline_*.npz, social_snippet_gold.npz) before
+copying those vectors, so the oracle is pinned to the reference's goldens.
+"""
+
+from __future__ import annotations
+
+import os
+import shutil
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(REPO))
+sys.path.insert(0, str(REPO / "tests" / "golden"))
+
+REF_SRC = Path(os.environ.get("TOWNLET_REFERENCE", "/root/reference"))
+WORK = Path(tempfile.mkdtemp(prefix="townlet_ref_"))
+shutil.copytree(REF_SRC, WORK / "ref", symlinks=True)
+os.system(f"chmod -R u+w {WORK / 'ref'}")
+os.chdir(WORK / "ref")
+sys.path.insert(0, str(WORK / "ref" / "src"))
+sys.path.insert(0, str(WORK / "ref"))
+
+from fixture_io import GOLDEN_DIR, save_fixture  # noqa: E402
+
+from townlet.agents.models import Personality  # noqa: E402
+from townlet.config import load_config  # noqa: E402
+from townlet.core.sim_loop import SimulationLoop  # noqa: E402
+from townlet.lifecycle.manager import LifecycleManager  # noqa: E402
+from townlet.rewards.engine import RewardEngine  # noqa: E402
+from townlet.world.grid import AgentSnapshot, WorldState  # noqa: E402
+from townlet.world.observations.service import WorldObservationService  # noqa: E402
+
+from townlet_b200 import capi  # noqa: E402
+from townlet_b200.ingest import ingest_town, rows_to_batch  # noqa: E402
+from townlet_b200.params import ObsSpec, RewardSpec  # noqa: E402
+from townlet_b200.reward_events import normalise_events, reduce_social_events  # noqa: E402
+from townlet_b200.synth import TownDescription, assemble, synth_town  # noqa: E402
+
+BASE_CONFIG = Path("configs/examples/poc_hybrid.yaml")
+RELATION_SOURCE = {"empty": 0, "disabled": 0, "relationships": 1, "rivalry_fallback": 2}
+
+
+def make_config(variant: str = "hybrid", **overrides):
+    config = load_config(BASE_CONFIG)
+    data = config.model_dump()
+    data["features"]["systems"]["observations"] = variant
+    for dotted, value in overrides.items():
+        node = data
+        keys = dotted.split("__")
+        for key in keys[:-1]:
+            node = node[key]
+        node[keys[-1]] = value
+    return type(config).model_validate(data)
+
+
+def summary_from_metadata(meta: dict) -> np.ndarray:
+    row = np.zeros(capi.TL_N_SUMMARY, dtype=np.int32)
+    ls = meta["local_summary"]
+    row[0] = int(ls["agent_count"])
+    row[1] = int(ls["object_count"])
+    row[2] = int(ls["reserved_tiles"])
+    row[3] = int(round(ls["nearest_agent_distance"] ** 2))
+    sc = meta.get("social_context") or {}
+    row[4] = int(sc.get("filled_slots", 0))
+    row[5] = RELATION_SOURCE[sc.get("relation_source", "empty")]
+    return row
+
+
+def reference_obs(world, service, terminated):
+    batch = service.build_batch(world, terminated)
+    ids = list(batch)
+    maps = np.stack([batch[i]["map"] for i in ids]) if ids else np.zeros((0,), np.float32)
+    feats = np.stack([batch[i]["features"] for i in ids]) if ids else np.zeros((0,), np.float32)
+    summ = np.stack([summary_from_metadata(batch[i]["metadata"]) for i in ids])
+    return ids, maps, feats, summ, batch
+
+
+def ingest_for_obs(world, spec, terminated=None, reasons=None, max_edges=6):
+    pending = set(world._ctx_reset_requests)  # peek; build_batch consumes (grid.py:932-936)
+    slots = {aid: world.embedding_allocator.allocate(aid, world.tick) for aid in world.agents}
+    return ingest_town(
+        world, spec, terminated=terminated or {}, reasons=reasons or {}, pending_resets=pending, slots=slots, max_edges=max_edges
+    )
+
+
+def obs_fixture(name: str, world, config, terminated=None, note: str = "", check=None):
+    terminated = terminated or {}
+    spec = ObsSpec.from_config(config)
+    rows = ingest_for_obs(world, spec, terminated)
+    batch = rows_to_batch([rows], spec)
+    batch.validate(len(spec.object_channels))
+    service = WorldObservationService(config=config)
+    assert tuple(service.feature_names) == spec.feature_names, name
+    ids, maps, feats, summ, raw = reference_obs(world, service, terminated)
+    assert ids == rows.agent_ids
+    assert maps.shape[1:] == spec.map_shape, (maps.shape, spec.map_shape)
+    if check is not None:
+        check(raw)
+    save_fixture(
+        GOLDEN_DIR / f"{name}.npz",
+        batch,
+        spec,
+        RewardSpec.from_config(config),
+        capi.TL_PHASE_OBS,
+        1,
+        {"map": maps[None], "features": feats[None], "summary": summ[None]},
+        note=note,
+    )
+    print(f"  {name}: {len(ids)} agents, map {maps.shape[1:]}, F={feats.shape[1]}")
+
+
+# ---------------------------------------------------------------------------
+# 1. the reference's own stored goldens
+# ---------------------------------------------------------------------------
+def baselines():
+    for variant in ("hybrid", "full", "compact"):  # tests/test_observation_baselines.py:17-35
+        config = make_config(variant)
+        loop = SimulationLoop(config)
+        world = loop.world
+        world.agents.clear()
+        world.agents["alice"] = AgentSnapshot(
+            agent_id="alice", position=(0, 0), needs={"hunger": 0.4, "hygiene": 0.6, "energy": 0.8}, wallet=5.0
+        )
+        world.rebuild_spatial_index()
+        stored = np.load(Path("tests/data/observations") / f"baseline_{variant}.npz", allow_pickle=True)
+
+        def check(raw, stored=stored):
+            np.testing.assert_array_equal(raw["alice"]["map"], stored["map"])
+            np.testing.assert_array_equal(raw["alice"]["features"], stored["features"])
+            assert raw["alice"]["metadata"] == stored["metadata"][0]
+
+        obs_fixture(
+            f"ref_baseline_{variant}",
+            world,
+            config,
+            note=f"reference fixture tests/data/observations/baseline_{variant}.npz (bit-identical, checked at generation)",
+            check=check,
+        )
+
+
+def social_snippet():
+    config = load_config(BASE_CONFIG)  # tests/test_observations_social_snippet.py:20-41
+    world = WorldState.from_config(config)
+    world.agents["alice"] = AgentSnapshot(
+        agent_id="alice", position=(0, 0), needs={"hunger": 0.4, "hygiene": 0.5, "energy": 0.6}, wallet=5.0
+    )
+    world.agents["bob"] = AgentSnapshot(
+        agent_id="bob", position=(1, 0), needs={"hunger": 0.3, "hygiene": 0.2, "energy": 0.7}, wallet=3.0
+    )
+    world.register_rivalry_conflict("alice", "bob", intensity=1.0)  # tests/helpers/social.py:19-24
+    world.update_relationship("alice", "bob", trust=0.6, familiarity=0.3)
+    stored = np.load("tests/data/observations/social_snippet_gold.npz", allow_pickle=True)
+
+    def check(raw):
+        np.testing.assert_allclose(raw["alice"]["features"], stored["features"], atol=1e-6)
+        assert raw["alice"]["metadata"]["social_context"]["relation_source"] == "relationships"
+
+    obs_fixture(
+        "ref_social_snippet",
+        world,
+        config,
+        note="reference fixture tests/data/observations/social_snippet_gold.npz (atol 1e-6, checked at generation)",
+        check=check,
+    )
+
+
+# ---------------------------------------------------------------------------
+# 2. behavioural cases of the reference tests, as vectors
+# ---------------------------------------------------------------------------
+def builder_cases():
+    # tests/test_observation_builder.py:13-38 (targets on, two agents, stove, job loop)
+    config = make_config("hybrid", observations_config__hybrid__include_targets=True)
+    config.conflict.rivalry.avoid_threshold = 0.1
+    loop = SimulationLoop(config)
+    world = loop.world
+    world.agents.clear()
+    world.register_object(object_id="stove_test", object_type="stove", position=(2, 0))
+    world.agents["alice"] = AgentSnapshot(
+        agent_id="alice",
+        position=(0, 0),
+        needs={"hunger": 0.4, "hygiene": 0.5, "energy": 0.6},
+        wallet=2.0,
+        last_action_id="wait",
+        last_action_success=True,
+        last_action_duration=4,
+    )
+    world.agents["bob"] = AgentSnapshot(
+        agent_id="bob", position=(1, 0), needs={"hunger": 0.7, "hygiene": 0.8, "energy": 0.9}, wallet=3.0
+    )
+    world.assign_jobs_to_agents()
+    obs_fixture("builder_hybrid_targets", world, config, note="tests/test_observation_builder.py:41-99")
+    world.register_rivalry_conflict("alice", "bob")  # :115-124
+    world.request_ctx_reset("bob") if hasattr(world, "request_ctx_reset") else world._ctx_reset_requests.add("bob")
+    obs_fixture(
+        "builder_hybrid_rivalry_ctxreset",
+        world,
+        config,
+        terminated={"alice": True},
+        note="rivalry fallback + pending ctx reset + terminated (tests/test_observation_builder.py:102-124)",
+    )
+
+
+def crowded_cases():
+    # Appendix A3/A5: stacked agents and objects, reservations, all variants; unindexed agents (A1)
+    for variant, extra in (
+        ("hybrid", {}),
+        ("full", {"observations_config__hybrid__include_targets": True}),
+        (
+            "compact",
+            {
+                "observations_config__compact__object_channels": ["stove", "Fridge ", "stove"],
+                "observations_config__compact__normalize_counts": False,
+                "observations_config__compact__include_targets": True,
+            },
+        ),
+        ("compact", {}),
+    ):
+        config = make_config(variant, **extra)
+        world = WorldState.from_config(config)
+        world.tick = 777
+        for oid, otype, pos in (
+            ("stove_a", "stove", (2, 1)),
+            ("stove_b", "stove", (2, 1)),
+            ("fridge_a", "fridge", (2, 1)),
+            ("bed_a", "bed", (-3, 2)),
+            ("shower_a", "shower", (0, -4)),
+            ("Stove_caps", "Stove", (1, 1)),
+            ("fridge_far", "fridge", (9, 9)),
+        ):
+            world.register_object(object_id=oid, object_type=otype, position=pos)
+        spots = {
+            "a": (0, 0),
+            "b": (0, 0),
+            "c": (2, 0),
+            "d": (2, 1),
+            "e": (2, 1),
+            "f": (-5, -5),
+            "g": (3, 3),
+            "h": (-6, 0),
+        }
+        for k, (aid, pos) in enumerate(spots.items()):
+            world.agents[aid] = AgentSnapshot(
+                agent_id=aid,
+                position=pos,
+                needs={"hunger": 0.1 * (k + 1), "hygiene": 0.9 - 0.1 * k, "energy": 0.5},
+                wallet=float(k),
+                shift_state=("pre_shift", "on_time", "late", "absent", "post_shift", "idle", "await_start", "on_time")[k],
+                on_shift=bool(k % 2),
+                lateness_counter=k,
+                attendance_ratio=k / 8.0,
+                wages_withheld=0.01 * k,
+                last_action_id=("", "move", "request", "start", "release", "chat", "blocked", "noop")[k],
+                last_action_success=bool(k % 3 == 0),
+                last_action_duration=k,
+                episode_tick=200 * k,
+            )
+        world.rebuild_spatial_index()
+        world.agents["h"].position = (-6, 1)  # snapshot.position differs from the indexed tile (cache.py:30)
+        # A1: an agent assigned without touching the spatial index
+        world.agents["ghost"] = AgentSnapshot(
+            agent_id="ghost", position=(1, 0), needs={"hunger": 0.5, "hygiene": 0.5, "energy": 0.5}
+        )
+        # reservations: via active reservations -> tiles
+        world._active_reservations["stove_a"] = "d"
+        world._active_reservations["bed_a"] = "f"
+        world._spatial_index.set_reservation((2, 1), True)
+        world._spatial_index.set_reservation((-3, 2), True)
+        world._spatial_index.set_reservation((4, 4), True)  # a reserved tile without an object
+        world.queue_manager.request_access("shower_a", "g", world.tick)
+        world.queue_manager.request_access("shower_a", "h", world.tick)
+        # ties: more than top_friends + top_rivals, with ties in the sort keys
+        rel = world._relationships
+        rel.get_relationship_ledger("a").inject(
+            {
+                "b": {"trust": 0.2, "familiarity": 0.1, "rivalry": 0.05},
+                "c": {"trust": 0.1, "familiarity": 0.2, "rivalry": 0.30},
+                "d": {"trust": 0.5, "familiarity": 0.0, "rivalry": 0.30},
+                "e": {"trust": -0.2, "familiarity": 0.1, "rivalry": 0.00},
+                "zed": {"trust": 0.0, "familiarity": 0.0, "rivalry": 0.9},
+            }
+        )
+        rel.get_relationship_ledger("b").inject({"a": {"trust": 0.3, "familiarity": 0.3, "rivalry": 0.0}})
+        rel.get_rivalry_ledger("c").inject([("a", 0.4), ("d", 0.8), ("e", 0.8), ("g", 0.05)])
+        rel.get_rivalry_ledger("a").inject([("c", 0.75), ("b", 0.2)])
+        tag = variant if not extra else f"{variant}_opts"
+        obs_fixture(f"crowded_{tag}", world, config, terminated={"c": True}, note="SURVEY Appendix A1/A3/A5/A6 behaviours")
+
+
+# ---------------------------------------------------------------------------
+# 3. synthetic towns of the benchmark generator, materialised in the reference
+# ---------------------------------------------------------------------------
+def materialise(town: TownDescription, config) -> WorldState:
+    world = WorldState.from_config(config)
+    world.tick = town.tick
+    for oid, otype, pos in zip(town.object_ids, town.object_types, town.object_positions):
+        world.register_object(object_id=oid, object_type=otype, position=(int(pos[0]), int(pos[1])))
+    for i, aid in enumerate(town.agent_ids):
+        snap = AgentSnapshot(
+            agent_id=aid,
+            position=(int(town.positions[i, 0]), int(town.positions[i, 1])),
+            needs={"hunger": float(town.needs[i, 0]), "hygiene": float(town.needs[i, 1]), "energy": float(town.needs[i, 2])},
+            wallet=float(town.wallet[i]),
+            personality_profile=town.profile[i],
+            on_shift=bool(town.on_shift[i]),
+            lateness_counter=int(town.lateness[i]),
+            shift_state=town.shift_state[i],
+            attendance_ratio=float(town.attendance[i]),
+            wages_withheld=float(town.wages_withheld[i]),
+            last_action_id=town.last_action_id[i],
+            last_action_success=bool(town.last_action_success[i]),
+            last_action_duration=int(town.last_action_duration[i]),
+            episode_tick=int(town.episode_tick[i]),
+        )
+        snap.personality = Personality(
+            extroversion=float(town.personality[i, 0]),
+            forgiveness=float(town.personality[i, 1]),
+            ambition=float(town.personality[i, 2]),
+        )
+        world.agents[aid] = snap
+    for oid, holder in town.reservations.items():
+        world._active_reservations[oid] = holder
+    world.rebuild_spatial_index()
+    from townlet.world.queue.manager import QueueEntry
+
+    for i, aid in enumerate(town.agent_ids):  # waiting lists read by features.py:221-229
+        if town.in_queue[i]:
+            oid = town.object_ids[i % len(town.object_ids)]
+            world.queue_manager._queues.setdefault(oid, []).append(QueueEntry(agent_id=aid, joined_tick=town.tick))
+    rel = world._relationships
+    for i, aid in enumerate(town.agent_ids):
+        if town.ties[i]:
+            rel.get_relationship_ledger(aid).inject(
+                {other: {"trust": t, "familiarity": f, "rivalry": r} for other, t, f, r in town.ties[i]}
+            )
+        if town.rivalry[i]:
+            rel.get_rivalry_ledger(aid).inject(town.rivalry[i])
+    return world
+
+
+def patch_employment(world, town: TownDescription):
+    """Seed the employment context so the reference's wage / punctuality hooks return the synthetic values."""
+    for i, aid in enumerate(town.agent_ids):  # world/employment.py:209-222 reads these keys
+        ctx = world.employment_service.get_context(aid)
+        ctx["wages_paid"] = float(town.wages_paid[i])
+        ctx["scheduled_ticks"] = 1000
+        ctx["on_time_ticks"] = int(round(float(town.punctuality[i]) * 1000))
+
+
+def synth_cases():
+    cases = (
+        ("synth_hybrid_48x8", "hybrid", 48, 8, 4, {}),
+        ("synth_full_48x10", "full", 48, 10, 3, {}),
+        ("synth_compact_48x10", "compact", 48, 10, 3, {"observations_config__compact__object_channels": ["stove", "bed"]}),
+        ("synth_hybrid_128x64", "hybrid", 128, 64, 1, {"observations_config__hybrid__include_targets": True}),
+        (
+            "synth_hybrid_personality",
+            "hybrid",
+            24,
+            12,
+            2,
+            {"features__observations__personality_channels": True, "features__behavior__reward_multipliers": True},
+        ),
+    )
+    for name, variant, grid, agents, n_towns, extra in cases:
+        config = make_config(variant, employment__enforce_job_loop=False, **extra)
+        spec = ObsSpec.from_config(config)
+        rew = RewardSpec.from_config(config, fuse_faint=True)
+        towns = [synth_town(t, grid, agents, terminated_frac=0.1) for t in range(n_towns)]
+        # make some agents starve during the sequence and some sit at the episode cap
+        for town in towns:
+            town.needs[0, 0] = 0.05
+            town.needs[1 % agents, 0] = 0.031
+        n_ticks = 6
+        worlds = [materialise(t, config) for t in towns]
+        for w, t in zip(worlds, towns):
+            patch_employment(w, t)
+        services = [WorldObservationService(config=config) for _ in towns]
+        engines = [RewardEngine(config) for _ in towns]
+        lifecycles = [LifecycleManager(config) for _ in towns]
+        for eng, t in zip(engines, towns):
+            eng._episode_totals[t.agent_ids[-1]] = 49.9
+            eng._episode_totals[t.agent_ids[-2]] = -49.95
+        # ---- ingest the initial state (input of the fused tick) -------------
+        rows = []
+        for w, t, eng in zip(worlds, towns, engines):
+            term0 = {aid: bool(t.terminated[i]) for i, aid in enumerate(t.agent_ids)}
+            reasons0 = {aid: "eviction" if i % 2 else "unemployment" for i, aid in enumerate(t.agent_ids) if t.terminated[i]}
+            pending = set()
+            slots = {aid: w.embedding_allocator.allocate(aid, w.tick) for aid in w.agents}
+            rows.append(
+                ingest_town(
+                    w,
+                    spec,
+                    terminated=term0,
+                    reasons=reasons0,
+                    pending_resets=pending,
+                    slots=slots,
+                    episode_totals=dict(eng._episode_totals),
+                    termination_block=dict(eng._termination_block),
+                    origin=(0, 0),
+                )
+            )
+        batch = rows_to_batch(rows, spec, grid=(grid, grid))
+        batch.validate(len(spec.object_channels))
+        # the synthetic assembler must agree with the ingest of the materialised world
+        direct = assemble(towns, spec)
+        for fname, view in batch.views().items():
+            other = getattr(direct, fname)
+            if fname in ("episode_total", "slot"):
+                continue
+            if fname == "flags":
+                mask = ~np.uint32(capi.TL_F_REASON_MASK)
+                assert np.array_equal(view & mask, other & mask), fname
+                continue
+            assert np.array_equal(view, other), f"assemble vs ingest mismatch in {fname}"
+        # ---- run the reference for n_ticks ticks ------------------------------
+        N = batch.n_agents
+        ref = {
+            "map": np.zeros((n_ticks, N, *spec.map_shape), np.float32),
+            "features": np.zeros((n_ticks, N, spec.n_features), np.float32),
+            "summary": np.zeros((n_ticks, N, capi.TL_N_SUMMARY), np.int32),
+            "comps": np.zeros((n_ticks, N, capi.TL_N_COMPS)),
+            "terminated": np.zeros((n_ticks, N), np.uint8),
+            "needs": np.zeros((n_ticks, 3, N)),
+            "episode_total": np.zeros((n_ticks, N)),
+        }
+        for it in range(n_ticks):
+            a = 0
+            for ti, (w, t, svc, eng, life) in enumerate(zip(worlds, towns, services, engines, lifecycles)):
+                n = len(t.agent_ids)
+                w.tick += 1  # core/sim_loop.py:635,659
+                w._apply_need_decay()  # world/grid.py:1439
+                life_term = life.evaluate(w, w.tick)  # lifecycle/manager.py:32-46
+                life_reasons = dict(life._termination_reasons)
+                terminated = {}
+                reasons = {}
+                for i, aid in enumerate(t.agent_ids):
+                    host_flag = bool(t.terminated[i])  # persistent host-side terminations (employment exits)
+                    terminated[aid] = host_flag or bool(life_term.get(aid, False))
+                    if host_flag:
+                        reasons[aid] = "eviction" if i % 2 else "unemployment"
+                    elif aid in life_reasons:
+                        reasons[aid] = life_reasons[aid]
+                tpd = config.observations_config.hybrid.time_ticks_per_day
+                for snap in w.agents.values():  # world/core/context.py:283-289
+                    snap.episode_tick = (int(snap.episode_tick) + 1) % max(1, int(tpd))
+                breakdowns = eng.compute(w, terminated, reasons)
+                ids, maps, feats, summ, _ = reference_obs(w, svc, terminated)
+                assert ids == t.agent_ids
+                ref["map"][it, a : a + n] = maps
+                ref["features"][it, a : a + n] = feats
+                ref["summary"][it, a : a + n] = summ
+                for i, aid in enumerate(ids):
+                    bd = breakdowns[aid]
+                    row = ref["comps"][it, a + i]
+                    for c, cname in enumerate(capi.COMP_NAMES):
+                        if cname == "guardrail_active":
+                            row[c] = float(bd.guardrail_active)
+                        elif cname == "clipped":
+                            row[c] = float(bd.clipped)
+                        elif cname != "reserved":
+                            row[c] = float(getattr(bd, cname))
+                    ref["terminated"][it, a + i] = terminated[aid]
+                    snap = w.agents[aid]
+                    ref["needs"][it, :, a + i] = [snap.needs["hunger"], snap.needs["hygiene"], snap.needs["energy"]]
+                    ref["episode_total"][it, a + i] = eng._episode_totals[aid]
+                # the reference allocator released slots of terminated agents; re-allocate deterministically
+                for aid in ids:
+                    w.embedding_allocator._assignments.setdefault(aid, int(rows[ti].fields["slot"][ids.index(aid)]))
+                a += n
+        save_fixture(
+            GOLDEN_DIR / f"{name}.npz",
+            batch,
+            spec,
+            rew,
+            capi.TL_PHASE_ALL,
+            n_ticks,
+            ref,
+            note="synthetic towns materialised as reference WorldState; decay -> lifecycle -> reward -> observe per tick",
+        )
+        print(f"  {name}: {n_towns} towns x {agents} agents, {n_ticks} ticks")
+
+
+# ---------------------------------------------------------------------------
+# 4. reward engine cases with social events (tests/test_reward_engine.py)
+# ---------------------------------------------------------------------------
+def reward_cases():
+    config = make_config("hybrid", features__stages__social_rewards="C2")
+    rew = RewardSpec.from_config(config)
+    spec = ObsSpec.from_config(config)
+    world = WorldState.from_config(config)
+    world.tick = 100
+    needs = {
+        "alice": (0.5, 0.5, 0.5),
+        "bob": (0.9, 0.2, 0.7),
+        "carol": (0.1, 1.0, 1.0),  # deficit > 0.85 -> chat bonus suppressed (engine.py:348-353)
+        "dave": (1.0, 1.0, 1.0),
+    }
+    for k, (aid, (h, hy, e)) in enumerate(needs.items()):
+        world.agents[aid] = AgentSnapshot(agent_id=aid, position=(k, 0), needs={"hunger": h, "hygiene": hy, "energy": e}, wallet=1.0)
+    world.rebuild_spatial_index()
+    world.update_relationship("alice", "bob", trust=0.4, familiarity=0.2)
+    engine = RewardEngine(config)
+    n_ticks = 14
+    N = len(needs)
+    ref = {"comps": np.zeros((n_ticks, N, capi.TL_N_COMPS)), "episode_total": np.zeros((n_ticks, N))}
+    rows_per_tick = []
+    script = {
+        0: [("chat_success", "alice", "bob", 1.0), ("chat_success", "carol", "dave", 0.5)],
+        1: [("chat_failure", "bob", "alice", None)],
+        2: [("avoid", "dave")],
+        3: [("chat_success", "alice", "bob", 2.0), ("chat_success", "alice", "nobody", 0.25), ("avoid", "ghost")],
+    }
+    term_script = {4: ({"bob": True}, {"bob": "faint"}), 5: ({"dave": True}, {"dave": "eviction"}), 9: ({"alice": True}, {})}
+    for it in range(n_ticks):
+        world.tick += 1
+        for ev in script.get(it, []):
+            if ev[0] == "chat_success":
+                world.record_chat_success(ev[1], ev[2], ev[3])
+            elif ev[0] == "chat_failure":
+                world.record_chat_failure(ev[1], ev[2])
+            else:
+                world.record_relationship_guard_block(agent_id=ev[1], reason="queue_rival", target_agent="x", object_id="o")
+        terminated, reasons = term_script.get(it, ({}, {}))
+        totals_before = dict(engine._episode_totals)
+        block_before = dict(engine._termination_block)
+        recorded: dict[str, list] = {}
+        orig_chat, orig_avoid = world.consume_chat_events, world.consume_relationship_avoidance_events
+
+        def rec_chat(orig=orig_chat):
+            recorded["chat"] = list(orig())
+            return recorded["chat"]
+
+        def rec_avoid(orig=orig_avoid):
+            recorded["avoid"] = list(orig())
+            return recorded["avoid"]
+
+        world.consume_chat_events = rec_chat
+        world.consume_relationship_avoidance_events = rec_avoid
+        breakdowns = engine.compute(world, dict(terminated), dict(reasons))
+        world.consume_chat_events, world.consume_relationship_avoidance_events = orig_chat, orig_avoid
+        sums = reduce_social_events(
+            world, normalise_events(recorded.get("chat", [])), normalise_events(recorded.get("avoid", [])), rew
+        )
+        rows_per_tick.append(
+            ingest_town(
+                world,
+                spec,
+                terminated=terminated,
+                reasons=reasons,
+                episode_totals=totals_before,
+                termination_block=block_before,
+                social_sums=sums,
+                slots={aid: k for k, aid in enumerate(world.agents)},
+            )
+        )
+        for i, aid in enumerate(world.agents):
+            bd = breakdowns[aid]
+            for c, cname in enumerate(capi.COMP_NAMES):
+                if cname == "guardrail_active":
+                    ref["comps"][it, i, c] = float(bd.guardrail_active)
+                elif cname == "clipped":
+                    ref["comps"][it, i, c] = float(bd.clipped)
+                elif cname != "reserved":
+                    ref["comps"][it, i, c] = float(getattr(bd, cname))
+            ref["episode_total"][it, i] = engine._episode_totals[aid]
+    # one "town" per tick: each row set is an independent single-tick reward problem
+    batch = rows_to_batch(rows_per_tick, spec, grid=(16, 16))
+    flat = {
+        "comps": ref["comps"].reshape(1, n_ticks * N, capi.TL_N_COMPS),
+        "episode_total": ref["episode_total"].reshape(1, n_ticks * N),
+    }
+    save_fixture(
+        GOLDEN_DIR / "reward_social_events.npz",
+        batch,
+        spec,
+        rew,
+        capi.TL_PHASE_REWARD,
+        1,
+        flat,
+        note="RewardEngine.compute over 14 ticks with chat/avoidance events, faint/eviction, death window; one town per tick",
+    )
+    print(f"  reward_social_events: {n_ticks} ticks x {N} agents")
+
+
+def main():
+    print(f"reference: {REF_SRC} (copy at {WORK})")
+    baselines()
+    social_snippet()
+    builder_cases()
+    crowded_cases()
+    synth_cases()
+    reward_cases()
+    shutil.rmtree(WORK, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()
