@@ -1,0 +1,187 @@
+"""GPU: CUDA kernels (through the C ABI) against the reference goldens and the C oracle.
+
+Bars (north_star): map tensors, masks, integer summaries and the float32
+feature vector bit-exact; float64 need / reward state within 1e-6 relative.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from fixture_io import fixture_paths, load_fixture
+from helpers import REL_TOL, assert_obs_equal, assert_reward_close
+
+from townlet_b200 import capi
+from townlet_b200.params import ObsSpec, RewardSpec
+from townlet_b200.synth import synth_batch
+
+pytestmark = pytest.mark.gpu
+FIXTURES = fixture_paths()
+
+
+def _device_run(batch, obs, rew, phases, n_ticks, tick_by_tick=False):
+    import torch
+
+    from townlet_b200.engine import DeviceTownBatch
+
+    dev = DeviceTownBatch(batch, obs, rew)
+    out = dev.alloc_outputs(phases, n_ticks, summary=True, comps=True)
+    if tick_by_tick:
+        for it in range(n_ticks):
+            dev.tick(out, phases, 1, tick0=it)
+    else:
+        dev.tick(out, phases, n_ticks)
+    torch.cuda.synchronize()
+    dev.download_state()
+    return {k: v.cpu().numpy() for k, v in vars(out).items() if v is not None}
+
+
+def _host_run(batch, obs, rew, phases, n_ticks):
+    from townlet_b200.engine import HostEngine
+
+    eng = HostEngine(obs, rew)
+    out = eng.alloc_outputs(batch, phases, n_ticks)
+    eng.tick(batch, out, phases, n_ticks)
+    eng.close()
+    return out
+
+
+def _check_state(batch, ref):
+    if "needs" in ref:
+        np.testing.assert_allclose(batch.needs, ref["needs"][-1], rtol=REL_TOL, atol=1e-15)
+    if "episode_total" in ref:
+        np.testing.assert_allclose(batch.episode_total, ref["episode_total"][-1], rtol=REL_TOL, atol=1e-12)
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[p.stem for p in FIXTURES])
+def test_device_path_matches_reference_golden(path) -> None:
+    batch, obs, rew, meta, ref = load_fixture(path)
+    got = _device_run(batch, obs, rew, meta["phases"], meta["n_ticks"])
+    assert_obs_equal(got, ref, path.stem)
+    assert_reward_close(got, ref, path.stem)
+    _check_state(batch, ref)
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[p.stem for p in FIXTURES])
+def test_host_path_matches_reference_golden(path) -> None:
+    batch, obs, rew, meta, ref = load_fixture(path)
+    got = _host_run(batch, obs, rew, meta["phases"], meta["n_ticks"])
+    assert_obs_equal(got, ref, path.stem)
+    assert_reward_close(got, ref, path.stem)
+    _check_state(batch, ref)
+
+
+SYNTH_CASES = [
+    # name, variant, grid, agents, towns, ticks, extra ObsSpec kwargs
+    ("hybrid_48x8", "hybrid", 48, 8, 96, 4, {}),
+    ("hybrid_targets_48x8", "hybrid", 48, 8, 37, 2, {"include_targets": True, "personality_channels": True}),
+    ("full_48x10", "full", 48, 10, 64, 3, {}),
+    ("compact_48x10", "compact", 48, 10, 64, 3, {}),
+    ("compact_types_48x10", "compact", 48, 10, 33, 2, {"object_channels": ("stove", "bed", "fridge"), "normalize_counts": False}),
+    ("hybrid_128x64", "hybrid", 128, 64, 6, 3, {}),
+    ("hybrid_small_window", "hybrid", 16, 3, 50, 2, {"local_window": 5, "top_friends": 1, "top_rivals": 3, "embed_dim": 4}),
+    ("compact_big_window", "compact", 20, 5, 21, 2, {"compact_window": 13, "top_friends": 4, "top_rivals": 4, "embed_dim": 16}),
+    ("hybrid_no_social", "hybrid", 16, 4, 11, 2, {"top_friends": 0, "top_rivals": 0}),
+    ("single_agent_towns", "hybrid", 8, 1, 70, 2, {}),
+]
+
+
+@pytest.mark.parametrize("case", SYNTH_CASES, ids=[c[0] for c in SYNTH_CASES])
+def test_cuda_matches_oracle_on_synthetic_towns(case) -> None:
+    from oracle.oracle import oracle_tick
+
+    _, variant, grid, agents, towns, ticks, extra = case
+    obs = ObsSpec(variant=variant, **extra)
+    rew = RewardSpec(fuse_faint=True, personality_scaling=bool(extra.get("personality_channels")))
+    batch = synth_batch(towns, grid, agents, obs, terminated_frac=0.05)
+    batch.needs[0, ::7] = 0.045  # some agents faint during the run
+    batch.episode_total[::5] = 49.95
+    batch.episode_total[1::5] = -49.9
+    b_dev, b_ora = batch.copy(), batch.copy()
+    got = _device_run(b_dev, obs, rew, capi.TL_PHASE_ALL, ticks)
+    ref = oracle_tick(b_ora, obs, rew, capi.TL_PHASE_ALL, ticks)
+    assert_obs_equal(got, ref, case[0])
+    assert_reward_close(got, ref, case[0])
+    np.testing.assert_allclose(got["kpi"], ref["kpi"], rtol=1e-6, atol=1e-7)
+    for name in ("needs", "episode_total"):
+        np.testing.assert_allclose(getattr(b_dev, name), getattr(b_ora, name), rtol=REL_TOL, atol=1e-15)
+    for name in ("term_block_tick", "episode_tick", "flags", "town_tick"):
+        assert np.array_equal(getattr(b_dev, name), getattr(b_ora, name)), name
+
+
+def test_one_launch_of_n_ticks_equals_n_launches() -> None:
+    obs, rew = ObsSpec(), RewardSpec(fuse_faint=True)
+    batch = synth_batch(40, 48, 8, obs)
+    b1, b2 = batch.copy(), batch.copy()
+    fused = _device_run(b1, obs, rew, capi.TL_PHASE_ALL, 5)
+    stepped = _device_run(b2, obs, rew, capi.TL_PHASE_ALL, 5, tick_by_tick=True)
+    for key in fused:
+        assert np.array_equal(fused[key], stepped[key]), key
+    assert np.array_equal(b1.arena[: b1.layout.mutable_bytes], b2.arena[: b2.layout.mutable_bytes])
+
+
+def test_separate_entry_points_match_oracle() -> None:
+    import torch
+
+    from oracle.oracle import oracle_tick
+    from townlet_b200.engine import DeviceTownBatch
+
+    obs, rew = ObsSpec(variant="full"), RewardSpec()
+    batch = synth_batch(24, 48, 10, obs, terminated_frac=0.1)
+    ref_batch = batch.copy()
+    dev = DeviceTownBatch(batch, obs, rew)
+    out_r = dev.alloc_outputs(capi.TL_PHASE_DECAY | capi.TL_PHASE_REWARD, 1, comps=True)
+    dev.decay_reward(out_r, capi.TL_PHASE_DECAY)
+    dev.decay_reward(out_r, capi.TL_PHASE_REWARD)
+    out_o = dev.alloc_outputs(capi.TL_PHASE_OBS, 1, summary=True)
+    dev.obs_build(out_o)
+    torch.cuda.synchronize()
+    oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_DECAY, 1)
+    ref_r = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_REWARD, 1)
+    ref_o = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_OBS, 1)
+    got = {k: v.cpu().numpy() for k, v in vars(out_o).items() if v is not None}
+    got.update({k: v.cpu().numpy() for k, v in vars(out_r).items() if v is not None})
+    assert_obs_equal(got, ref_o, "separate obs")
+    assert_reward_close(got, ref_r, "separate reward")
+
+
+def test_obs_build_is_idempotent_and_stateless() -> None:
+    """Size-independent property at BASELINE config 2 size (1,024 towns x 8 agents)."""
+    import torch
+
+    from townlet_b200.engine import DeviceTownBatch
+
+    obs = ObsSpec()
+    batch = synth_batch(1024, 48, 8, obs)
+    dev = DeviceTownBatch(batch, obs, RewardSpec())
+    before = dev.arena.clone()
+    o1 = dev.alloc_outputs(capi.TL_PHASE_OBS, 1)
+    o2 = dev.alloc_outputs(capi.TL_PHASE_OBS, 1)
+    dev.obs_build(o1)
+    dev.obs_build(o2)
+    torch.cuda.synchronize()
+    assert torch.equal(o1.map, o2.map) and torch.equal(o1.features, o2.features)
+    assert torch.equal(before, dev.arena), "observation build must not modify state"
+    m = o1.map[0]
+    assert torch.all((m == 0) | (m == 1)), "hybrid channels are {0,1}"
+    assert torch.all(m[:, 0].sum(dim=(1, 2)) == 1), "exactly one self cell"
+    assert torch.all(m[:, 1, 5, 5] == 1), "observer counts on its own tile (map.py:109-110)"
+
+
+@pytest.mark.parametrize("variant,towns,grid,agents", [("compact", 16384, 48, 10), ("full", 16384, 48, 10), ("hybrid", 4096, 128, 64)])
+def test_full_size_configs_match_oracle(variant, towns, grid, agents) -> None:
+    """BASELINE configs 3 and 4 at full size against the multi-threaded oracle (towns tiled from 256 distinct)."""
+    import os
+
+    from oracle.oracle import oracle_tick
+    from townlet_b200.synth import tile_batch
+
+    obs, rew = ObsSpec(variant=variant), RewardSpec(fuse_faint=True)
+    base = synth_batch(256, grid, agents, obs)
+    batch = tile_batch(base, towns // 256)
+    b_dev, b_ora = batch.copy(), batch.copy()
+    got = _device_run(b_dev, obs, rew, capi.TL_PHASE_ALL, 1)
+    ref = oracle_tick(b_ora, obs, rew, capi.TL_PHASE_ALL, 1, n_threads=os.cpu_count() or 1, want_comps=True)
+    assert_obs_equal(got, ref, f"{variant} full size")
+    assert_reward_close(got, ref, f"{variant} full size")
+    np.testing.assert_allclose(b_dev.needs, b_ora.needs, rtol=REL_TOL, atol=1e-15)

@@ -1,0 +1,1221 @@
+// townlet_b200.cu — sm_100a kernels and C ABI for Townlet's per-tick agent hot path.
+//
+// One kernel template, tick_kernel<VARIANT>, runs the phases of one or more
+// ticks for a group of towns per CTA, in SimulationLoop.step order
+// (reference src/townlet/core/sim_loop.py:632): need decay (world/grid.py:1439)
+// -> faint predicate (lifecycle/manager.py:39-45) -> reward
+// (rewards/engine.py:34-178) -> observation build
+// (world/observations/service.py:201 and encoders/{map,features,social}.py).
+//
+// Shape of a CTA (256 threads, 8 warps) per tick:
+//   stage   every town of the CTA gets a packed uint16 tile grid in shared
+//           memory (agents:8 | objects:7 | reserved:1), built from the town's
+//           entity list with shared-memory atomics — the device form of
+//           build_local_cache (world/observations/cache.py:16-41);
+//   phase A one THREAD per agent, 32 agents per chunk: coalesced SoA loads,
+//           float64 decay / reward / guardrails, per-town KPI partials by
+//           segmented warp shuffles, scalar features into a shared row;
+//   phase B one WARP per agent: window gather from the staged grid into a
+//           channel-major staging tile, local summary by REDUX, social
+//           snippet by warp-cooperative stable ranking, then 16-byte
+//           vectorised coalesced stores of the map and the feature row.
+// The path is gather / elementwise and HBM-write bound; tensor cores are not
+// used.  There is no CPU fallback in this library.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "townlet_b200.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunk = 32;          // agents per phase-A pass
+constexpr int kMaxTownsPerCta = 8;  // towns sharing one CTA
+constexpr int kMaxSocialLen = TL_MAX_SOCIAL_SLOTS * (32 + 3) + 4;
+
+thread_local char g_error[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, const char* detail = "") { snprintf(g_error, sizeof(g_error), fmt, detail); }
+
+struct KParams {
+    TlTownBatch b;
+    TlObsParams obs;
+    TlRewardParams rew;
+    TlObsOut oo;
+    TlRewardOut ro;
+    uint32_t phases;
+    int32_t n_ticks;
+    int32_t towns_per_cta;
+    int32_t grid_tiles;    // grid_w * grid_h
+    int32_t feat_stride;   // floats per staged feature row (== n_features)
+    int32_t map_stride;    // floats per warp map staging tile (multiple of 4, >= map_elems + 4)
+    // shared memory offsets in bytes
+    int32_t off_grid;      // uint16 [towns_per_cta][grid_tiles]
+    int32_t off_ctype;     // uint16 [towns_per_cta][grid_tiles] (4 x 4-bit counters) or -1
+    int32_t off_feat;      // float [kChunk * feat_stride + 4]
+    int32_t off_map;       // float [kWarps][map_stride]
+    int32_t off_meta;      // ChunkMeta[kChunk]
+    int32_t smem_bytes;
+};
+
+struct ChunkMeta {
+    int32_t cx, cy;      // window centre
+    int32_t ox, oy;      // occupancy tile of the agent itself
+    int32_t town_slot;   // index of the agent's town inside the CTA
+    int32_t terminated;  // effective terminated flag of this tick
+    int32_t pad0, pad1;
+};
+
+struct TownMeta {
+    int32_t agent_begin, agent_end;
+    int32_t ent_begin, ent_end;
+    int32_t tick;
+    int32_t pad;
+};
+
+__device__ __forceinline__ int pos_x(int32_t p) { return (int)(int16_t)(p & 0xffff); }
+__device__ __forceinline__ int pos_y(int32_t p) { return (int)(int16_t)((uint32_t)p >> 16); }
+
+__device__ __forceinline__ double scale_bias(double value, double factor) {
+    // RewardEngine._apply_reward_biases._scale, rewards/engine.py:226-231
+    if (factor <= 0.0) return value;
+    if (value >= 0.0) return value * factor;
+    return value / factor;
+}
+
+// Sum of n <= 8 doubles the way numpy's add.reduce does it for np.mean
+// (encoders/social.py:245-254): sequential below 8, the unrolled pairwise block at 8.
+__device__ __forceinline__ double np_sum_le8(const double (&a)[TL_MAX_SOCIAL_SLOTS], int n) {
+    if (n < 8) {
+        double res = 0.0;
+#pragma unroll
+        for (int i = 0; i < TL_MAX_SOCIAL_SLOTS; ++i)
+            if (i < n) res += a[i];
+        return res;
+    }
+    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
+// ---------------------------------------------------------------------------
+// Phase A, reward part: RewardEngine.compute body for one agent
+// (rewards/engine.py:71-172).  All float64, as in the reference.
+// ---------------------------------------------------------------------------
+struct RewardResult {
+    double total;
+    double comps[TL_N_COMPS];
+};
+
+__device__ __forceinline__ void reward_agent(const KParams& p, int a, int tick, const double (&need)[3], uint32_t fl,
+                                             bool terminated, unsigned reason, RewardResult& out) {
+    const TlRewardParams& r = p.rew;
+    const int N = p.b.n_agents;
+    double* c = out.comps;
+#pragma unroll
+    for (int i = 0; i < TL_N_COMPS; ++i) c[i] = 0.0;
+    double total = r.survival_tick;
+    c[TL_COMP_SURVIVAL] = r.survival_tick;
+    double needs_penalty = 0.0;
+#pragma unroll
+    for (int k = 0; k < TL_N_NEEDS; ++k) {  // engine.py:76-80
+        double deficit = fmax(0.0, 1.0 - need[k]);
+        needs_penalty += r.need_weight[k] * (deficit * deficit);
+    }
+    total -= needs_penalty;
+    c[TL_COMP_NEEDS_PENALTY] = -needs_penalty;
+    double sb = 0.0, sp = 0.0, sa = 0.0;
+    if (p.b.social_in) {
+        sb = p.b.social_in[a];
+        sp = p.b.social_in[(size_t)N + a];
+        sa = p.b.social_in[2 * (size_t)N + a];
+    }
+    total += sb + sp + sa;  // engine.py:87
+    c[TL_COMP_SOCIAL_BONUS] = sb;
+    c[TL_COMP_SOCIAL_PENALTY] = sp;
+    c[TL_COMP_SOCIAL_AVOIDANCE] = sa;
+    c[TL_COMP_SOCIAL] = sb + sp + sa;
+    double wage = 0.0;  // engine.py:375-386
+    if (r.wage_rate > 0.0) wage = p.b.wages_paid[a] - p.b.wages_withheld[a];
+    total += wage;
+    c[TL_COMP_WAGE] = wage;
+    double punct = 0.0;  // engine.py:388-398
+    if (r.punctuality_bonus > 0.0) punct = r.punctuality_bonus * p.b.punctuality[a];
+    total += punct;
+    c[TL_COMP_PUNCTUALITY] = punct;
+    unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
+    if (r.reward_personality && profile != 0) {  // engine.py:104-106, 220-255
+        double delta = 0.0;
+        double f0 = r.reward_bias[profile][0], f1 = r.reward_bias[profile][1], f2 = r.reward_bias[profile][2];
+        if (f0 != 1.0) {
+#pragma unroll
+            for (int idx = TL_COMP_SOCIAL_BONUS; idx <= TL_COMP_SOCIAL_AVOIDANCE; ++idx) {
+                double base = c[idx], adj = scale_bias(base, f0);
+                c[idx] = adj;
+                delta += adj - base;
+            }
+            c[TL_COMP_SOCIAL] = c[TL_COMP_SOCIAL_BONUS] + c[TL_COMP_SOCIAL_PENALTY] + c[TL_COMP_SOCIAL_AVOIDANCE];
+        }
+        if (f1 != 1.0) {
+            double base = c[TL_COMP_WAGE], adj = scale_bias(base, f1);
+            c[TL_COMP_WAGE] = adj;
+            delta += adj - base;
+            base = c[TL_COMP_PUNCTUALITY];
+            adj = scale_bias(base, f1);
+            c[TL_COMP_PUNCTUALITY] = adj;
+            delta += adj - base;
+        }
+        if (f2 != 1.0) {
+            double base = c[TL_COMP_SURVIVAL], adj = scale_bias(base, f2);
+            c[TL_COMP_SURVIVAL] = adj;
+            delta += adj - base;
+        }
+        total += delta;
+    }
+    double penalty = 0.0;  // engine.py:400-413
+    if (terminated) {
+        if (reason == 1) penalty = r.faint_penalty;
+        else if (reason == 2) penalty = r.eviction_penalty;
+    }
+    total += penalty;
+    c[TL_COMP_TERMINAL_PENALTY] = penalty;
+    const double pre_guard = total;
+    // termination block: prune (engine.py:363-373), set (:113-114), test (:355-361)
+    int32_t block = p.b.term_block_tick[a];
+    if (r.block_window < 0) block = TL_TERM_BLOCK_NONE;
+    else if (block != TL_TERM_BLOCK_NONE && (int64_t)tick - (int64_t)block > (int64_t)r.block_window)
+        block = TL_TERM_BLOCK_NONE;
+    if (terminated) block = tick;
+    const bool blocked = r.block_window >= 0 && block != TL_TERM_BLOCK_NONE &&
+                         (int64_t)tick - (int64_t)block <= (int64_t)r.block_window;
+    p.b.term_block_tick[a] = block;
+    if ((terminated || blocked) && total > 0.0) total = 0.0;  // engine.py:116-122
+    const double guard_adjust = total - pre_guard;
+    const double post = fmax(fmin(total, r.clip_per_tick), -r.clip_per_tick);  // engine.py:126-128
+    const double tick_clip_adjust = post - total;
+    total = post;
+    const double prev = terminated ? 0.0 : p.b.episode_total[a];  // engine.py:415-424
+    double cumulative = prev + total;
+    double episode_clip_adjust = 0.0;
+    if (r.clip_per_episode > 0) {  // engine.py:130-139
+        cumulative = fmax(fmin(cumulative, r.clip_per_episode), -r.clip_per_episode);
+        const double new_total = cumulative - prev;
+        episode_clip_adjust = new_total - total;
+        total = new_total;
+    }
+    p.b.episode_total[a] = cumulative;
+    c[TL_COMP_CLIP_ADJUSTMENT] = guard_adjust + tick_clip_adjust + episode_clip_adjust;
+    c[TL_COMP_TOTAL] = total;
+    c[TL_COMP_HOMEOSTASIS] = c[TL_COMP_SURVIVAL] + c[TL_COMP_NEEDS_PENALTY];
+    c[TL_COMP_WORK] = c[TL_COMP_WAGE] + c[TL_COMP_PUNCTUALITY];
+    c[TL_COMP_GUARDRAIL_ACTIVE] = guard_adjust != 0.0 ? 1.0 : 0.0;
+    c[TL_COMP_CLIPPED] = (tick_clip_adjust != 0.0 || episode_clip_adjust != 0.0) ? 1.0 : 0.0;
+    out.total = total;
+}
+
+// Segmented (by town slot, contiguous lanes) suffix reduction: after the call
+// the first lane of every segment holds the segment's reduction.
+template <typename T, typename Op>
+__device__ __forceinline__ T seg_reduce(T v, int seg, int lane, Op op) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        T other = __shfl_down_sync(0xffffffffu, v, off);
+        int oseg = __shfl_down_sync(0xffffffffu, seg, off);
+        if (lane + off < 32 && oseg == seg) v = op(v, other);
+    }
+    return v;
+}
+
+struct KpiAcc {
+    double rsum, rsq, hmin, hsum, late, wallet;
+    int starving, term, count;
+};
+
+// ---------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------
+template <int VARIANT>
+__global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ TownMeta s_town[kMaxTownsPerCta];
+    __shared__ KpiAcc s_kpi[kMaxTownsPerCta];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int T = p.b.n_towns;
+    const int N = p.b.n_agents;
+    const int t0 = blockIdx.x * p.towns_per_cta;
+    const int n_towns = min(p.towns_per_cta, T - t0);
+    if (n_towns <= 0) return;
+
+    const bool do_decay = p.phases & TL_PHASE_DECAY;
+    const bool do_reward = p.phases & TL_PHASE_REWARD;
+    const bool do_obs = p.phases & TL_PHASE_OBS;
+    const bool do_advance = p.phases & TL_PHASE_ADVANCE;
+    const bool do_state = do_decay || do_reward;
+
+    uint16_t* s_grid = reinterpret_cast<uint16_t*>(smem + p.off_grid);
+    uint16_t* s_ctype = p.off_ctype >= 0 ? reinterpret_cast<uint16_t*>(smem + p.off_ctype) : nullptr;
+    float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);
+    float* s_map = reinterpret_cast<float*>(smem + p.off_map);
+    ChunkMeta* s_meta = reinterpret_cast<ChunkMeta*>(smem + p.off_meta);
+
+    const int W = p.obs.window;
+    const int R = W >> 1;
+    const int W2 = W * W;
+    const int F = p.obs.n_features;
+    const int GW = p.b.grid_w, GH = p.b.grid_h;
+    const int map_elems = p.obs.n_channels * W2;
+
+    if (tid < n_towns) {
+        TownMeta m;
+        m.agent_begin = p.b.town_agent_off[t0 + tid];
+        m.agent_end = p.b.town_agent_off[t0 + tid + 1];
+        m.ent_begin = p.b.town_ent_off[t0 + tid];
+        m.ent_end = p.b.town_ent_off[t0 + tid + 1];
+        m.tick = p.b.town_tick[t0 + tid];
+        m.pad = 0;
+        s_town[tid] = m;
+    }
+    __syncthreads();
+    const int a_begin = s_town[0].agent_begin;
+    const int a_end = s_town[n_towns - 1].agent_end;
+    const int e_begin = s_town[0].ent_begin;
+    const int e_end = s_town[n_towns - 1].ent_end;
+    const int n_chunks = (a_end - a_begin + kChunk - 1) / kChunk;
+
+    // per-lane window coordinates of tile (lane + 32 k) are advanced incrementally
+    const int row0 = lane / W, col0 = lane - row0 * W;
+    const int drow = 32 / W, dcol = 32 - drow * W;
+
+    for (int it = 0; it < p.n_ticks; ++it) {
+        // ---- tick bookkeeping (core/sim_loop.py:635,659) ---------------------
+        if (tid < n_towns) {
+            if (do_advance) {
+                s_town[tid].tick += 1;
+                p.b.town_tick[t0 + tid] = s_town[tid].tick;
+            }
+            KpiAcc z;
+            z.rsum = z.rsq = z.hsum = z.late = z.wallet = 0.0;
+            z.hmin = 1e300;
+            z.starving = z.term = z.count = 0;
+            s_kpi[tid] = z;
+        }
+        // ---- stage the town grids (cache.py:16-41) ---------------------------
+        if (do_obs) {
+            const int words = (n_towns * p.grid_tiles + 1) >> 1;
+            uint32_t* g32 = reinterpret_cast<uint32_t*>(s_grid);
+            for (int i = tid; i < words; i += kThreads) g32[i] = 0u;
+            if (s_ctype) {
+                uint32_t* c32 = reinterpret_cast<uint32_t*>(s_ctype);
+                for (int i = tid; i < words; i += kThreads) c32[i] = 0u;
+            }
+        }
+        __syncthreads();
+        if (do_obs) {
+            for (int e = e_begin + tid; e < e_end; e += kThreads) {
+                const uint32_t w = p.b.ent[e];
+                int slot = 0;
+#pragma unroll
+                for (int s = 1; s < kMaxTownsPerCta; ++s)
+                    if (s < n_towns && e >= s_town[s].ent_begin) slot = s;
+                const int idx = slot * p.grid_tiles + TL_ENT_Y(w) * GW + TL_ENT_X(w);
+                const unsigned kind = TL_ENT_KIND(w);
+                uint32_t* word = reinterpret_cast<uint32_t*>(s_grid) + (idx >> 1);
+                const int sh = (idx & 1) * 16;
+                if (kind == TL_KIND_AGENT) {
+                    atomicAdd(word, 1u << sh);
+                } else if (kind == TL_KIND_OBJECT) {
+                    if (TL_ENT_TILE(w)) {
+                        atomicAdd(word, 0x100u << sh);
+                        const unsigned ct = TL_ENT_CTYPE(w);
+                        if (s_ctype && ct > 0 && (int)ct <= p.obs.n_ctypes)
+                            atomicAdd(reinterpret_cast<uint32_t*>(s_ctype) + (idx >> 1), 1u << (sh + 4 * (ct - 1)));
+                    }
+                } else if (kind == TL_KIND_RESERVED) {
+                    atomicOr(word, 0x8000u << sh);
+                }
+            }
+        }
+        __syncthreads();
+
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const int c_begin = a_begin + chunk * kChunk;
+            const int c_n = min(kChunk, a_end - c_begin);
+            // feature staging mirrors the 16-byte misalignment of the global rows
+            float* feat_g0 = do_obs ? p.oo.features + (size_t)it * p.oo.features_tick_stride + (size_t)c_begin * F : nullptr;
+            const int feat_mis = do_obs ? (int)((reinterpret_cast<uintptr_t>(feat_g0) >> 2) & 3) : 0;
+            float* feat_s0 = s_feat + feat_mis;
+
+            // =================== phase A: one thread per agent ==================
+            if (warp == 0) {
+                const bool active = lane < c_n;
+                const int a = c_begin + (active ? lane : 0);
+                int slot = 0;
+#pragma unroll
+                for (int s = 1; s < kMaxTownsPerCta; ++s)
+                    if (s < n_towns && a >= s_town[s].agent_begin) slot = s;
+                const TownMeta tm = s_town[slot];
+                const int tick = tm.tick;
+                double need[3] = {0.0, 0.0, 0.0};
+                uint32_t fl = 0;
+                bool terminated = false;
+                unsigned reason = 0;
+                int episode_tick = 0;
+                double reward_total = 0.0;
+                if (active) {
+                    need[0] = p.b.needs[a];
+                    need[1] = p.b.needs[(size_t)N + a];
+                    need[2] = p.b.needs[2 * (size_t)N + a];
+                    fl = p.b.flags[a];
+                    episode_tick = p.b.episode_tick[a];
+                    const unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
+                    if (do_decay) {  // world/grid.py:1439-1455
+#pragma unroll
+                        for (int k = 0; k < TL_N_NEEDS; ++k) {
+                            double mult = 1.0;
+                            if (p.rew.decay_personality && profile != 0) {
+                                mult = p.rew.need_mult[profile][k];
+                                if (mult <= 0.0) mult = 1.0;
+                            }
+                            const double adjusted = p.rew.decay_rate[k] * mult;
+                            need[k] = fmax(0.0, need[k] - adjusted);
+                            p.b.needs[(size_t)k * N + a] = need[k];
+                        }
+                    }
+                    if (do_state && p.rew.fuse_faint) {  // lifecycle/manager.py:39-45
+                        fl = (fl & ~TL_F_FAINTED) | (need[0] <= p.rew.faint_threshold ? TL_F_FAINTED : 0u);
+                        p.b.flags[a] = fl;
+                    }
+                    terminated = (fl & (TL_F_TERMINATED | TL_F_FAINTED)) != 0;
+                    reason = (fl & TL_F_REASON_MASK) >> TL_F_REASON_SHIFT;
+                    if (reason == 0 && (fl & TL_F_FAINTED)) reason = 1;
+                    if (do_advance) {  // world/core/context.py:283-289
+                        const int span = max(1, p.obs.ticks_per_day);
+                        episode_tick = (episode_tick + 1) % span;
+                        p.b.episode_tick[a] = episode_tick;
+                    }
+                    if (do_reward) {
+                        RewardResult rr;
+                        reward_agent(p, a, tick, need, fl, terminated, reason, rr);
+                        reward_total = rr.total;
+                        if (p.ro.reward) p.ro.reward[(size_t)it * p.ro.reward_tick_stride + a] = (float)rr.total;
+                        if (p.ro.comps) {
+                            double* dst = p.ro.comps + (size_t)it * p.ro.comps_tick_stride + (size_t)a * TL_N_COMPS;
+#pragma unroll
+                            for (int i = 0; i < TL_N_COMPS; i += 2)
+                                *reinterpret_cast<double2*>(dst + i) = make_double2(rr.comps[i], rr.comps[i + 1]);
+                        }
+                    }
+                    if (do_state && p.ro.terminated)
+                        p.ro.terminated[(size_t)it * p.ro.terminated_tick_stride + a] = terminated ? 1 : 0;
+                }
+                // ---- per-town KPIs: segmented warp-shuffle reduction ------------
+                if (do_state && p.ro.kpi) {
+                    const int seg = active ? slot : -1 - lane;  // inactive lanes are their own segment
+                    const double hunger = need[0];
+                    const double late = active ? (double)p.b.lateness[a] : 0.0;
+                    const double wal = active ? p.b.wallet[a] : 0.0;
+                    auto add = [](double x, double y) { return x + y; };
+                    auto addi = [](int x, int y) { return x + y; };
+                    auto mn = [](double x, double y) { return fmin(x, y); };
+                    const double rsum = seg_reduce(reward_total, seg, lane, add);
+                    const double rsq = seg_reduce(reward_total * reward_total, seg, lane, add);
+                    const double hsum = seg_reduce(hunger, seg, lane, add);
+                    const double hmin = seg_reduce(active ? hunger : 1e300, seg, lane, mn);
+                    const double lsum = seg_reduce(late, seg, lane, add);
+                    const double wsum = seg_reduce(wal, seg, lane, add);
+                    const int starving = seg_reduce((int)(active && hunger <= p.rew.starvation_threshold), seg, lane, addi);
+                    const int term = seg_reduce((int)terminated, seg, lane, addi);
+                    const int cnt = seg_reduce((int)active, seg, lane, addi);
+                    const int prev_seg = __shfl_up_sync(0xffffffffu, seg, 1);
+                    if (active && (lane == 0 || prev_seg != seg)) {  // segment head; chunks arrive in order
+                        KpiAcc& k = s_kpi[slot];
+                        k.rsum += rsum;
+                        k.rsq += rsq;
+                        k.hsum += hsum;
+                        k.hmin = fmin(k.hmin, hmin);
+                        k.late += lsum;
+                        k.wallet += wsum;
+                        k.starving += starving;
+                        k.term += term;
+                        k.count += cnt;
+                    }
+                }
+                // ---- scalar features (encoders/features.py:43-404) ------------
+                if (do_obs && active) {
+                    float* f = feat_s0 + lane * F;
+                    const TlObsParams& o = p.obs;
+                    f[TL_FEAT_NEED_HUNGER] = (float)need[0];
+                    f[TL_FEAT_NEED_HYGIENE] = (float)need[1];
+                    f[TL_FEAT_NEED_ENERGY] = (float)need[2];
+                    f[TL_FEAT_WALLET] = (float)p.b.wallet[a];
+                    f[TL_FEAT_LATENESS] = (float)p.b.lateness[a];
+                    f[TL_FEAT_ON_SHIFT] = (fl & TL_F_ON_SHIFT) ? 1.0f : 0.0f;
+                    int m = tick % o.ticks_per_day;
+                    if (m < 0) m += o.ticks_per_day;
+                    const float2 sc = *reinterpret_cast<const float2*>(o.time_lut + 2 * m);
+                    f[TL_FEAT_TIME_SIN] = sc.x;
+                    f[TL_FEAT_TIME_COS] = sc.y;
+                    f[TL_FEAT_ATTENDANCE] = (float)p.b.attendance[a];
+                    f[TL_FEAT_WAGES_WITHHELD] = (float)p.b.wages_withheld[a];
+                    unsigned st = (fl & TL_F_SHIFT_MASK) >> TL_F_SHIFT_SHIFT;
+                    if (st > 4) st = 0;
+#pragma unroll
+                    for (unsigned k = 0; k < 5; ++k) f[TL_FEAT_SHIFT_PRE + k] = (k == st) ? 1.0f : 0.0f;
+                    const int slot_idx = p.b.slot[a];
+                    f[TL_FEAT_SLOT_NORM] = (slot_idx >= 0 && slot_idx < o.max_slots)
+                                               ? o.slot_lut[slot_idx]
+                                               : (float)((double)slot_idx / (double)o.max_slots);
+                    f[TL_FEAT_CTX_RESET] = ((fl & TL_F_CTX_RESET) || terminated) ? 1.0f : 0.0f;  // service.py:224-229
+                    f[TL_FEAT_EPISODE_PROGRESS] =
+                        episode_tick <= 0 ? 0.0f : o.progress_lut[min(episode_tick, o.ticks_per_day)];
+                    // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
+                    {
+                        const int K = p.b.max_edges;
+                        int nr = p.b.riv_count[a];
+                        nr = min(nr, o.rivalry_max_edges);
+                        double mx = 0.0;
+                        int avoid = 0;
+                        for (int j = 0; j < nr; ++j) {
+                            const double v = p.b.riv_score[(size_t)a * K + j];
+                            if (j == 0) mx = v;
+                            avoid += (v >= o.avoid_threshold) ? 1 : 0;
+                        }
+                        f[TL_FEAT_RIVALRY_MAX] = (float)mx;
+                        f[TL_FEAT_RIVALRY_AVOID] = (float)avoid;
+                    }
+                    f[TL_FEAT_LAST_HASH] = p.b.last_action_hash[a];
+                    f[TL_FEAT_LAST_SUCCESS] = (fl & TL_F_LAST_SUCCESS) ? 1.0f : 0.0f;
+                    f[TL_FEAT_LAST_DURATION] = (float)p.b.last_action_duration[a];
+                    f[TL_FEAT_RESERVATION] = (fl & TL_F_RESERVATION) ? 1.0f : 0.0f;
+                    f[TL_FEAT_IN_QUEUE] = (fl & TL_F_IN_QUEUE) ? 1.0f : 0.0f;
+                    // nearest object per landmark type: first minimum of the squared
+                    // distance in insertion order (world/observe.py:109-147)
+                    const int32_t pw = p.b.pos[a];
+                    const int cx = pos_x(pw), cy = pos_y(pw);
+                    int best_d2[5] = {-1, -1, -1, -1, -1};
+                    int best_dx[5] = {0, 0, 0, 0, 0}, best_dy[5] = {0, 0, 0, 0, 0};
+                    const bool all_types = o.landmark_base >= 0;
+                    const int e_obj = tm.ent_begin + (tm.agent_end - tm.agent_begin);
+                    for (int e = e_obj; e < tm.ent_end; ++e) {
+                        const uint32_t w = p.b.ent[e];
+                        if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w)) continue;
+                        const int lt = (int)TL_ENT_LTYPE(w);
+                        if (lt == 0 || (!all_types && lt != o.path_hint_ltype)) continue;
+                        const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
+                        const int d2 = dx * dx + dy * dy;
+#pragma unroll
+                        for (int l = 1; l <= 4; ++l) {
+                            if (l == lt && (best_d2[l] < 0 || d2 < best_d2[l])) {
+                                best_d2[l] = d2;
+                                best_dx[l] = dx;
+                                best_dy[l] = dy;
+                            }
+                        }
+                    }
+                    {  // _encode_path_hint, features.py:251-286
+                        double north = 0.0, south = 0.0, east = 0.0, west = 0.0;
+                        int hd2 = -1, hdx = 0, hdy = 0;
+#pragma unroll
+                        for (int l = 1; l <= 4; ++l)
+                            if (l == o.path_hint_ltype) {
+                                hd2 = best_d2[l];
+                                hdx = best_dx[l];
+                                hdy = best_dy[l];
+                            }
+                        if (hd2 >= 0) {
+                            const int norm = abs(hdx) + abs(hdy);
+                            if (norm != 0) {
+                                const double dn = (double)norm;
+                                north = fmax(0.0, (double)-hdy) / dn;
+                                south = fmax(0.0, (double)hdy) / dn;
+                                east = fmax(0.0, (double)hdx) / dn;
+                                west = fmax(0.0, (double)-hdx) / dn;
+                            }
+                        }
+                        f[TL_FEAT_PATH_NORTH + 0] = (float)north;
+                        f[TL_FEAT_PATH_NORTH + 1] = (float)south;
+                        f[TL_FEAT_PATH_NORTH + 2] = (float)east;
+                        f[TL_FEAT_PATH_NORTH + 3] = (float)west;
+                    }
+                    if (all_types) {  // _encode_landmarks, features.py:333-356
+#pragma unroll
+                        for (int l = 1; l <= 4; ++l) {
+                            float* dst = f + o.landmark_base + 3 * (l - 1);
+                            if (best_d2[l] < 0) {
+                                dst[0] = dst[1] = dst[2] = 0.0f;
+                            } else {
+                                // sqrt of an exact integer: equals np.hypot after the float32 store
+                                const double distance = sqrt((double)best_d2[l]);
+                                const double norm = distance > 0.0 ? distance : 1.0;
+                                dst[0] = (float)((double)best_dx[l] / norm);
+                                dst[1] = (float)((double)best_dy[l] / norm);
+                                dst[2] = (float)distance;
+                            }
+                        }
+                    }
+                    if (o.personality_base >= 0) {  // features.py:359-380
+                        const bool has = p.b.personality != nullptr;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            f[o.personality_base + k] = has ? p.b.personality[(size_t)k * N + a] : 0.0f;
+                    }
+                    ChunkMeta cm;
+                    cm.cx = cx;
+                    cm.cy = cy;
+                    const uint32_t self_e = p.b.ent[tm.ent_begin + (a - tm.agent_begin)];
+                    cm.ox = TL_ENT_X(self_e);
+                    cm.oy = TL_ENT_Y(self_e);
+                    cm.town_slot = slot;
+                    cm.terminated = terminated ? 1 : 0;
+                    cm.pad0 = cm.pad1 = 0;
+                    s_meta[lane] = cm;
+                }
+            }
+            if (!do_obs) continue;  // uniform for the CTA
+            __syncthreads();
+
+            // =================== phase B: one warp per agent =====================
+            for (int i = warp; i < c_n; i += kWarps) {
+                const int a = c_begin + i;
+                const ChunkMeta cm = s_meta[i];
+                const uint16_t* grid = s_grid + cm.town_slot * p.grid_tiles;
+                const uint16_t* cgrid = s_ctype ? s_ctype + cm.town_slot * p.grid_tiles : nullptr;
+                float* frow = feat_s0 + i * F;
+                const TlObsParams& o = p.obs;
+
+                // -- prefetch the relation rows (social.py:165-209): lane j holds relation j
+                const int K = p.b.max_edges, EW = p.b.embed_words;
+                const int n_ties = p.b.tie_count[a];
+                int n_rel = n_ties;
+                int source = n_ties > 0 ? 1 : 0;
+                double trust = 0.0, fam = 0.0, riv = 0.0;
+                const uint64_t* emb = nullptr;
+                if (o.social_base >= 0) {
+                    if (n_ties > 0) {
+                        if (lane < n_ties) {
+                            const size_t r = (size_t)a * K + lane;
+                            trust = p.b.tie_trust[r];
+                            fam = p.b.tie_fam[r];
+                            riv = p.b.tie_riv[r];
+                            emb = p.b.tie_embed + r * EW;
+                        }
+                    } else {
+                        n_rel = min((int)p.b.riv_count[a], o.top_rivals);  // rivalry_top(agent, top_rivals)
+                        source = n_rel > 0 ? 2 : 0;
+                        if (lane < n_rel) {
+                            const size_t r = (size_t)a * K + lane;
+                            riv = p.b.riv_score[r];
+                            emb = p.b.riv_embed + r * EW;
+                        }
+                    }
+                }
+
+                // -- window gather (encoders/map.py:39-148, 151-243) -----------
+                float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)a * map_elems;
+                const int map_mis = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
+                float* st = s_map + warp * p.map_stride + map_mis;
+                int others_sum = 0, objects_sum = 0, reserved_sum = 0;
+                unsigned nearest = 0xffffffffu;
+                int row = row0, col = col0;
+                for (int tile = lane; tile < W2; tile += 32) {
+                    const int dx = col - R, dy = row - R;
+                    const int x = cm.cx + dx, y = cm.cy + dy;
+                    const bool inb = (unsigned)x < (unsigned)GW && (unsigned)y < (unsigned)GH;
+                    const unsigned w = inb ? grid[y * GW + x] : 0u;
+                    const int agents = w & 0xff, objects = (w >> 8) & 0x7f, reserved = w >> 15;
+                    const bool centre = (dx == 0 && dy == 0);
+                    // LocalSummary (map.py:88-103): self excluded on the centre tile only
+                    const int cnt = agents - ((centre && agents > 0) ? 1 : 0);
+                    others_sum += cnt;
+                    objects_sum += objects;
+                    reserved_sum += reserved;
+                    if (cnt > 0 && !centre) nearest = min(nearest, (unsigned)(dx * dx + dy * dy));
+                    st[tile] = centre ? 1.0f : 0.0f;  // map.py:69 / :185-186
+                    if (VARIANT == TL_VARIANT_COMPACT) {
+                        const bool own = (x == cm.ox && y == cm.oy);
+                        const int others = agents - (own ? 1 : 0);  // map.py:198
+                        const bool norm = o.normalize_counts != 0;
+                        st[W2 + tile] = (float)(norm ? min(others, 1) : others);
+                        st[2 * W2 + tile] = (float)(norm ? min(objects, 1) : objects);
+                        st[3 * W2 + tile] = (float)reserved;
+                        const unsigned cw = (cgrid && inb) ? cgrid[y * GW + x] : 0u;
+                        for (int k = 0; k < o.n_ctypes; ++k) {
+                            const int c = (cw >> (4 * k)) & 15;
+                            st[(4 + k) * W2 + tile] = (float)(norm ? min(c, 1) : c);
+                        }
+                        const bool blockd = others > 0 || objects > 0 || reserved || centre;  // map.py:231-241
+                        st[(4 + o.n_ctypes) * W2 + tile] = blockd ? 0.0f : 1.0f;
+                    } else {
+                        st[W2 + tile] = agents > 0 ? 1.0f : 0.0f;  // includes the observer (map.py:109-110)
+                        st[2 * W2 + tile] = objects > 0 ? 1.0f : 0.0f;
+                        st[3 * W2 + tile] = (float)reserved;
+                        if (VARIANT == TL_VARIANT_FULL) {
+                            st[4 * W2 + tile] = o.path_lut[tile];
+                            st[5 * W2 + tile] = o.path_lut[W2 + tile];
+                        }
+                    }
+                    col += dcol;
+                    row += drow;
+                    if (col >= W) {
+                        col -= W;
+                        row += 1;
+                    }
+                }
+                others_sum = __reduce_add_sync(0xffffffffu, others_sum);
+                objects_sum = __reduce_add_sync(0xffffffffu, objects_sum);
+                reserved_sum = __reduce_add_sync(0xffffffffu, reserved_sum);
+                nearest = __reduce_min_sync(0xffffffffu, nearest);
+                const int nearest_d2 = nearest == 0xffffffffu ? 0 : (int)nearest;
+                if (lane == 0) {  // _encode_local_summary, features.py:289-330 via host LUTs
+                    frow[TL_FEAT_AGENT_RATIO] = o.agent_ratio_lut[min(others_sum, W2 - 1)];
+                    frow[TL_FEAT_OBJECT_RATIO] = o.tile_ratio_lut[min(objects_sum, W2)];
+                    frow[TL_FEAT_RESERVED_RATIO] = o.tile_ratio_lut[min(reserved_sum, W2)];
+                    frow[TL_FEAT_NEAREST] = o.nearest_lut[nearest_d2];
+                }
+
+                // -- social snippet (encoders/social.py:27-163) ----------------
+                int filled = 0;
+                if (o.social_base >= 0) {
+                    const int slot_dim = o.embed_dim + 3;
+                    const int total_slots = o.top_friends + o.top_rivals;
+                    const int social_len = total_slots * slot_dim + (o.include_aggregates ? 4 : 0);
+                    float* srow = frow + o.social_base;
+                    for (int k = lane; k < social_len; k += 32) srow[k] = 0.0f;
+                    // stable descending rank == position in sorted(..., reverse=True)
+                    const double key = trust + fam;
+                    int frank = 0;
+                    for (int j = 0; j < n_rel; ++j) {
+                        const double kj = __shfl_sync(0xffffffffu, key, j);
+                        frank += (kj > key || (kj == key && j < lane)) ? 1 : 0;
+                    }
+                    const bool valid = lane < n_rel;
+                    const bool is_friend = valid && frank < o.top_friends;
+                    const int n_friends = min(n_rel, o.top_friends);
+                    int rrank = 0;
+                    for (int j = 0; j < n_rel; ++j) {
+                        const double rj = __shfl_sync(0xffffffffu, riv, j);
+                        const int fj = __shfl_sync(0xffffffffu, (int)is_friend, j);
+                        if (!fj) rrank += (rj > riv || (rj == riv && j < lane)) ? 1 : 0;
+                    }
+                    const bool is_rival = valid && !is_friend && rrank < o.top_rivals;
+                    const int my_slot = is_friend ? frank : (is_rival ? n_friends + rrank : -1);
+                    filled = n_friends + min(o.top_rivals, n_rel - n_friends);
+                    __syncwarp();
+                    if (my_slot >= 0) {
+                        float* dst = srow + my_slot * slot_dim;
+                        for (int d = 0; d < o.embed_dim; ++d) {  // social.py:236-242, float32 division
+                            const unsigned byte = (unsigned)(emb[d >> 3] >> (8 * (d & 7))) & 255u;
+                            dst[d] = __fdiv_rn((float)byte, 255.0f);
+                        }
+                        dst[o.embed_dim + 0] = (float)trust;
+                        dst[o.embed_dim + 1] = (float)fam;
+                        dst[o.embed_dim + 2] = (float)riv;
+                    }
+                    if (o.include_aggregates && filled > 0) {  // social.py:90-105, 245-254
+                        double tv[TL_MAX_SOCIAL_SLOTS], rv[TL_MAX_SOCIAL_SLOTS];
+#pragma unroll
+                        for (int s = 0; s < TL_MAX_SOCIAL_SLOTS; ++s) {
+                            const unsigned owners = __ballot_sync(0xffffffffu, my_slot == s);
+                            const int src = owners ? __ffs(owners) - 1 : 0;
+                            const double t_s = __shfl_sync(0xffffffffu, trust, src);
+                            const double r_s = __shfl_sync(0xffffffffu, riv, src);
+                            tv[s] = owners ? t_s : 0.0;
+                            rv[s] = owners ? r_s : 0.0;
+                        }
+                        if (lane == 0) {
+                            double tmax = tv[0], rmax = rv[0];
+#pragma unroll
+                            for (int s = 1; s < TL_MAX_SOCIAL_SLOTS; ++s)
+                                if (s < filled) {
+                                    tmax = fmax(tmax, tv[s]);
+                                    rmax = fmax(rmax, rv[s]);
+                                }
+                            float* agg = srow + total_slots * slot_dim;
+                            agg[0] = (float)(np_sum_le8(tv, filled) / (double)filled);
+                            agg[1] = (float)tmax;
+                            agg[2] = (float)(np_sum_le8(rv, filled) / (double)filled);
+                            agg[3] = (float)rmax;
+                        }
+                    }
+                }
+                __syncwarp();
+
+                // -- 16-byte vectorised coalesced stores -----------------------
+                {
+                    const int head = (4 - map_mis) & 3;
+                    if (lane < head) mrow_g[lane] = st[lane];
+                    const int nvec = (map_elems - head) >> 2;
+                    float4* g4 = reinterpret_cast<float4*>(mrow_g + head);
+                    const float4* s4 = reinterpret_cast<const float4*>(st + head);
+                    for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
+                    const int tail0 = head + (nvec << 2);
+                    if (lane < map_elems - tail0) mrow_g[tail0 + lane] = st[tail0 + lane];
+                }
+                {
+                    float* frow_g = feat_g0 + (size_t)i * F;
+                    const int mis = (int)((reinterpret_cast<uintptr_t>(frow_g) >> 2) & 3);
+                    const int head = min((4 - mis) & 3, F);
+                    if (lane < head) frow_g[lane] = frow[lane];
+                    const int nvec = (F - head) >> 2;
+                    float4* g4 = reinterpret_cast<float4*>(frow_g + head);
+                    const float4* s4 = reinterpret_cast<const float4*>(frow + head);
+                    for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
+                    const int tail0 = head + (nvec << 2);
+                    if (lane < F - tail0) frow_g[tail0 + lane] = frow[tail0 + lane];
+                }
+                if (p.oo.summary && lane < TL_N_SUMMARY) {
+                    int v = 0;
+                    if (lane == TL_SUM_OTHER_AGENTS) v = others_sum;
+                    else if (lane == TL_SUM_OBJECTS) v = objects_sum;
+                    else if (lane == TL_SUM_RESERVED) v = reserved_sum;
+                    else if (lane == TL_SUM_NEAREST_D2) v = nearest_d2;
+                    else if (lane == TL_SUM_FILLED_SLOTS) v = filled;
+                    else if (lane == TL_SUM_RELATION_SOURCE) v = source;
+                    p.oo.summary[(size_t)it * p.oo.summary_tick_stride + (size_t)a * TL_N_SUMMARY + lane] = v;
+                }
+            }
+            __syncthreads();  // staging rows are reused by the next chunk
+        }
+
+        // ---- per-town KPI rows --------------------------------------------------
+        if (do_state && p.ro.kpi) {
+            __syncthreads();
+            if (tid < n_towns) {
+                const KpiAcc k = s_kpi[tid];
+                float* dst = p.ro.kpi + (size_t)it * p.ro.kpi_tick_stride + (size_t)(t0 + tid) * TL_N_KPI;
+                const double n = (double)k.count;
+                dst[TL_KPI_REWARD_SUM] = (float)k.rsum;
+                dst[TL_KPI_REWARD_SUMSQ] = (float)k.rsq;
+                dst[TL_KPI_HUNGER_MIN] = k.count ? (float)k.hmin : 0.0f;
+                dst[TL_KPI_HUNGER_MEAN] = k.count ? (float)(k.hsum / n) : 0.0f;
+                dst[TL_KPI_STARVING] = (float)k.starving;
+                dst[TL_KPI_TERMINATED] = (float)k.term;
+                dst[TL_KPI_LATENESS_MEAN] = k.count ? (float)(k.late / n) : 0.0f;
+                dst[TL_KPI_WALLET_MEAN] = k.count ? (float)(k.wallet / n) : 0.0f;
+            }
+        }
+        __syncthreads();  // state written this tick is visible to the CTA's next tick
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    snprintf(g_error, sizeof(g_error), "%s: %s", what, cudaGetErrorString(e));
+    return false;
+}
+
+int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlObsOut* oo,
+             const TlRewardOut* ro, uint32_t phases, int n_ticks) {
+    if (!b) return set_error("batch is NULL"), TL_ERR_ARG;
+    if (n_ticks < 0) return set_error("n_ticks < 0"), TL_ERR_ARG;
+    if (b->n_towns < 0 || b->n_agents < 0 || b->n_entities < 0) return set_error("negative batch size"), TL_ERR_ARG;
+    if (b->max_edges < 1 || b->max_edges > TL_MAX_EDGES) return set_error("max_edges out of range"), TL_ERR_ARG;
+    if (b->embed_words < 1 || b->embed_words > 4) return set_error("embed_words out of range"), TL_ERR_ARG;
+    if (b->grid_w < 1 || b->grid_h < 1 || b->grid_w > TL_MAX_GRID || b->grid_h > TL_MAX_GRID)
+        return set_error("grid size out of range"), TL_ERR_ARG;
+    if (!(phases & (TL_PHASE_DECAY | TL_PHASE_REWARD | TL_PHASE_OBS | TL_PHASE_ADVANCE)))
+        return set_error("empty phase mask"), TL_ERR_ARG;
+    if (phases & (TL_PHASE_DECAY | TL_PHASE_REWARD)) {
+        if (!rew) return set_error("reward params are NULL"), TL_ERR_ARG;
+    }
+    if (phases & (TL_PHASE_OBS | TL_PHASE_ADVANCE)) {
+        if (!obs) return set_error("observation params are NULL"), TL_ERR_ARG;
+    }
+    if (phases & TL_PHASE_OBS) {
+        if (!oo || !oo->map || !oo->features) return set_error("observation outputs are NULL"), TL_ERR_ARG;
+        if (obs->variant < 0 || obs->variant > 2) return set_error("unknown variant"), TL_ERR_ARG;
+        if (obs->window < 3 || obs->window > TL_MAX_WINDOW || !(obs->window & 1))
+            return set_error("window must be odd and in 3..21"), TL_ERR_ARG;
+        if (obs->n_ctypes < 0 || obs->n_ctypes > TL_MAX_CTYPES) return set_error("too many object channels"), TL_ERR_ARG;
+        const int expect_c = obs->variant == TL_VARIANT_HYBRID ? 4 : obs->variant == TL_VARIANT_FULL ? 6 : 5 + obs->n_ctypes;
+        if (obs->n_channels != expect_c) return set_error("n_channels does not match the variant"), TL_ERR_ARG;
+        if (obs->top_friends < 0 || obs->top_rivals < 0 || obs->top_friends + obs->top_rivals > TL_MAX_SOCIAL_SLOTS)
+            return set_error("social slots out of range"), TL_ERR_ARG;
+        if (obs->embed_dim < 1 || obs->embed_dim > 8 * b->embed_words)
+            return set_error("embed_dim exceeds the stored embedding words"), TL_ERR_ARG;
+        if (obs->n_features < TL_N_BASE_FEATURES) return set_error("n_features too small"), TL_ERR_ARG;
+        if (!obs->time_lut || !obs->progress_lut || !obs->slot_lut || !obs->agent_ratio_lut || !obs->tile_ratio_lut ||
+            !obs->nearest_lut || (obs->variant == TL_VARIANT_FULL && !obs->path_lut))
+            return set_error("a look-up table pointer is NULL"), TL_ERR_ARG;
+        if (obs->ticks_per_day < 1 || obs->max_slots < 1) return set_error("ticks_per_day / max_slots < 1"), TL_ERR_ARG;
+    }
+    (void)ro;
+    return TL_OK;
+}
+
+int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlObsOut* oo,
+           const TlRewardOut* ro, uint32_t phases, int n_ticks, cudaStream_t stream, int towns_per_cta_override) {
+    int rc = validate(b, obs, rew, oo, ro, phases, n_ticks);
+    if (rc != TL_OK) return rc;
+    if (b->n_towns == 0 || n_ticks == 0) return TL_OK;
+
+    KParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.b = *b;
+    if (obs) kp.obs = *obs;
+    if (rew) kp.rew = *rew;
+    if (oo) kp.oo = *oo;
+    if (ro) kp.ro = *ro;
+    kp.phases = phases;
+    kp.n_ticks = n_ticks;
+    const bool do_obs = phases & TL_PHASE_OBS;
+    if (!obs) {
+        kp.obs.window = 3;
+        kp.obs.ticks_per_day = 1;
+        kp.obs.n_features = TL_N_BASE_FEATURES;
+        kp.obs.social_base = -1;
+        kp.obs.landmark_base = -1;
+        kp.obs.personality_base = -1;
+    }
+
+    int device = 0;
+    if (!cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return TL_ERR_CUDA;
+    int max_smem = 0;
+    if (!cuda_ok(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device),
+                 "cudaDeviceGetAttribute"))
+        return TL_ERR_CUDA;
+
+    // towns per CTA: aim at one full phase-A warp (32 agents) per CTA
+    const int avg_agents = b->n_towns > 0 ? (b->n_agents + b->n_towns - 1) / b->n_towns : 1;
+    int tpc = towns_per_cta_override > 0 ? towns_per_cta_override : kChunk / (avg_agents > 0 ? avg_agents : 1);
+    if (tpc < 1) tpc = 1;
+    if (tpc > kMaxTownsPerCta) tpc = kMaxTownsPerCta;
+    kp.grid_tiles = b->grid_w * b->grid_h;
+    const int map_elems = do_obs ? kp.obs.n_channels * kp.obs.window * kp.obs.window : 0;
+    kp.feat_stride = kp.obs.n_features;
+    kp.map_stride = round_up(map_elems + 4, 4);
+    for (;;) {
+        int off = 0;
+        kp.off_grid = off;
+        off += do_obs ? round_up(tpc * kp.grid_tiles * 2, 16) : 0;
+        kp.off_ctype = -1;
+        if (do_obs && kp.obs.variant == TL_VARIANT_COMPACT && kp.obs.n_ctypes > 0) {
+            kp.off_ctype = off;
+            off += round_up(tpc * kp.grid_tiles * 2, 16);
+        }
+        kp.off_feat = off;
+        off += do_obs ? round_up((kChunk * kp.feat_stride + 4) * 4, 16) : 16;
+        kp.off_map = off;
+        off += do_obs ? kWarps * kp.map_stride * 4 : 0;
+        kp.off_meta = off;
+        off += (int)sizeof(ChunkMeta) * kChunk;
+        kp.smem_bytes = off;
+        if (off <= max_smem || tpc == 1) break;
+        --tpc;
+    }
+    if (kp.smem_bytes > max_smem) return set_error("town grid does not fit in shared memory"), TL_ERR_UNSUPPORTED;
+    kp.towns_per_cta = tpc;
+    const int grid = (b->n_towns + tpc - 1) / tpc;
+
+    auto run = [&](auto kernel) -> int {
+        if (!cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem_bytes),
+                     "cudaFuncSetAttribute"))
+            return TL_ERR_CUDA;
+        kernel<<<grid, kThreads, kp.smem_bytes, stream>>>(kp);
+        if (!cuda_ok(cudaGetLastError(), "kernel launch")) return TL_ERR_CUDA;
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return TL_OK;
+    };
+    switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
+        case TL_VARIANT_HYBRID: return run(tick_kernel<TL_VARIANT_HYBRID>);
+        case TL_VARIANT_FULL: return run(tick_kernel<TL_VARIANT_FULL>);
+        case TL_VARIANT_COMPACT: return run(tick_kernel<TL_VARIANT_COMPACT>);
+        default: return set_error("unknown variant"), TL_ERR_ARG;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* tl_last_error(void) { return g_error; }
+int tl_abi_version(void) { return TL_ABI_VERSION; }
+
+int tl_abi_struct_size(int idx) {
+    switch (idx) {
+        case 0: return (int)sizeof(TlTownBatch);
+        case 1: return (int)sizeof(TlObsParams);
+        case 2: return (int)sizeof(TlRewardParams);
+        case 3: return (int)sizeof(TlObsOut);
+        case 4: return (int)sizeof(TlRewardOut);
+        default: return -1;
+    }
+}
+
+int tl_device_sm_count(void) {
+    int device = 0, sms = 0;
+    if (!cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return TL_ERR_CUDA;
+    if (!cuda_ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute"))
+        return TL_ERR_CUDA;
+    return sms;
+}
+
+int64_t tl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int tl_obs_build(const TlTownBatch* batch, const TlObsParams* obs, const TlObsOut* out, tl_stream_t stream) {
+    return launch(batch, obs, nullptr, out, nullptr, TL_PHASE_OBS, 1, (cudaStream_t)stream, 0);
+}
+
+int tl_decay_reward(const TlTownBatch* batch, const TlRewardParams* rew, const TlRewardOut* out, uint32_t phases,
+                    tl_stream_t stream) {
+    if (phases & ~(TL_PHASE_DECAY | TL_PHASE_REWARD)) return set_error("tl_decay_reward accepts DECAY | REWARD only"), TL_ERR_ARG;
+    return launch(batch, nullptr, rew, nullptr, out, phases, 1, (cudaStream_t)stream, 0);
+}
+
+int tl_tick(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardParams* rew, const TlObsOut* obs_out,
+            const TlRewardOut* rew_out, uint32_t phases, int32_t n_ticks, tl_stream_t stream) {
+    return launch(batch, obs, rew, obs_out, rew_out, phases, n_ticks, (cudaStream_t)stream, 0);
+}
+
+// ---- host-buffer context ----------------------------------------------------
+struct TlContext {
+    int device;
+    cudaStream_t stream;
+    unsigned char* d_arena;
+    size_t arena_cap;
+    unsigned char* d_out;
+    size_t out_cap;
+    int64_t last_h2d, last_d2h;
+};
+
+TlContext* tl_context_create(int device) {
+    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
+    TlContext* ctx = new TlContext();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        delete ctx;
+        return nullptr;
+    }
+    return ctx;
+}
+
+void tl_context_destroy(TlContext* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_arena) cudaFree(ctx->d_arena);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int64_t tl_context_last_h2d_bytes(const TlContext* ctx) { return ctx ? ctx->last_h2d : 0; }
+int64_t tl_context_last_d2h_bytes(const TlContext* ctx) { return ctx ? ctx->last_d2h : 0; }
+
+namespace {
+
+struct Span {
+    const void* host;
+    void** slot;   // pointer field inside the device copy of the struct
+    size_t bytes;
+    bool writeback;
+};
+
+bool ensure(unsigned char** buf, size_t* cap, size_t need) {
+    if (need <= *cap) return true;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    size_t want = need + need / 4 + 4096;
+    if (!cuda_ok(cudaMalloc(reinterpret_cast<void**>(buf), want), "cudaMalloc")) return false;
+    *cap = want;
+    return true;
+}
+
+}  // namespace
+
+int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, const TlRewardParams* rew,
+                 const TlObsOut* hoo, const TlRewardOut* hro, uint32_t phases, int32_t n_ticks) {
+    if (!ctx) return set_error("context is NULL"), TL_ERR_ARG;
+    int rc = validate(hb, obs, rew, hoo, hro, phases, n_ticks);
+    if (rc != TL_OK) return rc;
+    if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return TL_ERR_CUDA;
+    ctx->last_h2d = ctx->last_d2h = 0;
+    if (hb->n_towns == 0 || n_ticks == 0) return TL_OK;
+
+    const size_t T = hb->n_towns, N = hb->n_agents, E = hb->n_entities, K = hb->max_edges, EW = hb->embed_words;
+    TlTownBatch db = *hb;
+    TlObsParams dobs;
+    memset(&dobs, 0, sizeof(dobs));
+    if (obs) dobs = *obs;
+    const bool do_obs = phases & TL_PHASE_OBS;
+    const bool do_state = phases & (TL_PHASE_DECAY | TL_PHASE_REWARD);
+    const bool do_adv = phases & TL_PHASE_ADVANCE;
+
+    Span spans[48];
+    int ns = 0;
+    auto add = [&](const void* host, void** slot, size_t bytes, bool wb) {
+        if (!host || bytes == 0) {
+            if (slot && !host) *slot = nullptr;
+            return;
+        }
+        spans[ns++] = Span{host, slot, bytes, wb};
+    };
+#define FIELD(name, bytes, wb) add(hb->name, (void**)&db.name, (bytes), (wb))
+    FIELD(town_agent_off, (T + 1) * 4, false);
+    FIELD(town_ent_off, (T + 1) * 4, false);
+    FIELD(town_tick, T * 4, do_adv);
+    FIELD(ent, E * 4, false);
+    FIELD(pos, N * 4, false);
+    FIELD(needs, 3 * N * 8, (phases & TL_PHASE_DECAY) != 0);
+    FIELD(wallet, N * 8, false);
+    FIELD(attendance, N * 8, false);
+    FIELD(wages_withheld, N * 8, false);
+    FIELD(wages_paid, N * 8, false);
+    FIELD(punctuality, N * 8, false);
+    FIELD(episode_total, N * 8, (phases & TL_PHASE_REWARD) != 0);
+    FIELD(social_in, 3 * N * 8, false);
+    FIELD(term_block_tick, N * 4, (phases & TL_PHASE_REWARD) != 0);
+    FIELD(lateness, N * 4, false);
+    FIELD(last_action_duration, N * 4, false);
+    FIELD(episode_tick, N * 4, do_adv);
+    FIELD(slot, N * 4, false);
+    FIELD(flags, N * 4, do_state);
+    FIELD(last_action_hash, N * 4, false);
+    FIELD(personality, 3 * N * 4, false);
+    FIELD(tie_count, N, false);
+    FIELD(tie_embed, N * K * EW * 8, false);
+    FIELD(tie_trust, N * K * 8, false);
+    FIELD(tie_fam, N * K * 8, false);
+    FIELD(tie_riv, N * K * 8, false);
+    FIELD(riv_count, N, false);
+    FIELD(riv_embed, N * K * EW * 8, false);
+    FIELD(riv_score, N * K * 8, false);
+#undef FIELD
+    const int n_batch_spans = ns;
+    if (do_obs) {
+        const size_t W2 = (size_t)obs->window * obs->window, R = obs->window / 2;
+        add(obs->time_lut, (void**)&dobs.time_lut, (size_t)obs->ticks_per_day * 2 * 4, false);
+        add(obs->progress_lut, (void**)&dobs.progress_lut, ((size_t)obs->ticks_per_day + 1) * 4, false);
+        add(obs->slot_lut, (void**)&dobs.slot_lut, (size_t)obs->max_slots * 4, false);
+        add(obs->agent_ratio_lut, (void**)&dobs.agent_ratio_lut, W2 * 4, false);
+        add(obs->tile_ratio_lut, (void**)&dobs.tile_ratio_lut, (W2 + 1) * 4, false);
+        add(obs->nearest_lut, (void**)&dobs.nearest_lut, (2 * R * R + 1) * 4, false);
+        add(obs->path_lut, (void**)&dobs.path_lut, 2 * W2 * 4, false);
+    }
+
+    // If the batch fields sit in one host arena, move them with a single copy.
+    uintptr_t lo = UINTPTR_MAX, hi = 0;
+    size_t sum = 0;
+    for (int i = 0; i < n_batch_spans; ++i) {
+        const uintptr_t p0 = (uintptr_t)spans[i].host;
+        lo = p0 < lo ? p0 : lo;
+        hi = p0 + spans[i].bytes > hi ? p0 + spans[i].bytes : hi;
+        sum += spans[i].bytes;
+    }
+    const bool contiguous = n_batch_spans > 0 && (hi - lo) <= sum + sum / 4 + 64 * 1024 && (lo % 16) == 0;
+    size_t need = 0;
+    if (contiguous) need = round_up((int)((hi - lo + 255) / 256), 1) * (size_t)256;
+    size_t cursor = need;
+    size_t dev_off[48];
+    for (int i = 0; i < ns; ++i) {
+        if (contiguous && i < n_batch_spans) {
+            dev_off[i] = (uintptr_t)spans[i].host - lo;
+        } else {
+            dev_off[i] = cursor;
+            cursor += (spans[i].bytes + 255) / 256 * 256;
+        }
+    }
+    if (!ensure(&ctx->d_arena, &ctx->arena_cap, cursor)) return TL_ERR_CUDA;
+    if (contiguous) {
+        if (!cuda_ok(cudaMemcpyAsync(ctx->d_arena, (const void*)lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream), "H2D arena"))
+            return TL_ERR_CUDA;
+        ctx->last_h2d += (int64_t)(hi - lo);
+    }
+    for (int i = 0; i < ns; ++i) {
+        *spans[i].slot = ctx->d_arena + dev_off[i];
+        if (contiguous && i < n_batch_spans) continue;
+        if (!cuda_ok(cudaMemcpyAsync(ctx->d_arena + dev_off[i], spans[i].host, spans[i].bytes, cudaMemcpyHostToDevice,
+                                     ctx->stream),
+                     "H2D field"))
+            return TL_ERR_CUDA;
+        ctx->last_h2d += (int64_t)spans[i].bytes;
+    }
+
+    // outputs
+    TlObsOut doo;
+    TlRewardOut dro;
+    memset(&doo, 0, sizeof(doo));
+    memset(&dro, 0, sizeof(dro));
+    struct OutSpan {
+        void* host;
+        size_t off, bytes;
+    } outs[8];
+    int no = 0;
+    size_t ocur = 0;
+    auto add_out = [&](void* host, size_t bytes) -> size_t {
+        const size_t off = ocur;
+        outs[no++] = OutSpan{host, off, bytes};
+        ocur += (bytes + 255) / 256 * 256;
+        return off;
+    };
+    size_t o_map = 0, o_feat = 0, o_sum = 0, o_rew = 0, o_comps = 0, o_term = 0, o_kpi = 0;
+    const size_t nt = (size_t)n_ticks;
+    if (do_obs) {
+        const size_t me = (size_t)obs->n_channels * obs->window * obs->window;
+        doo = *hoo;
+        auto span_elems = [&](int64_t stride, size_t per_tick) { return (nt - 1) * (size_t)stride + per_tick; };
+        o_map = add_out(hoo->map, span_elems(hoo->map_tick_stride, N * me) * 4);
+        o_feat = add_out(hoo->features, span_elems(hoo->features_tick_stride, N * (size_t)obs->n_features) * 4);
+        if (hoo->summary) o_sum = add_out(hoo->summary, span_elems(hoo->summary_tick_stride, N * TL_N_SUMMARY) * 4);
+    }
+    if (do_state && hro) {
+        dro = *hro;
+        auto span_elems = [&](int64_t stride, size_t per_tick) { return (nt - 1) * (size_t)stride + per_tick; };
+        if (hro->reward) o_rew = add_out(hro->reward, span_elems(hro->reward_tick_stride, N) * 4);
+        if (hro->comps) o_comps = add_out(hro->comps, span_elems(hro->comps_tick_stride, N * TL_N_COMPS) * 8);
+        if (hro->terminated) o_term = add_out(hro->terminated, span_elems(hro->terminated_tick_stride, N));
+        if (hro->kpi) o_kpi = add_out(hro->kpi, span_elems(hro->kpi_tick_stride, T * TL_N_KPI) * 4);
+    }
+    if (!ensure(&ctx->d_out, &ctx->out_cap, ocur ? ocur : 256)) return TL_ERR_CUDA;
+    if (do_obs) {
+        doo.map = (float*)(ctx->d_out + o_map);
+        doo.features = (float*)(ctx->d_out + o_feat);
+        doo.summary = hoo->summary ? (int32_t*)(ctx->d_out + o_sum) : nullptr;
+    }
+    if (do_state && hro) {
+        dro.reward = hro->reward ? (float*)(ctx->d_out + o_rew) : nullptr;
+        dro.comps = hro->comps ? (double*)(ctx->d_out + o_comps) : nullptr;
+        dro.terminated = hro->terminated ? (uint8_t*)(ctx->d_out + o_term) : nullptr;
+        dro.kpi = hro->kpi ? (float*)(ctx->d_out + o_kpi) : nullptr;
+    }
+
+    rc = launch(&db, obs ? &dobs : nullptr, rew, do_obs ? &doo : nullptr, (do_state && hro) ? &dro : nullptr, phases,
+                n_ticks, ctx->stream, 0);
+    if (rc != TL_OK) return rc;
+
+    for (int i = 0; i < no; ++i) {
+        if (!cuda_ok(cudaMemcpyAsync(outs[i].host, ctx->d_out + outs[i].off, outs[i].bytes, cudaMemcpyDeviceToHost, ctx->stream),
+                     "D2H output"))
+            return TL_ERR_CUDA;
+        ctx->last_d2h += (int64_t)outs[i].bytes;
+    }
+    for (int i = 0; i < n_batch_spans; ++i) {
+        if (!spans[i].writeback) continue;
+        if (!cuda_ok(cudaMemcpyAsync(const_cast<void*>(spans[i].host), ctx->d_arena + dev_off[i], spans[i].bytes,
+                                     cudaMemcpyDeviceToHost, ctx->stream),
+                     "D2H state"))
+            return TL_ERR_CUDA;
+        ctx->last_d2h += (int64_t)spans[i].bytes;
+    }
+    if (!cuda_ok(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize")) return TL_ERR_CUDA;
+    return TL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,277 @@
+"""Device-resident town batch and launch wrappers around the C ABI.
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream.  The
+arithmetic happens in ``libtownlet_b200.so`` (``csrc/townlet_b200.cu``); when
+that library is missing every entry point raises (no CPU fallback).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import capi
+from .params import ObsSpec, RewardSpec
+from .soa import MUTABLE_FIELDS, TownBatch
+
+_TORCH_DTYPES = {
+    "f8": torch.float64,
+    "f4": torch.float32,
+    "i4": torch.int32,
+    "u4": torch.int32,  # bit-identical storage; torch lacks arithmetic uint32
+    "u1": torch.uint8,
+    "u8": torch.int64,
+}
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+@dataclass
+class TickOutputs:
+    """Device tensors written by one launch (leading axis = ticks)."""
+
+    map: torch.Tensor | None = None
+    features: torch.Tensor | None = None
+    summary: torch.Tensor | None = None
+    reward: torch.Tensor | None = None
+    comps: torch.Tensor | None = None
+    terminated: torch.Tensor | None = None
+    kpi: torch.Tensor | None = None
+
+
+class DeviceTownBatch:
+    """A ``TownBatch`` resident in HBM plus the look-up tables of one ``ObsSpec``."""
+
+    def __init__(
+        self,
+        batch: TownBatch,
+        obs: ObsSpec | None = None,
+        rew: RewardSpec | None = None,
+        device: torch.device | str = "cuda:0",
+    ) -> None:
+        self.lib = capi.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise capi.TownletB200Error("townlet_b200 runs on CUDA devices only (no CPU fallback)")
+        self.host = batch
+        self.obs = obs
+        self.rew = rew
+        self.layout = batch.layout
+        host_t = torch.from_numpy(batch.arena[: batch.layout.total_bytes])
+        self.arena = host_t.to(self.device, non_blocking=False)
+        self._struct = batch.struct(self.arena.data_ptr())
+        self._luts: dict[str, torch.Tensor] = {}
+        self._obs_struct: capi.TlObsParams | None = None
+        self._rew_struct: capi.TlRewardParams | None = rew.struct() if rew is not None else None
+        if obs is not None:
+            for name, table in obs.luts().items():
+                self._luts[name] = torch.from_numpy(np.ascontiguousarray(table)).to(self.device)
+            self._obs_struct = obs.struct({k: v.data_ptr() for k, v in self._luts.items()})
+
+    # sizes ----------------------------------------------------------------
+    @property
+    def n_agents(self) -> int:
+        return self.layout.n_agents
+
+    @property
+    def n_towns(self) -> int:
+        return self.layout.n_towns
+
+    def field(self, name: str) -> torch.Tensor:
+        """Typed device view of one SoA field (shares the arena's memory)."""
+        lay = self.layout
+        dtype = lay.dtypes[name]
+        shape = lay.shapes[name]
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        off = lay.offsets[name]
+        return self.arena[off : off + nbytes].view(_TORCH_DTYPES[dtype.str[1:]]).view(*shape)
+
+    def upload(self, batch: TownBatch | None = None) -> None:
+        """Host → device copy of the whole arena (one copy)."""
+        src = batch or self.host
+        self.arena.copy_(torch.from_numpy(src.arena[: self.layout.total_bytes]), non_blocking=True)
+
+    def download_state(self) -> TownBatch:
+        """Device → host copy of the mutable fields into ``self.host`` (one copy)."""
+        n = self.layout.mutable_bytes
+        self.host.arena[:n] = self.arena[:n].cpu().numpy()
+        return self.host
+
+    # outputs --------------------------------------------------------------
+    def alloc_outputs(
+        self,
+        phases: int,
+        n_ticks: int = 1,
+        *,
+        summary: bool = False,
+        comps: bool = False,
+        kpi: bool = True,
+        reward: bool = True,
+        terminated: bool = True,
+    ) -> TickOutputs:
+        out = TickOutputs()
+        n, t, dev = self.n_agents, self.n_towns, self.device
+        if phases & capi.TL_PHASE_OBS:
+            assert self.obs is not None
+            out.map = torch.empty((n_ticks, n, *self.obs.map_shape), dtype=torch.float32, device=dev)
+            out.features = torch.empty((n_ticks, n, self.obs.n_features), dtype=torch.float32, device=dev)
+            if summary:
+                out.summary = torch.empty((n_ticks, n, capi.TL_N_SUMMARY), dtype=torch.int32, device=dev)
+        if phases & (capi.TL_PHASE_DECAY | capi.TL_PHASE_REWARD):
+            if reward:
+                out.reward = torch.zeros((n_ticks, n), dtype=torch.float32, device=dev)
+            if comps:
+                out.comps = torch.zeros((n_ticks, n, capi.TL_N_COMPS), dtype=torch.float64, device=dev)
+            if terminated:
+                out.terminated = torch.zeros((n_ticks, n), dtype=torch.uint8, device=dev)
+            if kpi:
+                out.kpi = torch.zeros((n_ticks, t, capi.TL_N_KPI), dtype=torch.float32, device=dev)
+        return out
+
+    @staticmethod
+    def _out_structs(out: TickOutputs, tick0: int = 0) -> tuple[capi.TlObsOut, capi.TlRewardOut]:
+        oo = capi.TlObsOut()
+        ro = capi.TlRewardOut()
+
+        def bind(struct, name, tensor):
+            if tensor is None:
+                return
+            view = tensor[tick0:]
+            setattr(struct, name, C.c_void_p(view.data_ptr()))
+            setattr(struct, f"{name}_tick_stride", int(tensor.stride(0)))
+
+        bind(oo, "map", out.map)
+        bind(oo, "features", out.features)
+        bind(oo, "summary", out.summary)
+        bind(ro, "reward", out.reward)
+        bind(ro, "comps", out.comps)
+        bind(ro, "terminated", out.terminated)
+        bind(ro, "kpi", out.kpi)
+        return oo, ro
+
+    # launches -------------------------------------------------------------
+    def tick(self, out: TickOutputs, phases: int = capi.TL_PHASE_ALL, n_ticks: int = 1, tick0: int = 0) -> None:
+        """One launch advancing ``n_ticks`` ticks; outputs go to ``out[tick0 : tick0 + n_ticks]``."""
+        oo, ro = self._out_structs(out, tick0)
+        obs_p = C.byref(self._obs_struct) if self._obs_struct is not None else None
+        rew_p = C.byref(self._rew_struct) if self._rew_struct is not None else None
+        with torch.cuda.device(self.device):
+            status = self.lib.tl_tick(
+                C.byref(self._struct), obs_p, rew_p, C.byref(oo), C.byref(ro), phases, n_ticks, _stream_ptr(self.device)
+            )
+        capi.check(status)
+
+    def obs_build(self, out: TickOutputs) -> None:
+        """``WorldObservationService.build_batch`` for every agent of the batch (service.py:201)."""
+        oo, _ = self._out_structs(out)
+        assert self._obs_struct is not None
+        with torch.cuda.device(self.device):
+            status = self.lib.tl_obs_build(C.byref(self._struct), C.byref(self._obs_struct), C.byref(oo), _stream_ptr(self.device))
+        capi.check(status)
+
+    def decay_reward(self, out: TickOutputs, phases: int = capi.TL_PHASE_DECAY | capi.TL_PHASE_REWARD) -> None:
+        """Need decay (grid.py:1439) and / or ``RewardEngine.compute`` (engine.py:34) in place."""
+        _, ro = self._out_structs(out)
+        assert self._rew_struct is not None
+        with torch.cuda.device(self.device):
+            status = self.lib.tl_decay_reward(
+                C.byref(self._struct), C.byref(self._rew_struct), C.byref(ro), phases, _stream_ptr(self.device)
+            )
+        capi.check(status)
+
+
+class HostEngine:
+    """Host-buffer path: one ``tl_host_tick`` call = H2D + kernels + D2H + sync.
+
+    This is what the drop-in services use and what the bench's ``e2e`` times.
+    Buffers may be pinned (``pin=True`` allocates them with torch) so copies
+    run at full PCIe rate.
+    """
+
+    def __init__(self, obs: ObsSpec | None, rew: RewardSpec | None, device: int = 0) -> None:
+        self.lib = capi.load_library()
+        self.obs = obs
+        self.rew = rew
+        self.ctx = self.lib.tl_context_create(device)
+        if not self.ctx:
+            capi.check(-2)
+        self._luts = {k: np.ascontiguousarray(v) for k, v in obs.luts().items()} if obs is not None else {}
+        self._obs_struct = obs.struct({k: v.ctypes.data for k, v in self._luts.items()}) if obs is not None else None
+        self._rew_struct = rew.struct() if rew is not None else None
+        self._pinned: list[torch.Tensor] = []
+
+    def close(self) -> None:
+        if self.ctx:
+            self.lib.tl_context_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pinned_array(self, shape: tuple[int, ...], dtype: np.dtype | str) -> np.ndarray:
+        """numpy view of a pinned torch buffer (kept alive by the engine)."""
+        np_dtype = np.dtype(dtype)
+        nbytes = max(1, int(np.prod(shape, dtype=np.int64)) * np_dtype.itemsize)
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        self._pinned.append(t)
+        return t.numpy()[: int(np.prod(shape, dtype=np.int64)) * np_dtype.itemsize].view(np_dtype).reshape(shape)
+
+    def alloc_outputs(
+        self, batch: TownBatch, phases: int, n_ticks: int = 1, *, summary: bool = True, comps: bool = True, pin: bool = False
+    ) -> dict[str, np.ndarray]:
+        make = self.pinned_array if pin else (lambda shape, dtype: np.zeros(shape, dtype=dtype))
+        n, t = batch.n_agents, batch.n_towns
+        out: dict[str, np.ndarray] = {}
+        if phases & capi.TL_PHASE_OBS:
+            assert self.obs is not None
+            out["map"] = make((n_ticks, n, *self.obs.map_shape), np.float32)
+            out["features"] = make((n_ticks, n, self.obs.n_features), np.float32)
+            if summary:
+                out["summary"] = make((n_ticks, n, capi.TL_N_SUMMARY), np.int32)
+        if phases & (capi.TL_PHASE_DECAY | capi.TL_PHASE_REWARD):
+            out["reward"] = make((n_ticks, n), np.float32)
+            out["terminated"] = make((n_ticks, n), np.uint8)
+            out["kpi"] = make((n_ticks, t, capi.TL_N_KPI), np.float32)
+            if comps:
+                out["comps"] = make((n_ticks, n, capi.TL_N_COMPS), np.float64)
+        return out
+
+    def tick(self, batch: TownBatch, out: dict[str, np.ndarray], phases: int, n_ticks: int = 1) -> None:
+        """Run on HOST buffers; ``batch`` state fields are updated in place."""
+        oo = capi.TlObsOut()
+        ro = capi.TlRewardOut()
+        for struct, names in ((oo, ("map", "features", "summary")), (ro, ("reward", "comps", "terminated", "kpi"))):
+            for name in names:
+                arr = out.get(name)
+                if arr is None:
+                    continue
+                setattr(struct, name, C.c_void_p(arr.ctypes.data))
+                setattr(struct, f"{name}_tick_stride", int(arr.strides[0] // arr.itemsize))
+        bs = batch.struct()
+        status = self.lib.tl_host_tick(
+            self.ctx,
+            C.byref(bs),
+            C.byref(self._obs_struct) if self._obs_struct is not None else None,
+            C.byref(self._rew_struct) if self._rew_struct is not None else None,
+            C.byref(oo),
+            C.byref(ro),
+            phases,
+            n_ticks,
+        )
+        capi.check(status)
+
+    @property
+    def last_h2d_bytes(self) -> int:
+        return int(self.lib.tl_context_last_h2d_bytes(self.ctx))
+
+    @property
+    def last_d2h_bytes(self) -> int:
+        return int(self.lib.tl_context_last_d2h_bytes(self.ctx))
