@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
         self.samples: list[int] = []
         self.reasons: set[str] = set()
         self.max_mhz = 0
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self) -> None:
         try:
@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             }
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 for bit, name in names.items():
@@ -98,7 +98,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
 
     def stop(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz or None, "reasons": sorted(self.reasons)}

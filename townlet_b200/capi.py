@@ -244,6 +244,7 @@ def nvcc_command(out: Path = LIB_PATH) -> list[str]:
         "-gencode",
         "arch=compute_100a,code=sm_100a",
         "-O3",
+        "-fmad=false",  # float64 reward guardrail flags must round exactly like the reference (no FMA contraction)
         "-lineinfo",
         "-std=c++17",
         "-Xcompiler",

@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
                 const int K = p.b.max_edges, EW = p.b.embed_words;
                 const int n_ties = p.b.tie_count[a];
                 int n_rel = n_ties;
-                int source = n_ties > 0 ? 1 : 0;
+                int source = (n_ties > 0 && o.social_base >= 0) ? 1 : 0;
                 double trust = 0.0, fam = 0.0, riv = 0.0;
                 const uint64_t* emb = nullptr;
                 if (o.social_base >= 0) {
