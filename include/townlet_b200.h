@@ -287,6 +287,7 @@ typedef struct TlObsParams {
     const float* tile_ratio_lut;  /* [W*W+1] min(1, n/W*W); index min(n, W*W) (map.py:129-130) */
     const float* nearest_lut;     /* [2*r*r+1] clamp01(hypot/max(1,r)) by squared distance (map.py:131-134) */
     const float* path_lut;        /* [2][W*W] dx/|d|, dy/|d| (map.py:115-125); full variant only */
+    const float* embed_lut;       /* [256] float32(b) / 255.0f in float32 (social.py:236-242) */
 } TlObsParams;
 
 /* Reward / decay parameters derived from config.rewards (config/rewards.py). */

@@ -53,8 +53,10 @@ def _check_state(batch, ref):
         np.testing.assert_allclose(batch.episode_total, ref["episode_total"][-1], rtol=REL_TOL, atol=1e-12)
 
 
+@pytest.mark.parametrize("mode", ["ent", "grid"])
 @pytest.mark.parametrize("path", FIXTURES, ids=[p.stem for p in FIXTURES])
-def test_device_path_matches_reference_golden(path) -> None:
+def test_device_path_matches_reference_golden(path, mode, monkeypatch) -> None:
+    monkeypatch.setenv("TL_MODE", mode)  # both kernel forms: entity list and dense shared-memory grid
     batch, obs, rew, meta, ref = load_fixture(path)
     got = _device_run(batch, obs, rew, meta["phases"], meta["n_ticks"])
     assert_obs_equal(got, ref, path.stem)
@@ -86,9 +88,14 @@ SYNTH_CASES = [
 ]
 
 
+@pytest.mark.parametrize("mode", ["ent", "grid", "ent-chunk8"])
 @pytest.mark.parametrize("case", SYNTH_CASES, ids=[c[0] for c in SYNTH_CASES])
-def test_cuda_matches_oracle_on_synthetic_towns(case) -> None:
+def test_cuda_matches_oracle_on_synthetic_towns(case, mode, monkeypatch) -> None:
     from oracle.oracle import oracle_tick
+
+    monkeypatch.setenv("TL_MODE", mode.split("-")[0])
+    if mode == "ent-chunk8":
+        monkeypatch.setenv("TL_CHUNK", "8")
 
     _, variant, grid, agents, towns, ticks, extra = case
     obs = ObsSpec(variant=variant, **extra)

@@ -168,6 +168,7 @@ class TlObsParams(C.Structure):
         ("tile_ratio_lut", _p),
         ("nearest_lut", _p),
         ("path_lut", _p),
+        ("embed_lut", _p),
     ]
 
 

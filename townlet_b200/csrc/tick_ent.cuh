@@ -1,0 +1,548 @@
+// tick_ent.cuh — entity-list form of the tick kernel (included by townlet_b200.cu
+// inside its anonymous namespace; uses KParams, reward_agent, KpiAcc, pos_x/pos_y).
+//
+// One WARP (= one CTA of 32 threads) owns a group of consecutive towns whose
+// agents fill one phase-A pass.  No block barriers: warps are independent and
+// the hardware block scheduler balances them.
+//
+//   phase A  one THREAD per agent (coalesced SoA loads): float64 need decay,
+//            faint predicate, reward with guardrails, per-town KPI partials by
+//            segmented warp shuffles, every scalar feature and the whole social
+//            snippet (stable top-k by repeated first-argmax) into a shared row.
+//   phase B  the WARP serves one agent at a time: the staging tile is cleared
+//            with 16-byte stores, each lane tests one entity of the agent's town
+//            against the egocentric window and sets its cell (the sparse form
+//            of build_local_cache + the window loop, cache.py:16-41 /
+//            encoders/map.py:80-125), the local summary comes from REDUX over
+//            the same tests, and the tile leaves with 16-byte coalesced stores.
+//   The feature rows of the whole pass are written back in one coalesced sweep.
+//
+// Per agent this is ~100 warp instructions instead of ~1400 for the dense
+// grid-gather form (profiles/r1_*), which is what lets the path reach the
+// HBM write roofline.  The dense shared-memory grid form stays available
+// (tick_kernel) for towns with hundreds of entities.
+
+template <int VARIANT>
+__global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);
+    float* s_map = reinterpret_cast<float*>(smem + p.off_map);
+    KpiAcc* s_kpi = reinterpret_cast<KpiAcc*>(smem + p.off_meta);
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int T = p.b.n_towns;
+    const int N = p.b.n_agents;
+    const int t0 = blockIdx.x * p.towns_per_cta;
+    const int n_towns = min(p.towns_per_cta, T - t0);
+    if (n_towns <= 0) return;
+
+    const bool do_decay = p.phases & TL_PHASE_DECAY;
+    const bool do_reward = p.phases & TL_PHASE_REWARD;
+    const bool do_obs = p.phases & TL_PHASE_OBS;
+    const bool do_advance = p.phases & TL_PHASE_ADVANCE;
+    const bool do_state = do_decay || do_reward;
+    const bool do_kpi = do_state && p.ro.kpi != nullptr;
+
+    const TlObsParams& o = p.obs;
+    const int W = o.window;
+    const int R = W >> 1;
+    const int W2 = W * W;
+    const int F = o.n_features;
+    const int map_elems = o.n_channels * W2;
+    const int chunk_cap = p.chunk;  // agents per phase-A pass (<= 32)
+
+    // lane s holds the offsets of town t0 + s (s <= n_towns)
+    int my_aoff = 0, my_eoff = 0, my_tick = 0;
+    if (lane <= n_towns) {
+        my_aoff = p.b.town_agent_off[t0 + lane];
+        my_eoff = p.b.town_ent_off[t0 + lane];
+    }
+    if (lane < n_towns) my_tick = p.b.town_tick[t0 + lane];
+    const int a_begin = __shfl_sync(FULL, my_aoff, 0);
+    const int a_end = __shfl_sync(FULL, my_aoff, n_towns);
+    const int n_chunks = (a_end - a_begin + chunk_cap - 1) / chunk_cap;
+
+    for (int it = 0; it < p.n_ticks; ++it) {
+        if (do_advance && lane < n_towns) {  // core/sim_loop.py:635,659
+            my_tick += 1;
+            p.b.town_tick[t0 + lane] = my_tick;
+        }
+        if (do_kpi && lane < n_towns) {
+            KpiAcc z;
+            z.rsum = z.rsq = z.hsum = z.late = z.wallet = 0.0;
+            z.hmin = 1e300;
+            z.starving = z.term = z.count = 0;
+            s_kpi[lane] = z;
+        }
+        __syncwarp();
+
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            const int c_begin = a_begin + chunk * chunk_cap;
+            const int c_n = min(chunk_cap, a_end - c_begin);
+            float* feat_g0 = do_obs ? p.oo.features + (size_t)it * p.oo.features_tick_stride + (size_t)c_begin * F : nullptr;
+            const int feat_mis = do_obs ? (int)((reinterpret_cast<uintptr_t>(feat_g0) >> 2) & 3) : 0;
+            float* feat_s0 = s_feat + feat_mis;  // mirrors the 16-byte misalignment of the global rows
+
+            // =================== phase A: one thread per agent ==================
+            const bool active = lane < c_n;
+            const int a = c_begin + (active ? lane : 0);
+            int slot = 0;
+            for (int s = 1; s < n_towns; ++s) slot += (a >= __shfl_sync(FULL, my_aoff, s)) ? 1 : 0;
+            const int town_abeg = __shfl_sync(FULL, my_aoff, slot);
+            const int town_aend = __shfl_sync(FULL, my_aoff, slot + 1);
+            const int town_ebeg = __shfl_sync(FULL, my_eoff, slot);
+            const int town_eend = __shfl_sync(FULL, my_eoff, slot + 1);
+            const int tick = __shfl_sync(FULL, my_tick, slot);
+
+            double need0 = 0.0;
+            uint32_t fl = 0;
+            bool terminated = false;
+            double reward_total = 0.0;
+            int cx = 0, cy = 0, filled = 0, source = 0;
+            if (active) {
+                double need[3];
+                need[0] = p.b.needs[a];
+                need[1] = p.b.needs[(size_t)N + a];
+                need[2] = p.b.needs[2 * (size_t)N + a];
+                fl = p.b.flags[a];
+                int episode_tick = p.b.episode_tick[a];
+                const unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
+                if (do_decay) {  // world/grid.py:1439-1455
+#pragma unroll
+                    for (int k = 0; k < TL_N_NEEDS; ++k) {
+                        double mult = 1.0;
+                        if (p.rew.decay_personality && profile != 0) {
+                            mult = p.rew.need_mult[profile][k];
+                            if (mult <= 0.0) mult = 1.0;
+                        }
+                        const double adjusted = p.rew.decay_rate[k] * mult;
+                        need[k] = fmax(0.0, need[k] - adjusted);
+                        p.b.needs[(size_t)k * N + a] = need[k];
+                    }
+                }
+                if (do_state && p.rew.fuse_faint) {  // lifecycle/manager.py:39-45
+                    fl = (fl & ~TL_F_FAINTED) | (need[0] <= p.rew.faint_threshold ? TL_F_FAINTED : 0u);
+                    p.b.flags[a] = fl;
+                }
+                terminated = (fl & (TL_F_TERMINATED | TL_F_FAINTED)) != 0;
+                unsigned reason = (fl & TL_F_REASON_MASK) >> TL_F_REASON_SHIFT;
+                if (reason == 0 && (fl & TL_F_FAINTED)) reason = 1;
+                if (do_advance) {  // world/core/context.py:283-289
+                    const int span = max(1, o.ticks_per_day);
+                    episode_tick = (episode_tick + 1) % span;
+                    p.b.episode_tick[a] = episode_tick;
+                }
+                if (do_reward) {
+                    RewardResult rr;
+                    reward_agent(p, a, tick, need, fl, terminated, reason, rr);
+                    reward_total = rr.total;
+                    if (p.ro.reward) p.ro.reward[(size_t)it * p.ro.reward_tick_stride + a] = (float)rr.total;
+                    if (p.ro.comps) {
+                        double* dst = p.ro.comps + (size_t)it * p.ro.comps_tick_stride + (size_t)a * TL_N_COMPS;
+#pragma unroll
+                        for (int i = 0; i < TL_N_COMPS; i += 2)
+                            *reinterpret_cast<double2*>(dst + i) = make_double2(rr.comps[i], rr.comps[i + 1]);
+                    }
+                }
+                if (do_state && p.ro.terminated)
+                    p.ro.terminated[(size_t)it * p.ro.terminated_tick_stride + a] = terminated ? 1 : 0;
+                need0 = need[0];
+
+                if (do_obs) {  // encoders/features.py:43-404
+                    float* f = feat_s0 + lane * F;
+                    f[TL_FEAT_NEED_HUNGER] = (float)need[0];
+                    f[TL_FEAT_NEED_HYGIENE] = (float)need[1];
+                    f[TL_FEAT_NEED_ENERGY] = (float)need[2];
+                    f[TL_FEAT_WALLET] = (float)p.b.wallet[a];
+                    f[TL_FEAT_LATENESS] = (float)p.b.lateness[a];
+                    f[TL_FEAT_ON_SHIFT] = (fl & TL_F_ON_SHIFT) ? 1.0f : 0.0f;
+                    int m = tick % o.ticks_per_day;
+                    if (m < 0) m += o.ticks_per_day;
+                    const float2 sc = *reinterpret_cast<const float2*>(o.time_lut + 2 * m);
+                    f[TL_FEAT_TIME_SIN] = sc.x;
+                    f[TL_FEAT_TIME_COS] = sc.y;
+                    f[TL_FEAT_ATTENDANCE] = (float)p.b.attendance[a];
+                    f[TL_FEAT_WAGES_WITHHELD] = (float)p.b.wages_withheld[a];
+                    unsigned st = (fl & TL_F_SHIFT_MASK) >> TL_F_SHIFT_SHIFT;
+                    if (st > 4) st = 0;
+#pragma unroll
+                    for (unsigned k = 0; k < 5; ++k) f[TL_FEAT_SHIFT_PRE + k] = (k == st) ? 1.0f : 0.0f;
+                    const int slot_idx = p.b.slot[a];
+                    f[TL_FEAT_SLOT_NORM] = (slot_idx >= 0 && slot_idx < o.max_slots)
+                                               ? o.slot_lut[slot_idx]
+                                               : (float)((double)slot_idx / (double)o.max_slots);
+                    f[TL_FEAT_CTX_RESET] = ((fl & TL_F_CTX_RESET) || terminated) ? 1.0f : 0.0f;  // service.py:224-229
+                    f[TL_FEAT_EPISODE_PROGRESS] =
+                        episode_tick <= 0 ? 0.0f : o.progress_lut[min(episode_tick, o.ticks_per_day)];
+                    const int K = p.b.max_edges;
+                    const size_t rbase = (size_t)a * K;
+                    const int n_riv = p.b.riv_count[a];
+                    {  // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
+                        const int nr = min(n_riv, o.rivalry_max_edges);
+                        double mx = 0.0;
+                        int avoid = 0;
+                        for (int j = 0; j < nr; ++j) {
+                            const double v = p.b.riv_score[rbase + j];
+                            if (j == 0) mx = v;
+                            avoid += (v >= o.avoid_threshold) ? 1 : 0;
+                        }
+                        f[TL_FEAT_RIVALRY_MAX] = (float)mx;
+                        f[TL_FEAT_RIVALRY_AVOID] = (float)avoid;
+                    }
+                    f[TL_FEAT_LAST_HASH] = p.b.last_action_hash[a];
+                    f[TL_FEAT_LAST_SUCCESS] = (fl & TL_F_LAST_SUCCESS) ? 1.0f : 0.0f;
+                    f[TL_FEAT_LAST_DURATION] = (float)p.b.last_action_duration[a];
+                    f[TL_FEAT_RESERVATION] = (fl & TL_F_RESERVATION) ? 1.0f : 0.0f;
+                    f[TL_FEAT_IN_QUEUE] = (fl & TL_F_IN_QUEUE) ? 1.0f : 0.0f;
+                    // nearest object per landmark type: first minimum of the squared
+                    // distance in insertion order (world/observe.py:109-147)
+                    const int32_t pw = p.b.pos[a];
+                    cx = pos_x(pw);
+                    cy = pos_y(pw);
+                    int best_d2[5] = {-1, -1, -1, -1, -1};
+                    int best_dx[5] = {0, 0, 0, 0, 0}, best_dy[5] = {0, 0, 0, 0, 0};
+                    const bool all_types = o.landmark_base >= 0;
+                    const int e_obj = town_ebeg + (town_aend - town_abeg);
+                    for (int e = e_obj; e < town_eend; ++e) {
+                        const uint32_t w = __ldg(p.b.ent + e);
+                        if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w)) continue;
+                        const int lt = (int)TL_ENT_LTYPE(w);
+                        if (lt == 0 || (!all_types && lt != o.path_hint_ltype)) continue;
+                        const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
+                        const int d2 = dx * dx + dy * dy;
+#pragma unroll
+                        for (int l = 1; l <= 4; ++l) {
+                            if (l == lt && (best_d2[l] < 0 || d2 < best_d2[l])) {
+                                best_d2[l] = d2;
+                                best_dx[l] = dx;
+                                best_dy[l] = dy;
+                            }
+                        }
+                    }
+                    {  // _encode_path_hint, features.py:251-286
+                        double north = 0.0, south = 0.0, east = 0.0, west = 0.0;
+                        int hd2 = -1, hdx = 0, hdy = 0;
+#pragma unroll
+                        for (int l = 1; l <= 4; ++l)
+                            if (l == o.path_hint_ltype) {
+                                hd2 = best_d2[l];
+                                hdx = best_dx[l];
+                                hdy = best_dy[l];
+                            }
+                        if (hd2 >= 0) {
+                            const int norm = abs(hdx) + abs(hdy);
+                            if (norm != 0) {
+                                const double dn = (double)norm;
+                                north = fmax(0.0, (double)-hdy) / dn;
+                                south = fmax(0.0, (double)hdy) / dn;
+                                east = fmax(0.0, (double)hdx) / dn;
+                                west = fmax(0.0, (double)-hdx) / dn;
+                            }
+                        }
+                        f[TL_FEAT_PATH_NORTH + 0] = (float)north;
+                        f[TL_FEAT_PATH_NORTH + 1] = (float)south;
+                        f[TL_FEAT_PATH_NORTH + 2] = (float)east;
+                        f[TL_FEAT_PATH_NORTH + 3] = (float)west;
+                    }
+                    if (all_types) {  // _encode_landmarks, features.py:333-356
+#pragma unroll
+                        for (int l = 1; l <= 4; ++l) {
+                            float* dst = f + o.landmark_base + 3 * (l - 1);
+                            if (best_d2[l] < 0) {
+                                dst[0] = dst[1] = dst[2] = 0.0f;
+                            } else {
+                                // sqrt of an exact integer: equals np.hypot after the float32 store
+                                const double distance = sqrt((double)best_d2[l]);
+                                const double norm = distance > 0.0 ? distance : 1.0;
+                                dst[0] = (float)((double)best_dx[l] / norm);
+                                dst[1] = (float)((double)best_dy[l] / norm);
+                                dst[2] = (float)distance;
+                            }
+                        }
+                    }
+                    if (o.personality_base >= 0) {  // features.py:359-380
+                        const bool has = p.b.personality != nullptr;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            f[o.personality_base + k] = has ? p.b.personality[(size_t)k * N + a] : 0.0f;
+                    }
+
+                    // ---- social snippet (encoders/social.py:27-254) -------------
+                    if (o.social_base >= 0) {
+                        const int slot_dim = o.embed_dim + 3;
+                        const int total_slots = o.top_friends + o.top_rivals;
+                        const int social_len = total_slots * slot_dim + (o.include_aggregates ? 4 : 0);
+                        float* srow = f + o.social_base;
+                        for (int k = 0; k < social_len; ++k) srow[k] = 0.0f;
+                        const int EW = p.b.embed_words;
+                        const int n_t = p.b.tie_count[a];
+                        const bool from_ties = n_t > 0;  // _resolve_relationships, social.py:165-209
+                        const int n_rel = from_ties ? n_t : min(n_riv, o.top_rivals);
+                        source = from_ties ? 1 : (n_rel > 0 ? 2 : 0);
+                        const double* kt = p.b.tie_trust + rbase;
+                        const double* kf = p.b.tie_fam + rbase;
+                        const double* kr = from_ties ? p.b.tie_riv + rbase : p.b.riv_score + rbase;
+                        const uint64_t* ke = (from_ties ? p.b.tie_embed : p.b.riv_embed) + rbase * EW;
+                        // sorted(..., reverse=True)[:k] is stable: repeated FIRST argmax (social.py:137-156)
+                        unsigned chosen = 0, sel = 0;
+                        const int n_friends = min(n_rel, o.top_friends);
+                        for (int s = 0; s < n_friends; ++s) {
+                            int best = -1;
+                            double bk = 0.0;
+                            for (int j = 0; j < n_rel; ++j) {
+                                if ((chosen >> j) & 1u) continue;
+                                const double key = from_ties ? kt[j] + kf[j] : 0.0;
+                                if (best < 0 || key > bk) {
+                                    best = j;
+                                    bk = key;
+                                }
+                            }
+                            chosen |= 1u << best;
+                            sel |= (unsigned)best << (4 * s);
+                        }
+                        const int n_rivals = min(o.top_rivals, n_rel - n_friends);
+                        for (int s = 0; s < n_rivals; ++s) {
+                            int best = -1;
+                            double bk = 0.0;
+                            for (int j = 0; j < n_rel; ++j) {
+                                if ((chosen >> j) & 1u) continue;
+                                const double key = kr[j];
+                                if (best < 0 || key > bk) {
+                                    best = j;
+                                    bk = key;
+                                }
+                            }
+                            chosen |= 1u << best;
+                            sel |= (unsigned)best << (4 * (n_friends + s));
+                        }
+                        filled = n_friends + n_rivals;
+                        double tsum = 0.0, rsum = 0.0, tmax = 0.0, rmax = 0.0;
+                        for (int s = 0; s < filled; ++s) {
+                            const int j = (sel >> (4 * s)) & 15;
+                            const double trust = from_ties ? kt[j] : 0.0;
+                            const double fam = from_ties ? kf[j] : 0.0;
+                            const double riv = kr[j];
+                            float* dst = srow + s * slot_dim;
+                            for (int d = 0; d < o.embed_dim; ++d) {  // social.py:236-242
+                                const unsigned byte = (unsigned)(ke[(size_t)j * EW + (d >> 3)] >> (8 * (d & 7))) & 255u;
+                                dst[d] = __ldg(o.embed_lut + byte);
+                            }
+                            dst[o.embed_dim + 0] = (float)trust;
+                            dst[o.embed_dim + 1] = (float)fam;
+                            dst[o.embed_dim + 2] = (float)riv;
+                            tsum += trust;  // numpy sums left to right below 8 values
+                            rsum += riv;
+                            tmax = s == 0 ? trust : fmax(tmax, trust);
+                            rmax = s == 0 ? riv : fmax(rmax, riv);
+                        }
+                        if (o.include_aggregates && filled > 0) {  // social.py:90-105, 245-254
+                            if (filled == 8) {  // numpy's unrolled pairwise block
+                                double tv[8], rv[8];
+#pragma unroll
+                                for (int s = 0; s < 8; ++s) {
+                                    const int j = (sel >> (4 * s)) & 15;
+                                    tv[s] = from_ties ? kt[j] : 0.0;
+                                    rv[s] = kr[j];
+                                }
+                                tsum = ((tv[0] + tv[1]) + (tv[2] + tv[3])) + ((tv[4] + tv[5]) + (tv[6] + tv[7]));
+                                rsum = ((rv[0] + rv[1]) + (rv[2] + rv[3])) + ((rv[4] + rv[5]) + (rv[6] + rv[7]));
+                            }
+                            float* agg = srow + total_slots * slot_dim;
+                            agg[0] = (float)(tsum / (double)filled);
+                            agg[1] = (float)tmax;
+                            agg[2] = (float)(rsum / (double)filled);
+                            agg[3] = (float)rmax;
+                        }
+                    }
+                }
+            }
+
+            // ---- per-town KPIs: segmented warp-shuffle reduction ----------------
+            if (do_kpi) {
+                const int seg = active ? slot : -1 - lane;  // inactive lanes are their own segment
+                double v_r = reward_total, v_q = reward_total * reward_total, v_h = active ? need0 : 0.0;
+                double v_m = active ? need0 : 1e300, v_w = active ? p.b.wallet[a] : 0.0;
+                int v_l = active ? p.b.lateness[a] : 0;
+                // starving | terminated | count packed in 10-bit fields
+                int v_c = active ? ((need0 <= p.rew.starvation_threshold ? 1 : 0) | (terminated ? 1 << 10 : 0) | (1 << 20)) : 0;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int oseg = __shfl_down_sync(FULL, seg, off);
+                    const double o_r = __shfl_down_sync(FULL, v_r, off), o_q = __shfl_down_sync(FULL, v_q, off);
+                    const double o_h = __shfl_down_sync(FULL, v_h, off), o_m = __shfl_down_sync(FULL, v_m, off);
+                    const double o_w = __shfl_down_sync(FULL, v_w, off);
+                    const int o_l = __shfl_down_sync(FULL, v_l, off), o_c = __shfl_down_sync(FULL, v_c, off);
+                    if (lane + off < 32 && oseg == seg) {
+                        v_r += o_r;
+                        v_q += o_q;
+                        v_h += o_h;
+                        v_m = fmin(v_m, o_m);
+                        v_w += o_w;
+                        v_l += o_l;
+                        v_c += o_c;
+                    }
+                }
+                const int prev_seg = __shfl_up_sync(FULL, seg, 1);
+                if (active && (lane == 0 || prev_seg != seg)) {  // segment head; passes arrive in order
+                    KpiAcc& k = s_kpi[slot];
+                    k.rsum += v_r;
+                    k.rsq += v_q;
+                    k.hsum += v_h;
+                    k.hmin = fmin(k.hmin, v_m);
+                    k.wallet += v_w;
+                    k.late += (double)v_l;
+                    k.starving += v_c & 1023;
+                    k.term += (v_c >> 10) & 1023;
+                    k.count += v_c >> 20;
+                }
+            }
+            if (!do_obs) continue;  // warp-uniform
+            __syncwarp();
+
+            // =================== phase B: the warp serves one agent at a time =====
+            const int fill_vecs = p.map_stride >> 2;
+            for (int i = 0; i < c_n; ++i) {
+                const int a_i = c_begin + i;
+                const int cxi = __shfl_sync(FULL, cx, i), cyi = __shfl_sync(FULL, cy, i);
+                const int eb = __shfl_sync(FULL, town_ebeg, i), ee = __shfl_sync(FULL, town_eend, i);
+                const int self_e = eb + (a_i - __shfl_sync(FULL, town_abeg, i));
+                float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)a_i * map_elems;
+                const int map_mis = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
+                float* buf = s_map + (i & 1) * p.map_stride;  // double buffered: no barrier after the stores
+                float* st = buf + map_mis;
+                {
+                    float4* b4 = reinterpret_cast<float4*>(buf);
+                    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    for (int v = lane; v < fill_vecs; v += 32) b4[v] = z;
+                }
+                __syncwarp();
+                const int centre_tile = R * W + R;
+                if (VARIANT == TL_VARIANT_COMPACT) {
+                    float* walk = st + (4 + o.n_ctypes) * W2;  // map.py:231-241: empty tiles are walkable
+                    for (int k = lane; k < W2; k += 32) walk[k] = (k == centre_tile) ? 0.0f : 1.0f;
+                } else if (VARIANT == TL_VARIANT_FULL) {
+                    for (int k = lane; k < 2 * W2; k += 32) st[4 * W2 + k] = __ldg(o.path_lut + k);  // map.py:115-125
+                }
+                if (lane == 0) st[centre_tile] = 1.0f;  // map.py:69 / :185-186
+                if (VARIANT == TL_VARIANT_COMPACT) __syncwarp();
+
+                int n_ag = 0, n_obj = 0, n_res = 0, centre_has = 0;
+                unsigned nearest = 0xffffffffu;
+                for (int e0 = eb; e0 < ee; e0 += 32) {
+                    const int e = e0 + lane;
+                    const bool valid = e < ee;
+                    const uint32_t w = valid ? __ldg(p.b.ent + e) : 0u;
+                    const int dx = TL_ENT_X(w) - cxi, dy = TL_ENT_Y(w) - cyi;
+                    const bool inwin = valid && (unsigned)(dx + R) <= (unsigned)(2 * R) && (unsigned)(dy + R) <= (unsigned)(2 * R);
+                    const int tile = (dy + R) * W + (dx + R);
+                    const unsigned kind = TL_ENT_KIND(w);
+                    const bool is_agent = inwin && kind == TL_KIND_AGENT;
+                    const bool is_obj = inwin && kind == TL_KIND_OBJECT && TL_ENT_TILE(w);
+                    const bool is_res = inwin && kind == TL_KIND_RESERVED;
+                    // LocalSummary (map.py:88-103)
+                    n_ag += is_agent ? 1 : 0;
+                    n_obj += is_obj ? 1 : 0;
+                    n_res += is_res ? 1 : 0;
+                    const int d2 = dx * dx + dy * dy;
+                    if (is_agent) {
+                        if (d2 == 0) centre_has = 1;
+                        else nearest = min(nearest, (unsigned)d2);
+                    }
+                    if (VARIANT == TL_VARIANT_COMPACT) {
+                        const bool is_other = is_agent && e != self_e;  // map.py:198
+                        const bool norm = o.normalize_counts != 0;
+                        if (is_other) {
+                            if (norm) st[W2 + tile] = 1.0f;
+                            else atomicAdd(st + W2 + tile, 1.0f);
+                        }
+                        if (is_obj) {
+                            if (norm) st[2 * W2 + tile] = 1.0f;
+                            else atomicAdd(st + 2 * W2 + tile, 1.0f);
+                            const int ct = (int)TL_ENT_CTYPE(w);
+                            if (ct > 0 && ct <= o.n_ctypes) {  // map.py:214-229
+                                if (norm) st[(3 + ct) * W2 + tile] = 1.0f;
+                                else atomicAdd(st + (3 + ct) * W2 + tile, 1.0f);
+                            }
+                        }
+                        if (is_res) st[3 * W2 + tile] = 1.0f;
+                        if (is_other || is_obj || is_res) st[(4 + o.n_ctypes) * W2 + tile] = 0.0f;
+                    } else {
+                        if (is_agent) st[W2 + tile] = 1.0f;  // includes the observer (map.py:109-110)
+                        if (is_obj) st[2 * W2 + tile] = 1.0f;
+                        if (is_res) st[3 * W2 + tile] = 1.0f;
+                    }
+                }
+                n_ag = __reduce_add_sync(FULL, n_ag);
+                n_obj = __reduce_add_sync(FULL, n_obj);
+                n_res = __reduce_add_sync(FULL, n_res);
+                centre_has = __reduce_max_sync(FULL, centre_has);
+                nearest = __reduce_min_sync(FULL, nearest);
+                const int others_sum = n_ag - centre_has;  // self excluded on the centre tile only
+                const int nearest_d2 = nearest == 0xffffffffu ? 0 : (int)nearest;
+                if (lane == 0) {  // _encode_local_summary, features.py:289-330 via host LUTs
+                    float* frow = feat_s0 + i * F;
+                    frow[TL_FEAT_AGENT_RATIO] = o.agent_ratio_lut[min(others_sum, W2 - 1)];
+                    frow[TL_FEAT_OBJECT_RATIO] = o.tile_ratio_lut[min(n_obj, W2)];
+                    frow[TL_FEAT_RESERVED_RATIO] = o.tile_ratio_lut[min(n_res, W2)];
+                    frow[TL_FEAT_NEAREST] = o.nearest_lut[nearest_d2];
+                }
+                if (p.oo.summary) {
+                    const int fil = __shfl_sync(FULL, filled, i), src = __shfl_sync(FULL, source, i);
+                    if (lane < TL_N_SUMMARY) {
+                        int v = 0;
+                        if (lane == TL_SUM_OTHER_AGENTS) v = others_sum;
+                        else if (lane == TL_SUM_OBJECTS) v = n_obj;
+                        else if (lane == TL_SUM_RESERVED) v = n_res;
+                        else if (lane == TL_SUM_NEAREST_D2) v = nearest_d2;
+                        else if (lane == TL_SUM_FILLED_SLOTS) v = fil;
+                        else if (lane == TL_SUM_RELATION_SOURCE) v = src;
+                        p.oo.summary[(size_t)it * p.oo.summary_tick_stride + (size_t)a_i * TL_N_SUMMARY + lane] = v;
+                    }
+                }
+                __syncwarp();
+                {  // 16-byte vectorised coalesced stores of the map tile
+                    const int head = (4 - map_mis) & 3;
+                    if (lane < head) mrow_g[lane] = st[lane];
+                    const int nvec = (map_elems - head) >> 2;
+                    float4* g4 = reinterpret_cast<float4*>(mrow_g + head);
+                    const float4* s4 = reinterpret_cast<const float4*>(st + head);
+                    for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
+                    const int tail0 = head + (nvec << 2);
+                    if (lane < map_elems - tail0) mrow_g[tail0 + lane] = st[tail0 + lane];
+                }
+            }
+            __syncwarp();
+            {  // feature rows of the whole pass: one coalesced 16-byte sweep
+                const int total = c_n * F;
+                const int head = min((4 - feat_mis) & 3, total);
+                if (lane < head) feat_g0[lane] = feat_s0[lane];
+                const int nvec = (total - head) >> 2;
+                float4* g4 = reinterpret_cast<float4*>(feat_g0 + head);
+                const float4* s4 = reinterpret_cast<const float4*>(feat_s0 + head);
+                for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
+                const int tail0 = head + (nvec << 2);
+                if (lane < total - tail0) feat_g0[tail0 + lane] = feat_s0[tail0 + lane];
+            }
+            __syncwarp();  // staging rows are reused by the next pass
+        }
+
+        if (do_kpi) {
+            __syncwarp();
+            if (lane < n_towns) {
+                const KpiAcc k = s_kpi[lane];
+                float* dst = p.ro.kpi + (size_t)it * p.ro.kpi_tick_stride + (size_t)(t0 + lane) * TL_N_KPI;
+                const double n = (double)k.count;
+                dst[TL_KPI_REWARD_SUM] = (float)k.rsum;
+                dst[TL_KPI_REWARD_SUMSQ] = (float)k.rsq;
+                dst[TL_KPI_HUNGER_MIN] = k.count ? (float)k.hmin : 0.0f;
+                dst[TL_KPI_HUNGER_MEAN] = k.count ? (float)(k.hsum / n) : 0.0f;
+                dst[TL_KPI_STARVING] = (float)k.starving;
+                dst[TL_KPI_TERMINATED] = (float)k.term;
+                dst[TL_KPI_LATENESS_MEAN] = k.count ? (float)(k.late / n) : 0.0f;
+                dst[TL_KPI_WALLET_MEAN] = k.count ? (float)(k.wallet / n) : 0.0f;
+            }
+            __syncwarp();
+        }
+    }
+}

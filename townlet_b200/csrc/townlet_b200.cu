@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -36,7 +37,8 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 32;          // agents per phase-A pass
-constexpr int kMaxTownsPerCta = 8;  // towns sharing one CTA
+constexpr int kMaxTownsPerCta = 8;  // towns sharing one CTA (grid form)
+constexpr int kMaxTownsPerWarp = 16;  // towns sharing one warp (entity form)
 constexpr int kMaxSocialLen = TL_MAX_SOCIAL_SLOTS * (32 + 3) + 4;
 
 thread_local char g_error[512] = "";
@@ -61,8 +63,10 @@ struct KParams {
     int32_t off_ctype;     // uint16 [towns_per_cta][grid_tiles] (4 x 4-bit counters) or -1
     int32_t off_feat;      // float [kChunk * feat_stride + 4]
     int32_t off_map;       // float [kWarps][map_stride]
-    int32_t off_meta;      // ChunkMeta[kChunk]
+    int32_t off_meta;      // ChunkMeta[kChunk] (grid form) / KpiAcc[towns_per_cta] (entity form)
     int32_t smem_bytes;
+    int32_t chunk;         // entity form: agents per phase-A pass (<= 32)
+    int32_t mode;          // 0 entity-list form, 1 dense shared-memory grid form
 };
 
 struct ChunkMeta {
@@ -806,6 +810,8 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
     }
 }
 
+#include "tick_ent.cuh"
+
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
@@ -848,7 +854,7 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
             return set_error("embed_dim exceeds the stored embedding words"), TL_ERR_ARG;
         if (obs->n_features < TL_N_BASE_FEATURES) return set_error("n_features too small"), TL_ERR_ARG;
         if (!obs->time_lut || !obs->progress_lut || !obs->slot_lut || !obs->agent_ratio_lut || !obs->tile_ratio_lut ||
-            !obs->nearest_lut || (obs->variant == TL_VARIANT_FULL && !obs->path_lut))
+            !obs->nearest_lut || !obs->embed_lut || (obs->variant == TL_VARIANT_FULL && !obs->path_lut))
             return set_error("a look-up table pointer is NULL"), TL_ERR_ARG;
         if (obs->ticks_per_day < 1 || obs->max_slots < 1) return set_error("ticks_per_day / max_slots < 1"), TL_ERR_ARG;
     }
@@ -888,47 +894,92 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
                  "cudaDeviceGetAttribute"))
         return TL_ERR_CUDA;
 
-    // towns per CTA: aim at one full phase-A warp (32 agents) per CTA
     const int avg_agents = b->n_towns > 0 ? (b->n_agents + b->n_towns - 1) / b->n_towns : 1;
-    int tpc = towns_per_cta_override > 0 ? towns_per_cta_override : kChunk / (avg_agents > 0 ? avg_agents : 1);
-    if (tpc < 1) tpc = 1;
-    if (tpc > kMaxTownsPerCta) tpc = kMaxTownsPerCta;
-    kp.grid_tiles = b->grid_w * b->grid_h;
+    const int avg_entities = b->n_towns > 0 ? (b->n_entities + b->n_towns - 1) / b->n_towns : 1;
     const int map_elems = do_obs ? kp.obs.n_channels * kp.obs.window * kp.obs.window : 0;
     kp.feat_stride = kp.obs.n_features;
     kp.map_stride = round_up(map_elems + 4, 4);
-    for (;;) {
+    kp.grid_tiles = b->grid_w * b->grid_h;
+    auto env_int = [](const char* name, int dflt) {
+        const char* v = getenv(name);
+        return v && *v ? atoi(v) : dflt;
+    };
+    // The entity-list form costs O(entities of the town) per agent, the dense grid form O(window);
+    // the former wins until a town holds several hundred entities (DESIGN.md "Kernel forms").
+    const char* mode_env = getenv("TL_MODE");
+    kp.mode = avg_entities > 384 ? 1 : 0;
+    if (mode_env && !strcmp(mode_env, "grid")) kp.mode = 1;
+    if (mode_env && !strcmp(mode_env, "ent")) kp.mode = 0;
+
+    int grid = 0, threads = kThreads;
+    if (kp.mode == 0) {
+        threads = 32;
+        int chunk = env_int("TL_CHUNK", 32);
+        if (chunk < 1) chunk = 1;
+        if (chunk > 32) chunk = 32;
+        kp.chunk = chunk;
+        int tpc = towns_per_cta_override > 0 ? towns_per_cta_override : env_int("TL_TPC", chunk / (avg_agents > 0 ? avg_agents : 1));
+        if (tpc < 1) tpc = 1;
+        if (tpc > kMaxTownsPerWarp) tpc = kMaxTownsPerWarp;
         int off = 0;
-        kp.off_grid = off;
-        off += do_obs ? round_up(tpc * kp.grid_tiles * 2, 16) : 0;
+        kp.off_grid = 0;
         kp.off_ctype = -1;
-        if (do_obs && kp.obs.variant == TL_VARIANT_COMPACT && kp.obs.n_ctypes > 0) {
-            kp.off_ctype = off;
-            off += round_up(tpc * kp.grid_tiles * 2, 16);
-        }
         kp.off_feat = off;
-        off += do_obs ? round_up((kChunk * kp.feat_stride + 4) * 4, 16) : 16;
+        off += do_obs ? round_up((chunk * kp.feat_stride + 4) * 4, 16) : 16;
         kp.off_map = off;
-        off += do_obs ? kWarps * kp.map_stride * 4 : 0;
+        off += do_obs ? 2 * kp.map_stride * 4 : 0;
         kp.off_meta = off;
-        off += (int)sizeof(ChunkMeta) * kChunk;
+        off += round_up((int)sizeof(KpiAcc) * tpc, 16);
         kp.smem_bytes = off;
-        if (off <= max_smem || tpc == 1) break;
-        --tpc;
+        if (off > max_smem) return set_error("observation staging does not fit in shared memory"), TL_ERR_UNSUPPORTED;
+        kp.towns_per_cta = tpc;
+        grid = (b->n_towns + tpc - 1) / tpc;
+    } else {
+        // towns per CTA: aim at one full phase-A warp (32 agents) per CTA
+        int tpc = towns_per_cta_override > 0 ? towns_per_cta_override : kChunk / (avg_agents > 0 ? avg_agents : 1);
+        if (tpc < 1) tpc = 1;
+        if (tpc > kMaxTownsPerCta) tpc = kMaxTownsPerCta;
+        for (;;) {
+            int off = 0;
+            kp.off_grid = off;
+            off += do_obs ? round_up(tpc * kp.grid_tiles * 2, 16) : 0;
+            kp.off_ctype = -1;
+            if (do_obs && kp.obs.variant == TL_VARIANT_COMPACT && kp.obs.n_ctypes > 0) {
+                kp.off_ctype = off;
+                off += round_up(tpc * kp.grid_tiles * 2, 16);
+            }
+            kp.off_feat = off;
+            off += do_obs ? round_up((kChunk * kp.feat_stride + 4) * 4, 16) : 16;
+            kp.off_map = off;
+            off += do_obs ? kWarps * kp.map_stride * 4 : 0;
+            kp.off_meta = off;
+            off += (int)sizeof(ChunkMeta) * kChunk;
+            kp.smem_bytes = off;
+            if (off <= max_smem || tpc == 1) break;
+            --tpc;
+        }
+        if (kp.smem_bytes > max_smem) return set_error("town grid does not fit in shared memory"), TL_ERR_UNSUPPORTED;
+        kp.towns_per_cta = tpc;
+        grid = (b->n_towns + tpc - 1) / tpc;
     }
-    if (kp.smem_bytes > max_smem) return set_error("town grid does not fit in shared memory"), TL_ERR_UNSUPPORTED;
-    kp.towns_per_cta = tpc;
-    const int grid = (b->n_towns + tpc - 1) / tpc;
 
     auto run = [&](auto kernel) -> int {
         if (!cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem_bytes),
                      "cudaFuncSetAttribute"))
             return TL_ERR_CUDA;
-        kernel<<<grid, kThreads, kp.smem_bytes, stream>>>(kp);
+        kernel<<<grid, threads, kp.smem_bytes, stream>>>(kp);
         if (!cuda_ok(cudaGetLastError(), "kernel launch")) return TL_ERR_CUDA;
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return TL_OK;
     };
+    if (kp.mode == 0) {
+        switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
+            case TL_VARIANT_HYBRID: return run(tick_kernel_ent<TL_VARIANT_HYBRID>);
+            case TL_VARIANT_FULL: return run(tick_kernel_ent<TL_VARIANT_FULL>);
+            case TL_VARIANT_COMPACT: return run(tick_kernel_ent<TL_VARIANT_COMPACT>);
+            default: return set_error("unknown variant"), TL_ERR_ARG;
+        }
+    }
     switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
         case TL_VARIANT_HYBRID: return run(tick_kernel<TL_VARIANT_HYBRID>);
         case TL_VARIANT_FULL: return run(tick_kernel<TL_VARIANT_FULL>);
@@ -1108,6 +1159,7 @@ int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, 
         add(obs->tile_ratio_lut, (void**)&dobs.tile_ratio_lut, (W2 + 1) * 4, false);
         add(obs->nearest_lut, (void**)&dobs.nearest_lut, (2 * R * R + 1) * 4, false);
         add(obs->path_lut, (void**)&dobs.path_lut, 2 * W2 * 4, false);
+        add(obs->embed_lut, (void**)&dobs.embed_lut, 256 * 4, false);
     }
 
     // If the batch fields sit in one host arena, move them with a single copy.

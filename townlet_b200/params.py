@@ -300,6 +300,8 @@ class ObsSpec:
             "tile_ratio_lut": tile_ratio,
             "nearest_lut": nearest,
             "path_lut": path,
+            # values.astype(np.float32) / 255.0 stays float32 (social.py:238-239)
+            "embed_lut": (np.arange(256, dtype=np.uint8).astype(np.float32) / 255.0).astype(np.float32),
         }
 
     def struct(self, lut_ptrs: dict[str, int] | None = None) -> capi.TlObsParams:
