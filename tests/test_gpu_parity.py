@@ -88,7 +88,7 @@ SYNTH_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["ent", "grid", "ent-chunk8"])
+@pytest.mark.parametrize("mode", ["ent", "grid", "ent-chunk8", "ent-generic"])
 @pytest.mark.parametrize("case", SYNTH_CASES, ids=[c[0] for c in SYNTH_CASES])
 def test_cuda_matches_oracle_on_synthetic_towns(case, mode, monkeypatch) -> None:
     from oracle.oracle import oracle_tick
@@ -96,6 +96,8 @@ def test_cuda_matches_oracle_on_synthetic_towns(case, mode, monkeypatch) -> None
     monkeypatch.setenv("TL_MODE", mode.split("-")[0])
     if mode == "ent-chunk8":
         monkeypatch.setenv("TL_CHUNK", "8")
+    if mode == "ent-generic":
+        monkeypatch.setenv("TL_GENERIC", "1")  # runtime-window kernels instead of the unrolled specialisations
 
     _, variant, grid, agents, towns, ticks, extra = case
     obs = ObsSpec(variant=variant, **extra)

@@ -22,8 +22,10 @@
 // HBM write roofline.  The dense shared-memory grid form stays available
 // (tick_kernel) for towns with hundreds of entities.
 
-template <int VARIANT>
-__global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KParams p) {
+// WT > 0 fixes the window (and n_ctypes = 0) at compile time so the short per-agent
+// loops unroll; WT = 0 is the generic form for any window / object channels.
+template <int VARIANT, int WT>
+__global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);
     float* s_map = reinterpret_cast<float*>(smem + p.off_map);
@@ -45,11 +47,17 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
     const bool do_kpi = do_state && p.ro.kpi != nullptr;
 
     const TlObsParams& o = p.obs;
-    const int W = o.window;
+    constexpr bool kStatic = WT > 0;
+    constexpr int kChannels = VARIANT == TL_VARIANT_HYBRID ? 4 : (VARIANT == TL_VARIANT_FULL ? 6 : 5);
+    constexpr int kMapElems = kStatic ? kChannels * WT * WT : 4;
+    constexpr int kMapStride = (kMapElems + 4 + 3) / 4 * 4;
+    const int W = kStatic ? WT : o.window;
     const int R = W >> 1;
     const int W2 = W * W;
     const int F = o.n_features;
-    const int map_elems = o.n_channels * W2;
+    const int n_ct = kStatic ? 0 : o.n_ctypes;
+    const int map_elems = kStatic ? kMapElems : o.n_channels * W2;
+    const int map_stride = kStatic ? kMapStride : p.map_stride;
     const int chunk_cap = p.chunk;  // agents per phase-A pass (<= 32)
 
     // lane s holds the offsets of town t0 + s (s <= n_towns)
@@ -75,6 +83,18 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
             z.starving = z.term = z.count = 0;
             s_kpi[lane] = z;
         }
+        if (VARIANT == TL_VARIANT_FULL && kStatic && do_obs) {
+            // path_dx / path_dy are agent independent (map.py:115-125): keep them resident in both
+            // staging buffers, at the misalignment each buffer has during this tick
+            const float* m0 = p.oo.map + (size_t)it * p.oo.map_tick_stride;
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+                const int first = a_begin + ((a_begin & 1) == par ? 0 : 1);  // first agent with this parity
+                const int mis = (int)((reinterpret_cast<uintptr_t>(m0 + (size_t)first * map_elems) >> 2) & 3);
+                float* dst = s_map + par * map_stride + mis + 4 * W2;
+                for (int k = lane; k < 2 * W2; k += 32) dst[k] = __ldg(o.path_lut + k);
+            }
+        }
         __syncwarp();
 
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
@@ -99,14 +119,59 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
             uint32_t fl = 0;
             bool terminated = false;
             double reward_total = 0.0;
-            int cx = 0, cy = 0, filled = 0, source = 0;
+            int cx = 0, cy = 0, filled = 0, source = 0, kpi_late = 0;
+            double kpi_wallet = 0.0;
             if (active) {
+                // ---- every global input of the agent is loaded up front so the loads overlap
                 double need[3];
                 need[0] = p.b.needs[a];
                 need[1] = p.b.needs[(size_t)N + a];
                 need[2] = p.b.needs[2 * (size_t)N + a];
                 fl = p.b.flags[a];
                 int episode_tick = p.b.episode_tick[a];
+                RewardIn rin;
+                if (do_reward) rin = load_reward_in(p, a);
+                const double wallet = __ldg(p.b.wallet + a);
+                const int lateness = __ldg(p.b.lateness + a);
+                kpi_wallet = wallet;
+                kpi_late = lateness;
+                double attendance = 0.0, wages_withheld = 0.0;
+                int duration = 0, slot_idx = 0, n_riv = 0, n_t = 0;
+                float last_hash = 0.0f, pers[3] = {0.0f, 0.0f, 0.0f};
+                int32_t pw = 0;
+                const int K = p.b.max_edges;
+                const int EW = p.b.embed_words;
+                const size_t rbase = (size_t)a * K;
+                double r_trust[TL_MAX_EDGES], r_fam[TL_MAX_EDGES], r_riv[TL_MAX_EDGES], r_score[TL_MAX_EDGES];
+                uint64_t r_emb[TL_MAX_EDGES];
+                if (do_obs) {
+                    attendance = __ldg(p.b.attendance + a);
+                    wages_withheld = __ldg(p.b.wages_withheld + a);
+                    duration = __ldg(p.b.last_action_duration + a);
+                    slot_idx = __ldg(p.b.slot + a);
+                    last_hash = __ldg(p.b.last_action_hash + a);
+                    pw = __ldg(p.b.pos + a);
+                    n_riv = __ldg(p.b.riv_count + a);
+                    n_t = __ldg(p.b.tie_count + a);
+                    if (o.personality_base >= 0 && p.b.personality) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) pers[k] = __ldg(p.b.personality + (size_t)k * N + a);
+                    }
+#pragma unroll
+                    for (int j = 0; j < TL_MAX_EDGES; ++j) {
+                        r_trust[j] = r_fam[j] = r_riv[j] = r_score[j] = 0.0;
+                        r_emb[j] = 0;
+                        if (j < K) {
+                            r_score[j] = __ldg(p.b.riv_score + rbase + j);
+                            if (o.social_base >= 0) {
+                                r_trust[j] = __ldg(p.b.tie_trust + rbase + j);
+                                r_fam[j] = __ldg(p.b.tie_fam + rbase + j);
+                                r_riv[j] = __ldg(p.b.tie_riv + rbase + j);
+                            }
+                        }
+                    }
+                }
+
                 const unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
                 if (do_decay) {  // world/grid.py:1439-1455
 #pragma unroll
@@ -135,7 +200,9 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
                 }
                 if (do_reward) {
                     RewardResult rr;
-                    reward_agent(p, a, tick, need, fl, terminated, reason, rr);
+                    reward_agent(p.rew, rin, tick, need, fl, terminated, reason, rr);
+                    p.b.term_block_tick[a] = rr.block;
+                    p.b.episode_total[a] = rr.cumulative;
                     reward_total = rr.total;
                     if (p.ro.reward) p.ro.reward[(size_t)it * p.ro.reward_tick_stride + a] = (float)rr.total;
                     if (p.ro.comps) {
@@ -154,50 +221,41 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
                     f[TL_FEAT_NEED_HUNGER] = (float)need[0];
                     f[TL_FEAT_NEED_HYGIENE] = (float)need[1];
                     f[TL_FEAT_NEED_ENERGY] = (float)need[2];
-                    f[TL_FEAT_WALLET] = (float)p.b.wallet[a];
-                    f[TL_FEAT_LATENESS] = (float)p.b.lateness[a];
+                    f[TL_FEAT_WALLET] = (float)wallet;
+                    f[TL_FEAT_LATENESS] = (float)lateness;
                     f[TL_FEAT_ON_SHIFT] = (fl & TL_F_ON_SHIFT) ? 1.0f : 0.0f;
                     int m = tick % o.ticks_per_day;
                     if (m < 0) m += o.ticks_per_day;
-                    const float2 sc = *reinterpret_cast<const float2*>(o.time_lut + 2 * m);
+                    const float2 sc = __ldg(reinterpret_cast<const float2*>(o.time_lut + 2 * m));
                     f[TL_FEAT_TIME_SIN] = sc.x;
                     f[TL_FEAT_TIME_COS] = sc.y;
-                    f[TL_FEAT_ATTENDANCE] = (float)p.b.attendance[a];
-                    f[TL_FEAT_WAGES_WITHHELD] = (float)p.b.wages_withheld[a];
+                    f[TL_FEAT_ATTENDANCE] = (float)attendance;
+                    f[TL_FEAT_WAGES_WITHHELD] = (float)wages_withheld;
                     unsigned st = (fl & TL_F_SHIFT_MASK) >> TL_F_SHIFT_SHIFT;
                     if (st > 4) st = 0;
 #pragma unroll
                     for (unsigned k = 0; k < 5; ++k) f[TL_FEAT_SHIFT_PRE + k] = (k == st) ? 1.0f : 0.0f;
-                    const int slot_idx = p.b.slot[a];
                     f[TL_FEAT_SLOT_NORM] = (slot_idx >= 0 && slot_idx < o.max_slots)
-                                               ? o.slot_lut[slot_idx]
+                                               ? __ldg(o.slot_lut + slot_idx)
                                                : (float)((double)slot_idx / (double)o.max_slots);
                     f[TL_FEAT_CTX_RESET] = ((fl & TL_F_CTX_RESET) || terminated) ? 1.0f : 0.0f;  // service.py:224-229
                     f[TL_FEAT_EPISODE_PROGRESS] =
-                        episode_tick <= 0 ? 0.0f : o.progress_lut[min(episode_tick, o.ticks_per_day)];
-                    const int K = p.b.max_edges;
-                    const size_t rbase = (size_t)a * K;
-                    const int n_riv = p.b.riv_count[a];
+                        episode_tick <= 0 ? 0.0f : __ldg(o.progress_lut + min(episode_tick, o.ticks_per_day));
                     {  // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
                         const int nr = min(n_riv, o.rivalry_max_edges);
-                        double mx = 0.0;
                         int avoid = 0;
-                        for (int j = 0; j < nr; ++j) {
-                            const double v = p.b.riv_score[rbase + j];
-                            if (j == 0) mx = v;
-                            avoid += (v >= o.avoid_threshold) ? 1 : 0;
-                        }
-                        f[TL_FEAT_RIVALRY_MAX] = (float)mx;
+#pragma unroll
+                        for (int j = 0; j < TL_MAX_EDGES; ++j) avoid += (j < nr && r_score[j] >= o.avoid_threshold) ? 1 : 0;
+                        f[TL_FEAT_RIVALRY_MAX] = (float)(nr > 0 ? r_score[0] : 0.0);
                         f[TL_FEAT_RIVALRY_AVOID] = (float)avoid;
                     }
-                    f[TL_FEAT_LAST_HASH] = p.b.last_action_hash[a];
+                    f[TL_FEAT_LAST_HASH] = last_hash;
                     f[TL_FEAT_LAST_SUCCESS] = (fl & TL_F_LAST_SUCCESS) ? 1.0f : 0.0f;
-                    f[TL_FEAT_LAST_DURATION] = (float)p.b.last_action_duration[a];
+                    f[TL_FEAT_LAST_DURATION] = (float)duration;
                     f[TL_FEAT_RESERVATION] = (fl & TL_F_RESERVATION) ? 1.0f : 0.0f;
                     f[TL_FEAT_IN_QUEUE] = (fl & TL_F_IN_QUEUE) ? 1.0f : 0.0f;
                     // nearest object per landmark type: first minimum of the squared
                     // distance in insertion order (world/observe.py:109-147)
-                    const int32_t pw = p.b.pos[a];
                     cx = pos_x(pw);
                     cy = pos_y(pw);
                     int best_d2[5] = {-1, -1, -1, -1, -1};
@@ -262,10 +320,8 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
                         }
                     }
                     if (o.personality_base >= 0) {  // features.py:359-380
-                        const bool has = p.b.personality != nullptr;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                            f[o.personality_base + k] = has ? p.b.personality[(size_t)k * N + a] : 0.0f;
+                        for (int k = 0; k < 3; ++k) f[o.personality_base + k] = pers[k];
                     }
 
                     // ---- social snippet (encoders/social.py:27-254) -------------
@@ -275,83 +331,77 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
                         const int social_len = total_slots * slot_dim + (o.include_aggregates ? 4 : 0);
                         float* srow = f + o.social_base;
                         for (int k = 0; k < social_len; ++k) srow[k] = 0.0f;
-                        const int EW = p.b.embed_words;
-                        const int n_t = p.b.tie_count[a];
                         const bool from_ties = n_t > 0;  // _resolve_relationships, social.py:165-209
                         const int n_rel = from_ties ? n_t : min(n_riv, o.top_rivals);
                         source = from_ties ? 1 : (n_rel > 0 ? 2 : 0);
-                        const double* kt = p.b.tie_trust + rbase;
-                        const double* kf = p.b.tie_fam + rbase;
-                        const double* kr = from_ties ? p.b.tie_riv + rbase : p.b.riv_score + rbase;
                         const uint64_t* ke = (from_ties ? p.b.tie_embed : p.b.riv_embed) + rbase * EW;
-                        // sorted(..., reverse=True)[:k] is stable: repeated FIRST argmax (social.py:137-156)
-                        unsigned chosen = 0, sel = 0;
+#pragma unroll
+                        for (int j = 0; j < TL_MAX_EDGES; ++j) {
+                            if (j < n_rel) r_emb[j] = __ldg(ke + (size_t)j * EW);
+                            if (!from_ties) {  // rivalry fallback: trust = familiarity = 0 (social.py:197-206)
+                                r_trust[j] = 0.0;
+                                r_fam[j] = 0.0;
+                                r_riv[j] = r_score[j];
+                            }
+                        }
+                        // sorted(..., reverse=True)[:k] is stable: repeated FIRST argmax (social.py:137-156).
+                        // slot_of packs, per relation j, its destination slot in 4 bits (15 = none).
+                        unsigned chosen = 0, slot_of = 0xffffffffu;
                         const int n_friends = min(n_rel, o.top_friends);
-                        for (int s = 0; s < n_friends; ++s) {
-                            int best = -1;
-                            double bk = 0.0;
-                            for (int j = 0; j < n_rel; ++j) {
-                                if ((chosen >> j) & 1u) continue;
-                                const double key = from_ties ? kt[j] + kf[j] : 0.0;
-                                if (best < 0 || key > bk) {
-                                    best = j;
-                                    bk = key;
-                                }
-                            }
-                            chosen |= 1u << best;
-                            sel |= (unsigned)best << (4 * s);
-                        }
                         const int n_rivals = min(o.top_rivals, n_rel - n_friends);
-                        for (int s = 0; s < n_rivals; ++s) {
+                        filled = n_friends + n_rivals;
+                        for (int s = 0; s < filled; ++s) {
+                            const bool friend_pass = s < n_friends;
                             int best = -1;
                             double bk = 0.0;
-                            for (int j = 0; j < n_rel; ++j) {
-                                if ((chosen >> j) & 1u) continue;
-                                const double key = kr[j];
-                                if (best < 0 || key > bk) {
+#pragma unroll
+                            for (int j = 0; j < TL_MAX_EDGES; ++j) {
+                                const double key = friend_pass ? r_trust[j] + r_fam[j] : r_riv[j];
+                                const bool free_j = j < n_rel && !((chosen >> j) & 1u);
+                                if (free_j && (best < 0 || key > bk)) {
                                     best = j;
                                     bk = key;
                                 }
                             }
                             chosen |= 1u << best;
-                            sel |= (unsigned)best << (4 * (n_friends + s));
+                            slot_of = (slot_of & ~(15u << (4 * best))) | ((unsigned)s << (4 * best));
                         }
-                        filled = n_friends + n_rivals;
-                        double tsum = 0.0, rsum = 0.0, tmax = 0.0, rmax = 0.0;
-                        for (int s = 0; s < filled; ++s) {
-                            const int j = (sel >> (4 * s)) & 15;
-                            const double trust = from_ties ? kt[j] : 0.0;
-                            const double fam = from_ties ? kf[j] : 0.0;
-                            const double riv = kr[j];
-                            float* dst = srow + s * slot_dim;
-                            for (int d = 0; d < o.embed_dim; ++d) {  // social.py:236-242
-                                const unsigned byte = (unsigned)(ke[(size_t)j * EW + (d >> 3)] >> (8 * (d & 7))) & 255u;
-                                dst[d] = __ldg(o.embed_lut + byte);
+                        double tv[TL_MAX_SOCIAL_SLOTS], rv[TL_MAX_SOCIAL_SLOTS];
+#pragma unroll
+                        for (int s = 0; s < TL_MAX_SOCIAL_SLOTS; ++s) tv[s] = rv[s] = 0.0;
+#pragma unroll
+                        for (int j = 0; j < TL_MAX_EDGES; ++j) {
+                            const unsigned s = (slot_of >> (4 * j)) & 15u;
+                            if (j < n_rel && s != 15u) {
+                                float* dst = srow + s * slot_dim;
+                                for (int d = 0; d < o.embed_dim; ++d) {  // social.py:236-242
+                                    const uint64_t word = (d < 8) ? r_emb[j] : __ldg(ke + (size_t)j * EW + (d >> 3));
+                                    const unsigned byte = (unsigned)(word >> (8 * (d & 7))) & 255u;
+                                    dst[d] = __ldg(o.embed_lut + byte);
+                                }
+                                dst[o.embed_dim + 0] = (float)r_trust[j];
+                                dst[o.embed_dim + 1] = (float)r_fam[j];
+                                dst[o.embed_dim + 2] = (float)r_riv[j];
+#pragma unroll
+                                for (int q = 0; q < TL_MAX_SOCIAL_SLOTS; ++q)
+                                    if (q == (int)s) {
+                                        tv[q] = r_trust[j];
+                                        rv[q] = r_riv[j];
+                                    }
                             }
-                            dst[o.embed_dim + 0] = (float)trust;
-                            dst[o.embed_dim + 1] = (float)fam;
-                            dst[o.embed_dim + 2] = (float)riv;
-                            tsum += trust;  // numpy sums left to right below 8 values
-                            rsum += riv;
-                            tmax = s == 0 ? trust : fmax(tmax, trust);
-                            rmax = s == 0 ? riv : fmax(rmax, riv);
                         }
                         if (o.include_aggregates && filled > 0) {  // social.py:90-105, 245-254
-                            if (filled == 8) {  // numpy's unrolled pairwise block
-                                double tv[8], rv[8];
+                            double tmax = tv[0], rmax = rv[0];
 #pragma unroll
-                                for (int s = 0; s < 8; ++s) {
-                                    const int j = (sel >> (4 * s)) & 15;
-                                    tv[s] = from_ties ? kt[j] : 0.0;
-                                    rv[s] = kr[j];
+                            for (int s = 1; s < TL_MAX_SOCIAL_SLOTS; ++s)
+                                if (s < filled) {
+                                    tmax = fmax(tmax, tv[s]);
+                                    rmax = fmax(rmax, rv[s]);
                                 }
-                                tsum = ((tv[0] + tv[1]) + (tv[2] + tv[3])) + ((tv[4] + tv[5]) + (tv[6] + tv[7]));
-                                rsum = ((rv[0] + rv[1]) + (rv[2] + rv[3])) + ((rv[4] + rv[5]) + (rv[6] + rv[7]));
-                            }
                             float* agg = srow + total_slots * slot_dim;
-                            agg[0] = (float)(tsum / (double)filled);
+                            agg[0] = (float)(np_sum_le8(tv, filled) / (double)filled);
                             agg[1] = (float)tmax;
-                            agg[2] = (float)(rsum / (double)filled);
+                            agg[2] = (float)(np_sum_le8(rv, filled) / (double)filled);
                             agg[3] = (float)rmax;
                         }
                     }
@@ -362,8 +412,8 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
             if (do_kpi) {
                 const int seg = active ? slot : -1 - lane;  // inactive lanes are their own segment
                 double v_r = reward_total, v_q = reward_total * reward_total, v_h = active ? need0 : 0.0;
-                double v_m = active ? need0 : 1e300, v_w = active ? p.b.wallet[a] : 0.0;
-                int v_l = active ? p.b.lateness[a] : 0;
+                double v_m = active ? need0 : 1e300, v_w = kpi_wallet;
+                int v_l = kpi_late;
                 // starving | terminated | count packed in 10-bit fields
                 int v_c = active ? ((need0 <= p.rew.starvation_threshold ? 1 : 0) | (terminated ? 1 << 10 : 0) | (1 << 20)) : 0;
 #pragma unroll
@@ -401,27 +451,57 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
             __syncwarp();
 
             // =================== phase B: the warp serves one agent at a time =====
-            const int fill_vecs = p.map_stride >> 2;
-            for (int i = 0; i < c_n; ++i) {
+            // Lane i keeps the integer summary of agent i; the look-ups run thread-per-agent afterwards.
+            int my_others = 0, my_objs = 0, my_res = 0, my_d2 = 0;
+            float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)c_begin * map_elems;
+            const int centre_tile = R * W + R;
+            for (int i = 0; i < c_n; ++i, mrow_g += map_elems) {
                 const int a_i = c_begin + i;
                 const int cxi = __shfl_sync(FULL, cx, i), cyi = __shfl_sync(FULL, cy, i);
                 const int eb = __shfl_sync(FULL, town_ebeg, i), ee = __shfl_sync(FULL, town_eend, i);
                 const int self_e = eb + (a_i - __shfl_sync(FULL, town_abeg, i));
-                float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)a_i * map_elems;
                 const int map_mis = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
-                float* buf = s_map + (i & 1) * p.map_stride;  // double buffered: no barrier after the stores
+                // double buffered by agent parity (a fixed misalignment per buffer for the full variant)
+                float* buf = s_map + (a_i & 1) * map_stride;
                 float* st = buf + map_mis;
-                {
+                if (VARIANT == TL_VARIANT_FULL && kStatic) {
+                    // channels 0-3 only (8-byte aligned): the path channels stay resident in the buffer
+                    float2* b2 = reinterpret_cast<float2*>(st);
+                    const float2 z2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int k = 0; k < (2 * W2 + 31) / 32; ++k) {
+                        const int v = lane + 32 * k;
+                        if (v < 2 * W2) b2[v] = z2;
+                    }
+                } else {
                     float4* b4 = reinterpret_cast<float4*>(buf);
                     const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    for (int v = lane; v < fill_vecs; v += 32) b4[v] = z;
+                    if (kStatic) {
+#pragma unroll
+                        for (int k = 0; k < (kMapStride / 4 + 31) / 32; ++k) {
+                            const int v = lane + 32 * k;
+                            if (v < kMapStride / 4) b4[v] = z;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int v = lane; v < (map_stride >> 2); v += 32) b4[v] = z;
+                    }
                 }
                 __syncwarp();
-                const int centre_tile = R * W + R;
                 if (VARIANT == TL_VARIANT_COMPACT) {
-                    float* walk = st + (4 + o.n_ctypes) * W2;  // map.py:231-241: empty tiles are walkable
-                    for (int k = lane; k < W2; k += 32) walk[k] = (k == centre_tile) ? 0.0f : 1.0f;
-                } else if (VARIANT == TL_VARIANT_FULL) {
+                    float* walk = st + (4 + n_ct) * W2;  // map.py:231-241: empty tiles are walkable
+                    if (kStatic) {
+#pragma unroll
+                        for (int k = 0; k < (W2 + 31) / 32; ++k) {
+                            const int v = lane + 32 * k;
+                            if (v < W2) walk[v] = (v == centre_tile) ? 0.0f : 1.0f;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int k = lane; k < W2; k += 32) walk[k] = (k == centre_tile) ? 0.0f : 1.0f;
+                    }
+                } else if (VARIANT == TL_VARIANT_FULL && !kStatic) {
+#pragma unroll 1
                     for (int k = lane; k < 2 * W2; k += 32) st[4 * W2 + k] = __ldg(o.path_lut + k);  // map.py:115-125
                 }
                 if (lane == 0) st[centre_tile] = 1.0f;  // map.py:69 / :185-186
@@ -429,6 +509,7 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
 
                 int n_ag = 0, n_obj = 0, n_res = 0, centre_has = 0;
                 unsigned nearest = 0xffffffffu;
+#pragma unroll 1
                 for (int e0 = eb; e0 < ee; e0 += 32) {
                     const int e = e0 + lane;
                     const bool valid = e < ee;
@@ -460,13 +541,13 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
                             if (norm) st[2 * W2 + tile] = 1.0f;
                             else atomicAdd(st + 2 * W2 + tile, 1.0f);
                             const int ct = (int)TL_ENT_CTYPE(w);
-                            if (ct > 0 && ct <= o.n_ctypes) {  // map.py:214-229
+                            if (ct > 0 && ct <= n_ct) {  // map.py:214-229
                                 if (norm) st[(3 + ct) * W2 + tile] = 1.0f;
                                 else atomicAdd(st + (3 + ct) * W2 + tile, 1.0f);
                             }
                         }
                         if (is_res) st[3 * W2 + tile] = 1.0f;
-                        if (is_other || is_obj || is_res) st[(4 + o.n_ctypes) * W2 + tile] = 0.0f;
+                        if (is_other || is_obj || is_res) st[(4 + n_ct) * W2 + tile] = 0.0f;
                     } else {
                         if (is_agent) st[W2 + tile] = 1.0f;  // includes the observer (map.py:109-110)
                         if (is_obj) st[2 * W2 + tile] = 1.0f;
@@ -478,38 +559,46 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
                 n_res = __reduce_add_sync(FULL, n_res);
                 centre_has = __reduce_max_sync(FULL, centre_has);
                 nearest = __reduce_min_sync(FULL, nearest);
-                const int others_sum = n_ag - centre_has;  // self excluded on the centre tile only
-                const int nearest_d2 = nearest == 0xffffffffu ? 0 : (int)nearest;
-                if (lane == 0) {  // _encode_local_summary, features.py:289-330 via host LUTs
-                    float* frow = feat_s0 + i * F;
-                    frow[TL_FEAT_AGENT_RATIO] = o.agent_ratio_lut[min(others_sum, W2 - 1)];
-                    frow[TL_FEAT_OBJECT_RATIO] = o.tile_ratio_lut[min(n_obj, W2)];
-                    frow[TL_FEAT_RESERVED_RATIO] = o.tile_ratio_lut[min(n_res, W2)];
-                    frow[TL_FEAT_NEAREST] = o.nearest_lut[nearest_d2];
-                }
-                if (p.oo.summary) {
-                    const int fil = __shfl_sync(FULL, filled, i), src = __shfl_sync(FULL, source, i);
-                    if (lane < TL_N_SUMMARY) {
-                        int v = 0;
-                        if (lane == TL_SUM_OTHER_AGENTS) v = others_sum;
-                        else if (lane == TL_SUM_OBJECTS) v = n_obj;
-                        else if (lane == TL_SUM_RESERVED) v = n_res;
-                        else if (lane == TL_SUM_NEAREST_D2) v = nearest_d2;
-                        else if (lane == TL_SUM_FILLED_SLOTS) v = fil;
-                        else if (lane == TL_SUM_RELATION_SOURCE) v = src;
-                        p.oo.summary[(size_t)it * p.oo.summary_tick_stride + (size_t)a_i * TL_N_SUMMARY + lane] = v;
-                    }
+                if (lane == i) {
+                    my_others = n_ag - centre_has;  // self excluded on the centre tile only
+                    my_objs = n_obj;
+                    my_res = n_res;
+                    my_d2 = nearest == 0xffffffffu ? 0 : (int)nearest;
                 }
                 __syncwarp();
                 {  // 16-byte vectorised coalesced stores of the map tile
                     const int head = (4 - map_mis) & 3;
-                    if (lane < head) mrow_g[lane] = st[lane];
                     const int nvec = (map_elems - head) >> 2;
                     float4* g4 = reinterpret_cast<float4*>(mrow_g + head);
                     const float4* s4 = reinterpret_cast<const float4*>(st + head);
-                    for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
-                    const int tail0 = head + (nvec << 2);
-                    if (lane < map_elems - tail0) mrow_g[tail0 + lane] = st[tail0 + lane];
+                    if (kStatic) {
+#pragma unroll
+                        for (int k = 0; k < (kMapElems / 4 + 31) / 32; ++k) {
+                            const int v = lane + 32 * k;
+                            if (v < nvec) g4[v] = s4[v];
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
+                    }
+                    if (kMapElems % 4 != 0 || !kStatic || map_mis != 0) {
+                        if (lane < head) mrow_g[lane] = st[lane];
+                        const int tail0 = head + (nvec << 2);
+                        if (lane < map_elems - tail0) mrow_g[tail0 + lane] = st[tail0 + lane];
+                    }
+                }
+            }
+            // local summary features, thread-per-agent (features.py:289-330 via the host LUTs)
+            if (active) {
+                float* frow = feat_s0 + lane * F;
+                frow[TL_FEAT_AGENT_RATIO] = __ldg(o.agent_ratio_lut + min(my_others, W2 - 1));
+                frow[TL_FEAT_OBJECT_RATIO] = __ldg(o.tile_ratio_lut + min(my_objs, W2));
+                frow[TL_FEAT_RESERVED_RATIO] = __ldg(o.tile_ratio_lut + min(my_res, W2));
+                frow[TL_FEAT_NEAREST] = __ldg(o.nearest_lut + my_d2);
+                if (p.oo.summary) {
+                    int4* srow = reinterpret_cast<int4*>(p.oo.summary + (size_t)it * p.oo.summary_tick_stride + (size_t)a * TL_N_SUMMARY);
+                    srow[0] = make_int4(my_others, my_objs, my_res, my_d2);
+                    srow[1] = make_int4(filled, source, 0, 0);
                 }
             }
             __syncwarp();
@@ -520,6 +609,7 @@ __global__ void __launch_bounds__(32) tick_kernel_ent(const __grid_constant__ KP
                 const int nvec = (total - head) >> 2;
                 float4* g4 = reinterpret_cast<float4*>(feat_g0 + head);
                 const float4* s4 = reinterpret_cast<const float4*>(feat_s0 + head);
+#pragma unroll 4
                 for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
                 const int tail0 = head + (nvec << 2);
                 if (lane < total - tail0) feat_g0[tail0 + lane] = feat_s0[tail0 + lane];

@@ -114,12 +114,38 @@ __device__ __forceinline__ double np_sum_le8(const double (&a)[TL_MAX_SOCIAL_SLO
 struct RewardResult {
     double total;
     double comps[TL_N_COMPS];
+    double cumulative;  // new RewardEngine._episode_totals entry
+    int32_t block;      // new RewardEngine._termination_block entry
 };
 
-__device__ __forceinline__ void reward_agent(const KParams& p, int a, int tick, const double (&need)[3], uint32_t fl,
-                                             bool terminated, unsigned reason, RewardResult& out) {
-    const TlRewardParams& r = p.rew;
-    const int N = p.b.n_agents;
+// Per-agent reward inputs, loaded up front so the global loads overlap.
+struct RewardIn {
+    double sb, sp, sa;                        // social bonus / penalty / avoidance (engine.py:54-63)
+    double wages_paid, wages_withheld, punctuality;
+    double episode_total;
+    int32_t block;
+};
+
+__device__ __forceinline__ RewardIn load_reward_in(const KParams& p, int a) {
+    RewardIn in;
+    const size_t N = (size_t)p.b.n_agents;
+    in.sb = in.sp = in.sa = 0.0;
+    if (p.b.social_in) {
+        in.sb = __ldg(p.b.social_in + a);
+        in.sp = __ldg(p.b.social_in + N + a);
+        in.sa = __ldg(p.b.social_in + 2 * N + a);
+    }
+    in.wages_paid = __ldg(p.b.wages_paid + a);
+    in.wages_withheld = __ldg(p.b.wages_withheld + a);
+    in.punctuality = __ldg(p.b.punctuality + a);
+    in.episode_total = p.b.episode_total[a];
+    in.block = p.b.term_block_tick[a];
+    return in;
+}
+
+__device__ __forceinline__ void reward_agent(const TlRewardParams& r, const RewardIn& in, int tick,
+                                             const double (&need)[3], uint32_t fl, bool terminated, unsigned reason,
+                                             RewardResult& out) {
     double* c = out.comps;
 #pragma unroll
     for (int i = 0; i < TL_N_COMPS; ++i) c[i] = 0.0;
@@ -133,23 +159,18 @@ __device__ __forceinline__ void reward_agent(const KParams& p, int a, int tick, 
     }
     total -= needs_penalty;
     c[TL_COMP_NEEDS_PENALTY] = -needs_penalty;
-    double sb = 0.0, sp = 0.0, sa = 0.0;
-    if (p.b.social_in) {
-        sb = p.b.social_in[a];
-        sp = p.b.social_in[(size_t)N + a];
-        sa = p.b.social_in[2 * (size_t)N + a];
-    }
+    const double sb = in.sb, sp = in.sp, sa = in.sa;
     total += sb + sp + sa;  // engine.py:87
     c[TL_COMP_SOCIAL_BONUS] = sb;
     c[TL_COMP_SOCIAL_PENALTY] = sp;
     c[TL_COMP_SOCIAL_AVOIDANCE] = sa;
     c[TL_COMP_SOCIAL] = sb + sp + sa;
     double wage = 0.0;  // engine.py:375-386
-    if (r.wage_rate > 0.0) wage = p.b.wages_paid[a] - p.b.wages_withheld[a];
+    if (r.wage_rate > 0.0) wage = in.wages_paid - in.wages_withheld;
     total += wage;
     c[TL_COMP_WAGE] = wage;
     double punct = 0.0;  // engine.py:388-398
-    if (r.punctuality_bonus > 0.0) punct = r.punctuality_bonus * p.b.punctuality[a];
+    if (r.punctuality_bonus > 0.0) punct = r.punctuality_bonus * in.punctuality;
     total += punct;
     c[TL_COMP_PUNCTUALITY] = punct;
     unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
@@ -190,20 +211,20 @@ __device__ __forceinline__ void reward_agent(const KParams& p, int a, int tick, 
     c[TL_COMP_TERMINAL_PENALTY] = penalty;
     const double pre_guard = total;
     // termination block: prune (engine.py:363-373), set (:113-114), test (:355-361)
-    int32_t block = p.b.term_block_tick[a];
+    int32_t block = in.block;
     if (r.block_window < 0) block = TL_TERM_BLOCK_NONE;
     else if (block != TL_TERM_BLOCK_NONE && (int64_t)tick - (int64_t)block > (int64_t)r.block_window)
         block = TL_TERM_BLOCK_NONE;
     if (terminated) block = tick;
     const bool blocked = r.block_window >= 0 && block != TL_TERM_BLOCK_NONE &&
                          (int64_t)tick - (int64_t)block <= (int64_t)r.block_window;
-    p.b.term_block_tick[a] = block;
+    out.block = block;
     if ((terminated || blocked) && total > 0.0) total = 0.0;  // engine.py:116-122
     const double guard_adjust = total - pre_guard;
     const double post = fmax(fmin(total, r.clip_per_tick), -r.clip_per_tick);  // engine.py:126-128
     const double tick_clip_adjust = post - total;
     total = post;
-    const double prev = terminated ? 0.0 : p.b.episode_total[a];  // engine.py:415-424
+    const double prev = terminated ? 0.0 : in.episode_total;  // engine.py:415-424
     double cumulative = prev + total;
     double episode_clip_adjust = 0.0;
     if (r.clip_per_episode > 0) {  // engine.py:130-139
@@ -212,7 +233,7 @@ __device__ __forceinline__ void reward_agent(const KParams& p, int a, int tick, 
         episode_clip_adjust = new_total - total;
         total = new_total;
     }
-    p.b.episode_total[a] = cumulative;
+    out.cumulative = cumulative;
     c[TL_COMP_CLIP_ADJUSTMENT] = guard_adjust + tick_clip_adjust + episode_clip_adjust;
     c[TL_COMP_TOTAL] = total;
     c[TL_COMP_HOMEOSTASIS] = c[TL_COMP_SURVIVAL] + c[TL_COMP_NEEDS_PENALTY];
@@ -407,7 +428,10 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
                     }
                     if (do_reward) {
                         RewardResult rr;
-                        reward_agent(p, a, tick, need, fl, terminated, reason, rr);
+                        const RewardIn rin = load_reward_in(p, a);
+                        reward_agent(p.rew, rin, tick, need, fl, terminated, reason, rr);
+                        p.b.term_block_tick[a] = rr.block;
+                        p.b.episode_total[a] = rr.cumulative;
                         reward_total = rr.total;
                         if (p.ro.reward) p.ro.reward[(size_t)it * p.ro.reward_tick_stride + a] = (float)rr.total;
                         if (p.ro.comps) {
@@ -921,6 +945,17 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         int tpc = towns_per_cta_override > 0 ? towns_per_cta_override : env_int("TL_TPC", chunk / (avg_agents > 0 ? avg_agents : 1));
         if (tpc < 1) tpc = 1;
         if (tpc > kMaxTownsPerWarp) tpc = kMaxTownsPerWarp;
+        if (towns_per_cta_override <= 0 && !getenv("TL_TPC")) {
+            // small batches: prefer more, emptier warps over idle SMs (>= 8 warps per SM when possible)
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            while (tpc > 1 && (b->n_towns + tpc - 1) / tpc < 8 * sms) --tpc;
+        }
+        {
+            // staging only needs to hold the agents one warp owns per pass
+            const int need = tpc * avg_agents;
+            if (!getenv("TL_CHUNK") && need < chunk) kp.chunk = chunk = need < 8 ? 8 : (need + 7) / 8 * 8;
+        }
         int off = 0;
         kp.off_grid = 0;
         kp.off_ctype = -1;
@@ -973,10 +1008,18 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         return TL_OK;
     };
     if (kp.mode == 0) {
+        const bool generic = getenv("TL_GENERIC") != nullptr;  // force the runtime-window form (tests)
+        const int win = do_obs ? kp.obs.window : 0;
         switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
-            case TL_VARIANT_HYBRID: return run(tick_kernel_ent<TL_VARIANT_HYBRID>);
-            case TL_VARIANT_FULL: return run(tick_kernel_ent<TL_VARIANT_FULL>);
-            case TL_VARIANT_COMPACT: return run(tick_kernel_ent<TL_VARIANT_COMPACT>);
+            case TL_VARIANT_HYBRID:
+                if (win == 11 && !generic) return run(tick_kernel_ent<TL_VARIANT_HYBRID, 11>);
+                return run(tick_kernel_ent<TL_VARIANT_HYBRID, 0>);
+            case TL_VARIANT_FULL:
+                if (win == 11 && !generic && (((uintptr_t)kp.oo.map) & 7) == 0) return run(tick_kernel_ent<TL_VARIANT_FULL, 11>);
+                return run(tick_kernel_ent<TL_VARIANT_FULL, 0>);
+            case TL_VARIANT_COMPACT:
+                if (win == 7 && kp.obs.n_ctypes == 0 && !generic) return run(tick_kernel_ent<TL_VARIANT_COMPACT, 7>);
+                return run(tick_kernel_ent<TL_VARIANT_COMPACT, 0>);
             default: return set_error("unknown variant"), TL_ERR_ARG;
         }
     }
