@@ -9,18 +9,21 @@
 //            faint predicate, reward with guardrails, per-town KPI partials by
 //            segmented warp shuffles, every scalar feature and the whole social
 //            snippet (stable top-k by repeated first-argmax) into a shared row.
-//   phase B  the WARP serves one agent at a time: the staging tile is cleared
-//            with 16-byte stores, each lane tests one entity of the agent's town
-//            against the egocentric window and sets its cell (the sparse form
-//            of build_local_cache + the window loop, cache.py:16-41 /
-//            encoders/map.py:80-125), the local summary comes from REDUX over
-//            the same tests, and the tile leaves with 16-byte coalesced stores.
+//   phase B  the WARP serves one agent at a time.  The egocentric tile is
+//            "template + patches": the template (all zeros, the self cell, the
+//            constant path_dx/path_dy or walkable channels) leaves with 16-byte
+//            coalesced stores, then each lane tests ONE entity of the agent's
+//            town against the window and patches its cell — the sparse form of
+//            build_local_cache + the window loop (cache.py:16-41,
+//            encoders/map.py:80-125).  The local summary comes from REDUX over
+//            the same tests.  The entity words of a town stay in registers while
+//            the warp walks through the town's agents.
 //   The feature rows of the whole pass are written back in one coalesced sweep.
 //
-// Per agent this is ~100 warp instructions instead of ~1400 for the dense
-// grid-gather form (profiles/r1_*), which is what lets the path reach the
-// HBM write roofline.  The dense shared-memory grid form stays available
-// (tick_kernel) for towns with hundreds of entities.
+// The dense shared-memory grid form (tick_kernel) stays available for towns
+// with hundreds of entities, where O(window) beats O(entities) per agent.
+
+constexpr int kEntCache = 4;  // entity words per lane kept in registers (128 entities per town)
 
 // WT > 0 fixes the window (and n_ctypes = 0) at compile time so the short per-agent
 // loops unroll; WT = 0 is the generic form for any window / object channels.
@@ -28,7 +31,7 @@ template <int VARIANT, int WT>
 __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);
-    float* s_map = reinterpret_cast<float*>(smem + p.off_map);
+    float* s_tmpl = reinterpret_cast<float*>(smem + p.off_map);
     KpiAcc* s_kpi = reinterpret_cast<KpiAcc*>(smem + p.off_meta);
 
     const unsigned FULL = 0xffffffffu;
@@ -50,15 +53,31 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
     constexpr bool kStatic = WT > 0;
     constexpr int kChannels = VARIANT == TL_VARIANT_HYBRID ? 4 : (VARIANT == TL_VARIANT_FULL ? 6 : 5);
     constexpr int kMapElems = kStatic ? kChannels * WT * WT : 4;
-    constexpr int kMapStride = (kMapElems + 4 + 3) / 4 * 4;
     const int W = kStatic ? WT : o.window;
     const int R = W >> 1;
     const int W2 = W * W;
     const int F = o.n_features;
     const int n_ct = kStatic ? 0 : o.n_ctypes;
     const int map_elems = kStatic ? kMapElems : o.n_channels * W2;
-    const int map_stride = kStatic ? kMapStride : p.map_stride;
     const int chunk_cap = p.chunk;  // agents per phase-A pass (<= 32)
+    const int centre_tile = R * W + R;
+    const int walk_off = (4 + n_ct) * W2;  // compact: first float of the walkable channel
+
+    // ---- tile templates, one per reachable 16-byte misalignment of a global tile ----------
+    if (do_obs && p.tmpl_mask) {
+#pragma unroll 1
+        for (int m = 0; m < 4; ++m) {
+            if (!((p.tmpl_mask >> m) & 1)) continue;
+            float* t = s_tmpl + p.tmpl_off[m] + m;
+#pragma unroll 1
+            for (int k = lane; k < map_elems; k += 32) {
+                float v = (k == centre_tile) ? 1.0f : 0.0f;  // self channel (map.py:69 / :185-186)
+                if (VARIANT == TL_VARIANT_FULL && k >= 4 * W2) v = __ldg(o.path_lut + (k - 4 * W2));  // map.py:115-125
+                if (VARIANT == TL_VARIANT_COMPACT && k >= walk_off) v = (k - walk_off == centre_tile) ? 0.0f : 1.0f;  // map.py:231-241
+                t[k] = v;
+            }
+        }
+    }
 
     // lane s holds the offsets of town t0 + s (s <= n_towns)
     int my_aoff = 0, my_eoff = 0, my_tick = 0;
@@ -70,7 +89,13 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
     const int a_begin = __shfl_sync(FULL, my_aoff, 0);
     const int a_end = __shfl_sync(FULL, my_aoff, n_towns);
     const int n_chunks = (a_end - a_begin + chunk_cap - 1) / chunk_cap;
+    __syncwarp();
 
+    // entity words of the town being served (lane l holds entities cached_eb + l + 32 k)
+    int cached_eb = -1;
+    uint32_t wc[kEntCache] = {0u, 0u, 0u, 0u};
+
+#pragma unroll 1
     for (int it = 0; it < p.n_ticks; ++it) {
         if (do_advance && lane < n_towns) {  // core/sim_loop.py:635,659
             my_tick += 1;
@@ -83,20 +108,9 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
             z.starving = z.term = z.count = 0;
             s_kpi[lane] = z;
         }
-        if (VARIANT == TL_VARIANT_FULL && kStatic && do_obs) {
-            // path_dx / path_dy are agent independent (map.py:115-125): keep them resident in both
-            // staging buffers, at the misalignment each buffer has during this tick
-            const float* m0 = p.oo.map + (size_t)it * p.oo.map_tick_stride;
-#pragma unroll
-            for (int par = 0; par < 2; ++par) {
-                const int first = a_begin + ((a_begin & 1) == par ? 0 : 1);  // first agent with this parity
-                const int mis = (int)((reinterpret_cast<uintptr_t>(m0 + (size_t)first * map_elems) >> 2) & 3);
-                float* dst = s_map + par * map_stride + mis + 4 * W2;
-                for (int k = lane; k < 2 * W2; k += 32) dst[k] = __ldg(o.path_lut + k);
-            }
-        }
         __syncwarp();
 
+#pragma unroll 1
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
             const int c_begin = a_begin + chunk * chunk_cap;
             const int c_n = min(chunk_cap, a_end - c_begin);
@@ -108,6 +122,7 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
             const bool active = lane < c_n;
             const int a = c_begin + (active ? lane : 0);
             int slot = 0;
+#pragma unroll 1
             for (int s = 1; s < n_towns; ++s) slot += (a >= __shfl_sync(FULL, my_aoff, s)) ? 1 : 0;
             const int town_abeg = __shfl_sync(FULL, my_aoff, slot);
             const int town_aend = __shfl_sync(FULL, my_aoff, slot + 1);
@@ -115,19 +130,17 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
             const int town_eend = __shfl_sync(FULL, my_eoff, slot + 1);
             const int tick = __shfl_sync(FULL, my_tick, slot);
 
-            double need0 = 0.0;
-            uint32_t fl = 0;
+            double need0 = 0.0, reward_total = 0.0, kpi_wallet = 0.0;
             bool terminated = false;
-            double reward_total = 0.0;
-            int cx = 0, cy = 0, filled = 0, source = 0, kpi_late = 0;
-            double kpi_wallet = 0.0;
+            int32_t pw = 0;
+            int filled = 0, source = 0, kpi_late = 0;
             if (active) {
-                // ---- every global input of the agent is loaded up front so the loads overlap
+                // ---- the agent's scalar inputs are loaded up front so the loads overlap
                 double need[3];
                 need[0] = p.b.needs[a];
                 need[1] = p.b.needs[(size_t)N + a];
                 need[2] = p.b.needs[2 * (size_t)N + a];
-                fl = p.b.flags[a];
+                uint32_t fl = p.b.flags[a];
                 int episode_tick = p.b.episode_tick[a];
                 RewardIn rin;
                 if (do_reward) rin = load_reward_in(p, a);
@@ -137,13 +150,7 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
                 kpi_late = lateness;
                 double attendance = 0.0, wages_withheld = 0.0;
                 int duration = 0, slot_idx = 0, n_riv = 0, n_t = 0;
-                float last_hash = 0.0f, pers[3] = {0.0f, 0.0f, 0.0f};
-                int32_t pw = 0;
-                const int K = p.b.max_edges;
-                const int EW = p.b.embed_words;
-                const size_t rbase = (size_t)a * K;
-                double r_trust[TL_MAX_EDGES], r_fam[TL_MAX_EDGES], r_riv[TL_MAX_EDGES], r_score[TL_MAX_EDGES];
-                uint64_t r_emb[TL_MAX_EDGES];
+                float last_hash = 0.0f;
                 if (do_obs) {
                     attendance = __ldg(p.b.attendance + a);
                     wages_withheld = __ldg(p.b.wages_withheld + a);
@@ -153,23 +160,6 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
                     pw = __ldg(p.b.pos + a);
                     n_riv = __ldg(p.b.riv_count + a);
                     n_t = __ldg(p.b.tie_count + a);
-                    if (o.personality_base >= 0 && p.b.personality) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) pers[k] = __ldg(p.b.personality + (size_t)k * N + a);
-                    }
-#pragma unroll
-                    for (int j = 0; j < TL_MAX_EDGES; ++j) {
-                        r_trust[j] = r_fam[j] = r_riv[j] = r_score[j] = 0.0;
-                        r_emb[j] = 0;
-                        if (j < K) {
-                            r_score[j] = __ldg(p.b.riv_score + rbase + j);
-                            if (o.social_base >= 0) {
-                                r_trust[j] = __ldg(p.b.tie_trust + rbase + j);
-                                r_fam[j] = __ldg(p.b.tie_fam + rbase + j);
-                                r_riv[j] = __ldg(p.b.tie_riv + rbase + j);
-                            }
-                        }
-                    }
                 }
 
                 const unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
@@ -241,12 +231,19 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
                     f[TL_FEAT_CTX_RESET] = ((fl & TL_F_CTX_RESET) || terminated) ? 1.0f : 0.0f;  // service.py:224-229
                     f[TL_FEAT_EPISODE_PROGRESS] =
                         episode_tick <= 0 ? 0.0f : __ldg(o.progress_lut + min(episode_tick, o.ticks_per_day));
+                    const int K = p.b.max_edges;
+                    const size_t rbase = (size_t)a * K;
                     {  // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
                         const int nr = min(n_riv, o.rivalry_max_edges);
                         int avoid = 0;
-#pragma unroll
-                        for (int j = 0; j < TL_MAX_EDGES; ++j) avoid += (j < nr && r_score[j] >= o.avoid_threshold) ? 1 : 0;
-                        f[TL_FEAT_RIVALRY_MAX] = (float)(nr > 0 ? r_score[0] : 0.0);
+                        double mx = 0.0;
+#pragma unroll 1
+                        for (int j = 0; j < nr; ++j) {
+                            const double v = __ldg(p.b.riv_score + rbase + j);
+                            if (j == 0) mx = v;
+                            avoid += (v >= o.avoid_threshold) ? 1 : 0;
+                        }
+                        f[TL_FEAT_RIVALRY_MAX] = (float)mx;
                         f[TL_FEAT_RIVALRY_AVOID] = (float)avoid;
                     }
                     f[TL_FEAT_LAST_HASH] = last_hash;
@@ -256,56 +253,52 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
                     f[TL_FEAT_IN_QUEUE] = (fl & TL_F_IN_QUEUE) ? 1.0f : 0.0f;
                     // nearest object per landmark type: first minimum of the squared
                     // distance in insertion order (world/observe.py:109-147)
-                    cx = pos_x(pw);
-                    cy = pos_y(pw);
-                    int best_d2[5] = {-1, -1, -1, -1, -1};
-                    int best_dx[5] = {0, 0, 0, 0, 0}, best_dy[5] = {0, 0, 0, 0, 0};
+                    const int cx = pos_x(pw), cy = pos_y(pw);
                     const bool all_types = o.landmark_base >= 0;
                     const int e_obj = town_ebeg + (town_aend - town_abeg);
-                    for (int e = e_obj; e < town_eend; ++e) {
-                        const uint32_t w = __ldg(p.b.ent + e);
-                        if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w)) continue;
-                        const int lt = (int)TL_ENT_LTYPE(w);
-                        if (lt == 0 || (!all_types && lt != o.path_hint_ltype)) continue;
-                        const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
-                        const int d2 = dx * dx + dy * dy;
-#pragma unroll
-                        for (int l = 1; l <= 4; ++l) {
-                            if (l == lt && (best_d2[l] < 0 || d2 < best_d2[l])) {
-                                best_d2[l] = d2;
-                                best_dx[l] = dx;
-                                best_dy[l] = dy;
+                    int hd2 = -1, hdx = 0, hdy = 0;
+                    if (!all_types) {
+#pragma unroll 1
+                        for (int e = e_obj; e < town_eend; ++e) {
+                            const uint32_t w = __ldg(p.b.ent + e);
+                            // object kind, landmark-visible, of the path-hint type
+                            if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w) || (int)TL_ENT_LTYPE(w) != o.path_hint_ltype)
+                                continue;
+                            const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
+                            const int d2 = dx * dx + dy * dy;
+                            if (hd2 < 0 || d2 < hd2) {
+                                hd2 = d2;
+                                hdx = dx;
+                                hdy = dy;
                             }
                         }
-                    }
-                    {  // _encode_path_hint, features.py:251-286
-                        double north = 0.0, south = 0.0, east = 0.0, west = 0.0;
-                        int hd2 = -1, hdx = 0, hdy = 0;
+                    } else {
+                        int best_d2[5] = {-1, -1, -1, -1, -1};
+                        int best_dx[5] = {0, 0, 0, 0, 0}, best_dy[5] = {0, 0, 0, 0, 0};
+#pragma unroll 1
+                        for (int e = e_obj; e < town_eend; ++e) {
+                            const uint32_t w = __ldg(p.b.ent + e);
+                            if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w)) continue;
+                            const int lt = (int)TL_ENT_LTYPE(w);
+                            if (lt == 0) continue;
+                            const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
+                            const int d2 = dx * dx + dy * dy;
 #pragma unroll
-                        for (int l = 1; l <= 4; ++l)
+                            for (int l = 1; l <= 4; ++l) {
+                                if (l == lt && (best_d2[l] < 0 || d2 < best_d2[l])) {
+                                    best_d2[l] = d2;
+                                    best_dx[l] = dx;
+                                    best_dy[l] = dy;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int l = 1; l <= 4; ++l) {  // _encode_landmarks, features.py:333-356
                             if (l == o.path_hint_ltype) {
                                 hd2 = best_d2[l];
                                 hdx = best_dx[l];
                                 hdy = best_dy[l];
                             }
-                        if (hd2 >= 0) {
-                            const int norm = abs(hdx) + abs(hdy);
-                            if (norm != 0) {
-                                const double dn = (double)norm;
-                                north = fmax(0.0, (double)-hdy) / dn;
-                                south = fmax(0.0, (double)hdy) / dn;
-                                east = fmax(0.0, (double)hdx) / dn;
-                                west = fmax(0.0, (double)-hdx) / dn;
-                            }
-                        }
-                        f[TL_FEAT_PATH_NORTH + 0] = (float)north;
-                        f[TL_FEAT_PATH_NORTH + 1] = (float)south;
-                        f[TL_FEAT_PATH_NORTH + 2] = (float)east;
-                        f[TL_FEAT_PATH_NORTH + 3] = (float)west;
-                    }
-                    if (all_types) {  // _encode_landmarks, features.py:333-356
-#pragma unroll
-                        for (int l = 1; l <= 4; ++l) {
                             float* dst = f + o.landmark_base + 3 * (l - 1);
                             if (best_d2[l] < 0) {
                                 dst[0] = dst[1] = dst[2] = 0.0f;
@@ -319,90 +312,110 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
                             }
                         }
                     }
+                    {  // _encode_path_hint, features.py:251-286
+                        double north = 0.0, south = 0.0, east = 0.0, west = 0.0;
+                        if (hd2 > 0) {
+                            const double dn = (double)(abs(hdx) + abs(hdy));
+                            north = fmax(0.0, (double)-hdy) / dn;
+                            south = fmax(0.0, (double)hdy) / dn;
+                            east = fmax(0.0, (double)hdx) / dn;
+                            west = fmax(0.0, (double)-hdx) / dn;
+                        }
+                        f[TL_FEAT_PATH_NORTH + 0] = (float)north;
+                        f[TL_FEAT_PATH_NORTH + 1] = (float)south;
+                        f[TL_FEAT_PATH_NORTH + 2] = (float)east;
+                        f[TL_FEAT_PATH_NORTH + 3] = (float)west;
+                    }
                     if (o.personality_base >= 0) {  // features.py:359-380
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) f[o.personality_base + k] = pers[k];
+                        for (int k = 0; k < 3; ++k)
+                            f[o.personality_base + k] = p.b.personality ? __ldg(p.b.personality + (size_t)k * N + a) : 0.0f;
                     }
 
                     // ---- social snippet (encoders/social.py:27-254) -------------
                     if (o.social_base >= 0) {
                         const int slot_dim = o.embed_dim + 3;
                         const int total_slots = o.top_friends + o.top_rivals;
-                        const int social_len = total_slots * slot_dim + (o.include_aggregates ? 4 : 0);
                         float* srow = f + o.social_base;
-                        for (int k = 0; k < social_len; ++k) srow[k] = 0.0f;
+                        const int EW = p.b.embed_words;
                         const bool from_ties = n_t > 0;  // _resolve_relationships, social.py:165-209
                         const int n_rel = from_ties ? n_t : min(n_riv, o.top_rivals);
                         source = from_ties ? 1 : (n_rel > 0 ? 2 : 0);
+                        const double* kt = p.b.tie_trust + rbase;
+                        const double* kf = p.b.tie_fam + rbase;
+                        const double* kr = (from_ties ? p.b.tie_riv : p.b.riv_score) + rbase;
                         const uint64_t* ke = (from_ties ? p.b.tie_embed : p.b.riv_embed) + rbase * EW;
-#pragma unroll
-                        for (int j = 0; j < TL_MAX_EDGES; ++j) {
-                            if (j < n_rel) r_emb[j] = __ldg(ke + (size_t)j * EW);
-                            if (!from_ties) {  // rivalry fallback: trust = familiarity = 0 (social.py:197-206)
-                                r_trust[j] = 0.0;
-                                r_fam[j] = 0.0;
-                                r_riv[j] = r_score[j];
-                            }
-                        }
                         // sorted(..., reverse=True)[:k] is stable: repeated FIRST argmax (social.py:137-156).
-                        // slot_of packs, per relation j, its destination slot in 4 bits (15 = none).
-                        unsigned chosen = 0, slot_of = 0xffffffffu;
+                        // In the rivalry fallback trust = familiarity = 0, so friends are the first entries.
+                        unsigned chosen = 0, sel = 0;
                         const int n_friends = min(n_rel, o.top_friends);
                         const int n_rivals = min(o.top_rivals, n_rel - n_friends);
                         filled = n_friends + n_rivals;
+#pragma unroll 1
                         for (int s = 0; s < filled; ++s) {
                             const bool friend_pass = s < n_friends;
                             int best = -1;
                             double bk = 0.0;
-#pragma unroll
-                            for (int j = 0; j < TL_MAX_EDGES; ++j) {
-                                const double key = friend_pass ? r_trust[j] + r_fam[j] : r_riv[j];
-                                const bool free_j = j < n_rel && !((chosen >> j) & 1u);
-                                if (free_j && (best < 0 || key > bk)) {
+#pragma unroll 1
+                            for (int j = 0; j < n_rel; ++j) {
+                                if ((chosen >> j) & 1u) continue;
+                                const double key = friend_pass ? (from_ties ? __ldg(kt + j) + __ldg(kf + j) : 0.0) : __ldg(kr + j);
+                                if (best < 0 || key > bk) {
                                     best = j;
                                     bk = key;
                                 }
                             }
                             chosen |= 1u << best;
-                            slot_of = (slot_of & ~(15u << (4 * best))) | ((unsigned)s << (4 * best));
+                            sel |= (unsigned)best << (4 * s);
                         }
-                        double tv[TL_MAX_SOCIAL_SLOTS], rv[TL_MAX_SOCIAL_SLOTS];
-#pragma unroll
-                        for (int s = 0; s < TL_MAX_SOCIAL_SLOTS; ++s) tv[s] = rv[s] = 0.0;
-#pragma unroll
-                        for (int j = 0; j < TL_MAX_EDGES; ++j) {
-                            const unsigned s = (slot_of >> (4 * j)) & 15u;
-                            if (j < n_rel && s != 15u) {
-                                float* dst = srow + s * slot_dim;
-                                for (int d = 0; d < o.embed_dim; ++d) {  // social.py:236-242
-                                    const uint64_t word = (d < 8) ? r_emb[j] : __ldg(ke + (size_t)j * EW + (d >> 3));
-                                    const unsigned byte = (unsigned)(word >> (8 * (d & 7))) & 255u;
-                                    dst[d] = __ldg(o.embed_lut + byte);
-                                }
-                                dst[o.embed_dim + 0] = (float)r_trust[j];
-                                dst[o.embed_dim + 1] = (float)r_fam[j];
-                                dst[o.embed_dim + 2] = (float)r_riv[j];
-#pragma unroll
-                                for (int q = 0; q < TL_MAX_SOCIAL_SLOTS; ++q)
-                                    if (q == (int)s) {
-                                        tv[q] = r_trust[j];
-                                        rv[q] = r_riv[j];
-                                    }
+                        double tsum = 0.0, rsum = 0.0, tmax = 0.0, rmax = 0.0;
+#pragma unroll 1
+                        for (int s = 0; s < total_slots; ++s) {
+                            float* dst = srow + s * slot_dim;
+                            if (s >= filled) {  // _empty_relationship_entry, social.py:226-233
+#pragma unroll 1
+                                for (int d = 0; d < slot_dim; ++d) dst[d] = 0.0f;
+                                continue;
                             }
+                            const int j = (sel >> (4 * s)) & 15;
+                            const double trust = from_ties ? __ldg(kt + j) : 0.0;
+                            const double fam = from_ties ? __ldg(kf + j) : 0.0;
+                            const double riv = __ldg(kr + j);
+                            uint64_t word = 0;
+#pragma unroll 1
+                            for (int d = 0; d < o.embed_dim; ++d) {  // _embed_agent_id, social.py:236-242
+                                if ((d & 7) == 0) word = __ldg(ke + (size_t)j * EW + (d >> 3));
+                                dst[d] = __ldg(o.embed_lut + ((unsigned)(word >> (8 * (d & 7))) & 255u));
+                            }
+                            dst[o.embed_dim + 0] = (float)trust;
+                            dst[o.embed_dim + 1] = (float)fam;
+                            dst[o.embed_dim + 2] = (float)riv;
+                            tsum += trust;  // numpy sums left to right below 8 values
+                            rsum += riv;
+                            tmax = s == 0 ? trust : fmax(tmax, trust);
+                            rmax = s == 0 ? riv : fmax(rmax, riv);
                         }
-                        if (o.include_aggregates && filled > 0) {  // social.py:90-105, 245-254
-                            double tmax = tv[0], rmax = rv[0];
-#pragma unroll
-                            for (int s = 1; s < TL_MAX_SOCIAL_SLOTS; ++s)
-                                if (s < filled) {
-                                    tmax = fmax(tmax, tv[s]);
-                                    rmax = fmax(rmax, rv[s]);
-                                }
+                        if (o.include_aggregates) {  // _compute_aggregates, social.py:90-105, 245-254
                             float* agg = srow + total_slots * slot_dim;
-                            agg[0] = (float)(np_sum_le8(tv, filled) / (double)filled);
-                            agg[1] = (float)tmax;
-                            agg[2] = (float)(np_sum_le8(rv, filled) / (double)filled);
-                            agg[3] = (float)rmax;
+                            if (filled > 0) {
+                                if (filled == 8) {  // numpy's unrolled pairwise block of 8
+                                    double tv[8], rv[8];
+#pragma unroll
+                                    for (int s = 0; s < 8; ++s) {
+                                        const int j = (sel >> (4 * s)) & 15;
+                                        tv[s] = from_ties ? __ldg(kt + j) : 0.0;
+                                        rv[s] = __ldg(kr + j);
+                                    }
+                                    tsum = ((tv[0] + tv[1]) + (tv[2] + tv[3])) + ((tv[4] + tv[5]) + (tv[6] + tv[7]));
+                                    rsum = ((rv[0] + rv[1]) + (rv[2] + rv[3])) + ((rv[4] + rv[5]) + (rv[6] + rv[7]));
+                                }
+                                agg[0] = (float)(tsum / (double)filled);
+                                agg[1] = (float)tmax;
+                                agg[2] = (float)(rsum / (double)filled);
+                                agg[3] = (float)rmax;
+                            } else {
+                                agg[0] = agg[1] = agg[2] = agg[3] = 0.0f;
+                            }
                         }
                     }
                 }
@@ -448,72 +461,66 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
                 }
             }
             if (!do_obs) continue;  // warp-uniform
-            __syncwarp();
 
             // =================== phase B: the warp serves one agent at a time =====
             // Lane i keeps the integer summary of agent i; the look-ups run thread-per-agent afterwards.
             int my_others = 0, my_objs = 0, my_res = 0, my_d2 = 0;
             float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)c_begin * map_elems;
-            const int centre_tile = R * W + R;
+#pragma unroll 1
             for (int i = 0; i < c_n; ++i, mrow_g += map_elems) {
-                const int a_i = c_begin + i;
-                const int cxi = __shfl_sync(FULL, cx, i), cyi = __shfl_sync(FULL, cy, i);
+                const int32_t pwi = __shfl_sync(FULL, pw, i);
+                const int cxi = pos_x(pwi), cyi = pos_y(pwi);
                 const int eb = __shfl_sync(FULL, town_ebeg, i), ee = __shfl_sync(FULL, town_eend, i);
-                const int self_e = eb + (a_i - __shfl_sync(FULL, town_abeg, i));
-                const int map_mis = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
-                // double buffered by agent parity (a fixed misalignment per buffer for the full variant)
-                float* buf = s_map + (a_i & 1) * map_stride;
-                float* st = buf + map_mis;
-                if (VARIANT == TL_VARIANT_FULL && kStatic) {
-                    // channels 0-3 only (8-byte aligned): the path channels stay resident in the buffer
-                    float2* b2 = reinterpret_cast<float2*>(st);
-                    const float2 z2 = make_float2(0.0f, 0.0f);
+                const int self_e = eb + (c_begin + i - __shfl_sync(FULL, town_abeg, i));
+                if (eb != cached_eb) {  // the warp moved on to the next town: fetch its entity words
+                    cached_eb = eb;
 #pragma unroll
-                    for (int k = 0; k < (2 * W2 + 31) / 32; ++k) {
+                    for (int k = 0; k < kEntCache; ++k) {
+                        const int e = eb + 32 * k + lane;
+                        wc[k] = e < ee ? __ldg(p.b.ent + e) : 0u;
+                    }
+                }
+                // ---- template tile: 16-byte vectorised coalesced stores -------------
+                const int map_mis = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
+                const int head = (4 - map_mis) & 3;
+                const int nvec = (map_elems - head) >> 2;
+                float4* g4 = reinterpret_cast<float4*>(mrow_g + head);
+                if (kStatic && VARIANT == TL_VARIANT_HYBRID && map_mis == 0) {
+                    // all zeros except the self cell (flat float centre_tile)
+#pragma unroll
+                    for (int k = 0; k < (kMapElems / 4 + 31) / 32; ++k) {
                         const int v = lane + 32 * k;
-                        if (v < 2 * W2) b2[v] = z2;
+                        const bool c4 = (v == (centre_tile >> 2));
+                        if (v < kMapElems / 4)
+                            g4[v] = make_float4((c4 && (centre_tile & 3) == 0) ? 1.0f : 0.0f,
+                                                (c4 && (centre_tile & 3) == 1) ? 1.0f : 0.0f,
+                                                (c4 && (centre_tile & 3) == 2) ? 1.0f : 0.0f,
+                                                (c4 && (centre_tile & 3) == 3) ? 1.0f : 0.0f);
                     }
                 } else {
-                    float4* b4 = reinterpret_cast<float4*>(buf);
-                    const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    const float* t = s_tmpl + p.tmpl_off[map_mis] + map_mis;
+                    const float4* s4 = reinterpret_cast<const float4*>(t + head);
                     if (kStatic) {
 #pragma unroll
-                        for (int k = 0; k < (kMapStride / 4 + 31) / 32; ++k) {
+                        for (int k = 0; k < (kMapElems / 4 + 31) / 32; ++k) {
                             const int v = lane + 32 * k;
-                            if (v < kMapStride / 4) b4[v] = z;
+                            if (v < nvec) g4[v] = s4[v];
                         }
                     } else {
 #pragma unroll 1
-                        for (int v = lane; v < (map_stride >> 2); v += 32) b4[v] = z;
+                        for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
                     }
+                    if (lane < head) mrow_g[lane] = t[lane];
+                    const int tail0 = head + (nvec << 2);
+                    if (lane < map_elems - tail0) mrow_g[tail0 + lane] = t[tail0 + lane];
                 }
-                __syncwarp();
-                if (VARIANT == TL_VARIANT_COMPACT) {
-                    float* walk = st + (4 + n_ct) * W2;  // map.py:231-241: empty tiles are walkable
-                    if (kStatic) {
-#pragma unroll
-                        for (int k = 0; k < (W2 + 31) / 32; ++k) {
-                            const int v = lane + 32 * k;
-                            if (v < W2) walk[v] = (v == centre_tile) ? 0.0f : 1.0f;
-                        }
-                    } else {
-#pragma unroll 1
-                        for (int k = lane; k < W2; k += 32) walk[k] = (k == centre_tile) ? 0.0f : 1.0f;
-                    }
-                } else if (VARIANT == TL_VARIANT_FULL && !kStatic) {
-#pragma unroll 1
-                    for (int k = lane; k < 2 * W2; k += 32) st[4 * W2 + k] = __ldg(o.path_lut + k);  // map.py:115-125
-                }
-                if (lane == 0) st[centre_tile] = 1.0f;  // map.py:69 / :185-186
-                if (VARIANT == TL_VARIANT_COMPACT) __syncwarp();
+                __syncwarp();  // orders the template stores before the patches of other lanes
 
+                // ---- patches: one entity per lane (cache.py:16-41 + map.py:80-125) ----
                 int n_ag = 0, n_obj = 0, n_res = 0, centre_has = 0;
                 unsigned nearest = 0xffffffffu;
-#pragma unroll 1
-                for (int e0 = eb; e0 < ee; e0 += 32) {
-                    const int e = e0 + lane;
+                auto serve = [&](uint32_t w, int e) {
                     const bool valid = e < ee;
-                    const uint32_t w = valid ? __ldg(p.b.ent + e) : 0u;
                     const int dx = TL_ENT_X(w) - cxi, dy = TL_ENT_Y(w) - cyi;
                     const bool inwin = valid && (unsigned)(dx + R) <= (unsigned)(2 * R) && (unsigned)(dy + R) <= (unsigned)(2 * R);
                     const int tile = (dy + R) * W + (dx + R);
@@ -534,25 +541,33 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
                         const bool is_other = is_agent && e != self_e;  // map.py:198
                         const bool norm = o.normalize_counts != 0;
                         if (is_other) {
-                            if (norm) st[W2 + tile] = 1.0f;
-                            else atomicAdd(st + W2 + tile, 1.0f);
+                            if (norm) mrow_g[W2 + tile] = 1.0f;
+                            else atomicAdd(mrow_g + W2 + tile, 1.0f);
                         }
                         if (is_obj) {
-                            if (norm) st[2 * W2 + tile] = 1.0f;
-                            else atomicAdd(st + 2 * W2 + tile, 1.0f);
+                            if (norm) mrow_g[2 * W2 + tile] = 1.0f;
+                            else atomicAdd(mrow_g + 2 * W2 + tile, 1.0f);
                             const int ct = (int)TL_ENT_CTYPE(w);
                             if (ct > 0 && ct <= n_ct) {  // map.py:214-229
-                                if (norm) st[(3 + ct) * W2 + tile] = 1.0f;
-                                else atomicAdd(st + (3 + ct) * W2 + tile, 1.0f);
+                                if (norm) mrow_g[(3 + ct) * W2 + tile] = 1.0f;
+                                else atomicAdd(mrow_g + (3 + ct) * W2 + tile, 1.0f);
                             }
                         }
-                        if (is_res) st[3 * W2 + tile] = 1.0f;
-                        if (is_other || is_obj || is_res) st[(4 + n_ct) * W2 + tile] = 0.0f;
+                        if (is_res) mrow_g[3 * W2 + tile] = 1.0f;
+                        if (is_other || is_obj || is_res) mrow_g[walk_off + tile] = 0.0f;
                     } else {
-                        if (is_agent) st[W2 + tile] = 1.0f;  // includes the observer (map.py:109-110)
-                        if (is_obj) st[2 * W2 + tile] = 1.0f;
-                        if (is_res) st[3 * W2 + tile] = 1.0f;
+                        if (is_agent) mrow_g[W2 + tile] = 1.0f;  // includes the observer (map.py:109-110)
+                        if (is_obj) mrow_g[2 * W2 + tile] = 1.0f;
+                        if (is_res) mrow_g[3 * W2 + tile] = 1.0f;
                     }
+                };
+#pragma unroll
+                for (int k = 0; k < kEntCache; ++k)
+                    if (eb + 32 * k < ee) serve(wc[k], eb + 32 * k + lane);
+#pragma unroll 1
+                for (int e0 = eb + 32 * kEntCache; e0 < ee; e0 += 32) {
+                    const int e = e0 + lane;
+                    serve(e < ee ? __ldg(p.b.ent + e) : 0u, e);
                 }
                 n_ag = __reduce_add_sync(FULL, n_ag);
                 n_obj = __reduce_add_sync(FULL, n_obj);
@@ -564,28 +579,6 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
                     my_objs = n_obj;
                     my_res = n_res;
                     my_d2 = nearest == 0xffffffffu ? 0 : (int)nearest;
-                }
-                __syncwarp();
-                {  // 16-byte vectorised coalesced stores of the map tile
-                    const int head = (4 - map_mis) & 3;
-                    const int nvec = (map_elems - head) >> 2;
-                    float4* g4 = reinterpret_cast<float4*>(mrow_g + head);
-                    const float4* s4 = reinterpret_cast<const float4*>(st + head);
-                    if (kStatic) {
-#pragma unroll
-                        for (int k = 0; k < (kMapElems / 4 + 31) / 32; ++k) {
-                            const int v = lane + 32 * k;
-                            if (v < nvec) g4[v] = s4[v];
-                        }
-                    } else {
-#pragma unroll 1
-                        for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
-                    }
-                    if (kMapElems % 4 != 0 || !kStatic || map_mis != 0) {
-                        if (lane < head) mrow_g[lane] = st[lane];
-                        const int tail0 = head + (nvec << 2);
-                        if (lane < map_elems - tail0) mrow_g[tail0 + lane] = st[tail0 + lane];
-                    }
                 }
             }
             // local summary features, thread-per-agent (features.py:289-330 via the host LUTs)

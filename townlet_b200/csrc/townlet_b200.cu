@@ -67,6 +67,8 @@ struct KParams {
     int32_t smem_bytes;
     int32_t chunk;         // entity form: agents per phase-A pass (<= 32)
     int32_t mode;          // 0 entity-list form, 1 dense shared-memory grid form
+    int32_t tmpl_mask;     // entity form: bit m set = a tile template for 16-byte misalignment m floats exists
+    int32_t tmpl_off[4];   // entity form: float offset of template m inside the template area
 };
 
 struct ChunkMeta {
@@ -962,7 +964,22 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         kp.off_feat = off;
         off += do_obs ? round_up((chunk * kp.feat_stride + 4) * 4, 16) : 16;
         kp.off_map = off;
-        off += do_obs ? 2 * kp.map_stride * 4 : 0;
+        kp.tmpl_mask = 0;
+        if (do_obs) {
+            // which 16-byte misalignments (in floats) can a tile of the output tensor have?
+            const int base = (int)(((uintptr_t)kp.oo.map >> 2) & 3);
+            const int sa = map_elems & 3, st = (int)(kp.oo.map_tick_stride & 3);
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) kp.tmpl_mask |= 1 << ((base + i * sa + j * st) & 3);
+            const bool static_hybrid = kp.obs.variant == TL_VARIANT_HYBRID && kp.obs.window == 11 && !getenv("TL_GENERIC");
+            if (static_hybrid && kp.tmpl_mask == 1) kp.tmpl_mask = 0;  // aligned zero tiles come from registers
+            int toff = 0;
+            for (int m = 0; m < 4; ++m) {
+                kp.tmpl_off[m] = toff;
+                if ((kp.tmpl_mask >> m) & 1) toff += kp.map_stride;
+            }
+            off += toff * 4;
+        }
         kp.off_meta = off;
         off += round_up((int)sizeof(KpiAcc) * tpc, 16);
         kp.smem_bytes = off;
