@@ -1,0 +1,131 @@
+"""GPU: the drop-in classes end to end (fake world -> ingest -> tl_host_tick -> dicts) against the oracle."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from fake_world import FakeWorld, fake_config
+
+from townlet_b200 import capi
+from townlet_b200.params import ObsSpec, RewardSpec
+from townlet_b200.synth import assemble, synth_town
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("variant", ["hybrid", "full", "compact"])
+def test_observation_service_on_fake_world(variant) -> None:
+    from oracle.oracle import oracle_tick
+    from townlet_b200.observation_service import B200ObservationService
+
+    config = fake_config(variant)
+    town = synth_town(3, 48, 10)
+    world = FakeWorld(town, config)
+    world.request_ctx_reset(town.agent_ids[2])
+    terminated = {town.agent_ids[1]: True}
+    service = B200ObservationService(config=config)
+    batch_out = service.build_batch(world, terminated)
+    assert list(batch_out) == town.agent_ids
+    assert world.ctx_reset_consumed == 1
+    assert world.embedding_allocator.released == [town.agent_ids[1]]
+
+    spec = ObsSpec.from_config(config)
+    town.terminated[:] = False
+    ref_batch = assemble([town], spec)
+    ref_batch.flags[1] |= capi.TL_F_TERMINATED
+    ref_batch.flags[2] |= capi.TL_F_CTX_RESET
+    ref = oracle_tick(ref_batch, spec, RewardSpec(), capi.TL_PHASE_OBS, 1)
+    for i, aid in enumerate(town.agent_ids):
+        entry = batch_out[aid]
+        assert entry["map"].shape == spec.map_shape and entry["map"].dtype == np.float32
+        assert np.array_equal(entry["map"], ref["map"][0, i]), aid
+        assert np.array_equal(entry["features"].view(np.uint32), ref["features"][0, i].view(np.uint32)), aid
+        meta = entry["metadata"]
+        assert meta["variant"] == variant and meta["embedding_slot"] == i
+        assert meta["local_summary"]["agent_count"] == float(ref["summary"][0, i, 0])
+        assert meta["social_context"]["filled_slots"] == int(ref["summary"][0, i, 4])
+    with pytest.raises(KeyError):
+        service.build_single(world, "nobody")
+
+
+def test_reward_engine_on_fake_world() -> None:
+    from oracle.oracle import oracle_tick
+    from townlet_b200.reward_engine import B200RewardEngine
+
+    config = fake_config("hybrid")
+    town = synth_town(5, 48, 8)
+    world = FakeWorld(town, config)
+    a0, a1, a2 = town.agent_ids[:3]
+    world.chat_events = [{"event": "chat_success", "speaker": a0, "listener": a1, "quality": 0.5}, {"event": "chat_failure", "speaker": a2, "listener": a0}]
+    world.avoidance_events = [{"agent": a1, "object_id": "o", "reason": "queue_rival"}]
+    engine = B200RewardEngine(config)
+    out = engine.compute(world, {a2: True}, {a2: "faint"})
+    assert list(out) == town.agent_ids
+    assert world.events_consumed == 1 and not world.chat_events
+    assert out[a0].social_bonus > 0 and out[a0].social_penalty < 0 and out[a1].social_avoidance > 0
+    assert out[a2].terminal_penalty == -1.0 and engine._termination_block == {a2: world.tick}
+    # same numbers from the oracle on the equivalent batch
+    spec = RewardSpec.from_config(config)
+    from townlet_b200.reward_events import reduce_social_events
+
+    world2 = FakeWorld(town, config)
+    sums = reduce_social_events(
+        world2,
+        [{"event": "chat_success", "speaker": a0, "listener": a1, "quality": 0.5}, {"event": "chat_failure", "speaker": a2, "listener": a0}],
+        [{"agent": a1, "object_id": "o", "reason": "queue_rival"}],
+        spec,
+    )
+    town.terminated[:] = False
+    batch = assemble([town])
+    batch.flags[2] |= capi.TL_F_TERMINATED | (1 << capi.TL_F_REASON_SHIFT)
+    for k in range(3):
+        for i, aid in enumerate(town.agent_ids):
+            batch.social_in[k, i] = sums[k].get(aid, 0.0)
+    ref = oracle_tick(batch, ObsSpec(), spec, capi.TL_PHASE_REWARD, 1)
+    for i, aid in enumerate(town.agent_ids):
+        assert out[aid].total == pytest.approx(ref["comps"][0, i, 0], rel=1e-6, abs=1e-12)
+        assert out[aid].needs_penalty == pytest.approx(ref["comps"][0, i, 2], rel=1e-6, abs=1e-12)
+    # second tick: death window guard for the terminated agent, episode totals carried on the host
+    world.tick += 1
+    out2 = engine.compute(world, {}, {})
+    assert out2[a2].total <= 0.0
+    assert engine._episode_totals[a0] == pytest.approx(out[a0].total + out2[a0].total, rel=1e-9)
+
+
+def test_need_decay_hook_on_fake_world() -> None:
+    from townlet_b200.reward_engine import install_need_decay
+
+    config = fake_config("hybrid")
+    town = synth_town(9, 48, 8)
+    world = FakeWorld(town, config)
+    before = {aid: dict(s.needs) for aid, s in world.agents.items()}
+    hook = install_need_decay(world)
+    hook()
+    for aid, snap in world.agents.items():
+        assert snap.needs["hunger"] == max(0.0, before[aid]["hunger"] - 0.01)
+        assert snap.needs["hygiene"] == max(0.0, before[aid]["hygiene"] - 0.005)
+        assert snap.needs["energy"] == max(0.0, before[aid]["energy"] - 0.008)
+
+
+def test_parallel_env_steps() -> None:
+    import torch
+
+    from oracle.oracle import oracle_tick
+    from townlet_b200.env import TownletParallelEnv
+    from townlet_b200.synth import synth_batch
+
+    obs, rew = ObsSpec(variant="compact"), RewardSpec(fuse_faint=True)
+    batch = synth_batch(12, 48, 10, obs)
+    env = TownletParallelEnv(batch, obs, rew, max_ticks=3)
+    observations, infos = env.reset()
+    assert observations["map"].shape == (batch.n_agents, *obs.map_shape) and infos == {}
+    ref_batch = batch.copy()
+    for step in range(3):
+        observations, rewards, terminations, truncations, infos = env.step(None)
+        ref = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_ALL, 1)
+        torch.cuda.synchronize()
+        assert np.array_equal(observations["map"].cpu().numpy(), ref["map"][0])
+        np.testing.assert_allclose(rewards.cpu().numpy(), ref["reward"][0], rtol=1e-6, atol=1e-9)
+        assert np.array_equal(terminations.cpu().numpy(), ref["terminated"][0].astype(bool))
+        assert bool(truncations.all()) == (step == 2)
+        assert infos["kpi"].shape == (batch.n_towns, capi.TL_N_KPI)

@@ -52,6 +52,8 @@ def resolve_adapter(world: Any) -> Any:
     """Normalise WorldState / WorldContext / adapter like ``ensure_world_adapter``
     (world/core/runtime_adapter.py:192-213) when the reference is importable;
     otherwise accept any object that already quacks like the adapter."""
+    if hasattr(world, "agent_snapshots_view") and hasattr(world, "_employment_context_wages"):
+        return world  # already an adapter (or a duck-typed stand-in)
     try:
         from townlet.world.core.runtime_adapter import ensure_world_adapter  # type: ignore
 
