@@ -66,7 +66,8 @@ struct KParams {
     int32_t off_meta;      // ChunkMeta[kChunk] (grid form) / KpiAcc[towns_per_cta] (entity form)
     int32_t smem_bytes;
     int32_t chunk;         // entity form: agents per phase-A pass (<= 32)
-    int32_t mode;          // 0 entity-list form, 1 dense shared-memory grid form
+    int32_t mode;          // 0 entity-list form with role-parallel warps, 1 dense shared-memory grid form,
+                           // 2 entity-list form with one warp per CTA
     int32_t tmpl_mask;     // entity form: bit m set = a tile template for 16-byte misalignment m floats exists
     int32_t tmpl_off[4];   // entity form: float offset of template m inside the template area
 };
@@ -837,6 +838,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
 }
 
 #include "tick_ent.cuh"
+#include "tick_roles.cuh"
 
 // ---------------------------------------------------------------------------
 // Host side
@@ -936,10 +938,11 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     kp.mode = avg_entities > 384 ? 1 : 0;
     if (mode_env && !strcmp(mode_env, "grid")) kp.mode = 1;
     if (mode_env && !strcmp(mode_env, "ent")) kp.mode = 0;
+    if (mode_env && !strcmp(mode_env, "ent1")) kp.mode = 2;
 
     int grid = 0, threads = kThreads;
-    if (kp.mode == 0) {
-        threads = 32;
+    if (kp.mode != 1) {
+        threads = kp.mode == 0 ? 32 * kRoleWarps : 32;
         int chunk = env_int("TL_CHUNK", 32);
         if (chunk < 1) chunk = 1;
         if (chunk > 32) chunk = 32;
@@ -962,7 +965,8 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         kp.off_grid = 0;
         kp.off_ctype = -1;
         kp.off_feat = off;
-        off += do_obs ? round_up((chunk * kp.feat_stride + 4) * 4, 16) : 16;
+        // role-parallel form: two row buffers of ((chunk * F + 4 + 3) & ~3) floats
+        off += do_obs ? (kp.mode == 0 ? 2 : 1) * round_up((chunk * kp.feat_stride + 4) * 4, 16) : 16;
         kp.off_map = off;
         kp.tmpl_mask = 0;
         if (do_obs) {
@@ -1026,6 +1030,22 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     };
     if (kp.mode == 0) {
         const bool generic = getenv("TL_GENERIC") != nullptr;  // force the runtime-window form (tests)
+        const int win = do_obs ? kp.obs.window : 0;
+        switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
+            case TL_VARIANT_HYBRID:
+                if (win == 11 && !generic) return run(tick_kernel_roles<TL_VARIANT_HYBRID, 11>);
+                return run(tick_kernel_roles<TL_VARIANT_HYBRID, 0>);
+            case TL_VARIANT_FULL:
+                if (win == 11 && !generic) return run(tick_kernel_roles<TL_VARIANT_FULL, 11>);
+                return run(tick_kernel_roles<TL_VARIANT_FULL, 0>);
+            case TL_VARIANT_COMPACT:
+                if (win == 7 && kp.obs.n_ctypes == 0 && !generic) return run(tick_kernel_roles<TL_VARIANT_COMPACT, 7>);
+                return run(tick_kernel_roles<TL_VARIANT_COMPACT, 0>);
+            default: return set_error("unknown variant"), TL_ERR_ARG;
+        }
+    }
+    if (kp.mode == 2) {
+        const bool generic = getenv("TL_GENERIC") != nullptr;
         const int win = do_obs ? kp.obs.window : 0;
         switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
             case TL_VARIANT_HYBRID:
