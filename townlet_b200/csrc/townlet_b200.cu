@@ -951,10 +951,13 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         if (tpc < 1) tpc = 1;
         if (tpc > kMaxTownsPerWarp) tpc = kMaxTownsPerWarp;
         if (towns_per_cta_override <= 0 && !getenv("TL_TPC")) {
-            // small batches: prefer more, emptier warps over idle SMs (>= 8 warps per SM when possible)
+            // small batches: prefer more, emptier CTAs over idle SMs (measured on configs[1]:
+            // 2 towns per 4-warp CTA beat 1, 3 and 4; the single-warp form wants >= 8 warps per SM)
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-            while (tpc > 1 && (b->n_towns + tpc - 1) / tpc < 8 * sms) --tpc;
+            const int want = kp.mode == 0 ? 3 * sms : 8 * sms;
+            const int floor_tpc = (kp.mode == 0 && 2 * avg_agents <= chunk) ? 2 : 1;
+            while (tpc > floor_tpc && (b->n_towns + tpc - 1) / tpc < want) --tpc;
         }
         {
             // staging only needs to hold the agents one warp owns per pass
