@@ -73,6 +73,8 @@ class ClockSampler(threading.Thread):
         self.reasons: set[str] = set()
         self.max_mhz = 0
         self._halt = threading.Event()
+        self.ready = threading.Event()
+        self.go = threading.Event()
 
     def run(self) -> None:
         try:
@@ -87,15 +89,19 @@ class ClockSampler(threading.Thread):
                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             }
-            while not self._halt.is_set():
+            self.ready.set()
+            self.go.wait()
+            while True:  # at least one sample, taken while the timed launches are queued / running
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 for bit, name in names.items():
                     if mask & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                if self._halt.wait(0.005):
+                    break
         except Exception as exc:  # pragma: no cover - NVML missing
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+            self.ready.set()
 
     def stop(self) -> dict:
         self._halt.set()
@@ -132,7 +138,8 @@ def run_reference_arm(args, wl: dict) -> None:
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step_budget = 1.0
+    # bounded sample per step: the whole run stays within about a minute whatever K and W are
+    per_step_budget = min(1.0, 60.0 / max(1, args.warmup + args.steps))
     rates = []
     sample = ""
     for i in range(args.warmup + args.steps):
@@ -171,12 +178,12 @@ def run_reference_arm(args, wl: dict) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=512)
-    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=8192)
+    ap.add_argument("--warmup", type=int, default=256)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--ticks-per-launch", type=int, default=32)
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -232,11 +239,14 @@ def main() -> None:
     events = [torch.cuda.Event(enable_timing=True) for _ in range(n_launch + 1)]
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.ready.wait(timeout=10)
     launches0 = lib.tl_launch_count()
     events[0].record()
     for i in range(n_launch):
         launch(i)
         events[i + 1].record()
+        if i == 0:
+            sampler.go.set()  # the first sample falls inside the timed region
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -268,7 +278,7 @@ def main() -> None:
         "unit": "GB/s",
         "frac": achieved / peak,
         "traffic": None,
-        "kernel": f"tick_kernel<{wl['variant']}>",
+        "kernel": f"tick_kernel_roles<{wl['variant']}>",
         "algorithmic_bytes_per_launch": algo_bytes,
         "avg_launch_ms": avg_launch_s * 1e3,
         "peak_source": peak_src,
