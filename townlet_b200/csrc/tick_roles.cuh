@@ -358,10 +358,44 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                 }
             } else if (warp == 1) {
                 // =================== role "social": one thread per agent =================
+                // The relation rows of the pass are one contiguous block per table: stage them in
+                // shared memory with coalesced loads (one round trip), then select from there.
+                const int K = p.b.max_edges;
+                const int EW = p.b.embed_words;
+                double* s_trust = reinterpret_cast<double*>(smem + p.off_social);
+                double* s_fam = s_trust + chunk_cap * K;
+                double* s_riv = s_fam + chunk_cap * K;
+                double* s_score = s_riv + chunk_cap * K;
+                uint64_t* s_temb = reinterpret_cast<uint64_t*>(s_score + chunk_cap * K);
+                uint64_t* s_remb = s_temb + chunk_cap * K * EW;
+                if (do_obs) {
+                    const size_t r0 = (size_t)c_begin * K;
+                    const int n_rows = c_n * K;
+#pragma unroll 2
+                    for (int i = lane; i < n_rows; i += 32) {
+                        const double v_score = __ldg(p.b.riv_score + r0 + i);
+                        if (o.social_base >= 0) {
+                            const double v_t = __ldg(p.b.tie_trust + r0 + i), v_f = __ldg(p.b.tie_fam + r0 + i);
+                            const double v_r = __ldg(p.b.tie_riv + r0 + i);
+                            s_trust[i] = v_t;
+                            s_fam[i] = v_f;
+                            s_riv[i] = v_r;
+                        }
+                        s_score[i] = v_score;
+                    }
+                    if (o.social_base >= 0) {
+#pragma unroll 2
+                        for (int i = lane; i < n_rows * EW; i += 32) {
+                            const uint64_t v_t = __ldg(p.b.tie_embed + r0 * EW + i), v_r = __ldg(p.b.riv_embed + r0 * EW + i);
+                            s_temb[i] = v_t;
+                            s_remb[i] = v_r;
+                        }
+                    }
+                }
+                __syncwarp();
                 if (active && do_obs) {
                     float* f = feat_s0 + lane * F;
-                    const int K = p.b.max_edges;
-                    const size_t rbase = (size_t)a * K;
+                    const int rbase = lane * K;  // row of this agent inside the staged block
                     const int n_riv = __ldg(p.b.riv_count + a);
                     const int n_t = __ldg(p.b.tie_count + a);
                     {  // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
@@ -370,7 +404,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                         double mx = 0.0;
 #pragma unroll 1
                         for (int j = 0; j < nr; ++j) {
-                            const double v = __ldg(p.b.riv_score + rbase + j);
+                            const double v = s_score[rbase + j];
                             if (j == 0) mx = v;
                             avoid += (v >= o.avoid_threshold) ? 1 : 0;
                         }
@@ -382,14 +416,13 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                         const int slot_dim = o.embed_dim + 3;
                         const int total_slots = o.top_friends + o.top_rivals;
                         float* srow = f + o.social_base;
-                        const int EW = p.b.embed_words;
                         const bool from_ties = n_t > 0;  // _resolve_relationships, social.py:165-209
                         const int n_rel = from_ties ? n_t : min(n_riv, o.top_rivals);
                         source = from_ties ? 1 : (n_rel > 0 ? 2 : 0);
-                        const double* kt = p.b.tie_trust + rbase;
-                        const double* kf = p.b.tie_fam + rbase;
-                        const double* kr = (from_ties ? p.b.tie_riv : p.b.riv_score) + rbase;
-                        const uint64_t* ke = (from_ties ? p.b.tie_embed : p.b.riv_embed) + rbase * EW;
+                        const double* kt = s_trust + rbase;
+                        const double* kf = s_fam + rbase;
+                        const double* kr = (from_ties ? s_riv : s_score) + rbase;
+                        const uint64_t* ke = (from_ties ? s_temb : s_remb) + rbase * EW;
                         // sorted(..., reverse=True)[:k] is stable: repeated FIRST argmax (social.py:137-156).
                         // In the rivalry fallback trust = familiarity = 0, so friends are the first entries.
                         unsigned chosen = 0, sel = 0;
@@ -404,7 +437,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
 #pragma unroll 1
                             for (int j = 0; j < n_rel; ++j) {
                                 if ((chosen >> j) & 1u) continue;
-                                const double key = friend_pass ? (from_ties ? __ldg(kt + j) + __ldg(kf + j) : 0.0) : __ldg(kr + j);
+                                const double key = friend_pass ? (from_ties ? kt[j] + kf[j] : 0.0) : kr[j];
                                 if (best < 0 || key > bk) {
                                     best = j;
                                     bk = key;
@@ -423,13 +456,13 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                                 continue;
                             }
                             const int j = (sel >> (4 * s)) & 15;
-                            const double trust = from_ties ? __ldg(kt + j) : 0.0;
-                            const double fam = from_ties ? __ldg(kf + j) : 0.0;
-                            const double riv = __ldg(kr + j);
+                            const double trust = from_ties ? kt[j] : 0.0;
+                            const double fam = from_ties ? kf[j] : 0.0;
+                            const double riv = kr[j];
                             uint64_t word = 0;
 #pragma unroll 1
                             for (int d = 0; d < o.embed_dim; ++d) {  // _embed_agent_id, social.py:236-242
-                                if ((d & 7) == 0) word = __ldg(ke + (size_t)j * EW + (d >> 3));
+                                if ((d & 7) == 0) word = ke[j * EW + (d >> 3)];
                                 dst[d] = __ldg(o.embed_lut + ((unsigned)(word >> (8 * (d & 7))) & 255u));
                             }
                             dst[o.embed_dim + 0] = (float)trust;
@@ -448,8 +481,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
 #pragma unroll
                                     for (int s = 0; s < 8; ++s) {
                                         const int j = (sel >> (4 * s)) & 15;
-                                        tv[s] = from_ties ? __ldg(kt + j) : 0.0;
-                                        rv[s] = __ldg(kr + j);
+                                        tv[s] = from_ties ? kt[j] : 0.0;
+                                        rv[s] = kr[j];
                                     }
                                     tsum = ((tv[0] + tv[1]) + (tv[2] + tv[3])) + ((tv[4] + tv[5]) + (tv[6] + tv[7]));
                                     rsum = ((rv[0] + rv[1]) + (rv[2] + rv[3])) + ((rv[4] + rv[5]) + (rv[6] + rv[7]));

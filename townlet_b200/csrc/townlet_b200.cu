@@ -68,6 +68,7 @@ struct KParams {
     int32_t chunk;         // entity form: agents per phase-A pass (<= 32)
     int32_t mode;          // 0 entity-list form with role-parallel warps, 1 dense shared-memory grid form,
                            // 2 entity-list form with one warp per CTA
+    int32_t off_social;    // role form: staged relation rows of a pass (4 x double + 2 x embed words per edge)
     int32_t tmpl_mask;     // entity form: bit m set = a tile template for 16-byte misalignment m floats exists
     int32_t tmpl_off[4];   // entity form: float offset of template m inside the template area
 };
@@ -989,6 +990,8 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         }
         kp.off_meta = off;
         off += round_up((int)sizeof(KpiAcc) * tpc, 16);
+        kp.off_social = off;
+        if (kp.mode == 0 && do_obs) off += chunk * b->max_edges * (4 * 8 + 2 * 8 * b->embed_words);
         kp.smem_bytes = off;
         if (off > max_smem) return set_error("observation staging does not fit in shared memory"), TL_ERR_UNSUPPORTED;
         kp.towns_per_cta = tpc;
