@@ -77,6 +77,12 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
         }
     }
 
+    if (do_obs) {  // shared copy of the byte -> float32 table of the id embedding
+        float* elut = reinterpret_cast<float*>(smem + p.off_social) +
+                      (size_t)chunk_cap * p.b.max_edges * (8 + 4 * p.b.embed_words);
+        for (int k = tid; k < 256; k += 32 * kRoleWarps) elut[k] = __ldg(o.embed_lut + k);
+    }
+
     // every warp: lane s holds the offsets of town t0 + s (s <= n_towns)
     int my_aoff = 0, my_eoff = 0, my_tick = 0;
     if (lane <= n_towns) {
@@ -368,6 +374,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                 double* s_score = s_riv + chunk_cap * K;
                 uint64_t* s_temb = reinterpret_cast<uint64_t*>(s_score + chunk_cap * K);
                 uint64_t* s_remb = s_temb + chunk_cap * K * EW;
+                const float* s_elut = reinterpret_cast<const float*>(s_remb + chunk_cap * K * EW);  // byte / 255.0f
                 if (do_obs) {
                     const size_t r0 = (size_t)c_begin * K;
                     const int n_rows = c_n * K;
@@ -459,11 +466,24 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                             const double trust = from_ties ? kt[j] : 0.0;
                             const double fam = from_ties ? kf[j] : 0.0;
                             const double riv = kr[j];
-                            uint64_t word = 0;
+                            if (o.embed_dim == 8) {  // _embed_agent_id, social.py:236-242; bytes via PRMT
+                                const uint64_t word = ke[j * EW];
+                                const unsigned lo = (unsigned)word, hi = (unsigned)(word >> 32);
+                                dst[0] = s_elut[__byte_perm(lo, 0, 0x4440)];
+                                dst[1] = s_elut[__byte_perm(lo, 0, 0x4441)];
+                                dst[2] = s_elut[__byte_perm(lo, 0, 0x4442)];
+                                dst[3] = s_elut[__byte_perm(lo, 0, 0x4443)];
+                                dst[4] = s_elut[__byte_perm(hi, 0, 0x4440)];
+                                dst[5] = s_elut[__byte_perm(hi, 0, 0x4441)];
+                                dst[6] = s_elut[__byte_perm(hi, 0, 0x4442)];
+                                dst[7] = s_elut[__byte_perm(hi, 0, 0x4443)];
+                            } else {
+                                uint64_t word = 0;
 #pragma unroll 1
-                            for (int d = 0; d < o.embed_dim; ++d) {  // _embed_agent_id, social.py:236-242
-                                if ((d & 7) == 0) word = ke[j * EW + (d >> 3)];
-                                dst[d] = __ldg(o.embed_lut + ((unsigned)(word >> (8 * (d & 7))) & 255u));
+                                for (int d = 0; d < o.embed_dim; ++d) {
+                                    if ((d & 7) == 0) word = ke[j * EW + (d >> 3)];
+                                    dst[d] = s_elut[(unsigned)(word >> (8 * (d & 7))) & 255u];
+                                }
                             }
                             dst[o.embed_dim + 0] = (float)trust;
                             dst[o.embed_dim + 1] = (float)fam;
@@ -603,21 +623,39 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                             if (is_res) mrow_g[3 * W2 + tile] = 1.0f;
                         }
                     };
-#pragma unroll
-                    for (int k = 0; k < kEntCache; ++k)
-                        if (eb + 32 * k < ee) serve(wc[k], eb + 32 * k + lane);
+                    // towns of up to 32 entities (the common case) need one pass and one branch
+                    serve(wc[0], eb + lane);
+                    if (ee - eb > 32) {
+                        serve(wc[1], eb + 32 + lane);
+                        if (ee - eb > 64) {
+                            serve(wc[2], eb + 64 + lane);
+                            if (ee - eb > 96) {
+                                serve(wc[3], eb + 96 + lane);
 #pragma unroll 1
-                    for (int e0 = eb + 32 * kEntCache; e0 < ee; e0 += 32) {
-                        const int e = e0 + lane;
-                        serve(e < ee ? __ldg(p.b.ent + e) : 0u, e);
+                                for (int e0 = eb + 32 * kEntCache; e0 < ee; e0 += 32) {
+                                    const int e = e0 + lane;
+                                    serve(e < ee ? __ldg(p.b.ent + e) : 0u, e);
+                                }
+                            }
+                        }
                     }
-                    n_ag = __reduce_add_sync(FULL, n_ag);
-                    n_obj = __reduce_add_sync(FULL, n_obj);
-                    n_res = __reduce_add_sync(FULL, n_res);
-                    centre_has = __reduce_max_sync(FULL, centre_has);
+                    // three warp reductions: packed counts (agents | objects << 10 | reserved << 20, each
+                    // below 1024 because a window holds fewer than 1024 entities), centre flag, nearest
+                    int counts, centre;
+                    if (ee - eb < 1024) {
+                        counts = __reduce_add_sync(FULL, n_ag | (n_obj << 10) | (n_res << 20));
+                        n_ag = counts & 1023;
+                        n_obj = (counts >> 10) & 1023;
+                        n_res = (counts >> 20) & 1023;
+                    } else {
+                        n_ag = __reduce_add_sync(FULL, n_ag);
+                        n_obj = __reduce_add_sync(FULL, n_obj);
+                        n_res = __reduce_add_sync(FULL, n_res);
+                    }
+                    centre = __reduce_or_sync(FULL, (unsigned)centre_has);
                     nearest = __reduce_min_sync(FULL, nearest);
                     if (lane == i) {
-                        my_others = n_ag - centre_has;  // self excluded on the centre tile only
+                        my_others = n_ag - centre;  // self excluded on the centre tile only
                         my_objs = n_obj;
                         my_res = n_res;
                         my_d2 = nearest == 0xffffffffu ? 0 : (int)nearest;

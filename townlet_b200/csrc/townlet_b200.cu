@@ -991,7 +991,7 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         kp.off_meta = off;
         off += round_up((int)sizeof(KpiAcc) * tpc, 16);
         kp.off_social = off;
-        if (kp.mode == 0 && do_obs) off += chunk * b->max_edges * (4 * 8 + 2 * 8 * b->embed_words);
+        if (kp.mode == 0 && do_obs) off += chunk * b->max_edges * (4 * 8 + 2 * 8 * b->embed_words) + 256 * 4;
         kp.smem_bytes = off;
         if (off > max_smem) return set_error("observation staging does not fit in shared memory"), TL_ERR_UNSUPPORTED;
         kp.towns_per_cta = tpc;
