@@ -306,10 +306,13 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                             double north = 0.0, south = 0.0, east = 0.0, west = 0.0;
                             if (hd2 > 0) {
                                 const double dn = (double)(abs(hdx) + abs(hdy));
-                                north = fmax(0.0, (double)-hdy) / dn;
-                                south = fmax(0.0, (double)hdy) / dn;
-                                east = fmax(0.0, (double)hdx) / dn;
-                                west = fmax(0.0, (double)-hdx) / dn;
+                                // max(0, -dy)/norm etc.: one of each opposite pair is exactly 0.0, so two
+                                // IEEE divisions give the four values
+                                const double ns = (double)abs(hdy) / dn, ew = (double)abs(hdx) / dn;
+                                north = hdy < 0 ? ns : 0.0;
+                                south = hdy > 0 ? ns : 0.0;
+                                east = hdx > 0 ? ew : 0.0;
+                                west = hdx < 0 ? ew : 0.0;
                             }
                             f[TL_FEAT_PATH_NORTH + 0] = (float)north;
                             f[TL_FEAT_PATH_NORTH + 1] = (float)south;
@@ -548,16 +551,14 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                     const int nvec = (map_elems - head) >> 2;
                     float4* g4 = reinterpret_cast<float4*>(mrow_g + head);
                     if (kStatic && VARIANT == TL_VARIANT_HYBRID && map_mis == 0) {
-                        // all zeros except the self cell (flat float centre_tile)
+                        // all zeros except the self cell: flat float centre_tile (60 for W = 11) sits in
+                        // float4 number 15, component 0, which lane 15 writes in its first store
+                        static_assert(!kStatic || VARIANT != TL_VARIANT_HYBRID || (((WT / 2) * WT + WT / 2) & 3) == 0, "self cell component");
+                        const float self0 = (lane == (centre_tile >> 2)) ? 1.0f : 0.0f;
 #pragma unroll
                         for (int k = 0; k < (kMapElems / 4 + 31) / 32; ++k) {
                             const int v = lane + 32 * k;
-                            const bool c4 = (v == (centre_tile >> 2));
-                            if (v < kMapElems / 4)
-                                g4[v] = make_float4((c4 && (centre_tile & 3) == 0) ? 1.0f : 0.0f,
-                                                    (c4 && (centre_tile & 3) == 1) ? 1.0f : 0.0f,
-                                                    (c4 && (centre_tile & 3) == 2) ? 1.0f : 0.0f,
-                                                    (c4 && (centre_tile & 3) == 3) ? 1.0f : 0.0f);
+                            if (v < kMapElems / 4) g4[v] = make_float4(k == 0 ? self0 : 0.0f, 0.0f, 0.0f, 0.0f);
                         }
                     } else {
                         const float* t = s_tmpl + p.tmpl_off[map_mis] + map_mis;
@@ -697,15 +698,15 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
             if (lane < n_towns) {
                 const KpiAcc k = s_kpi[lane];
                 float* dst = p.ro.kpi + (size_t)it * p.ro.kpi_tick_stride + (size_t)(t0 + lane) * TL_N_KPI;
-                const double n = (double)k.count;
+                const double inv = k.count ? 1.0 / (double)k.count : 0.0;  // one division for the three means
                 dst[TL_KPI_REWARD_SUM] = (float)k.rsum;
                 dst[TL_KPI_REWARD_SUMSQ] = (float)k.rsq;
                 dst[TL_KPI_HUNGER_MIN] = k.count ? (float)k.hmin : 0.0f;
-                dst[TL_KPI_HUNGER_MEAN] = k.count ? (float)(k.hsum / n) : 0.0f;
+                dst[TL_KPI_HUNGER_MEAN] = (float)(k.hsum * inv);
                 dst[TL_KPI_STARVING] = (float)k.starving;
                 dst[TL_KPI_TERMINATED] = (float)k.term;
-                dst[TL_KPI_LATENESS_MEAN] = k.count ? (float)(k.late / n) : 0.0f;
-                dst[TL_KPI_WALLET_MEAN] = k.count ? (float)(k.wallet / n) : 0.0f;
+                dst[TL_KPI_LATENESS_MEAN] = (float)(k.late * inv);
+                dst[TL_KPI_WALLET_MEAN] = (float)(k.wallet * inv);
             }
             __syncwarp();
         }
