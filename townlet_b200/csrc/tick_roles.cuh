@@ -20,10 +20,14 @@
 // coalesced 16-byte sweep done by all four warps.  See tick_ent.cuh for the
 // single-warp form this was derived from (kept for very small launches).
 
-constexpr int kRoleWarps = 4;
+#ifndef TL_TILE_WARPS
+#define TL_TILE_WARPS 2
+#endif
+constexpr int kTileWarps = TL_TILE_WARPS;  // warps in the tiles role
+constexpr int kRoleWarps = 2 + kTileWarps;
 
 template <int VARIANT, int WT>
-__global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick_kernel_roles(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);  // [2][chunk * F + 4]
     float* s_tmpl = reinterpret_cast<float*>(smem + p.off_map);
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                 int my_others = 0, my_objs = 0, my_res = 0, my_d2 = 0;
                 float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)(c_begin + parity) * map_elems;
 #pragma unroll 1
-                for (int i = parity; i < c_n; i += 2, mrow_g += 2 * map_elems) {
+                for (int i = parity; i < c_n; i += kTileWarps, mrow_g += kTileWarps * map_elems) {
                     const int32_t pwi = __shfl_sync(FULL, pw, i);
                     const int cxi = pos_x(pwi), cyi = pos_y(pwi);
                     const int eb = __shfl_sync(FULL, town_ebeg, i), ee = __shfl_sync(FULL, town_eend, i);
@@ -582,10 +586,12 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                     // ---- patches: one entity per lane (cache.py:16-41 + map.py:80-125) ----
                     int n_ag = 0, n_obj = 0, n_res = 0, centre_has = 0;
                     unsigned nearest = 0xffffffffu;
-                    auto serve = [&](uint32_t w, int e) {
+                    auto serve = [&](uint32_t w, int e, bool may_skip) {
                         const bool valid = e < ee;
                         const int dx = TL_ENT_X(w) - cxi, dy = TL_ENT_Y(w) - cyi;
                         const bool inwin = valid && (unsigned)(dx + R) <= (unsigned)(2 * R) && (unsigned)(dy + R) <= (unsigned)(2 * R);
+                        // later passes of a large town rarely touch the window: one vote skips the rest
+                        if (may_skip && !__any_sync(FULL, inwin)) return;
                         const int tile = (dy + R) * W + (dx + R);
                         const unsigned kind = TL_ENT_KIND(w);
                         const bool is_agent = inwin && kind == TL_KIND_AGENT;
@@ -625,17 +631,17 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                         }
                     };
                     // towns of up to 32 entities (the common case) need one pass and one branch
-                    serve(wc[0], eb + lane);
+                    serve(wc[0], eb + lane, false);
                     if (ee - eb > 32) {
-                        serve(wc[1], eb + 32 + lane);
+                        serve(wc[1], eb + 32 + lane, true);
                         if (ee - eb > 64) {
-                            serve(wc[2], eb + 64 + lane);
+                            serve(wc[2], eb + 64 + lane, true);
                             if (ee - eb > 96) {
-                                serve(wc[3], eb + 96 + lane);
+                                serve(wc[3], eb + 96 + lane, true);
 #pragma unroll 1
                                 for (int e0 = eb + 32 * kEntCache; e0 < ee; e0 += 32) {
                                     const int e = e0 + lane;
-                                    serve(e < ee ? __ldg(p.b.ent + e) : 0u, e);
+                                    serve(e < ee ? __ldg(p.b.ent + e) : 0u, e, true);
                                 }
                             }
                         }
@@ -663,7 +669,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 4) tick_kernel_roles(const __
                     }
                 }
                 // local summary features, thread-per-agent (features.py:289-330 via the host LUTs)
-                if (active && (lane & 1) == parity) {
+                if (active && (lane % kTileWarps) == parity) {
                     float* frow = feat_s0 + lane * F;
                     frow[TL_FEAT_AGENT_RATIO] = __ldg(o.agent_ratio_lut + min(my_others, W2 - 1));
                     frow[TL_FEAT_OBJECT_RATIO] = __ldg(o.tile_ratio_lut + min(my_objs, W2));
