@@ -286,7 +286,10 @@ def main() -> None:
     traffic_file = ROOT / "profiles" / "traffic.json"
     if traffic_file.exists():
         try:
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get(args.workload)
+            t = json.loads(traffic_file.read_text()).get(args.workload)
+            if t:  # ncu dram__bytes_read.sum + dram__bytes_write.sum per agent-step x agent-steps of one launch
+                roofline["traffic"] = t["dram_bytes_per_agent_step"] * n_agents * tpl
+                roofline["traffic_source"] = "profiles/traffic.json (ncu --set full, bytes per agent-step x agent-steps per launch)"
         except Exception:
             pass
 

@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(32, 16) tick_kernel_ent(const __grid_constant_
                     slot_idx = __ldg(p.b.slot + a);
                     last_hash = __ldg(p.b.last_action_hash + a);
                     pw = __ldg(p.b.pos + a);
-                    n_riv = __ldg(p.b.riv_count + a);
-                    n_t = __ldg(p.b.tie_count + a);
+                    n_riv = min((int)__ldg(p.b.riv_count + a), p.b.max_edges);  // counts are clamped to the row stride
+                    n_t = min((int)__ldg(p.b.tie_count + a), p.b.max_edges);
                 }
 
                 const unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;

@@ -410,8 +410,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 if (active && do_obs) {
                     float* f = feat_s0 + lane * F;
                     const int rbase = lane * K;  // row of this agent inside the staged block
-                    const int n_riv = __ldg(p.b.riv_count + a);
-                    const int n_t = __ldg(p.b.tie_count + a);
+                    const int n_riv = min((int)__ldg(p.b.riv_count + a), K);  // counts are clamped to the row stride
+                    const int n_t = min((int)__ldg(p.b.tie_count + a), K);
                     {  // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
                         const int nr = min(n_riv, o.rivalry_max_edges);
                         int avoid = 0;

@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
 #pragma unroll
                 for (int s = 1; s < kMaxTownsPerCta; ++s)
                     if (s < n_towns && e >= s_town[s].ent_begin) slot = s;
+                if (TL_ENT_X(w) >= GW || TL_ENT_Y(w) >= GH) continue;  // outside the declared grid: ignored, never out of bounds
                 const int idx = slot * p.grid_tiles + TL_ENT_Y(w) * GW + TL_ENT_X(w);
                 const unsigned kind = TL_ENT_KIND(w);
                 uint32_t* word = reinterpret_cast<uint32_t*>(s_grid) + (idx >> 1);
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
                     // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
                     {
                         const int K = p.b.max_edges;
-                        int nr = p.b.riv_count[a];
+                        int nr = min((int)p.b.riv_count[a], K);
                         nr = min(nr, o.rivalry_max_edges);
                         double mx = 0.0;
                         int avoid = 0;
@@ -625,7 +626,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
 
                 // -- prefetch the relation rows (social.py:165-209): lane j holds relation j
                 const int K = p.b.max_edges, EW = p.b.embed_words;
-                const int n_ties = p.b.tie_count[a];
+                const int n_ties = min((int)p.b.tie_count[a], p.b.max_edges);
                 int n_rel = n_ties;
                 int source = (n_ties > 0 && o.social_base >= 0) ? 1 : 0;
                 double trust = 0.0, fam = 0.0, riv = 0.0;
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
                             emb = p.b.tie_embed + r * EW;
                         }
                     } else {
-                        n_rel = min((int)p.b.riv_count[a], o.top_rivals);  // rivalry_top(agent, top_rivals)
+                        n_rel = min(min((int)p.b.riv_count[a], K), o.top_rivals);  // rivalry_top(agent, top_rivals)
                         source = n_rel > 0 ? 2 : 0;
                         if (lane < n_rel) {
                             const size_t r = (size_t)a * K + lane;
