@@ -37,6 +37,9 @@ WORKLOADS = {
                     name="configs[2]: full, 16,384 towns x 48x48 x 10 agents"),
     "c4": dict(variant="hybrid", towns=4096, grid=128, agents=64, bytes_per_agent_step=2712,
                name="configs[3]: hybrid, 4,096 towns x 128x128 x 64 agents"),
+    # configs[4] per GPU: 65,536 towns over 8 GPUs = 8,192 towns per rank, policy forward in the loop
+    "c5": dict(variant="hybrid", towns=8192, grid=48, agents=8, bytes_per_agent_step=2712, policy=True,
+               name="configs[4]: PPO rollout capture, 8,192 towns per GPU x 48x48 x 8 agents, policy forward in-loop"),
 }
 L2_BYTES = 126 * 1024 * 1024
 DISTINCT_TOWNS = 256  # towns generated on the host; larger batches tile them
@@ -223,9 +226,26 @@ def main() -> None:
     out_bytes_per_tick = n_agents * (obs.map_elems + obs.n_features + 1) * 4
     ring = max(tpl, -(-2 * L2_BYTES // out_bytes_per_tick))  # ring of tick slots > 2 x L2
     ring = -(-ring // tpl) * tpl
+    if wl.get("policy"):
+        ring = tpl  # a rollout buffer of tpl ticks, consumed by the policy every tick
     out = dev.alloc_outputs(capi.TL_PHASE_ALL, ring, summary=False, comps=False, kpi=True)
 
+    capture = None
+    if wl.get("policy"):
+        # rollout capture: one tick launch + one batched policy forward per tick, GAE scan and KPI
+        # all-reduce at the end of every rollout of `tpl` ticks (townlet_b200/rollout.py)
+        from townlet_b200.rollout import PolicyMLP, RolloutCapture
+
+        torch.manual_seed(1234 + rank)
+        capture = RolloutCapture(dev, PolicyMLP(obs.n_features, obs.map_shape, action_dim=9))
+
     def launch(i: int) -> None:
+        if capture is not None:
+            ro = capture.capture(tpl, out)
+            totals = ro.kpi.sum(dim=(0, 1)).double()
+            if world > 1:
+                dist.all_reduce(totals, op=dist.ReduceOp.SUM)
+            return
         dev.tick(out, capi.TL_PHASE_ALL, tpl, tick0=(i * tpl) % ring)
 
     for i in range(-(-warm // tpl)):
@@ -278,7 +298,7 @@ def main() -> None:
         "unit": "GB/s",
         "frac": achieved / peak,
         "traffic": None,
-        "kernel": f"tick_kernel_roles<{wl['variant']}>",
+        "kernel": f"tick_kernel_roles<{wl['variant']}>" + (" + batched policy forward + gae_kernel" if wl.get("policy") else ""),
         "algorithmic_bytes_per_launch": algo_bytes,
         "avg_launch_ms": avg_launch_s * 1e3,
         "peak_source": peak_src,

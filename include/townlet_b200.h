@@ -359,6 +359,14 @@ int tl_tick(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardPara
 /* Number of kernels launched by this library since load (the bench reports it). */
 int64_t tl_launch_count(void);
 
+/* Generalised advantage estimation over a device rollout (replaces the
+ * Python double loop of compute_gae, src/townlet/policy/backends/pytorch/ppo_utils.py:55-67).
+ * Layout is time-major as the tick kernels write it: rewards[T][N], dones[T][N] (1.0 = episode ended),
+ * values[T + (bootstrap ? 1 : 0)][N]; outputs advantages[T][N], returns[T][N].  float32 arithmetic in
+ * the reference's operation order.  Device pointers, asynchronous on the stream. */
+int tl_gae(const float* rewards, const float* values, const float* dones, float* advantages, float* returns,
+           int32_t n_steps, int32_t n_agents, int32_t bootstrap, double gamma, double gae_lambda, tl_stream_t stream);
+
 /* Host-buffer entry: every pointer (batch, LUTs, outputs) is HOST memory.
  * Copies the batch to the context's device arena, runs tl_tick, copies the
  * requested outputs and the mutated state back, and synchronises. */

@@ -50,6 +50,26 @@ def load() -> C.CDLL:
     return _lib
 
 
+def oracle_gae(rewards: np.ndarray, values: np.ndarray, dones: np.ndarray, gamma: float, gae_lambda: float):
+    """GAE on time-major float32 arrays ``[T, N]`` (values ``[T or T+1, N]``); returns (advantages, returns)."""
+    lib = load()
+    lib.tlo_gae.restype = C.c_int
+    lib.tlo_gae.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double]
+    rewards = np.ascontiguousarray(rewards, dtype=np.float32)
+    values = np.ascontiguousarray(values, dtype=np.float32)
+    dones = np.ascontiguousarray(dones, dtype=np.float32)
+    steps, agents = rewards.shape
+    adv = np.zeros_like(rewards)
+    ret = np.zeros_like(rewards)
+    status = lib.tlo_gae(
+        rewards.ctypes.data, values.ctypes.data, dones.ctypes.data, adv.ctypes.data, ret.ctypes.data,
+        steps, agents, int(values.shape[0] == steps + 1), gamma, gae_lambda,
+    )
+    if status != 0:
+        raise RuntimeError(f"oracle tlo_gae failed with {status}")
+    return adv, ret
+
+
 def oracle_tick(
     batch: TownBatch,
     obs: ObsSpec | None,

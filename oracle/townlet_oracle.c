@@ -722,4 +722,31 @@ int tlo_tick(const TlTownBatch* b, const TlObsParams* p, const TlRewardParams* r
     return status;
 }
 
+/* compute_gae, policy/backends/pytorch/ppo_utils.py:19-67, on the time-major layout of the rollout
+ * (the reference indexes [batch, t]; here [t][agent]).  float32 like the reference's tensors; the Python
+ * float scalars gamma and gamma * gae_lambda enter float32 tensor ops rounded to float32. */
+int tlo_gae(const float* rewards, const float* values, const float* dones, float* advantages, float* returns,
+            int32_t n_steps, int32_t n_agents, int32_t bootstrap, double gamma, double gae_lambda) {
+    if (!rewards || !values || !dones || !advantages || !returns || n_steps < 0 || n_agents < 0) return TL_ERR_ARG;
+    const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
+    for (int b = 0; b < n_agents; ++b) {
+        volatile float gae = 0.0f; /* volatile: keep every intermediate rounded to float32 */
+        for (int t = n_steps - 1; t >= 0; --t) {
+            size_t i = (size_t)t * (size_t)n_agents + (size_t)b;
+            volatile float mask = 1.0f - dones[i];
+            float next_value = bootstrap ? values[(size_t)(t + 1) * (size_t)n_agents + (size_t)b] : values[i];
+            volatile float t1 = g * next_value;
+            volatile float t2 = t1 * mask;
+            volatile float t3 = rewards[i] + t2;
+            volatile float delta = t3 - values[i];
+            volatile float c1 = gl * mask;
+            volatile float c2 = c1 * gae;
+            gae = delta + c2;
+            advantages[i] = gae;
+            returns[i] = gae + values[i];
+        }
+    }
+    return TL_OK;
+}
+
 int tlo_abi_version(void) { return TL_ABI_VERSION; }

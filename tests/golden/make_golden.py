@@ -603,14 +603,39 @@ def reward_cases():
     print(f"  reward_social_events: {n_ticks} ticks x {N} agents")
 
 
+def gae_case():
+    """compute_gae (policy/backends/pytorch/ppo_utils.py:19-67) on random float32 rollouts, both value layouts."""
+    import torch
+
+    from townlet.policy.backends.pytorch.ppo_utils import compute_gae
+
+    rng = np.random.default_rng(4321)
+    out = {}
+    for name, (batch, steps, bootstrap) in {"boot": (37, 19, True), "noboot": (5, 64, False), "one": (3, 1, True)}.items():
+        rewards = rng.uniform(-0.2, 0.2, size=(batch, steps)).astype(np.float32)
+        values = rng.normal(0.0, 0.5, size=(batch, steps + (1 if bootstrap else 0))).astype(np.float32)
+        dones = (rng.random((batch, steps)) < 0.15).astype(np.float32)
+        res = compute_gae(torch.from_numpy(rewards), torch.from_numpy(values), torch.from_numpy(dones), gamma=0.99, gae_lambda=0.95)
+        for key, arr in (("rewards", rewards), ("values", values), ("dones", dones), ("advantages", res.advantages.numpy()), ("returns", res.returns.numpy())):
+            out[f"{name}_{key}"] = arr
+    (GOLDEN_DIR / "gae").mkdir(exist_ok=True)
+    np.savez_compressed(GOLDEN_DIR / "gae" / "ref_gae.npz", gamma=0.99, gae_lambda=0.95, **out)
+    print("  gae/ref_gae: compute_gae on 3 random rollouts (batch-major arrays as the reference takes them)")
+
+
 def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
+    if os.environ.get("TL_GOLDEN_ONLY") == "gae":
+        gae_case()
+        shutil.rmtree(WORK, ignore_errors=True)
+        return
     baselines()
     social_snippet()
     builder_cases()
     crowded_cases()
     synth_cases()
     reward_cases()
+    gae_case()
     shutil.rmtree(WORK, ignore_errors=True)
 
 

@@ -1,0 +1,79 @@
+"""GAE scan: the C oracle against the reference's compute_gae golden (CPU), the kernel against the oracle (GPU)."""
+
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle.oracle import oracle_gae
+
+GOLD = Path(__file__).resolve().parent / "golden" / "gae" / "ref_gae.npz"
+
+
+@pytest.mark.parametrize("name", ["boot", "noboot", "one"])
+def test_oracle_gae_matches_reference_compute_gae(name) -> None:
+    d = np.load(GOLD)
+    adv, ret = oracle_gae(d[f"{name}_rewards"].T, d[f"{name}_values"].T, d[f"{name}_dones"].T, float(d["gamma"]), float(d["gae_lambda"]))
+    assert np.array_equal(adv.T, d[f"{name}_advantages"])  # bit-exact float32
+    assert np.array_equal(ret.T, d[f"{name}_returns"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("steps,agents,bootstrap", [(19, 37, True), (64, 5, False), (1, 3, True), (128, 8192, True)])
+def test_gae_kernel_matches_oracle(steps, agents, bootstrap) -> None:
+    import torch
+
+    from townlet_b200.rollout import gae
+
+    rng = np.random.default_rng(steps * 1000 + agents)
+    rewards = rng.uniform(-0.2, 0.2, size=(steps, agents)).astype(np.float32)
+    values = rng.normal(0.0, 0.5, size=(steps + int(bootstrap), agents)).astype(np.float32)
+    dones = (rng.random((steps, agents)) < 0.1).astype(np.float32)
+    adv, ret = gae(torch.from_numpy(rewards).cuda(), torch.from_numpy(values).cuda(), torch.from_numpy(dones).cuda(), 0.99, 0.95)
+    ref_adv, ref_ret = oracle_gae(rewards, values, dones, 0.99, 0.95)
+    assert np.array_equal(adv.cpu().numpy(), ref_adv)
+    assert np.array_equal(ret.cpu().numpy(), ref_ret)
+
+
+@pytest.mark.gpu
+def test_reference_gae_golden_through_the_kernel() -> None:
+    import torch
+
+    from townlet_b200.rollout import gae
+
+    d = np.load(GOLD)
+    for name in ("boot", "noboot", "one"):
+        t = lambda k: torch.from_numpy(np.ascontiguousarray(d[f"{name}_{k}"].T)).cuda()  # noqa: E731
+        adv, ret = gae(t("rewards"), t("values"), t("dones"), float(d["gamma"]), float(d["gae_lambda"]))
+        assert np.array_equal(adv.cpu().numpy().T, d[f"{name}_advantages"])
+        assert np.array_equal(ret.cpu().numpy().T, d[f"{name}_returns"])
+
+
+@pytest.mark.gpu
+def test_rollout_capture_matches_tick_by_tick_oracle() -> None:
+    import torch
+
+    from oracle.oracle import oracle_tick
+    from townlet_b200 import capi
+    from townlet_b200.engine import DeviceTownBatch
+    from townlet_b200.params import ObsSpec, RewardSpec
+    from townlet_b200.rollout import PolicyMLP, RolloutCapture
+    from townlet_b200.synth import synth_batch
+
+    obs, rew = ObsSpec(), RewardSpec(fuse_faint=True)
+    batch = synth_batch(24, 48, 8, obs)
+    ref_batch = batch.copy()
+    dev = DeviceTownBatch(batch, obs, rew)
+    torch.manual_seed(0)
+    policy = PolicyMLP(obs.n_features, obs.map_shape, action_dim=9)
+    ro = RolloutCapture(dev, policy, autocast_dtype=None).capture(5)
+    ref = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_ALL, 5)
+    assert np.array_equal(ro.map.cpu().numpy(), ref["map"])
+    assert np.array_equal(ro.features.cpu().numpy().view(np.uint32), ref["features"].view(np.uint32))
+    np.testing.assert_allclose(ro.rewards.cpu().numpy(), ref["reward"], rtol=1e-6, atol=1e-9)
+    assert np.array_equal(ro.dones.cpu().numpy(), ref["terminated"].astype(np.float32))
+    assert ro.values.shape == (6, batch.n_agents) and ro.actions.shape == (5, batch.n_agents)
+    ref_adv, ref_ret = oracle_gae(ro.rewards.cpu().numpy(), ro.values.cpu().numpy(), ro.dones.cpu().numpy(), 0.99, 0.95)
+    assert np.array_equal(ro.advantages.cpu().numpy(), ref_adv) and np.array_equal(ro.returns.cpu().numpy(), ref_ret)

@@ -227,6 +227,7 @@ EXPORTED_SYMBOLS = (
     "tl_decay_reward",
     "tl_tick",
     "tl_launch_count",
+    "tl_gae",
     "tl_context_create",
     "tl_context_destroy",
     "tl_host_tick",
@@ -319,6 +320,8 @@ def load_library() -> C.CDLL:
         C.c_int32,
         _p,
     ]
+    lib.tl_gae.restype = C.c_int
+    lib.tl_gae.argtypes = [_p, _p, _p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, _p]
     lib.tl_context_create.restype = _p
     lib.tl_context_create.argtypes = [C.c_int]
     lib.tl_context_destroy.restype = None

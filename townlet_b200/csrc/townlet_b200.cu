@@ -842,6 +842,30 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
 #include "tick_ent.cuh"
 #include "tick_roles.cuh"
 
+// Backward GAE scan, one thread per agent, coalesced over the agent axis of the time-major rollout
+// (reference: compute_gae, src/townlet/policy/backends/pytorch/ppo_utils.py:55-67).  float32 arithmetic
+// in the reference's operation order; built without FMA contraction (-fmad=false).
+__global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                                                  const float* __restrict__ dones, float* __restrict__ advantages,
+                                                  float* __restrict__ returns, int n_steps, int n_agents, int bootstrap,
+                                                  float gamma, float gamma_lambda) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n_agents) return;
+    float gae = 0.0f;
+    float next_value = bootstrap ? values[(size_t)n_steps * n_agents + a] : 0.0f;
+    for (int t = n_steps - 1; t >= 0; --t) {
+        const size_t i = (size_t)t * n_agents + a;
+        const float v = values[i];
+        const float mask = 1.0f - dones[i];
+        const float nv = bootstrap ? next_value : v;  // without a bootstrap row the reference reuses value[t]
+        const float delta = rewards[i] + gamma * nv * mask - v;
+        gae = delta + gamma_lambda * mask * gae;
+        advantages[i] = gae;
+        returns[i] = gae + v;
+        next_value = v;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
@@ -1105,6 +1129,21 @@ int tl_device_sm_count(void) {
 }
 
 int64_t tl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int tl_gae(const float* rewards, const float* values, const float* dones, float* advantages, float* returns,
+           int32_t n_steps, int32_t n_agents, int32_t bootstrap, double gamma, double gae_lambda, tl_stream_t stream) {
+    if (!rewards || !values || !dones || !advantages || !returns) return set_error("tl_gae: NULL pointer"), TL_ERR_ARG;
+    if (n_steps < 0 || n_agents < 0) return set_error("tl_gae: negative size"), TL_ERR_ARG;
+    if (n_steps == 0 || n_agents == 0) return TL_OK;
+    // the reference multiplies float32 tensors by Python floats: the scalars gamma and
+    // gamma * gae_lambda (a float64 product) are rounded to float32 once
+    const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
+    gae_kernel<<<(n_agents + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, advantages, returns, n_steps,
+                                                                        n_agents, bootstrap ? 1 : 0, g, gl);
+    if (!cuda_ok(cudaGetLastError(), "gae kernel launch")) return TL_ERR_CUDA;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return TL_OK;
+}
 
 int tl_obs_build(const TlTownBatch* batch, const TlObsParams* obs, const TlObsOut* out, tl_stream_t stream) {
     return launch(batch, obs, nullptr, out, nullptr, TL_PHASE_OBS, 1, (cudaStream_t)stream, 0);

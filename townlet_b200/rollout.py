@@ -1,0 +1,122 @@
+"""Device-resident rollout capture: tick kernels + batched in-loop policy forward + GAE scan.
+
+The step immediately downstream of the hot path.  The reference converts every
+observation tensor to nested Python lists (world/dto/factory.py:231-235), re-stacks them per agent
+(policy/replay.py:550-636), runs one batch-size-1 forward per agent per tick (policy/runner.py:444-488) and
+computes GAE with a Python double loop (policy/backends/pytorch/ppo_utils.py:55-67).  Here the tick kernel
+writes straight into ``[T, N, ...]`` rollout tensors, the policy runs once per tick over all agents of all
+towns (plain torch modules -> cuBLAS; the network is not part of the hot path), and GAE is one scan kernel.
+
+Action application (movement, queueing) is upstream of the path and stays with the caller; sampled actions
+are recorded, not applied.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+from torch import nn
+
+from . import capi
+from .engine import DeviceTownBatch, TickOutputs, _stream_ptr
+
+
+class PolicyMLP(nn.Module):
+    """Same architecture as ``ConflictAwarePolicyNetwork`` (src/townlet/policy/models.py:36-69):
+    flattened-map and feature encoders (Linear + ReLU), a shared Linear + ReLU, policy and value heads."""
+
+    def __init__(self, feature_dim: int, map_shape: tuple[int, int, int], action_dim: int, hidden_dim: int = 256) -> None:
+        super().__init__()
+        flat_map = map_shape[0] * map_shape[1] * map_shape[2]
+        self.map_encoder = nn.Sequential(nn.Flatten(), nn.Linear(flat_map, hidden_dim), nn.ReLU())
+        self.feature_encoder = nn.Sequential(nn.Linear(feature_dim, hidden_dim), nn.ReLU())
+        self.shared = nn.Sequential(nn.Linear(hidden_dim * 2, hidden_dim), nn.ReLU())
+        self.policy_head = nn.Linear(hidden_dim, action_dim)
+        self.value_head = nn.Linear(hidden_dim, 1)
+
+    def forward(self, map_tensor: torch.Tensor, features: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        hidden = torch.cat([self.map_encoder(map_tensor), self.feature_encoder(features)], dim=-1)
+        hidden = self.shared(hidden)
+        return self.policy_head(hidden), self.value_head(hidden).squeeze(-1)
+
+
+def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, gamma: float, gae_lambda: float):
+    """``compute_gae`` on time-major CUDA tensors ``[T, N]`` (``values`` ``[T, N]`` or ``[T + 1, N]``)."""
+    if rewards.ndim != 2 or dones.ndim != 2:
+        raise ValueError("Rewards and dones must be 2D tensors (timesteps, agents)")
+    steps, agents = rewards.shape
+    if values.ndim != 2 or values.shape[0] not in (steps, steps + 1) or values.shape[1] != agents:
+        raise ValueError("values must align with rewards (same length) or provide a bootstrap row")
+    if not rewards.is_cuda:
+        raise capi.TownletB200Error("townlet_b200.rollout.gae runs on CUDA tensors only (no CPU fallback)")
+    rewards, values, dones = (t.contiguous().float() for t in (rewards, values, dones))
+    advantages = torch.empty_like(rewards)
+    returns = torch.empty_like(rewards)
+    lib = capi.load_library()
+    with torch.cuda.device(rewards.device):
+        status = lib.tl_gae(
+            rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), advantages.data_ptr(), returns.data_ptr(),
+            steps, agents, int(values.shape[0] == steps + 1), float(gamma), float(gae_lambda), _stream_ptr(rewards.device),
+        )
+    capi.check(status)
+    return advantages, returns
+
+
+@dataclass
+class Rollout:
+    """``[T, N, ...]`` tensors of one capture, all on the device."""
+
+    map: torch.Tensor
+    features: torch.Tensor
+    rewards: torch.Tensor
+    dones: torch.Tensor
+    values: torch.Tensor  # [T + 1, N], last row = bootstrap value of the final observation
+    actions: torch.Tensor
+    log_probs: torch.Tensor
+    advantages: torch.Tensor
+    returns: torch.Tensor
+    kpi: torch.Tensor  # [T, towns, 8]
+
+
+class RolloutCapture:
+    """Collect ``n_ticks`` ticks of every agent of a device batch with the policy in the loop."""
+
+    def __init__(self, dev: DeviceTownBatch, policy: nn.Module, gamma: float = 0.99, gae_lambda: float = 0.95,
+                 autocast_dtype: torch.dtype | None = torch.bfloat16) -> None:
+        assert dev.obs is not None and dev.rew is not None
+        self.dev = dev
+        self.policy = policy.to(dev.device).eval()
+        self.gamma, self.gae_lambda = gamma, gae_lambda
+        self.autocast_dtype = autocast_dtype
+
+    @torch.no_grad()
+    def _forward(self, map_t: torch.Tensor, feat_t: torch.Tensor):
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                logits, value = self.policy(map_t, feat_t)
+        else:
+            logits, value = self.policy(map_t, feat_t)
+        return logits.float(), value.float()
+
+    @torch.no_grad()
+    def capture(self, n_ticks: int, out: TickOutputs | None = None) -> Rollout:
+        dev = self.dev
+        n = dev.n_agents
+        out = out or dev.alloc_outputs(capi.TL_PHASE_ALL, n_ticks)
+        values = torch.empty((n_ticks + 1, n), dtype=torch.float32, device=dev.device)
+        actions = torch.empty((n_ticks, n), dtype=torch.int64, device=dev.device)
+        log_probs = torch.empty((n_ticks, n), dtype=torch.float32, device=dev.device)
+        for t in range(n_ticks):
+            dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)  # obs / reward / done of tick t land in slot t
+            logits, value = self._forward(out.map[t], out.features[t])
+            dist = torch.distributions.Categorical(logits=logits)
+            act = dist.sample()
+            actions[t], log_probs[t], values[t] = act, dist.log_prob(act), value
+        # bootstrap value: the policy on the last observation (no further tick is simulated)
+        values[n_ticks] = values[n_ticks - 1] if n_ticks else 0.0
+        dones = out.terminated[:n_ticks].float()
+        advantages, returns = gae(out.reward[:n_ticks], values, dones, self.gamma, self.gae_lambda)
+        return Rollout(out.map[:n_ticks], out.features[:n_ticks], out.reward[:n_ticks], dones, values, actions,
+                       log_probs, advantages, returns, out.kpi[:n_ticks])
