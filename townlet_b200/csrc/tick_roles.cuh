@@ -102,10 +102,12 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     int cached_eb = -1;
     uint32_t wc[kEntCache] = {0u, 0u, 0u, 0u};
     int pass = 0;
+    int slot = 0, town_abeg = 0, town_aend = 0, town_ebeg = 0, town_eend = 0, kpi_steps = 32;
     __syncthreads();
 
 #pragma unroll 1
     for (int it = 0; it < p.n_ticks; ++it) {
+        cached_eb = -1;  // every tick re-reads the entity words of its towns
         if (warp == 0) {
             if (do_advance && lane < n_towns) {  // core/sim_loop.py:635,659
                 my_tick += 1;
@@ -132,13 +134,20 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
 
             const bool active = lane < c_n;
             const int a = c_begin + (active ? lane : 0);
-            int slot = 0;
+            // town of this lane's agent; with a single pass per tick the answer is the same every tick
+            if (n_chunks > 1 || it == 0) {
+                slot = 0;
 #pragma unroll 1
-            for (int s = 1; s < n_towns; ++s) slot += (a >= __shfl_sync(FULL, my_aoff, s)) ? 1 : 0;
-            const int town_abeg = __shfl_sync(FULL, my_aoff, slot);
-            const int town_aend = __shfl_sync(FULL, my_aoff, slot + 1);
-            const int town_ebeg = __shfl_sync(FULL, my_eoff, slot);
-            const int town_eend = __shfl_sync(FULL, my_eoff, slot + 1);
+                for (int s = 1; s < n_towns; ++s) slot += (a >= __shfl_sync(FULL, my_aoff, s)) ? 1 : 0;
+                town_abeg = __shfl_sync(FULL, my_aoff, slot);
+                town_aend = __shfl_sync(FULL, my_aoff, slot + 1);
+                town_ebeg = __shfl_sync(FULL, my_eoff, slot);
+                town_eend = __shfl_sync(FULL, my_eoff, slot + 1);
+                // segmented KPI reduction needs offsets below the longest town segment of the pass only
+                const int seg_len = __reduce_max_sync(FULL, active ? min(town_aend, c_begin + c_n) - max(town_abeg, c_begin) : 1);
+                kpi_steps = 1;
+                while (kpi_steps < seg_len) kpi_steps <<= 1;
+            }
 
             if (warp == 0) {
                 // =================== role "state": one thread per agent ==================
@@ -338,8 +347,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                     int v_l = kpi_late;
                     // starving | terminated | count packed in 10-bit fields
                     int v_c = active ? ((need0 <= p.rew.starvation_threshold ? 1 : 0) | (terminated ? 1 << 10 : 0) | (1 << 20)) : 0;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll 1
+                    for (int off = 1; off < kpi_steps; off <<= 1) {
                         const int oseg = __shfl_down_sync(FULL, seg, off);
                         const double o_r = __shfl_down_sync(FULL, v_r, off), o_q = __shfl_down_sync(FULL, v_q, off);
                         const double o_h = __shfl_down_sync(FULL, v_h, off), o_m = __shfl_down_sync(FULL, v_m, off);
