@@ -603,6 +603,54 @@ def reward_cases():
     print(f"  reward_social_events: {n_ticks} ticks x {N} agents")
 
 
+def snapshot_cases():
+    """BASELINE configs[2]: parity on world states LOADED FROM SNAPSHOTS at ticks 10 / 25 / 50.
+
+    The shipped snapshot-{10,25,50}.json hold zero agents, so the same recipe
+    (tests/fixtures/baselines/capture_snapshots.py:16-57) is re-run on a populated loop: positioned objects,
+    eight spawned agents, `loop.step()` to the target tick, `snapshot_from_world` -> `SnapshotManager.save` ->
+    `SnapshotManager.load` -> `apply_snapshot_to_world` into a FRESH world, and the observation service runs on
+    that live restored state.
+    """
+    from townlet.snapshots import SnapshotManager, apply_snapshot_to_world, snapshot_from_world
+
+    objects = (
+        ("fridge_1", "fridge", (2, 2)), ("stove_1", "stove", (5, 2)), ("bed_1", "bed", (8, 3)), ("shower_1", "shower", (3, 7)),
+        ("fridge_2", "fridge", (10, 9)), ("stove_2", "stove", (12, 4)), ("bed_2", "bed", (6, 11)), ("shower_2", "shower", (14, 12)),
+    )
+    spawns = ((1, 1), (4, 4), (7, 2), (9, 6), (3, 9), (11, 11), (13, 5), (6, 7))
+    for variant in ("hybrid", "full", "compact"):
+        config = make_config(variant, runtime__telemetry__provider="stub")
+        loop = SimulationLoop(config)
+        for oid, otype, pos in objects:
+            loop.world.register_object(object_id=oid, object_type=otype, position=pos)
+        for i, pos in enumerate(spawns):
+            loop.world.lifecycle_service.spawn_agent(
+                f"agent_{i}", pos, needs={"hunger": 0.9 - 0.08 * i, "hygiene": 0.5 + 0.05 * i, "energy": 0.7}, wallet=2.0 + i
+            )
+        manager = SnapshotManager(WORK / f"snapshots_{variant}")
+        for tick_target in (10, 25, 50):
+            while loop.tick < tick_target:
+                loop.step()
+            snapshot = snapshot_from_world(
+                config=loop.config, world=loop.world, lifecycle=loop.lifecycle, telemetry=loop.telemetry,
+                perturbations=loop.perturbations, stability=loop.stability, promotion=loop.promotion,
+                rng_streams={"world": loop._rng_world, "events": loop._rng_events, "policy": loop._rng_policy},
+            )
+            path = manager.save(snapshot)
+            restored = SimulationLoop(config)
+            for oid, otype, pos in objects:  # the snapshot schema drops object positions (snapshots/state.py:92-123)
+                restored.world.register_object(object_id=oid, object_type=otype, position=pos)
+            apply_snapshot_to_world(restored.world, manager.load(path, config), lifecycle=restored.lifecycle)
+            assert len(restored.world.agents) >= 1, "snapshot lost its agents"
+            obs_fixture(
+                f"snapshot_{tick_target}_{variant}",
+                restored.world,
+                config,
+                note=f"world state restored from a populated snapshot-{tick_target}.json (capture_snapshots.py recipe)",
+            )
+
+
 def gae_case():
     """compute_gae (policy/backends/pytorch/ppo_utils.py:19-67) on random float32 rollouts, both value layouts."""
     import torch
@@ -625,8 +673,9 @@ def gae_case():
 
 def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
-    if os.environ.get("TL_GOLDEN_ONLY") == "gae":
-        gae_case()
+    only = os.environ.get("TL_GOLDEN_ONLY")
+    if only:
+        {"gae": gae_case, "snapshots": snapshot_cases}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()
@@ -635,6 +684,7 @@ def main():
     crowded_cases()
     synth_cases()
     reward_cases()
+    snapshot_cases()
     gae_case()
     shutil.rmtree(WORK, ignore_errors=True)
 
