@@ -238,10 +238,11 @@ def main() -> None:
 
         torch.manual_seed(1234 + rank)
         capture = RolloutCapture(dev, PolicyMLP(obs.n_features, obs.map_shape, action_dim=9))
+        graphed = None if os.environ.get("TL_NO_GRAPH") else capture.build_graph(tpl, out)
 
     def launch(i: int) -> None:
         if capture is not None:
-            ro = capture.capture(tpl, out)
+            ro = graphed.replay() if graphed is not None else capture.capture(tpl, out)
             totals = ro.kpi.sum(dim=(0, 1)).double()
             if world > 1:
                 dist.all_reduce(totals, op=dist.ReduceOp.SUM)

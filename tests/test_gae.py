@@ -77,3 +77,31 @@ def test_rollout_capture_matches_tick_by_tick_oracle() -> None:
     assert ro.values.shape == (6, batch.n_agents) and ro.actions.shape == (5, batch.n_agents)
     ref_adv, ref_ret = oracle_gae(ro.rewards.cpu().numpy(), ro.values.cpu().numpy(), ro.dones.cpu().numpy(), 0.99, 0.95)
     assert np.array_equal(ro.advantages.cpu().numpy(), ref_adv) and np.array_equal(ro.returns.cpu().numpy(), ref_ret)
+
+
+@pytest.mark.gpu
+def test_graphed_rollout_equals_eager_rollout() -> None:
+    import torch
+
+    from townlet_b200 import capi
+    from townlet_b200.engine import DeviceTownBatch
+    from townlet_b200.params import ObsSpec, RewardSpec
+    from townlet_b200.rollout import PolicyMLP, RolloutCapture
+    from townlet_b200.synth import synth_batch
+
+    obs, rew = ObsSpec(variant="compact"), RewardSpec(fuse_faint=True)
+    batch = synth_batch(16, 48, 10, obs)
+    policy = PolicyMLP(obs.n_features, obs.map_shape, action_dim=9)
+    eager_dev = DeviceTownBatch(batch.copy(), obs, rew)
+    graph_dev = DeviceTownBatch(batch.copy(), obs, rew)
+    eager = RolloutCapture(eager_dev, policy, autocast_dtype=None)
+    graphed = RolloutCapture(graph_dev, policy, autocast_dtype=None).build_graph(4)
+    for _ in range(2):  # two consecutive rollouts: the graph continues from the device state
+        a = eager.capture(4)
+        b = graphed.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(a.map, b.map) and torch.equal(a.features, b.features)
+        assert torch.equal(a.rewards, b.rewards) and torch.equal(a.dones, b.dones)
+        assert torch.allclose(a.values, b.values)
+    assert torch.equal(eager_dev.arena, graph_dev.arena)
+    assert capi.load_library().tl_launch_count() > 0
