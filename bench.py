@@ -238,7 +238,13 @@ def main() -> None:
 
         torch.manual_seed(1234 + rank)
         capture = RolloutCapture(dev, PolicyMLP(obs.n_features, obs.map_shape, action_dim=9))
-        graphed = None if os.environ.get("TL_NO_GRAPH") else capture.build_graph(tpl, out)
+        graphed = None
+        graph_launches = 0
+        if not os.environ.get("TL_NO_GRAPH"):
+            before = lib.tl_launch_count()
+            graphed = capture.build_graph(tpl, out)
+            graph_launches = tpl + 1  # kernels of this library inside the captured rollout: tpl ticks + 1 GAE scan
+            del before
 
     def launch(i: int) -> None:
         if capture is not None:
@@ -273,6 +279,8 @@ def main() -> None:
         dist.barrier()
     torch.cuda.synchronize()
     launches = lib.tl_launch_count() - launches0
+    if wl.get("policy") and graphed is not None:
+        launches += n_launch * graph_launches  # graph replays re-issue the captured launches
     clocks = sampler.stop()
     elapsed_ms = events[0].elapsed_time(events[-1])
     per_launch_ms = [events[i].elapsed_time(events[i + 1]) for i in range(n_launch)]

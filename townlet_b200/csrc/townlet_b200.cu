@@ -1051,9 +1051,16 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     }
 
     auto run = [&](auto kernel) -> int {
-        if (!cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kp.smem_bytes),
-                     "cudaFuncSetAttribute"))
-            return TL_ERR_CUDA;
+        // opt in to the device's full dynamic shared memory once per kernel and device, so that later
+        // launches issue no attribute call (legal inside CUDA-graph stream capture)
+        static std::atomic<uint64_t> opted_in{0};  // one static per kernel instantiation; bit = device
+        const uint64_t bit = 1ull << (device & 63);
+        if (!(opted_in.load(std::memory_order_acquire) & bit)) {
+            if (!cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
+                         "cudaFuncSetAttribute"))
+                return TL_ERR_CUDA;
+            opted_in.fetch_or(bit, std::memory_order_release);
+        }
         kernel<<<grid, threads, kp.smem_bytes, stream>>>(kp);
         if (!cuda_ok(cudaGetLastError(), "kernel launch")) return TL_ERR_CUDA;
         g_launches.fetch_add(1, std::memory_order_relaxed);

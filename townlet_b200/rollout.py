@@ -144,7 +144,7 @@ class RolloutCapture:
         for t in range(n_ticks):
             dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)  # obs / reward / done of tick t land in slot t
             logits, value = self._forward(out.map[t], out.features[t])
-            dist = torch.distributions.Categorical(logits=logits)
+            dist = torch.distributions.Categorical(logits=logits, validate_args=False)  # validation would sync
             act = dist.sample()
             actions[t], log_probs[t], values[t] = act, dist.log_prob(act), value
         # bootstrap value: the policy on the last observation (no further tick is simulated)
