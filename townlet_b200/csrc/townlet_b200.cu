@@ -29,6 +29,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "townlet_b200.h"
 
@@ -947,6 +949,7 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     if (!cuda_ok(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device),
                  "cudaDeviceGetAttribute"))
         return TL_ERR_CUDA;
+    max_smem -= 1024;  // room for the kernels' static shared memory (the opt-in limit covers static + dynamic)
 
     const int avg_agents = b->n_towns > 0 ? (b->n_agents + b->n_towns - 1) / b->n_towns : 1;
     const int avg_entities = b->n_towns > 0 ? (b->n_entities + b->n_towns - 1) / b->n_towns : 1;
@@ -1052,14 +1055,20 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
 
     auto run = [&](auto kernel) -> int {
         // opt in to the device's full dynamic shared memory once per kernel and device, so that later
-        // launches issue no attribute call (legal inside CUDA-graph stream capture)
-        static std::atomic<uint64_t> opted_in{0};  // one static per kernel instantiation; bit = device
-        const uint64_t bit = 1ull << (device & 63);
-        if (!(opted_in.load(std::memory_order_acquire) & bit)) {
-            if (!cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
-                         "cudaFuncSetAttribute"))
-                return TL_ERR_CUDA;
-            opted_in.fetch_or(bit, std::memory_order_release);
+        // launches issue no attribute call (legal inside CUDA-graph stream capture).  Keyed by the
+        // function address: all instantiations share one function-pointer type.
+        {
+            static std::mutex mu;
+            static std::unordered_map<const void*, uint64_t> opted_in;
+            const uint64_t bit = 1ull << (device & 63);
+            std::lock_guard<std::mutex> lock(mu);
+            uint64_t& mask = opted_in[reinterpret_cast<const void*>(kernel)];
+            if (!(mask & bit)) {
+                if (!cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
+                             "cudaFuncSetAttribute"))
+                    return TL_ERR_CUDA;
+                mask |= bit;
+            }
         }
         kernel<<<grid, threads, kp.smem_bytes, stream>>>(kp);
         if (!cuda_ok(cudaGetLastError(), "kernel launch")) return TL_ERR_CUDA;
