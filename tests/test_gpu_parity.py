@@ -194,3 +194,78 @@ def test_full_size_configs_match_oracle(variant, towns, grid, agents) -> None:
     assert_obs_equal(got, ref, f"{variant} full size")
     assert_reward_close(got, ref, f"{variant} full size")
     np.testing.assert_allclose(b_dev.needs, b_ora.needs, rtol=REL_TOL, atol=1e-15)
+
+
+def _ragged_batch(obs, sizes, grid, extra_objects=0):
+    """Towns of different sizes in one batch (ragged agent / entity ranges)."""
+    from townlet_b200.synth import assemble, synth_town
+
+    towns = []
+    for t, n in enumerate(sizes):
+        town = synth_town(1000 + t, grid, n, terminated_frac=0.1)
+        if extra_objects:
+            rng = np.random.default_rng(t)
+            k = extra_objects
+            town.object_ids += [f"extra_{i}" for i in range(k)]
+            town.object_types += [("stove", "crate", "bed", "Fridge")[i % 4] for i in range(k)]
+            town.object_positions = np.concatenate([town.object_positions, rng.integers(0, grid, size=(k, 2))])
+        towns.append(town)
+    return assemble(towns, obs)
+
+
+@pytest.mark.parametrize("mode", ["ent", "grid", "ent1", "ent-generic"])
+@pytest.mark.parametrize(
+    "variant,sizes,grid,extra",
+    [
+        ("hybrid", [1, 33, 7, 64, 2, 2, 2, 40, 5, 9, 70, 3], 40, 0),  # ragged, several passes per town
+        ("compact", [3, 1, 1, 1, 17, 32, 31, 33, 8], 24, 30),  # stacked extra objects, unknown types
+        ("full", [12, 5, 65], 64, 150),  # more than 128 entities per town: the uncached entity loop
+    ],
+)
+def test_ragged_towns_match_oracle(variant, sizes, grid, extra, mode, monkeypatch) -> None:
+    from oracle.oracle import oracle_tick
+
+    monkeypatch.setenv("TL_MODE", mode.split("-")[0])
+    if mode.endswith("-generic"):
+        monkeypatch.setenv("TL_GENERIC", "1")
+    obs = ObsSpec(variant=variant, include_targets=True, object_channels=("stove", "fridge") if variant == "compact" else ())
+    rew = RewardSpec(fuse_faint=True)
+    batch = _ragged_batch(obs, sizes, grid, extra)
+    batch.validate(len(obs.object_channels) if variant == "compact" else 0)
+    b_dev, b_ora = batch.copy(), batch.copy()
+    got = _device_run(b_dev, obs, rew, capi.TL_PHASE_ALL, 3)
+    ref = oracle_tick(b_ora, obs, rew, capi.TL_PHASE_ALL, 3)
+    assert_obs_equal(got, ref, f"ragged {variant}")
+    assert_reward_close(got, ref, f"ragged {variant}")
+    np.testing.assert_allclose(got["kpi"], ref["kpi"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(b_dev.flags, b_ora.flags)
+
+
+def test_batches_with_empty_towns_and_no_agents() -> None:
+    """Empty inputs: towns without agents inside a batch, and a batch with no agents at all."""
+    from oracle.oracle import oracle_tick
+    from townlet_b200.soa import BatchLayout, TownBatch
+
+    obs, rew = ObsSpec(), RewardSpec(fuse_faint=True)
+    base = _ragged_batch(obs, [4, 6], 32)
+    # splice two empty towns around the populated ones by rewriting the offset tables
+    lay = BatchLayout.make(4, base.n_agents, base.n_entities, 6, 1)
+    batch = TownBatch(lay, 32, 32)
+    for name, view in base.views().items():
+        if name not in ("town_agent_off", "town_ent_off", "town_tick"):
+            getattr(batch, name)[...] = view
+    a, e = base.town_agent_off, base.town_ent_off
+    batch.town_agent_off[...] = [0, 0, a[1], a[1], a[2]]
+    batch.town_ent_off[...] = [0, 0, e[1], e[1], e[2]]
+    batch.town_tick[...] = [5, base.town_tick[0], 7, base.town_tick[1]]
+    b_dev, b_ora = batch.copy(), batch.copy()
+    got = _device_run(b_dev, obs, rew, capi.TL_PHASE_ALL, 2)
+    ref = oracle_tick(b_ora, obs, rew, capi.TL_PHASE_ALL, 2)
+    assert_obs_equal(got, ref, "empty towns")
+    assert_reward_close(got, ref, "empty towns")
+    np.testing.assert_allclose(got["kpi"], ref["kpi"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(b_dev.town_tick, b_ora.town_tick)
+    # nothing to do at all: zero towns
+    empty = TownBatch(BatchLayout.make(0, 0, 0, 6, 1), 16, 16)
+    out = _device_run(empty, obs, rew, capi.TL_PHASE_ALL, 1)
+    assert out["map"].shape[1] == 0 and out["reward"].shape[1] == 0

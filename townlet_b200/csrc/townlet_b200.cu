@@ -920,6 +920,8 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
 
 int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlObsOut* oo,
            const TlRewardOut* ro, uint32_t phases, int n_ticks, cudaStream_t stream, int towns_per_cta_override) {
+    // an empty batch is a valid no-op (its zero-length arrays may well be NULL pointers)
+    if (b && b->n_towns == 0 && b->n_agents == 0 && n_ticks >= 0) return TL_OK;
     int rc = validate(b, obs, rew, oo, ro, phases, n_ticks);
     if (rc != TL_OK) return rc;
     if (b->n_towns == 0 || n_ticks == 0) return TL_OK;
