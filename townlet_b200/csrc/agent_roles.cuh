@@ -1,0 +1,344 @@
+// agent_roles.cuh — the thread-per-agent parts of the tick, shared by the role-parallel entity kernel
+// (tick_roles.cuh) and the dense grid kernel (townlet_b200.cu).  Included inside the anonymous namespace
+// of townlet_b200.cu; uses KParams, RewardIn / reward_agent, pos_x / pos_y.
+
+struct StateRoleOut {
+    double need0 = 0.0;         // hunger after decay (KPI)
+    double reward_total = 0.0;  // reward of the tick (KPI)
+    double kpi_wallet = 0.0;
+    int kpi_late = 0;
+    bool terminated = false;    // effective terminated flag of the tick
+};
+
+// Role "state" for ONE agent: float64 need decay (world/grid.py:1439-1455), faint predicate
+// (lifecycle/manager.py:39-45), episode tick (world/core/context.py:283-289), reward with guardrails
+// (rewards/engine.py:71-172) and, when `f` is not null, the scalar features, path hint, landmarks and
+// personality channels of encode_feature_vector (encoders/features.py:43-404).
+__device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a, int tick, int town_abeg, int town_aend,
+                                                 int town_ebeg, int town_eend, float* f, StateRoleOut& out) {
+    const TlObsParams& o = p.obs;
+    const int N = p.b.n_agents;
+    const bool do_decay = p.phases & TL_PHASE_DECAY;
+    const bool do_reward = p.phases & TL_PHASE_REWARD;
+    const bool do_obs = (p.phases & TL_PHASE_OBS) && f != nullptr;
+    const bool do_advance = p.phases & TL_PHASE_ADVANCE;
+    const bool do_state = do_decay || do_reward;
+    double& need0 = out.need0;
+    double& reward_total = out.reward_total;
+    double& kpi_wallet = out.kpi_wallet;
+    int& kpi_late = out.kpi_late;
+    bool& terminated = out.terminated;
+    // the agent's scalar inputs are loaded up front so the loads overlap
+    double need[3];
+    need[0] = p.b.needs[a];
+    need[1] = p.b.needs[(size_t)N + a];
+    need[2] = p.b.needs[2 * (size_t)N + a];
+    uint32_t fl = p.b.flags[a];
+    int episode_tick = p.b.episode_tick[a];
+    RewardIn rin;
+    if (do_reward) rin = load_reward_in(p, a);
+    const double wallet = __ldg(p.b.wallet + a);
+    const int lateness = __ldg(p.b.lateness + a);
+    kpi_wallet = wallet;
+    kpi_late = lateness;
+    double attendance = 0.0, wages_withheld = 0.0;
+    int duration = 0, slot_idx = 0;
+    float last_hash = 0.0f;
+    int32_t pw = 0;
+    if (do_obs) {
+        attendance = __ldg(p.b.attendance + a);
+        wages_withheld = __ldg(p.b.wages_withheld + a);
+        duration = __ldg(p.b.last_action_duration + a);
+        slot_idx = __ldg(p.b.slot + a);
+        last_hash = __ldg(p.b.last_action_hash + a);
+        pw = __ldg(p.b.pos + a);
+    }
+    const unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
+    if (do_decay) {  // world/grid.py:1439-1455
+#pragma unroll
+        for (int k = 0; k < TL_N_NEEDS; ++k) {
+            double mult = 1.0;
+            if (p.rew.decay_personality && profile != 0) {
+                mult = p.rew.need_mult[profile][k];
+                if (mult <= 0.0) mult = 1.0;
+            }
+            const double adjusted = p.rew.decay_rate[k] * mult;
+            need[k] = fmax(0.0, need[k] - adjusted);
+            p.b.needs[(size_t)k * N + a] = need[k];
+        }
+    }
+    if (do_state && p.rew.fuse_faint) {  // lifecycle/manager.py:39-45
+        fl = (fl & ~TL_F_FAINTED) | (need[0] <= p.rew.faint_threshold ? TL_F_FAINTED : 0u);
+        p.b.flags[a] = fl;
+    }
+    terminated = (fl & (TL_F_TERMINATED | TL_F_FAINTED)) != 0;
+    unsigned reason = (fl & TL_F_REASON_MASK) >> TL_F_REASON_SHIFT;
+    if (reason == 0 && (fl & TL_F_FAINTED)) reason = 1;
+    if (do_advance) {  // world/core/context.py:283-289
+        const int span = max(1, o.ticks_per_day);
+        episode_tick = (episode_tick + 1) % span;
+        p.b.episode_tick[a] = episode_tick;
+    }
+    if (do_reward) {
+        RewardResult rr;
+        reward_agent(p.rew, rin, tick, need, fl, terminated, reason, rr);
+        p.b.term_block_tick[a] = rr.block;
+        p.b.episode_total[a] = rr.cumulative;
+        reward_total = rr.total;
+        if (p.ro.reward) p.ro.reward[(size_t)it * p.ro.reward_tick_stride + a] = (float)rr.total;
+        if (p.ro.comps) {
+            double* dst = p.ro.comps + (size_t)it * p.ro.comps_tick_stride + (size_t)a * TL_N_COMPS;
+#pragma unroll
+            for (int i = 0; i < TL_N_COMPS; i += 2)
+                *reinterpret_cast<double2*>(dst + i) = make_double2(rr.comps[i], rr.comps[i + 1]);
+        }
+    }
+    if (do_state && p.ro.terminated)
+        p.ro.terminated[(size_t)it * p.ro.terminated_tick_stride + a] = terminated ? 1 : 0;
+    need0 = need[0];
+
+    if (do_obs) {  // encoders/features.py:43-404
+        f[TL_FEAT_NEED_HUNGER] = (float)need[0];
+        f[TL_FEAT_NEED_HYGIENE] = (float)need[1];
+        f[TL_FEAT_NEED_ENERGY] = (float)need[2];
+        f[TL_FEAT_WALLET] = (float)wallet;
+        f[TL_FEAT_LATENESS] = (float)lateness;
+        f[TL_FEAT_ON_SHIFT] = (fl & TL_F_ON_SHIFT) ? 1.0f : 0.0f;
+        int m = tick % o.ticks_per_day;
+        if (m < 0) m += o.ticks_per_day;
+        const float2 sc = __ldg(reinterpret_cast<const float2*>(o.time_lut + 2 * m));
+        f[TL_FEAT_TIME_SIN] = sc.x;
+        f[TL_FEAT_TIME_COS] = sc.y;
+        f[TL_FEAT_ATTENDANCE] = (float)attendance;
+        f[TL_FEAT_WAGES_WITHHELD] = (float)wages_withheld;
+        unsigned st = (fl & TL_F_SHIFT_MASK) >> TL_F_SHIFT_SHIFT;
+        if (st > 4) st = 0;
+#pragma unroll
+        for (unsigned k = 0; k < 5; ++k) f[TL_FEAT_SHIFT_PRE + k] = (k == st) ? 1.0f : 0.0f;
+        f[TL_FEAT_SLOT_NORM] = (slot_idx >= 0 && slot_idx < o.max_slots)
+                                   ? __ldg(o.slot_lut + slot_idx)
+                                   : (float)((double)slot_idx / (double)o.max_slots);
+        f[TL_FEAT_CTX_RESET] = ((fl & TL_F_CTX_RESET) || terminated) ? 1.0f : 0.0f;  // service.py:224-229
+        f[TL_FEAT_EPISODE_PROGRESS] =
+            episode_tick <= 0 ? 0.0f : __ldg(o.progress_lut + min(episode_tick, o.ticks_per_day));
+        f[TL_FEAT_LAST_HASH] = last_hash;
+        f[TL_FEAT_LAST_SUCCESS] = (fl & TL_F_LAST_SUCCESS) ? 1.0f : 0.0f;
+        f[TL_FEAT_LAST_DURATION] = (float)duration;
+        f[TL_FEAT_RESERVATION] = (fl & TL_F_RESERVATION) ? 1.0f : 0.0f;
+        f[TL_FEAT_IN_QUEUE] = (fl & TL_F_IN_QUEUE) ? 1.0f : 0.0f;
+        // nearest object per landmark type: first minimum of the squared
+        // distance in insertion order (world/observe.py:109-147)
+        const int cx = pos_x(pw), cy = pos_y(pw);
+        const bool all_types = o.landmark_base >= 0;
+        const int e_obj = town_ebeg + (town_aend - town_abeg);
+        int hd2 = -1, hdx = 0, hdy = 0;
+        if (!all_types) {
+#pragma unroll 1
+            for (int e = e_obj; e < town_eend; ++e) {
+                const uint32_t w = __ldg(p.b.ent + e);
+                if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w) || (int)TL_ENT_LTYPE(w) != o.path_hint_ltype)
+                    continue;
+                const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
+                const int d2 = dx * dx + dy * dy;
+                if (hd2 < 0 || d2 < hd2) {
+                    hd2 = d2;
+                    hdx = dx;
+                    hdy = dy;
+                }
+            }
+        } else {
+            int best_d2[5] = {-1, -1, -1, -1, -1};
+            int best_dx[5] = {0, 0, 0, 0, 0}, best_dy[5] = {0, 0, 0, 0, 0};
+#pragma unroll 1
+            for (int e = e_obj; e < town_eend; ++e) {
+                const uint32_t w = __ldg(p.b.ent + e);
+                if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w)) continue;
+                const int lt = (int)TL_ENT_LTYPE(w);
+                if (lt == 0) continue;
+                const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
+                const int d2 = dx * dx + dy * dy;
+#pragma unroll
+                for (int l = 1; l <= 4; ++l) {
+                    if (l == lt && (best_d2[l] < 0 || d2 < best_d2[l])) {
+                        best_d2[l] = d2;
+                        best_dx[l] = dx;
+                        best_dy[l] = dy;
+                    }
+                }
+            }
+#pragma unroll
+            for (int l = 1; l <= 4; ++l) {  // _encode_landmarks, features.py:333-356
+                if (l == o.path_hint_ltype) {
+                    hd2 = best_d2[l];
+                    hdx = best_dx[l];
+                    hdy = best_dy[l];
+                }
+                float* dst = f + o.landmark_base + 3 * (l - 1);
+                if (best_d2[l] < 0) {
+                    dst[0] = dst[1] = dst[2] = 0.0f;
+                } else {
+                    // sqrt of an exact integer: equals np.hypot after the float32 store
+                    const double distance = sqrt((double)best_d2[l]);
+                    const double norm = distance > 0.0 ? distance : 1.0;
+                    dst[0] = (float)((double)best_dx[l] / norm);
+                    dst[1] = (float)((double)best_dy[l] / norm);
+                    dst[2] = (float)distance;
+                }
+            }
+        }
+        {  // _encode_path_hint, features.py:251-286
+            double north = 0.0, south = 0.0, east = 0.0, west = 0.0;
+            if (hd2 > 0) {
+                const double dn = (double)(abs(hdx) + abs(hdy));
+                // max(0, -dy)/norm etc.: one of each opposite pair is exactly 0.0, so two
+                // IEEE divisions give the four values
+                const double ns = (double)abs(hdy) / dn, ew = (double)abs(hdx) / dn;
+                north = hdy < 0 ? ns : 0.0;
+                south = hdy > 0 ? ns : 0.0;
+                east = hdx > 0 ? ew : 0.0;
+                west = hdx < 0 ? ew : 0.0;
+            }
+            f[TL_FEAT_PATH_NORTH + 0] = (float)north;
+            f[TL_FEAT_PATH_NORTH + 1] = (float)south;
+            f[TL_FEAT_PATH_NORTH + 2] = (float)east;
+            f[TL_FEAT_PATH_NORTH + 3] = (float)west;
+        }
+        if (o.personality_base >= 0) {  // features.py:359-380
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                f[o.personality_base + k] = p.b.personality ? __ldg(p.b.personality + (size_t)k * N + a) : 0.0f;
+        }
+    }
+}
+
+// Role "social" for ONE agent: rivalry features (encoders/features.py:232-248) and the social snippet
+// (encoders/social.py:27-254).  The relation rows may live in shared memory (staged by the caller) or in
+// global memory; `elut` is the byte -> float32 table of the id embedding.
+__device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, int n_t, const double* s_trust_row,
+                                                  const double* s_fam_row, const double* s_riv_row,
+                                                  const double* s_score_row, const uint64_t* s_temb_row,
+                                                  const uint64_t* s_remb_row, const float* s_elut, float* f, int& filled,
+                                                  int& source) {
+    const TlObsParams& o = p.obs;
+    const int EW = p.b.embed_words;
+    // row-relative views: index j addresses relation j of this agent
+    const double* s_trust = s_trust_row;
+    const double* s_fam = s_fam_row;
+    const double* s_riv = s_riv_row;
+    const double* s_score = s_score_row;
+    const uint64_t* s_temb = s_temb_row;
+    const uint64_t* s_remb = s_remb_row;
+    const int rbase = 0;
+    filled = 0;
+    source = 0;
+    {  // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
+        const int nr = min(n_riv, o.rivalry_max_edges);
+        int avoid = 0;
+        double mx = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < nr; ++j) {
+            const double v = s_score[rbase + j];
+            if (j == 0) mx = v;
+            avoid += (v >= o.avoid_threshold) ? 1 : 0;
+        }
+        f[TL_FEAT_RIVALRY_MAX] = (float)mx;
+        f[TL_FEAT_RIVALRY_AVOID] = (float)avoid;
+    }
+    if (o.social_base >= 0) {  // encoders/social.py:27-254
+        const int slot_dim = o.embed_dim + 3;
+        const int total_slots = o.top_friends + o.top_rivals;
+        float* srow = f + o.social_base;
+        const bool from_ties = n_t > 0;  // _resolve_relationships, social.py:165-209
+        const int n_rel = from_ties ? n_t : min(n_riv, o.top_rivals);
+        source = from_ties ? 1 : (n_rel > 0 ? 2 : 0);
+        const double* kt = s_trust + rbase;
+        const double* kf = s_fam + rbase;
+        const double* kr = (from_ties ? s_riv : s_score) + rbase;
+        const uint64_t* ke = (from_ties ? s_temb : s_remb) + rbase * EW;
+        // sorted(..., reverse=True)[:k] is stable: repeated FIRST argmax (social.py:137-156).
+        // In the rivalry fallback trust = familiarity = 0, so friends are the first entries.
+        unsigned chosen = 0, sel = 0;
+        const int n_friends = min(n_rel, o.top_friends);
+        const int n_rivals = min(o.top_rivals, n_rel - n_friends);
+        filled = n_friends + n_rivals;
+#pragma unroll 1
+        for (int s = 0; s < filled; ++s) {
+            const bool friend_pass = s < n_friends;
+            int best = -1;
+            double bk = 0.0;
+#pragma unroll 1
+            for (int j = 0; j < n_rel; ++j) {
+                if ((chosen >> j) & 1u) continue;
+                const double key = friend_pass ? (from_ties ? kt[j] + kf[j] : 0.0) : kr[j];
+                if (best < 0 || key > bk) {
+                    best = j;
+                    bk = key;
+                }
+            }
+            chosen |= 1u << best;
+            sel |= (unsigned)best << (4 * s);
+        }
+        double tsum = 0.0, rsum = 0.0, tmax = 0.0, rmax = 0.0;
+#pragma unroll 1
+        for (int s = 0; s < total_slots; ++s) {
+            float* dst = srow + s * slot_dim;
+            if (s >= filled) {  // _empty_relationship_entry, social.py:226-233
+#pragma unroll 1
+                for (int d = 0; d < slot_dim; ++d) dst[d] = 0.0f;
+                continue;
+            }
+            const int j = (sel >> (4 * s)) & 15;
+            const double trust = from_ties ? kt[j] : 0.0;
+            const double fam = from_ties ? kf[j] : 0.0;
+            const double riv = kr[j];
+            if (o.embed_dim == 8) {  // _embed_agent_id, social.py:236-242; bytes via PRMT
+                const uint64_t word = ke[j * EW];
+                const unsigned lo = (unsigned)word, hi = (unsigned)(word >> 32);
+                dst[0] = s_elut[__byte_perm(lo, 0, 0x4440)];
+                dst[1] = s_elut[__byte_perm(lo, 0, 0x4441)];
+                dst[2] = s_elut[__byte_perm(lo, 0, 0x4442)];
+                dst[3] = s_elut[__byte_perm(lo, 0, 0x4443)];
+                dst[4] = s_elut[__byte_perm(hi, 0, 0x4440)];
+                dst[5] = s_elut[__byte_perm(hi, 0, 0x4441)];
+                dst[6] = s_elut[__byte_perm(hi, 0, 0x4442)];
+                dst[7] = s_elut[__byte_perm(hi, 0, 0x4443)];
+            } else {
+                uint64_t word = 0;
+#pragma unroll 1
+                for (int d = 0; d < o.embed_dim; ++d) {
+                    if ((d & 7) == 0) word = ke[j * EW + (d >> 3)];
+                    dst[d] = s_elut[(unsigned)(word >> (8 * (d & 7))) & 255u];
+                }
+            }
+            dst[o.embed_dim + 0] = (float)trust;
+            dst[o.embed_dim + 1] = (float)fam;
+            dst[o.embed_dim + 2] = (float)riv;
+            tsum += trust;  // numpy sums left to right below 8 values
+            rsum += riv;
+            tmax = s == 0 ? trust : fmax(tmax, trust);
+            rmax = s == 0 ? riv : fmax(rmax, riv);
+        }
+        if (o.include_aggregates) {  // _compute_aggregates, social.py:90-105, 245-254
+            float* agg = srow + total_slots * slot_dim;
+            if (filled > 0) {
+                if (filled == 8) {  // numpy's unrolled pairwise block of 8
+                    double tv[8], rv[8];
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        const int j = (sel >> (4 * s)) & 15;
+                        tv[s] = from_ties ? kt[j] : 0.0;
+                        rv[s] = kr[j];
+                    }
+                    tsum = ((tv[0] + tv[1]) + (tv[2] + tv[3])) + ((tv[4] + tv[5]) + (tv[6] + tv[7]));
+                    rsum = ((rv[0] + rv[1]) + (rv[2] + rv[3])) + ((rv[4] + rv[5]) + (rv[6] + rv[7]));
+                }
+                agg[0] = (float)(tsum / (double)filled);
+                agg[1] = (float)tmax;
+                agg[2] = (float)(rsum / (double)filled);
+                agg[3] = (float)rmax;
+            } else {
+                agg[0] = agg[1] = agg[2] = agg[3] = 0.0f;
+            }
+        }
+    }
+}

@@ -841,6 +841,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
     }
 }
 
+#include "agent_roles.cuh"
 #include "tick_ent.cuh"
 #include "tick_roles.cuh"
 
