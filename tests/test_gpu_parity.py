@@ -53,7 +53,7 @@ def _check_state(batch, ref):
         np.testing.assert_allclose(batch.episode_total, ref["episode_total"][-1], rtol=REL_TOL, atol=1e-12)
 
 
-@pytest.mark.parametrize("mode", ["ent", "grid", "ent1"])
+@pytest.mark.parametrize("mode", ["ent", "grid"])
 @pytest.mark.parametrize("path", FIXTURES, ids=[p.stem for p in FIXTURES])
 def test_device_path_matches_reference_golden(path, mode, monkeypatch) -> None:
     monkeypatch.setenv("TL_MODE", mode)  # both kernel forms: entity list and dense shared-memory grid
@@ -88,7 +88,7 @@ SYNTH_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["ent", "grid", "ent-chunk8", "ent-generic", "ent1", "ent1-generic"])
+@pytest.mark.parametrize("mode", ["ent", "grid", "ent-chunk8", "ent-generic"])
 @pytest.mark.parametrize("case", SYNTH_CASES, ids=[c[0] for c in SYNTH_CASES])
 def test_cuda_matches_oracle_on_synthetic_towns(case, mode, monkeypatch) -> None:
     from oracle.oracle import oracle_tick
@@ -213,7 +213,7 @@ def _ragged_batch(obs, sizes, grid, extra_objects=0):
     return assemble(towns, obs)
 
 
-@pytest.mark.parametrize("mode", ["ent", "grid", "ent1", "ent-generic"])
+@pytest.mark.parametrize("mode", ["ent", "grid", "ent-generic"])
 @pytest.mark.parametrize(
     "variant,sizes,grid,extra",
     [

@@ -262,7 +262,7 @@ def nvcc_command(out: Path = LIB_PATH) -> list[str]:
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     src = CSRC / "townlet_b200.cu"
-    deps = [src, INCLUDE / "townlet_b200.h"]
+    deps = [src, INCLUDE / "townlet_b200.h", *sorted(CSRC.glob("*.cuh"))]
     if LIB_PATH.exists() and not force:
         if all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
             return LIB_PATH

@@ -212,23 +212,16 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
 }
 
 // Role "social" for ONE agent: rivalry features (encoders/features.py:232-248) and the social snippet
-// (encoders/social.py:27-254).  The relation rows may live in shared memory (staged by the caller) or in
-// global memory; `elut` is the byte -> float32 table of the id embedding.
-__device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, int n_t, const double* s_trust_row,
-                                                  const double* s_fam_row, const double* s_riv_row,
-                                                  const double* s_score_row, const uint64_t* s_temb_row,
-                                                  const uint64_t* s_remb_row, const float* s_elut, float* f, int& filled,
-                                                  int& source) {
+// (encoders/social.py:27-254).  kt / kf / ktr are the agent's tie rows (trust, familiarity, rivalry),
+// `score` its rivalry-ledger row, temb / remb the id-embedding words of the two tables; the rows may live
+// in shared memory (staged by the caller) or in global memory.  `elut` is the byte -> float32 table of
+// the id embedding.
+__device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, int n_t, const double* kt,
+                                                  const double* kf, const double* ktr, const double* score,
+                                                  const uint64_t* temb, const uint64_t* remb, const float* elut,
+                                                  float* f, int& filled, int& source) {
     const TlObsParams& o = p.obs;
     const int EW = p.b.embed_words;
-    // row-relative views: index j addresses relation j of this agent
-    const double* s_trust = s_trust_row;
-    const double* s_fam = s_fam_row;
-    const double* s_riv = s_riv_row;
-    const double* s_score = s_score_row;
-    const uint64_t* s_temb = s_temb_row;
-    const uint64_t* s_remb = s_remb_row;
-    const int rbase = 0;
     filled = 0;
     source = 0;
     {  // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
@@ -237,7 +230,7 @@ __device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, i
         double mx = 0.0;
 #pragma unroll 1
         for (int j = 0; j < nr; ++j) {
-            const double v = s_score[rbase + j];
+            const double v = score[j];
             if (j == 0) mx = v;
             avoid += (v >= o.avoid_threshold) ? 1 : 0;
         }
@@ -251,10 +244,8 @@ __device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, i
         const bool from_ties = n_t > 0;  // _resolve_relationships, social.py:165-209
         const int n_rel = from_ties ? n_t : min(n_riv, o.top_rivals);
         source = from_ties ? 1 : (n_rel > 0 ? 2 : 0);
-        const double* kt = s_trust + rbase;
-        const double* kf = s_fam + rbase;
-        const double* kr = (from_ties ? s_riv : s_score) + rbase;
-        const uint64_t* ke = (from_ties ? s_temb : s_remb) + rbase * EW;
+        const double* kr = from_ties ? ktr : score;
+        const uint64_t* ke = from_ties ? temb : remb;
         // sorted(..., reverse=True)[:k] is stable: repeated FIRST argmax (social.py:137-156).
         // In the rivalry fallback trust = familiarity = 0, so friends are the first entries.
         unsigned chosen = 0, sel = 0;
@@ -294,20 +285,20 @@ __device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, i
             if (o.embed_dim == 8) {  // _embed_agent_id, social.py:236-242; bytes via PRMT
                 const uint64_t word = ke[j * EW];
                 const unsigned lo = (unsigned)word, hi = (unsigned)(word >> 32);
-                dst[0] = s_elut[__byte_perm(lo, 0, 0x4440)];
-                dst[1] = s_elut[__byte_perm(lo, 0, 0x4441)];
-                dst[2] = s_elut[__byte_perm(lo, 0, 0x4442)];
-                dst[3] = s_elut[__byte_perm(lo, 0, 0x4443)];
-                dst[4] = s_elut[__byte_perm(hi, 0, 0x4440)];
-                dst[5] = s_elut[__byte_perm(hi, 0, 0x4441)];
-                dst[6] = s_elut[__byte_perm(hi, 0, 0x4442)];
-                dst[7] = s_elut[__byte_perm(hi, 0, 0x4443)];
+                dst[0] = elut[__byte_perm(lo, 0, 0x4440)];
+                dst[1] = elut[__byte_perm(lo, 0, 0x4441)];
+                dst[2] = elut[__byte_perm(lo, 0, 0x4442)];
+                dst[3] = elut[__byte_perm(lo, 0, 0x4443)];
+                dst[4] = elut[__byte_perm(hi, 0, 0x4440)];
+                dst[5] = elut[__byte_perm(hi, 0, 0x4441)];
+                dst[6] = elut[__byte_perm(hi, 0, 0x4442)];
+                dst[7] = elut[__byte_perm(hi, 0, 0x4443)];
             } else {
                 uint64_t word = 0;
 #pragma unroll 1
                 for (int d = 0; d < o.embed_dim; ++d) {
                     if ((d & 7) == 0) word = ke[j * EW + (d >> 3)];
-                    dst[d] = s_elut[(unsigned)(word >> (8 * (d & 7))) & 255u];
+                    dst[d] = elut[(unsigned)(word >> (8 * (d & 7))) & 255u];
                 }
             }
             dst[o.embed_dim + 0] = (float)trust;

@@ -17,8 +17,7 @@
 //                     by REDUX over the same tests.
 //
 // One block barrier per pass hands the double-buffered feature rows to a
-// coalesced 16-byte sweep done by all four warps.  See tick_ent.cuh for the
-// single-warp form this was derived from (kept for very small launches).
+// coalesced 16-byte sweep done by all four warps.
 
 #ifndef TL_TILE_WARPS
 #define TL_TILE_WARPS 2
@@ -38,7 +37,6 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int T = p.b.n_towns;
-    const int N = p.b.n_agents;
     const int t0 = blockIdx.x * p.towns_per_cta;
     const int n_towns = min(p.towns_per_cta, T - t0);
     if (n_towns <= 0) return;

@@ -40,8 +40,8 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 32;          // agents per phase-A pass
 constexpr int kMaxTownsPerCta = 8;  // towns sharing one CTA (grid form)
-constexpr int kMaxTownsPerWarp = 16;  // towns sharing one warp (entity form)
-constexpr int kMaxSocialLen = TL_MAX_SOCIAL_SLOTS * (32 + 3) + 4;
+constexpr int kMaxTownsPerWarp = 16;  // towns sharing one CTA (entity form)
+constexpr int kEntCache = 4;  // entity words per lane kept in registers (128 entities per town)
 
 thread_local char g_error[512] = "";
 std::atomic<int64_t> g_launches{0};
@@ -68,26 +68,10 @@ struct KParams {
     int32_t off_meta;      // ChunkMeta[kChunk] (grid form) / KpiAcc[towns_per_cta] (entity form)
     int32_t smem_bytes;
     int32_t chunk;         // entity form: agents per phase-A pass (<= 32)
-    int32_t mode;          // 0 entity-list form with role-parallel warps, 1 dense shared-memory grid form,
-                           // 2 entity-list form with one warp per CTA
+    int32_t mode;          // 0 entity-list form with role-parallel warps, 1 dense shared-memory grid form
     int32_t off_social;    // role form: staged relation rows of a pass (4 x double + 2 x embed words per edge)
     int32_t tmpl_mask;     // entity form: bit m set = a tile template for 16-byte misalignment m floats exists
     int32_t tmpl_off[4];   // entity form: float offset of template m inside the template area
-};
-
-struct ChunkMeta {
-    int32_t cx, cy;      // window centre
-    int32_t ox, oy;      // occupancy tile of the agent itself
-    int32_t town_slot;   // index of the agent's town inside the CTA
-    int32_t terminated;  // effective terminated flag of this tick
-    int32_t pad0, pad1;
-};
-
-struct TownMeta {
-    int32_t agent_begin, agent_end;
-    int32_t ent_begin, ent_end;
-    int32_t tick;
-    int32_t pad;
 };
 
 __device__ __forceinline__ int pos_x(int32_t p) { return (int)(int16_t)(p & 0xffff); }
@@ -98,19 +82,6 @@ __device__ __forceinline__ double scale_bias(double value, double factor) {
     if (factor <= 0.0) return value;
     if (value >= 0.0) return value * factor;
     return value / factor;
-}
-
-// Sum of n <= 8 doubles the way numpy's add.reduce does it for np.mean
-// (encoders/social.py:245-254): sequential below 8, the unrolled pairwise block at 8.
-__device__ __forceinline__ double np_sum_le8(const double (&a)[TL_MAX_SOCIAL_SLOTS], int n) {
-    if (n < 8) {
-        double res = 0.0;
-#pragma unroll
-        for (int i = 0; i < TL_MAX_SOCIAL_SLOTS; ++i)
-            if (i < n) res += a[i];
-        return res;
-    }
-    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
 // ---------------------------------------------------------------------------
@@ -267,582 +238,8 @@ struct KpiAcc {
     int starving, term, count;
 };
 
-// ---------------------------------------------------------------------------
-// The kernel
-// ---------------------------------------------------------------------------
-template <int VARIANT>
-__global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ KParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ TownMeta s_town[kMaxTownsPerCta];
-    __shared__ KpiAcc s_kpi[kMaxTownsPerCta];
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int T = p.b.n_towns;
-    const int N = p.b.n_agents;
-    const int t0 = blockIdx.x * p.towns_per_cta;
-    const int n_towns = min(p.towns_per_cta, T - t0);
-    if (n_towns <= 0) return;
-
-    const bool do_decay = p.phases & TL_PHASE_DECAY;
-    const bool do_reward = p.phases & TL_PHASE_REWARD;
-    const bool do_obs = p.phases & TL_PHASE_OBS;
-    const bool do_advance = p.phases & TL_PHASE_ADVANCE;
-    const bool do_state = do_decay || do_reward;
-
-    uint16_t* s_grid = reinterpret_cast<uint16_t*>(smem + p.off_grid);
-    uint16_t* s_ctype = p.off_ctype >= 0 ? reinterpret_cast<uint16_t*>(smem + p.off_ctype) : nullptr;
-    float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);
-    float* s_map = reinterpret_cast<float*>(smem + p.off_map);
-    ChunkMeta* s_meta = reinterpret_cast<ChunkMeta*>(smem + p.off_meta);
-
-    const int W = p.obs.window;
-    const int R = W >> 1;
-    const int W2 = W * W;
-    const int F = p.obs.n_features;
-    const int GW = p.b.grid_w, GH = p.b.grid_h;
-    const int map_elems = p.obs.n_channels * W2;
-
-    if (tid < n_towns) {
-        TownMeta m;
-        m.agent_begin = p.b.town_agent_off[t0 + tid];
-        m.agent_end = p.b.town_agent_off[t0 + tid + 1];
-        m.ent_begin = p.b.town_ent_off[t0 + tid];
-        m.ent_end = p.b.town_ent_off[t0 + tid + 1];
-        m.tick = p.b.town_tick[t0 + tid];
-        m.pad = 0;
-        s_town[tid] = m;
-    }
-    __syncthreads();
-    const int a_begin = s_town[0].agent_begin;
-    const int a_end = s_town[n_towns - 1].agent_end;
-    const int e_begin = s_town[0].ent_begin;
-    const int e_end = s_town[n_towns - 1].ent_end;
-    const int n_chunks = (a_end - a_begin + kChunk - 1) / kChunk;
-
-    // per-lane window coordinates of tile (lane + 32 k) are advanced incrementally
-    const int row0 = lane / W, col0 = lane - row0 * W;
-    const int drow = 32 / W, dcol = 32 - drow * W;
-
-    for (int it = 0; it < p.n_ticks; ++it) {
-        // ---- tick bookkeeping (core/sim_loop.py:635,659) ---------------------
-        if (tid < n_towns) {
-            if (do_advance) {
-                s_town[tid].tick += 1;
-                p.b.town_tick[t0 + tid] = s_town[tid].tick;
-            }
-            KpiAcc z;
-            z.rsum = z.rsq = z.hsum = z.late = z.wallet = 0.0;
-            z.hmin = 1e300;
-            z.starving = z.term = z.count = 0;
-            s_kpi[tid] = z;
-        }
-        // ---- stage the town grids (cache.py:16-41) ---------------------------
-        if (do_obs) {
-            const int words = (n_towns * p.grid_tiles + 1) >> 1;
-            uint32_t* g32 = reinterpret_cast<uint32_t*>(s_grid);
-            for (int i = tid; i < words; i += kThreads) g32[i] = 0u;
-            if (s_ctype) {
-                uint32_t* c32 = reinterpret_cast<uint32_t*>(s_ctype);
-                for (int i = tid; i < words; i += kThreads) c32[i] = 0u;
-            }
-        }
-        __syncthreads();
-        if (do_obs) {
-            for (int e = e_begin + tid; e < e_end; e += kThreads) {
-                const uint32_t w = p.b.ent[e];
-                int slot = 0;
-#pragma unroll
-                for (int s = 1; s < kMaxTownsPerCta; ++s)
-                    if (s < n_towns && e >= s_town[s].ent_begin) slot = s;
-                if (TL_ENT_X(w) >= GW || TL_ENT_Y(w) >= GH) continue;  // outside the declared grid: ignored, never out of bounds
-                const int idx = slot * p.grid_tiles + TL_ENT_Y(w) * GW + TL_ENT_X(w);
-                const unsigned kind = TL_ENT_KIND(w);
-                uint32_t* word = reinterpret_cast<uint32_t*>(s_grid) + (idx >> 1);
-                const int sh = (idx & 1) * 16;
-                if (kind == TL_KIND_AGENT) {
-                    atomicAdd(word, 1u << sh);
-                } else if (kind == TL_KIND_OBJECT) {
-                    if (TL_ENT_TILE(w)) {
-                        atomicAdd(word, 0x100u << sh);
-                        const unsigned ct = TL_ENT_CTYPE(w);
-                        if (s_ctype && ct > 0 && (int)ct <= p.obs.n_ctypes)
-                            atomicAdd(reinterpret_cast<uint32_t*>(s_ctype) + (idx >> 1), 1u << (sh + 4 * (ct - 1)));
-                    }
-                } else if (kind == TL_KIND_RESERVED) {
-                    atomicOr(word, 0x8000u << sh);
-                }
-            }
-        }
-        __syncthreads();
-
-        for (int chunk = 0; chunk < n_chunks; ++chunk) {
-            const int c_begin = a_begin + chunk * kChunk;
-            const int c_n = min(kChunk, a_end - c_begin);
-            // feature staging mirrors the 16-byte misalignment of the global rows
-            float* feat_g0 = do_obs ? p.oo.features + (size_t)it * p.oo.features_tick_stride + (size_t)c_begin * F : nullptr;
-            const int feat_mis = do_obs ? (int)((reinterpret_cast<uintptr_t>(feat_g0) >> 2) & 3) : 0;
-            float* feat_s0 = s_feat + feat_mis;
-
-            // =================== phase A: one thread per agent ==================
-            if (warp == 0) {
-                const bool active = lane < c_n;
-                const int a = c_begin + (active ? lane : 0);
-                int slot = 0;
-#pragma unroll
-                for (int s = 1; s < kMaxTownsPerCta; ++s)
-                    if (s < n_towns && a >= s_town[s].agent_begin) slot = s;
-                const TownMeta tm = s_town[slot];
-                const int tick = tm.tick;
-                double need[3] = {0.0, 0.0, 0.0};
-                uint32_t fl = 0;
-                bool terminated = false;
-                unsigned reason = 0;
-                int episode_tick = 0;
-                double reward_total = 0.0;
-                if (active) {
-                    need[0] = p.b.needs[a];
-                    need[1] = p.b.needs[(size_t)N + a];
-                    need[2] = p.b.needs[2 * (size_t)N + a];
-                    fl = p.b.flags[a];
-                    episode_tick = p.b.episode_tick[a];
-                    const unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
-                    if (do_decay) {  // world/grid.py:1439-1455
-#pragma unroll
-                        for (int k = 0; k < TL_N_NEEDS; ++k) {
-                            double mult = 1.0;
-                            if (p.rew.decay_personality && profile != 0) {
-                                mult = p.rew.need_mult[profile][k];
-                                if (mult <= 0.0) mult = 1.0;
-                            }
-                            const double adjusted = p.rew.decay_rate[k] * mult;
-                            need[k] = fmax(0.0, need[k] - adjusted);
-                            p.b.needs[(size_t)k * N + a] = need[k];
-                        }
-                    }
-                    if (do_state && p.rew.fuse_faint) {  // lifecycle/manager.py:39-45
-                        fl = (fl & ~TL_F_FAINTED) | (need[0] <= p.rew.faint_threshold ? TL_F_FAINTED : 0u);
-                        p.b.flags[a] = fl;
-                    }
-                    terminated = (fl & (TL_F_TERMINATED | TL_F_FAINTED)) != 0;
-                    reason = (fl & TL_F_REASON_MASK) >> TL_F_REASON_SHIFT;
-                    if (reason == 0 && (fl & TL_F_FAINTED)) reason = 1;
-                    if (do_advance) {  // world/core/context.py:283-289
-                        const int span = max(1, p.obs.ticks_per_day);
-                        episode_tick = (episode_tick + 1) % span;
-                        p.b.episode_tick[a] = episode_tick;
-                    }
-                    if (do_reward) {
-                        RewardResult rr;
-                        const RewardIn rin = load_reward_in(p, a);
-                        reward_agent(p.rew, rin, tick, need, fl, terminated, reason, rr);
-                        p.b.term_block_tick[a] = rr.block;
-                        p.b.episode_total[a] = rr.cumulative;
-                        reward_total = rr.total;
-                        if (p.ro.reward) p.ro.reward[(size_t)it * p.ro.reward_tick_stride + a] = (float)rr.total;
-                        if (p.ro.comps) {
-                            double* dst = p.ro.comps + (size_t)it * p.ro.comps_tick_stride + (size_t)a * TL_N_COMPS;
-#pragma unroll
-                            for (int i = 0; i < TL_N_COMPS; i += 2)
-                                *reinterpret_cast<double2*>(dst + i) = make_double2(rr.comps[i], rr.comps[i + 1]);
-                        }
-                    }
-                    if (do_state && p.ro.terminated)
-                        p.ro.terminated[(size_t)it * p.ro.terminated_tick_stride + a] = terminated ? 1 : 0;
-                }
-                // ---- per-town KPIs: segmented warp-shuffle reduction ------------
-                if (do_state && p.ro.kpi) {
-                    const int seg = active ? slot : -1 - lane;  // inactive lanes are their own segment
-                    const double hunger = need[0];
-                    const double late = active ? (double)p.b.lateness[a] : 0.0;
-                    const double wal = active ? p.b.wallet[a] : 0.0;
-                    auto add = [](double x, double y) { return x + y; };
-                    auto addi = [](int x, int y) { return x + y; };
-                    auto mn = [](double x, double y) { return fmin(x, y); };
-                    const double rsum = seg_reduce(reward_total, seg, lane, add);
-                    const double rsq = seg_reduce(reward_total * reward_total, seg, lane, add);
-                    const double hsum = seg_reduce(hunger, seg, lane, add);
-                    const double hmin = seg_reduce(active ? hunger : 1e300, seg, lane, mn);
-                    const double lsum = seg_reduce(late, seg, lane, add);
-                    const double wsum = seg_reduce(wal, seg, lane, add);
-                    const int starving = seg_reduce((int)(active && hunger <= p.rew.starvation_threshold), seg, lane, addi);
-                    const int term = seg_reduce((int)terminated, seg, lane, addi);
-                    const int cnt = seg_reduce((int)active, seg, lane, addi);
-                    const int prev_seg = __shfl_up_sync(0xffffffffu, seg, 1);
-                    if (active && (lane == 0 || prev_seg != seg)) {  // segment head; chunks arrive in order
-                        KpiAcc& k = s_kpi[slot];
-                        k.rsum += rsum;
-                        k.rsq += rsq;
-                        k.hsum += hsum;
-                        k.hmin = fmin(k.hmin, hmin);
-                        k.late += lsum;
-                        k.wallet += wsum;
-                        k.starving += starving;
-                        k.term += term;
-                        k.count += cnt;
-                    }
-                }
-                // ---- scalar features (encoders/features.py:43-404) ------------
-                if (do_obs && active) {
-                    float* f = feat_s0 + lane * F;
-                    const TlObsParams& o = p.obs;
-                    f[TL_FEAT_NEED_HUNGER] = (float)need[0];
-                    f[TL_FEAT_NEED_HYGIENE] = (float)need[1];
-                    f[TL_FEAT_NEED_ENERGY] = (float)need[2];
-                    f[TL_FEAT_WALLET] = (float)p.b.wallet[a];
-                    f[TL_FEAT_LATENESS] = (float)p.b.lateness[a];
-                    f[TL_FEAT_ON_SHIFT] = (fl & TL_F_ON_SHIFT) ? 1.0f : 0.0f;
-                    int m = tick % o.ticks_per_day;
-                    if (m < 0) m += o.ticks_per_day;
-                    const float2 sc = *reinterpret_cast<const float2*>(o.time_lut + 2 * m);
-                    f[TL_FEAT_TIME_SIN] = sc.x;
-                    f[TL_FEAT_TIME_COS] = sc.y;
-                    f[TL_FEAT_ATTENDANCE] = (float)p.b.attendance[a];
-                    f[TL_FEAT_WAGES_WITHHELD] = (float)p.b.wages_withheld[a];
-                    unsigned st = (fl & TL_F_SHIFT_MASK) >> TL_F_SHIFT_SHIFT;
-                    if (st > 4) st = 0;
-#pragma unroll
-                    for (unsigned k = 0; k < 5; ++k) f[TL_FEAT_SHIFT_PRE + k] = (k == st) ? 1.0f : 0.0f;
-                    const int slot_idx = p.b.slot[a];
-                    f[TL_FEAT_SLOT_NORM] = (slot_idx >= 0 && slot_idx < o.max_slots)
-                                               ? o.slot_lut[slot_idx]
-                                               : (float)((double)slot_idx / (double)o.max_slots);
-                    f[TL_FEAT_CTX_RESET] = ((fl & TL_F_CTX_RESET) || terminated) ? 1.0f : 0.0f;  // service.py:224-229
-                    f[TL_FEAT_EPISODE_PROGRESS] =
-                        episode_tick <= 0 ? 0.0f : o.progress_lut[min(episode_tick, o.ticks_per_day)];
-                    // rivalry_top(agent, max_edges): rows are pre-sorted (features.py:232-248)
-                    {
-                        const int K = p.b.max_edges;
-                        int nr = min((int)p.b.riv_count[a], K);
-                        nr = min(nr, o.rivalry_max_edges);
-                        double mx = 0.0;
-                        int avoid = 0;
-                        for (int j = 0; j < nr; ++j) {
-                            const double v = p.b.riv_score[(size_t)a * K + j];
-                            if (j == 0) mx = v;
-                            avoid += (v >= o.avoid_threshold) ? 1 : 0;
-                        }
-                        f[TL_FEAT_RIVALRY_MAX] = (float)mx;
-                        f[TL_FEAT_RIVALRY_AVOID] = (float)avoid;
-                    }
-                    f[TL_FEAT_LAST_HASH] = p.b.last_action_hash[a];
-                    f[TL_FEAT_LAST_SUCCESS] = (fl & TL_F_LAST_SUCCESS) ? 1.0f : 0.0f;
-                    f[TL_FEAT_LAST_DURATION] = (float)p.b.last_action_duration[a];
-                    f[TL_FEAT_RESERVATION] = (fl & TL_F_RESERVATION) ? 1.0f : 0.0f;
-                    f[TL_FEAT_IN_QUEUE] = (fl & TL_F_IN_QUEUE) ? 1.0f : 0.0f;
-                    // nearest object per landmark type: first minimum of the squared
-                    // distance in insertion order (world/observe.py:109-147)
-                    const int32_t pw = p.b.pos[a];
-                    const int cx = pos_x(pw), cy = pos_y(pw);
-                    int best_d2[5] = {-1, -1, -1, -1, -1};
-                    int best_dx[5] = {0, 0, 0, 0, 0}, best_dy[5] = {0, 0, 0, 0, 0};
-                    const bool all_types = o.landmark_base >= 0;
-                    const int e_obj = tm.ent_begin + (tm.agent_end - tm.agent_begin);
-                    for (int e = e_obj; e < tm.ent_end; ++e) {
-                        const uint32_t w = p.b.ent[e];
-                        if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w)) continue;
-                        const int lt = (int)TL_ENT_LTYPE(w);
-                        if (lt == 0 || (!all_types && lt != o.path_hint_ltype)) continue;
-                        const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
-                        const int d2 = dx * dx + dy * dy;
-#pragma unroll
-                        for (int l = 1; l <= 4; ++l) {
-                            if (l == lt && (best_d2[l] < 0 || d2 < best_d2[l])) {
-                                best_d2[l] = d2;
-                                best_dx[l] = dx;
-                                best_dy[l] = dy;
-                            }
-                        }
-                    }
-                    {  // _encode_path_hint, features.py:251-286
-                        double north = 0.0, south = 0.0, east = 0.0, west = 0.0;
-                        int hd2 = -1, hdx = 0, hdy = 0;
-#pragma unroll
-                        for (int l = 1; l <= 4; ++l)
-                            if (l == o.path_hint_ltype) {
-                                hd2 = best_d2[l];
-                                hdx = best_dx[l];
-                                hdy = best_dy[l];
-                            }
-                        if (hd2 >= 0) {
-                            const int norm = abs(hdx) + abs(hdy);
-                            if (norm != 0) {
-                                const double dn = (double)norm;
-                                north = fmax(0.0, (double)-hdy) / dn;
-                                south = fmax(0.0, (double)hdy) / dn;
-                                east = fmax(0.0, (double)hdx) / dn;
-                                west = fmax(0.0, (double)-hdx) / dn;
-                            }
-                        }
-                        f[TL_FEAT_PATH_NORTH + 0] = (float)north;
-                        f[TL_FEAT_PATH_NORTH + 1] = (float)south;
-                        f[TL_FEAT_PATH_NORTH + 2] = (float)east;
-                        f[TL_FEAT_PATH_NORTH + 3] = (float)west;
-                    }
-                    if (all_types) {  // _encode_landmarks, features.py:333-356
-#pragma unroll
-                        for (int l = 1; l <= 4; ++l) {
-                            float* dst = f + o.landmark_base + 3 * (l - 1);
-                            if (best_d2[l] < 0) {
-                                dst[0] = dst[1] = dst[2] = 0.0f;
-                            } else {
-                                // sqrt of an exact integer: equals np.hypot after the float32 store
-                                const double distance = sqrt((double)best_d2[l]);
-                                const double norm = distance > 0.0 ? distance : 1.0;
-                                dst[0] = (float)((double)best_dx[l] / norm);
-                                dst[1] = (float)((double)best_dy[l] / norm);
-                                dst[2] = (float)distance;
-                            }
-                        }
-                    }
-                    if (o.personality_base >= 0) {  // features.py:359-380
-                        const bool has = p.b.personality != nullptr;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                            f[o.personality_base + k] = has ? p.b.personality[(size_t)k * N + a] : 0.0f;
-                    }
-                    ChunkMeta cm;
-                    cm.cx = cx;
-                    cm.cy = cy;
-                    const uint32_t self_e = p.b.ent[tm.ent_begin + (a - tm.agent_begin)];
-                    cm.ox = TL_ENT_X(self_e);
-                    cm.oy = TL_ENT_Y(self_e);
-                    cm.town_slot = slot;
-                    cm.terminated = terminated ? 1 : 0;
-                    cm.pad0 = cm.pad1 = 0;
-                    s_meta[lane] = cm;
-                }
-            }
-            if (!do_obs) continue;  // uniform for the CTA
-            __syncthreads();
-
-            // =================== phase B: one warp per agent =====================
-            for (int i = warp; i < c_n; i += kWarps) {
-                const int a = c_begin + i;
-                const ChunkMeta cm = s_meta[i];
-                const uint16_t* grid = s_grid + cm.town_slot * p.grid_tiles;
-                const uint16_t* cgrid = s_ctype ? s_ctype + cm.town_slot * p.grid_tiles : nullptr;
-                float* frow = feat_s0 + i * F;
-                const TlObsParams& o = p.obs;
-
-                // -- prefetch the relation rows (social.py:165-209): lane j holds relation j
-                const int K = p.b.max_edges, EW = p.b.embed_words;
-                const int n_ties = min((int)p.b.tie_count[a], p.b.max_edges);
-                int n_rel = n_ties;
-                int source = (n_ties > 0 && o.social_base >= 0) ? 1 : 0;
-                double trust = 0.0, fam = 0.0, riv = 0.0;
-                const uint64_t* emb = nullptr;
-                if (o.social_base >= 0) {
-                    if (n_ties > 0) {
-                        if (lane < n_ties) {
-                            const size_t r = (size_t)a * K + lane;
-                            trust = p.b.tie_trust[r];
-                            fam = p.b.tie_fam[r];
-                            riv = p.b.tie_riv[r];
-                            emb = p.b.tie_embed + r * EW;
-                        }
-                    } else {
-                        n_rel = min(min((int)p.b.riv_count[a], K), o.top_rivals);  // rivalry_top(agent, top_rivals)
-                        source = n_rel > 0 ? 2 : 0;
-                        if (lane < n_rel) {
-                            const size_t r = (size_t)a * K + lane;
-                            riv = p.b.riv_score[r];
-                            emb = p.b.riv_embed + r * EW;
-                        }
-                    }
-                }
-
-                // -- window gather (encoders/map.py:39-148, 151-243) -----------
-                float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)a * map_elems;
-                const int map_mis = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
-                float* st = s_map + warp * p.map_stride + map_mis;
-                int others_sum = 0, objects_sum = 0, reserved_sum = 0;
-                unsigned nearest = 0xffffffffu;
-                int row = row0, col = col0;
-                for (int tile = lane; tile < W2; tile += 32) {
-                    const int dx = col - R, dy = row - R;
-                    const int x = cm.cx + dx, y = cm.cy + dy;
-                    const bool inb = (unsigned)x < (unsigned)GW && (unsigned)y < (unsigned)GH;
-                    const unsigned w = inb ? grid[y * GW + x] : 0u;
-                    const int agents = w & 0xff, objects = (w >> 8) & 0x7f, reserved = w >> 15;
-                    const bool centre = (dx == 0 && dy == 0);
-                    // LocalSummary (map.py:88-103): self excluded on the centre tile only
-                    const int cnt = agents - ((centre && agents > 0) ? 1 : 0);
-                    others_sum += cnt;
-                    objects_sum += objects;
-                    reserved_sum += reserved;
-                    if (cnt > 0 && !centre) nearest = min(nearest, (unsigned)(dx * dx + dy * dy));
-                    st[tile] = centre ? 1.0f : 0.0f;  // map.py:69 / :185-186
-                    if (VARIANT == TL_VARIANT_COMPACT) {
-                        const bool own = (x == cm.ox && y == cm.oy);
-                        const int others = agents - (own ? 1 : 0);  // map.py:198
-                        const bool norm = o.normalize_counts != 0;
-                        st[W2 + tile] = (float)(norm ? min(others, 1) : others);
-                        st[2 * W2 + tile] = (float)(norm ? min(objects, 1) : objects);
-                        st[3 * W2 + tile] = (float)reserved;
-                        const unsigned cw = (cgrid && inb) ? cgrid[y * GW + x] : 0u;
-                        for (int k = 0; k < o.n_ctypes; ++k) {
-                            const int c = (cw >> (4 * k)) & 15;
-                            st[(4 + k) * W2 + tile] = (float)(norm ? min(c, 1) : c);
-                        }
-                        const bool blockd = others > 0 || objects > 0 || reserved || centre;  // map.py:231-241
-                        st[(4 + o.n_ctypes) * W2 + tile] = blockd ? 0.0f : 1.0f;
-                    } else {
-                        st[W2 + tile] = agents > 0 ? 1.0f : 0.0f;  // includes the observer (map.py:109-110)
-                        st[2 * W2 + tile] = objects > 0 ? 1.0f : 0.0f;
-                        st[3 * W2 + tile] = (float)reserved;
-                        if (VARIANT == TL_VARIANT_FULL) {
-                            st[4 * W2 + tile] = o.path_lut[tile];
-                            st[5 * W2 + tile] = o.path_lut[W2 + tile];
-                        }
-                    }
-                    col += dcol;
-                    row += drow;
-                    if (col >= W) {
-                        col -= W;
-                        row += 1;
-                    }
-                }
-                others_sum = __reduce_add_sync(0xffffffffu, others_sum);
-                objects_sum = __reduce_add_sync(0xffffffffu, objects_sum);
-                reserved_sum = __reduce_add_sync(0xffffffffu, reserved_sum);
-                nearest = __reduce_min_sync(0xffffffffu, nearest);
-                const int nearest_d2 = nearest == 0xffffffffu ? 0 : (int)nearest;
-                if (lane == 0) {  // _encode_local_summary, features.py:289-330 via host LUTs
-                    frow[TL_FEAT_AGENT_RATIO] = o.agent_ratio_lut[min(others_sum, W2 - 1)];
-                    frow[TL_FEAT_OBJECT_RATIO] = o.tile_ratio_lut[min(objects_sum, W2)];
-                    frow[TL_FEAT_RESERVED_RATIO] = o.tile_ratio_lut[min(reserved_sum, W2)];
-                    frow[TL_FEAT_NEAREST] = o.nearest_lut[nearest_d2];
-                }
-
-                // -- social snippet (encoders/social.py:27-163) ----------------
-                int filled = 0;
-                if (o.social_base >= 0) {
-                    const int slot_dim = o.embed_dim + 3;
-                    const int total_slots = o.top_friends + o.top_rivals;
-                    const int social_len = total_slots * slot_dim + (o.include_aggregates ? 4 : 0);
-                    float* srow = frow + o.social_base;
-                    for (int k = lane; k < social_len; k += 32) srow[k] = 0.0f;
-                    // stable descending rank == position in sorted(..., reverse=True)
-                    const double key = trust + fam;
-                    int frank = 0;
-                    for (int j = 0; j < n_rel; ++j) {
-                        const double kj = __shfl_sync(0xffffffffu, key, j);
-                        frank += (kj > key || (kj == key && j < lane)) ? 1 : 0;
-                    }
-                    const bool valid = lane < n_rel;
-                    const bool is_friend = valid && frank < o.top_friends;
-                    const int n_friends = min(n_rel, o.top_friends);
-                    int rrank = 0;
-                    for (int j = 0; j < n_rel; ++j) {
-                        const double rj = __shfl_sync(0xffffffffu, riv, j);
-                        const int fj = __shfl_sync(0xffffffffu, (int)is_friend, j);
-                        if (!fj) rrank += (rj > riv || (rj == riv && j < lane)) ? 1 : 0;
-                    }
-                    const bool is_rival = valid && !is_friend && rrank < o.top_rivals;
-                    const int my_slot = is_friend ? frank : (is_rival ? n_friends + rrank : -1);
-                    filled = n_friends + min(o.top_rivals, n_rel - n_friends);
-                    __syncwarp();
-                    if (my_slot >= 0) {
-                        float* dst = srow + my_slot * slot_dim;
-                        for (int d = 0; d < o.embed_dim; ++d) {  // social.py:236-242, float32 division
-                            const unsigned byte = (unsigned)(emb[d >> 3] >> (8 * (d & 7))) & 255u;
-                            dst[d] = __fdiv_rn((float)byte, 255.0f);
-                        }
-                        dst[o.embed_dim + 0] = (float)trust;
-                        dst[o.embed_dim + 1] = (float)fam;
-                        dst[o.embed_dim + 2] = (float)riv;
-                    }
-                    if (o.include_aggregates && filled > 0) {  // social.py:90-105, 245-254
-                        double tv[TL_MAX_SOCIAL_SLOTS], rv[TL_MAX_SOCIAL_SLOTS];
-#pragma unroll
-                        for (int s = 0; s < TL_MAX_SOCIAL_SLOTS; ++s) {
-                            const unsigned owners = __ballot_sync(0xffffffffu, my_slot == s);
-                            const int src = owners ? __ffs(owners) - 1 : 0;
-                            const double t_s = __shfl_sync(0xffffffffu, trust, src);
-                            const double r_s = __shfl_sync(0xffffffffu, riv, src);
-                            tv[s] = owners ? t_s : 0.0;
-                            rv[s] = owners ? r_s : 0.0;
-                        }
-                        if (lane == 0) {
-                            double tmax = tv[0], rmax = rv[0];
-#pragma unroll
-                            for (int s = 1; s < TL_MAX_SOCIAL_SLOTS; ++s)
-                                if (s < filled) {
-                                    tmax = fmax(tmax, tv[s]);
-                                    rmax = fmax(rmax, rv[s]);
-                                }
-                            float* agg = srow + total_slots * slot_dim;
-                            agg[0] = (float)(np_sum_le8(tv, filled) / (double)filled);
-                            agg[1] = (float)tmax;
-                            agg[2] = (float)(np_sum_le8(rv, filled) / (double)filled);
-                            agg[3] = (float)rmax;
-                        }
-                    }
-                }
-                __syncwarp();
-
-                // -- 16-byte vectorised coalesced stores -----------------------
-                {
-                    const int head = (4 - map_mis) & 3;
-                    if (lane < head) mrow_g[lane] = st[lane];
-                    const int nvec = (map_elems - head) >> 2;
-                    float4* g4 = reinterpret_cast<float4*>(mrow_g + head);
-                    const float4* s4 = reinterpret_cast<const float4*>(st + head);
-                    for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
-                    const int tail0 = head + (nvec << 2);
-                    if (lane < map_elems - tail0) mrow_g[tail0 + lane] = st[tail0 + lane];
-                }
-                {
-                    float* frow_g = feat_g0 + (size_t)i * F;
-                    const int mis = (int)((reinterpret_cast<uintptr_t>(frow_g) >> 2) & 3);
-                    const int head = min((4 - mis) & 3, F);
-                    if (lane < head) frow_g[lane] = frow[lane];
-                    const int nvec = (F - head) >> 2;
-                    float4* g4 = reinterpret_cast<float4*>(frow_g + head);
-                    const float4* s4 = reinterpret_cast<const float4*>(frow + head);
-                    for (int v = lane; v < nvec; v += 32) g4[v] = s4[v];
-                    const int tail0 = head + (nvec << 2);
-                    if (lane < F - tail0) frow_g[tail0 + lane] = frow[tail0 + lane];
-                }
-                if (p.oo.summary && lane < TL_N_SUMMARY) {
-                    int v = 0;
-                    if (lane == TL_SUM_OTHER_AGENTS) v = others_sum;
-                    else if (lane == TL_SUM_OBJECTS) v = objects_sum;
-                    else if (lane == TL_SUM_RESERVED) v = reserved_sum;
-                    else if (lane == TL_SUM_NEAREST_D2) v = nearest_d2;
-                    else if (lane == TL_SUM_FILLED_SLOTS) v = filled;
-                    else if (lane == TL_SUM_RELATION_SOURCE) v = source;
-                    p.oo.summary[(size_t)it * p.oo.summary_tick_stride + (size_t)a * TL_N_SUMMARY + lane] = v;
-                }
-            }
-            __syncthreads();  // staging rows are reused by the next chunk
-        }
-
-        // ---- per-town KPI rows --------------------------------------------------
-        if (do_state && p.ro.kpi) {
-            __syncthreads();
-            if (tid < n_towns) {
-                const KpiAcc k = s_kpi[tid];
-                float* dst = p.ro.kpi + (size_t)it * p.ro.kpi_tick_stride + (size_t)(t0 + tid) * TL_N_KPI;
-                const double n = (double)k.count;
-                dst[TL_KPI_REWARD_SUM] = (float)k.rsum;
-                dst[TL_KPI_REWARD_SUMSQ] = (float)k.rsq;
-                dst[TL_KPI_HUNGER_MIN] = k.count ? (float)k.hmin : 0.0f;
-                dst[TL_KPI_HUNGER_MEAN] = k.count ? (float)(k.hsum / n) : 0.0f;
-                dst[TL_KPI_STARVING] = (float)k.starving;
-                dst[TL_KPI_TERMINATED] = (float)k.term;
-                dst[TL_KPI_LATENESS_MEAN] = k.count ? (float)(k.late / n) : 0.0f;
-                dst[TL_KPI_WALLET_MEAN] = k.count ? (float)(k.wallet / n) : 0.0f;
-            }
-        }
-        __syncthreads();  // state written this tick is visible to the CTA's next tick
-    }
-}
-
 #include "agent_roles.cuh"
-#include "tick_ent.cuh"
+#include "tick_grid.cuh"
 #include "tick_roles.cuh"
 
 // Backward GAE scan, one thread per agent, coalesced over the agent axis of the time-major rollout
@@ -970,11 +367,10 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     kp.mode = avg_entities > 384 ? 1 : 0;
     if (mode_env && !strcmp(mode_env, "grid")) kp.mode = 1;
     if (mode_env && !strcmp(mode_env, "ent")) kp.mode = 0;
-    if (mode_env && !strcmp(mode_env, "ent1")) kp.mode = 2;
 
     int grid = 0, threads = kThreads;
     if (kp.mode != 1) {
-        threads = kp.mode == 0 ? 32 * kRoleWarps : 32;
+        threads = 32 * kRoleWarps;
         int chunk = env_int("TL_CHUNK", 32);
         if (chunk < 1) chunk = 1;
         if (chunk > 32) chunk = 32;
@@ -984,11 +380,11 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         if (tpc > kMaxTownsPerWarp) tpc = kMaxTownsPerWarp;
         if (towns_per_cta_override <= 0 && !getenv("TL_TPC")) {
             // small batches: prefer more, emptier CTAs over idle SMs (measured on configs[1]:
-            // 2 towns per 4-warp CTA beat 1, 3 and 4; the single-warp form wants >= 8 warps per SM)
+            // 2 towns per 4-warp CTA beat 1, 3 and 4)
             int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-            const int want = kp.mode == 0 ? 3 * sms : 8 * sms;
-            const int floor_tpc = (kp.mode == 0 && 2 * avg_agents <= chunk) ? 2 : 1;
+            const int want = 3 * sms;
+            const int floor_tpc = 2 * avg_agents <= chunk ? 2 : 1;
             while (tpc > floor_tpc && (b->n_towns + tpc - 1) / tpc < want) --tpc;
         }
         {
@@ -1000,8 +396,8 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         kp.off_grid = 0;
         kp.off_ctype = -1;
         kp.off_feat = off;
-        // role-parallel form: two row buffers of ((chunk * F + 4 + 3) & ~3) floats
-        off += do_obs ? (kp.mode == 0 ? 2 : 1) * round_up((chunk * kp.feat_stride + 4) * 4, 16) : 16;
+        // two row buffers of ((chunk * F + 4 + 3) & ~3) floats
+        off += do_obs ? 2 * round_up((chunk * kp.feat_stride + 4) * 4, 16) : 16;
         kp.off_map = off;
         kp.tmpl_mask = 0;
         if (do_obs) {
@@ -1022,7 +418,7 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         kp.off_meta = off;
         off += round_up((int)sizeof(KpiAcc) * tpc, 16);
         kp.off_social = off;
-        if (kp.mode == 0 && do_obs) off += chunk * b->max_edges * (4 * 8 + 2 * 8 * b->embed_words) + 256 * 4;
+        if (do_obs) off += chunk * b->max_edges * (4 * 8 + 2 * 8 * b->embed_words) + 256 * 4;
         kp.smem_bytes = off;
         if (off > max_smem) return set_error("observation staging does not fit in shared memory"), TL_ERR_UNSUPPORTED;
         kp.towns_per_cta = tpc;
@@ -1091,22 +487,6 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
             case TL_VARIANT_COMPACT:
                 if (win == 7 && kp.obs.n_ctypes == 0 && !generic) return run(tick_kernel_roles<TL_VARIANT_COMPACT, 7>);
                 return run(tick_kernel_roles<TL_VARIANT_COMPACT, 0>);
-            default: return set_error("unknown variant"), TL_ERR_ARG;
-        }
-    }
-    if (kp.mode == 2) {
-        const bool generic = getenv("TL_GENERIC") != nullptr;
-        const int win = do_obs ? kp.obs.window : 0;
-        switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
-            case TL_VARIANT_HYBRID:
-                if (win == 11 && !generic) return run(tick_kernel_ent<TL_VARIANT_HYBRID, 11>);
-                return run(tick_kernel_ent<TL_VARIANT_HYBRID, 0>);
-            case TL_VARIANT_FULL:
-                if (win == 11 && !generic && (((uintptr_t)kp.oo.map) & 7) == 0) return run(tick_kernel_ent<TL_VARIANT_FULL, 11>);
-                return run(tick_kernel_ent<TL_VARIANT_FULL, 0>);
-            case TL_VARIANT_COMPACT:
-                if (win == 7 && kp.obs.n_ctypes == 0 && !generic) return run(tick_kernel_ent<TL_VARIANT_COMPACT, 7>);
-                return run(tick_kernel_ent<TL_VARIANT_COMPACT, 0>);
             default: return set_error("unknown variant"), TL_ERR_ARG;
         }
     }
