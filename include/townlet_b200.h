@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 1
+#define TL_ABI_VERSION 2
 
 #define TL_N_NEEDS 3          /* hunger, hygiene, energy (snapshot.py:15) */
 #define TL_MAX_EDGES 8        /* upper bound for max_edges (ledger capacity) */
@@ -70,6 +70,40 @@ extern "C" {
 #define TL_PHASE_REWARD 2u
 #define TL_PHASE_OBS 4u
 #define TL_PHASE_ADVANCE 8u /* tick += 1, episode_tick = (episode_tick+1) % tpd (world/core/context.py:283-289) */
+/* phases upstream of the hot path; they need TlDynamicsParams (tl_tick_world) */
+#define TL_PHASE_ACTIONS 16u      /* apply the tick's action words: moves + outcome bookkeeping
+                                     (world/actions.py:44-105, world/systems/affordances.py:105-229) */
+#define TL_PHASE_SOCIAL_DECAY 32u /* RelationshipService.decay (world/agents/relationships_service.py:165-191) */
+
+/*
+ * Action word (uint32), one per agent and tick; what process_actions leaves on the agent snapshot.
+ *   bits  0- 3  kind   TL_ACT_*; 0 = no action this tick (nothing is recorded)
+ *   bit   4     success as resolved by the host services for kinds other than move
+ *                      (queue grant, affordance start / release, chat); ignored for a move with a position
+ *   bit   5     has_position (move only; a move without one is recorded as unsuccessful, affordances.py:157)
+ *   bits  6-15  x      town-relative target tile of a move
+ *   bits 16-25  y
+ *   bits 26-31  duration 0..63 (action["duration"], default 1)
+ */
+#define TL_ACT_NONE 0u
+#define TL_ACT_MOVE 1u
+#define TL_ACT_NOOP 2u
+#define TL_ACT_WAIT 3u
+#define TL_ACT_REQUEST 4u
+#define TL_ACT_START 5u
+#define TL_ACT_RELEASE 6u
+#define TL_ACT_CHAT 7u
+#define TL_ACT_BLOCKED 8u
+#define TL_N_ACT_KINDS 16
+#define TL_ACT_KIND(a) ((a) & 15u)
+#define TL_ACT_SUCCESS(a) (((a) >> 4) & 1u)
+#define TL_ACT_HAS_POS(a) (((a) >> 5) & 1u)
+#define TL_ACT_X(a) ((int)(((a) >> 6) & 1023u))
+#define TL_ACT_Y(a) ((int)(((a) >> 16) & 1023u))
+#define TL_ACT_DURATION(a) ((int)((a) >> 26))
+#define TL_ACT_PACK(kind, success, has_pos, x, y, duration)                                        \
+    (((uint32_t)(kind) & 15u) | (((uint32_t)(success) & 1u) << 4) | (((uint32_t)(has_pos) & 1u) << 5) | \
+     (((uint32_t)(x) & 1023u) << 6) | (((uint32_t)(y) & 1023u) << 16) | (((uint32_t)(duration) & 63u) << 26))
 
 /*
  * Entity word (uint32), one per thing that occupies a tile of a town.
@@ -219,10 +253,10 @@ typedef struct TlTownBatch {
     int32_t* town_tick;            /* [T] world.tick */
 
     /* entities */
-    const uint32_t* ent; /* [E] */
+    uint32_t* ent; /* [E]; the agents' own words are rewritten by TL_PHASE_ACTIONS (spatial index, world/spatial.py:62-83) */
 
     /* agents: identity / geometry */
-    const int32_t* pos; /* [N] window centre snapshot.position: (x & 0xffff) | (y << 16), int16 each, town-relative */
+    int32_t* pos; /* [N] window centre snapshot.position: (x & 0xffff) | (y << 16), int16 each, town-relative */
 
     /* agents: float64 state (grid.py / snapshot.py fields stay float64) */
     double* needs;                /* [3][N] hunger, hygiene, energy */
@@ -237,24 +271,25 @@ typedef struct TlTownBatch {
     /* agents: integer state */
     int32_t* term_block_tick;            /* [N] RewardEngine._termination_block or TL_TERM_BLOCK_NONE */
     const int32_t* lateness;             /* [N] lateness_counter */
-    const int32_t* last_action_duration; /* [N] */
+    int32_t* last_action_duration;       /* [N] */
     int32_t* episode_tick;               /* [N] */
     const int32_t* slot;                 /* [N] embedding slot (host allocator, embedding.py:35) */
     uint32_t* flags;                     /* [N] TL_F_* */
-    const float* last_action_hash;       /* [N] blake2s(last_action_id)[:4]/2^32 (features.py:194-200) */
+    float* last_action_hash;             /* [N] blake2s(last_action_id)[:4]/2^32 (features.py:194-200) */
     const float* personality;            /* [3][N] extroversion, forgiveness, ambition; may be NULL */
 
-    /* relationship ties in ledger insertion order (social.py:171-186) */
-    const uint8_t* tie_count;  /* [N] */
-    const uint64_t* tie_embed; /* [N][K][EW] blake2s(other_id) digest bytes, little-endian words */
-    const double* tie_trust;   /* [N][K] */
-    const double* tie_fam;     /* [N][K] */
-    const double* tie_riv;     /* [N][K] */
+    /* relationship ties in ledger insertion order (social.py:171-186); rows are decayed and compacted in
+     * place by TL_PHASE_SOCIAL_DECAY (entries at and beyond the count are zero afterwards) */
+    uint8_t* tie_count;  /* [N] */
+    uint64_t* tie_embed; /* [N][K][EW] blake2s(other_id) digest bytes, little-endian words */
+    double* tie_trust;   /* [N][K] */
+    double* tie_fam;     /* [N][K] */
+    double* tie_riv;     /* [N][K] */
 
     /* rivalry edges as returned by rivalry_top(agent, K): already sorted (rivalry.py:101-110) */
-    const uint8_t* riv_count;  /* [N] */
-    const uint64_t* riv_embed; /* [N][K][EW] */
-    const double* riv_score;   /* [N][K] */
+    uint8_t* riv_count;  /* [N] */
+    uint64_t* riv_embed; /* [N][K][EW] */
+    double* riv_score;   /* [N][K] */
 } TlTownBatch;
 
 /* Observation parameters derived from SimulationConfig (config/observations.py). */
@@ -332,12 +367,36 @@ typedef struct TlRewardOut {
     int64_t kpi_tick_stride;
 } TlRewardOut;
 
+/*
+ * World dynamics around the hot path, in WorldContext.tick order
+ * (world/core/context.py:229-289): actions are applied first, the ledgers decay in the
+ * "relationships" system step after need decay, both before reward and observation.
+ */
+typedef struct TlDynamicsParams {
+    /* RelationshipLedger.decay (world/relationships.py:78-89): a value moves towards 0 by its decay
+     * (no change when the decay is <= 0); a tie whose three values are 0.0 afterwards is evicted */
+    double trust_decay;
+    double familiarity_decay;
+    double tie_rivalry_decay;
+    /* RivalryLedger.decay(ticks=1) (world/rivalry.py:68-83): clamp(v - decay_per_tick, min, max);
+     * an edge at or below the eviction threshold is evicted */
+    double rivalry_decay_per_tick;
+    double rivalry_min;
+    double rivalry_max;
+    double rivalry_eviction_threshold;
+    /* action words of the launch, [n_ticks][N] (tick stride in elements, 0 = the same row every tick) */
+    const uint32_t* actions;
+    int64_t actions_tick_stride;
+    /* last_action_id feature per kind code: blake2s(kind)[:4] / 2^32 as float32 (features.py:194-200) */
+    float action_hash[TL_N_ACT_KINDS];
+} TlDynamicsParams;
+
 typedef void* tl_stream_t; /* cudaStream_t */
 
 const char* tl_last_error(void);
 int tl_abi_version(void);
 /* sizeof of the idx-th ABI struct (0 TlTownBatch, 1 TlObsParams, 2 TlRewardParams,
- * 3 TlObsOut, 4 TlRewardOut) so bindings can verify their layout; -1 otherwise */
+ * 3 TlObsOut, 4 TlRewardOut, 5 TlDynamicsParams) so bindings can verify their layout; -1 otherwise */
 int tl_abi_struct_size(int idx);
 /* number of SMs of the current device, or a negative error */
 int tl_device_sm_count(void);
@@ -355,6 +414,13 @@ int tl_decay_reward(const TlTownBatch* batch, const TlRewardParams* rew, const T
 int tl_tick(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardParams* rew,
             const TlObsOut* obs_out, const TlRewardOut* rew_out, uint32_t phases, int32_t n_ticks,
             tl_stream_t stream);
+
+/* tl_tick plus the world-dynamics phases (TL_PHASE_ACTIONS, TL_PHASE_SOCIAL_DECAY); per tick:
+ * actions -> need decay -> ledger decay -> faint -> reward -> episode_tick -> observe.
+ * dyn may be NULL when neither phase is requested. */
+int tl_tick_world(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardParams* rew,
+                  const TlDynamicsParams* dyn, const TlObsOut* obs_out, const TlRewardOut* rew_out,
+                  uint32_t phases, int32_t n_ticks, tl_stream_t stream);
 
 /* Number of kernels launched by this library since load (the bench reports it). */
 int64_t tl_launch_count(void);

@@ -15,7 +15,7 @@ from pathlib import Path
 import numpy as np
 
 from townlet_b200 import capi
-from townlet_b200.params import ObsSpec, RewardSpec
+from townlet_b200.params import DynamicsSpec, ObsSpec, RewardSpec
 from townlet_b200.soa import TownBatch
 
 HERE = Path(__file__).resolve().parent
@@ -36,11 +36,12 @@ def load() -> C.CDLL:
     if _lib is None:
         build()
         _lib = C.CDLL(str(LIB))
-        _lib.tlo_tick.restype = C.c_int
-        _lib.tlo_tick.argtypes = [
+        _lib.tlo_tick_world.restype = C.c_int
+        _lib.tlo_tick_world.argtypes = [
             C.POINTER(capi.TlTownBatch),
             C.POINTER(capi.TlObsParams),
             C.POINTER(capi.TlRewardParams),
+            C.POINTER(capi.TlDynamicsParams),
             C.POINTER(capi.TlObsOut),
             C.POINTER(capi.TlRewardOut),
             C.c_uint32,
@@ -78,10 +79,13 @@ def oracle_tick(
     n_ticks: int = 1,
     n_threads: int = 1,
     want_comps: bool = True,
+    dyn: DynamicsSpec | None = None,
+    actions: np.ndarray | None = None,
 ) -> dict[str, np.ndarray]:
     """Run the oracle IN PLACE on ``batch`` (host arena); returns the output arrays.
 
-    Outputs carry a leading tick axis of length ``n_ticks``.
+    Outputs carry a leading tick axis of length ``n_ticks``.  ``dyn`` / ``actions`` (uint32 words,
+    ``[n_agents]`` or ``[n_ticks, n_agents]``) feed the world-dynamics phases.
     """
     lib = load()
     n, t = batch.n_agents, batch.n_towns
@@ -121,10 +125,20 @@ def oracle_tick(
             out["comps"] = np.zeros((n_ticks, n, capi.TL_N_COMPS), dtype=np.float64)
             ro.comps = out["comps"].ctypes.data
             ro.comps_tick_stride = n * capi.TL_N_COMPS
-    status = lib.tlo_tick(
+    dp = None
+    if phases & (capi.TL_PHASE_ACTIONS | capi.TL_PHASE_SOCIAL_DECAY):
+        assert dyn is not None
+        dp = dyn.struct()
+        if phases & capi.TL_PHASE_ACTIONS:
+            assert actions is not None and actions.shape[-1] == n
+            actions = np.ascontiguousarray(actions, dtype=np.uint32)
+            dp.actions = actions.ctypes.data
+            dp.actions_tick_stride = n if actions.ndim == 2 else 0
+    status = lib.tlo_tick_world(
         C.byref(bs),
         C.byref(op) if op is not None else None,
         C.byref(rp) if rp is not None else None,
+        C.byref(dp) if dp is not None else None,
         C.byref(oo) if oo is not None else None,
         C.byref(ro) if ro is not None else None,
         phases,

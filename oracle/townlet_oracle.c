@@ -608,16 +608,97 @@ static double reward_agent(const TlTownBatch* b, const TlRewardParams* r, int t,
     return total;
 }
 
+/* What process_actions leaves on one agent (world/systems/affordances.py:124-229 after
+ * world/actions.py:44-105): a move with a position relocates the agent (snapshot.position and the
+ * spatial index, world/spatial.py:62-83) and succeeds; every other kind carries the success the host
+ * services resolved; apply_affordance_outcome (world/affordances/core.py:198-206) records kind,
+ * success and duration. */
+static void apply_action(const TlTownBatch* b, const TlDynamicsParams* d, int t, int a, uint32_t w) {
+    unsigned kind = TL_ACT_KIND(w);
+    if (kind == TL_ACT_NONE) return;
+    int success = (int)TL_ACT_SUCCESS(w);
+    if (kind == TL_ACT_MOVE) {
+        success = 0;
+        if (TL_ACT_HAS_POS(w)) {
+            int x = TL_ACT_X(w), y = TL_ACT_Y(w);
+            b->pos[a] = (int32_t)(((uint32_t)x & 0xffffu) | ((uint32_t)y << 16));
+            uint32_t* self_e = b->ent + b->town_ent_off[t] + (a - b->town_agent_off[t]);
+            *self_e = (*self_e & ~0xfffffu) | (uint32_t)x | ((uint32_t)y << 10);
+            success = 1;
+        }
+    }
+    b->flags[a] = (b->flags[a] & ~TL_F_LAST_SUCCESS) | (success ? TL_F_LAST_SUCCESS : 0u);
+    b->last_action_duration[a] = TL_ACT_DURATION(w);
+    b->last_action_hash[a] = d->action_hash[kind];
+}
+
+/* _decay_value, world/relationships.py:155-162 */
+static double decay_value(double value, double decay) {
+    if (decay <= 0.0) return value;
+    if (value > 0) return fmax(0.0, value - decay);
+    if (value < 0) return fmin(0.0, value + decay);
+    return 0.0;
+}
+
+/* RelationshipService.decay for one agent (world/agents/relationships_service.py:165-191): the rivalry
+ * ledger first (RivalryLedger.decay, world/rivalry.py:68-83), then the relationship ledger
+ * (RelationshipLedger.decay, world/relationships.py:78-89).  Evicted entries leave the row, the rest
+ * keep their order; the freed tail is zeroed. */
+static void social_decay(const TlTownBatch* b, const TlDynamicsParams* d, int a) {
+    const int K = b->max_edges, EW = b->embed_words;
+    const size_t r = (size_t)a * K;
+    {
+        int n = b->riv_count[a] < K ? b->riv_count[a] : K, w = 0;
+        const double amount = d->rivalry_decay_per_tick * 1.0; /* decay_per_tick * float(ticks) */
+        for (int j = 0; j < n; ++j) {
+            double v = b->riv_score[r + j] - amount;
+            v = fmax(d->rivalry_min, fmin(d->rivalry_max, v)); /* _clamp, world/rivalry.py:131-134 */
+            if (v <= d->rivalry_eviction_threshold) continue;
+            b->riv_score[r + w] = v;
+            if (w != j) memcpy(b->riv_embed + (r + w) * EW, b->riv_embed + (r + j) * EW, sizeof(uint64_t) * EW);
+            ++w;
+        }
+        for (int j = w; j < n; ++j) {
+            b->riv_score[r + j] = 0.0;
+            memset(b->riv_embed + (r + j) * EW, 0, sizeof(uint64_t) * EW);
+        }
+        b->riv_count[a] = (uint8_t)w;
+    }
+    {
+        int n = b->tie_count[a] < K ? b->tie_count[a] : K, w = 0;
+        for (int j = 0; j < n; ++j) {
+            const double tr = decay_value(b->tie_trust[r + j], d->trust_decay);
+            const double fa = decay_value(b->tie_fam[r + j], d->familiarity_decay);
+            const double rv = decay_value(b->tie_riv[r + j], d->tie_rivalry_decay); /* `minimum` is unused there */
+            if (tr == 0.0 && fa == 0.0 && rv == 0.0) continue;
+            b->tie_trust[r + w] = tr;
+            b->tie_fam[r + w] = fa;
+            b->tie_riv[r + w] = rv;
+            if (w != j) memcpy(b->tie_embed + (r + w) * EW, b->tie_embed + (r + j) * EW, sizeof(uint64_t) * EW);
+            ++w;
+        }
+        for (int j = w; j < n; ++j) {
+            b->tie_trust[r + j] = b->tie_fam[r + j] = b->tie_riv[r + j] = 0.0;
+            memset(b->tie_embed + (r + j) * EW, 0, sizeof(uint64_t) * EW);
+        }
+        b->tie_count[a] = (uint8_t)w;
+    }
+}
+
 /* One town, one tick, in SimulationLoop.step order (core/sim_loop.py:632-958). */
-static void town_tick(const TlTownBatch* b, const TlObsParams* p, const TlRewardParams* r, const TlObsOut* oo,
-                      const TlRewardOut* ro, uint32_t phases, int t, int it, TownCache* cache, float* map_scratch) {
+static void town_tick(const TlTownBatch* b, const TlObsParams* p, const TlRewardParams* r, const TlDynamicsParams* d,
+                      const TlObsOut* oo, const TlRewardOut* ro, uint32_t phases, int t, int it, TownCache* cache,
+                      float* map_scratch) {
     int a0 = b->town_agent_off[t], a1 = b->town_agent_off[t + 1];
     int N = b->n_agents;
     if (phases & TL_PHASE_ADVANCE) b->town_tick[t] += 1; /* sim_loop.py:635,659 */
+    if ((phases & TL_PHASE_ACTIONS) && d->actions) /* world/core/context.py:253-257 */
+        for (int a = a0; a < a1; ++a) apply_action(b, d, t, a, d->actions[(size_t)it * d->actions_tick_stride + a]);
     double k_rsum = 0, k_rsq = 0, k_hmin = INFINITY, k_hsum = 0, k_late = 0, k_wallet = 0;
     int k_starving = 0, k_term = 0;
     for (int a = a0; a < a1; ++a) {
         if (phases & TL_PHASE_DECAY) need_decay(b, r, a);
+        if (phases & TL_PHASE_SOCIAL_DECAY) social_decay(b, d, a); /* systems order, world/systems/__init__.py:9-19 */
         uint32_t fl = b->flags[a];
         if (r && r->fuse_faint && (phases & (TL_PHASE_DECAY | TL_PHASE_REWARD))) {
             /* LifecycleManager.evaluate, lifecycle/manager.py:39-45: recomputed every tick */
@@ -691,9 +772,10 @@ static void town_tick(const TlTownBatch* b, const TlObsParams* p, const TlReward
 /* Oracle entry point: same argument meaning as tl_tick, every pointer HOST
  * memory.  n_threads > 1 shards towns over OpenMP threads (towns are
  * independent; used by the CPU baseline timing only). */
-int tlo_tick(const TlTownBatch* b, const TlObsParams* p, const TlRewardParams* r, const TlObsOut* oo,
-             const TlRewardOut* ro, uint32_t phases, int32_t n_ticks, int32_t n_threads) {
+int tlo_tick_world(const TlTownBatch* b, const TlObsParams* p, const TlRewardParams* r, const TlDynamicsParams* d,
+                   const TlObsOut* oo, const TlRewardOut* ro, uint32_t phases, int32_t n_ticks, int32_t n_threads) {
     if (!b || n_ticks < 0) return TL_ERR_ARG;
+    if ((phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY)) && !d) return TL_ERR_ARG;
     if ((phases & TL_PHASE_OBS) && (!p || !oo || !oo->features)) return TL_ERR_ARG;
     if ((phases & (TL_PHASE_DECAY | TL_PHASE_REWARD)) && !r) return TL_ERR_ARG;
     if (b->max_edges > TL_MAX_EDGES) return TL_ERR_ARG;
@@ -714,12 +796,17 @@ int tlo_tick(const TlTownBatch* b, const TlObsParams* p, const TlRewardParams* r
 #pragma omp for schedule(static)
 #endif
             for (int t = 0; t < b->n_towns; ++t)
-                for (int it = 0; it < n_ticks; ++it) town_tick(b, p, r, oo, ro, phases, t, it, &cache, scratch);
+                for (int it = 0; it < n_ticks; ++it) town_tick(b, p, r, d, oo, ro, phases, t, it, &cache, scratch);
         }
         cache_free(&cache);
         free(scratch);
     }
     return status;
+}
+
+int tlo_tick(const TlTownBatch* b, const TlObsParams* p, const TlRewardParams* r, const TlObsOut* oo,
+             const TlRewardOut* ro, uint32_t phases, int32_t n_ticks, int32_t n_threads) {
+    return tlo_tick_world(b, p, r, NULL, oo, ro, phases, n_ticks, n_threads);
 }
 
 /* compute_gae, policy/backends/pytorch/ppo_utils.py:19-67, on the time-major layout of the rollout

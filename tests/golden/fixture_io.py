@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-from townlet_b200.params import ObsSpec, RewardSpec
+from townlet_b200.params import DynamicsSpec, ObsSpec, RewardSpec
 from townlet_b200.soa import BatchLayout, TownBatch
 
 GOLDEN_DIR = Path(__file__).resolve().parent
@@ -28,6 +28,8 @@ def save_fixture(
     n_ticks: int,
     ref: dict[str, np.ndarray],
     note: str = "",
+    dyn: DynamicsSpec | None = None,
+    actions: np.ndarray | None = None,
 ) -> None:
     lay = batch.layout
     meta = {
@@ -46,7 +48,11 @@ def save_fixture(
         "n_ticks": int(n_ticks),
         "note": note,
     }
+    if dyn is not None:
+        meta["dyn"] = asdict(dyn)
     arrays = {f"ref_{k}": v for k, v in ref.items()}
+    if actions is not None:
+        arrays["in_actions"] = np.ascontiguousarray(actions, dtype=np.uint32)
     np.savez_compressed(path, arena=batch.arena, meta=np.array(json.dumps(meta)), **arrays)
 
 
@@ -62,8 +68,16 @@ def load_fixture(path: Path):
     obs = ObsSpec(**obs_kwargs)
     rew = RewardSpec(**meta["rew"])
     ref = {k[4:]: data[k] for k in data.files if k.startswith("ref_")}
+    if "dyn" in meta:  # world-dynamics fixtures (tests/golden/world/)
+        meta["dyn_spec"] = DynamicsSpec(**meta["dyn"])
+        meta["actions"] = np.array(data["in_actions"]) if "in_actions" in data.files else None
     return batch, obs, rew, meta, ref
 
 
 def fixture_paths() -> list[Path]:
     return sorted(GOLDEN_DIR.glob("*.npz"))
+
+
+def world_fixture_paths() -> list[Path]:
+    """Fixtures that also drive the world-dynamics phases (actions, ledger decay)."""
+    return sorted((GOLDEN_DIR / "world").glob("*.npz"))

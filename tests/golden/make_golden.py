@@ -52,7 +52,8 @@ from townlet.world.observations.service import WorldObservationService  # noqa: 
 
 from townlet_b200 import capi  # noqa: E402
 from townlet_b200.ingest import ingest_town, rows_to_batch  # noqa: E402
-from townlet_b200.params import ObsSpec, RewardSpec  # noqa: E402
+from townlet_b200.actions import encode_actions  # noqa: E402
+from townlet_b200.params import DynamicsSpec, ObsSpec, RewardSpec  # noqa: E402
 from townlet_b200.reward_events import normalise_events, reduce_social_events  # noqa: E402
 from townlet_b200.synth import TownDescription, assemble, synth_town  # noqa: E402
 
@@ -651,6 +652,165 @@ def snapshot_cases():
             )
 
 
+def world_dynamics_cases():
+    """actions (moves + outcome bookkeeping) and ledger decay inside the tick.
+
+    Per tick, in WorldContext.tick order (world/core/context.py:229-289): apply_actions + process_actions
+    (world/actions.py:44, world/systems/affordances.py:105), need decay, RelationshipService.decay
+    (world/agents/relationships_service.py:165), lifecycle, episode_tick, reward, observe.  The fixture stores the
+    action words, the per-tick reference outputs and the ledgers / positions of the final world.
+    """
+    from townlet.world.actions import apply_actions
+    from townlet.world.systems.affordances import process_actions
+
+    cases = (
+        ("world_hybrid_48x8", "hybrid", 48, 8, 3, 8, {}, {}),
+        ("world_compact_24x10", "compact", 24, 10, 2, 6, {"observations_config__compact__object_channels": ["stove", "bed"]}, {}),
+        ("world_full_tie_decay", "full", 16, 6, 2, 7, {}, {"trust_decay": 0.04, "familiarity_decay": 0.03}),
+        ("world_hybrid_128x64", "hybrid", 128, 64, 1, 3, {}, {}),
+    )
+    (GOLDEN_DIR / "world").mkdir(exist_ok=True)
+    for name, variant, grid, agents, n_towns, n_ticks, extra, tie_params in cases:
+        config = make_config(variant, employment__enforce_job_loop=False, **extra)
+        spec = ObsSpec.from_config(config)
+        rew = RewardSpec.from_config(config, fuse_faint=True)
+        dyn = DynamicsSpec.from_config(config)
+        for key, value in tie_params.items():
+            setattr(dyn, key, value)
+        rng = np.random.default_rng(77 + grid + agents)
+        towns = [synth_town(t, grid, agents, terminated_frac=0.1) for t in range(n_towns)]
+        for town in towns:  # edges that leave the ledgers during the sequence
+            town.rivalry[0] = [(other, 0.052 + 0.004 * j) for j, (other, _) in enumerate(town.rivalry[0])]
+            town.rivalry[1] = [(other, 0.05) for other, _ in town.rivalry[1]]  # all evicted at once -> rivalry features drop to 0
+            first = town.ties[2][0][0]
+            town.ties[2] = [(first, 0.0, 0.0, 0.0)] + town.ties[2][1:]  # a zero tie is evicted by the first decay
+            second = town.ties[3][1][0]
+            town.ties[3] = [town.ties[3][0], (second, 0.0, 0.0, 0.015)] + town.ties[3][2:]  # gone after two ticks
+            town.ties[4] = [(other, 0.0, 0.0, 0.005) for other, _, _, _ in town.ties[4]]  # falls back to the rivalry ledger
+        worlds = [materialise(t, config) for t in towns]
+        for w, t in zip(worlds, towns):
+            patch_employment(w, t)
+            for ledger in w._relationships._relationship_ledgers.values():
+                for key, value in tie_params.items():  # non-default RelationshipParameters (world/relationships.py:14-21)
+                    setattr(ledger.params, key, value)
+        services = [WorldObservationService(config=config) for _ in towns]
+        engines = [RewardEngine(config) for _ in towns]
+        lifecycles = [LifecycleManager(config) for _ in towns]
+
+        def ingest_all():
+            rows = []
+            for w, t, eng in zip(worlds, towns, engines):
+                term0 = {aid: bool(t.terminated[i]) for i, aid in enumerate(t.agent_ids)}
+                reasons0 = {aid: "eviction" if i % 2 else "unemployment" for i, aid in enumerate(t.agent_ids) if t.terminated[i]}
+                slots = {aid: w.embedding_allocator.allocate(aid, w.tick) for aid in w.agents}
+                rows.append(
+                    ingest_town(
+                        w, spec, terminated=term0, reasons=reasons0, pending_resets=set(), slots=slots,
+                        episode_totals=dict(eng._episode_totals), termination_block=dict(eng._termination_block), origin=(0, 0),
+                    )
+                )
+            return rows
+
+        rows = ingest_all()
+        batch = rows_to_batch(rows, spec, grid=(grid, grid))
+        batch.validate(len(spec.object_channels))
+        N = batch.n_agents
+        ref = {
+            "map": np.zeros((n_ticks, N, *spec.map_shape), np.float32),
+            "features": np.zeros((n_ticks, N, spec.n_features), np.float32),
+            "summary": np.zeros((n_ticks, N, capi.TL_N_SUMMARY), np.int32),
+            "comps": np.zeros((n_ticks, N, capi.TL_N_COMPS)),
+            "terminated": np.zeros((n_ticks, N), np.uint8),
+            "needs": np.zeros((n_ticks, 3, N)),
+            "episode_total": np.zeros((n_ticks, N)),
+        }
+        words = np.zeros((n_ticks, N), np.uint32)
+        for it in range(n_ticks):
+            a = 0
+            for ti, (w, t, svc, eng, life) in enumerate(zip(worlds, towns, services, engines, lifecycles)):
+                n = len(t.agent_ids)
+                w.tick += 1
+                # ---- this tick's actions: moves (anywhere on the grid, also onto other agents), a move without a
+                # position, wait / noop with durations, and agents without an action
+                actions = {}
+                for i, aid in enumerate(t.agent_ids):
+                    roll = rng.random()
+                    if roll < 0.45:
+                        actions[aid] = {"kind": "move", "position": (int(rng.integers(0, grid)), int(rng.integers(0, grid)))}
+                        if rng.random() < 0.3:
+                            actions[aid]["duration"] = int(rng.integers(1, 9))
+                    elif roll < 0.5:
+                        actions[aid] = {"kind": "move"}
+                    elif roll < 0.6:
+                        actions[aid] = {"kind": "wait", "duration": int(rng.integers(1, 60))}
+                    elif roll < 0.7:
+                        actions[aid] = {"kind": "noop"}
+                    elif roll < 0.75 and i > 0:  # lands on another agent's tile
+                        other = w.agents[t.agent_ids[i - 1]]
+                        actions[aid] = {"kind": "move", "position": tuple(other.position)}
+                words[it, a : a + n] = encode_actions(t.agent_ids, actions)
+                coerced = w.context._coerce_actions(actions) if hasattr(w, "context") and w.context is not None else None
+                if coerced is None:
+                    from townlet.world.actions import Action
+
+                    coerced = [Action(agent_id=k, kind=str(v.get("kind", "noop")), payload=dict(v)) for k, v in actions.items()]
+                if coerced:
+                    apply_actions(w, coerced)  # emits action.invalid for the move without a position
+                if actions:
+                    process_actions(w, actions, tick=w.tick)
+                w._apply_need_decay()
+                w._relationships.decay()  # the "relationships" system step (world/systems/relationships.py:13-25)
+                life_term = life.evaluate(w, w.tick)
+                life_reasons = dict(life._termination_reasons)
+                terminated, reasons = {}, {}
+                for i, aid in enumerate(t.agent_ids):
+                    host_flag = bool(t.terminated[i])
+                    terminated[aid] = host_flag or bool(life_term.get(aid, False))
+                    if host_flag:
+                        reasons[aid] = "eviction" if i % 2 else "unemployment"
+                    elif aid in life_reasons:
+                        reasons[aid] = life_reasons[aid]
+                tpd = config.observations_config.hybrid.time_ticks_per_day
+                for snap in w.agents.values():
+                    snap.episode_tick = (int(snap.episode_tick) + 1) % max(1, int(tpd))
+                breakdowns = eng.compute(w, terminated, reasons)
+                ids, maps, feats, summ, _ = reference_obs(w, svc, terminated)
+                assert ids == t.agent_ids
+                ref["map"][it, a : a + n] = maps
+                ref["features"][it, a : a + n] = feats
+                ref["summary"][it, a : a + n] = summ
+                for i, aid in enumerate(ids):
+                    bd = breakdowns[aid]
+                    row = ref["comps"][it, a + i]
+                    for c, cname in enumerate(capi.COMP_NAMES):
+                        if cname == "guardrail_active":
+                            row[c] = float(bd.guardrail_active)
+                        elif cname == "clipped":
+                            row[c] = float(bd.clipped)
+                        elif cname != "reserved":
+                            row[c] = float(getattr(bd, cname))
+                    ref["terminated"][it, a + i] = terminated[aid]
+                    snap = w.agents[aid]
+                    ref["needs"][it, :, a + i] = [snap.needs["hunger"], snap.needs["hygiene"], snap.needs["energy"]]
+                    ref["episode_total"][it, a + i] = eng._episode_totals[aid]
+                for aid in ids:
+                    w.embedding_allocator._assignments.setdefault(aid, int(rows[ti].fields["slot"][ids.index(aid)]))
+                a += n
+        # ---- the final world, ingested again: ledgers, positions and spatial index after the sequence
+        final = rows_to_batch(ingest_all(), spec, grid=(grid, grid))
+        for fname in ("pos", "ent", "tie_count", "tie_trust", "tie_fam", "tie_riv", "tie_embed", "riv_count", "riv_score",
+                      "riv_embed", "last_action_duration", "last_action_hash"):
+            ref[f"final_{fname}"] = np.array(getattr(final, fname))
+        ref["final_last_success"] = (np.array(final.flags) & capi.TL_F_LAST_SUCCESS).astype(np.uint32)
+        save_fixture(
+            GOLDEN_DIR / "world" / f"{name}.npz", batch, spec, rew, capi.TL_PHASE_WORLD, n_ticks, ref,
+            note="actions -> need decay -> ledger decay -> lifecycle -> reward -> observe per tick, on reference WorldStates",
+            dyn=dyn, actions=words,
+        )
+        evicted = int(batch.riv_count.sum()) - int(final.riv_count.sum()), int(batch.tie_count.sum()) - int(final.tie_count.sum())
+        print(f"  world/{name}: {n_towns} towns x {agents} agents, {n_ticks} ticks; evicted rivalry/ties {evicted}")
+
+
 def gae_case():
     """compute_gae (policy/backends/pytorch/ppo_utils.py:19-67) on random float32 rollouts, both value layouts."""
     import torch
@@ -675,7 +835,7 @@ def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
     only = os.environ.get("TL_GOLDEN_ONLY")
     if only:
-        {"gae": gae_case, "snapshots": snapshot_cases}[only]()
+        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()
@@ -685,6 +845,7 @@ def main():
     synth_cases()
     reward_cases()
     snapshot_cases()
+    world_dynamics_cases()
     gae_case()
     shutil.rmtree(WORK, ignore_errors=True)
 

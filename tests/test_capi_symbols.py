@@ -25,10 +25,12 @@ def test_header_symbols_are_exported(lib) -> None:
 
 
 def test_struct_layouts_match_the_header(lib) -> None:
-    for idx, struct in enumerate((capi.TlTownBatch, capi.TlObsParams, capi.TlRewardParams, capi.TlObsOut, capi.TlRewardOut)):
+    for idx, struct in enumerate((capi.TlTownBatch, capi.TlObsParams, capi.TlRewardParams, capi.TlObsOut, capi.TlRewardOut, capi.TlDynamicsParams)):
         assert lib.tl_abi_struct_size(idx) == C.sizeof(struct), struct.__name__
     assert lib.tl_abi_struct_size(99) == -1
-    assert lib.tl_abi_version() == 1
+    assert lib.tl_abi_version() == capi.TL_ABI_VERSION == int(
+        re.search(r"#define TL_ABI_VERSION (\d+)", (capi.INCLUDE / "townlet_b200.h").read_text()).group(1)
+    )
 
 
 def test_argument_errors_are_reported_without_a_gpu(lib) -> None:
@@ -42,6 +44,13 @@ def test_argument_errors_are_reported_without_a_gpu(lib) -> None:
     assert b"reward params" in lib.tl_last_error()
     assert lib.tl_tick(None, None, None, None, None, capi.TL_PHASE_DECAY, 1, None) == -1
     assert lib.tl_decay_reward(C.byref(b), None, None, capi.TL_PHASE_OBS, None) == -1
+    # the world-dynamics phases need TlDynamicsParams, and action words when actions are requested
+    assert lib.tl_tick(C.byref(b), None, None, None, None, capi.TL_PHASE_SOCIAL_DECAY, 1, None) == -1
+    assert b"tl_tick_world" in lib.tl_last_error()
+    d = capi.TlDynamicsParams()
+    assert lib.tl_tick_world(C.byref(b), None, None, C.byref(d), None, None, capi.TL_PHASE_ACTIONS, 1, None) == -1
+    assert b"action words" in lib.tl_last_error()
+    assert lib.tl_tick_world(C.byref(b), None, None, C.byref(d), None, None, 1 << 9, 1, None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path) -> None:

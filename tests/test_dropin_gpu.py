@@ -129,3 +129,34 @@ def test_parallel_env_steps() -> None:
         assert np.array_equal(terminations.cpu().numpy(), ref["terminated"][0].astype(bool))
         assert bool(truncations.all()) == (step == 2)
         assert infos["kpi"].shape == (batch.n_towns, capi.TL_N_KPI)
+
+
+def test_parallel_env_applies_action_words_on_the_device() -> None:
+    """With a DynamicsSpec the env moves agents and decays the ledgers inside the tick."""
+    import torch
+
+    from oracle.oracle import oracle_tick
+    from townlet_b200.env import TownletParallelEnv
+    from townlet_b200.params import DynamicsSpec, pack_actions
+    from townlet_b200.synth import synth_batch
+
+    obs, rew, dyn = ObsSpec(), RewardSpec(fuse_faint=True), DynamicsSpec()
+    batch = synth_batch(9, 32, 6, obs)
+    env = TownletParallelEnv(batch, obs, rew, dyn=dyn)
+    env.reset()
+    ref_batch = batch.copy()
+    rng = np.random.default_rng(3)
+    for step in range(4):
+        n = batch.n_agents
+        words = pack_actions(rng.choice([0, 1, 3], size=n), 0, 1, rng.integers(0, 32, n), rng.integers(0, 32, n), 1)
+        act = torch.from_numpy(words.view(np.int32)).cuda() if step else None  # first step: nobody acts
+        observations, rewards, _, _, _ = env.step(act)
+        ref = oracle_tick(
+            ref_batch, obs, rew, capi.TL_PHASE_WORLD, 1, dyn=dyn, actions=words if step else np.zeros(n, np.uint32)
+        )
+        torch.cuda.synchronize()
+        assert np.array_equal(observations["map"].cpu().numpy(), ref["map"][0])
+        assert np.array_equal(observations["features"].cpu().numpy().view(np.uint32), ref["features"][0].view(np.uint32))
+        np.testing.assert_allclose(rewards.cpu().numpy(), ref["reward"][0], rtol=1e-6, atol=1e-9)
+    state = env.state().download_state()
+    assert np.array_equal(state.pos, ref_batch.pos) and np.array_equal(state.riv_score, ref_batch.riv_score)

@@ -6,8 +6,8 @@ CUDA kernels behind a C ABI (``include/townlet_b200.h``).  See DESIGN.md.
 """
 
 from . import capi
-from .params import ObsSpec, RewardSpec
+from .params import DynamicsSpec, ObsSpec, RewardSpec
 from .soa import BatchLayout, TownBatch
 
-__all__ = ["BatchLayout", "ObsSpec", "RewardSpec", "TownBatch", "capi"]
+__all__ = ["BatchLayout", "DynamicsSpec", "ObsSpec", "RewardSpec", "TownBatch", "capi"]
 __version__ = "0.1.0"

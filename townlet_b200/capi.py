@@ -18,6 +18,7 @@ CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtownlet_b200.so"
 INCLUDE = ROOT / "include"
 
+TL_ABI_VERSION = 2
 TL_N_NEEDS = 3
 TL_MAX_EDGES = 8
 TL_MAX_SOCIAL_SLOTS = 8
@@ -37,6 +38,13 @@ TL_PHASE_REWARD = 2
 TL_PHASE_OBS = 4
 TL_PHASE_ADVANCE = 8
 TL_PHASE_ALL = 15
+TL_PHASE_ACTIONS = 16  # needs TlDynamicsParams (tl_tick_world)
+TL_PHASE_SOCIAL_DECAY = 32
+TL_PHASE_WORLD = TL_PHASE_ALL | TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY
+
+# action kinds of the action word (include/townlet_b200.h: TL_ACT_*)
+TL_N_ACT_KINDS = 16
+ACT_KINDS = ("", "move", "noop", "wait", "request", "start", "release", "chat", "blocked")
 
 TL_KIND_AGENT = 0
 TL_KIND_OBJECT = 1
@@ -218,6 +226,21 @@ class TlRewardOut(C.Structure):
     ]
 
 
+class TlDynamicsParams(C.Structure):
+    _fields_ = [
+        ("trust_decay", C.c_double),
+        ("familiarity_decay", C.c_double),
+        ("tie_rivalry_decay", C.c_double),
+        ("rivalry_decay_per_tick", C.c_double),
+        ("rivalry_min", C.c_double),
+        ("rivalry_max", C.c_double),
+        ("rivalry_eviction_threshold", C.c_double),
+        ("actions", _p),
+        ("actions_tick_stride", C.c_int64),
+        ("action_hash", C.c_float * TL_N_ACT_KINDS),
+    ]
+
+
 EXPORTED_SYMBOLS = (
     "tl_last_error",
     "tl_abi_version",
@@ -226,6 +249,7 @@ EXPORTED_SYMBOLS = (
     "tl_obs_build",
     "tl_decay_reward",
     "tl_tick",
+    "tl_tick_world",
     "tl_launch_count",
     "tl_gae",
     "tl_context_create",
@@ -320,6 +344,18 @@ def load_library() -> C.CDLL:
         C.c_int32,
         _p,
     ]
+    lib.tl_tick_world.restype = C.c_int
+    lib.tl_tick_world.argtypes = [
+        C.POINTER(TlTownBatch),
+        C.POINTER(TlObsParams),
+        C.POINTER(TlRewardParams),
+        C.POINTER(TlDynamicsParams),
+        C.POINTER(TlObsOut),
+        C.POINTER(TlRewardOut),
+        C.c_uint32,
+        C.c_int32,
+        _p,
+    ]
     lib.tl_gae.restype = C.c_int
     lib.tl_gae.argtypes = [_p, _p, _p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, _p]
     lib.tl_context_create.restype = _p
@@ -341,9 +377,9 @@ def load_library() -> C.CDLL:
     lib.tl_context_last_h2d_bytes.argtypes = [_p]
     lib.tl_context_last_d2h_bytes.restype = C.c_int64
     lib.tl_context_last_d2h_bytes.argtypes = [_p]
-    if lib.tl_abi_version() != 1:
+    if lib.tl_abi_version() != TL_ABI_VERSION:
         raise TownletB200Error("libtownlet_b200.so ABI version mismatch")
-    for idx, struct in enumerate((TlTownBatch, TlObsParams, TlRewardParams, TlObsOut, TlRewardOut)):
+    for idx, struct in enumerate((TlTownBatch, TlObsParams, TlRewardParams, TlObsOut, TlRewardOut, TlDynamicsParams)):
         if lib.tl_abi_struct_size(idx) != C.sizeof(struct):
             raise TownletB200Error(
                 f"struct layout mismatch for {struct.__name__}: C {lib.tl_abi_struct_size(idx)} vs ctypes {C.sizeof(struct)}"

@@ -14,6 +14,9 @@ struct StateRoleOut {
 // (lifecycle/manager.py:39-45), episode tick (world/core/context.py:283-289), reward with guardrails
 // (rewards/engine.py:71-172) and, when `f` is not null, the scalar features, path hint, landmarks and
 // personality channels of encode_feature_vector (encoders/features.py:43-404).
+// MUT: the world-dynamics phases rewrite pos / ent / the last-action fields inside the launch, so they
+// are read with plain loads; otherwise through the read-only path.
+template <bool MUT>
 __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a, int tick, int town_abeg, int town_aend,
                                                  int town_ebeg, int town_eend, float* f, StateRoleOut& out) {
     const TlObsParams& o = p.obs;
@@ -48,10 +51,10 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
     if (do_obs) {
         attendance = __ldg(p.b.attendance + a);
         wages_withheld = __ldg(p.b.wages_withheld + a);
-        duration = __ldg(p.b.last_action_duration + a);
+        duration = ld_state<MUT>(p.b.last_action_duration + a);
         slot_idx = __ldg(p.b.slot + a);
-        last_hash = __ldg(p.b.last_action_hash + a);
-        pw = __ldg(p.b.pos + a);
+        last_hash = ld_state<MUT>(p.b.last_action_hash + a);
+        pw = ld_state<MUT>(p.b.pos + a);
     }
     const unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
     if (do_decay) {  // world/grid.py:1439-1455
@@ -135,7 +138,7 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
         if (!all_types) {
 #pragma unroll 1
             for (int e = e_obj; e < town_eend; ++e) {
-                const uint32_t w = __ldg(p.b.ent + e);
+                const uint32_t w = ld_state<MUT>(p.b.ent + e);
                 if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w) || (int)TL_ENT_LTYPE(w) != o.path_hint_ltype)
                     continue;
                 const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
@@ -151,7 +154,7 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
             int best_dx[5] = {0, 0, 0, 0, 0}, best_dy[5] = {0, 0, 0, 0, 0};
 #pragma unroll 1
             for (int e = e_obj; e < town_eend; ++e) {
-                const uint32_t w = __ldg(p.b.ent + e);
+                const uint32_t w = ld_state<MUT>(p.b.ent + e);
                 if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w)) continue;
                 const int lt = (int)TL_ENT_LTYPE(w);
                 if (lt == 0) continue;
@@ -331,5 +334,96 @@ __device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, i
                 agg[0] = agg[1] = agg[2] = agg[3] = 0.0f;
             }
         }
+    }
+}
+
+// TL_PHASE_ACTIONS for the agents of one CTA's towns [t0, t0 + n_towns): what process_actions leaves on
+// the agent snapshot (world/systems/affordances.py:124-229 after world/actions.py:44-105).  A move with a
+// position relocates the agent — snapshot.position and the spatial index (world/spatial.py:62-83), i.e.
+// the agent's own entity word — and succeeds; every other kind carries the success the host services
+// resolved; apply_affordance_outcome (world/affordances/core.py:198-206) records kind, success, duration.
+// The caller puts a block barrier between this and any read of pos / ent / the last-action fields.
+__device__ __forceinline__ void apply_actions_cta(const KParams& p, int it, int t0, int n_towns, int tid, int n_threads) {
+    const int a_begin = p.b.town_agent_off[t0], a_end = p.b.town_agent_off[t0 + n_towns];
+    const uint32_t* act = p.dyn.actions + (size_t)it * p.dyn.actions_tick_stride;
+#pragma unroll 1
+    for (int a = a_begin + tid; a < a_end; a += n_threads) {
+        const uint32_t w = __ldg(act + a);
+        const unsigned kind = TL_ACT_KIND(w);
+        if (kind == TL_ACT_NONE) continue;
+        bool success = TL_ACT_SUCCESS(w) != 0;
+        if (kind == TL_ACT_MOVE) {
+            success = TL_ACT_HAS_POS(w) != 0;
+            if (success) {
+                int s = 0;
+                while (s + 1 < n_towns && a >= p.b.town_agent_off[t0 + s + 1]) ++s;
+                const int self_e = p.b.town_ent_off[t0 + s] + (a - p.b.town_agent_off[t0 + s]);
+                const uint32_t x = (uint32_t)TL_ACT_X(w), y = (uint32_t)TL_ACT_Y(w);
+                p.b.pos[a] = (int32_t)(x | (y << 16));
+                p.b.ent[self_e] = (p.b.ent[self_e] & ~0xfffffu) | x | (y << 10);
+            }
+        }
+        p.b.flags[a] = (p.b.flags[a] & ~TL_F_LAST_SUCCESS) | (success ? TL_F_LAST_SUCCESS : 0u);
+        p.b.last_action_duration[a] = TL_ACT_DURATION(w);
+        p.b.last_action_hash[a] = p.dyn.action_hash[kind];
+    }
+}
+
+// _decay_value, world/relationships.py:155-162
+__device__ __forceinline__ double decay_value(double value, double decay) {
+    if (decay <= 0.0) return value;
+    if (value > 0.0) return fmax(0.0, value - decay);
+    if (value < 0.0) return fmin(0.0, value + decay);
+    return 0.0;
+}
+
+// TL_PHASE_SOCIAL_DECAY for ONE agent, in place on its rows (shared or global memory):
+// RivalryLedger.decay(ticks=1) (world/rivalry.py:68-83) then RelationshipLedger.decay
+// (world/relationships.py:78-89), the order of RelationshipService.decay
+// (world/agents/relationships_service.py:165-191).  Evicted entries leave the row, the rest keep their
+// order, the freed tail is zeroed.  n_riv / n_t come in clamped to the row stride and go out updated.
+__device__ __forceinline__ void social_decay_agent(const KParams& p, int& n_riv, int& n_t, double* kt, double* kf,
+                                                   double* ktr, double* score, uint64_t* temb, uint64_t* remb) {
+    const TlDynamicsParams& d = p.dyn;
+    const int EW = p.b.embed_words;
+    {
+        int w = 0;
+#pragma unroll 1
+        for (int j = 0; j < n_riv; ++j) {
+            const double v = fmax(d.rivalry_min, fmin(d.rivalry_max, score[j] - d.rivalry_decay_per_tick));
+            if (v <= d.rivalry_eviction_threshold) continue;
+            score[w] = v;
+            if (w != j)
+                for (int k = 0; k < EW; ++k) remb[w * EW + k] = remb[j * EW + k];
+            ++w;
+        }
+#pragma unroll 1
+        for (int j = w; j < n_riv; ++j) {
+            score[j] = 0.0;
+            for (int k = 0; k < EW; ++k) remb[j * EW + k] = 0ull;
+        }
+        n_riv = w;
+    }
+    {
+        int w = 0;
+#pragma unroll 1
+        for (int j = 0; j < n_t; ++j) {
+            const double tr = decay_value(kt[j], d.trust_decay);
+            const double fa = decay_value(kf[j], d.familiarity_decay);
+            const double rv = decay_value(ktr[j], d.tie_rivalry_decay);
+            if (tr == 0.0 && fa == 0.0 && rv == 0.0) continue;
+            kt[w] = tr;
+            kf[w] = fa;
+            ktr[w] = rv;
+            if (w != j)
+                for (int k = 0; k < EW; ++k) temb[w * EW + k] = temb[j * EW + k];
+            ++w;
+        }
+#pragma unroll 1
+        for (int j = w; j < n_t; ++j) {
+            kt[j] = kf[j] = ktr[j] = 0.0;
+            for (int k = 0; k < EW; ++k) temb[j * EW + k] = 0ull;
+        }
+        n_t = w;
     }
 }

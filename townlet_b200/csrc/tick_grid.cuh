@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
     const bool do_obs = p.phases & TL_PHASE_OBS;
     const bool do_advance = p.phases & TL_PHASE_ADVANCE;
     const bool do_state = do_decay || do_reward;
+    const bool do_actions = p.phases & TL_PHASE_ACTIONS;
+    const bool do_social_decay = p.phases & TL_PHASE_SOCIAL_DECAY;
 
     uint16_t* s_grid = reinterpret_cast<uint16_t*>(smem + p.off_grid);
     uint16_t* s_ctype = p.off_ctype >= 0 ? reinterpret_cast<uint16_t*>(smem + p.off_ctype) : nullptr;
@@ -97,6 +99,8 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
             z.starving = z.term = z.count = 0;
             s_kpi[tid] = z;
         }
+        // world/core/context.py:253-257: actions land before any system or observer runs
+        if (do_actions) apply_actions_cta(p, it, t0, n_towns, tid, kThreads);
         // ---- stage the town grids (cache.py:16-41) ---------------------------
         if (do_obs) {
             const int words = (n_towns * p.grid_tiles + 1) >> 1;
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
                 if (warp == 0) {
                     StateRoleOut so;
                     if (active)
-                        state_role_agent(p, it, a, tm.tick, tm.agent_begin, tm.agent_end, tm.ent_begin, tm.ent_end,
+                        state_role_agent<true>(p, it, a, tm.tick, tm.agent_begin, tm.agent_end, tm.ent_begin, tm.ent_end,
                                          do_obs ? feat_s0 + lane * F : nullptr, so);
                     // ---- per-town KPIs: segmented warp-shuffle reduction ------------
                     if (do_state && p.ro.kpi) {
@@ -200,21 +204,27 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
                         cm.pad[0] = cm.pad[1] = cm.pad[2] = 0;
                         s_meta[lane] = cm;
                     }
-                } else if (do_obs && active) {
+                } else if ((do_obs || do_social_decay) && active) {
                     // rows are read straight from global memory: this form is not bound by the social role
                     const size_t K = (size_t)p.b.max_edges, EW = (size_t)p.b.embed_words;
-                    const int n_riv = min((int)p.b.riv_count[a], (int)K);  // counts are clamped to the row stride
-                    const int n_t = min((int)p.b.tie_count[a], (int)K);
-                    const bool social = o.social_base >= 0;
+                    int n_riv = min((int)p.b.riv_count[a], (int)K);  // counts are clamped to the row stride
+                    int n_t = min((int)p.b.tie_count[a], (int)K);
                     const size_t r = (size_t)a * K;
-                    int filled = 0, source = 0;
-                    social_role_agent(p, n_riv, n_t, social ? p.b.tie_trust + r : nullptr, social ? p.b.tie_fam + r : nullptr,
-                                      social ? p.b.tie_riv + r : nullptr, p.b.riv_score + r,
-                                      social ? p.b.tie_embed + r * EW : nullptr, social ? p.b.riv_embed + r * EW : nullptr,
-                                      o.embed_lut, feat_s0 + lane * F, filled, source);
-                    if (p.oo.summary) {
-                        int* srow_i = p.oo.summary + (size_t)it * p.oo.summary_tick_stride + (size_t)a * TL_N_SUMMARY;
-                        *reinterpret_cast<int4*>(srow_i + TL_SUM_FILLED_SLOTS) = make_int4(filled, source, 0, 0);
+                    if (do_social_decay) {
+                        social_decay_agent(p, n_riv, n_t, p.b.tie_trust + r, p.b.tie_fam + r, p.b.tie_riv + r,
+                                           p.b.riv_score + r, p.b.tie_embed + r * EW, p.b.riv_embed + r * EW);
+                        p.b.riv_count[a] = (uint8_t)n_riv;
+                        p.b.tie_count[a] = (uint8_t)n_t;
+                    }
+                    if (do_obs) {
+                        int filled = 0, source = 0;
+                        social_role_agent(p, n_riv, n_t, p.b.tie_trust + r, p.b.tie_fam + r, p.b.tie_riv + r,
+                                          p.b.riv_score + r, p.b.tie_embed + r * EW, p.b.riv_embed + r * EW, o.embed_lut,
+                                          feat_s0 + lane * F, filled, source);
+                        if (p.oo.summary) {
+                            int* srow_i = p.oo.summary + (size_t)it * p.oo.summary_tick_stride + (size_t)a * TL_N_SUMMARY;
+                            *reinterpret_cast<int4*>(srow_i + TL_SUM_FILLED_SLOTS) = make_int4(filled, source, 0, 0);
+                        }
                     }
                 }
             }

@@ -25,7 +25,7 @@
 constexpr int kTileWarps = TL_TILE_WARPS;  // warps in the tiles role
 constexpr int kRoleWarps = 2 + kTileWarps;
 
-template <int VARIANT, int WT>
+template <int VARIANT, int WT, bool WORLD>
 __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick_kernel_roles(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);  // [2][chunk * F + 4]
@@ -47,6 +47,9 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     const bool do_advance = p.phases & TL_PHASE_ADVANCE;
     const bool do_state = do_decay || do_reward;
     const bool do_kpi = do_state && p.ro.kpi != nullptr;
+    // WORLD: the launch runs world-dynamics phases (they rewrite pos / ent / ledger rows: plain loads)
+    const bool do_actions = WORLD && (p.phases & TL_PHASE_ACTIONS);
+    const bool do_social_decay = WORLD && (p.phases & TL_PHASE_SOCIAL_DECAY);
 
     const TlObsParams& o = p.obs;
     constexpr bool kStatic = WT > 0;
@@ -106,6 +109,10 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
 #pragma unroll 1
     for (int it = 0; it < p.n_ticks; ++it) {
         cached_eb = -1;  // every tick re-reads the entity words of its towns
+        if (do_actions) {  // world/core/context.py:253-257: actions land before any system or observer runs
+            apply_actions_cta(p, it, t0, n_towns, tid, 32 * kRoleWarps);
+            __syncthreads();
+        }
         if (warp == 0) {
             if (do_advance && lane < n_towns) {  // core/sim_loop.py:635,659
                 my_tick += 1;
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 const int tick = __shfl_sync(FULL, my_tick, slot);
                 StateRoleOut so;
                 if (active)
-                    state_role_agent(p, it, a, tick, town_abeg, town_aend, town_ebeg, town_eend,
+                    state_role_agent<WORLD>(p, it, a, tick, town_abeg, town_aend, town_ebeg, town_eend,
                                      do_obs ? feat_s0 + lane * F : nullptr, so);
                 const double need0 = so.need0, reward_total = so.reward_total, kpi_wallet = so.kpi_wallet;
                 const bool terminated = so.terminated;
@@ -209,36 +216,69 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 uint64_t* s_temb = reinterpret_cast<uint64_t*>(s_score + chunk_cap * K);
                 uint64_t* s_remb = s_temb + chunk_cap * K * EW;
                 const float* s_elut = reinterpret_cast<const float*>(s_remb + chunk_cap * K * EW);  // byte / 255.0f
-                if (do_obs) {
-                    const size_t r0 = (size_t)c_begin * K;
-                    const int n_rows = c_n * K;
+                const bool stage_ties = o.social_base >= 0 || do_social_decay;
+                const size_t r0 = (size_t)c_begin * K;
+                const int n_rows = c_n * K;
+                if (do_obs || do_social_decay) {
 #pragma unroll 2
                     for (int i = lane; i < n_rows; i += 32) {
-                        const double v_score = __ldg(p.b.riv_score + r0 + i);
-                        if (o.social_base >= 0) {
-                            const double v_t = __ldg(p.b.tie_trust + r0 + i), v_f = __ldg(p.b.tie_fam + r0 + i);
-                            const double v_r = __ldg(p.b.tie_riv + r0 + i);
+                        const double v_score = ld_state<WORLD>(p.b.riv_score + r0 + i);
+                        if (stage_ties) {
+                            const double v_t = ld_state<WORLD>(p.b.tie_trust + r0 + i), v_f = ld_state<WORLD>(p.b.tie_fam + r0 + i);
+                            const double v_r = ld_state<WORLD>(p.b.tie_riv + r0 + i);
                             s_trust[i] = v_t;
                             s_fam[i] = v_f;
                             s_riv[i] = v_r;
                         }
                         s_score[i] = v_score;
                     }
-                    if (o.social_base >= 0) {
+                    if (stage_ties) {
 #pragma unroll 2
                         for (int i = lane; i < n_rows * EW; i += 32) {
-                            const uint64_t v_t = __ldg(p.b.tie_embed + r0 * EW + i), v_r = __ldg(p.b.riv_embed + r0 * EW + i);
+                            const uint64_t v_t = ld_state<WORLD>(p.b.tie_embed + r0 * EW + i), v_r = ld_state<WORLD>(p.b.riv_embed + r0 * EW + i);
                             s_temb[i] = v_t;
                             s_remb[i] = v_r;
                         }
                     }
                 }
                 __syncwarp();
+                const int rbase = lane * K;  // row of this agent inside the staged block
+                int n_riv = 0, n_t = 0;
+                if (active && (do_obs || do_social_decay)) {
+                    n_riv = min((int)ld_state<WORLD>(p.b.riv_count + a), K);  // counts are clamped to the row stride
+                    n_t = min((int)ld_state<WORLD>(p.b.tie_count + a), K);
+                }
+                if (do_social_decay) {
+                    // ledger decay in the staged rows, then the block goes back with coalesced stores
+                    const int n_riv0 = n_riv, n_t0 = n_t;
+                    if (active) {
+                        social_decay_agent(p, n_riv, n_t, s_trust + rbase, s_fam + rbase, s_riv + rbase, s_score + rbase,
+                                           s_temb + rbase * EW, s_remb + rbase * EW);
+                        if (n_riv != n_riv0) p.b.riv_count[a] = (uint8_t)n_riv;
+                        if (n_t != n_t0) p.b.tie_count[a] = (uint8_t)n_t;
+                    }
+                    const bool riv_moved = __any_sync(FULL, n_riv != n_riv0), tie_moved = __any_sync(FULL, n_t != n_t0);
+                    const bool tie_decays = p.dyn.trust_decay > 0.0 || p.dyn.familiarity_decay > 0.0 || p.dyn.tie_rivalry_decay > 0.0;
+                    __syncwarp();
+#pragma unroll 2
+                    for (int i = lane; i < n_rows; i += 32) {
+                        p.b.riv_score[r0 + i] = s_score[i];
+                        if (tie_decays || tie_moved) {
+                            p.b.tie_trust[r0 + i] = s_trust[i];
+                            p.b.tie_fam[r0 + i] = s_fam[i];
+                            p.b.tie_riv[r0 + i] = s_riv[i];
+                        }
+                    }
+                    if (riv_moved || tie_moved) {
+#pragma unroll 2
+                        for (int i = lane; i < n_rows * EW; i += 32) {
+                            if (tie_moved) p.b.tie_embed[r0 * EW + i] = s_temb[i];
+                            if (riv_moved) p.b.riv_embed[r0 * EW + i] = s_remb[i];
+                        }
+                    }
+                }
                 if (active && do_obs) {
                     float* f = feat_s0 + lane * F;
-                    const int rbase = lane * K;  // row of this agent inside the staged block
-                    const int n_riv = min((int)__ldg(p.b.riv_count + a), K);  // counts are clamped to the row stride
-                    const int n_t = min((int)__ldg(p.b.tie_count + a), K);
                     int filled = 0, source = 0;
                     social_role_agent(p, n_riv, n_t, s_trust + rbase, s_fam + rbase, s_riv + rbase, s_score + rbase,
                                       s_temb + rbase * EW, s_remb + rbase * EW, s_elut, f, filled, source);
@@ -251,7 +291,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 // =================== role "tiles": the warp serves one agent at a time ====
                 // Lane i keeps the integer summary of agent i; the look-ups run thread-per-agent afterwards.
                 const int parity = warp - 2;
-                const int32_t pw = active ? __ldg(p.b.pos + a) : 0;
+                const int32_t pw = active ? ld_state<WORLD>(p.b.pos + a) : 0;
                 int my_others = 0, my_objs = 0, my_res = 0, my_d2 = 0;
                 float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)(c_begin + parity) * map_elems;
 #pragma unroll 1
@@ -265,7 +305,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
 #pragma unroll
                         for (int k = 0; k < kEntCache; ++k) {
                             const int e = eb + 32 * k + lane;
-                            wc[k] = e < ee ? __ldg(p.b.ent + e) : 0u;
+                            wc[k] = e < ee ? ld_state<WORLD>(p.b.ent + e) : 0u;
                         }
                     }
                     // ---- template tile: 16-byte vectorised coalesced stores -------------
@@ -360,7 +400,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
 #pragma unroll 1
                                 for (int e0 = eb + 32 * kEntCache; e0 < ee; e0 += 32) {
                                     const int e = e0 + lane;
-                                    serve(e < ee ? __ldg(p.b.ent + e) : 0u, e, true);
+                                    serve(e < ee ? ld_state<WORLD>(p.b.ent + e) : 0u, e, true);
                                 }
                             }
                         }

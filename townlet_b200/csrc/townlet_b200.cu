@@ -30,6 +30,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 #include "townlet_b200.h"
@@ -54,6 +55,7 @@ struct KParams {
     TlRewardParams rew;
     TlObsOut oo;
     TlRewardOut ro;
+    TlDynamicsParams dyn;
     uint32_t phases;
     int32_t n_ticks;
     int32_t towns_per_cta;
@@ -73,6 +75,14 @@ struct KParams {
     int32_t tmpl_mask;     // entity form: bit m set = a tile template for 16-byte misalignment m floats exists
     int32_t tmpl_off[4];   // entity form: float offset of template m inside the template area
 };
+
+// State the world-dynamics phases may rewrite inside a launch is read with plain loads when they run
+// (MUT) and through the read-only path otherwise.
+template <bool MUT, typename T>
+__device__ __forceinline__ T ld_state(const T* ptr) {
+    if constexpr (MUT) return *ptr;
+    else return __ldg(ptr);
+}
 
 __device__ __forceinline__ int pos_x(int32_t p) { return (int)(int16_t)(p & 0xffff); }
 __device__ __forceinline__ int pos_y(int32_t p) { return (int)(int16_t)((uint32_t)p >> 16); }
@@ -277,8 +287,8 @@ bool cuda_ok(cudaError_t e, const char* what) {
     return false;
 }
 
-int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlObsOut* oo,
-             const TlRewardOut* ro, uint32_t phases, int n_ticks) {
+int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlDynamicsParams* dyn,
+             const TlObsOut* oo, const TlRewardOut* ro, uint32_t phases, int n_ticks) {
     if (!b) return set_error("batch is NULL"), TL_ERR_ARG;
     if (n_ticks < 0) return set_error("n_ticks < 0"), TL_ERR_ARG;
     if (b->n_towns < 0 || b->n_agents < 0 || b->n_entities < 0) return set_error("negative batch size"), TL_ERR_ARG;
@@ -286,8 +296,14 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
     if (b->embed_words < 1 || b->embed_words > 4) return set_error("embed_words out of range"), TL_ERR_ARG;
     if (b->grid_w < 1 || b->grid_h < 1 || b->grid_w > TL_MAX_GRID || b->grid_h > TL_MAX_GRID)
         return set_error("grid size out of range"), TL_ERR_ARG;
-    if (!(phases & (TL_PHASE_DECAY | TL_PHASE_REWARD | TL_PHASE_OBS | TL_PHASE_ADVANCE)))
-        return set_error("empty phase mask"), TL_ERR_ARG;
+    const uint32_t known = TL_PHASE_DECAY | TL_PHASE_REWARD | TL_PHASE_OBS | TL_PHASE_ADVANCE | TL_PHASE_ACTIONS |
+                           TL_PHASE_SOCIAL_DECAY;
+    if (!(phases & known)) return set_error("empty phase mask"), TL_ERR_ARG;
+    if (phases & ~known) return set_error("unknown phase bit"), TL_ERR_ARG;
+    if (phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY)) {
+        if (!dyn) return set_error("dynamics params are NULL (use tl_tick_world)"), TL_ERR_ARG;
+        if ((phases & TL_PHASE_ACTIONS) && !dyn->actions) return set_error("action words are NULL"), TL_ERR_ARG;
+    }
     if (phases & (TL_PHASE_DECAY | TL_PHASE_REWARD)) {
         if (!rew) return set_error("reward params are NULL"), TL_ERR_ARG;
     }
@@ -316,11 +332,12 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
     return TL_OK;
 }
 
-int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlObsOut* oo,
-           const TlRewardOut* ro, uint32_t phases, int n_ticks, cudaStream_t stream, int towns_per_cta_override) {
+int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlDynamicsParams* dyn,
+           const TlObsOut* oo, const TlRewardOut* ro, uint32_t phases, int n_ticks, cudaStream_t stream,
+           int towns_per_cta_override) {
     // an empty batch is a valid no-op (its zero-length arrays may well be NULL pointers)
     if (b && b->n_towns == 0 && b->n_agents == 0 && n_ticks >= 0) return TL_OK;
-    int rc = validate(b, obs, rew, oo, ro, phases, n_ticks);
+    int rc = validate(b, obs, rew, dyn, oo, ro, phases, n_ticks);
     if (rc != TL_OK) return rc;
     if (b->n_towns == 0 || n_ticks == 0) return TL_OK;
 
@@ -331,6 +348,7 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     if (rew) kp.rew = *rew;
     if (oo) kp.oo = *oo;
     if (ro) kp.ro = *ro;
+    if (dyn) kp.dyn = *dyn;
     kp.phases = phases;
     kp.n_ticks = n_ticks;
     const bool do_obs = phases & TL_PHASE_OBS;
@@ -418,7 +436,7 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         kp.off_meta = off;
         off += round_up((int)sizeof(KpiAcc) * tpc, 16);
         kp.off_social = off;
-        if (do_obs) off += chunk * b->max_edges * (4 * 8 + 2 * 8 * b->embed_words) + 256 * 4;
+        if (do_obs || (phases & TL_PHASE_SOCIAL_DECAY)) off += chunk * b->max_edges * (4 * 8 + 2 * 8 * b->embed_words) + 256 * 4;
         kp.smem_bytes = off;
         if (off > max_smem) return set_error("observation staging does not fit in shared memory"), TL_ERR_UNSUPPORTED;
         kp.towns_per_cta = tpc;
@@ -477,16 +495,23 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     if (kp.mode == 0) {
         const bool generic = getenv("TL_GENERIC") != nullptr;  // force the runtime-window form (tests)
         const int win = do_obs ? kp.obs.window : 0;
+        const bool world = phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY);
+        auto pick = [&](auto variant, auto window) -> int {
+            if (world) return run(tick_kernel_roles<decltype(variant)::value, decltype(window)::value, true>);
+            return run(tick_kernel_roles<decltype(variant)::value, decltype(window)::value, false>);
+        };
+        using std::integral_constant;
         switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
             case TL_VARIANT_HYBRID:
-                if (win == 11 && !generic) return run(tick_kernel_roles<TL_VARIANT_HYBRID, 11>);
-                return run(tick_kernel_roles<TL_VARIANT_HYBRID, 0>);
+                if (win == 11 && !generic) return pick(integral_constant<int, TL_VARIANT_HYBRID>{}, integral_constant<int, 11>{});
+                return pick(integral_constant<int, TL_VARIANT_HYBRID>{}, integral_constant<int, 0>{});
             case TL_VARIANT_FULL:
-                if (win == 11 && !generic) return run(tick_kernel_roles<TL_VARIANT_FULL, 11>);
-                return run(tick_kernel_roles<TL_VARIANT_FULL, 0>);
+                if (win == 11 && !generic) return pick(integral_constant<int, TL_VARIANT_FULL>{}, integral_constant<int, 11>{});
+                return pick(integral_constant<int, TL_VARIANT_FULL>{}, integral_constant<int, 0>{});
             case TL_VARIANT_COMPACT:
-                if (win == 7 && kp.obs.n_ctypes == 0 && !generic) return run(tick_kernel_roles<TL_VARIANT_COMPACT, 7>);
-                return run(tick_kernel_roles<TL_VARIANT_COMPACT, 0>);
+                if (win == 7 && kp.obs.n_ctypes == 0 && !generic)
+                    return pick(integral_constant<int, TL_VARIANT_COMPACT>{}, integral_constant<int, 7>{});
+                return pick(integral_constant<int, TL_VARIANT_COMPACT>{}, integral_constant<int, 0>{});
             default: return set_error("unknown variant"), TL_ERR_ARG;
         }
     }
@@ -515,6 +540,7 @@ int tl_abi_struct_size(int idx) {
         case 2: return (int)sizeof(TlRewardParams);
         case 3: return (int)sizeof(TlObsOut);
         case 4: return (int)sizeof(TlRewardOut);
+        case 5: return (int)sizeof(TlDynamicsParams);
         default: return -1;
     }
 }
@@ -545,18 +571,24 @@ int tl_gae(const float* rewards, const float* values, const float* dones, float*
 }
 
 int tl_obs_build(const TlTownBatch* batch, const TlObsParams* obs, const TlObsOut* out, tl_stream_t stream) {
-    return launch(batch, obs, nullptr, out, nullptr, TL_PHASE_OBS, 1, (cudaStream_t)stream, 0);
+    return launch(batch, obs, nullptr, nullptr, out, nullptr, TL_PHASE_OBS, 1, (cudaStream_t)stream, 0);
 }
 
 int tl_decay_reward(const TlTownBatch* batch, const TlRewardParams* rew, const TlRewardOut* out, uint32_t phases,
                     tl_stream_t stream) {
     if (phases & ~(TL_PHASE_DECAY | TL_PHASE_REWARD)) return set_error("tl_decay_reward accepts DECAY | REWARD only"), TL_ERR_ARG;
-    return launch(batch, nullptr, rew, nullptr, out, phases, 1, (cudaStream_t)stream, 0);
+    return launch(batch, nullptr, rew, nullptr, nullptr, out, phases, 1, (cudaStream_t)stream, 0);
 }
 
 int tl_tick(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardParams* rew, const TlObsOut* obs_out,
             const TlRewardOut* rew_out, uint32_t phases, int32_t n_ticks, tl_stream_t stream) {
-    return launch(batch, obs, rew, obs_out, rew_out, phases, n_ticks, (cudaStream_t)stream, 0);
+    return launch(batch, obs, rew, nullptr, obs_out, rew_out, phases, n_ticks, (cudaStream_t)stream, 0);
+}
+
+int tl_tick_world(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardParams* rew,
+                  const TlDynamicsParams* dyn, const TlObsOut* obs_out, const TlRewardOut* rew_out, uint32_t phases,
+                  int32_t n_ticks, tl_stream_t stream) {
+    return launch(batch, obs, rew, dyn, obs_out, rew_out, phases, n_ticks, (cudaStream_t)stream, 0);
 }
 
 // ---- host-buffer context ----------------------------------------------------
@@ -619,7 +651,9 @@ bool ensure(unsigned char** buf, size_t* cap, size_t need) {
 int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, const TlRewardParams* rew,
                  const TlObsOut* hoo, const TlRewardOut* hro, uint32_t phases, int32_t n_ticks) {
     if (!ctx) return set_error("context is NULL"), TL_ERR_ARG;
-    int rc = validate(hb, obs, rew, hoo, hro, phases, n_ticks);
+    if (phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY))
+        return set_error("the world-dynamics phases run on device-resident batches (tl_tick_world)"), TL_ERR_UNSUPPORTED;
+    int rc = validate(hb, obs, rew, nullptr, hoo, hro, phases, n_ticks);
     if (rc != TL_OK) return rc;
     if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return TL_ERR_CUDA;
     ctx->last_h2d = ctx->last_d2h = 0;
@@ -773,7 +807,7 @@ int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, 
         dro.kpi = hro->kpi ? (float*)(ctx->d_out + o_kpi) : nullptr;
     }
 
-    rc = launch(&db, obs ? &dobs : nullptr, rew, do_obs ? &doo : nullptr, (do_state && hro) ? &dro : nullptr, phases,
+    rc = launch(&db, obs ? &dobs : nullptr, rew, nullptr, do_obs ? &doo : nullptr, (do_state && hro) ? &dro : nullptr, phases,
                 n_ticks, ctx->stream, 0);
     if (rc != TL_OK) return rc;
 

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .params import ObsSpec, RewardSpec
+from .params import DynamicsSpec, ObsSpec, RewardSpec
 from .soa import MUTABLE_FIELDS, TownBatch
 
 _TORCH_DTYPES = {
@@ -53,6 +53,7 @@ class DeviceTownBatch:
         obs: ObsSpec | None = None,
         rew: RewardSpec | None = None,
         device: torch.device | str = "cuda:0",
+        dyn: DynamicsSpec | None = None,
     ) -> None:
         self.lib = capi.load_library()
         self.device = torch.device(device)
@@ -68,6 +69,8 @@ class DeviceTownBatch:
         self._luts: dict[str, torch.Tensor] = {}
         self._obs_struct: capi.TlObsParams | None = None
         self._rew_struct: capi.TlRewardParams | None = rew.struct() if rew is not None else None
+        self.dyn = dyn
+        self._dyn_struct: capi.TlDynamicsParams | None = dyn.struct() if dyn is not None else None
         if obs is not None:
             for name, table in obs.luts().items():
                 self._luts[name] = torch.from_numpy(np.ascontiguousarray(table)).to(self.device)
@@ -97,8 +100,12 @@ class DeviceTownBatch:
         self.arena.copy_(torch.from_numpy(src.arena[: self.layout.total_bytes]), non_blocking=True)
 
     def download_state(self) -> TownBatch:
-        """Device → host copy of the mutable fields into ``self.host`` (one copy)."""
-        n = self.layout.mutable_bytes
+        """Device → host copy of the mutable fields into ``self.host`` (one copy).
+
+        With a ``DynamicsSpec`` the world-dynamics phases may have rewritten positions, entity words and
+        ledger rows as well, so the whole arena comes back.
+        """
+        n = self.layout.mutable_bytes if self.dyn is None else self.layout.total_bytes
         self.host.arena[:n] = self.arena[:n].cpu().numpy()
         return self.host
 
@@ -155,14 +162,42 @@ class DeviceTownBatch:
         return oo, ro
 
     # launches -------------------------------------------------------------
-    def tick(self, out: TickOutputs, phases: int = capi.TL_PHASE_ALL, n_ticks: int = 1, tick0: int = 0) -> None:
-        """One launch advancing ``n_ticks`` ticks; outputs go to ``out[tick0 : tick0 + n_ticks]``."""
+    def tick(
+        self,
+        out: TickOutputs,
+        phases: int = capi.TL_PHASE_ALL,
+        n_ticks: int = 1,
+        tick0: int = 0,
+        actions: torch.Tensor | None = None,
+    ) -> None:
+        """One launch advancing ``n_ticks`` ticks; outputs go to ``out[tick0 : tick0 + n_ticks]``.
+
+        ``actions`` (``TL_PHASE_ACTIONS``): device action words, ``[n_agents]`` (applied every tick of the
+        launch) or ``[n_ticks, n_agents]``, int32 / uint32 bit patterns of ``params.pack_actions``.
+        """
         oo, ro = self._out_structs(out, tick0)
         obs_p = C.byref(self._obs_struct) if self._obs_struct is not None else None
         rew_p = C.byref(self._rew_struct) if self._rew_struct is not None else None
+        dyn_p = None
+        if phases & (capi.TL_PHASE_ACTIONS | capi.TL_PHASE_SOCIAL_DECAY):
+            if self._dyn_struct is None:
+                raise capi.TownletB200Error("the world-dynamics phases need a DynamicsSpec")
+            self._dyn_struct.actions = None
+            self._dyn_struct.actions_tick_stride = 0
+            if phases & capi.TL_PHASE_ACTIONS:
+                if actions is None or actions.device != self.arena.device or actions.element_size() != 4:
+                    raise capi.TownletB200Error("TL_PHASE_ACTIONS needs a 32-bit action tensor on the batch's device")
+                if not actions.is_contiguous() or actions.shape[-1] != self.n_agents:
+                    raise capi.TownletB200Error("actions must be contiguous [n_agents] or [n_ticks, n_agents]")
+                if actions.dim() == 2 and actions.shape[0] != n_ticks:
+                    raise capi.TownletB200Error("actions has the wrong number of ticks")
+                self._dyn_struct.actions = actions.data_ptr()
+                self._dyn_struct.actions_tick_stride = self.n_agents if actions.dim() == 2 else 0
+            dyn_p = C.byref(self._dyn_struct)
         with torch.cuda.device(self.device):
-            status = self.lib.tl_tick(
-                C.byref(self._struct), obs_p, rew_p, C.byref(oo), C.byref(ro), phases, n_ticks, _stream_ptr(self.device)
+            status = self.lib.tl_tick_world(
+                C.byref(self._struct), obs_p, rew_p, dyn_p, C.byref(oo), C.byref(ro), phases, n_ticks,
+                _stream_ptr(self.device),
             )
         capi.check(status)
 

@@ -8,8 +8,11 @@ convention (``reset`` / ``step`` returning observations, rewards, terminations,
 truncations, infos) over all towns of a device batch at once, duck-typed so
 that ``pettingzoo`` itself is not required.
 
-Action application (movement, queueing) is upstream of the hot path
- and stays with the caller: pass ``apply_actions`` to
+Actions: with a ``DynamicsSpec`` the tick applies device-resident action words itself (moves and
+outcome bookkeeping, ``TL_PHASE_ACTIONS``) and decays the relationship / rivalry ledgers
+(``TL_PHASE_SOCIAL_DECAY``) in ``WorldContext.tick`` order (world/core/context.py:229-289); pass the words
+to ``step`` (``townlet_b200.actions.encode_actions`` / ``params.pack_actions``).  Kinds that go through host
+services (queues, affordances, chat) are resolved by the caller, who may also pass ``apply_actions`` to
 mutate the device batch before the tick.
 """
 
@@ -22,7 +25,7 @@ import torch
 
 from . import capi
 from .engine import DeviceTownBatch, TickOutputs
-from .params import ObsSpec, RewardSpec
+from .params import DynamicsSpec, ObsSpec, RewardSpec
 from .soa import TownBatch
 
 
@@ -39,6 +42,7 @@ class TownletParallelEnv:
         device: str | torch.device = "cuda:0",
         apply_actions: Callable[[DeviceTownBatch, Any], None] | None = None,
         max_ticks: int | None = None,
+        dyn: DynamicsSpec | None = None,
     ) -> None:
         self._initial = batch.copy()
         self.obs_spec = obs
@@ -46,7 +50,9 @@ class TownletParallelEnv:
         self.device = torch.device(device)
         self._apply_actions = apply_actions
         self._max_ticks = max_ticks
-        self._dev = DeviceTownBatch(batch.copy(), obs, rew, self.device)
+        self._dev = DeviceTownBatch(batch.copy(), obs, rew, self.device, dyn=dyn)
+        self._world_phases = dyn is not None
+        self._no_actions = torch.zeros(batch.n_agents, dtype=torch.int32, device=self.device) if dyn is not None else None
         self._out: TickOutputs = self._dev.alloc_outputs(capi.TL_PHASE_ALL, 1)
         self._ticks = 0
         self.num_agents = batch.n_agents
@@ -70,9 +76,16 @@ class TownletParallelEnv:
         return self._observations(), {}
 
     def step(self, actions: Any = None):
+        """Advance every town one tick.  ``actions``: int32 device tensor ``[n_agents]`` of action words when
+        the env was built with a ``DynamicsSpec`` (``None`` = nobody acts); otherwise whatever the
+        ``apply_actions`` callback expects."""
         if self._apply_actions is not None:
             self._apply_actions(self._dev, actions)
-        self._dev.tick(self._out, capi.TL_PHASE_ALL, 1)
+        if self._world_phases:
+            words = actions if isinstance(actions, torch.Tensor) else self._no_actions
+            self._dev.tick(self._out, capi.TL_PHASE_WORLD, 1, actions=words)
+        else:
+            self._dev.tick(self._out, capi.TL_PHASE_ALL, 1)
         self._ticks += 1
         assert self._out.reward is not None and self._out.terminated is not None and self._out.kpi is not None
         terminations = self._out.terminated[0].bool()

@@ -417,3 +417,59 @@ class RewardSpec:
         p.reward_personality = int(self.personality_scaling)
         p.fuse_faint = int(self.fuse_faint)
         return p
+
+
+@dataclass
+class DynamicsSpec:
+    """World dynamics around the hot path.
+
+    Relationship ties decay with ``RelationshipParameters`` (world/relationships.py:14-21; the service
+    builds them with defaults, relationships_service.py:237-238), the rivalry ledger with
+    ``conflict.rivalry`` (config/conflict.py:17-24, relationships_service.py:240-249).
+    """
+
+    trust_decay: float = 0.0
+    familiarity_decay: float = 0.0
+    tie_rivalry_decay: float = 0.01
+    rivalry_decay_per_tick: float = 0.005
+    rivalry_min: float = 0.0
+    rivalry_max: float = 1.0
+    rivalry_eviction_threshold: float = 0.05
+
+    @classmethod
+    def from_config(cls, config: Any) -> "DynamicsSpec":
+        cfg = config.conflict.rivalry
+        return cls(
+            rivalry_decay_per_tick=float(cfg.decay_per_tick),
+            rivalry_min=float(cfg.min_value),
+            rivalry_max=float(cfg.max_value),
+            rivalry_eviction_threshold=float(cfg.eviction_threshold),
+        )
+
+    def struct(self) -> capi.TlDynamicsParams:
+        from .hashing import last_action_hash
+
+        d = capi.TlDynamicsParams()
+        d.trust_decay = self.trust_decay
+        d.familiarity_decay = self.familiarity_decay
+        d.tie_rivalry_decay = self.tie_rivalry_decay
+        d.rivalry_decay_per_tick = self.rivalry_decay_per_tick
+        d.rivalry_min = self.rivalry_min
+        d.rivalry_max = self.rivalry_max
+        d.rivalry_eviction_threshold = self.rivalry_eviction_threshold
+        for code, kind in enumerate(capi.ACT_KINDS):
+            d.action_hash[code] = last_action_hash(kind)
+        return d
+
+
+def pack_actions(kind, success=0, has_pos=0, x=0, y=0, duration=1):
+    """Action words (include/townlet_b200.h: TL_ACT_PACK) from integer arrays or scalars."""
+    kind, success, has_pos, x, y, duration = (np.asarray(v, dtype=np.int64) for v in (kind, success, has_pos, x, y, duration))
+    if np.any((kind < 0) | (kind >= capi.TL_N_ACT_KINDS)):
+        raise ValueError("action kind code out of range")
+    if np.any((duration < 0) | (duration > 63)):
+        raise ValueError("action duration must lie in 0..63")
+    if np.any(has_pos.astype(bool) & ((x < 0) | (x >= capi.TL_MAX_GRID) | (y < 0) | (y >= capi.TL_MAX_GRID))):
+        raise ValueError("move target outside 0..1023")
+    word = (kind & 15) | ((success & 1) << 4) | ((has_pos & 1) << 5) | ((x & 1023) << 6) | ((y & 1023) << 16) | ((duration & 63) << 26)
+    return word.astype(np.uint32)
