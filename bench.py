@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — agent-steps/s of the per-tick hot path (obs build + need decay + reward).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3-compact|c3-full|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3-compact|c3-full|c4|c5|c2-world]
     python bench.py --impl reference ...      # the CPU arm (oracle port, all host threads)
 
 A "step" is ONE TICK of the whole synthetic batch: need decay -> faint
@@ -37,6 +37,10 @@ WORKLOADS = {
                     name="configs[2]: full, 16,384 towns x 48x48 x 10 agents"),
     "c4": dict(variant="hybrid", towns=4096, grid=128, agents=64, bytes_per_agent_step=2712,
                name="configs[3]: hybrid, 4,096 towns x 128x128 x 64 agents"),
+    # configs[1] with the world-dynamics phases: random action words every tick, ledger decay;
+    # +24 B per agent-step (action word read, pos / entity word / flags / last-action duration and hash write-back)
+    "c2-world": dict(variant="hybrid", towns=1024, grid=48, agents=8, bytes_per_agent_step=2712 + 24, world=True,
+                     name="configs[1] + actions and ledger decay in the tick: hybrid, 1,024 towns x 48x48 x 8 agents"),
     # configs[4] per GPU: 65,536 towns over 8 GPUs = 8,192 towns per rank, policy forward in the loop
     "c5": dict(variant="hybrid", towns=8192, grid=48, agents=8, bytes_per_agent_step=2712, policy=True,
                name="configs[4]: PPO rollout capture, 8,192 towns per GPU x 48x48 x 8 agents, policy forward in-loop"),
@@ -117,17 +121,23 @@ def cpu_oracle_rate(wl: dict, budget_s: float, threads: int) -> tuple[float, str
     """agent-steps/s of the C oracle (CPU restatement of the reference) on a bounded sample."""
     from oracle.oracle import oracle_tick
     from townlet_b200 import capi
-    from townlet_b200.params import RewardSpec
+    from townlet_b200.params import DynamicsSpec, RewardSpec
 
     sample_towns = min(wl["towns"], DISTINCT_TOWNS)
     small = dict(wl, towns=sample_towns)
     batch, obs = make_batch(small, 0)
     rew = RewardSpec(fuse_faint=True)
-    oracle_tick(batch, obs, rew, capi.TL_PHASE_ALL, 1, n_threads=threads, want_comps=False)  # warm-up
+    phases, extra = capi.TL_PHASE_ALL, {}
+    if wl.get("world"):
+        from townlet_b200.synth import random_actions
+
+        phases = capi.TL_PHASE_WORLD
+        extra = dict(dyn=DynamicsSpec(), actions=random_actions(batch, 4, seed=4321))
+    oracle_tick(batch, obs, rew, phases, 4, n_threads=threads, want_comps=False, **extra)  # warm-up
     ticks_done = 0
     t0 = time.perf_counter()
     while True:
-        oracle_tick(batch, obs, rew, capi.TL_PHASE_ALL, 4, n_threads=threads, want_comps=False)
+        oracle_tick(batch, obs, rew, phases, 4, n_threads=threads, want_comps=False, **extra)
         ticks_done += 4
         if time.perf_counter() - t0 >= budget_s:
             break
@@ -201,7 +211,7 @@ def main() -> None:
 
     from townlet_b200 import capi
     from townlet_b200.engine import DeviceTownBatch, HostEngine
-    from townlet_b200.params import RewardSpec
+    from townlet_b200.params import DynamicsSpec, RewardSpec
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -218,7 +228,8 @@ def main() -> None:
     # every rank owns its own block of towns (towns are independent: no collective in the tick)
     batch, obs = make_batch(wl, rank)
     rew = RewardSpec(fuse_faint=True)
-    dev = DeviceTownBatch(batch, obs, rew, device)
+    dyn = DynamicsSpec() if wl.get("world") else None
+    dev = DeviceTownBatch(batch, obs, rew, device, dyn=dyn)
     n_agents = batch.n_agents
     tpl = max(1, min(args.ticks_per_launch, args.steps))
     steps = (args.steps // tpl) * tpl
@@ -229,6 +240,18 @@ def main() -> None:
     if wl.get("policy"):
         ring = tpl  # a rollout buffer of tpl ticks, consumed by the policy every tick
     out = dev.alloc_outputs(capi.TL_PHASE_ALL, ring, summary=False, comps=False, kpi=True)
+
+    phases = capi.TL_PHASE_WORLD if wl.get("world") else capi.TL_PHASE_ALL
+    if os.environ.get("TL_BENCH_PHASES"):  # experiments only: override the phase mask
+        phases = int(os.environ["TL_BENCH_PHASES"], 0)
+    action_words = pristine = None
+    if wl.get("world"):
+        # seeded action words for every tick of a launch (60 % moves to a random tile, waits, idle agents); every
+        # launch starts from the pristine state (an episode reset), so the ledgers are live in every launch
+        from townlet_b200.synth import random_actions
+
+        action_words = torch.from_numpy(random_actions(batch, tpl, seed=4321 + rank).view("int32")).to(device)
+        pristine = dev.arena.clone()
 
     capture = None
     if wl.get("policy"):
@@ -253,7 +276,9 @@ def main() -> None:
             if world > 1:
                 dist.all_reduce(totals, op=dist.ReduceOp.SUM)
             return
-        dev.tick(out, capi.TL_PHASE_ALL, tpl, tick0=(i * tpl) % ring)
+        if pristine is not None:
+            dev.arena.copy_(pristine)
+        dev.tick(out, phases, tpl, tick0=(i * tpl) % ring, actions=action_words)
 
     for i in range(-(-warm // tpl)):
         launch(i)
@@ -307,7 +332,8 @@ def main() -> None:
         "unit": "GB/s",
         "frac": achieved / peak,
         "traffic": None,
-        "kernel": f"tick_kernel_roles<{wl['variant']}>" + (" + batched policy forward + gae_kernel" if wl.get("policy") else ""),
+        "kernel": f"tick_kernel_roles<{wl['variant']}{', world' if wl.get('world') else ''}>"
+        + (" + batched policy forward + gae_kernel" if wl.get("policy") else ""),
         "algorithmic_bytes_per_launch": algo_bytes,
         "avg_launch_ms": avg_launch_s * 1e3,
         "peak_source": peak_src,
@@ -324,7 +350,40 @@ def main() -> None:
 
     # ---- e2e: host buffers through tl_host_tick (H2D + kernel + D2H per step) --
     e2e = None
-    if rank == 0 or world > 1:
+    if wl.get("world"):
+        # the world phases run on device-resident batches: per step the action words come from pinned host memory
+        # and the observations / rewards go back to pinned host memory through the public DeviceTownBatch API
+        eout = dev.alloc_outputs(phases, 1, summary=False, comps=False, kpi=True)
+        h_act = torch.zeros(n_agents, dtype=torch.int32, pin_memory=True)
+        h_act.copy_(action_words[0].cpu())
+        d_act = torch.empty(n_agents, dtype=torch.int32, device=device)
+        h_out = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in vars(eout).items() if v is not None}
+
+        def e2e_step() -> None:
+            d_act.copy_(h_act, non_blocking=True)
+            dev.tick(eout, phases, 1, actions=d_act)
+            for k, v in h_out.items():
+                v.copy_(getattr(eout, k), non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {
+            "value": world * n_agents * args.e2e_steps / float(te.item()),
+            "unit": "agent-steps/s",
+            "h2d_bytes_per_step": int(h_act.numel() * 4),
+            "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in h_out.values())),
+            "api": "DeviceTownBatch.tick (device-resident towns; action words in, observations out through pinned host buffers)",
+        }
+    elif rank == 0 or world > 1:
         host = HostEngine(obs, rew, local_rank)
         pinned = torch.empty(batch.layout.total_bytes, dtype=torch.uint8, pin_memory=True)
         pinned.numpy()[:] = batch.arena[: batch.layout.total_bytes]

@@ -19,7 +19,7 @@ from oracle.oracle import oracle_tick
 from townlet_b200 import capi
 from townlet_b200.actions import encode_actions
 from townlet_b200.params import DynamicsSpec, ObsSpec, RewardSpec, pack_actions
-from townlet_b200.synth import synth_batch
+from townlet_b200.synth import random_actions, synth_batch
 
 FIXTURES = world_fixture_paths()
 LEDGER_FIELDS = ("tie_count", "tie_trust", "tie_fam", "tie_riv", "tie_embed", "riv_count", "riv_score", "riv_embed")
@@ -36,19 +36,6 @@ def _check_final_state(batch, ref, what: str) -> None:
     assert np.array_equal(got_success, ref["final_last_success"]), f"{what}: last_action_success"
     np.testing.assert_allclose(batch.needs, ref["needs"][-1], rtol=REL_TOL, atol=1e-15)
     np.testing.assert_allclose(batch.episode_total, ref["episode_total"][-1], rtol=REL_TOL, atol=1e-12)
-
-
-def random_actions(batch, n_ticks: int, seed: int) -> np.ndarray:
-    """Seeded action words: moves anywhere on the grid, moves without a position, waits, idle agents."""
-    rng = np.random.default_rng(seed)
-    n = batch.n_agents
-    kind = rng.choice([0, 1, 1, 1, 2, 3, 7], size=(n_ticks, n))
-    has_pos = (kind == 1) & (rng.random((n_ticks, n)) < 0.9)
-    x = rng.integers(0, batch.grid_w, size=(n_ticks, n))
-    y = rng.integers(0, batch.grid_h, size=(n_ticks, n))
-    success = rng.integers(0, 2, size=(n_ticks, n))
-    duration = rng.integers(0, 64, size=(n_ticks, n))
-    return pack_actions(kind, success, has_pos, x, y, duration)
 
 
 # ---------------------------------------------------------------------------

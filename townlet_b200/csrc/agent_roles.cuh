@@ -10,6 +10,46 @@ struct StateRoleOut {
     bool terminated = false;    // effective terminated flag of the tick
 };
 
+// What process_actions leaves on ONE agent (world/systems/affordances.py:124-229 after
+// world/actions.py:44-105).  A move with a position relocates the agent — snapshot.position and the spatial
+// index (world/spatial.py:62-83), i.e. the agent's own entity word — and succeeds; every other kind carries
+// the success the host services resolved; apply_affordance_outcome (world/affordances/core.py:198-206)
+// records kind, success and duration.  The caller's copies of the fields are updated along with memory
+// (flags are left to the caller, which rewrites them anyway).
+__device__ __forceinline__ void apply_action_agent(const KParams& p, int a, int self_e, uint32_t w, uint32_t& fl,
+                                                   int& duration, float& last_hash, int32_t& pw) {
+    const unsigned kind = TL_ACT_KIND(w);
+    bool success = TL_ACT_SUCCESS(w) != 0;
+    if (kind == TL_ACT_MOVE) {
+        success = TL_ACT_HAS_POS(w) != 0;
+        if (success) {
+            const uint32_t x = (uint32_t)TL_ACT_X(w), y = (uint32_t)TL_ACT_Y(w);
+            pw = (int32_t)(x | (y << 16));
+            p.b.pos[a] = pw;
+            p.b.ent[self_e] = (p.b.ent[self_e] & ~0xfffffu) | x | (y << 10);
+        }
+    }
+    fl = (fl & ~TL_F_LAST_SUCCESS) | (success ? TL_F_LAST_SUCCESS : 0u);
+    duration = TL_ACT_DURATION(w);
+    last_hash = p.dyn.action_hash[kind];
+    p.b.last_action_duration[a] = duration;
+    p.b.last_action_hash[a] = last_hash;
+}
+
+// The position part of an action word on top of a packed position / entity word: what every reader of
+// pos / ent uses inside a launch that applies actions, so that it does not depend on whether the owning
+// thread has written the move back yet.
+__device__ __forceinline__ int32_t moved_pos(int32_t pw, uint32_t act_w) {
+    if (TL_ACT_KIND(act_w) == TL_ACT_MOVE && TL_ACT_HAS_POS(act_w))
+        return (int32_t)((uint32_t)TL_ACT_X(act_w) | ((uint32_t)TL_ACT_Y(act_w) << 16));
+    return pw;
+}
+__device__ __forceinline__ uint32_t moved_ent(uint32_t ew, uint32_t act_w) {
+    if (TL_ACT_KIND(act_w) == TL_ACT_MOVE && TL_ACT_HAS_POS(act_w))
+        return (ew & ~0xfffffu) | (uint32_t)TL_ACT_X(act_w) | ((uint32_t)TL_ACT_Y(act_w) << 10);
+    return ew;
+}
+
 // Role "state" for ONE agent: float64 need decay (world/grid.py:1439-1455), faint predicate
 // (lifecycle/manager.py:39-45), episode tick (world/core/context.py:283-289), reward with guardrails
 // (rewards/engine.py:71-172) and, when `f` is not null, the scalar features, path hint, landmarks and
@@ -18,7 +58,8 @@ struct StateRoleOut {
 // are read with plain loads; otherwise through the read-only path.
 template <bool MUT>
 __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a, int tick, int town_abeg, int town_aend,
-                                                 int town_ebeg, int town_eend, float* f, StateRoleOut& out) {
+                                                 int town_ebeg, int town_eend, uint32_t act_w, float* f,
+                                                 StateRoleOut& out) {
     const TlObsParams& o = p.obs;
     const int N = p.b.n_agents;
     const bool do_decay = p.phases & TL_PHASE_DECAY;
@@ -55,6 +96,12 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
         slot_idx = __ldg(p.b.slot + a);
         last_hash = ld_state<MUT>(p.b.last_action_hash + a);
         pw = ld_state<MUT>(p.b.pos + a);
+    }
+    if (MUT && TL_ACT_KIND(act_w) != TL_ACT_NONE) {
+        // TL_PHASE_ACTIONS, applied by the agent's own thread (the tiles role derives the same positions from
+        // the action words, so no barrier is needed between this write-back and its reads)
+        apply_action_agent(p, a, town_ebeg + (a - town_abeg), act_w, fl, duration, last_hash, pw);
+        p.b.flags[a] = fl;
     }
     const unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
     if (do_decay) {  // world/grid.py:1439-1455
@@ -337,35 +384,25 @@ __device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, i
     }
 }
 
-// TL_PHASE_ACTIONS for the agents of one CTA's towns [t0, t0 + n_towns): what process_actions leaves on
-// the agent snapshot (world/systems/affordances.py:124-229 after world/actions.py:44-105).  A move with a
-// position relocates the agent — snapshot.position and the spatial index (world/spatial.py:62-83), i.e.
-// the agent's own entity word — and succeeds; every other kind carries the success the host services
-// resolved; apply_affordance_outcome (world/affordances/core.py:198-206) records kind, success, duration.
-// The caller puts a block barrier between this and any read of pos / ent / the last-action fields.
+// TL_PHASE_ACTIONS for the agents of one CTA's towns [t0, t0 + n_towns), all threads of the CTA (the grid
+// form, which stages the entity words of a tick before any agent is served).  The caller puts a block
+// barrier between this and any read of pos / ent / the last-action fields.
 __device__ __forceinline__ void apply_actions_cta(const KParams& p, int it, int t0, int n_towns, int tid, int n_threads) {
     const int a_begin = p.b.town_agent_off[t0], a_end = p.b.town_agent_off[t0 + n_towns];
     const uint32_t* act = p.dyn.actions + (size_t)it * p.dyn.actions_tick_stride;
 #pragma unroll 1
     for (int a = a_begin + tid; a < a_end; a += n_threads) {
         const uint32_t w = __ldg(act + a);
-        const unsigned kind = TL_ACT_KIND(w);
-        if (kind == TL_ACT_NONE) continue;
-        bool success = TL_ACT_SUCCESS(w) != 0;
-        if (kind == TL_ACT_MOVE) {
-            success = TL_ACT_HAS_POS(w) != 0;
-            if (success) {
-                int s = 0;
-                while (s + 1 < n_towns && a >= p.b.town_agent_off[t0 + s + 1]) ++s;
-                const int self_e = p.b.town_ent_off[t0 + s] + (a - p.b.town_agent_off[t0 + s]);
-                const uint32_t x = (uint32_t)TL_ACT_X(w), y = (uint32_t)TL_ACT_Y(w);
-                p.b.pos[a] = (int32_t)(x | (y << 16));
-                p.b.ent[self_e] = (p.b.ent[self_e] & ~0xfffffu) | x | (y << 10);
-            }
-        }
-        p.b.flags[a] = (p.b.flags[a] & ~TL_F_LAST_SUCCESS) | (success ? TL_F_LAST_SUCCESS : 0u);
-        p.b.last_action_duration[a] = TL_ACT_DURATION(w);
-        p.b.last_action_hash[a] = p.dyn.action_hash[kind];
+        if (TL_ACT_KIND(w) == TL_ACT_NONE) continue;
+        int s = 0;
+        while (s + 1 < n_towns && a >= p.b.town_agent_off[t0 + s + 1]) ++s;
+        const int self_e = p.b.town_ent_off[t0 + s] + (a - p.b.town_agent_off[t0 + s]);
+        uint32_t fl = p.b.flags[a];
+        int duration;
+        float last_hash;
+        int32_t pw;
+        apply_action_agent(p, a, self_e, w, fl, duration, last_hash, pw);
+        p.b.flags[a] = fl;
     }
 }
 

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
                     StateRoleOut so;
                     if (active)
                         state_role_agent<true>(p, it, a, tm.tick, tm.agent_begin, tm.agent_end, tm.ent_begin, tm.ent_end,
+                                         0u /* actions were applied before the grid was staged */,
                                          do_obs ? feat_s0 + lane * F : nullptr, so);
                     // ---- per-town KPIs: segmented warp-shuffle reduction ------------
                     if (do_state && p.ro.kpi) {

@@ -109,10 +109,9 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
 #pragma unroll 1
     for (int it = 0; it < p.n_ticks; ++it) {
         cached_eb = -1;  // every tick re-reads the entity words of its towns
-        if (do_actions) {  // world/core/context.py:253-257: actions land before any system or observer runs
-            apply_actions_cta(p, it, t0, n_towns, tid, 32 * kRoleWarps);
-            __syncthreads();
-        }
+        // world/core/context.py:253-257: actions land before any system or observer runs.  No barrier: the state
+        // role writes its agent's move back, and every reader of pos / ent re-derives it from the action words.
+        const uint32_t* act = do_actions ? p.dyn.actions + (size_t)it * p.dyn.actions_tick_stride : nullptr;
         if (warp == 0) {
             if (do_advance && lane < n_towns) {  // core/sim_loop.py:635,659
                 my_tick += 1;
@@ -160,7 +159,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 StateRoleOut so;
                 if (active)
                     state_role_agent<WORLD>(p, it, a, tick, town_abeg, town_aend, town_ebeg, town_eend,
-                                     do_obs ? feat_s0 + lane * F : nullptr, so);
+                                            do_actions ? __ldg(act + a) : 0u, do_obs ? feat_s0 + lane * F : nullptr, so);
                 const double need0 = so.need0, reward_total = so.reward_total, kpi_wallet = so.kpi_wallet;
                 const bool terminated = so.terminated;
                 const int kpi_late = so.kpi_late;
@@ -219,6 +218,12 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 const bool stage_ties = o.social_base >= 0 || do_social_decay;
                 const size_t r0 = (size_t)c_begin * K;
                 const int n_rows = c_n * K;
+                const int rbase = lane * K;  // row of this agent inside the staged block
+                int n_riv = 0, n_t = 0;
+                if (active && (do_obs || do_social_decay)) {
+                    n_riv = min((int)ld_state<WORLD>(p.b.riv_count + a), K);  // counts are clamped to the row stride
+                    n_t = min((int)ld_state<WORLD>(p.b.tie_count + a), K);
+                }
                 if (do_obs || do_social_decay) {
 #pragma unroll 2
                     for (int i = lane; i < n_rows; i += 32) {
@@ -242,12 +247,6 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                     }
                 }
                 __syncwarp();
-                const int rbase = lane * K;  // row of this agent inside the staged block
-                int n_riv = 0, n_t = 0;
-                if (active && (do_obs || do_social_decay)) {
-                    n_riv = min((int)ld_state<WORLD>(p.b.riv_count + a), K);  // counts are clamped to the row stride
-                    n_t = min((int)ld_state<WORLD>(p.b.tie_count + a), K);
-                }
                 if (do_social_decay) {
                     // ledger decay in the staged rows, then the block goes back with coalesced stores
                     const int n_riv0 = n_riv, n_t0 = n_t;
@@ -291,7 +290,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 // =================== role "tiles": the warp serves one agent at a time ====
                 // Lane i keeps the integer summary of agent i; the look-ups run thread-per-agent afterwards.
                 const int parity = warp - 2;
-                const int32_t pw = active ? ld_state<WORLD>(p.b.pos + a) : 0;
+                int32_t pw = active ? ld_state<WORLD>(p.b.pos + a) : 0;
+                if (do_actions && active) pw = moved_pos(pw, __ldg(act + a));
                 int my_others = 0, my_objs = 0, my_res = 0, my_d2 = 0;
                 float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)(c_begin + parity) * map_elems;
 #pragma unroll 1
@@ -299,14 +299,19 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                     const int32_t pwi = __shfl_sync(FULL, pw, i);
                     const int cxi = pos_x(pwi), cyi = pos_y(pwi);
                     const int eb = __shfl_sync(FULL, town_ebeg, i), ee = __shfl_sync(FULL, town_eend, i);
-                    const int self_e = eb + (c_begin + i - __shfl_sync(FULL, town_abeg, i));
+                    const int ab = __shfl_sync(FULL, town_abeg, i);
+                    const int self_e = eb + (c_begin + i - ab);
+                    // entity word e of the served town; the first (town's agent count) words are its agents
+                    const int n_town_agents = do_actions ? __shfl_sync(FULL, town_aend, i) - ab : 0;
+                    auto ent_word = [&](int e) -> uint32_t {
+                        if (e >= ee) return 0u;
+                        const uint32_t w = ld_state<WORLD>(p.b.ent + e);
+                        return (do_actions && e - eb < n_town_agents) ? moved_ent(w, __ldg(act + ab + (e - eb))) : w;
+                    };
                     if (eb != cached_eb) {  // the warp moved on to the next town: fetch its entity words
                         cached_eb = eb;
 #pragma unroll
-                        for (int k = 0; k < kEntCache; ++k) {
-                            const int e = eb + 32 * k + lane;
-                            wc[k] = e < ee ? ld_state<WORLD>(p.b.ent + e) : 0u;
-                        }
+                        for (int k = 0; k < kEntCache; ++k) wc[k] = ent_word(eb + 32 * k + lane);
                     }
                     // ---- template tile: 16-byte vectorised coalesced stores -------------
                     const int map_mis = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
@@ -399,8 +404,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                                 serve(wc[3], eb + 96 + lane, true);
 #pragma unroll 1
                                 for (int e0 = eb + 32 * kEntCache; e0 < ee; e0 += 32) {
-                                    const int e = e0 + lane;
-                                    serve(e < ee ? ld_state<WORLD>(p.b.ent + e) : 0u, e, true);
+                                    serve(ent_word(e0 + lane), e0 + lane, true);
                                 }
                             }
                         }

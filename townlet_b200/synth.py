@@ -20,7 +20,7 @@ import numpy as np
 
 from . import capi
 from .hashing import id_embedding_words, last_action_hash
-from .params import LTYPE_CODE, PROFILE_CODE, SHIFT_CODE, ObsSpec
+from .params import LTYPE_CODE, PROFILE_CODE, SHIFT_CODE, ObsSpec, pack_actions
 from .soa import BatchLayout, TownBatch, pack_entity, pack_pos
 
 OBJECT_TYPES = ("fridge", "stove", "bed", "shower")
@@ -277,3 +277,16 @@ def tile_batch(base: TownBatch, repeats: int) -> TownBatch:
         else:
             dst[...] = np.tile(src, (repeats,) + (1,) * (src.ndim - 1))
     return out
+
+
+def random_actions(batch: TownBatch, n_ticks: int, seed: int) -> np.ndarray:
+    """Seeded action words: moves anywhere on the grid, moves without a position, waits, idle agents."""
+    rng = np.random.default_rng(seed)
+    n = batch.n_agents
+    kind = rng.choice([0, 1, 1, 1, 2, 3, 7], size=(n_ticks, n))
+    has_pos = (kind == 1) & (rng.random((n_ticks, n)) < 0.9)
+    x = rng.integers(0, batch.grid_w, size=(n_ticks, n))
+    y = rng.integers(0, batch.grid_h, size=(n_ticks, n))
+    success = rng.integers(0, 2, size=(n_ticks, n))
+    duration = rng.integers(0, 64, size=(n_ticks, n))
+    return pack_actions(kind, success, has_pos, x, y, duration)
