@@ -104,6 +104,9 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     uint32_t wc[kEntCache] = {0u, 0u, 0u, 0u};
     int pass = 0;
     int slot = 0, town_abeg = 0, town_aend = 0, town_ebeg = 0, town_eend = 0, kpi_steps = 32;
+    // social role: rows and edge counts of the coming pass were requested at the end of the previous one
+    bool rows_in_flight = false;
+    int pre_n_riv = 0, pre_n_t = 0;
     __syncthreads();
 
 #pragma unroll 1
@@ -216,37 +219,41 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 uint64_t* s_remb = s_temb + chunk_cap * K * EW;
                 const float* s_elut = reinterpret_cast<const float*>(s_remb + chunk_cap * K * EW);  // byte / 255.0f
                 const bool stage_ties = o.social_base >= 0 || do_social_decay;
+                const bool stage_any = do_obs || do_social_decay;
                 const size_t r0 = (size_t)c_begin * K;
                 const int n_rows = c_n * K;
                 const int rbase = lane * K;  // row of this agent inside the staged block
-                int n_riv = 0, n_t = 0;
-                if (active && (do_obs || do_social_decay)) {
-                    n_riv = min((int)ld_state<WORLD>(p.b.riv_count + a), K);  // counts are clamped to the row stride
-                    n_t = min((int)ld_state<WORLD>(p.b.tie_count + a), K);
-                }
-                if (do_obs || do_social_decay) {
+                // Asynchronous global -> shared copies of the relation rows (and register loads of the edge
+                // counts) of the pass that starts at agent `cb`: every copy is in flight at once.
+                auto prefetch_rows = [&](int cb, int cn) {
+                    const size_t q0 = (size_t)cb * K;
+                    const int nr = cn * K;
 #pragma unroll 2
-                    for (int i = lane; i < n_rows; i += 32) {
-                        const double v_score = ld_state<WORLD>(p.b.riv_score + r0 + i);
+                    for (int i = lane; i < nr; i += 32) {
+                        cp_async8(s_score + i, p.b.riv_score + q0 + i);
                         if (stage_ties) {
-                            const double v_t = ld_state<WORLD>(p.b.tie_trust + r0 + i), v_f = ld_state<WORLD>(p.b.tie_fam + r0 + i);
-                            const double v_r = ld_state<WORLD>(p.b.tie_riv + r0 + i);
-                            s_trust[i] = v_t;
-                            s_fam[i] = v_f;
-                            s_riv[i] = v_r;
+                            cp_async8(s_trust + i, p.b.tie_trust + q0 + i);
+                            cp_async8(s_fam + i, p.b.tie_fam + q0 + i);
+                            cp_async8(s_riv + i, p.b.tie_riv + q0 + i);
                         }
-                        s_score[i] = v_score;
                     }
                     if (stage_ties) {
 #pragma unroll 2
-                        for (int i = lane; i < n_rows * EW; i += 32) {
-                            const uint64_t v_t = ld_state<WORLD>(p.b.tie_embed + r0 * EW + i), v_r = ld_state<WORLD>(p.b.riv_embed + r0 * EW + i);
-                            s_temb[i] = v_t;
-                            s_remb[i] = v_r;
+                        for (int i = lane; i < nr * EW; i += 32) {
+                            cp_async8(s_temb + i, p.b.tie_embed + q0 * EW + i);
+                            cp_async8(s_remb + i, p.b.riv_embed + q0 * EW + i);
                         }
                     }
-                }
+                    pre_n_riv = pre_n_t = 0;
+                    if (lane < cn) {  // counts are clamped to the row stride
+                        pre_n_riv = min((int)ld_state<WORLD>(p.b.riv_count + cb + lane), K);
+                        pre_n_t = min((int)ld_state<WORLD>(p.b.tie_count + cb + lane), K);
+                    }
+                };
+                if (stage_any && !rows_in_flight) prefetch_rows(c_begin, c_n);  // first pass of the launch
+                cp_async_wait_all();
                 __syncwarp();
+                int n_riv = pre_n_riv, n_t = pre_n_t;
                 if (do_social_decay) {
                     // ledger decay in the staged rows, then the block goes back with coalesced stores
                     const int n_riv0 = n_riv, n_t0 = n_t;
@@ -284,6 +291,20 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                     if (p.oo.summary) {
                         int* srow_i = p.oo.summary + (size_t)it * p.oo.summary_tick_stride + (size_t)a * TL_N_SUMMARY;
                         *reinterpret_cast<int4*>(srow_i + 4) = make_int4(filled, source, 0, 0);
+                    }
+                }
+                // The rows of the NEXT pass (next block of this tick, or the first block of the next tick) start
+                // their trip now and land while this warp waits at the barrier and sweeps: they are re-read from
+                // global memory every pass, only earlier.
+                rows_in_flight = false;
+                if (stage_any) {
+                    int ncb = -1;
+                    if (chunk + 1 < n_chunks) ncb = c_begin + chunk_cap;
+                    else if (it + 1 < p.n_ticks) ncb = a_begin;
+                    if (ncb >= 0) {
+                        __syncwarp();  // every lane is done with the staged rows (and their write-back)
+                        prefetch_rows(ncb, min(chunk_cap, a_end - ncb));
+                        rows_in_flight = true;
                     }
                 }
             } else if (do_obs) {

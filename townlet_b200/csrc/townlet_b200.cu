@@ -84,6 +84,13 @@ __device__ __forceinline__ T ld_state(const T* ptr) {
     else return __ldg(ptr);
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS) and the wait for all copies of this thread
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ int pos_x(int32_t p) { return (int)(int16_t)(p & 0xffff); }
 __device__ __forceinline__ int pos_y(int32_t p) { return (int)(int16_t)((uint32_t)p >> 16); }
 
