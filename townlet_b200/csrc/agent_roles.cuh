@@ -50,6 +50,106 @@ __device__ __forceinline__ uint32_t moved_ent(uint32_t ew, uint32_t act_w) {
     return ew;
 }
 
+// The scalar inputs of ONE agent for one tick (AgentSnapshot fields, world/agents/snapshot.py:19-44, the
+// employment context and the reward engine's per-agent state).
+struct StateIn {
+    double need[3];
+    double wallet, attendance, wages_withheld;
+    RewardIn rin;
+    uint32_t fl;
+    int episode_tick, lateness, duration, slot_idx;
+    float last_hash;
+    int32_t pw;
+};
+
+// Staging rows of the state role in shared memory: kStateF64 rows of 32 doubles, then kStateI32 rows of
+// 32 four-byte values (lane = agent of the pass).
+constexpr int kStateF64 = 12, kStateI32 = 8;
+constexpr int kStateStageBytes = 32 * (8 * kStateF64 + 4 * kStateI32);
+
+// Straight from global memory (the grid form).
+template <bool MUT>
+__device__ __forceinline__ StateIn load_state_in(const KParams& p, int a) {
+    const size_t N = (size_t)p.b.n_agents;
+    StateIn in;
+    in.need[0] = p.b.needs[a];
+    in.need[1] = p.b.needs[N + a];
+    in.need[2] = p.b.needs[2 * N + a];
+    in.fl = p.b.flags[a];
+    in.episode_tick = p.b.episode_tick[a];
+    in.rin = load_reward_in(p, a);
+    in.wallet = __ldg(p.b.wallet + a);
+    in.lateness = __ldg(p.b.lateness + a);
+    in.attendance = __ldg(p.b.attendance + a);
+    in.wages_withheld = in.rin.wages_withheld;
+    in.duration = ld_state<MUT>(p.b.last_action_duration + a);
+    in.slot_idx = __ldg(p.b.slot + a);
+    in.last_hash = ld_state<MUT>(p.b.last_action_hash + a);
+    in.pw = ld_state<MUT>(p.b.pos + a);
+    return in;
+}
+
+// Asynchronous global -> shared copies of the same inputs for agent `a` into column `lane` of the
+// staging rows; read them back with staged_state_in after cp_async_wait_all() (same thread).
+__device__ __forceinline__ void prefetch_state_in(const KParams& p, unsigned char* stage, int a, int lane) {
+    const size_t N = (size_t)p.b.n_agents;
+    double* d = reinterpret_cast<double*>(stage) + lane;
+    int32_t* w = reinterpret_cast<int32_t*>(stage + 32 * 8 * kStateF64) + lane;
+    cp_async8(d + 0 * 32, p.b.needs + a);
+    cp_async8(d + 1 * 32, p.b.needs + N + a);
+    cp_async8(d + 2 * 32, p.b.needs + 2 * N + a);
+    cp_async8(d + 3 * 32, p.b.wallet + a);
+    cp_async8(d + 4 * 32, p.b.attendance + a);
+    cp_async8(d + 5 * 32, p.b.wages_withheld + a);
+    cp_async8(d + 6 * 32, p.b.wages_paid + a);
+    cp_async8(d + 7 * 32, p.b.punctuality + a);
+    cp_async8(d + 8 * 32, p.b.episode_total + a);
+    if (p.b.social_in) {
+        cp_async8(d + 9 * 32, p.b.social_in + a);
+        cp_async8(d + 10 * 32, p.b.social_in + N + a);
+        cp_async8(d + 11 * 32, p.b.social_in + 2 * N + a);
+    }
+    cp_async4(w + 0 * 32, p.b.flags + a);
+    cp_async4(w + 1 * 32, p.b.episode_tick + a);
+    cp_async4(w + 2 * 32, p.b.term_block_tick + a);
+    cp_async4(w + 3 * 32, p.b.lateness + a);
+    cp_async4(w + 4 * 32, p.b.last_action_duration + a);
+    cp_async4(w + 5 * 32, p.b.slot + a);
+    cp_async4(w + 6 * 32, p.b.last_action_hash + a);
+    cp_async4(w + 7 * 32, p.b.pos + a);
+}
+
+__device__ __forceinline__ StateIn staged_state_in(const KParams& p, const unsigned char* stage, int lane) {
+    const double* d = reinterpret_cast<const double*>(stage) + lane;
+    const int32_t* w = reinterpret_cast<const int32_t*>(stage + 32 * 8 * kStateF64) + lane;
+    StateIn in;
+    in.need[0] = d[0 * 32];
+    in.need[1] = d[1 * 32];
+    in.need[2] = d[2 * 32];
+    in.wallet = d[3 * 32];
+    in.attendance = d[4 * 32];
+    in.wages_withheld = d[5 * 32];
+    in.rin.wages_withheld = in.wages_withheld;
+    in.rin.wages_paid = d[6 * 32];
+    in.rin.punctuality = d[7 * 32];
+    in.rin.episode_total = d[8 * 32];
+    in.rin.sb = in.rin.sp = in.rin.sa = 0.0;
+    if (p.b.social_in) {
+        in.rin.sb = d[9 * 32];
+        in.rin.sp = d[10 * 32];
+        in.rin.sa = d[11 * 32];
+    }
+    in.fl = (uint32_t)w[0 * 32];
+    in.episode_tick = w[1 * 32];
+    in.rin.block = w[2 * 32];
+    in.lateness = w[3 * 32];
+    in.duration = w[4 * 32];
+    in.slot_idx = w[5 * 32];
+    in.last_hash = __int_as_float(w[6 * 32]);
+    in.pw = w[7 * 32];
+    return in;
+}
+
 // Role "state" for ONE agent: float64 need decay (world/grid.py:1439-1455), faint predicate
 // (lifecycle/manager.py:39-45), episode tick (world/core/context.py:283-289), reward with guardrails
 // (rewards/engine.py:71-172) and, when `f` is not null, the scalar features, path hint, landmarks and
@@ -58,8 +158,8 @@ __device__ __forceinline__ uint32_t moved_ent(uint32_t ew, uint32_t act_w) {
 // are read with plain loads; otherwise through the read-only path.
 template <bool MUT>
 __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a, int tick, int town_abeg, int town_aend,
-                                                 int town_ebeg, int town_eend, uint32_t act_w, float* f,
-                                                 StateRoleOut& out) {
+                                                 int town_ebeg, int town_eend, uint32_t act_w, const StateIn& in,
+                                                 float* f, StateRoleOut& out) {
     const TlObsParams& o = p.obs;
     const int N = p.b.n_agents;
     const bool do_decay = p.phases & TL_PHASE_DECAY;
@@ -72,31 +172,19 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
     double& kpi_wallet = out.kpi_wallet;
     int& kpi_late = out.kpi_late;
     bool& terminated = out.terminated;
-    // the agent's scalar inputs are loaded up front so the loads overlap
-    double need[3];
-    need[0] = p.b.needs[a];
-    need[1] = p.b.needs[(size_t)N + a];
-    need[2] = p.b.needs[2 * (size_t)N + a];
-    uint32_t fl = p.b.flags[a];
-    int episode_tick = p.b.episode_tick[a];
-    RewardIn rin;
-    if (do_reward) rin = load_reward_in(p, a);
-    const double wallet = __ldg(p.b.wallet + a);
-    const int lateness = __ldg(p.b.lateness + a);
+    double need[3] = {in.need[0], in.need[1], in.need[2]};
+    uint32_t fl = in.fl;
+    int episode_tick = in.episode_tick;
+    const RewardIn& rin = in.rin;
+    const double wallet = in.wallet;
+    const int lateness = in.lateness;
     kpi_wallet = wallet;
     kpi_late = lateness;
-    double attendance = 0.0, wages_withheld = 0.0;
-    int duration = 0, slot_idx = 0;
-    float last_hash = 0.0f;
-    int32_t pw = 0;
-    if (do_obs) {
-        attendance = __ldg(p.b.attendance + a);
-        wages_withheld = __ldg(p.b.wages_withheld + a);
-        duration = ld_state<MUT>(p.b.last_action_duration + a);
-        slot_idx = __ldg(p.b.slot + a);
-        last_hash = ld_state<MUT>(p.b.last_action_hash + a);
-        pw = ld_state<MUT>(p.b.pos + a);
-    }
+    const double attendance = in.attendance, wages_withheld = in.wages_withheld;
+    int duration = in.duration;
+    const int slot_idx = in.slot_idx;
+    float last_hash = in.last_hash;
+    int32_t pw = in.pw;
     if (MUT && TL_ACT_KIND(act_w) != TL_ACT_NONE) {
         // TL_PHASE_ACTIONS, applied by the agent's own thread (the tiles role derives the same positions from
         // the action words, so no barrier is needed between this write-back and its reads)

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
                     if (active)
                         state_role_agent<true>(p, it, a, tm.tick, tm.agent_begin, tm.agent_end, tm.ent_begin, tm.ent_end,
                                          0u /* actions were applied before the grid was staged */,
-                                         do_obs ? feat_s0 + lane * F : nullptr, so);
+                                         load_state_in<true>(p, a), do_obs ? feat_s0 + lane * F : nullptr, so);
                     // ---- per-town KPIs: segmented warp-shuffle reduction ------------
                     if (do_state && p.ro.kpi) {
                         const int seg = active ? slot : -1 - lane;  // inactive lanes are their own segment

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     int pass = 0;
     int slot = 0, town_abeg = 0, town_aend = 0, town_ebeg = 0, town_eend = 0, kpi_steps = 32;
     // social role: rows and edge counts of the coming pass were requested at the end of the previous one
-    bool rows_in_flight = false;
+    bool rows_in_flight = false, state_in_flight = false;
     int pre_n_riv = 0, pre_n_t = 0;
     __syncthreads();
 
@@ -159,10 +159,15 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
             if (warp == 0) {
                 // =================== role "state": one thread per agent ==================
                 const int tick = __shfl_sync(FULL, my_tick, slot);
+                // the inputs of this pass were requested at the end of the previous one (same lane = same column)
+                unsigned char* s_state = smem + p.off_state;
+                if (!state_in_flight && active) prefetch_state_in(p, s_state, a, lane);
+                cp_async_wait_all();
                 StateRoleOut so;
                 if (active)
                     state_role_agent<WORLD>(p, it, a, tick, town_abeg, town_aend, town_ebeg, town_eend,
-                                            do_actions ? __ldg(act + a) : 0u, do_obs ? feat_s0 + lane * F : nullptr, so);
+                                            do_actions ? __ldg(act + a) : 0u, staged_state_in(p, s_state, lane),
+                                            do_obs ? feat_s0 + lane * F : nullptr, so);
                 const double need0 = so.need0, reward_total = so.reward_total, kpi_wallet = so.kpi_wallet;
                 const bool terminated = so.terminated;
                 const int kpi_late = so.kpi_late;
@@ -203,6 +208,18 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                         k.starving += v_c & 1023;
                         k.term += (v_c >> 10) & 1023;
                         k.count += v_c >> 20;
+                    }
+                }
+                // The inputs of the NEXT pass start their trip now, after this pass's stores to the same
+                // arrays; they are re-read from global memory every pass, only earlier.
+                state_in_flight = false;
+                {
+                    int ncb = -1;
+                    if (chunk + 1 < n_chunks) ncb = c_begin + chunk_cap;
+                    else if (it + 1 < p.n_ticks) ncb = a_begin;
+                    if (ncb >= 0) {
+                        if (lane < min(chunk_cap, a_end - ncb)) prefetch_state_in(p, s_state, ncb + lane, lane);
+                        state_in_flight = true;
                     }
                 }
             } else if (warp == 1) {

@@ -72,6 +72,7 @@ struct KParams {
     int32_t chunk;         // entity form: agents per phase-A pass (<= 32)
     int32_t mode;          // 0 entity-list form with role-parallel warps, 1 dense shared-memory grid form
     int32_t off_social;    // role form: staged relation rows of a pass (4 x double + 2 x embed words per edge)
+    int32_t off_state;     // role form: staged per-agent inputs of the state role (kStateStageBytes)
     int32_t tmpl_mask;     // entity form: bit m set = a tile template for 16-byte misalignment m floats exists
     int32_t tmpl_off[4];   // entity form: float offset of template m inside the template area
 };
@@ -87,6 +88,10 @@ __device__ __forceinline__ T ld_state(const T* ptr) {
 // 8-byte asynchronous global -> shared copy (LDGSTS) and the wait for all copies of this thread
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
@@ -442,6 +447,8 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         }
         kp.off_meta = off;
         off += round_up((int)sizeof(KpiAcc) * tpc, 16);
+        kp.off_state = off;
+        off += kStateStageBytes;
         kp.off_social = off;
         if (do_obs || (phases & TL_PHASE_SOCIAL_DECAY)) off += chunk * b->max_edges * (4 * 8 + 2 * 8 * b->embed_words) + 256 * 4;
         kp.smem_bytes = off;
