@@ -271,11 +271,13 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
         const int e_obj = town_ebeg + (town_aend - town_abeg);
         int hd2 = -1, hdx = 0, hdy = 0;
         if (!all_types) {
-#pragma unroll 1
+            // object, nearest-of-type candidate, landmark type of the path hint: one masked compare
+            const uint32_t lm_mask = (3u << 20) | (7u << 22) | (1u << 29);
+            const uint32_t lm_want = (TL_KIND_OBJECT << 20) | ((uint32_t)o.path_hint_ltype << 22) | (1u << 29);
+#pragma unroll 2
             for (int e = e_obj; e < town_eend; ++e) {
                 const uint32_t w = ld_state<MUT>(p.b.ent + e);
-                if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w) || (int)TL_ENT_LTYPE(w) != o.path_hint_ltype)
-                    continue;
+                if ((w & lm_mask) != lm_want) continue;
                 const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
                 const int d2 = dx * dx + dy * dy;
                 if (hd2 < 0 || d2 < hd2) {

@@ -19,6 +19,14 @@
 // One block barrier per pass hands the double-buffered feature rows to a
 // coalesced 16-byte sweep done by all four warps.
 
+// -DTL_ROLE_TIMING: two CTAs print the cycles each role spends per tick in its role body and at the pass
+// barrier + sweep (scripts/role_timing.sh; never part of the shipped library)
+#ifdef TL_ROLE_TIMING
+#define TL_TIMING(...) __VA_ARGS__
+#else
+#define TL_TIMING(...)
+#endif
+
 #ifndef TL_TILE_WARPS
 #define TL_TILE_WARPS 2
 #endif
@@ -109,6 +117,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     int pre_n_riv = 0, pre_n_t = 0;
     __syncthreads();
 
+    TL_TIMING(long long t_role = 0, t_rest = 0; const long long t_begin = clock64();)
 #pragma unroll 1
     for (int it = 0; it < p.n_ticks; ++it) {
         cached_eb = -1;  // every tick re-reads the entity words of its towns
@@ -139,6 +148,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
             // double buffered rows; each mirrors the 16-byte misalignment of the global rows
             float* feat_s0 = s_feat + (pass & 1) * feat_buf_floats + feat_mis;
 
+            TL_TIMING(const long long tt0 = clock64();)
             const bool active = lane < c_n;
             const int a = c_begin + (active ? lane : 0);
             // town of this lane's agent; with a single pass per tick the answer is the same every tick
@@ -482,6 +492,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                     }
                 }
             }
+            TL_TIMING(const long long tt1 = clock64();)
             if (!do_obs) continue;  // CTA-uniform
             __syncthreads();  // the rows of this pass are complete
             {  // feature rows of the whole pass: one coalesced 16-byte sweep by all four warps
@@ -496,6 +507,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 const int tail0 = head + (nvec << 2);
                 if (tid < total - tail0) feat_g0[tail0 + tid] = feat_s0[tail0 + tid];
             }
+            TL_TIMING(t_role += tt1 - tt0; t_rest += clock64() - tt1;)
             // no second barrier: the next pass fills the other buffer, and the barrier of
             // that pass orders this sweep before the buffer is written again
         }
@@ -518,4 +530,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
             __syncwarp();
         }
     }
+    TL_TIMING(if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && lane == 0 && p.n_ticks > 1)
+                  printf("TL_ROLE_TIMING cta %d warp %d (%s) role %lld barrier+sweep %lld total %lld cycles per tick\n", blockIdx.x, warp,
+                         warp == 0 ? "state" : (warp == 1 ? "social" : "tiles"), t_role / p.n_ticks, t_rest / p.n_ticks,
+                         (clock64() - t_begin) / p.n_ticks);)
 }
