@@ -392,16 +392,35 @@ __device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, i
         const int n_friends = min(n_rel, o.top_friends);
         const int n_rivals = min(o.top_rivals, n_rel - n_friends);
         filled = n_friends + n_rivals;
+        if (from_ties) {
 #pragma unroll 1
-        for (int s = 0; s < filled; ++s) {
-            const bool friend_pass = s < n_friends;
+            for (int s = 0; s < n_friends; ++s) {  // friends by trust + familiarity
+                int best = -1;
+                double bk = 0.0;
+#pragma unroll 1
+                for (int j = 0; j < n_rel; ++j) {
+                    const double key = kt[j] + kf[j];
+                    if (!((chosen >> j) & 1u) && (best < 0 || key > bk)) {
+                        best = j;
+                        bk = key;
+                    }
+                }
+                chosen |= 1u << best;
+                sel |= (unsigned)best << (4 * s);
+            }
+        } else {  // every friend key is 0.0: the first entries in order
+#pragma unroll 1
+            for (int s = 0; s < n_friends; ++s) sel |= (unsigned)s << (4 * s);
+            chosen = (1u << n_friends) - 1u;
+        }
+#pragma unroll 1
+        for (int s = n_friends; s < filled; ++s) {  // rivals by rivalry among the rest
             int best = -1;
             double bk = 0.0;
 #pragma unroll 1
             for (int j = 0; j < n_rel; ++j) {
-                if ((chosen >> j) & 1u) continue;
-                const double key = friend_pass ? (from_ties ? kt[j] + kf[j] : 0.0) : kr[j];
-                if (best < 0 || key > bk) {
+                const double key = kr[j];
+                if (!((chosen >> j) & 1u) && (best < 0 || key > bk)) {
                     best = j;
                     bk = key;
                 }
@@ -414,8 +433,13 @@ __device__ __forceinline__ void social_role_agent(const KParams& p, int n_riv, i
         for (int s = 0; s < total_slots; ++s) {
             float* dst = srow + s * slot_dim;
             if (s >= filled) {  // _empty_relationship_entry, social.py:226-233
+                if (o.embed_dim == 8) {
+#pragma unroll
+                    for (int d = 0; d < 11; ++d) dst[d] = 0.0f;
+                } else {
 #pragma unroll 1
-                for (int d = 0; d < slot_dim; ++d) dst[d] = 0.0f;
+                    for (int d = 0; d < slot_dim; ++d) dst[d] = 0.0f;
+                }
                 continue;
             }
             const int j = (sel >> (4 * s)) & 15;

@@ -272,15 +272,15 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                         }
                     }
                     pre_n_riv = pre_n_t = 0;
-                    if (lane < cn) {  // counts are clamped to the row stride
-                        pre_n_riv = min((int)ld_state<WORLD>(p.b.riv_count + cb + lane), K);
-                        pre_n_t = min((int)ld_state<WORLD>(p.b.tie_count + cb + lane), K);
+                    if (lane < cn) {  // raw counts: nothing may wait for these loads before the next pass uses them
+                        pre_n_riv = ld_state<WORLD>(p.b.riv_count + cb + lane);
+                        pre_n_t = ld_state<WORLD>(p.b.tie_count + cb + lane);
                     }
                 };
                 if (stage_any && !rows_in_flight) prefetch_rows(c_begin, c_n);  // first pass of the launch
                 cp_async_wait_all();
                 __syncwarp();
-                int n_riv = pre_n_riv, n_t = pre_n_t;
+                int n_riv = min(pre_n_riv, K), n_t = min(pre_n_t, K);  // counts are clamped to the row stride
                 if (do_social_decay) {
                     // ledger decay in the staged rows, then the block goes back with coalesced stores
                     const int n_riv0 = n_riv, n_t0 = n_t;
