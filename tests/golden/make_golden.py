@@ -811,6 +811,52 @@ def world_dynamics_cases():
         print(f"  world/{name}: {n_towns} towns x {agents} agents, {n_ticks} ticks; evicted rivalry/ties {evicted}")
 
 
+def replay_case():
+    """frames_to_replay_sample + build_batch (policy/replay.py:550-636, 245-276) on random per-agent frames.
+
+    The frames carry what TrajectoryService._frames_from_envelope (policy/trajectory_service.py:91-140) puts in them:
+    nested-list map / features, action_id, log_prob, value_pred, rewards / dones lists.
+    """
+    from townlet.policy.replay import build_batch, frames_to_replay_sample
+
+    rng = np.random.default_rng(99)
+    steps, agents, shape, feat = 6, 5, (4, 11, 11), 81
+    tm = {
+        "map": (rng.random((steps, agents, *shape)) < 0.05).astype(np.float32),
+        "features": rng.normal(size=(steps, agents, feat)).astype(np.float32),
+        "actions": rng.integers(0, 9, size=(steps, agents)).astype(np.int64),
+        "log_probs": rng.normal(-2.0, 0.3, size=(steps, agents)).astype(np.float32),
+        "values": rng.normal(0.0, 0.5, size=(steps + 1, agents)).astype(np.float32),
+        "rewards": rng.uniform(-0.2, 0.2, size=(steps, agents)).astype(np.float32),
+        "dones": (rng.random((steps, agents)) < 0.2).astype(np.float32),
+    }
+    samples = []
+    for a in range(agents):
+        frames = [
+            {
+                "map": tm["map"][t, a].tolist(),
+                "features": tm["features"][t, a].tolist(),
+                "action_id": int(tm["actions"][t, a]),
+                "log_prob": float(tm["log_probs"][t, a]),
+                "value_pred": float(tm["values"][t, a]),
+                "rewards": [float(tm["rewards"][t, a])],
+                "dones": [bool(tm["dones"][t, a])],
+                "metadata": {},
+            }
+            for t in range(steps)
+        ]
+        samples.append(frames_to_replay_sample(frames))
+    batch = build_batch(samples)
+    (GOLDEN_DIR / "replay").mkdir(exist_ok=True)
+    np.savez_compressed(
+        GOLDEN_DIR / "replay" / "ref_replay.npz",
+        **{f"in_{k}": v for k, v in tm.items()},
+        maps=batch.maps, features=batch.features, actions=batch.actions, old_log_probs=batch.old_log_probs,
+        value_preds=batch.value_preds, rewards=batch.rewards, dones=batch.dones,
+    )
+    print("  replay/ref_replay: frames_to_replay_sample + build_batch on 5 agents x 6 steps")
+
+
 def gae_case():
     """compute_gae (policy/backends/pytorch/ppo_utils.py:19-67) on random float32 rollouts, both value layouts."""
     import torch
@@ -835,7 +881,7 @@ def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
     only = os.environ.get("TL_GOLDEN_ONLY")
     if only:
-        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases}[only]()
+        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()
@@ -846,6 +892,7 @@ def main():
     reward_cases()
     snapshot_cases()
     world_dynamics_cases()
+    replay_case()
     gae_case()
     shutil.rmtree(WORK, ignore_errors=True)
 

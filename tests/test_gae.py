@@ -105,3 +105,31 @@ def test_graphed_rollout_equals_eager_rollout() -> None:
         assert torch.allclose(a.values, b.values)
     assert torch.equal(eager_dev.arena, graph_dev.arena)
     assert capi.load_library().tl_launch_count() > 0
+
+
+def test_rollout_replay_batch_matches_reference_frames_to_replay_sample() -> None:
+    """Time-major rollout tensors -> the reference's ReplayBatch arrays (policy/replay.py:550-636, 245-276).
+
+    CPU tensors suffice: the export is a transpose of the rollout buffers, whatever device they live on.
+    """
+    import torch
+
+    from townlet_b200.rollout import Rollout
+
+    d = np.load(Path(__file__).resolve().parent / "golden" / "replay" / "ref_replay.npz")
+    t = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("in_")}
+    steps, agents = t["rewards"].shape
+    rollout = Rollout(
+        map=t["map"], features=t["features"], rewards=t["rewards"], dones=t["dones"], values=t["values"],
+        actions=t["actions"], log_probs=t["log_probs"], advantages=torch.zeros(steps, agents),
+        returns=torch.zeros(steps, agents), kpi=torch.zeros(steps, 1, 8),
+    )
+    got = rollout.replay_batch(bootstrap="repeat")
+    for key in ("maps", "features", "actions", "old_log_probs", "value_preds", "rewards", "dones"):
+        assert got[key].dtype == d[key].dtype, key
+        assert np.array_equal(got[key], d[key]), key
+    # the device rollout also carries the real bootstrap value of the final observation
+    boot = rollout.replay_batch(agents=slice(1, 4))
+    assert boot["value_preds"].shape == (3, steps + 1)
+    assert np.array_equal(boot["value_preds"][:, -1], d["in_values"][-1, 1:4])
+    assert np.array_equal(boot["maps"], d["maps"][1:4])

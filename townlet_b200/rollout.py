@@ -79,6 +79,39 @@ class Rollout:
     returns: torch.Tensor
     kpi: torch.Tensor  # [T, towns, 8]
 
+    def replay_batch(self, agents: slice | None = None, bootstrap: str = "value") -> dict[str, "np.ndarray"]:
+        """The arrays of the reference's ``ReplayBatch`` (policy/replay.py:161-243), one sample per agent.
+
+        What ``frames_to_replay_sample`` (policy/replay.py:550-636) builds per agent from the envelope's nested
+        lists and ``build_batch`` (replay.py:245-276) stacks — ``maps [B, T, C, W, W]``, ``features [B, T, F]``,
+        ``actions [B, T]`` int64, ``old_log_probs`` / ``rewards [B, T]`` float32, ``dones [B, T]`` bool,
+        ``value_preds [B, T + 1]`` — taken straight from the time-major device rollout (one transpose, one D2H).
+        ``bootstrap="value"`` keeps the policy's value of the final observation in the last ``value_preds`` column;
+        ``"repeat"`` repeats the last step's value as the reference does (replay.py:603-607).
+        """
+        import numpy as np
+
+        sel = agents if agents is not None else slice(None)
+
+        def agent_major(t: torch.Tensor) -> "np.ndarray":
+            return t[:, sel].transpose(0, 1).contiguous().cpu().numpy()
+
+        values = self.values.float()
+        steps = self.rewards.shape[0]
+        if bootstrap == "repeat" or values.shape[0] == steps:
+            values = torch.cat([values[:steps], values[steps - 1 : steps]], dim=0)
+        elif bootstrap != "value":
+            raise ValueError("bootstrap must be 'value' or 'repeat'")
+        return {
+            "maps": agent_major(self.map.float()),
+            "features": agent_major(self.features.float()),
+            "actions": agent_major(self.actions.long()).astype(np.int64),
+            "old_log_probs": agent_major(self.log_probs.float()),
+            "value_preds": agent_major(values),
+            "rewards": agent_major(self.rewards.float()),
+            "dones": agent_major(self.dones) != 0,
+        }
+
 
 @dataclass
 class GraphedRollout:
