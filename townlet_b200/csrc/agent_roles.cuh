@@ -274,17 +274,16 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
             // object, nearest-of-type candidate, landmark type of the path hint: one masked compare
             const uint32_t lm_mask = (3u << 20) | (7u << 22) | (1u << 29);
             const uint32_t lm_want = (TL_KIND_OBJECT << 20) | ((uint32_t)o.path_hint_ltype << 22) | (1u << 29);
-#pragma unroll 2
+            // branch-free body: the lanes of a warp scan different towns, so a `continue` would diverge every step
+#pragma unroll 4
             for (int e = e_obj; e < town_eend; ++e) {
                 const uint32_t w = ld_state<MUT>(p.b.ent + e);
-                if ((w & lm_mask) != lm_want) continue;
                 const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
                 const int d2 = dx * dx + dy * dy;
-                if (hd2 < 0 || d2 < hd2) {
-                    hd2 = d2;
-                    hdx = dx;
-                    hdy = dy;
-                }
+                const bool better = (w & lm_mask) == lm_want && (hd2 < 0 || d2 < hd2);
+                hd2 = better ? d2 : hd2;
+                hdx = better ? dx : hdx;
+                hdy = better ? dy : hdy;
             }
         } else {
             int best_d2[5] = {-1, -1, -1, -1, -1};
