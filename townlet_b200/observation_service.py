@@ -53,12 +53,26 @@ class B200ObservationService:
         if self._max_edges > capi.TL_MAX_EDGES:
             raise ValueError(f"max_edges above {capi.TL_MAX_EDGES} is not supported")
         self._engine = HostEngine(self.spec, None, device)
+        # the configuration sections the reference service exposes (service.py:36-38, 62-63); its tests read them
+        self.hybrid_cfg = config.observations_config.hybrid
+        self.compact_cfg = config.observations_config.compact
+        self.social_cfg = config.observations_config.social_snippet
+        self.full_channels = ("self", "agents", "objects", "reservations", "path_dx", "path_dy")
+        self.compact_map_channels = (
+            "self", "agents", "objects", "reservations", *(f"object:{name}" for name in self.spec.object_channels), "walkable",
+        )
         # float64 nearest distance by squared distance, np.hypot as in map.py:95
         radius = self.spec.radius
         self._hypot_by_d2: dict[int, float] = {}
         for dy in range(-radius, radius + 1):
             for dx in range(-radius, radius + 1):
                 self._hypot_by_d2.setdefault(dx * dx + dy * dy, float(np.hypot(dx, dy)))
+
+    def _aggregate_names(self) -> list[str]:
+        """service.py:505-514"""
+        if self.social_cfg.include_aggregates:
+            return ["social_trust_mean", "social_trust_max", "social_rivalry_mean", "social_rivalry_max"]
+        return []
 
     # ---- protocol properties ---------------------------------------------
     @property

