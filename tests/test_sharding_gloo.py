@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from townlet_b200 import capi
 from townlet_b200.params import ObsSpec, RewardSpec
-from townlet_b200.sharding import gather_kpi_rows, reduce_kpi_totals, shard_batch, town_range
+from townlet_b200.sharding import gather_kpi_rows, reduce_kpi_totals, shard_actions, shard_batch, town_range
 from townlet_b200.synth import synth_batch
 
 N_TOWNS = 7
@@ -80,3 +80,25 @@ def test_shards_partition_the_state() -> None:
     assert np.array_equal(np.concatenate([p.ent for p in parts]), full.ent)
     for p in parts:
         p.validate()
+
+
+def test_sharded_world_phases_equal_the_unsharded_run() -> None:
+    """Action words shard with the agents; moves and ledger decay never cross a town, so shards stay independent."""
+    from oracle.oracle import oracle_tick
+    from townlet_b200.params import DynamicsSpec
+    from townlet_b200.synth import random_actions
+
+    obs, rew, dyn = ObsSpec(), RewardSpec(fuse_faint=True), DynamicsSpec()
+    full = synth_batch(N_TOWNS, 32, 6, obs)
+    words = random_actions(full, 4, seed=11)
+    parts = [shard_batch(full, r, 3) for r in range(3)]
+    outs = [
+        oracle_tick(part, obs, rew, capi.TL_PHASE_WORLD, 4, dyn=dyn, actions=np.ascontiguousarray(shard_actions(words, full, r, 3)))
+        for r, part in enumerate(parts)
+    ]
+    ref = oracle_tick(full, obs, rew, capi.TL_PHASE_WORLD, 4, dyn=dyn, actions=words)
+    for key in ("map", "features", "reward", "terminated"):
+        assert np.array_equal(np.concatenate([o[key] for o in outs], axis=1), ref[key], equal_nan=True), key
+    assert np.array_equal(np.concatenate([p.pos for p in parts]), full.pos)
+    assert np.array_equal(np.concatenate([p.riv_score for p in parts]), full.riv_score)
+    assert np.array_equal(np.concatenate([p.tie_count for p in parts]), full.tie_count)

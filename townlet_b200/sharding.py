@@ -10,6 +10,7 @@ on GPUs, gloo in the CPU tests.
 
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -30,6 +31,13 @@ def shard_batch(batch: TownBatch, rank: int, world_size: int) -> TownBatch:
     """The rank's block of towns as its own batch (offsets rebased to zero)."""
     t0, t1 = town_range(batch.n_towns, rank, world_size)
     return batch.slice_towns(t0, t1)
+
+
+def shard_actions(actions: "np.ndarray | torch.Tensor", batch: TownBatch, rank: int, world_size: int):
+    """The rank's columns of action words ``[..., n_agents]`` (agents are town-major, so a shard is a slice)."""
+    t0, t1 = town_range(batch.n_towns, rank, world_size)
+    a0, a1 = int(batch.town_agent_off[t0]), int(batch.town_agent_off[t1])
+    return actions[..., a0:a1]
 
 
 def reduce_kpi_totals(kpi: torch.Tensor, group: dist.ProcessGroup | None = None) -> torch.Tensor:
