@@ -269,3 +269,49 @@ def test_batches_with_empty_towns_and_no_agents() -> None:
     empty = TownBatch(BatchLayout.make(0, 0, 0, 6, 1), 16, 16)
     out = _device_run(empty, obs, rew, capi.TL_PHASE_ALL, 1)
     assert out["map"].shape[1] == 0 and out["reward"].shape[1] == 0
+
+
+@pytest.mark.parametrize("world_phases", [False, True], ids=["hot-path", "world-phases"])
+def test_long_horizon_rollout_matches_oracle(world_phases) -> None:
+    """1 500 ticks in one launch: needs run to zero, agents faint, episode totals reach the caps and the death
+    window opens and closes — every reward, flag and KPI row of every tick against the oracle, observations of the
+    last tick (the map / feature outputs overwrite one slot: tick stride 0) and the final state."""
+    import torch
+
+    from oracle.oracle import oracle_tick
+    from townlet_b200.engine import DeviceTownBatch
+    from townlet_b200.params import DynamicsSpec
+    from townlet_b200.synth import random_actions
+
+    ticks = 1500
+    obs, rew = ObsSpec(), RewardSpec(fuse_faint=True)
+    dyn = DynamicsSpec(rivalry_decay_per_tick=0.0002, tie_rivalry_decay=0.0003) if world_phases else None
+    phases = capi.TL_PHASE_WORLD if world_phases else capi.TL_PHASE_ALL
+    base = synth_batch(6, 48, 8, obs)
+    actions = random_actions(base, ticks, seed=77) if world_phases else None
+    cpu, gpu = base.copy(), base.copy()
+    want = oracle_tick(cpu, obs, rew, phases, ticks, dyn=dyn, actions=actions, want_comps=False)
+
+    dev = DeviceTownBatch(gpu, obs, rew, dyn=dyn)
+    out = dev.alloc_outputs(phases, ticks, summary=False, comps=False)
+    n = gpu.n_agents
+    out.map = torch.empty((1, n, *obs.map_shape), dtype=torch.float32, device=dev.device).expand(ticks, -1, -1, -1, -1)
+    out.features = torch.empty((1, n, obs.n_features), dtype=torch.float32, device=dev.device).expand(ticks, -1, -1)
+    act = torch.from_numpy(actions.view(np.int32)).to(dev.device) if actions is not None else None
+    dev.tick(out, phases, ticks, actions=act)
+    torch.cuda.synchronize()
+    dev.download_state()
+
+    got_reward = out.reward.cpu().numpy()
+    np.testing.assert_allclose(got_reward, want["reward"], rtol=REL_TOL, atol=1e-9)
+    assert np.array_equal(out.terminated.cpu().numpy(), want["terminated"])
+    np.testing.assert_allclose(out.kpi.cpu().numpy(), want["kpi"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(out.map[0].cpu().numpy().view(np.uint32), want["map"][-1].view(np.uint32))
+    assert np.array_equal(out.features[0].cpu().numpy().view(np.uint32), want["features"][-1].view(np.uint32))
+    np.testing.assert_allclose(gpu.needs, cpu.needs, rtol=REL_TOL, atol=1e-15)
+    np.testing.assert_allclose(gpu.episode_total, cpu.episode_total, rtol=REL_TOL, atol=1e-12)
+    assert np.array_equal(gpu.flags, cpu.flags) and np.array_equal(gpu.term_block_tick, cpu.term_block_tick)
+    assert want["terminated"].any() and not want["terminated"].all()  # the horizon crosses the faint threshold
+    if world_phases:
+        for field in ("pos", "ent", "riv_count", "riv_score", "tie_count", "tie_riv"):
+            assert np.array_equal(getattr(gpu, field), getattr(cpu, field)), field
