@@ -45,8 +45,10 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int T = p.b.n_towns;
-    const int t0 = blockIdx.x * p.towns_per_cta;
-    const int n_towns = min(p.towns_per_cta, T - t0);
+    // the first n_big_ctas CTAs own towns_per_cta consecutive towns, the others one fewer
+    const int cta = blockIdx.x;
+    const int t0 = cta * p.towns_per_cta - max(0, cta - p.n_big_ctas);
+    const int n_towns = min(p.towns_per_cta - (cta >= p.n_big_ctas ? 1 : 0), T - t0);
     if (n_towns <= 0) return;
 
     const bool do_decay = p.phases & TL_PHASE_DECAY;

@@ -58,7 +58,8 @@ struct KParams {
     TlDynamicsParams dyn;
     uint32_t phases;
     int32_t n_ticks;
-    int32_t towns_per_cta;
+    int32_t towns_per_cta;  // most towns a CTA owns
+    int32_t n_big_ctas;     // role form: the first n_big_ctas CTAs own towns_per_cta towns, the rest one fewer
     int32_t grid_tiles;    // grid_w * grid_h
     int32_t feat_stride;   // floats per staged feature row (== n_features)
     int32_t map_stride;    // floats per warp map staging tile (multiple of 4, >= map_elems + 4)
@@ -455,6 +456,20 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         if (off > max_smem) return set_error("observation staging does not fit in shared memory"), TL_ERR_UNSUPPORTED;
         kp.towns_per_cta = tpc;
         grid = (b->n_towns + tpc - 1) / tpc;
+        kp.n_big_ctas = grid;  // every CTA owns tpc towns (the last one possibly fewer)
+        if (towns_per_cta_override <= 0 && !getenv("TL_TPC") && tpc > 1) {
+            // A grid that is not a multiple of the SM count leaves some SMs one CTA more than others for the whole
+            // launch (the CTAs loop over every tick); round it up and hand the towns out one fewer to the last CTAs.
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            const int even = (grid + sms - 1) / sms * sms;
+            if (even != grid && even <= b->n_towns && even / sms <= 8 && !getenv("TL_NO_EVEN_GRID")) {
+                grid = even;
+                kp.towns_per_cta = b->n_towns / grid + 1;
+                kp.n_big_ctas = b->n_towns % grid;
+                if (kp.n_big_ctas == 0) kp.towns_per_cta -= 1, kp.n_big_ctas = grid;
+            }
+        }
     } else {
         // towns per CTA: aim at one full phase-A warp (32 agents) per CTA
         int tpc = towns_per_cta_override > 0 ? towns_per_cta_override : kChunk / (avg_agents > 0 ? avg_agents : 1);
@@ -482,6 +497,7 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         if (kp.smem_bytes > max_smem) return set_error("town grid does not fit in shared memory"), TL_ERR_UNSUPPORTED;
         kp.towns_per_cta = tpc;
         grid = (b->n_towns + tpc - 1) / tpc;
+        kp.n_big_ctas = grid;
     }
 
     auto run = [&](auto kernel) -> int {
