@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     extern __shared__ __align__(16) unsigned char smem[];
     float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);  // [2][chunk * F + 4]
     float* s_tmpl = reinterpret_cast<float*>(smem + p.off_map);
-    KpiAcc* s_kpi = reinterpret_cast<KpiAcc*>(smem + p.off_meta);
+    KpiAcc* s_kpi_all = reinterpret_cast<KpiAcc*>(smem + p.off_meta);  // [2][towns_per_cta], by tick parity
 
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
@@ -126,6 +126,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
         // world/core/context.py:253-257: actions land before any system or observer runs.  No barrier: the state
         // role writes its agent's move back, and every reader of pos / ent re-derives it from the action words.
         const uint32_t* act = do_actions ? p.dyn.actions + (size_t)it * p.dyn.actions_tick_stride : nullptr;
+        // KPI partials of this tick; the other parity is being written out by a tile warp (see below)
+        KpiAcc* s_kpi = s_kpi_all + (it & 1) * p.towns_per_cta;
         if (warp == 0) {
             if (do_advance && lane < n_towns) {  // core/sim_loop.py:635,659
                 my_tick += 1;
@@ -514,7 +516,10 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
             // that pass orders this sweep before the buffer is written again
         }
 
-        if (do_kpi && warp == 0) {
+        // Small passes leave the tile warps idle while the state role is the long pole; the host then lets a tile warp
+        // write the KPI rows out (after the barrier of the tick's last pass), while the state warp already starts the
+        // next tick on the other parity.
+        if (do_kpi && warp == (do_obs ? p.kpi_out_warp : 0)) {
             __syncwarp();
             if (lane < n_towns) {
                 const KpiAcc k = s_kpi[lane];
