@@ -17,12 +17,9 @@ non-decay tail of that method (employment / economy bookkeeping).
 from __future__ import annotations
 
 import sys
-
 from collections.abc import Mapping
 from dataclasses import dataclass, field
 from typing import Any
-
-import numpy as np
 
 from . import capi
 from .engine import HostEngine
