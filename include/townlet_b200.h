@@ -442,7 +442,12 @@ void tl_context_destroy(TlContext* ctx);
 int tl_host_tick(TlContext* ctx, const TlTownBatch* host_batch, const TlObsParams* obs,
                  const TlRewardParams* rew, const TlObsOut* host_obs_out, const TlRewardOut* host_rew_out,
                  uint32_t phases, int32_t n_ticks);
-/* bytes moved by the last tl_host_tick call */
+/* tl_host_tick plus the world-dynamics phases: dyn->actions is HOST memory too; positions, the agents' entity words,
+ * the last-action fields and the ledgers are copied back with the rest of the mutated state. */
+int tl_host_tick_world(TlContext* ctx, const TlTownBatch* host_batch, const TlObsParams* obs,
+                       const TlRewardParams* rew, const TlDynamicsParams* dyn, const TlObsOut* host_obs_out,
+                       const TlRewardOut* host_rew_out, uint32_t phases, int32_t n_ticks);
+/* bytes moved by the last tl_host_tick / tl_host_tick_world call */
 int64_t tl_context_last_h2d_bytes(const TlContext* ctx);
 int64_t tl_context_last_d2h_bytes(const TlContext* ctx);
 

@@ -51,6 +51,8 @@ def test_argument_errors_are_reported_without_a_gpu(lib) -> None:
     assert lib.tl_tick_world(C.byref(b), None, None, C.byref(d), None, None, capi.TL_PHASE_ACTIONS, 1, None) == -1
     assert b"action words" in lib.tl_last_error()
     assert lib.tl_tick_world(C.byref(b), None, None, C.byref(d), None, None, 1 << 9, 1, None) == -1
+    assert lib.tl_host_tick(None, C.byref(b), None, None, None, None, capi.TL_PHASE_SOCIAL_DECAY, 1) == -1
+    assert b"tl_host_tick_world" in lib.tl_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path) -> None:

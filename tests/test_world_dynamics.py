@@ -135,6 +135,22 @@ def test_device_matches_reference_world(path, mode, monkeypatch) -> None:
     _check_final_state(batch, ref, path.stem)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIXTURES, ids=[p.stem for p in FIXTURES])
+def test_host_path_matches_reference_world(path) -> None:
+    """The same fixtures through tl_host_tick_world: HOST buffers in, HOST buffers and mutated state out."""
+    from townlet_b200.engine import HostEngine
+
+    batch, obs, rew, meta, ref = load_fixture(path)
+    eng = HostEngine(obs, rew)
+    out = eng.alloc_outputs(batch, meta["phases"], meta["n_ticks"])
+    eng.tick(batch, out, meta["phases"], meta["n_ticks"], dyn=meta["dyn_spec"], actions=meta["actions"])
+    eng.close()
+    assert_obs_equal(out, ref, path.stem)
+    assert_reward_close(out, ref, path.stem)
+    _check_final_state(batch, ref, path.stem)
+
+
 WORLD_SYNTH = [
     # name, variant, grid, agents, towns, ticks, ObsSpec kwargs, DynamicsSpec kwargs
     ("hybrid_48x8", "hybrid", 48, 8, 96, 12, {}, {}),

@@ -255,6 +255,7 @@ EXPORTED_SYMBOLS = (
     "tl_context_create",
     "tl_context_destroy",
     "tl_host_tick",
+    "tl_host_tick_world",
     "tl_context_last_h2d_bytes",
     "tl_context_last_d2h_bytes",
 )
@@ -368,6 +369,18 @@ def load_library() -> C.CDLL:
         C.POINTER(TlTownBatch),
         C.POINTER(TlObsParams),
         C.POINTER(TlRewardParams),
+        C.POINTER(TlObsOut),
+        C.POINTER(TlRewardOut),
+        C.c_uint32,
+        C.c_int32,
+    ]
+    lib.tl_host_tick_world.restype = C.c_int
+    lib.tl_host_tick_world.argtypes = [
+        _p,
+        C.POINTER(TlTownBatch),
+        C.POINTER(TlObsParams),
+        C.POINTER(TlRewardParams),
+        C.POINTER(TlDynamicsParams),
         C.POINTER(TlObsOut),
         C.POINTER(TlRewardOut),
         C.c_uint32,

@@ -682,10 +682,16 @@ bool ensure(unsigned char** buf, size_t* cap, size_t need) {
 
 int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, const TlRewardParams* rew,
                  const TlObsOut* hoo, const TlRewardOut* hro, uint32_t phases, int32_t n_ticks) {
-    if (!ctx) return set_error("context is NULL"), TL_ERR_ARG;
     if (phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY))
-        return set_error("the world-dynamics phases run on device-resident batches (tl_tick_world)"), TL_ERR_UNSUPPORTED;
-    int rc = validate(hb, obs, rew, nullptr, hoo, hro, phases, n_ticks);
+        return set_error("the world-dynamics phases need TlDynamicsParams (tl_host_tick_world)"), TL_ERR_ARG;
+    return tl_host_tick_world(ctx, hb, obs, rew, nullptr, hoo, hro, phases, n_ticks);
+}
+
+int tl_host_tick_world(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, const TlRewardParams* rew,
+                       const TlDynamicsParams* dyn, const TlObsOut* hoo, const TlRewardOut* hro, uint32_t phases,
+                       int32_t n_ticks) {
+    if (!ctx) return set_error("context is NULL"), TL_ERR_ARG;
+    int rc = validate(hb, obs, rew, dyn, hoo, hro, phases, n_ticks);
     if (rc != TL_OK) return rc;
     if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return TL_ERR_CUDA;
     ctx->last_h2d = ctx->last_d2h = 0;
@@ -699,6 +705,11 @@ int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, 
     const bool do_obs = phases & TL_PHASE_OBS;
     const bool do_state = phases & (TL_PHASE_DECAY | TL_PHASE_REWARD);
     const bool do_adv = phases & TL_PHASE_ADVANCE;
+    const bool do_act = phases & TL_PHASE_ACTIONS;       // rewrites positions, agent entity words, last-action fields
+    const bool do_led = phases & TL_PHASE_SOCIAL_DECAY;  // rewrites the relationship and rivalry ledgers
+    TlDynamicsParams ddyn;
+    memset(&ddyn, 0, sizeof(ddyn));
+    if (dyn) ddyn = *dyn;
 
     Span spans[48];
     int ns = 0;
@@ -713,8 +724,8 @@ int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, 
     FIELD(town_agent_off, (T + 1) * 4, false);
     FIELD(town_ent_off, (T + 1) * 4, false);
     FIELD(town_tick, T * 4, do_adv);
-    FIELD(ent, E * 4, false);
-    FIELD(pos, N * 4, false);
+    FIELD(ent, E * 4, do_act);
+    FIELD(pos, N * 4, do_act);
     FIELD(needs, 3 * N * 8, (phases & TL_PHASE_DECAY) != 0);
     FIELD(wallet, N * 8, false);
     FIELD(attendance, N * 8, false);
@@ -725,22 +736,24 @@ int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, 
     FIELD(social_in, 3 * N * 8, false);
     FIELD(term_block_tick, N * 4, (phases & TL_PHASE_REWARD) != 0);
     FIELD(lateness, N * 4, false);
-    FIELD(last_action_duration, N * 4, false);
+    FIELD(last_action_duration, N * 4, do_act);
     FIELD(episode_tick, N * 4, do_adv);
     FIELD(slot, N * 4, false);
-    FIELD(flags, N * 4, do_state);
-    FIELD(last_action_hash, N * 4, false);
+    FIELD(flags, N * 4, do_state || do_act);
+    FIELD(last_action_hash, N * 4, do_act);
     FIELD(personality, 3 * N * 4, false);
-    FIELD(tie_count, N, false);
-    FIELD(tie_embed, N * K * EW * 8, false);
-    FIELD(tie_trust, N * K * 8, false);
-    FIELD(tie_fam, N * K * 8, false);
-    FIELD(tie_riv, N * K * 8, false);
-    FIELD(riv_count, N, false);
-    FIELD(riv_embed, N * K * EW * 8, false);
-    FIELD(riv_score, N * K * 8, false);
+    FIELD(tie_count, N, do_led);
+    FIELD(tie_embed, N * K * EW * 8, do_led);
+    FIELD(tie_trust, N * K * 8, do_led);
+    FIELD(tie_fam, N * K * 8, do_led);
+    FIELD(tie_riv, N * K * 8, do_led);
+    FIELD(riv_count, N, do_led);
+    FIELD(riv_embed, N * K * EW * 8, do_led);
+    FIELD(riv_score, N * K * 8, do_led);
 #undef FIELD
     const int n_batch_spans = ns;
+    if (do_act)  // action words of the launch, [n_ticks][N] with the caller's tick stride
+        add(dyn->actions, (void**)&ddyn.actions, ((size_t)(n_ticks - 1) * (size_t)dyn->actions_tick_stride + N) * 4, false);
     if (do_obs) {
         const size_t W2 = (size_t)obs->window * obs->window, R = obs->window / 2;
         add(obs->time_lut, (void**)&dobs.time_lut, (size_t)obs->ticks_per_day * 2 * 4, false);
@@ -839,8 +852,8 @@ int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, 
         dro.kpi = hro->kpi ? (float*)(ctx->d_out + o_kpi) : nullptr;
     }
 
-    rc = launch(&db, obs ? &dobs : nullptr, rew, nullptr, do_obs ? &doo : nullptr, (do_state && hro) ? &dro : nullptr, phases,
-                n_ticks, ctx->stream, 0);
+    rc = launch(&db, obs ? &dobs : nullptr, rew, dyn ? &ddyn : nullptr, do_obs ? &doo : nullptr,
+                (do_state && hro) ? &dro : nullptr, phases, n_ticks, ctx->stream, 0);
     if (rc != TL_OK) return rc;
 
     for (int i = 0; i < no; ++i) {

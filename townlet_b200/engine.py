@@ -279,8 +279,19 @@ class HostEngine:
                 out["comps"] = make((n_ticks, n, capi.TL_N_COMPS), np.float64)
         return out
 
-    def tick(self, batch: TownBatch, out: dict[str, np.ndarray], phases: int, n_ticks: int = 1) -> None:
-        """Run on HOST buffers; ``batch`` state fields are updated in place."""
+    def tick(
+        self,
+        batch: TownBatch,
+        out: dict[str, np.ndarray],
+        phases: int,
+        n_ticks: int = 1,
+        dyn: DynamicsSpec | None = None,
+        actions: np.ndarray | None = None,
+    ) -> None:
+        """Run on HOST buffers; ``batch`` state fields are updated in place.
+
+        The world-dynamics phases take a ``DynamicsSpec`` and (``TL_PHASE_ACTIONS``) host action words
+        ``[n_agents]`` or ``[n_ticks, n_agents]`` (uint32 / int32)."""
         oo = capi.TlObsOut()
         ro = capi.TlRewardOut()
         for struct, names in ((oo, ("map", "features", "summary")), (ro, ("reward", "comps", "terminated", "kpi"))):
@@ -291,11 +302,26 @@ class HostEngine:
                 setattr(struct, name, C.c_void_p(arr.ctypes.data))
                 setattr(struct, f"{name}_tick_stride", int(arr.strides[0] // arr.itemsize))
         bs = batch.struct()
-        status = self.lib.tl_host_tick(
+        dyn_p = None
+        if phases & (capi.TL_PHASE_ACTIONS | capi.TL_PHASE_SOCIAL_DECAY):
+            if dyn is None:
+                raise capi.TownletB200Error("the world-dynamics phases need a DynamicsSpec")
+            ds = dyn.struct()
+            if phases & capi.TL_PHASE_ACTIONS:
+                if actions is None or actions.shape[-1] != batch.n_agents or actions.dtype.itemsize != 4:
+                    raise capi.TownletB200Error("TL_PHASE_ACTIONS needs 32-bit action words [n_agents] or [n_ticks, n_agents]")
+                actions = np.ascontiguousarray(actions)
+                if actions.ndim == 2 and actions.shape[0] != n_ticks:
+                    raise capi.TownletB200Error("actions has the wrong number of ticks")
+                ds.actions = actions.ctypes.data
+                ds.actions_tick_stride = batch.n_agents if actions.ndim == 2 else 0
+            dyn_p = C.byref(ds)
+        status = self.lib.tl_host_tick_world(
             self.ctx,
             C.byref(bs),
             C.byref(self._obs_struct) if self._obs_struct is not None else None,
             C.byref(self._rew_struct) if self._rew_struct is not None else None,
+            dyn_p,
             C.byref(oo),
             C.byref(ro),
             phases,
