@@ -345,6 +345,8 @@ def main() -> None:
             if t:  # ncu dram__bytes_read.sum + dram__bytes_write.sum per agent-step x agent-steps of one launch
                 roofline["traffic"] = t["dram_bytes_per_agent_step"] * n_agents * tpl
                 roofline["traffic_source"] = "profiles/traffic.json (ncu --set full, bytes per agent-step x agent-steps per launch)"
+                # the same fraction by measured DRAM bytes: SoA reads that stay in L2 count in `achieved` but not here
+                roofline["frac_by_traffic"] = roofline["traffic"] / avg_launch_s / 1e9 / peak
         except Exception:
             pass
 
