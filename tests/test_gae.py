@@ -133,3 +133,53 @@ def test_rollout_replay_batch_matches_reference_frames_to_replay_sample() -> Non
     assert boot["value_preds"].shape == (3, steps + 1)
     assert np.array_equal(boot["value_preds"][:, -1], d["in_values"][-1, 1:4])
     assert np.array_equal(boot["maps"], d["maps"][1:4])
+
+
+@pytest.mark.gpu
+def test_rollout_capture_with_the_policy_moving_the_agents() -> None:
+    """act_on_world: the sampled actions become action words, the next tick applies them (SURVEY §8f ranks 2 + 3).
+
+    The oracle replays the same rollout from the recorded action indices: word t is built from action t - 1 and the
+    positions before tick t, exactly as the capture does on the device.
+    """
+    import torch
+
+    from oracle.oracle import oracle_tick
+    from townlet_b200 import capi
+    from townlet_b200.engine import DeviceTownBatch
+    from townlet_b200.params import DynamicsSpec, ObsSpec, RewardSpec, pack_actions
+    from townlet_b200.rollout import PolicyMLP, RolloutCapture
+    from townlet_b200.synth import synth_batch
+
+    obs, rew, dyn = ObsSpec(), RewardSpec(fuse_faint=True), DynamicsSpec()
+    batch = synth_batch(12, 24, 6, obs)
+    ref_batch = batch.copy()
+    dev = DeviceTownBatch(batch, obs, rew, dyn=dyn)
+    torch.manual_seed(3)
+    policy = PolicyMLP(obs.n_features, obs.map_shape, action_dim=9)
+    steps = 6
+    ro = RolloutCapture(dev, policy, autocast_dtype=None, act_on_world=True).capture(steps)
+    torch.cuda.synchronize()
+    actions = ro.actions.cpu().numpy()
+    kinds = np.array(RolloutCapture.ACTION_KIND + (4,) * 11)[:16]
+    dxs = np.array(RolloutCapture.ACTION_DX + (0,) * 11)[:16]
+    dys = np.array(RolloutCapture.ACTION_DY + (0,) * 11)[:16]
+    moved = False
+    for t in range(steps):
+        if t == 0:
+            words = np.zeros(batch.n_agents, np.uint32)
+        else:
+            idx = np.minimum(actions[t - 1], 15)
+            x = ref_batch.pos.view(np.uint32) & 0xFFFF
+            y = (ref_batch.pos.view(np.uint32) >> 16) & 0xFFFF
+            nx = np.clip(x.astype(np.int64) + dxs[idx], 0, ref_batch.grid_w - 1)
+            ny = np.clip(y.astype(np.int64) + dys[idx], 0, ref_batch.grid_h - 1)
+            words = pack_actions(kinds[idx], 0, kinds[idx] == 1, nx, ny, 1)
+            moved = moved or bool(np.any((kinds[idx] == 1) & ((nx != x) | (ny != y))))
+        ref = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_WORLD, 1, dyn=dyn, actions=words)
+        assert np.array_equal(ro.map[t].cpu().numpy(), ref["map"][0]), t
+        assert np.array_equal(ro.features[t].cpu().numpy().view(np.uint32), ref["features"][0].view(np.uint32)), t
+        np.testing.assert_allclose(ro.rewards[t].cpu().numpy(), ref["reward"][0], rtol=1e-6, atol=1e-9)
+    assert moved, "the sampled actions never moved an agent"
+    state = dev.download_state()
+    assert np.array_equal(state.pos, ref_batch.pos) and np.array_equal(state.ent, ref_batch.ent)

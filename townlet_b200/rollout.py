@@ -128,13 +128,41 @@ class GraphedRollout:
 class RolloutCapture:
     """Collect ``n_ticks`` ticks of every agent of a device batch with the policy in the loop."""
 
+    # What a sampled action index does when the policy drives the world (``act_on_world=True``): 0 waits, 1-4 move one
+    # tile north / south / east / west (clamped to the grid), anything above is a kind the host services would have
+    # to resolve and is recorded as an unsuccessful request.  The reference has no fixed action space (its policy
+    # runtime numbers action payloads as they appear, policy/runner.py:254-258), so this table is this wrapper's.
+    ACTION_KIND = (3, 1, 1, 1, 1)  # TL_ACT_WAIT, TL_ACT_MOVE x 4
+    ACTION_DX = (0, 0, 0, 1, -1)
+    ACTION_DY = (0, -1, 1, 0, 0)
+
     def __init__(self, dev: DeviceTownBatch, policy: nn.Module, gamma: float = 0.99, gae_lambda: float = 0.95,
-                 autocast_dtype: torch.dtype | None = torch.bfloat16) -> None:
+                 autocast_dtype: torch.dtype | None = torch.bfloat16, act_on_world: bool = False) -> None:
         assert dev.obs is not None and dev.rew is not None
         self.dev = dev
         self.policy = policy.to(dev.device).eval()
         self.gamma, self.gae_lambda = gamma, gae_lambda
         self.autocast_dtype = autocast_dtype
+        self.act_on_world = act_on_world
+        if act_on_world:
+            if dev.dyn is None:
+                raise capi.TownletB200Error("act_on_world needs a device batch built with a DynamicsSpec")
+            table = lambda values, fill: torch.tensor(list(values) + [fill] * 11, dtype=torch.int32, device=dev.device)[:16]
+            self._kind = table(self.ACTION_KIND, 4)  # TL_ACT_REQUEST for the indices without a device meaning
+            self._dx, self._dy = table(self.ACTION_DX, 0), table(self.ACTION_DY, 0)
+            self._words = torch.zeros(dev.n_agents, dtype=torch.int32, device=dev.device)
+
+    def _action_words(self, act: torch.Tensor) -> torch.Tensor:
+        """Action words (include/townlet_b200.h: TL_ACT_PACK) of the sampled indices, from the agents' positions."""
+        idx = act.clamp(max=15).to(torch.int64)
+        kind, dx, dy = self._kind[idx], self._dx[idx], self._dy[idx]
+        pos = self.dev.field("pos")
+        x = (pos & 0xFFFF).clamp(max=self.dev.host.grid_w - 1)
+        y = ((pos >> 16) & 0xFFFF).clamp(max=self.dev.host.grid_h - 1)
+        nx = (x + dx).clamp(0, self.dev.host.grid_w - 1)
+        ny = (y + dy).clamp(0, self.dev.host.grid_h - 1)
+        is_move = (kind == 1).to(torch.int32)
+        return kind | (is_move << 5) | (nx << 6) | (ny << 16) | (1 << 26)
 
     @torch.no_grad()
     def _forward(self, map_t: torch.Tensor, feat_t: torch.Tensor):
@@ -175,11 +203,18 @@ class RolloutCapture:
         actions = torch.empty((n_ticks, n), dtype=torch.int64, device=dev.device)
         log_probs = torch.empty((n_ticks, n), dtype=torch.float32, device=dev.device)
         for t in range(n_ticks):
-            dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)  # obs / reward / done of tick t land in slot t
+            # obs / reward / done of tick t land in slot t; with act_on_world the tick first applies the action words
+            # the policy chose on the previous observation (moves), then decays needs and ledgers
+            if self.act_on_world:
+                dev.tick(out, capi.TL_PHASE_WORLD, 1, tick0=t, actions=self._words)
+            else:
+                dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)
             logits, value = self._forward(out.map[t], out.features[t])
             dist = torch.distributions.Categorical(logits=logits, validate_args=False)  # validation would sync
             act = dist.sample()
             actions[t], log_probs[t], values[t] = act, dist.log_prob(act), value
+            if self.act_on_world:
+                self._words.copy_(self._action_words(act))
         # bootstrap value: the policy on the last observation (no further tick is simulated)
         values[n_ticks] = values[n_ticks - 1] if n_ticks else 0.0
         dones = out.terminated[:n_ticks].float()
