@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — agent-steps/s of the per-tick hot path (obs build + need decay + reward).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3-compact|c3-full|c4|c5|c2-world]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3-compact|c3-full|c4|c5|c2-world|c5-world]
     python bench.py --impl reference ...      # the CPU arm (oracle port, all host threads)
 
 A "step" is ONE TICK of the whole synthetic batch: need decay -> faint
@@ -44,6 +44,9 @@ WORKLOADS = {
     # configs[4] per GPU: 65,536 towns over 8 GPUs = 8,192 towns per rank, policy forward in the loop
     "c5": dict(variant="hybrid", towns=8192, grid=48, agents=8, bytes_per_agent_step=2712, policy=True,
                name="configs[4]: PPO rollout capture, 8,192 towns per GPU x 48x48 x 8 agents, policy forward in-loop"),
+    # configs[4] with the sampled actions applied by the next tick (moves) and ledger decay: the policy drives the world
+    "c5-world": dict(variant="hybrid", towns=8192, grid=48, agents=8, bytes_per_agent_step=2712 + 24, policy=True, world=True,
+                     name="configs[4] + the policy's actions applied on the device: 8,192 towns per GPU x 48x48 x 8 agents"),
 }
 L2_BYTES = 126 * 1024 * 1024
 DISTINCT_TOWNS = 256  # towns generated on the host; larger batches tile them
@@ -245,7 +248,7 @@ def main() -> None:
     if os.environ.get("TL_BENCH_PHASES"):  # experiments only: override the phase mask
         phases = int(os.environ["TL_BENCH_PHASES"], 0)
     action_words = pristine = None
-    if wl.get("world"):
+    if wl.get("world") and not wl.get("policy"):
         # seeded action words for every tick of a launch (60 % moves to a random tile, waits, idle agents); every
         # launch starts from the pristine state (an episode reset), so the ledgers are live in every launch
         from townlet_b200.synth import random_actions
@@ -260,7 +263,7 @@ def main() -> None:
         from townlet_b200.rollout import PolicyMLP, RolloutCapture
 
         torch.manual_seed(1234 + rank)
-        capture = RolloutCapture(dev, PolicyMLP(obs.n_features, obs.map_shape, action_dim=9))
+        capture = RolloutCapture(dev, PolicyMLP(obs.n_features, obs.map_shape, action_dim=9), act_on_world=bool(wl.get("world")))
         graphed = None
         graph_launches = 0
         if not os.environ.get("TL_NO_GRAPH"):
@@ -352,7 +355,9 @@ def main() -> None:
 
     # ---- e2e: host buffers through tl_host_tick (H2D + kernel + D2H per step) --
     e2e = None
-    if wl.get("world"):
+    if wl.get("world") and wl.get("policy"):
+        e2e = None  # the rollout never leaves the device; see c5 for the host-buffer figure of the same batch
+    elif wl.get("world"):
         # the world phases run on device-resident batches: per step the action words come from pinned host memory
         # and the observations / rewards go back to pinned host memory through the public DeviceTownBatch API
         eout = dev.alloc_outputs(phases, 1, summary=False, comps=False, kpi=True)
