@@ -198,7 +198,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=256)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--ticks-per-launch", type=int, default=32)
+    ap.add_argument("--ticks-per-launch", type=int, default=None,
+                    help="ticks advanced by one launch (default: 128 for the configs[1]-sized workloads, a rollout as in "
+                    "configs[4]; 32 for the larger ones, whose 128-tick output ring would not fit)")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -234,6 +236,8 @@ def main() -> None:
     dyn = DynamicsSpec() if wl.get("world") else None
     dev = DeviceTownBatch(batch, obs, rew, device, dyn=dyn)
     n_agents = batch.n_agents
+    if args.ticks_per_launch is None:
+        args.ticks_per_launch = 128 if wl["towns"] * wl["agents"] <= 16384 and not wl.get("policy") else 32
     tpl = max(1, min(args.ticks_per_launch, args.steps))
     steps = (args.steps // tpl) * tpl
     warm = max(3, args.warmup)
