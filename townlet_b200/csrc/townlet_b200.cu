@@ -862,13 +862,31 @@ int tl_host_tick_world(TlContext* ctx, const TlTownBatch* hb, const TlObsParams*
             return TL_ERR_CUDA;
         ctx->last_d2h += (int64_t)outs[i].bytes;
     }
+    // Mutated state goes back.  When the batch is one host arena whose mutated fields sit together (the layout of
+    // soa.py puts them first), one copy covers them: the bytes in between are unchanged and equal on both sides.
+    uintptr_t wlo = UINTPTR_MAX, whi = 0;
+    size_t wsum = 0;
     for (int i = 0; i < n_batch_spans; ++i) {
         if (!spans[i].writeback) continue;
-        if (!cuda_ok(cudaMemcpyAsync(const_cast<void*>(spans[i].host), ctx->d_arena + dev_off[i], spans[i].bytes,
-                                     cudaMemcpyDeviceToHost, ctx->stream),
+        const uintptr_t p0 = (uintptr_t)spans[i].host;
+        wlo = p0 < wlo ? p0 : wlo;
+        whi = p0 + spans[i].bytes > whi ? p0 + spans[i].bytes : whi;
+        wsum += spans[i].bytes;
+    }
+    if (contiguous && wsum > 0 && (whi - wlo) <= wsum + wsum / 2 + 4096) {
+        if (!cuda_ok(cudaMemcpyAsync((void*)wlo, ctx->d_arena + (wlo - lo), whi - wlo, cudaMemcpyDeviceToHost, ctx->stream),
                      "D2H state"))
             return TL_ERR_CUDA;
-        ctx->last_d2h += (int64_t)spans[i].bytes;
+        ctx->last_d2h += (int64_t)(whi - wlo);
+    } else {
+        for (int i = 0; i < n_batch_spans; ++i) {
+            if (!spans[i].writeback) continue;
+            if (!cuda_ok(cudaMemcpyAsync(const_cast<void*>(spans[i].host), ctx->d_arena + dev_off[i], spans[i].bytes,
+                                         cudaMemcpyDeviceToHost, ctx->stream),
+                         "D2H state"))
+                return TL_ERR_CUDA;
+            ctx->last_d2h += (int64_t)spans[i].bytes;
+        }
     }
     if (!cuda_ok(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize")) return TL_ERR_CUDA;
     return TL_OK;
