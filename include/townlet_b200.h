@@ -148,7 +148,7 @@ extern "C" {
 #define TL_F_TERMINATED (1u << 7)
 #define TL_F_REASON_SHIFT 8 /* bits 8-9: 0 none 1 faint 2 eviction 3 other */
 #define TL_F_REASON_MASK (3u << 8)
-#define TL_F_CTX_RESET (1u << 10)
+#define TL_F_CTX_RESET (1u << 10) /* pending ctx-reset request: reported and CLEARED by the observation phase (grid.py:932-936) */
 #define TL_F_PROFILE_SHIFT 11 /* bits 11-13: 0 none, 1 balanced, 2 socialite, 3 industrious, 4 stoic */
 #define TL_F_PROFILE_MASK (7u << 11)
 #define TL_F_FAINTED (1u << 14) /* written by the fused faint predicate each tick; effective terminated = TERMINATED | FAINTED */
@@ -401,7 +401,7 @@ int tl_abi_struct_size(int idx);
 /* number of SMs of the current device, or a negative error */
 int tl_device_sm_count(void);
 
-/* O1-O8: observation build for every agent of the batch (no state change). */
+/* O1-O8: observation build for every agent of the batch (no state change except consuming TL_F_CTX_RESET). */
 int tl_obs_build(const TlTownBatch* batch, const TlObsParams* obs, const TlObsOut* out, tl_stream_t stream);
 
 /* D1 + T1 + R1 + K: need decay, faint predicate, reward with guardrails, per-town KPIs. */

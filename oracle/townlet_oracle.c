@@ -468,8 +468,9 @@ static void encode_features(const TlTownBatch* b, const TlObsParams* p, int t, i
     /* social splice, service.py:300-315 */
     int filled = 0, source = 0;
     if (p->social_base >= 0) encode_social(b, p, a, f + p->social_base, &filled, &source);
-    /* ctx reset, service.py:224-229 */
+    /* ctx reset, service.py:224-229: a pending request is reported once (consume_ctx_reset_requests, grid.py:932-936) */
     if ((fl & TL_F_CTX_RESET) || terminated) f[TL_FEAT_CTX_RESET] = 1.0f;
+    if (fl & TL_F_CTX_RESET) b->flags[a] = fl & ~TL_F_CTX_RESET;
 
     if (summary) {
         summary[TL_SUM_OTHER_AGENTS] = ls->other_agents;

@@ -857,6 +857,114 @@ def replay_case():
     print("  replay/ref_replay: frames_to_replay_sample + build_batch on 5 agents x 6 steps")
 
 
+def fuzz_oracle(n_worlds: int = 240, seed: int = 2026) -> None:
+    """Random reference worlds through the reference and through the C oracle, compared on the spot (nothing stored).
+
+    Each world draws its own size, variant, window, social configuration, agent and object placement (stacked agents,
+    agents at negative and far coordinates, objects sharing tiles, reservations, queues), needs near the thresholds,
+    relationship and rivalry ledgers of every fill level, terminated agents and pending ctx resets; the reference runs
+    build_batch + _apply_need_decay + lifecycle + reward for a few ticks, the oracle the same ticks on the ingested batch.
+    Maps, features and integer summaries must be bit-identical, rewards within 1e-9.
+    """
+    import sys as _sys
+
+    _sys.path.insert(0, str(REPO / "tests"))
+    from helpers import assert_obs_equal, assert_reward_close
+    from oracle.oracle import oracle_tick
+
+    rng = np.random.default_rng(seed)
+    checked_agents = 0
+    for w_index in range(n_worlds):
+        variant = ("hybrid", "full", "compact")[w_index % 3]
+        extra = {}
+        if variant == "compact":
+            extra["observations_config__compact__map_window"] = int(rng.choice([5, 7, 9]))
+            if rng.random() < 0.5:
+                extra["observations_config__compact__object_channels"] = list(rng.choice(["stove", "bed", "fridge", "shower"], size=int(rng.integers(1, 4)), replace=False))
+            extra["observations_config__compact__normalize_counts"] = bool(rng.random() < 0.5)
+        else:
+            extra["observations_config__hybrid__local_window"] = int(rng.choice([7, 9, 11, 13]))
+            extra["observations_config__hybrid__include_targets"] = bool(rng.random() < 0.4)
+        extra["observations_config__social_snippet__top_friends"] = int(rng.integers(0, 4))
+        extra["observations_config__social_snippet__top_rivals"] = int(rng.integers(0, 4))
+        extra["observations_config__social_snippet__include_aggregates"] = bool(rng.random() < 0.7)
+        if extra["observations_config__social_snippet__top_friends"] + extra["observations_config__social_snippet__top_rivals"] == 0:
+            extra["observations_config__social_snippet__include_aggregates"] = False
+        config = make_config(variant, employment__enforce_job_loop=False, **extra)
+        spec = ObsSpec.from_config(config)
+        rew = RewardSpec.from_config(config, fuse_faint=True)
+        grid = int(rng.choice([6, 12, 24, 48]))
+        n_agents = int(rng.integers(1, 13))
+        town = synth_town(int(rng.integers(0, 10_000)), grid, n_agents, terminated_frac=float(rng.choice([0.0, 0.2])))
+        # crowd some agents onto shared tiles and push needs to the faint / starvation thresholds
+        for i in range(n_agents):
+            if rng.random() < 0.3:
+                town.positions[i] = town.positions[int(rng.integers(0, n_agents))]
+            if rng.random() < 0.2:
+                town.needs[i, 0] = float(rng.choice([0.0, 0.03, 0.031, 0.04, 0.05, 0.051]))
+            k_ties = int(rng.integers(0, min(6, n_agents - 1) + 1)) if n_agents > 1 else 0
+            town.ties[i] = town.ties[i][:k_ties]
+            town.rivalry[i] = town.rivalry[i][: int(rng.integers(0, len(town.rivalry[i]) + 1))]
+        world = materialise(town, config)
+        patch_employment(world, town)
+        for aid in town.agent_ids:
+            if rng.random() < 0.15:
+                world.request_ctx_reset(aid)
+        service = WorldObservationService(config=config)
+        engine = RewardEngine(config)
+        life = LifecycleManager(config)
+        term0 = {aid: bool(town.terminated[i]) for i, aid in enumerate(town.agent_ids)}
+        reasons0 = {aid: "eviction" if i % 2 else "unemployment" for i, aid in enumerate(town.agent_ids) if town.terminated[i]}
+        pending = set(world._ctx_reset_requests)
+        slots = {aid: world.embedding_allocator.allocate(aid, world.tick) for aid in world.agents}
+        rows = ingest_town(world, spec, terminated=term0, reasons=reasons0, pending_resets=pending, slots=slots,
+                           episode_totals={}, termination_block={}, origin=(0, 0))
+        batch = rows_to_batch([rows], spec, grid=(grid, grid))
+        batch.validate(len(spec.object_channels))
+        n_ticks = int(rng.integers(1, 4))
+        N = batch.n_agents
+        ref = {"map": np.zeros((n_ticks, N, *spec.map_shape), np.float32), "features": np.zeros((n_ticks, N, spec.n_features), np.float32),
+               "summary": np.zeros((n_ticks, N, capi.TL_N_SUMMARY), np.int32), "comps": np.zeros((n_ticks, N, capi.TL_N_COMPS)),
+               "terminated": np.zeros((n_ticks, N), np.uint8)}
+        for it in range(n_ticks):
+            world.tick += 1
+            world._apply_need_decay()
+            life_term = life.evaluate(world, world.tick)
+            life_reasons = dict(life._termination_reasons)
+            terminated, reasons = {}, {}
+            for i, aid in enumerate(town.agent_ids):
+                host_flag = bool(town.terminated[i])
+                terminated[aid] = host_flag or bool(life_term.get(aid, False))
+                if host_flag:
+                    reasons[aid] = "eviction" if i % 2 else "unemployment"
+                elif aid in life_reasons:
+                    reasons[aid] = life_reasons[aid]
+            tpd = config.observations_config.hybrid.time_ticks_per_day
+            for snap in world.agents.values():
+                snap.episode_tick = (int(snap.episode_tick) + 1) % max(1, int(tpd))
+            breakdowns = engine.compute(world, terminated, reasons)
+            ids, maps, feats, summ, _ = reference_obs(world, service, terminated)
+            ref["map"][it], ref["features"][it], ref["summary"][it] = maps, feats, summ
+            for i, aid in enumerate(ids):
+                bd = breakdowns[aid]
+                for c, cname in enumerate(capi.COMP_NAMES):
+                    if cname == "guardrail_active":
+                        ref["comps"][it, i, c] = float(bd.guardrail_active)
+                    elif cname == "clipped":
+                        ref["comps"][it, i, c] = float(bd.clipped)
+                    elif cname != "reserved":
+                        ref["comps"][it, i, c] = float(getattr(bd, cname))
+                ref["terminated"][it, i] = terminated[aid]
+            for aid in ids:
+                world.embedding_allocator._assignments.setdefault(aid, int(rows.fields["slot"][ids.index(aid)]))
+        out = oracle_tick(batch, spec, rew, capi.TL_PHASE_ALL, n_ticks)
+        what = f"fuzz world {w_index} ({variant}, grid {grid}, {n_agents} agents, {n_ticks} ticks)"
+        assert_obs_equal(out, ref, what)
+        assert_reward_close(out, ref, what)
+        checked_agents += N * n_ticks
+    print(f"  fuzz: {n_worlds} random worlds, {checked_agents} agent-ticks, oracle == reference (maps / features / summaries bit-exact)")
+
+
 def gae_case():
     """compute_gae (policy/backends/pytorch/ppo_utils.py:19-67) on random float32 rollouts, both value layouts."""
     import torch
@@ -881,7 +989,7 @@ def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
     only = os.environ.get("TL_GOLDEN_ONLY")
     if only:
-        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case}[only]()
+        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()

@@ -315,3 +315,23 @@ def test_long_horizon_rollout_matches_oracle(world_phases) -> None:
     if world_phases:
         for field in ("pos", "ent", "riv_count", "riv_score", "tie_count", "tie_riv"):
             assert np.array_equal(getattr(gpu, field), getattr(cpu, field)), field
+
+
+def test_ctx_reset_request_is_reported_once() -> None:
+    """A pending ctx-reset request is consumed by the observation that reports it (service.py:224-229,
+    grid.py:932-936): in a fused launch the flag shows on the first tick only (unless the agent is terminated)."""
+    from oracle.oracle import oracle_tick
+
+    obs, rew = ObsSpec(), RewardSpec(fuse_faint=True)
+    base = synth_batch(20, 24, 6, obs)
+    base.needs[0, :] = 0.9  # nobody faints during the sequence
+    base.flags[:] &= ~np.uint32(capi.TL_F_TERMINATED | capi.TL_F_FAINTED)
+    marked = np.arange(base.n_agents) % 3 == 0
+    base.flags[marked] |= np.uint32(capi.TL_F_CTX_RESET)
+    cpu, gpu = base.copy(), base.copy()
+    want = oracle_tick(cpu, obs, rew, capi.TL_PHASE_ALL, 3)
+    got = _device_run(gpu, obs, rew, capi.TL_PHASE_ALL, 3)
+    assert_obs_equal(got, want, "ctx reset")
+    ctx = got["features"][:, :, 16]  # TL_FEAT_CTX_RESET
+    assert np.array_equal(ctx[0], marked.astype(np.float32)) and not ctx[1:].any()
+    assert not (gpu.flags & capi.TL_F_CTX_RESET).any() and np.array_equal(gpu.flags, cpu.flags)

@@ -257,6 +257,10 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
                                    ? __ldg(o.slot_lut + slot_idx)
                                    : (float)((double)slot_idx / (double)o.max_slots);
         f[TL_FEAT_CTX_RESET] = ((fl & TL_F_CTX_RESET) || terminated) ? 1.0f : 0.0f;  // service.py:224-229
+        if (fl & TL_F_CTX_RESET) {  // a pending request is reported once (consume_ctx_reset_requests, grid.py:932-936)
+            fl &= ~TL_F_CTX_RESET;
+            p.b.flags[a] = fl;
+        }
         f[TL_FEAT_EPISODE_PROGRESS] =
             episode_tick <= 0 ? 0.0f : __ldg(o.progress_lut + min(episode_tick, o.ticks_per_day));
         f[TL_FEAT_LAST_HASH] = last_hash;

@@ -739,7 +739,7 @@ int tl_host_tick_world(TlContext* ctx, const TlTownBatch* hb, const TlObsParams*
     FIELD(last_action_duration, N * 4, do_act);
     FIELD(episode_tick, N * 4, do_adv);
     FIELD(slot, N * 4, false);
-    FIELD(flags, N * 4, do_state || do_act);
+    FIELD(flags, N * 4, do_state || do_act || do_obs);  // the observation consumes TL_F_CTX_RESET
     FIELD(last_action_hash, N * 4, do_act);
     FIELD(personality, 3 * N * 4, false);
     FIELD(tie_count, N, do_led);
