@@ -857,7 +857,7 @@ def replay_case():
     print("  replay/ref_replay: frames_to_replay_sample + build_batch on 5 agents x 6 steps")
 
 
-def fuzz_oracle(n_worlds: int = 240, seed: int = 2026) -> None:
+def fuzz_oracle(n_worlds: int = int(os.environ.get("TL_FUZZ_WORLDS", 240)), seed: int = int(os.environ.get("TL_FUZZ_SEED", 2026))) -> None:
     """Random reference worlds through the reference and through the C oracle, compared on the spot (nothing stored).
 
     Each world draws its own size, variant, window, social configuration, agent and object placement (stacked agents,
@@ -965,6 +965,123 @@ def fuzz_oracle(n_worlds: int = 240, seed: int = 2026) -> None:
     print(f"  fuzz: {n_worlds} random worlds, {checked_agents} agent-ticks, oracle == reference (maps / features / summaries bit-exact)")
 
 
+def fuzz_world(n_worlds: int = int(os.environ.get("TL_FUZZ_WORLDS", 120)), seed: int = int(os.environ.get("TL_FUZZ_SEED", 4242))) -> None:
+    """Random worlds with random actions and ledger decay through the reference and the oracle (nothing stored).
+
+    Per tick, in WorldContext.tick order: apply_actions + process_actions, need decay, RelationshipService.decay,
+    lifecycle, reward, observe (as world_dynamics_cases); afterwards the final world is ingested again and its
+    positions, entity words, last-action fields and ledgers are compared with the oracle's batch byte for byte.
+    """
+    import sys as _sys
+
+    _sys.path.insert(0, str(REPO / "tests"))
+    from helpers import assert_obs_equal, assert_reward_close
+    from oracle.oracle import oracle_tick
+    from townlet.world.actions import Action, apply_actions
+    from townlet.world.systems.affordances import process_actions
+
+    rng = np.random.default_rng(seed)
+    agent_ticks = 0
+    for w_index in range(n_worlds):
+        variant = ("hybrid", "compact", "full")[w_index % 3]
+        extra = {"conflict__rivalry__decay_per_tick": float(rng.choice([0.0, 0.005, 0.02, 0.05])),
+                 "conflict__rivalry__eviction_threshold": float(rng.choice([0.0, 0.05, 0.1]))}
+        config = make_config(variant, employment__enforce_job_loop=False, **extra)
+        spec = ObsSpec.from_config(config)
+        rew = RewardSpec.from_config(config, fuse_faint=True)
+        dyn = DynamicsSpec.from_config(config)
+        tie_params = {"trust_decay": float(rng.choice([0.0, 0.03, 0.2])), "familiarity_decay": float(rng.choice([0.0, 0.05])),
+                      "rivalry_decay": float(rng.choice([0.0, 0.01, 0.1]))}
+        dyn.trust_decay, dyn.familiarity_decay, dyn.tie_rivalry_decay = tie_params["trust_decay"], tie_params["familiarity_decay"], tie_params["rivalry_decay"]
+        grid = int(rng.choice([8, 16, 32]))
+        n_agents = int(rng.integers(2, 11))
+        town = synth_town(int(rng.integers(0, 10_000)), grid, n_agents, terminated_frac=0.1)
+        for i in range(n_agents):  # values that cross the eviction / zero thresholds within a few ticks
+            town.rivalry[i] = [(o, float(rng.choice([0.04, 0.051, 0.06, 0.1, 0.3]))) for o, _ in town.rivalry[i]]
+            town.ties[i] = [(o, float(rng.choice([0.0, 0.02, 0.3])), float(rng.choice([0.0, 0.04, 0.2])), float(rng.choice([0.0, 0.005, 0.15])))
+                            for o, _, _, _ in town.ties[i]]
+        world = materialise(town, config)
+        patch_employment(world, town)
+        for ledger in world._relationships._relationship_ledgers.values():
+            for key, value in tie_params.items():
+                setattr(ledger.params, key, value)
+        service, engine, life = WorldObservationService(config=config), RewardEngine(config), LifecycleManager(config)
+
+        def ingest():
+            term0 = {aid: bool(town.terminated[i]) for i, aid in enumerate(town.agent_ids)}
+            reasons0 = {aid: "eviction" if i % 2 else "unemployment" for i, aid in enumerate(town.agent_ids) if town.terminated[i]}
+            slots = {aid: world.embedding_allocator.allocate(aid, world.tick) for aid in world.agents}
+            return ingest_town(world, spec, terminated=term0, reasons=reasons0, pending_resets=set(), slots=slots,
+                               episode_totals=dict(engine._episode_totals), termination_block=dict(engine._termination_block), origin=(0, 0))
+
+        rows = ingest()
+        batch = rows_to_batch([rows], spec, grid=(grid, grid))
+        n_ticks = int(rng.integers(1, 7))
+        N = batch.n_agents
+        ref = {"map": np.zeros((n_ticks, N, *spec.map_shape), np.float32), "features": np.zeros((n_ticks, N, spec.n_features), np.float32),
+               "summary": np.zeros((n_ticks, N, capi.TL_N_SUMMARY), np.int32), "comps": np.zeros((n_ticks, N, capi.TL_N_COMPS)),
+               "terminated": np.zeros((n_ticks, N), np.uint8)}
+        words = np.zeros((n_ticks, N), np.uint32)
+        for it in range(n_ticks):
+            world.tick += 1
+            actions = {}
+            for i, aid in enumerate(town.agent_ids):
+                roll = rng.random()
+                if roll < 0.5:
+                    actions[aid] = {"kind": "move", "position": (int(rng.integers(0, grid)), int(rng.integers(0, grid))), "duration": int(rng.integers(1, 20))}
+                elif roll < 0.55:
+                    actions[aid] = {"kind": "move"}
+                elif roll < 0.7:
+                    actions[aid] = {"kind": str(rng.choice(["wait", "noop"])), "duration": int(rng.integers(1, 60))}
+            words[it] = encode_actions(town.agent_ids, actions)
+            coerced = [Action(agent_id=k, kind=str(v.get("kind", "noop")), payload=dict(v)) for k, v in actions.items()]
+            if coerced:
+                apply_actions(world, coerced)
+            if actions:
+                process_actions(world, actions, tick=world.tick)
+            world._apply_need_decay()
+            world._relationships.decay()
+            life_term = life.evaluate(world, world.tick)
+            life_reasons = dict(life._termination_reasons)
+            terminated, reasons = {}, {}
+            for i, aid in enumerate(town.agent_ids):
+                host_flag = bool(town.terminated[i])
+                terminated[aid] = host_flag or bool(life_term.get(aid, False))
+                if host_flag:
+                    reasons[aid] = "eviction" if i % 2 else "unemployment"
+                elif aid in life_reasons:
+                    reasons[aid] = life_reasons[aid]
+            tpd = config.observations_config.hybrid.time_ticks_per_day
+            for snap in world.agents.values():
+                snap.episode_tick = (int(snap.episode_tick) + 1) % max(1, int(tpd))
+            breakdowns = engine.compute(world, terminated, reasons)
+            ids, maps, feats, summ, _ = reference_obs(world, service, terminated)
+            ref["map"][it], ref["features"][it], ref["summary"][it] = maps, feats, summ
+            for i, aid in enumerate(ids):
+                bd = breakdowns[aid]
+                for c, cname in enumerate(capi.COMP_NAMES):
+                    if cname == "guardrail_active":
+                        ref["comps"][it, i, c] = float(bd.guardrail_active)
+                    elif cname == "clipped":
+                        ref["comps"][it, i, c] = float(bd.clipped)
+                    elif cname != "reserved":
+                        ref["comps"][it, i, c] = float(getattr(bd, cname))
+                ref["terminated"][it, i] = terminated[aid]
+            for aid in ids:
+                world.embedding_allocator._assignments.setdefault(aid, int(rows.fields["slot"][ids.index(aid)]))
+        final = rows_to_batch([ingest()], spec, grid=(grid, grid))
+        out = oracle_tick(batch, spec, rew, capi.TL_PHASE_WORLD, n_ticks, dyn=dyn, actions=words)
+        what = f"fuzz world {w_index} ({variant}, grid {grid}, {n_agents} agents, {n_ticks} ticks, {tie_params}, {extra})"
+        assert_obs_equal(out, ref, what)
+        assert_reward_close(out, ref, what)
+        for fname in ("pos", "ent", "tie_count", "tie_trust", "tie_fam", "tie_riv", "tie_embed", "riv_count", "riv_score", "riv_embed",
+                      "last_action_duration", "last_action_hash"):
+            got, want = np.asarray(getattr(batch, fname)), np.asarray(getattr(final, fname))
+            assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), f"{what}: final {fname}"
+        agent_ticks += N * n_ticks
+    print(f"  fuzz-world: {n_worlds} random worlds, {agent_ticks} agent-ticks with actions and ledger decay, oracle == reference")
+
+
 def gae_case():
     """compute_gae (policy/backends/pytorch/ppo_utils.py:19-67) on random float32 rollouts, both value layouts."""
     import torch
@@ -989,7 +1106,7 @@ def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
     only = os.environ.get("TL_GOLDEN_ONLY")
     if only:
-        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle}[only]()
+        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()
