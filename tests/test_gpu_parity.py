@@ -335,3 +335,65 @@ def test_ctx_reset_request_is_reported_once() -> None:
     ctx = got["features"][:, :, 16]  # TL_FEAT_CTX_RESET
     assert np.array_equal(ctx[0], marked.astype(np.float32)) and not ctx[1:].any()
     assert not (gpu.flags & capi.TL_F_CTX_RESET).any() and np.array_equal(gpu.flags, cpu.flags)
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("TL_FUZZ_SEEDS", "24"))))
+def test_kernels_against_oracle_on_random_configurations(seed, monkeypatch) -> None:
+    """Fuzz: random variant, window, social layout, object channels, town sizes (ragged), phases and kernel form;
+    every output and the whole final state against the oracle."""
+    from oracle.oracle import oracle_tick
+    from townlet_b200.params import DynamicsSpec
+    from townlet_b200.synth import assemble, random_actions, synth_town
+
+    rng = np.random.default_rng(1000 + seed)
+    variant = ("hybrid", "full", "compact")[seed % 3]
+    kw = dict(
+        variant=variant,
+        top_friends=int(rng.integers(0, 5)),
+        top_rivals=int(rng.integers(0, 4)),
+        embed_dim=int(rng.choice([4, 8, 8, 12, 16])),
+        include_aggregates=bool(rng.random() < 0.7),
+        include_targets=bool(rng.random() < 0.3),
+        personality_channels=bool(rng.random() < 0.3),
+    )
+    if variant == "compact":
+        kw["compact_window"] = int(rng.choice([3, 5, 7, 7, 9, 13]))
+        kw["normalize_counts"] = bool(rng.random() < 0.5)
+        kw["object_channels"] = tuple(rng.choice(["stove", "bed", "fridge", "shower"], size=int(rng.integers(0, 4)), replace=False))
+    else:
+        kw["local_window"] = int(rng.choice([5, 9, 11, 11, 15, 21]))
+    obs, rew = ObsSpec(**kw), RewardSpec(fuse_faint=True, personality_scaling=bool(rng.random() < 0.3))
+    grid = int(rng.choice([8, 24, 48, 96]))
+    towns = [synth_town(int(rng.integers(0, 5000)), grid, int(rng.integers(1, 41)), terminated_frac=0.1) for _ in range(int(rng.integers(1, 30)))]
+    base = assemble(towns, obs)
+    ticks = int(rng.integers(1, 6))
+    world_phases = bool(rng.random() < 0.5)
+    dyn = DynamicsSpec(trust_decay=float(rng.choice([0.0, 0.05])), rivalry_decay_per_tick=float(rng.choice([0.005, 0.05]))) if world_phases else None
+    phases = capi.TL_PHASE_WORLD if world_phases else capi.TL_PHASE_ALL
+    actions = random_actions(base, ticks, seed=seed) if world_phases else None
+    mode = ("ent", "grid", "ent")[int(rng.integers(0, 3))]
+    monkeypatch.setenv("TL_MODE", mode)
+    if rng.random() < 0.3:
+        monkeypatch.setenv("TL_CHUNK", str(int(rng.choice([8, 16, 24]))))
+    if rng.random() < 0.3:
+        monkeypatch.setenv("TL_GENERIC", "1")
+
+    import torch
+
+    from townlet_b200.engine import DeviceTownBatch
+
+    cpu, gpu = base.copy(), base.copy()
+    want = oracle_tick(cpu, obs, rew, phases, ticks, dyn=dyn, actions=actions)
+    dev = DeviceTownBatch(gpu, obs, rew, dyn=dyn)
+    out = dev.alloc_outputs(phases, ticks, summary=True, comps=True)
+    act = torch.from_numpy(actions.view(np.int32)).to(dev.device) if actions is not None else None
+    dev.tick(out, phases, ticks, actions=act)
+    torch.cuda.synchronize()
+    dev.download_state()
+    got = {k: v.cpu().numpy() for k, v in vars(out).items() if v is not None}
+    what = f"seed {seed}: {kw}, grid {grid}, {len(towns)} towns, {base.n_agents} agents, {ticks} ticks, mode {mode}, world {world_phases}"
+    assert_obs_equal(got, want, what)
+    assert_reward_close(got, want, what)
+    np.testing.assert_allclose(gpu.needs, cpu.needs, rtol=REL_TOL, atol=1e-15, err_msg=what)
+    for field in ("flags", "pos", "ent", "episode_tick", "term_block_tick", "tie_count", "tie_trust", "riv_count", "riv_score"):
+        assert np.array_equal(getattr(gpu, field), getattr(cpu, field)), f"{what}: {field}"
