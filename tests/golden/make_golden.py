@@ -1082,6 +1082,87 @@ def fuzz_world(n_worlds: int = int(os.environ.get("TL_FUZZ_WORLDS", 120)), seed:
     print(f"  fuzz-world: {n_worlds} random worlds, {agent_ticks} agent-ticks with actions and ledger decay, oracle == reference")
 
 
+def fuzz_dropin(n_worlds: int = int(os.environ.get("TL_FUZZ_WORLDS", 150)), seed: int = int(os.environ.get("TL_FUZZ_SEED", 515))) -> None:
+    """The drop-in classes against the reference classes on random worlds (host logic: the compute underneath is the
+    oracle through the test-only engine): build_batch dictionaries including the metadata, RewardEngine.compute
+    breakdowns and the need-decay hook over a few ticks of twin worlds built from the same description."""
+    import sys as _sys
+
+    _sys.path.insert(0, str(REPO / "tests"))
+    import townlet_b200.observation_service as obs_mod
+    import townlet_b200.reward_engine as rew_mod
+    from oracle_engine import OracleHostEngine
+
+    obs_mod.HostEngine = OracleHostEngine
+    rew_mod.HostEngine = OracleHostEngine
+    rng = np.random.default_rng(seed)
+    compared = 0
+    for w_index in range(n_worlds):
+        variant = ("hybrid", "full", "compact")[w_index % 3]
+        extra = {"observations_config__social_snippet__top_friends": int(rng.integers(0, 4)),
+                 "observations_config__social_snippet__top_rivals": int(rng.integers(1, 4)),
+                 "observations_config__hybrid__include_targets": bool(rng.random() < 0.4),
+                 "features__observations__personality_channels": bool(rng.random() < 0.3)}
+        if variant == "compact" and rng.random() < 0.5:
+            extra["observations_config__compact__object_channels"] = ["stove", "bed"]
+        config = make_config(variant, employment__enforce_job_loop=False, **extra)
+        grid = int(rng.choice([6, 16, 48]))
+        n_agents = int(rng.integers(1, 10))
+        town = synth_town(int(rng.integers(0, 10_000)), grid, n_agents, terminated_frac=0.0)
+        for i in range(n_agents):
+            if rng.random() < 0.3:
+                town.positions[i] = town.positions[int(rng.integers(0, n_agents))]
+            if rng.random() < 0.2:
+                town.needs[i, 0] = float(rng.choice([0.0, 0.03, 0.031, 0.05]))
+        offset = (int(rng.integers(-40, 40)), int(rng.integers(-40, 40)))  # the reference has no coordinate bounds
+        town.positions = town.positions + np.array(offset)
+        town.object_positions = town.object_positions + np.array(offset)
+        twins = []
+        for _ in range(2):
+            world = materialise(town, config)
+            patch_employment(world, town)
+            twins.append(world)
+        ref_world, our_world = twins
+        resets = [aid for aid in town.agent_ids if rng.random() < 0.2]
+        for world in twins:
+            for aid in resets:
+                world.request_ctx_reset(aid)
+        ref_service, our_service = WorldObservationService(config=config), obs_mod.B200ObservationService(config=config)
+        ref_engine, our_engine = RewardEngine(config), rew_mod.B200RewardEngine(config)
+        rew_mod.install_need_decay(our_world)
+        life_a, life_b = LifecycleManager(config), LifecycleManager(config)
+        for it in range(int(rng.integers(1, 4))):
+            terminated = []
+            for world, life in ((ref_world, life_a), (our_world, life_b)):
+                world.tick += 1
+                world._apply_need_decay()
+                terminated.append(dict(life.evaluate(world, world.tick)))
+            assert terminated[0] == terminated[1], f"fuzz-dropin world {w_index}: lifecycle after decay"
+            for aid in town.agent_ids:
+                assert ref_world.agents[aid].needs == our_world.agents[aid].needs, f"fuzz-dropin world {w_index}: needs of {aid}"
+            reasons = {aid: "faint" for aid, flag in terminated[0].items() if flag}
+            bd_ref = ref_engine.compute(ref_world, terminated[0], reasons)
+            bd_our = our_engine.compute(our_world, terminated[1], reasons)
+            assert list(bd_ref) == list(bd_our)
+            for aid in bd_ref:
+                a, b = bd_ref[aid].model_dump(), bd_our[aid].model_dump()
+                for key, value in a.items():
+                    if isinstance(value, float):
+                        assert abs(value - b[key]) <= 1e-9 + 1e-6 * abs(value), f"fuzz-dropin world {w_index}: reward {key} of {aid}: {value} vs {b[key]}"
+                    else:
+                        assert value == b[key], f"fuzz-dropin world {w_index}: reward {key} of {aid}"
+            want = ref_service.build_batch(ref_world, terminated[0])
+            got = our_service.build_batch(our_world, terminated[1])
+            assert list(want) == list(got), f"fuzz-dropin world {w_index}: agent order"
+            for aid in want:
+                assert np.array_equal(got[aid]["map"], want[aid]["map"]), f"fuzz-dropin world {w_index} tick {it}: map of {aid}"
+                assert np.array_equal(got[aid]["features"].view(np.uint32), want[aid]["features"].view(np.uint32)), (
+                    f"fuzz-dropin world {w_index} tick {it} ({variant}): features of {aid}")
+                assert got[aid]["metadata"] == want[aid]["metadata"], f"fuzz-dropin world {w_index} tick {it}: metadata of {aid}"
+                compared += 1
+    print(f"  fuzz-dropin: {n_worlds} twin worlds, {compared} observations with metadata, rewards and decayed needs equal to the reference's")
+
+
 def gae_case():
     """compute_gae (policy/backends/pytorch/ppo_utils.py:19-67) on random float32 rollouts, both value layouts."""
     import torch
@@ -1106,7 +1187,7 @@ def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
     only = os.environ.get("TL_GOLDEN_ONLY")
     if only:
-        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world}[only]()
+        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world, "fuzz-dropin": fuzz_dropin}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()
