@@ -1141,6 +1141,22 @@ def fuzz_dropin(n_worlds: int = int(os.environ.get("TL_FUZZ_WORLDS", 150)), seed
             for aid in town.agent_ids:
                 assert ref_world.agents[aid].needs == our_world.agents[aid].needs, f"fuzz-dropin world {w_index}: needs of {aid}"
             reasons = {aid: "faint" for aid, flag in terminated[0].items() if flag}
+            # social events of the tick (rewards/engine.py:257-317): chats that succeed or fail between random pairs
+            # (also with an id the world does not know), avoidance blocks; recorded identically in both worlds
+            events = []
+            for _ in range(int(rng.integers(0, 5))):
+                kind = str(rng.choice(["chat_success", "chat_failure", "avoid"]))
+                speaker = str(rng.choice(town.agent_ids))
+                listener = str(rng.choice(town.agent_ids + ["stranger"]))
+                events.append((kind, speaker, listener, float(rng.choice([0.0, 0.25, 0.5, 1.0, 2.0]))))
+            for world in twins:
+                for kind, speaker, listener, quality in events:
+                    if kind == "chat_success":
+                        world.record_chat_success(speaker, listener, quality)
+                    elif kind == "chat_failure":
+                        world.record_chat_failure(speaker, listener)
+                    else:
+                        world.record_relationship_guard_block(agent_id=speaker, reason="queue_rival", target_agent=listener, object_id="o")
             bd_ref = ref_engine.compute(ref_world, terminated[0], reasons)
             bd_our = our_engine.compute(our_world, terminated[1], reasons)
             assert list(bd_ref) == list(bd_our)
