@@ -1179,6 +1179,26 @@ def fuzz_dropin(n_worlds: int = int(os.environ.get("TL_FUZZ_WORLDS", 150)), seed
     print(f"  fuzz-dropin: {n_worlds} twin worlds, {compared} observations with metadata, rewards and decayed needs equal to the reference's")
 
 
+def fuzz_gae(n_cases: int = int(os.environ.get("TL_FUZZ_WORLDS", 200)), seed: int = int(os.environ.get("TL_FUZZ_SEED", 77))) -> None:
+    """compute_gae (policy/backends/pytorch/ppo_utils.py:19-67) against the oracle's scan on random rollouts."""
+    import torch
+
+    from oracle.oracle import oracle_gae
+    from townlet.policy.backends.pytorch.ppo_utils import compute_gae
+
+    rng = np.random.default_rng(seed)
+    for case in range(n_cases):
+        batch, steps, bootstrap = int(rng.integers(1, 40)), int(rng.integers(1, 70)), bool(rng.random() < 0.5)
+        gamma, lam = float(rng.choice([0.9, 0.99, 0.999, 1.0])), float(rng.choice([0.0, 0.5, 0.95, 1.0]))
+        rewards = rng.uniform(-1.0, 1.0, size=(batch, steps)).astype(np.float32)
+        values = rng.normal(0.0, 1.0, size=(batch, steps + int(bootstrap))).astype(np.float32)
+        dones = (rng.random((batch, steps)) < rng.choice([0.0, 0.1, 0.5])).astype(np.float32)
+        res = compute_gae(torch.from_numpy(rewards), torch.from_numpy(values), torch.from_numpy(dones), gamma=gamma, gae_lambda=lam)
+        adv, ret = oracle_gae(rewards.T, values.T, dones.T, gamma, lam)
+        assert np.array_equal(adv.T, res.advantages.numpy()) and np.array_equal(ret.T, res.returns.numpy()), (case, batch, steps, bootstrap, gamma, lam)
+    print(f"  fuzz-gae: {n_cases} random rollouts, oracle == compute_gae bit for bit")
+
+
 def gae_case():
     """compute_gae (policy/backends/pytorch/ppo_utils.py:19-67) on random float32 rollouts, both value layouts."""
     import torch
@@ -1203,7 +1223,7 @@ def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
     only = os.environ.get("TL_GOLDEN_ONLY")
     if only:
-        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world, "fuzz-dropin": fuzz_dropin}[only]()
+        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world, "fuzz-dropin": fuzz_dropin, "fuzz-gae": fuzz_gae}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()

@@ -21,7 +21,7 @@ HERE = Path(__file__).resolve().parent
 pytestmark = pytest.mark.skipif(not (REF / "src" / "townlet").exists(), reason="reference checkout not available")
 
 
-@pytest.mark.parametrize("mode,worlds", [("fuzz", 45), ("fuzz-world", 30), ("fuzz-dropin", 30)])
+@pytest.mark.parametrize("mode,worlds", [("fuzz", 45), ("fuzz-world", 30), ("fuzz-dropin", 30), ("fuzz-gae", 100)])
 def test_random_worlds_agree_with_the_reference(mode, worlds) -> None:
     env = dict(os.environ, TL_GOLDEN_ONLY=mode, TL_FUZZ_WORLDS=str(worlds), TL_FUZZ_SEED="20261020")
     proc = subprocess.run([sys.executable, str(HERE / "golden" / "make_golden.py")], env=env, capture_output=True, text=True, timeout=900)
