@@ -214,7 +214,9 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
     if (reason == 0 && (fl & TL_F_FAINTED)) reason = 1;
     if (do_advance) {  // world/core/context.py:283-289
         const int span = max(1, o.ticks_per_day);
-        episode_tick = (episode_tick + 1) % span;
+        // (episode_tick + 1) % span; the division only runs for a value outside [0, span) (never after the first tick)
+        episode_tick += 1;
+        if ((unsigned)episode_tick >= (unsigned)span) episode_tick = episode_tick == span ? 0 : episode_tick % span;
         p.b.episode_tick[a] = episode_tick;
     }
     if (do_reward) {
