@@ -711,7 +711,8 @@ static void town_tick(const TlTownBatch* b, const TlObsParams* p, const TlReward
         if (reason == 0 && (fl & TL_F_FAINTED)) reason = 1; /* reasons.setdefault(agent, "faint") */
         if (phases & TL_PHASE_ADVANCE) { /* world/core/context.py:283-289 */
             int span = p ? (p->ticks_per_day > 1 ? p->ticks_per_day : 1) : 1;
-            b->episode_tick[a] = (b->episode_tick[a] + 1) % span;
+            int e = (b->episode_tick[a] + 1) % span;
+            b->episode_tick[a] = e < 0 ? e + span : e; /* Python's modulo is never negative */
         }
         if (phases & TL_PHASE_REWARD) {
             double* comps = (ro && ro->comps) ? ro->comps + (size_t)it * ro->comps_tick_stride + (size_t)a * TL_N_COMPS : NULL;

@@ -397,3 +397,19 @@ def test_kernels_against_oracle_on_random_configurations(seed, monkeypatch) -> N
     np.testing.assert_allclose(gpu.needs, cpu.needs, rtol=REL_TOL, atol=1e-15, err_msg=what)
     for field in ("flags", "pos", "ent", "episode_tick", "term_block_tick", "tie_count", "tie_trust", "riv_count", "riv_score"):
         assert np.array_equal(getattr(gpu, field), getattr(cpu, field)), f"{what}: {field}"
+
+
+def test_episode_tick_wraps_like_python_modulo() -> None:
+    """(episode_tick + 1) % ticks_per_day with Python semantics (world/core/context.py:283-289), also for inputs
+    outside [0, ticks_per_day)."""
+    from oracle.oracle import oracle_tick
+
+    obs, rew = ObsSpec(), RewardSpec(fuse_faint=True)
+    base = synth_batch(4, 16, 6, obs)
+    base.episode_tick[:] = np.array([-7, -1, 0, 1438, 1439, 1440, 5000, -1441] * 3, dtype=np.int32)[: base.n_agents]
+    cpu, gpu = base.copy(), base.copy()
+    want = oracle_tick(cpu, obs, rew, capi.TL_PHASE_ALL, 2)
+    got = _device_run(gpu, obs, rew, capi.TL_PHASE_ALL, 2)
+    assert_obs_equal(got, want, "episode tick")
+    expect = (((base.episode_tick.astype(np.int64) + 1) % 1440) + 1) % 1440
+    assert np.array_equal(cpu.episode_tick, expect) and np.array_equal(gpu.episode_tick, expect)

@@ -216,7 +216,10 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
         const int span = max(1, o.ticks_per_day);
         // (episode_tick + 1) % span; the division only runs for a value outside [0, span) (never after the first tick)
         episode_tick += 1;
-        if ((unsigned)episode_tick >= (unsigned)span) episode_tick = episode_tick == span ? 0 : episode_tick % span;
+        if ((unsigned)episode_tick >= (unsigned)span) {
+            episode_tick %= span;
+            if (episode_tick < 0) episode_tick += span;  // Python's modulo is never negative
+        }
         p.b.episode_tick[a] = episode_tick;
     }
     if (do_reward) {
