@@ -273,7 +273,7 @@ def main() -> None:
         if not os.environ.get("TL_NO_GRAPH"):
             before = lib.tl_launch_count()
             graphed = capture.build_graph(tpl, out)
-            graph_launches = tpl + 1  # kernels of this library inside the captured rollout: tpl ticks + 1 GAE scan
+            graph_launches = 3 * tpl + 1  # kernels of this library in the captured rollout: per tick 1 tick + 2 cast/pad, + 1 GAE scan
             del before
 
     def launch(i: int) -> None:

@@ -433,6 +433,12 @@ int64_t tl_launch_count(void);
 int tl_gae(const float* rewards, const float* values, const float* dones, float* advantages, float* returns,
            int32_t n_steps, int32_t n_agents, int32_t bootstrap, double gamma, double gae_lambda, tl_stream_t stream);
 
+/* float32 rows [n_rows][width] -> bfloat16 rows [n_rows][padded_width], zero padded (padded_width even, >= width):
+ * the low-precision copy of the observation tensors the batched policy step consumes (the cast
+ * PolicyRuntime's autocast would do, policy/runner.py:444-488, fused with the padding that aligns the GEMM's reduction
+ * width).  Device pointers, asynchronous on the stream; round to nearest even. */
+int tl_cast_pad_bf16(const float* src, void* dst, int64_t n_rows, int32_t width, int32_t padded_width, tl_stream_t stream);
+
 /* Host-buffer entry: every pointer (batch, LUTs, outputs) is HOST memory.
  * Copies the batch to the context's device arena, runs tl_tick, copies the
  * requested outputs and the mutated state back, and synchronises. */

@@ -183,3 +183,38 @@ def test_rollout_capture_with_the_policy_moving_the_agents() -> None:
     assert moved, "the sampled actions never moved an agent"
     state = dev.download_state()
     assert np.array_equal(state.pos, ref_batch.pos) and np.array_equal(state.ent, ref_batch.ent)
+
+
+@pytest.mark.gpu
+def test_cast_pad_bf16_and_the_padded_policy_forward() -> None:
+    """tl_cast_pad_bf16 equals torch's float32 -> bfloat16 cast plus zero padding, and the policy's padded bfloat16
+    inference path agrees with plain autocast to bfloat16 rounding."""
+    import torch
+
+    from townlet_b200 import capi
+    from townlet_b200.rollout import PolicyMLP
+
+    lib = capi.load_library()
+    torch.manual_seed(1)
+    for rows, width, padded in ((1000, 484, 512), (77, 81, 128), (5, 7, 8), (3, 64, 64)):
+        src = torch.randn(rows, width, device="cuda") * 3
+        dst = torch.full((rows, padded), 7.0, dtype=torch.bfloat16, device="cuda")
+        capi.check(lib.tl_cast_pad_bf16(src.data_ptr(), dst.data_ptr(), rows, width, padded, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(dst[:, :width], src.to(torch.bfloat16)) and not dst[:, width:].any()
+    assert lib.tl_cast_pad_bf16(None, None, 1, 4, 4, None) == -1 and lib.tl_cast_pad_bf16(1, 1, 1, 5, 4, None) == -1
+
+    model = PolicyMLP(81, (4, 11, 11), 9).cuda().eval()
+    maps = (torch.rand(4096, 4, 11, 11, device="cuda") < 0.05).float()
+    feats = torch.randn(4096, 81, device="cuda")
+    with torch.no_grad():
+        exact_logits, exact_value = model(maps, feats)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits, value = model(maps, feats)  # padded path
+            hidden = torch.cat([model.map_encoder(maps), model.feature_encoder(feats)], dim=-1)
+            plain_logits = model.policy_head(model.shared(hidden))
+    assert hasattr(model, "_pad_map")
+    err_padded = (logits.float() - exact_logits).abs().max().item()
+    err_plain = (plain_logits.float() - exact_logits).abs().max().item()
+    assert err_padded < 2 * err_plain + 1e-3, (err_padded, err_plain)
+    assert (value.float() - exact_value).abs().max().item() < 0.02

@@ -252,6 +252,7 @@ EXPORTED_SYMBOLS = (
     "tl_tick_world",
     "tl_launch_count",
     "tl_gae",
+    "tl_cast_pad_bf16",
     "tl_context_create",
     "tl_context_destroy",
     "tl_host_tick",
@@ -359,6 +360,8 @@ def load_library() -> C.CDLL:
     ]
     lib.tl_gae.restype = C.c_int
     lib.tl_gae.argtypes = [_p, _p, _p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, _p]
+    lib.tl_cast_pad_bf16.restype = C.c_int
+    lib.tl_cast_pad_bf16.argtypes = [_p, _p, C.c_int64, C.c_int32, C.c_int32, _p]
     lib.tl_context_create.restype = _p
     lib.tl_context_create.argtypes = [C.c_int]
     lib.tl_context_destroy.restype = None

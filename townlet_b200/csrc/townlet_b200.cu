@@ -28,6 +28,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_bf16.h>
+
 #include <atomic>
 #include <mutex>
 #include <type_traits>
@@ -293,6 +295,37 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
+// float32 rows -> bfloat16 rows padded with zeros to a width the tensor-core GEMMs like (a multiple of 64): the cast the
+// policy step does anyway (autocast), fused with the padding that makes the reduction dimension aligned.  One block walks
+// rows; a thread converts one pair of neighbours (round to nearest even, as torch's float -> bfloat16 cast).
+__global__ void __launch_bounds__(256) cast_pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat162* __restrict__ dst,
+                                                            long long n_rows, int width, int padded, int vec4) {
+    if (vec4) {  // width and padded are multiples of 4 and both bases 16 / 8-byte aligned: 16-byte loads, 8-byte stores
+        const int quads = padded >> 2, in_quads = width >> 2;
+        for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+            const float4* in = reinterpret_cast<const float4*>(src + row * width);
+            uint2* out = reinterpret_cast<uint2*>(dst + row * (padded >> 1));
+            for (int j = threadIdx.x; j < quads; j += blockDim.x) {
+                const float4 v = j < in_quads ? __ldg(in + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                out[j] = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+            }
+        }
+        return;
+    }
+    const int pairs = padded >> 1;
+    for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const float* in = src + row * width;
+        __nv_bfloat162* out = dst + row * pairs;
+        for (int j = threadIdx.x; j < pairs; j += blockDim.x) {
+            const int e = 2 * j;
+            const float a = e < width ? __ldg(in + e) : 0.0f;
+            const float b = e + 1 < width ? __ldg(in + e + 1) : 0.0f;
+            out[j] = __floats2bfloat162_rn(a, b);
+        }
+    }
+}
+
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 bool cuda_ok(cudaError_t e, const char* what) {
@@ -598,6 +631,22 @@ int tl_gae(const float* rewards, const float* values, const float* dones, float*
     gae_kernel<<<(n_agents + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, advantages, returns, n_steps,
                                                                         n_agents, bootstrap ? 1 : 0, g, gl);
     if (!cuda_ok(cudaGetLastError(), "gae kernel launch")) return TL_ERR_CUDA;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return TL_OK;
+}
+
+int tl_cast_pad_bf16(const float* src, void* dst, int64_t n_rows, int32_t width, int32_t padded_width, tl_stream_t stream) {
+    if (!src || !dst) return set_error("tl_cast_pad_bf16: NULL pointer"), TL_ERR_ARG;
+    if (n_rows < 0 || width < 1 || padded_width < width || (padded_width & 1))
+        return set_error("tl_cast_pad_bf16: padded_width must be even and >= width"), TL_ERR_ARG;
+    if (n_rows == 0) return TL_OK;
+    const int vec4 = width % 4 == 0 && padded_width % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0;
+    const int items = vec4 ? padded_width / 4 : padded_width / 2;
+    const int threads = items >= 256 ? 256 : (items + 31) / 32 * 32;
+    const long long blocks = n_rows < 148LL * 16 ? n_rows : 148LL * 16;
+    cast_pad_bf16_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat162*)dst, n_rows, width,
+                                                                                padded_width, vec4);
+    if (!cuda_ok(cudaGetLastError(), "cast_pad_bf16 launch")) return TL_ERR_CUDA;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return TL_OK;
 }

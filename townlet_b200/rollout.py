@@ -37,9 +37,73 @@ class PolicyMLP(nn.Module):
         self.value_head = nn.Linear(hidden_dim, 1)
 
     def forward(self, map_tensor: torch.Tensor, features: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        if (
+            map_tensor.is_cuda
+            and map_tensor.dtype == torch.float32
+            and not torch.is_grad_enabled()
+            and torch.is_autocast_enabled()
+            and torch.get_autocast_dtype("cuda") == torch.bfloat16
+        ):
+            return self._forward_bf16_padded(map_tensor, features)
         hidden = torch.cat([self.map_encoder(map_tensor), self.feature_encoder(features)], dim=-1)
         hidden = self.shared(hidden)
         return self.policy_head(hidden), self.value_head(hidden).squeeze(-1)
+
+    def _forward_bf16_padded(self, map_tensor: torch.Tensor, features: torch.Tensor):
+        """The same network for bfloat16-autocast inference.  The two input widths (4·11·11 = 484 and 81) are not
+        multiples of 8, which pushes cuBLAS onto unaligned fall-back kernels; ``tl_cast_pad_bf16`` does the cast autocast
+        would do and pads the rows with zeros in the same pass (the zero columns meet zero weight rows); the shared
+        layer takes the two encoders' outputs through the two halves of its weight (no concatenation) and the policy
+        and value heads are one product."""
+        n = map_tensor.shape[0]
+        flat, feat = self.map_encoder[1].in_features, self.feature_encoder[0].in_features
+        hidden = self.map_encoder[1].out_features
+        actions = self.policy_head.out_features
+        dev = map_tensor.device
+        bf16 = torch.bfloat16
+        if getattr(self, "_pad_key", None) != (n, dev):
+            pad = lambda k: (k + 63) // 64 * 64
+            self._pad_map = torch.empty((n, pad(flat)), dtype=bf16, device=dev)
+            self._pad_feat = torch.empty((n, pad(feat)), dtype=bf16, device=dev)
+            self._pad_key = (n, dev)
+        versions = tuple(p._version for p in self.parameters())
+        if getattr(self, "_pad_versions", None) != versions:
+            def padded_t(weight: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+                w = torch.zeros((rows, cols), dtype=bf16, device=dev)  # [in, out], zero rows / columns for the padding
+                w[: weight.shape[1], : weight.shape[0]] = weight.detach().t().to(bf16)
+                return w
+
+            shared_w = self.shared[0].weight.detach()
+            heads = (actions + 1 + 15) // 16 * 16  # policy logits and the value in ONE product, padded to 16 columns
+            head_w = torch.cat([self.policy_head.weight.detach(), self.value_head.weight.detach()], dim=0)
+            head_b = torch.zeros(heads, dtype=bf16, device=dev)
+            head_b[: actions + 1] = torch.cat([self.policy_head.bias.detach(), self.value_head.bias.detach()]).to(bf16)
+            self._w = {
+                "map": padded_t(self.map_encoder[1].weight, self._pad_map.shape[1], hidden),
+                "feat": padded_t(self.feature_encoder[0].weight, self._pad_feat.shape[1], hidden),
+                # the shared layer reads cat([map, feat]): the two halves of its weight take the two encoders' outputs
+                "shared_map": shared_w[:, :hidden].t().contiguous().to(bf16),
+                "shared_feat": shared_w[:, hidden:].t().contiguous().to(bf16),
+                "heads": padded_t(head_w, hidden, heads),
+                "b_map": self.map_encoder[1].bias.detach().to(bf16),
+                "b_feat": self.feature_encoder[0].bias.detach().to(bf16),
+                "b_shared": self.shared[0].bias.detach().to(bf16),
+                "b_heads": head_b,
+            }
+            self._pad_versions = versions
+        w = self._w
+        lib = capi.load_library()
+        stream = _stream_ptr(dev)
+        src_map = map_tensor.reshape(n, flat)
+        src_feat = features.contiguous()
+        with torch.cuda.device(dev):
+            capi.check(lib.tl_cast_pad_bf16(src_map.data_ptr(), self._pad_map.data_ptr(), n, flat, self._pad_map.shape[1], stream))
+            capi.check(lib.tl_cast_pad_bf16(src_feat.data_ptr(), self._pad_feat.data_ptr(), n, feat, self._pad_feat.shape[1], stream))
+        h_map = torch.relu_(torch.addmm(w["b_map"], self._pad_map, w["map"]))
+        h_feat = torch.relu_(torch.addmm(w["b_feat"], self._pad_feat, w["feat"]))
+        shared = torch.addmm(w["b_shared"], h_map, w["shared_map"]).addmm_(h_feat, w["shared_feat"]).relu_()
+        out = torch.addmm(w["b_heads"], shared, w["heads"])
+        return out[:, :actions], out[:, actions]
 
 
 def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, gamma: float, gae_lambda: float):
@@ -210,9 +274,11 @@ class RolloutCapture:
             else:
                 dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)
             logits, value = self._forward(out.map[t], out.features[t])
-            dist = torch.distributions.Categorical(logits=logits, validate_args=False)  # validation would sync
-            act = dist.sample()
-            actions[t], log_probs[t], values[t] = act, dist.log_prob(act), value
+            # categorical sample by the Gumbel-max trick (argmax of log-probabilities minus log of Exp(1) noise): the
+            # same distribution as Categorical(logits).sample() in a third of the kernels, and no host sync
+            logp = torch.log_softmax(logits, dim=-1)
+            act = (logp - torch.empty_like(logp).exponential_().log_()).argmax(dim=-1)
+            actions[t], log_probs[t], values[t] = act, logp.gather(1, act.unsqueeze(1)).squeeze(1), value
             if self.act_on_world:
                 self._words.copy_(self._action_words(act))
         # bootstrap value: the policy on the last observation (no further tick is simulated)
