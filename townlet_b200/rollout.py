@@ -99,8 +99,14 @@ class PolicyMLP(nn.Module):
         with torch.cuda.device(dev):
             capi.check(lib.tl_cast_pad_bf16(src_map.data_ptr(), self._pad_map.data_ptr(), n, flat, self._pad_map.shape[1], stream))
             capi.check(lib.tl_cast_pad_bf16(src_feat.data_ptr(), self._pad_feat.data_ptr(), n, feat, self._pad_feat.shape[1], stream))
-        h_map = torch.relu_(torch.addmm(w["b_map"], self._pad_map, w["map"]))
-        h_feat = torch.relu_(torch.addmm(w["b_feat"], self._pad_feat, w["feat"]))
+        # bias + ReLU in the GEMM epilogue (cuBLASLt) instead of a separate pass over the activations
+        fused = getattr(torch, "_addmm_activation", None)  # cuBLASLt epilogue; plain addmm + relu_ where torch lacks it
+        if fused is not None:
+            h_map = fused(w["b_map"], self._pad_map, w["map"])
+            h_feat = fused(w["b_feat"], self._pad_feat, w["feat"])
+        else:
+            h_map = torch.relu_(torch.addmm(w["b_map"], self._pad_map, w["map"]))
+            h_feat = torch.relu_(torch.addmm(w["b_feat"], self._pad_feat, w["feat"]))
         shared = torch.addmm(w["b_shared"], h_map, w["shared_map"]).addmm_(h_feat, w["shared_feat"]).relu_()
         out = torch.addmm(w["b_heads"], shared, w["heads"])
         return out[:, :actions], out[:, actions]
