@@ -295,16 +295,17 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                         if (n_t != n_t0) p.b.tie_count[a] = (uint8_t)n_t;
                     }
                     const bool riv_moved = __any_sync(FULL, n_riv != n_riv0), tie_moved = __any_sync(FULL, n_t != n_t0);
-                    const bool tie_decays = p.dyn.trust_decay > 0.0 || p.dyn.familiarity_decay > 0.0 || p.dyn.tie_rivalry_decay > 0.0;
+                    // a table goes back when its values decay or an entry moved; an untouched table stays as it is
+                    const bool w_score = p.dyn.rivalry_decay_per_tick != 0.0 || riv_moved;
+                    const bool w_trust = p.dyn.trust_decay > 0.0 || tie_moved, w_fam = p.dyn.familiarity_decay > 0.0 || tie_moved;
+                    const bool w_riv = p.dyn.tie_rivalry_decay > 0.0 || tie_moved;
                     __syncwarp();
 #pragma unroll 2
                     for (int i = lane; i < n_rows; i += 32) {
-                        p.b.riv_score[r0 + i] = s_score[i];
-                        if (tie_decays || tie_moved) {
-                            p.b.tie_trust[r0 + i] = s_trust[i];
-                            p.b.tie_fam[r0 + i] = s_fam[i];
-                            p.b.tie_riv[r0 + i] = s_riv[i];
-                        }
+                        if (w_score) p.b.riv_score[r0 + i] = s_score[i];
+                        if (w_trust) p.b.tie_trust[r0 + i] = s_trust[i];
+                        if (w_fam) p.b.tie_fam[r0 + i] = s_fam[i];
+                        if (w_riv) p.b.tie_riv[r0 + i] = s_riv[i];
                     }
                     if (riv_moved || tie_moved) {
 #pragma unroll 2
