@@ -138,3 +138,48 @@ def test_reward_spec_struct_tables() -> None:
     assert p.need_mult[2][1] == 1.1 and p.need_mult[3][2] == 0.9 and p.need_mult[4][0] == 0.95 and p.need_mult[1][0] == 1.0
     assert p.reward_bias[2][0] == 1.2 and p.reward_bias[3][1] == 1.25 and p.reward_bias[4][2] == 1.1
     assert p.decay_personality == 1 and p.block_window == 10 and p.faint_threshold == 0.03
+
+
+# ---- property tests (hypothesis) --------------------------------------------------------------
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(0, 1023), st.integers(0, 1023), st.integers(0, 2), st.integers(0, 4), st.integers(0, 4), st.booleans(), st.booleans())
+def test_entity_word_fields_roundtrip(x, y, kind, ltype, ctype, lm, tile) -> None:
+    from townlet_b200.soa import pack_entity
+
+    w = int(pack_entity(x, y, kind, ltype, ctype, int(lm), int(tile)))
+    assert (w & 1023, (w >> 10) & 1023, (w >> 20) & 3, (w >> 22) & 7, (w >> 25) & 15, (w >> 29) & 1, (w >> 30) & 1) == (
+        x, y, kind, ltype, ctype, int(lm), int(tile))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(0, 15), st.booleans(), st.booleans(), st.integers(0, 1023), st.integers(0, 1023), st.integers(0, 63))
+def test_action_word_fields_roundtrip(kind, success, has_pos, x, y, duration) -> None:
+    from townlet_b200.params import pack_actions
+
+    w = int(pack_actions(kind, int(success), int(has_pos), x, y, duration))
+    assert (w & 15, (w >> 4) & 1, (w >> 5) & 1, (w >> 6) & 1023, (w >> 16) & 1023, w >> 26) == (
+        kind, int(success), int(has_pos), x, y, duration)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 9), st.integers(1, 7), st.integers(1, 5), st.data())
+def test_town_slices_partition_any_batch(n_towns, agents, world_size, data) -> None:
+    """Any split into contiguous blocks of towns keeps every field, and the blocks validate on their own."""
+    from townlet_b200.sharding import shard_batch
+    from townlet_b200.synth import assemble, synth_town
+
+    towns = [synth_town(data.draw(st.integers(0, 500)), 16, data.draw(st.integers(1, agents))) for _ in range(n_towns)]
+    full = assemble(towns, ObsSpec())
+    parts = [shard_batch(full, r, world_size) for r in range(world_size)]
+    assert sum(p.n_towns for p in parts) == full.n_towns
+    for name in ("pos", "flags", "ent", "tie_count", "riv_score", "town_tick"):
+        assert np.array_equal(np.concatenate([np.asarray(getattr(p, name)).reshape(-1) for p in parts]),
+                              np.asarray(getattr(full, name)).reshape(-1)), name
+    assert np.array_equal(np.concatenate([p.needs for p in parts], axis=1), full.needs)
+    for p in parts:
+        if p.n_towns:
+            p.validate()
