@@ -18,6 +18,17 @@
 //
 // One block barrier per pass hands the double-buffered feature rows to a
 // coalesced 16-byte sweep done by all four warps.
+//
+// Inputs of the thread-per-agent roles arrive by cp.async: the relation rows of
+// a pass (social) and the ~20 per-agent scalars (state) are requested at the end
+// of the previous pass, after that pass's stores to the same arrays, so their
+// global-memory latency overlaps the barrier wait and the sweep.  They are still
+// re-read from global memory every pass; nothing is kept across ticks.
+//
+// Template parameters: VARIANT (hybrid / full / compact), WT (compile-time
+// window for the common sizes, 0 = any odd window up to 21), WORLD (the launch
+// runs the world-dynamics phases — action words, ledger decay — whose state is
+// rewritten inside the launch and therefore read with plain loads).
 
 // -DTL_ROLE_TIMING: two CTAs print the cycles each role spends per tick in its role body and at the pass
 // barrier + sweep (scripts/role_timing.sh; never part of the shipped library)
