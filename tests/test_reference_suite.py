@@ -64,3 +64,22 @@ def test_reference_hot_path_tests_pass_with_the_dropins(tmp_path) -> None:
     failures = re.findall(r"^FAILED (\S+)", proc.stdout, flags=re.M)
     assert all(KNOWN_REFERENCE_FAILURE in name for name in failures), tail
     assert failed <= 1 and passed >= 160, tail
+
+
+@pytest.mark.skipif(not os.environ.get("TL_REFSUITE_FULL"), reason="set TL_REFSUITE_FULL=1: the reference's whole suite takes ~3 min")
+def test_whole_reference_suite_passes_with_the_dropins(tmp_path) -> None:
+    """Every test file of the reference (as its CI runs them: ``-k "not rollout_capture"``, .github/workflows/ci.yml)
+    with the drop-in classes patched in — 893 passed, 2 skipped when this was written."""
+    work = tmp_path / "ref"
+    shutil.copytree(REF, work, symlinks=True)
+    os.system(f"chmod -R u+w {work}")
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([str(HERE / "refsuite"), str(work / "src"), env.get("PYTHONPATH", "")])
+    env.setdefault("TL_REFSUITE_ENGINE", "oracle")
+    proc = subprocess.run(
+        [sys.executable, "-m", "pytest", "-p", "b200_plugin", "-p", "no:cacheprovider", "-o", "addopts=", "-q",
+         "--deselect", f"tests/test_observation_builder_parity.py::{KNOWN_REFERENCE_FAILURE}", "-k", "not rollout_capture", "tests"],
+        cwd=work, env=env, capture_output=True, text=True, timeout=2400,
+    )
+    summary = re.search(r"(?:(\d+) failed, )?(\d+) passed", proc.stdout)
+    assert summary and not summary.group(1) and int(summary.group(2)) >= 850, proc.stdout[-3000:]
