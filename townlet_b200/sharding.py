@@ -5,7 +5,9 @@ Towns never interact (every accessor of the path is scoped to one
 the tick needs NO collective.  The only communication is the optional
 end-of-rollout statistics exchange: an ``all_reduce(sum)`` of a small per-rank
 accumulator and / or an ``all_gather`` of per-town KPI rows — NCCL over NVLink
-on GPUs, gloo in the CPU tests.
+on GPUs, gloo in the CPU tests.  The reference itself has nothing distributed (one process, one
+``SimulationLoop``, src/townlet/core/sim_loop.py:632); its per-town KPIs are the telemetry publisher's
+(src/townlet/telemetry/publisher.py:2671-2694), which is what the gathered rows feed.
 """
 
 from __future__ import annotations
