@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 2
+#define TL_ABI_VERSION 3
 
 #define TL_N_NEEDS 3          /* hunger, hygiene, energy (snapshot.py:15) */
 #define TL_MAX_EDGES 8        /* upper bound for max_edges (ledger capacity) */
@@ -354,6 +354,14 @@ typedef struct TlObsOut {
     int64_t map_tick_stride;      /* elements between consecutive ticks (0 = overwrite) */
     int64_t features_tick_stride;
     int64_t summary_tick_stride;
+    /* ABI v3, device entry points only (tl_host_tick ignores it): optional bfloat16 mirror of `map` for a policy
+     * that reads the observation right after the tick (the reference casts per agent under
+     * autocast, policy/runner.py:444-488).  Row a of tick t = the flattened tile of agent a, round-to-nearest-even,
+     * zero-padded to map_bf16_row elements (a multiple of 8, >= C*W*W); the base is 16-byte aligned. */
+    uint16_t* map_bf16;            /* [N][map_bf16_row]; may be NULL */
+    int64_t map_bf16_tick_stride;  /* elements between consecutive ticks (0 = overwrite), a multiple of 8 */
+    int32_t map_bf16_row;
+    int32_t reserved0;
 } TlObsOut;
 
 typedef struct TlRewardOut {

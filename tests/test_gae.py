@@ -218,3 +218,111 @@ def test_cast_pad_bf16_and_the_padded_policy_forward() -> None:
     err_plain = (plain_logits.float() - exact_logits).abs().max().item()
     assert err_padded < 2 * err_plain + 1e-3, (err_padded, err_plain)
     assert (value.float() - exact_value).abs().max().item() < 0.02
+
+
+def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], three_dim: bool, n_ticks: int = 3) -> None:
+    import torch
+
+    from townlet_b200 import capi
+    from townlet_b200.engine import DeviceTownBatch
+    from townlet_b200.params import DynamicsSpec, ObsSpec, RewardSpec, pack_actions
+    from townlet_b200.synth import synth_batch
+
+    for key, value in env.items():
+        monkeypatch.setenv(key, value)
+    obs, rew = ObsSpec(variant=variant), RewardSpec(fuse_faint=True)
+    # stacked agents, objects and reserved tiles inside the windows: every patch kind is written
+    batch = synth_batch(37, 16, 9, obs)
+    dev = DeviceTownBatch(batch, obs, rew, dyn=DynamicsSpec() if world else None)
+    out = dev.alloc_outputs(capi.TL_PHASE_ALL, n_ticks)
+    flat = int(np.prod(obs.map_shape))
+    row = (flat + 63) // 64 * 64
+    shape = (n_ticks, batch.n_agents, row) if three_dim else (batch.n_agents, row)
+    out.map_bf16 = torch.full(shape, 7.0, dtype=torch.bfloat16, device="cuda")
+    if world:
+        rng = np.random.default_rng(5)
+        n = batch.n_agents
+        words = pack_actions(np.full(n, 1), 1, np.ones(n, bool), rng.integers(0, 16, n), rng.integers(0, 16, n), 1)
+        actions = torch.from_numpy(words.view(np.int32)).cuda()
+        dev.tick(out, capi.TL_PHASE_WORLD, n_ticks, actions=actions)
+    else:
+        dev.tick(out, capi.TL_PHASE_ALL, n_ticks)
+    torch.cuda.synchronize()
+    want = out.map.reshape(n_ticks, batch.n_agents, flat).to(torch.bfloat16)
+    got = out.map_bf16 if three_dim else out.map_bf16[None]
+    want = want if three_dim else want[-1:]
+    assert want.float().sum().item() > 2 * batch.n_agents  # more than the self cells
+    assert torch.equal(got[..., :flat].view(torch.int16), want.view(torch.int16))
+    assert not got[..., flat:].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize(
+    "variant,world,env,three_dim",
+    [
+        ("hybrid", False, {}, True),  # written by the tiles role
+        ("hybrid", False, {}, False),  # one buffer overwritten every tick
+        ("hybrid", True, {}, True),  # world-dynamics instantiation, agents moved by action words
+        ("hybrid", False, {"TL_NO_MIRROR_FUSE": "1"}, True),  # cast pass after the launch
+        ("hybrid", False, {"TL_MODE": "grid"}, True),
+        ("hybrid", False, {"TL_GENERIC": "1"}, False),
+        ("full", False, {}, True),  # path channels: round to nearest even
+        ("compact", False, {}, True),
+    ],
+)
+def test_bf16_mirror_of_the_map_equals_the_cast_of_the_float32_map(variant, world, env, three_dim, monkeypatch) -> None:
+    """TlObsOut.map_bf16 (ABI v3): every kernel form leaves the padded bfloat16 rows torch's cast of the float32 map gives."""
+    _mirror_case(variant, world, monkeypatch, env, three_dim)
+
+
+@pytest.mark.gpu
+def test_bf16_mirror_arguments_are_validated() -> None:
+    import torch
+
+    from townlet_b200 import capi
+    from townlet_b200.engine import DeviceTownBatch
+    from townlet_b200.params import ObsSpec, RewardSpec
+    from townlet_b200.synth import synth_batch
+
+    obs = ObsSpec()
+    batch = synth_batch(3, 16, 4, obs)
+    dev = DeviceTownBatch(batch, obs, RewardSpec())
+    out = dev.alloc_outputs(capi.TL_PHASE_ALL, 1)
+    for shape in ((batch.n_agents, 480), (batch.n_agents, 490)):  # narrower than the tile / not a multiple of 8
+        out.map_bf16 = torch.zeros(shape, dtype=torch.bfloat16, device="cuda")
+        with pytest.raises(capi.TownletB200Error, match="map_bf16"):
+            dev.tick(out, capi.TL_PHASE_ALL, 1)
+    out.map_bf16 = torch.zeros((batch.n_agents, 512), dtype=torch.float16, device="cuda")
+    with pytest.raises(capi.TownletB200Error, match="map_bf16"):
+        dev.tick(out, capi.TL_PHASE_ALL, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act_on_world", [False, True])
+def test_rollout_with_the_kernel_written_bf16_map_equals_the_cast_pass(act_on_world) -> None:
+    """The bfloat16 policy step reads the rows the tick kernel wrote instead of casting the float32 map itself: same
+    rollout bit for bit (same seeds), eager and graphed."""
+    import torch
+
+    from townlet_b200.engine import DeviceTownBatch
+    from townlet_b200.params import DynamicsSpec, ObsSpec, RewardSpec
+    from townlet_b200.rollout import PolicyMLP, RolloutCapture
+    from townlet_b200.synth import synth_batch
+
+    obs, rew = ObsSpec(), RewardSpec(fuse_faint=True)
+    torch.manual_seed(11)
+    policy = PolicyMLP(obs.n_features, obs.map_shape, action_dim=9)
+    rollouts = []
+    for fuse in (False, True):
+        dev = DeviceTownBatch(synth_batch(20, 24, 8, obs), obs, rew, dyn=DynamicsSpec() if act_on_world else None)
+        cap = RolloutCapture(dev, policy, act_on_world=act_on_world)
+        cap.fuse_map_cast = fuse
+        torch.manual_seed(23)
+        ro = cap.capture(6)
+        torch.cuda.synchronize()
+        assert (cap._map_bf16 is not None) == fuse
+        rollouts.append(ro)
+    a, b = rollouts
+    for name in ("map", "features", "rewards", "values", "actions", "log_probs", "advantages", "returns"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert len(torch.unique(b.actions)) > 1

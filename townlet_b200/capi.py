@@ -18,7 +18,7 @@ CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtownlet_b200.so"
 INCLUDE = ROOT / "include"
 
-TL_ABI_VERSION = 2
+TL_ABI_VERSION = 3
 TL_N_NEEDS = 3
 TL_MAX_EDGES = 8
 TL_MAX_SOCIAL_SLOTS = 8
@@ -210,6 +210,10 @@ class TlObsOut(C.Structure):
         ("map_tick_stride", C.c_int64),
         ("features_tick_stride", C.c_int64),
         ("summary_tick_stride", C.c_int64),
+        ("map_bf16", _p),
+        ("map_bf16_tick_stride", C.c_int64),
+        ("map_bf16_row", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

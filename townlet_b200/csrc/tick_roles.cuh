@@ -28,7 +28,10 @@
 // Template parameters: VARIANT (hybrid / full / compact), WT (compile-time
 // window for the common sizes, 0 = any odd window up to 21), WORLD (the launch
 // runs the world-dynamics phases — action words, ledger decay — whose state is
-// rewritten inside the launch and therefore read with plain loads).
+// rewritten inside the launch and therefore read with plain loads), MIRROR (the
+// tiles role also writes the bfloat16 mirror TlObsOut.map_bf16: a second, padded
+// template row and one 2-byte store beside every patch; static hybrid window only,
+// every other form takes the cast pass after the launch).
 
 // -DTL_ROLE_TIMING: two CTAs print the cycles each role spends per tick in its role body and at the pass
 // barrier + sweep (scripts/role_timing.sh; never part of the shipped library)
@@ -44,7 +47,7 @@
 constexpr int kTileWarps = TL_TILE_WARPS;  // warps in the tiles role
 constexpr int kRoleWarps = 2 + kTileWarps;
 
-template <int VARIANT, int WT, bool WORLD>
+template <int VARIANT, int WT, bool WORLD, bool MIRROR = false>
 __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick_kernel_roles(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);  // [2][chunk * F + 4]
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
 
     const TlObsParams& o = p.obs;
     constexpr bool kStatic = WT > 0;
+    static_assert(!MIRROR || (kStatic && VARIANT == TL_VARIANT_HYBRID), "the bfloat16 mirror is built for the static hybrid window");
     constexpr int kChannels = VARIANT == TL_VARIANT_HYBRID ? 4 : (VARIANT == TL_VARIANT_FULL ? 6 : 5);
     constexpr int kMapElems = kStatic ? kChannels * WT * WT : 4;
     const int W = kStatic ? WT : o.window;
@@ -358,8 +362,12 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 if (do_actions && active) pw = moved_pos(pw, __ldg(act + a));
                 int my_others = 0, my_objs = 0, my_res = 0, my_d2 = 0;
                 float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)(c_begin + parity) * map_elems;
+                // MIRROR: the same tile as bfloat16 (0 -> 0x0000, 1 -> 0x3f80: the cast is exact), rows padded with zeros
+                const int brow = MIRROR ? p.oo.map_bf16_row : 0;
+                uint16_t* brow_g = MIRROR ? p.oo.map_bf16 + (size_t)it * p.oo.map_bf16_tick_stride + (size_t)(c_begin + parity) * brow
+                                          : nullptr;
 #pragma unroll 1
-                for (int i = parity; i < c_n; i += kTileWarps, mrow_g += kTileWarps * map_elems) {
+                for (int i = parity; i < c_n; i += kTileWarps, mrow_g += kTileWarps * map_elems, brow_g += MIRROR ? kTileWarps * brow : 0) {
                     const int32_t pwi = __shfl_sync(FULL, pw, i);
                     const int cxi = pos_x(pwi), cyi = pos_y(pwi);
                     const int eb = __shfl_sync(FULL, town_ebeg, i), ee = __shfl_sync(FULL, town_eend, i);
@@ -409,6 +417,17 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                         const int tail0 = head + (nvec << 2);
                         if (lane < map_elems - tail0) mrow_g[tail0 + lane] = t[tail0 + lane];
                     }
+                    if (MIRROR) {  // padded bfloat16 row: zeros and the self cell, 16-byte stores of 8 elements
+                        uint4* b4 = reinterpret_cast<uint4*>(brow_g);
+                        const int nb = brow >> 3;
+                        const unsigned one = 0x3f80u << (16 * (centre_tile & 1));
+                        const int cw = (centre_tile & 7) >> 1;
+#pragma unroll 1
+                        for (int v = lane; v < nb; v += 32) {
+                            const unsigned self = v == (centre_tile >> 3) ? one : 0u;
+                            b4[v] = make_uint4(cw == 0 ? self : 0u, cw == 1 ? self : 0u, cw == 2 ? self : 0u, cw == 3 ? self : 0u);
+                        }
+                    }
                     __syncwarp();  // orders the template stores before the patches of other lanes
 
                     // ---- patches: one entity per lane (cache.py:16-41 + map.py:80-125) ----
@@ -456,6 +475,11 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                             if (is_agent) mrow_g[W2 + tile] = 1.0f;  // includes the observer (map.py:109-110)
                             if (is_obj) mrow_g[2 * W2 + tile] = 1.0f;
                             if (is_res) mrow_g[3 * W2 + tile] = 1.0f;
+                            if (MIRROR) {
+                                if (is_agent) brow_g[W2 + tile] = 0x3f80;
+                                if (is_obj) brow_g[2 * W2 + tile] = 0x3f80;
+                                if (is_res) brow_g[3 * W2 + tile] = 0x3f80;
+                            }
                         }
                     };
                     // towns of up to 32 entities (the common case) need one pass and one branch

@@ -327,6 +327,19 @@ __global__ void __launch_bounds__(256) cast_pad_bf16_kernel(const float* __restr
 }
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
+bool cuda_ok(cudaError_t e, const char* what);
+
+int cast_pad_rows(const float* src, void* dst, int64_t n_rows, int32_t width, int32_t padded_width, cudaStream_t stream) {
+    if (n_rows == 0) return TL_OK;
+    const int vec4 = width % 4 == 0 && padded_width % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0;
+    const int items = vec4 ? padded_width / 4 : padded_width / 2;
+    const int threads = items >= 256 ? 256 : (items + 31) / 32 * 32;
+    const long long blocks = n_rows < 148LL * 16 ? n_rows : 148LL * 16;
+    cast_pad_bf16_kernel<<<(unsigned)blocks, threads, 0, stream>>>(src, (__nv_bfloat162*)dst, n_rows, width, padded_width, vec4);
+    if (!cuda_ok(cudaGetLastError(), "cast_pad_bf16 launch")) return TL_ERR_CUDA;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return TL_OK;
+}
 
 bool cuda_ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
@@ -374,6 +387,11 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
             !obs->nearest_lut || !obs->embed_lut || (obs->variant == TL_VARIANT_FULL && !obs->path_lut))
             return set_error("a look-up table pointer is NULL"), TL_ERR_ARG;
         if (obs->ticks_per_day < 1 || obs->max_slots < 1) return set_error("ticks_per_day / max_slots < 1"), TL_ERR_ARG;
+        if (oo->map_bf16) {
+            if (oo->map_bf16_row < obs->n_channels * obs->window * obs->window || (oo->map_bf16_row & 7) ||
+                (oo->map_bf16_tick_stride & 7) || oo->map_bf16_tick_stride < 0 || ((uintptr_t)oo->map_bf16 & 15))
+                return set_error("map_bf16: rows are 16-byte aligned, a multiple of 8 elements and at least C*W*W wide"), TL_ERR_ARG;
+        }
     }
     (void)ro;
     return TL_OK;
@@ -557,6 +575,11 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return TL_OK;
     };
+    // The bfloat16 mirror of the map: written by the tiles role itself in the static hybrid form (TL_NO_MIRROR_FUSE
+    // keeps it out, for A/B runs), by one cast pass per tick after the launch in every other form.
+    const bool want_mirror = do_obs && oo->map_bf16 != nullptr;
+    bool mirror_in_kernel = false;
+    auto dispatch = [&]() -> int {
     if (kp.mode == 0) {
         const bool generic = getenv("TL_GENERIC") != nullptr;  // force the runtime-window form (tests)
         const int win = do_obs ? kp.obs.window : 0;
@@ -568,6 +591,11 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         using std::integral_constant;
         switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
             case TL_VARIANT_HYBRID:
+                if (win == 11 && !generic && want_mirror && !getenv("TL_NO_MIRROR_FUSE")) {
+                    mirror_in_kernel = true;
+                    if (world) return run(tick_kernel_roles<TL_VARIANT_HYBRID, 11, true, true>);
+                    return run(tick_kernel_roles<TL_VARIANT_HYBRID, 11, false, true>);
+                }
                 if (win == 11 && !generic) return pick(integral_constant<int, TL_VARIANT_HYBRID>{}, integral_constant<int, 11>{});
                 return pick(integral_constant<int, TL_VARIANT_HYBRID>{}, integral_constant<int, 0>{});
             case TL_VARIANT_FULL:
@@ -586,6 +614,15 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         case TL_VARIANT_COMPACT: return run(tick_kernel<TL_VARIANT_COMPACT>);
         default: return set_error("unknown variant"), TL_ERR_ARG;
     }
+    };
+    rc = dispatch();
+    if (rc != TL_OK || !want_mirror || mirror_in_kernel) return rc;
+    for (int it = 0; it < n_ticks; ++it) {
+        rc = cast_pad_rows(oo->map + (size_t)it * oo->map_tick_stride, oo->map_bf16 + (size_t)it * oo->map_bf16_tick_stride,
+                           b->n_agents, map_elems, oo->map_bf16_row, stream);
+        if (rc != TL_OK) return rc;
+    }
+    return TL_OK;
 }
 
 }  // namespace
@@ -639,16 +676,7 @@ int tl_cast_pad_bf16(const float* src, void* dst, int64_t n_rows, int32_t width,
     if (!src || !dst) return set_error("tl_cast_pad_bf16: NULL pointer"), TL_ERR_ARG;
     if (n_rows < 0 || width < 1 || padded_width < width || (padded_width & 1))
         return set_error("tl_cast_pad_bf16: padded_width must be even and >= width"), TL_ERR_ARG;
-    if (n_rows == 0) return TL_OK;
-    const int vec4 = width % 4 == 0 && padded_width % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0;
-    const int items = vec4 ? padded_width / 4 : padded_width / 2;
-    const int threads = items >= 256 ? 256 : (items + 31) / 32 * 32;
-    const long long blocks = n_rows < 148LL * 16 ? n_rows : 148LL * 16;
-    cast_pad_bf16_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat162*)dst, n_rows, width,
-                                                                                padded_width, vec4);
-    if (!cuda_ok(cudaGetLastError(), "cast_pad_bf16 launch")) return TL_ERR_CUDA;
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return TL_OK;
+    return cast_pad_rows(src, dst, n_rows, width, padded_width, (cudaStream_t)stream);
 }
 
 int tl_obs_build(const TlTownBatch* batch, const TlObsParams* obs, const TlObsOut* out, tl_stream_t stream) {
@@ -875,6 +903,7 @@ int tl_host_tick_world(TlContext* ctx, const TlTownBatch* hb, const TlObsParams*
     if (do_obs) {
         const size_t me = (size_t)obs->n_channels * obs->window * obs->window;
         doo = *hoo;
+        doo.map_bf16 = nullptr;  // device entry points only
         auto span_elems = [&](int64_t stride, size_t per_tick) { return (nt - 1) * (size_t)stride + per_tick; };
         o_map = add_out(hoo->map, span_elems(hoo->map_tick_stride, N * me) * 4);
         o_feat = add_out(hoo->features, span_elems(hoo->features_tick_stride, N * (size_t)obs->n_features) * 4);

@@ -42,6 +42,9 @@ class TickOutputs:
     comps: torch.Tensor | None = None
     terminated: torch.Tensor | None = None
     kpi: torch.Tensor | None = None
+    # optional bfloat16 mirror of ``map`` for an in-loop policy: ``[ticks, N, row]`` (or ``[N, row]``, overwritten every
+    # tick), rows zero-padded to a multiple of 8 elements (``TlObsOut.map_bf16``, device launches only)
+    map_bf16: torch.Tensor | None = None
 
 
 class DeviceTownBatch:
@@ -155,6 +158,14 @@ class DeviceTownBatch:
         bind(oo, "map", out.map)
         bind(oo, "features", out.features)
         bind(oo, "summary", out.summary)
+        if out.map_bf16 is not None:
+            mirror = out.map_bf16
+            if mirror.dtype != torch.bfloat16 or not mirror.is_contiguous() or mirror.dim() not in (2, 3):
+                raise capi.TownletB200Error("map_bf16 must be a contiguous bfloat16 tensor [N, row] or [ticks, N, row]")
+            view = mirror[tick0:] if mirror.dim() == 3 else mirror
+            oo.map_bf16 = C.c_void_p(view.data_ptr())
+            oo.map_bf16_tick_stride = int(mirror.stride(0)) if mirror.dim() == 3 else 0
+            oo.map_bf16_row = int(mirror.shape[-1])
         bind(ro, "reward", out.reward)
         bind(ro, "comps", out.comps)
         bind(ro, "terminated", out.terminated)

@@ -36,7 +36,10 @@ class PolicyMLP(nn.Module):
         self.policy_head = nn.Linear(hidden_dim, action_dim)
         self.value_head = nn.Linear(hidden_dim, 1)
 
-    def forward(self, map_tensor: torch.Tensor, features: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    def forward(self, map_tensor: torch.Tensor, features: torch.Tensor,
+                map_bf16: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+        """``map_bf16``: the padded bfloat16 rows of ``map_tensor`` when the tick kernel already wrote them
+        (``TickOutputs.map_bf16``, see ``padded_map_buffer``); the bfloat16 path then skips its cast pass over the map."""
         if (
             map_tensor.is_cuda
             and map_tensor.dtype == torch.float32
@@ -44,12 +47,17 @@ class PolicyMLP(nn.Module):
             and torch.is_autocast_enabled()
             and torch.get_autocast_dtype("cuda") == torch.bfloat16
         ):
-            return self._forward_bf16_padded(map_tensor, features)
+            return self._forward_bf16_padded(map_tensor, features, map_bf16)
         hidden = torch.cat([self.map_encoder(map_tensor), self.feature_encoder(features)], dim=-1)
         hidden = self.shared(hidden)
         return self.policy_head(hidden), self.value_head(hidden).squeeze(-1)
 
-    def _forward_bf16_padded(self, map_tensor: torch.Tensor, features: torch.Tensor):
+    def padded_map_buffer(self, n: int, device: torch.device) -> torch.Tensor:
+        """``[n, pad64(C·W·W)]`` bfloat16 rows the tick kernel can fill (``TickOutputs.map_bf16``)."""
+        flat = self.map_encoder[1].in_features
+        return torch.zeros((n, (flat + 63) // 64 * 64), dtype=torch.bfloat16, device=device)
+
+    def _forward_bf16_padded(self, map_tensor: torch.Tensor, features: torch.Tensor, map_bf16: torch.Tensor | None = None):
         """The same network for bfloat16-autocast inference.  The two input widths (4·11·11 = 484 and 81) are not
         multiples of 8, which pushes cuBLAS onto unaligned fall-back kernels; ``tl_cast_pad_bf16`` does the cast autocast
         would do and pads the rows with zeros in the same pass (the zero columns meet zero weight rows); the shared
@@ -96,16 +104,22 @@ class PolicyMLP(nn.Module):
         stream = _stream_ptr(dev)
         src_map = map_tensor.reshape(n, flat)
         src_feat = features.contiguous()
+        pad_map = self._pad_map
+        if map_bf16 is not None:
+            if map_bf16.shape != pad_map.shape or map_bf16.dtype != bf16 or not map_bf16.is_contiguous():
+                raise ValueError("map_bf16 must be the contiguous [n, pad64(C*W*W)] bfloat16 rows of map_tensor")
+            pad_map = map_bf16
         with torch.cuda.device(dev):
-            capi.check(lib.tl_cast_pad_bf16(src_map.data_ptr(), self._pad_map.data_ptr(), n, flat, self._pad_map.shape[1], stream))
+            if map_bf16 is None:
+                capi.check(lib.tl_cast_pad_bf16(src_map.data_ptr(), pad_map.data_ptr(), n, flat, pad_map.shape[1], stream))
             capi.check(lib.tl_cast_pad_bf16(src_feat.data_ptr(), self._pad_feat.data_ptr(), n, feat, self._pad_feat.shape[1], stream))
         # bias + ReLU in the GEMM epilogue (cuBLASLt) instead of a separate pass over the activations
         fused = getattr(torch, "_addmm_activation", None)  # cuBLASLt epilogue; plain addmm + relu_ where torch lacks it
         if fused is not None:
-            h_map = fused(w["b_map"], self._pad_map, w["map"])
+            h_map = fused(w["b_map"], pad_map, w["map"])
             h_feat = fused(w["b_feat"], self._pad_feat, w["feat"])
         else:
-            h_map = torch.relu_(torch.addmm(w["b_map"], self._pad_map, w["map"]))
+            h_map = torch.relu_(torch.addmm(w["b_map"], pad_map, w["map"]))
             h_feat = torch.relu_(torch.addmm(w["b_feat"], self._pad_feat, w["feat"]))
         shared = torch.addmm(w["b_shared"], h_map, w["shared_map"]).addmm_(h_feat, w["shared_feat"]).relu_()
         out = torch.addmm(w["b_heads"], shared, w["heads"])
@@ -214,6 +228,8 @@ class RolloutCapture:
         self.gamma, self.gae_lambda = gamma, gae_lambda
         self.autocast_dtype = autocast_dtype
         self.act_on_world = act_on_world
+        self.fuse_map_cast = True  # False: the policy step casts the float32 map itself (A/B runs, tests)
+        self._map_bf16: torch.Tensor | None = None
         if act_on_world:
             if dev.dyn is None:
                 raise capi.TownletB200Error("act_on_world needs a device batch built with a DynamicsSpec")
@@ -235,13 +251,22 @@ class RolloutCapture:
         return kind | (is_move << 5) | (nx << 6) | (ny << 16) | (1 << 26)
 
     @torch.no_grad()
-    def _forward(self, map_t: torch.Tensor, feat_t: torch.Tensor):
+    def _forward(self, map_t: torch.Tensor, feat_t: torch.Tensor, map_bf16: torch.Tensor | None = None):
         if self.autocast_dtype is not None:
             with torch.autocast("cuda", dtype=self.autocast_dtype):
-                logits, value = self.policy(map_t, feat_t)
+                logits, value = self.policy(map_t, feat_t, map_bf16) if map_bf16 is not None else self.policy(map_t, feat_t)
         else:
             logits, value = self.policy(map_t, feat_t)
         return logits.float(), value.float()
+
+    def _mirror(self) -> torch.Tensor | None:
+        """The padded bfloat16 rows the tick kernel writes beside the float32 map when the policy is the bfloat16
+        ``PolicyMLP`` (one buffer, overwritten every tick: the policy consumes it before the next tick runs)."""
+        if not (isinstance(self.policy, PolicyMLP) and self.autocast_dtype == torch.bfloat16 and self.fuse_map_cast):
+            return None
+        if self._map_bf16 is None:
+            self._map_bf16 = self.policy.padded_map_buffer(self.dev.n_agents, self.dev.device)
+        return self._map_bf16
 
     def build_graph(self, n_ticks: int, out: TickOutputs | None = None) -> "GraphedRollout":
         """Capture the whole ``n_ticks`` rollout (tick launches + policy steps + GAE) in ONE CUDA graph.
@@ -272,6 +297,8 @@ class RolloutCapture:
         values = torch.empty((n_ticks + 1, n), dtype=torch.float32, device=dev.device)
         actions = torch.empty((n_ticks, n), dtype=torch.int64, device=dev.device)
         log_probs = torch.empty((n_ticks, n), dtype=torch.float32, device=dev.device)
+        mirror = self._mirror()
+        caller_mirror, out.map_bf16 = out.map_bf16, mirror
         for t in range(n_ticks):
             # obs / reward / done of tick t land in slot t; with act_on_world the tick first applies the action words
             # the policy chose on the previous observation (moves), then decays needs and ledgers
@@ -279,7 +306,7 @@ class RolloutCapture:
                 dev.tick(out, capi.TL_PHASE_WORLD, 1, tick0=t, actions=self._words)
             else:
                 dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)
-            logits, value = self._forward(out.map[t], out.features[t])
+            logits, value = self._forward(out.map[t], out.features[t], mirror)
             # categorical sample by the Gumbel-max trick (argmax of log-probabilities minus log of Exp(1) noise): the
             # same distribution as Categorical(logits).sample() in a third of the kernels, and no host sync
             logp = torch.log_softmax(logits, dim=-1)
@@ -287,6 +314,7 @@ class RolloutCapture:
             actions[t], log_probs[t], values[t] = act, logp.gather(1, act.unsqueeze(1)).squeeze(1), value
             if self.act_on_world:
                 self._words.copy_(self._action_words(act))
+        out.map_bf16 = caller_mirror
         # bootstrap value: the policy on the last observation (no further tick is simulated)
         values[n_ticks] = values[n_ticks - 1] if n_ticks else 0.0
         dones = out.terminated[:n_ticks].float()
