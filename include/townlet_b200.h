@@ -447,6 +447,22 @@ int tl_gae(const float* rewards, const float* values, const float* dones, float*
  * width).  Device pointers, asynchronous on the stream; round to nearest even. */
 int tl_cast_pad_bf16(const float* src, void* dst, int64_t n_rows, int32_t width, int32_t padded_width, tl_stream_t stream);
 
+/* Sampling step of the batched policy (the reference takes log_softmax of the logits and the log
+ * probability of the action per agent at batch size 1, policy/runner.py:478-488).  heads: [n_rows][row] float32
+ * (TL_DTYPE_F32) or bfloat16 (TL_DTYPE_BF16) rows whose first n_actions columns are the policy logits and, when
+ * `values` is not NULL, whose column n_actions is the value.  Per row: float32 log_softmax, one categorical sample by
+ * the Gumbel-max trick (argmax_j logp_j - log(-log u_j)), outputs actions[r] (int64), log_probs[r] = logp of the action,
+ * values[r].  u_j = ((bits >> 9) + 0.5) * 2^-23 with bits = lane j % 4 of Philox4x32-10(counter = (draw, r), key = seed),
+ * draw = 4 * ((counter ? *counter : 0) + offset) + j / 4: `counter` is an optional DEVICE int64 the caller advances between
+ * rollouts (read at run time, so a replayed CUDA graph draws fresh numbers), `offset` the step inside the rollout.
+ * Device pointers, asynchronous on the stream. */
+#define TL_MAX_ACTIONS 16
+#define TL_DTYPE_F32 0
+#define TL_DTYPE_BF16 1
+int tl_sample_actions(const void* heads, int32_t heads_dtype, int64_t n_rows, int32_t row, int32_t n_actions, uint64_t seed,
+                      const int64_t* counter, int64_t offset, int64_t* actions, float* log_probs, float* values,
+                      tl_stream_t stream);
+
 /* Host-buffer entry: every pointer (batch, LUTs, outputs) is HOST memory.
  * Copies the batch to the context's device arena, runs tl_tick, copies the
  * requested outputs and the mutated state back, and synchronises. */

@@ -148,3 +148,44 @@ def oracle_tick(
     if status != 0:
         raise RuntimeError(f"oracle tlo_tick failed with {status}")
     return out
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11) on uint32
+    arrays; returns the four output words.  Known-answer vectors of the paper's Random123 library pin it in
+    tests/test_gae.py."""
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & np.uint64(0xFFFFFFFF) for c in (c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = m0 * c0, m1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def oracle_sample_actions(heads: np.ndarray, n_actions: int, seed: int, counter: int = 0, offset: int = 0):
+    """CPU restatement of ``tl_sample_actions`` (include/townlet_b200.h): float32 log_softmax of the first ``n_actions``
+    columns (what the reference computes per agent, policy/runner.py:478-488) and one Gumbel-max categorical sample
+    per row from Philox4x32-10 uniforms.  Returns ``(actions, log_probs, log_softmax, uniforms)``."""
+    x = np.asarray(heads, dtype=np.float32)[:, :n_actions]
+    n = x.shape[0]
+    top = x.max(axis=1, keepdims=True)
+    total = np.zeros((n, 1), dtype=np.float32)
+    for j in range(n_actions):  # the kernel's summation order
+        total[:, 0] += np.exp(x[:, j] - top[:, 0], dtype=np.float32)
+    logp = x - (top + np.log(total, dtype=np.float32))
+    rows = np.arange(n, dtype=np.uint64)
+    u = np.empty((n, n_actions), dtype=np.float32)
+    for d in range((n_actions + 3) // 4):
+        c = np.uint64(4 * (counter + offset) + d)
+        words = philox4x32_10(np.full(n, c & np.uint64(0xFFFFFFFF)), np.full(n, c >> np.uint64(32)), rows & np.uint64(0xFFFFFFFF),
+                              rows >> np.uint64(32), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        for lane in range(4):
+            if 4 * d + lane < n_actions:
+                u[:, 4 * d + lane] = ((words[lane] >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0**-23)
+    score = logp - np.log(-np.log(u, dtype=np.float32), dtype=np.float32)
+    actions = score.argmax(axis=1)
+    return actions.astype(np.int64), logp[np.arange(n), actions], logp, u

@@ -317,6 +317,7 @@ def test_rollout_with_the_kernel_written_bf16_map_equals_the_cast_pass(act_on_wo
         dev = DeviceTownBatch(synth_batch(20, 24, 8, obs), obs, rew, dyn=DynamicsSpec() if act_on_world else None)
         cap = RolloutCapture(dev, policy, act_on_world=act_on_world)
         cap.fuse_map_cast = fuse
+        cap.seed = 23  # Philox key of the sampling kernel (otherwise torch.initial_seed() at construction)
         torch.manual_seed(23)
         ro = cap.capture(6)
         torch.cuda.synchronize()
@@ -326,3 +327,93 @@ def test_rollout_with_the_kernel_written_bf16_map_equals_the_cast_pass(act_on_wo
     for name in ("map", "features", "rewards", "values", "actions", "log_probs", "advantages", "returns"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert len(torch.unique(b.actions)) > 1
+
+
+def test_philox_restatement_matches_the_random123_known_answers() -> None:
+    """The three Philox4x32-10 known-answer vectors of the Random123 library (kat_vectors) pin the oracle's generator."""
+    from oracle.oracle import philox4x32_10
+
+    m = 0xFFFFFFFF
+    cases = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((m, m, m, m), (m, m), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for counter, key, want in cases:
+        assert tuple(int(w) for w in philox4x32_10(*counter, *key)) == want
+
+
+def test_oracle_sampler_draws_the_softmax_distribution() -> None:
+    from oracle.oracle import oracle_sample_actions
+
+    logits = np.tile(np.array([0.5, -1.0, 2.0, 0.0, 1.0, -3.0, 0.25, 0.0, 1.5, 9.0], np.float32), (200_000, 1))
+    actions, logp_act, logp, u = oracle_sample_actions(logits, 9, seed=99, counter=3, offset=2)
+    p = np.exp(logp[0].astype(np.float64))
+    assert abs(p.sum() - 1.0) < 1e-6 and 0.0 < u.min() and u.max() < 1.0
+    freq = np.bincount(actions, minlength=9) / len(actions)
+    assert np.all(np.abs(freq - p) < 5 * np.sqrt(p * (1 - p) / len(actions)) + 1e-4), (freq, p)
+    assert np.array_equal(logp_act, logp[np.arange(len(actions)), actions])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,row,n_actions,with_value", [("float32", 9, 9, False), ("bfloat16", 16, 9, True), ("float32", 20, 16, True), ("bfloat16", 8, 1, False)])
+def test_sample_actions_kernel_matches_the_oracle(dtype, row, n_actions, with_value) -> None:
+    """tl_sample_actions against the numpy restatement: log-probabilities to float32 rounding, the same uniforms, hence
+    the same actions (a last-bit difference of logf between libm and CUDA may flip a near-tie: at most 1 row in 10 000),
+    and torch's own log_softmax as a second opinion."""
+    import torch
+
+    from oracle.oracle import oracle_sample_actions
+    from townlet_b200.rollout import sample_actions
+
+    torch.manual_seed(4)
+    n = 50_000
+    heads = (torch.randn(n, row, device="cuda") * 2).to(getattr(torch, dtype))
+    counter = torch.tensor([5], dtype=torch.int64, device="cuda")
+    got = sample_actions(heads, n_actions, 1234567890123, counter, 7, with_value=with_value)
+    torch.cuda.synchronize()
+    ref_act, ref_logp_act, ref_logp, _ = oracle_sample_actions(heads.float().cpu().numpy(), n_actions, 1234567890123, 5, 7)
+    act, logp_act = got[0].cpu().numpy(), got[1].cpu().numpy()
+    assert (act != ref_act).mean() <= 1e-4
+    np.testing.assert_allclose(logp_act, ref_logp[np.arange(n), act], rtol=0, atol=2e-6)
+    torch_logp = torch.log_softmax(heads[:, :n_actions].float(), dim=-1).gather(1, got[0].unsqueeze(1)).squeeze(1)
+    assert torch.allclose(got[1], torch_logp, rtol=0, atol=2e-6)
+    if with_value:
+        assert torch.equal(got[2], heads[:, n_actions].float())
+    # a pure function of (seed, counter + offset, row): the same draw again, another one a step later
+    again = sample_actions(heads, n_actions, 1234567890123, None, 12)
+    later = sample_actions(heads, n_actions, 1234567890123, counter, 8)
+    assert torch.equal(again[0], got[0])
+    assert n_actions == 1 or (later[0] != got[0]).float().mean().item() > 0.2
+
+
+@pytest.mark.gpu
+def test_sample_actions_rejects_bad_arguments_and_graph_replays_draw_fresh_numbers() -> None:
+    import torch
+
+    from townlet_b200 import capi
+    from townlet_b200.engine import DeviceTownBatch
+    from townlet_b200.params import ObsSpec, RewardSpec
+    from townlet_b200.rollout import PolicyMLP, RolloutCapture, sample_actions
+    from townlet_b200.synth import synth_batch
+
+    heads = torch.zeros(4, 17, device="cuda")
+    with pytest.raises(capi.TownletB200Error):
+        sample_actions(heads, 17, 0)  # more than TL_MAX_ACTIONS
+    with pytest.raises(capi.TownletB200Error):
+        sample_actions(heads[:, :9].contiguous(), 9, 0, with_value=True)  # no value column
+    with pytest.raises(capi.TownletB200Error):
+        sample_actions(heads.cpu(), 9, 0)
+
+    obs, rew = ObsSpec(), RewardSpec(fuse_faint=True)
+    torch.manual_seed(2)
+    policy = PolicyMLP(obs.n_features, obs.map_shape, action_dim=9)
+    cap = RolloutCapture(DeviceTownBatch(synth_batch(64, 24, 8, obs), obs, rew), policy)
+    graphed = cap.build_graph(3)
+    first = graphed.replay().actions.clone()
+    second = graphed.replay().actions.clone()
+    torch.cuda.synchronize()
+    assert (first != second).float().mean().item() > 0.3  # the device counter moved on between the replays
+    assert first.min().item() >= 0 and first.max().item() < 9
+    freq = torch.bincount(torch.cat([first, second]).flatten(), minlength=9).float()
+    assert (freq > 0).all()

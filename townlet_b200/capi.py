@@ -19,6 +19,8 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtownlet_b200.so"
 INCLUDE = ROOT / "include"
 
 TL_ABI_VERSION = 3
+TL_MAX_ACTIONS = 16
+TL_DTYPE_F32, TL_DTYPE_BF16 = 0, 1
 TL_N_NEEDS = 3
 TL_MAX_EDGES = 8
 TL_MAX_SOCIAL_SLOTS = 8
@@ -257,6 +259,7 @@ EXPORTED_SYMBOLS = (
     "tl_launch_count",
     "tl_gae",
     "tl_cast_pad_bf16",
+    "tl_sample_actions",
     "tl_context_create",
     "tl_context_destroy",
     "tl_host_tick",
@@ -366,6 +369,8 @@ def load_library() -> C.CDLL:
     lib.tl_gae.argtypes = [_p, _p, _p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, _p]
     lib.tl_cast_pad_bf16.restype = C.c_int
     lib.tl_cast_pad_bf16.argtypes = [_p, _p, C.c_int64, C.c_int32, C.c_int32, _p]
+    lib.tl_sample_actions.restype = C.c_int
+    lib.tl_sample_actions.argtypes = [_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _p, C.c_int64, _p, _p, _p, _p]
     lib.tl_context_create.restype = _p
     lib.tl_context_create.argtypes = [C.c_int]
     lib.tl_context_destroy.restype = None

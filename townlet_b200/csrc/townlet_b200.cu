@@ -292,6 +292,75 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
     }
 }
 
+// Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3) and key (k0, k1) -> four uint32.  Counter-based, so a draw is a
+// pure function of (seed, row, draw index): no generator state in device memory, replayable inside a CUDA graph.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ float head_value(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float head_value(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// The sampling step of the batched policy (the reference takes log_softmax of the logits and the log
+// probability of the chosen action per agent at batch size 1, policy/runner.py:478-488): one thread per agent row reads
+// the policy logits and the value of the fused heads product, takes log_softmax in float32, samples the categorical by
+// the Gumbel-max trick (argmax_j logp_j - log(-log u_j), u_j uniform in (0, 1) from Philox) and writes the action index,
+// its log probability and the value.  Draw index of action j of row r: 4 * (*counter + offset) + j / 4, lane j % 4.
+template <typename T>
+__global__ void __launch_bounds__(256) sample_actions_kernel(const T* __restrict__ heads, long long n_rows, int row, int n_actions,
+                                                             unsigned long long seed, const long long* __restrict__ counter,
+                                                             long long offset, long long* __restrict__ actions,
+                                                             float* __restrict__ log_probs, float* __restrict__ values) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const T* h = heads + r * row;
+    float x[TL_MAX_ACTIONS];
+    float top = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < TL_MAX_ACTIONS; ++j) {
+        x[j] = j < n_actions ? head_value(h + j) : -INFINITY;
+        top = fmaxf(top, x[j]);
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < TL_MAX_ACTIONS; ++j) sum += j < n_actions ? expf(x[j] - top) : 0.0f;
+    const float lse = top + logf(sum);
+    const unsigned long long base = 4ull * (unsigned long long)((counter ? *counter : 0ll) + offset);
+    int best = 0;
+    float best_score = -INFINITY, best_logp = 0.0f;
+#pragma unroll
+    for (int d = 0; d < TL_MAX_ACTIONS / 4; ++d) {
+        if (4 * d >= n_actions) break;
+        const unsigned long long c = base + d;
+        const uint4 bits = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)r, (uint32_t)((unsigned long long)r >> 32),
+                                         (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int j = 4 * d + l;
+            if (j >= n_actions) break;
+            const float u = ((float)(w[l] >> 9) + 0.5f) * 1.1920928955078125e-07f;  // (0, 1), exact in float32
+            const float logp = x[j] - lse;
+            const float score = logp - logf(-logf(u));
+            if (score > best_score) best_score = score, best = j, best_logp = logp;  // first maximum, as argmax
+        }
+    }
+    actions[r] = best;
+    log_probs[r] = best_logp;
+    if (values) values[r] = head_value(h + n_actions);
+}
+
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
@@ -668,6 +737,28 @@ int tl_gae(const float* rewards, const float* values, const float* dones, float*
     gae_kernel<<<(n_agents + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, advantages, returns, n_steps,
                                                                         n_agents, bootstrap ? 1 : 0, g, gl);
     if (!cuda_ok(cudaGetLastError(), "gae kernel launch")) return TL_ERR_CUDA;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return TL_OK;
+}
+
+int tl_sample_actions(const void* heads, int32_t heads_dtype, int64_t n_rows, int32_t row, int32_t n_actions, uint64_t seed,
+                      const int64_t* counter, int64_t offset, int64_t* actions, float* log_probs, float* values,
+                      tl_stream_t stream) {
+    if (!heads || !actions || !log_probs) return set_error("tl_sample_actions: NULL pointer"), TL_ERR_ARG;
+    if (heads_dtype != TL_DTYPE_F32 && heads_dtype != TL_DTYPE_BF16) return set_error("tl_sample_actions: unknown dtype"), TL_ERR_ARG;
+    if (n_rows < 0 || n_actions < 1 || n_actions > TL_MAX_ACTIONS || row < n_actions + (values ? 1 : 0) || offset < 0)
+        return set_error("tl_sample_actions: 1 <= n_actions <= 16, row >= n_actions (+ 1 with values), offset >= 0"), TL_ERR_ARG;
+    if (n_rows == 0) return TL_OK;
+    const unsigned blocks = (unsigned)((n_rows + 255) / 256);
+    if (heads_dtype == TL_DTYPE_BF16)
+        sample_actions_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)heads, n_rows, row, n_actions, seed,
+                                                                      (const long long*)counter, offset, (long long*)actions,
+                                                                      log_probs, values);
+    else
+        sample_actions_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float*)heads, n_rows, row, n_actions, seed,
+                                                                      (const long long*)counter, offset, (long long*)actions,
+                                                                      log_probs, values);
+    if (!cuda_ok(cudaGetLastError(), "sample_actions launch")) return TL_ERR_CUDA;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return TL_OK;
 }

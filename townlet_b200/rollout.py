@@ -57,7 +57,8 @@ class PolicyMLP(nn.Module):
         flat = self.map_encoder[1].in_features
         return torch.zeros((n, (flat + 63) // 64 * 64), dtype=torch.bfloat16, device=device)
 
-    def _forward_bf16_padded(self, map_tensor: torch.Tensor, features: torch.Tensor, map_bf16: torch.Tensor | None = None):
+    def _forward_bf16_padded(self, map_tensor: torch.Tensor, features: torch.Tensor, map_bf16: torch.Tensor | None = None,
+                             raw_heads: bool = False):
         """The same network for bfloat16-autocast inference.  The two input widths (4·11·11 = 484 and 81) are not
         multiples of 8, which pushes cuBLAS onto unaligned fall-back kernels; ``tl_cast_pad_bf16`` does the cast autocast
         would do and pads the rows with zeros in the same pass (the zero columns meet zero weight rows); the shared
@@ -123,6 +124,8 @@ class PolicyMLP(nn.Module):
             h_feat = torch.relu_(torch.addmm(w["b_feat"], self._pad_feat, w["feat"]))
         shared = torch.addmm(w["b_shared"], h_map, w["shared_map"]).addmm_(h_feat, w["shared_feat"]).relu_()
         out = torch.addmm(w["b_heads"], shared, w["heads"])
+        if raw_heads:
+            return out  # [n, pad16(actions + 1)] bfloat16: logits, value, zero columns (what tl_sample_actions reads)
         return out[:, :actions], out[:, actions]
 
 
@@ -146,6 +149,44 @@ def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, gamma:
         )
     capi.check(status)
     return advantages, returns
+
+
+def sample_actions(heads: torch.Tensor, n_actions: int, seed: int, counter: torch.Tensor | None = None, offset: int = 0,
+                   with_value: bool = False, out: tuple[torch.Tensor, ...] | None = None):
+    """One categorical sample per row of ``heads[:, :n_actions]`` (float32 or bfloat16 logits) in ONE kernel
+    (``tl_sample_actions``): float32 log_softmax, Gumbel-max on counter-based Philox uniforms, the action's log
+    probability and, ``with_value``, column ``n_actions`` as the value.  The same distribution as
+    ``Categorical(logits=...).sample()`` / ``log_softmax(...)[action]`` (policy/runner.py:478-488).  ``counter`` is an
+    optional int64 device scalar added to ``offset`` at run time, so a replayed CUDA graph draws fresh numbers once
+    the caller advances it.  ``out``: contiguous ``(actions int64, log_probs float32[, values float32])`` rows to fill."""
+    if not heads.is_cuda:
+        raise capi.TownletB200Error("townlet_b200.rollout.sample_actions runs on CUDA tensors only (no CPU fallback)")
+    if heads.dim() != 2 or heads.stride(1) != 1 or heads.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("heads must be [rows, columns] float32 or bfloat16 with unit column stride")
+    if counter is not None and (counter.dtype != torch.int64 or counter.device != heads.device or counter.numel() != 1):
+        raise ValueError("counter must be one int64 on the device of heads")
+    n = heads.shape[0]
+    if out is not None:
+        actions, log_probs = out[0], out[1]
+        values = out[2] if with_value else None
+        for t, dtype in ((actions, torch.int64), (log_probs, torch.float32), (values, torch.float32)):
+            if t is not None and (t.dtype != dtype or t.shape != (n,) or not t.is_contiguous() or t.device != heads.device):
+                raise ValueError("out rows must be contiguous [rows] int64 / float32 / float32 on the device of heads")
+    else:
+        actions = torch.empty(n, dtype=torch.int64, device=heads.device)
+        log_probs = torch.empty(n, dtype=torch.float32, device=heads.device)
+        values = torch.empty(n, dtype=torch.float32, device=heads.device) if with_value else None
+    lib = capi.load_library()
+    with torch.cuda.device(heads.device):
+        status = lib.tl_sample_actions(
+            heads.data_ptr(), capi.TL_DTYPE_BF16 if heads.dtype == torch.bfloat16 else capi.TL_DTYPE_F32, n,
+            int(heads.stride(0)) if n > 1 else int(heads.shape[1]), n_actions, seed & (2**64 - 1),
+            counter.data_ptr() if counter is not None else None, offset,
+            actions.data_ptr(), log_probs.data_ptr(), values.data_ptr() if values is not None else None,
+            _stream_ptr(heads.device),
+        )
+    capi.check(status)
+    return (actions, log_probs, values) if with_value else (actions, log_probs)
 
 
 @dataclass
@@ -229,6 +270,9 @@ class RolloutCapture:
         self.autocast_dtype = autocast_dtype
         self.act_on_world = act_on_world
         self.fuse_map_cast = True  # False: the policy step casts the float32 map itself (A/B runs, tests)
+        self.fuse_sampling = True  # False: log_softmax / Gumbel-max / gather as separate torch kernels (A/B runs)
+        self.seed = int(torch.initial_seed())  # Philox key of tl_sample_actions
+        self._draws = torch.zeros(1, dtype=torch.int64, device=dev.device)  # ticks sampled so far (device counter)
         self._map_bf16: torch.Tensor | None = None
         if act_on_world:
             if dev.dyn is None:
@@ -306,15 +350,28 @@ class RolloutCapture:
                 dev.tick(out, capi.TL_PHASE_WORLD, 1, tick0=t, actions=self._words)
             else:
                 dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)
-            logits, value = self._forward(out.map[t], out.features[t], mirror)
             # categorical sample by the Gumbel-max trick (argmax of log-probabilities minus log of Exp(1) noise): the
-            # same distribution as Categorical(logits).sample() in a third of the kernels, and no host sync
-            logp = torch.log_softmax(logits, dim=-1)
-            act = (logp - torch.empty_like(logp).exponential_().log_()).argmax(dim=-1)
-            actions[t], log_probs[t], values[t] = act, logp.gather(1, act.unsqueeze(1)).squeeze(1), value
+            # same distribution as Categorical(logits).sample(), and no host sync
+            if self.fuse_sampling and mirror is not None:
+                # bfloat16 PolicyMLP: one kernel reads the fused heads product and writes action, log-prob and value
+                # straight into the rollout rows
+                heads = self.policy._forward_bf16_padded(out.map[t], out.features[t], mirror, raw_heads=True)
+                act = sample_actions(heads, self.policy.policy_head.out_features, self.seed, self._draws, t,
+                                     with_value=True, out=(actions[t], log_probs[t], values[t]))[0]
+            else:
+                logits, value = self._forward(out.map[t], out.features[t], mirror)
+                if self.fuse_sampling and logits.shape[1] <= capi.TL_MAX_ACTIONS:
+                    act = sample_actions(logits.contiguous(), logits.shape[1], self.seed, self._draws, t,
+                                         out=(actions[t], log_probs[t]))[0]
+                else:
+                    logp = torch.log_softmax(logits, dim=-1)
+                    act = (logp - torch.empty_like(logp).exponential_().log_()).argmax(dim=-1)
+                    actions[t], log_probs[t] = act, logp.gather(1, act.unsqueeze(1)).squeeze(1)
+                values[t] = value
             if self.act_on_world:
                 self._words.copy_(self._action_words(act))
         out.map_bf16 = caller_mirror
+        self._draws += n_ticks  # on the device: the next capture (or graph replay) draws fresh numbers
         # bootstrap value: the policy on the last observation (no further tick is simulated)
         values[n_ticks] = values[n_ticks - 1] if n_ticks else 0.0
         dones = out.terminated[:n_ticks].float()
