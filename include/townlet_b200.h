@@ -361,7 +361,9 @@ typedef struct TlObsOut {
     uint16_t* map_bf16;            /* [N][map_bf16_row]; may be NULL */
     int64_t map_bf16_tick_stride;  /* elements between consecutive ticks (0 = overwrite), a multiple of 8 */
     int32_t map_bf16_row;
-    int32_t reserved0;
+    int32_t features_bf16_row;          /* a multiple of 8, >= F */
+    uint16_t* features_bf16;            /* [N][features_bf16_row]: the same mirror of `features`; may be NULL */
+    int64_t features_bf16_tick_stride;  /* a multiple of 8 */
 } TlObsOut;
 
 typedef struct TlRewardOut {

@@ -239,6 +239,8 @@ def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], th
     row = (flat + 63) // 64 * 64
     shape = (n_ticks, batch.n_agents, row) if three_dim else (batch.n_agents, row)
     out.map_bf16 = torch.full(shape, 7.0, dtype=torch.bfloat16, device="cuda")
+    frow = (obs.n_features + 63) // 64 * 64
+    out.features_bf16 = torch.full((*shape[:-1], frow), 7.0, dtype=torch.bfloat16, device="cuda")
     if world:
         rng = np.random.default_rng(5)
         n = batch.n_agents
@@ -254,6 +256,10 @@ def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], th
     assert want.float().sum().item() > 2 * batch.n_agents  # more than the self cells
     assert torch.equal(got[..., :flat].view(torch.int16), want.view(torch.int16))
     assert not got[..., flat:].any()
+    want_f = out.features.to(torch.bfloat16) if three_dim else out.features[-1:].to(torch.bfloat16)
+    got_f = out.features_bf16 if three_dim else out.features_bf16[None]
+    assert torch.equal(got_f[..., : obs.n_features].view(torch.int16), want_f.view(torch.int16))
+    assert not got_f[..., obs.n_features :].any()
 
 
 @pytest.mark.gpu
@@ -295,6 +301,15 @@ def test_bf16_mirror_arguments_are_validated() -> None:
     out.map_bf16 = torch.zeros((batch.n_agents, 512), dtype=torch.float16, device="cuda")
     with pytest.raises(capi.TownletB200Error, match="map_bf16"):
         dev.tick(out, capi.TL_PHASE_ALL, 1)
+    out.map_bf16 = None
+    out.features_bf16 = torch.zeros((batch.n_agents, 80), dtype=torch.bfloat16, device="cuda")  # narrower than F = 81
+    with pytest.raises(capi.TownletB200Error, match="features_bf16"):
+        dev.tick(out, capi.TL_PHASE_ALL, 1)
+    # either mirror alone is served
+    out.features_bf16 = torch.full((batch.n_agents, 88), 7.0, dtype=torch.bfloat16, device="cuda")
+    dev.tick(out, capi.TL_PHASE_OBS, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(out.features_bf16[:, :81], out.features[0].to(torch.bfloat16)) and not out.features_bf16[:, 81:].any()
 
 
 @pytest.mark.gpu

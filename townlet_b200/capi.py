@@ -215,7 +215,9 @@ class TlObsOut(C.Structure):
         ("map_bf16", _p),
         ("map_bf16_tick_stride", C.c_int64),
         ("map_bf16_row", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("features_bf16_row", C.c_int32),
+        ("features_bf16", _p),
+        ("features_bf16_tick_stride", C.c_int64),
     ]
 
 

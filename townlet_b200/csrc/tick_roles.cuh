@@ -364,10 +364,11 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 float* mrow_g = p.oo.map + (size_t)it * p.oo.map_tick_stride + (size_t)(c_begin + parity) * map_elems;
                 // MIRROR: the same tile as bfloat16 (0 -> 0x0000, 1 -> 0x3f80: the cast is exact), rows padded with zeros
                 const int brow = MIRROR ? p.oo.map_bf16_row : 0;
-                uint16_t* brow_g = MIRROR ? p.oo.map_bf16 + (size_t)it * p.oo.map_bf16_tick_stride + (size_t)(c_begin + parity) * brow
-                                          : nullptr;
+                uint16_t* brow_g = (MIRROR && p.oo.map_bf16)
+                                       ? p.oo.map_bf16 + (size_t)it * p.oo.map_bf16_tick_stride + (size_t)(c_begin + parity) * brow
+                                       : nullptr;
 #pragma unroll 1
-                for (int i = parity; i < c_n; i += kTileWarps, mrow_g += kTileWarps * map_elems, brow_g += MIRROR ? kTileWarps * brow : 0) {
+                for (int i = parity; i < c_n; i += kTileWarps, mrow_g += kTileWarps * map_elems, brow_g += (MIRROR && brow_g) ? kTileWarps * brow : 0) {
                     const int32_t pwi = __shfl_sync(FULL, pw, i);
                     const int cxi = pos_x(pwi), cyi = pos_y(pwi);
                     const int eb = __shfl_sync(FULL, town_ebeg, i), ee = __shfl_sync(FULL, town_eend, i);
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                         const int tail0 = head + (nvec << 2);
                         if (lane < map_elems - tail0) mrow_g[tail0 + lane] = t[tail0 + lane];
                     }
-                    if (MIRROR) {  // padded bfloat16 row: zeros and the self cell, 16-byte stores of 8 elements
+                    if (MIRROR && brow_g) {  // padded bfloat16 row: zeros and the self cell, 16-byte stores of 8 elements
                         uint4* b4 = reinterpret_cast<uint4*>(brow_g);
                         const int nb = brow >> 3;
                         const unsigned one = 0x3f80u << (16 * (centre_tile & 1));
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                             if (is_agent) mrow_g[W2 + tile] = 1.0f;  // includes the observer (map.py:109-110)
                             if (is_obj) mrow_g[2 * W2 + tile] = 1.0f;
                             if (is_res) mrow_g[3 * W2 + tile] = 1.0f;
-                            if (MIRROR) {
+                            if (MIRROR && brow_g) {
                                 if (is_agent) brow_g[W2 + tile] = 0x3f80;
                                 if (is_obj) brow_g[2 * W2 + tile] = 0x3f80;
                                 if (is_res) brow_g[3 * W2 + tile] = 0x3f80;
@@ -546,6 +547,24 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 for (int v = tid; v < nvec; v += 32 * kRoleWarps) g4[v] = s4[v];
                 const int tail0 = head + (nvec << 2);
                 if (tid < total - tail0) feat_g0[tail0 + tid] = feat_s0[tail0 + tid];
+            }
+            if (MIRROR && p.oo.features_bf16) {  // the same rows as padded bfloat16 (round to nearest even), 8 elements per store
+                const int frow = p.oo.features_bf16_row, per_row = frow >> 3;
+                uint4* b4 = reinterpret_cast<uint4*>(p.oo.features_bf16 + (size_t)it * p.oo.features_bf16_tick_stride +
+                                                     (size_t)c_begin * frow);
+#pragma unroll 1
+                for (int v = tid; v < c_n * per_row; v += 32 * kRoleWarps) {
+                    const int ag = v / per_row, e0 = (v - ag * per_row) << 3;
+                    const float* src = feat_s0 + ag * F;
+                    unsigned w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int e = e0 + 2 * k;
+                        const __nv_bfloat162 pair = __floats2bfloat162_rn(e < F ? src[e] : 0.0f, e + 1 < F ? src[e + 1] : 0.0f);
+                        w[k] = *reinterpret_cast<const unsigned*>(&pair);
+                    }
+                    b4[v] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
             }
             TL_TIMING(t_role += tt1 - tt0; t_rest += clock64() - tt1;)
             // no second barrier: the next pass fills the other buffer, and the barrier of

@@ -461,6 +461,11 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
                 (oo->map_bf16_tick_stride & 7) || oo->map_bf16_tick_stride < 0 || ((uintptr_t)oo->map_bf16 & 15))
                 return set_error("map_bf16: rows are 16-byte aligned, a multiple of 8 elements and at least C*W*W wide"), TL_ERR_ARG;
         }
+        if (oo->features_bf16) {
+            if (oo->features_bf16_row < obs->n_features || (oo->features_bf16_row & 7) || (oo->features_bf16_tick_stride & 7) ||
+                oo->features_bf16_tick_stride < 0 || ((uintptr_t)oo->features_bf16 & 15))
+                return set_error("features_bf16: rows are 16-byte aligned, a multiple of 8 elements and at least F wide"), TL_ERR_ARG;
+        }
     }
     (void)ro;
     return TL_OK;
@@ -646,7 +651,7 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     };
     // The bfloat16 mirror of the map: written by the tiles role itself in the static hybrid form (TL_NO_MIRROR_FUSE
     // keeps it out, for A/B runs), by one cast pass per tick after the launch in every other form.
-    const bool want_mirror = do_obs && oo->map_bf16 != nullptr;
+    const bool want_mirror = do_obs && (oo->map_bf16 != nullptr || oo->features_bf16 != nullptr);
     bool mirror_in_kernel = false;
     auto dispatch = [&]() -> int {
     if (kp.mode == 0) {
@@ -687,8 +692,13 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     rc = dispatch();
     if (rc != TL_OK || !want_mirror || mirror_in_kernel) return rc;
     for (int it = 0; it < n_ticks; ++it) {
-        rc = cast_pad_rows(oo->map + (size_t)it * oo->map_tick_stride, oo->map_bf16 + (size_t)it * oo->map_bf16_tick_stride,
-                           b->n_agents, map_elems, oo->map_bf16_row, stream);
+        if (oo->map_bf16)
+            rc = cast_pad_rows(oo->map + (size_t)it * oo->map_tick_stride, oo->map_bf16 + (size_t)it * oo->map_bf16_tick_stride,
+                               b->n_agents, map_elems, oo->map_bf16_row, stream);
+        if (rc == TL_OK && oo->features_bf16)
+            rc = cast_pad_rows(oo->features + (size_t)it * oo->features_tick_stride,
+                               oo->features_bf16 + (size_t)it * oo->features_bf16_tick_stride, b->n_agents, kp.obs.n_features,
+                               oo->features_bf16_row, stream);
         if (rc != TL_OK) return rc;
     }
     return TL_OK;
@@ -995,6 +1005,7 @@ int tl_host_tick_world(TlContext* ctx, const TlTownBatch* hb, const TlObsParams*
         const size_t me = (size_t)obs->n_channels * obs->window * obs->window;
         doo = *hoo;
         doo.map_bf16 = nullptr;  // device entry points only
+        doo.features_bf16 = nullptr;
         auto span_elems = [&](int64_t stride, size_t per_tick) { return (nt - 1) * (size_t)stride + per_tick; };
         o_map = add_out(hoo->map, span_elems(hoo->map_tick_stride, N * me) * 4);
         o_feat = add_out(hoo->features, span_elems(hoo->features_tick_stride, N * (size_t)obs->n_features) * 4);

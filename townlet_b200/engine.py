@@ -45,6 +45,7 @@ class TickOutputs:
     # optional bfloat16 mirror of ``map`` for an in-loop policy: ``[ticks, N, row]`` (or ``[N, row]``, overwritten every
     # tick), rows zero-padded to a multiple of 8 elements (``TlObsOut.map_bf16``, device launches only)
     map_bf16: torch.Tensor | None = None
+    features_bf16: torch.Tensor | None = None  # the same mirror of ``features``
 
 
 class DeviceTownBatch:
@@ -158,14 +159,16 @@ class DeviceTownBatch:
         bind(oo, "map", out.map)
         bind(oo, "features", out.features)
         bind(oo, "summary", out.summary)
-        if out.map_bf16 is not None:
-            mirror = out.map_bf16
+        for name in ("map_bf16", "features_bf16"):
+            mirror = getattr(out, name)
+            if mirror is None:
+                continue
             if mirror.dtype != torch.bfloat16 or not mirror.is_contiguous() or mirror.dim() not in (2, 3):
-                raise capi.TownletB200Error("map_bf16 must be a contiguous bfloat16 tensor [N, row] or [ticks, N, row]")
+                raise capi.TownletB200Error(f"{name} must be a contiguous bfloat16 tensor [N, row] or [ticks, N, row]")
             view = mirror[tick0:] if mirror.dim() == 3 else mirror
-            oo.map_bf16 = C.c_void_p(view.data_ptr())
-            oo.map_bf16_tick_stride = int(mirror.stride(0)) if mirror.dim() == 3 else 0
-            oo.map_bf16_row = int(mirror.shape[-1])
+            setattr(oo, name, C.c_void_p(view.data_ptr()))
+            setattr(oo, f"{name}_tick_stride", int(mirror.stride(0)) if mirror.dim() == 3 else 0)
+            setattr(oo, f"{name}_row", int(mirror.shape[-1]))
         bind(ro, "reward", out.reward)
         bind(ro, "comps", out.comps)
         bind(ro, "terminated", out.terminated)

@@ -36,10 +36,11 @@ class PolicyMLP(nn.Module):
         self.policy_head = nn.Linear(hidden_dim, action_dim)
         self.value_head = nn.Linear(hidden_dim, 1)
 
-    def forward(self, map_tensor: torch.Tensor, features: torch.Tensor,
-                map_bf16: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
-        """``map_bf16``: the padded bfloat16 rows of ``map_tensor`` when the tick kernel already wrote them
-        (``TickOutputs.map_bf16``, see ``padded_map_buffer``); the bfloat16 path then skips its cast pass over the map."""
+    def forward(self, map_tensor: torch.Tensor, features: torch.Tensor, map_bf16: torch.Tensor | None = None,
+                features_bf16: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+        """``map_bf16`` / ``features_bf16``: the padded bfloat16 rows of the two inputs when the tick kernel already wrote
+        them (``TickOutputs.map_bf16`` / ``.features_bf16``, see ``padded_map_buffer`` / ``padded_features_buffer``); the
+        bfloat16 path then skips its cast pass over that input."""
         if (
             map_tensor.is_cuda
             and map_tensor.dtype == torch.float32
@@ -47,7 +48,7 @@ class PolicyMLP(nn.Module):
             and torch.is_autocast_enabled()
             and torch.get_autocast_dtype("cuda") == torch.bfloat16
         ):
-            return self._forward_bf16_padded(map_tensor, features, map_bf16)
+            return self._forward_bf16_padded(map_tensor, features, map_bf16, features_bf16=features_bf16)
         hidden = torch.cat([self.map_encoder(map_tensor), self.feature_encoder(features)], dim=-1)
         hidden = self.shared(hidden)
         return self.policy_head(hidden), self.value_head(hidden).squeeze(-1)
@@ -57,8 +58,13 @@ class PolicyMLP(nn.Module):
         flat = self.map_encoder[1].in_features
         return torch.zeros((n, (flat + 63) // 64 * 64), dtype=torch.bfloat16, device=device)
 
+    def padded_features_buffer(self, n: int, device: torch.device) -> torch.Tensor:
+        """``[n, pad64(F)]`` bfloat16 rows the tick kernel can fill (``TickOutputs.features_bf16``)."""
+        feat = self.feature_encoder[0].in_features
+        return torch.zeros((n, (feat + 63) // 64 * 64), dtype=torch.bfloat16, device=device)
+
     def _forward_bf16_padded(self, map_tensor: torch.Tensor, features: torch.Tensor, map_bf16: torch.Tensor | None = None,
-                             raw_heads: bool = False):
+                             raw_heads: bool = False, features_bf16: torch.Tensor | None = None):
         """The same network for bfloat16-autocast inference.  The two input widths (4·11·11 = 484 and 81) are not
         multiples of 8, which pushes cuBLAS onto unaligned fall-back kernels; ``tl_cast_pad_bf16`` does the cast autocast
         would do and pads the rows with zeros in the same pass (the zero columns meet zero weight rows); the shared
@@ -104,24 +110,29 @@ class PolicyMLP(nn.Module):
         lib = capi.load_library()
         stream = _stream_ptr(dev)
         src_map = map_tensor.reshape(n, flat)
-        src_feat = features.contiguous()
-        pad_map = self._pad_map
+        pad_map, pad_feat = self._pad_map, self._pad_feat
         if map_bf16 is not None:
             if map_bf16.shape != pad_map.shape or map_bf16.dtype != bf16 or not map_bf16.is_contiguous():
                 raise ValueError("map_bf16 must be the contiguous [n, pad64(C*W*W)] bfloat16 rows of map_tensor")
             pad_map = map_bf16
+        if features_bf16 is not None:
+            if features_bf16.shape != pad_feat.shape or features_bf16.dtype != bf16 or not features_bf16.is_contiguous():
+                raise ValueError("features_bf16 must be the contiguous [n, pad64(F)] bfloat16 rows of features")
+            pad_feat = features_bf16
         with torch.cuda.device(dev):
             if map_bf16 is None:
                 capi.check(lib.tl_cast_pad_bf16(src_map.data_ptr(), pad_map.data_ptr(), n, flat, pad_map.shape[1], stream))
-            capi.check(lib.tl_cast_pad_bf16(src_feat.data_ptr(), self._pad_feat.data_ptr(), n, feat, self._pad_feat.shape[1], stream))
+            if features_bf16 is None:
+                src_feat = features.contiguous()
+                capi.check(lib.tl_cast_pad_bf16(src_feat.data_ptr(), pad_feat.data_ptr(), n, feat, pad_feat.shape[1], stream))
         # bias + ReLU in the GEMM epilogue (cuBLASLt) instead of a separate pass over the activations
         fused = getattr(torch, "_addmm_activation", None)  # cuBLASLt epilogue; plain addmm + relu_ where torch lacks it
         if fused is not None:
             h_map = fused(w["b_map"], pad_map, w["map"])
-            h_feat = fused(w["b_feat"], self._pad_feat, w["feat"])
+            h_feat = fused(w["b_feat"], pad_feat, w["feat"])
         else:
             h_map = torch.relu_(torch.addmm(w["b_map"], pad_map, w["map"]))
-            h_feat = torch.relu_(torch.addmm(w["b_feat"], self._pad_feat, w["feat"]))
+            h_feat = torch.relu_(torch.addmm(w["b_feat"], pad_feat, w["feat"]))
         shared = torch.addmm(w["b_shared"], h_map, w["shared_map"]).addmm_(h_feat, w["shared_feat"]).relu_()
         out = torch.addmm(w["b_heads"], shared, w["heads"])
         if raw_heads:
@@ -274,6 +285,7 @@ class RolloutCapture:
         self.seed = int(torch.initial_seed())  # Philox key of tl_sample_actions
         self._draws = torch.zeros(1, dtype=torch.int64, device=dev.device)  # ticks sampled so far (device counter)
         self._map_bf16: torch.Tensor | None = None
+        self._feat_bf16: torch.Tensor | None = None
         if act_on_world:
             if dev.dyn is None:
                 raise capi.TownletB200Error("act_on_world needs a device batch built with a DynamicsSpec")
@@ -298,7 +310,10 @@ class RolloutCapture:
     def _forward(self, map_t: torch.Tensor, feat_t: torch.Tensor, map_bf16: torch.Tensor | None = None):
         if self.autocast_dtype is not None:
             with torch.autocast("cuda", dtype=self.autocast_dtype):
-                logits, value = self.policy(map_t, feat_t, map_bf16) if map_bf16 is not None else self.policy(map_t, feat_t)
+                if map_bf16 is not None:
+                    logits, value = self.policy(map_t, feat_t, map_bf16, self._feat_bf16)
+                else:
+                    logits, value = self.policy(map_t, feat_t)
         else:
             logits, value = self.policy(map_t, feat_t)
         return logits.float(), value.float()
@@ -310,6 +325,7 @@ class RolloutCapture:
             return None
         if self._map_bf16 is None:
             self._map_bf16 = self.policy.padded_map_buffer(self.dev.n_agents, self.dev.device)
+            self._feat_bf16 = self.policy.padded_features_buffer(self.dev.n_agents, self.dev.device)
         return self._map_bf16
 
     def build_graph(self, n_ticks: int, out: TickOutputs | None = None) -> "GraphedRollout":
@@ -342,7 +358,8 @@ class RolloutCapture:
         actions = torch.empty((n_ticks, n), dtype=torch.int64, device=dev.device)
         log_probs = torch.empty((n_ticks, n), dtype=torch.float32, device=dev.device)
         mirror = self._mirror()
-        caller_mirror, out.map_bf16 = out.map_bf16, mirror
+        caller_mirror, out.map_bf16 = (out.map_bf16, out.features_bf16), mirror
+        out.features_bf16 = self._feat_bf16 if mirror is not None else None
         for t in range(n_ticks):
             # obs / reward / done of tick t land in slot t; with act_on_world the tick first applies the action words
             # the policy chose on the previous observation (moves), then decays needs and ledgers
@@ -355,7 +372,8 @@ class RolloutCapture:
             if self.fuse_sampling and mirror is not None:
                 # bfloat16 PolicyMLP: one kernel reads the fused heads product and writes action, log-prob and value
                 # straight into the rollout rows
-                heads = self.policy._forward_bf16_padded(out.map[t], out.features[t], mirror, raw_heads=True)
+                heads = self.policy._forward_bf16_padded(out.map[t], out.features[t], mirror, raw_heads=True,
+                                                         features_bf16=self._feat_bf16)
                 act = sample_actions(heads, self.policy.policy_head.out_features, self.seed, self._draws, t,
                                      with_value=True, out=(actions[t], log_probs[t], values[t]))[0]
             else:
@@ -370,7 +388,7 @@ class RolloutCapture:
                 values[t] = value
             if self.act_on_world:
                 self._words.copy_(self._action_words(act))
-        out.map_bf16 = caller_mirror
+        out.map_bf16, out.features_bf16 = caller_mirror
         self._draws += n_ticks  # on the device: the next capture (or graph replay) draws fresh numbers
         # bootstrap value: the policy on the last observation (no further tick is simulated)
         values[n_ticks] = values[n_ticks - 1] if n_ticks else 0.0
