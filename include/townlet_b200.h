@@ -354,16 +354,20 @@ typedef struct TlObsOut {
     int64_t map_tick_stride;      /* elements between consecutive ticks (0 = overwrite) */
     int64_t features_tick_stride;
     int64_t summary_tick_stride;
-    /* ABI v3, device entry points only (tl_host_tick ignores it): optional bfloat16 mirror of `map` for a policy
-     * that reads the observation right after the tick (the reference casts per agent under
-     * autocast, policy/runner.py:444-488).  Row a of tick t = the flattened tile of agent a, round-to-nearest-even,
-     * zero-padded to map_bf16_row elements (a multiple of 8, >= C*W*W); the base is 16-byte aligned. */
+    /* ABI v3, device entry points only (tl_host_tick ignores them): optional bfloat16 mirrors of `map` and `features`
+     * for a policy that reads the observation right after the tick (the reference casts per agent
+     * under autocast, policy/runner.py:444-488).  Row a of tick t = the flattened tile (feature vector) of agent a,
+     * round-to-nearest-even, followed by zeros up to *_width elements; rows are *_row elements apart (row >= width, so
+     * both mirrors can share one buffer of combined rows).  Widths, row and tick strides are multiples of 8 elements,
+     * the bases 16-byte aligned; width 0 means width = row. */
     uint16_t* map_bf16;            /* [N][map_bf16_row]; may be NULL */
-    int64_t map_bf16_tick_stride;  /* elements between consecutive ticks (0 = overwrite), a multiple of 8 */
+    int64_t map_bf16_tick_stride;  /* elements between consecutive ticks (0 = overwrite) */
     int32_t map_bf16_row;
-    int32_t features_bf16_row;          /* a multiple of 8, >= F */
-    uint16_t* features_bf16;            /* [N][features_bf16_row]: the same mirror of `features`; may be NULL */
-    int64_t features_bf16_tick_stride;  /* a multiple of 8 */
+    int32_t features_bf16_row;
+    uint16_t* features_bf16;       /* [N][features_bf16_row]; may be NULL */
+    int64_t features_bf16_tick_stride;
+    int32_t map_bf16_width;        /* >= C*W*W */
+    int32_t features_bf16_width;   /* >= F */
 } TlObsOut;
 
 typedef struct TlRewardOut {
@@ -448,6 +452,9 @@ int tl_gae(const float* rewards, const float* values, const float* dones, float*
  * PolicyRuntime's autocast would do, policy/runner.py:444-488, fused with the padding that aligns the GEMM's reduction
  * width).  Device pointers, asynchronous on the stream; round to nearest even. */
 int tl_cast_pad_bf16(const float* src, void* dst, int64_t n_rows, int32_t width, int32_t padded_width, tl_stream_t stream);
+/* the same with destination rows dst_stride elements apart (even, >= padded_width) */
+int tl_cast_pad_bf16_strided(const float* src, void* dst, int64_t n_rows, int32_t width, int32_t padded_width,
+                             int64_t dst_stride, tl_stream_t stream);
 
 /* Sampling step of the batched policy (the reference takes log_softmax of the logits and the log
  * probability of the action per agent at batch size 1, policy/runner.py:478-488).  heads: [n_rows][row] float32

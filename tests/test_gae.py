@@ -203,6 +203,16 @@ def test_cast_pad_bf16_and_the_padded_policy_forward() -> None:
         torch.cuda.synchronize()
         assert torch.equal(dst[:, :width], src.to(torch.bfloat16)) and not dst[:, width:].any()
     assert lib.tl_cast_pad_bf16(None, None, 1, 4, 4, None) == -1 and lib.tl_cast_pad_bf16(1, 1, 1, 5, 4, None) == -1
+    # destination rows inside a wider buffer (the policy's combined input rows)
+    for rows, width, padded, stride, col in ((300, 484, 512, 640, 0), (300, 81, 128, 640, 512), (9, 7, 8, 26, 2)):
+        src = torch.randn(rows, width, device="cuda")
+        buf = torch.full((rows, stride), 7.0, dtype=torch.bfloat16, device="cuda")
+        capi.check(lib.tl_cast_pad_bf16_strided(src.data_ptr(), buf[:, col:].data_ptr(), rows, width, padded, stride,
+                                                torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(buf[:, col : col + width], src.to(torch.bfloat16)) and not buf[:, col + width : col + padded].any()
+        assert (buf[:, :col] == 7).all() and (buf[:, col + padded :] == 7).all()
+    assert lib.tl_cast_pad_bf16_strided(1, 1, 1, 4, 8, 6, None) == -1
 
     model = PolicyMLP(81, (4, 11, 11), 9).cuda().eval()
     maps = (torch.rand(4096, 4, 11, 11, device="cuda") < 0.05).float()
@@ -213,14 +223,15 @@ def test_cast_pad_bf16_and_the_padded_policy_forward() -> None:
             logits, value = model(maps, feats)  # padded path
             hidden = torch.cat([model.map_encoder(maps), model.feature_encoder(feats)], dim=-1)
             plain_logits = model.policy_head(model.shared(hidden))
-    assert hasattr(model, "_pad_map")
+    assert hasattr(model, "_pad_in")
     err_padded = (logits.float() - exact_logits).abs().max().item()
     err_plain = (plain_logits.float() - exact_logits).abs().max().item()
     assert err_padded < 2 * err_plain + 1e-3, (err_padded, err_plain)
     assert (value.float() - exact_value).abs().max().item() < 0.02
 
 
-def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], three_dim: bool, n_ticks: int = 3) -> None:
+def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], three_dim: bool, n_ticks: int = 3,
+                 combined: bool = False) -> None:
     import torch
 
     from townlet_b200 import capi
@@ -238,9 +249,13 @@ def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], th
     flat = int(np.prod(obs.map_shape))
     row = (flat + 63) // 64 * 64
     shape = (n_ticks, batch.n_agents, row) if three_dim else (batch.n_agents, row)
-    out.map_bf16 = torch.full(shape, 7.0, dtype=torch.bfloat16, device="cuda")
     frow = (obs.n_features + 63) // 64 * 64
-    out.features_bf16 = torch.full((*shape[:-1], frow), 7.0, dtype=torch.bfloat16, device="cuda")
+    if combined:  # both mirrors as column slices of one buffer of combined rows (what PolicyMLP reads)
+        both = torch.full((*shape[:-1], row + frow + 8), 7.0, dtype=torch.bfloat16, device="cuda")
+        out.map_bf16, out.features_bf16 = both[..., :row], both[..., row : row + frow]
+    else:
+        out.map_bf16 = torch.full(shape, 7.0, dtype=torch.bfloat16, device="cuda")
+        out.features_bf16 = torch.full((*shape[:-1], frow), 7.0, dtype=torch.bfloat16, device="cuda")
     if world:
         rng = np.random.default_rng(5)
         n = batch.n_agents
@@ -260,6 +275,8 @@ def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], th
     got_f = out.features_bf16 if three_dim else out.features_bf16[None]
     assert torch.equal(got_f[..., : obs.n_features].view(torch.int16), want_f.view(torch.int16))
     assert not got_f[..., obs.n_features :].any()
+    if combined:
+        assert (both[..., row + frow :] == 7).all()  # nothing is written past the two widths
 
 
 @pytest.mark.gpu
@@ -279,6 +296,7 @@ def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], th
 def test_bf16_mirror_of_the_map_equals_the_cast_of_the_float32_map(variant, world, env, three_dim, monkeypatch) -> None:
     """TlObsOut.map_bf16 (ABI v3): every kernel form leaves the padded bfloat16 rows torch's cast of the float32 map gives."""
     _mirror_case(variant, world, monkeypatch, env, three_dim)
+    _mirror_case(variant, world, monkeypatch, env, three_dim, combined=True)
 
 
 @pytest.mark.gpu

@@ -218,6 +218,8 @@ class TlObsOut(C.Structure):
         ("features_bf16_row", C.c_int32),
         ("features_bf16", _p),
         ("features_bf16_tick_stride", C.c_int64),
+        ("map_bf16_width", C.c_int32),
+        ("features_bf16_width", C.c_int32),
     ]
 
 
@@ -261,6 +263,7 @@ EXPORTED_SYMBOLS = (
     "tl_launch_count",
     "tl_gae",
     "tl_cast_pad_bf16",
+    "tl_cast_pad_bf16_strided",
     "tl_sample_actions",
     "tl_context_create",
     "tl_context_destroy",
@@ -371,6 +374,8 @@ def load_library() -> C.CDLL:
     lib.tl_gae.argtypes = [_p, _p, _p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, _p]
     lib.tl_cast_pad_bf16.restype = C.c_int
     lib.tl_cast_pad_bf16.argtypes = [_p, _p, C.c_int64, C.c_int32, C.c_int32, _p]
+    lib.tl_cast_pad_bf16_strided.restype = C.c_int
+    lib.tl_cast_pad_bf16_strided.argtypes = [_p, _p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _p]
     lib.tl_sample_actions.restype = C.c_int
     lib.tl_sample_actions.argtypes = [_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _p, C.c_int64, _p, _p, _p, _p]
     lib.tl_context_create.restype = _p

@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                     }
                     if (MIRROR && brow_g) {  // padded bfloat16 row: zeros and the self cell, 16-byte stores of 8 elements
                         uint4* b4 = reinterpret_cast<uint4*>(brow_g);
-                        const int nb = brow >> 3;
+                        const int nb = p.oo.map_bf16_width >> 3;
                         const unsigned one = 0x3f80u << (16 * (centre_tile & 1));
                         const int cw = (centre_tile & 7) >> 1;
 #pragma unroll 1
@@ -549,9 +549,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 if (tid < total - tail0) feat_g0[tail0 + tid] = feat_s0[tail0 + tid];
             }
             if (MIRROR && p.oo.features_bf16) {  // the same rows as padded bfloat16 (round to nearest even), 8 elements per store
-                const int frow = p.oo.features_bf16_row, per_row = frow >> 3;
-                uint4* b4 = reinterpret_cast<uint4*>(p.oo.features_bf16 + (size_t)it * p.oo.features_bf16_tick_stride +
-                                                     (size_t)c_begin * frow);
+                const int frow = p.oo.features_bf16_row, per_row = p.oo.features_bf16_width >> 3;
+                uint16_t* b0 = p.oo.features_bf16 + (size_t)it * p.oo.features_bf16_tick_stride + (size_t)c_begin * frow;
 #pragma unroll 1
                 for (int v = tid; v < c_n * per_row; v += 32 * kRoleWarps) {
                     const int ag = v / per_row, e0 = (v - ag * per_row) << 3;
@@ -563,7 +562,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                         const __nv_bfloat162 pair = __floats2bfloat162_rn(e < F ? src[e] : 0.0f, e + 1 < F ? src[e + 1] : 0.0f);
                         w[k] = *reinterpret_cast<const unsigned*>(&pair);
                     }
-                    b4[v] = make_uint4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<uint4*>(b0 + (size_t)ag * frow + e0) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
             TL_TIMING(t_role += tt1 - tt0; t_rest += clock64() - tt1;)

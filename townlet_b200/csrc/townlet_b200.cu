@@ -368,12 +368,13 @@ __global__ void __launch_bounds__(256) sample_actions_kernel(const T* __restrict
 // policy step does anyway (autocast), fused with the padding that makes the reduction dimension aligned.  One block walks
 // rows; a thread converts one pair of neighbours (round to nearest even, as torch's float -> bfloat16 cast).
 __global__ void __launch_bounds__(256) cast_pad_bf16_kernel(const float* __restrict__ src, __nv_bfloat162* __restrict__ dst,
-                                                            long long n_rows, int width, int padded, int vec4) {
+                                                            long long n_rows, int width, int padded, int vec4,
+                                                            long long dst_stride) {
     if (vec4) {  // width and padded are multiples of 4 and both bases 16 / 8-byte aligned: 16-byte loads, 8-byte stores
         const int quads = padded >> 2, in_quads = width >> 2;
         for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
             const float4* in = reinterpret_cast<const float4*>(src + row * width);
-            uint2* out = reinterpret_cast<uint2*>(dst + row * (padded >> 1));
+            uint2* out = reinterpret_cast<uint2*>(dst + row * (dst_stride >> 1));
             for (int j = threadIdx.x; j < quads; j += blockDim.x) {
                 const float4 v = j < in_quads ? __ldg(in + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(256) cast_pad_bf16_kernel(const float* __restr
     const int pairs = padded >> 1;
     for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
         const float* in = src + row * width;
-        __nv_bfloat162* out = dst + row * pairs;
+        __nv_bfloat162* out = dst + row * (dst_stride >> 1);
         for (int j = threadIdx.x; j < pairs; j += blockDim.x) {
             const int e = 2 * j;
             const float a = e < width ? __ldg(in + e) : 0.0f;
@@ -398,13 +399,16 @@ __global__ void __launch_bounds__(256) cast_pad_bf16_kernel(const float* __restr
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 bool cuda_ok(cudaError_t e, const char* what);
 
-int cast_pad_rows(const float* src, void* dst, int64_t n_rows, int32_t width, int32_t padded_width, cudaStream_t stream) {
+int cast_pad_rows(const float* src, void* dst, int64_t n_rows, int32_t width, int32_t padded_width, int64_t dst_stride,
+                  cudaStream_t stream) {
     if (n_rows == 0) return TL_OK;
-    const int vec4 = width % 4 == 0 && padded_width % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0;
+    const int vec4 = width % 4 == 0 && padded_width % 4 == 0 && dst_stride % 4 == 0 && ((uintptr_t)src & 15) == 0 &&
+                     ((uintptr_t)dst & 7) == 0;
     const int items = vec4 ? padded_width / 4 : padded_width / 2;
     const int threads = items >= 256 ? 256 : (items + 31) / 32 * 32;
     const long long blocks = n_rows < 148LL * 16 ? n_rows : 148LL * 16;
-    cast_pad_bf16_kernel<<<(unsigned)blocks, threads, 0, stream>>>(src, (__nv_bfloat162*)dst, n_rows, width, padded_width, vec4);
+    cast_pad_bf16_kernel<<<(unsigned)blocks, threads, 0, stream>>>(src, (__nv_bfloat162*)dst, n_rows, width, padded_width, vec4,
+                                                                   dst_stride);
     if (!cuda_ok(cudaGetLastError(), "cast_pad_bf16 launch")) return TL_ERR_CUDA;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return TL_OK;
@@ -456,16 +460,17 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
             !obs->nearest_lut || !obs->embed_lut || (obs->variant == TL_VARIANT_FULL && !obs->path_lut))
             return set_error("a look-up table pointer is NULL"), TL_ERR_ARG;
         if (obs->ticks_per_day < 1 || obs->max_slots < 1) return set_error("ticks_per_day / max_slots < 1"), TL_ERR_ARG;
-        if (oo->map_bf16) {
-            if (oo->map_bf16_row < obs->n_channels * obs->window * obs->window || (oo->map_bf16_row & 7) ||
-                (oo->map_bf16_tick_stride & 7) || oo->map_bf16_tick_stride < 0 || ((uintptr_t)oo->map_bf16 & 15))
-                return set_error("map_bf16: rows are 16-byte aligned, a multiple of 8 elements and at least C*W*W wide"), TL_ERR_ARG;
-        }
-        if (oo->features_bf16) {
-            if (oo->features_bf16_row < obs->n_features || (oo->features_bf16_row & 7) || (oo->features_bf16_tick_stride & 7) ||
-                oo->features_bf16_tick_stride < 0 || ((uintptr_t)oo->features_bf16 & 15))
-                return set_error("features_bf16: rows are 16-byte aligned, a multiple of 8 elements and at least F wide"), TL_ERR_ARG;
-        }
+        auto mirror_ok = [](const uint16_t* base, int row, int width, int64_t tick_stride, int data) {
+            if (width == 0) width = row;
+            return !((uintptr_t)base & 15) && !(row & 7) && !(width & 7) && !(tick_stride & 7) && tick_stride >= 0 && width >= data &&
+                   row >= width;
+        };
+        if (oo->map_bf16 && !mirror_ok(oo->map_bf16, oo->map_bf16_row, oo->map_bf16_width, oo->map_bf16_tick_stride,
+                                       obs->n_channels * obs->window * obs->window))
+            return set_error("map_bf16: 16-byte aligned base, row >= width >= C*W*W, all multiples of 8 elements"), TL_ERR_ARG;
+        if (oo->features_bf16 && !mirror_ok(oo->features_bf16, oo->features_bf16_row, oo->features_bf16_width,
+                                            oo->features_bf16_tick_stride, obs->n_features))
+            return set_error("features_bf16: 16-byte aligned base, row >= width >= F, all multiples of 8 elements"), TL_ERR_ARG;
     }
     (void)ro;
     return TL_OK;
@@ -485,7 +490,11 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     kp.b = *b;
     if (obs) kp.obs = *obs;
     if (rew) kp.rew = *rew;
-    if (oo) kp.oo = *oo;
+    if (oo) {
+        kp.oo = *oo;
+        if (!kp.oo.map_bf16_width) kp.oo.map_bf16_width = kp.oo.map_bf16_row;
+        if (!kp.oo.features_bf16_width) kp.oo.features_bf16_width = kp.oo.features_bf16_row;
+    }
     if (ro) kp.ro = *ro;
     if (dyn) kp.dyn = *dyn;
     kp.phases = phases;
@@ -694,11 +703,11 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
     for (int it = 0; it < n_ticks; ++it) {
         if (oo->map_bf16)
             rc = cast_pad_rows(oo->map + (size_t)it * oo->map_tick_stride, oo->map_bf16 + (size_t)it * oo->map_bf16_tick_stride,
-                               b->n_agents, map_elems, oo->map_bf16_row, stream);
+                               b->n_agents, map_elems, kp.oo.map_bf16_width, oo->map_bf16_row, stream);
         if (rc == TL_OK && oo->features_bf16)
             rc = cast_pad_rows(oo->features + (size_t)it * oo->features_tick_stride,
                                oo->features_bf16 + (size_t)it * oo->features_bf16_tick_stride, b->n_agents, kp.obs.n_features,
-                               oo->features_bf16_row, stream);
+                               kp.oo.features_bf16_width, oo->features_bf16_row, stream);
         if (rc != TL_OK) return rc;
     }
     return TL_OK;
@@ -777,7 +786,15 @@ int tl_cast_pad_bf16(const float* src, void* dst, int64_t n_rows, int32_t width,
     if (!src || !dst) return set_error("tl_cast_pad_bf16: NULL pointer"), TL_ERR_ARG;
     if (n_rows < 0 || width < 1 || padded_width < width || (padded_width & 1))
         return set_error("tl_cast_pad_bf16: padded_width must be even and >= width"), TL_ERR_ARG;
-    return cast_pad_rows(src, dst, n_rows, width, padded_width, (cudaStream_t)stream);
+    return cast_pad_rows(src, dst, n_rows, width, padded_width, padded_width, (cudaStream_t)stream);
+}
+
+int tl_cast_pad_bf16_strided(const float* src, void* dst, int64_t n_rows, int32_t width, int32_t padded_width,
+                             int64_t dst_stride, tl_stream_t stream) {
+    if (!src || !dst) return set_error("tl_cast_pad_bf16: NULL pointer"), TL_ERR_ARG;
+    if (n_rows < 0 || width < 1 || padded_width < width || (padded_width & 1) || dst_stride < padded_width || (dst_stride & 1))
+        return set_error("tl_cast_pad_bf16: padded_width and dst_stride must be even, dst_stride >= padded_width >= width"), TL_ERR_ARG;
+    return cast_pad_rows(src, dst, n_rows, width, padded_width, dst_stride, (cudaStream_t)stream);
 }
 
 int tl_obs_build(const TlTownBatch* batch, const TlObsParams* obs, const TlObsOut* out, tl_stream_t stream) {

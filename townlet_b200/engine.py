@@ -42,8 +42,9 @@ class TickOutputs:
     comps: torch.Tensor | None = None
     terminated: torch.Tensor | None = None
     kpi: torch.Tensor | None = None
-    # optional bfloat16 mirror of ``map`` for an in-loop policy: ``[ticks, N, row]`` (or ``[N, row]``, overwritten every
-    # tick), rows zero-padded to a multiple of 8 elements (``TlObsOut.map_bf16``, device launches only)
+    # optional bfloat16 mirror of ``map`` for an in-loop policy: ``[ticks, N, width]`` (or ``[N, width]``, overwritten every
+    # tick), rows zero-padded to a multiple of 8 elements; may be a column slice of a wider buffer
+    # (``TlObsOut.map_bf16``, device launches only)
     map_bf16: torch.Tensor | None = None
     features_bf16: torch.Tensor | None = None  # the same mirror of ``features``
 
@@ -163,12 +164,14 @@ class DeviceTownBatch:
             mirror = getattr(out, name)
             if mirror is None:
                 continue
-            if mirror.dtype != torch.bfloat16 or not mirror.is_contiguous() or mirror.dim() not in (2, 3):
-                raise capi.TownletB200Error(f"{name} must be a contiguous bfloat16 tensor [N, row] or [ticks, N, row]")
+            # rows may be views into a wider buffer (both mirrors side by side in one combined row)
+            if mirror.dtype != torch.bfloat16 or mirror.dim() not in (2, 3) or mirror.stride(-1) != 1:
+                raise capi.TownletB200Error(f"{name} must be bfloat16 rows [N, width] or [ticks, N, width] with unit element stride")
             view = mirror[tick0:] if mirror.dim() == 3 else mirror
             setattr(oo, name, C.c_void_p(view.data_ptr()))
             setattr(oo, f"{name}_tick_stride", int(mirror.stride(0)) if mirror.dim() == 3 else 0)
-            setattr(oo, f"{name}_row", int(mirror.shape[-1]))
+            setattr(oo, f"{name}_row", int(mirror.stride(-2)))
+            setattr(oo, f"{name}_width", int(mirror.shape[-1]))
         bind(ro, "reward", out.reward)
         bind(ro, "comps", out.comps)
         bind(ro, "terminated", out.terminated)
