@@ -183,3 +183,43 @@ def test_town_slices_partition_any_batch(n_towns, agents, world_size, data) -> N
     for p in parts:
         if p.n_towns:
             p.validate()
+
+
+def test_bf16_mirror_views_bind_their_row_stride_and_width() -> None:
+    """TickOutputs.map_bf16 / .features_bf16 may be column slices of one combined buffer: the struct carries the row
+    stride, the written width and the tick stride separately (TlObsOut, ABI v3)."""
+    import torch
+
+    from townlet_b200 import capi
+    from townlet_b200.engine import DeviceTownBatch, TickOutputs
+
+    both = torch.zeros((3, 10, 648), dtype=torch.bfloat16)
+    out = TickOutputs(map_bf16=both[..., :512], features_bf16=both[..., 512:640])
+    oo, _ = DeviceTownBatch._out_structs(out, tick0=1)
+    assert (oo.map_bf16_row, oo.map_bf16_width, oo.map_bf16_tick_stride) == (648, 512, 6480)
+    assert (oo.features_bf16_row, oo.features_bf16_width, oo.features_bf16_tick_stride) == (648, 128, 6480)
+    assert oo.map_bf16 == both[1].data_ptr() and oo.features_bf16 == both[1].data_ptr() + 2 * 512
+    single = TickOutputs(map_bf16=torch.zeros((10, 512), dtype=torch.bfloat16))
+    oo, _ = DeviceTownBatch._out_structs(single)
+    assert (oo.map_bf16_row, oo.map_bf16_width, oo.map_bf16_tick_stride) == (512, 512, 0) and not oo.features_bf16
+    for bad in (torch.zeros((10, 512), dtype=torch.float16), torch.zeros((10, 512, 2), dtype=torch.bfloat16)[..., 0],
+                torch.zeros(512, dtype=torch.bfloat16)):
+        with pytest.raises(capi.TownletB200Error, match="map_bf16"):
+            DeviceTownBatch._out_structs(TickOutputs(map_bf16=bad))
+
+
+def test_policy_helpers_refuse_cpu_tensors() -> None:
+    """No CPU fallback: the sampling and GAE wrappers raise on host tensors instead of computing there."""
+    import torch
+
+    from townlet_b200 import capi
+    from townlet_b200.rollout import PolicyMLP, gae, sample_actions
+
+    with pytest.raises(capi.TownletB200Error, match="CUDA"):
+        sample_actions(torch.zeros(4, 9), 9, seed=1)
+    with pytest.raises(capi.TownletB200Error, match="CUDA"):
+        gae(torch.zeros(2, 3), torch.zeros(2, 3), torch.zeros(2, 3), 0.99, 0.95)
+    policy = PolicyMLP(81, (4, 11, 11), 9)
+    buf = policy.padded_input_buffer(5, torch.device("cpu"))
+    pm, pf = policy.input_views(buf)
+    assert buf.shape == (5, 640) and pm.shape == (5, 512) and pf.shape == (5, 128) and pf.data_ptr() == buf.data_ptr() + 1024
