@@ -274,7 +274,7 @@ class RolloutCapture:
         self.gamma, self.gae_lambda = gamma, gae_lambda
         self.autocast_dtype = autocast_dtype
         self.act_on_world = act_on_world
-        self.fuse_map_cast = True  # False: the policy step casts the float32 map itself (A/B runs, tests)
+        self.fuse_map_cast = True  # False: the policy step casts the float32 observation itself (A/B runs, tests)
         self.fuse_sampling = True  # False: log_softmax / Gumbel-max / gather as separate torch kernels (A/B runs)
         self.seed = int(torch.initial_seed())  # Philox key of tl_sample_actions
         self._draws = torch.zeros(1, dtype=torch.int64, device=dev.device)  # ticks sampled so far (device counter)
@@ -326,8 +326,8 @@ class RolloutCapture:
     def build_graph(self, n_ticks: int, out: TickOutputs | None = None) -> "GraphedRollout":
         """Capture the whole ``n_ticks`` rollout (tick launches + policy steps + GAE) in ONE CUDA graph.
 
-        The per-tick policy step is ~25 small torch kernels; launched eagerly their CPU launch cost dominates
-        the tick.  Replaying the graph keeps the device busy; the state lives in device memory, so every
+        A tick is a handful of short kernels (the tick kernel, the policy's GEMMs, the sampling kernel); launched
+        eagerly their CPU launch cost dominates the tick.  Replaying the graph keeps the device busy; the state lives in device memory, so every
         replay continues from where the previous rollout stopped.
         """
         out = out or self.dev.alloc_outputs(capi.TL_PHASE_ALL, n_ticks)
@@ -355,34 +355,36 @@ class RolloutCapture:
         mirror = self._mirror()
         caller_mirror, out.map_bf16 = (out.map_bf16, out.features_bf16), mirror
         out.features_bf16 = self._feat_bf16 if mirror is not None else None
-        for t in range(n_ticks):
-            # obs / reward / done of tick t land in slot t; with act_on_world the tick first applies the action words
-            # the policy chose on the previous observation (moves), then decays needs and ledgers
-            if self.act_on_world:
-                dev.tick(out, capi.TL_PHASE_WORLD, 1, tick0=t, actions=self._words)
-            else:
-                dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)
-            # categorical sample by the Gumbel-max trick (argmax of log-probabilities minus log of Exp(1) noise): the
-            # same distribution as Categorical(logits).sample(), and no host sync
-            if self.fuse_sampling and mirror is not None:
-                # bfloat16 PolicyMLP: one kernel reads the fused heads product and writes action, log-prob and value
-                # straight into the rollout rows
-                heads = self.policy._forward_bf16_padded(out.map[t], out.features[t], self._inputs_bf16, raw_heads=True)
-                act = sample_actions(heads, self.policy.policy_head.out_features, self.seed, self._draws, t,
-                                     with_value=True, out=(actions[t], log_probs[t], values[t]))[0]
-            else:
-                logits, value = self._forward(out.map[t], out.features[t], mirror)
-                if self.fuse_sampling and logits.shape[1] <= capi.TL_MAX_ACTIONS:
-                    act = sample_actions(logits.contiguous(), logits.shape[1], self.seed, self._draws, t,
-                                         out=(actions[t], log_probs[t]))[0]
+        try:
+            for t in range(n_ticks):
+                # obs / reward / done of tick t land in slot t; with act_on_world the tick first applies the action words
+                # the policy chose on the previous observation (moves), then decays needs and ledgers
+                if self.act_on_world:
+                    dev.tick(out, capi.TL_PHASE_WORLD, 1, tick0=t, actions=self._words)
                 else:
-                    logp = torch.log_softmax(logits, dim=-1)
-                    act = (logp - torch.empty_like(logp).exponential_().log_()).argmax(dim=-1)
-                    actions[t], log_probs[t] = act, logp.gather(1, act.unsqueeze(1)).squeeze(1)
-                values[t] = value
-            if self.act_on_world:
-                self._words.copy_(self._action_words(act))
-        out.map_bf16, out.features_bf16 = caller_mirror
+                    dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)
+                # categorical sample by the Gumbel-max trick (argmax of log-probabilities minus log of Exp(1) noise): the
+                # same distribution as Categorical(logits).sample(), and no host sync
+                if self.fuse_sampling and mirror is not None:
+                    # bfloat16 PolicyMLP: one kernel reads the fused heads product and writes action, log-prob and value
+                    # straight into the rollout rows
+                    heads = self.policy._forward_bf16_padded(out.map[t], out.features[t], self._inputs_bf16, raw_heads=True)
+                    act = sample_actions(heads, self.policy.policy_head.out_features, self.seed, self._draws, t,
+                                         with_value=True, out=(actions[t], log_probs[t], values[t]))[0]
+                else:
+                    logits, value = self._forward(out.map[t], out.features[t], mirror)
+                    if self.fuse_sampling and logits.shape[1] <= capi.TL_MAX_ACTIONS:
+                        act = sample_actions(logits.contiguous(), logits.shape[1], self.seed, self._draws, t,
+                                             out=(actions[t], log_probs[t]))[0]
+                    else:
+                        logp = torch.log_softmax(logits, dim=-1)
+                        act = (logp - torch.empty_like(logp).exponential_().log_()).argmax(dim=-1)
+                        actions[t], log_probs[t] = act, logp.gather(1, act.unsqueeze(1)).squeeze(1)
+                    values[t] = value
+                if self.act_on_world:
+                    self._words.copy_(self._action_words(act))
+        finally:
+            out.map_bf16, out.features_bf16 = caller_mirror
         self._draws += n_ticks  # on the device: the next capture (or graph replay) draws fresh numbers
         # bootstrap value: the policy on the last observation (no further tick is simulated)
         values[n_ticks] = values[n_ticks - 1] if n_ticks else 0.0
