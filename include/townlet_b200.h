@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 3
+#define TL_ABI_VERSION 4
 
 #define TL_N_NEEDS 3          /* hunger, hygiene, energy (snapshot.py:15) */
 #define TL_MAX_EDGES 8        /* upper bound for max_edges (ledger capacity) */
@@ -290,6 +290,13 @@ typedef struct TlTownBatch {
     uint8_t* riv_count;  /* [N] */
     uint64_t* riv_embed; /* [N][K][EW] */
     double* riv_score;   /* [N][K] */
+
+    /* ABI v4, host-buffer entry points only: when every array above lies inside ONE caller-owned block
+     * [arena_base, arena_base + arena_bytes) the batch crosses the bus as a single copy (the layout of soa.py).
+     * NULL / 0 = the arrays are separate allocations: one copy per array, and nothing outside an array is
+     * ever read or written.  Ignored by the device entry points. */
+    const void* arena_base;
+    int64_t arena_bytes;
 } TlTownBatch;
 
 /* Observation parameters derived from SimulationConfig (config/observations.py). */
@@ -438,6 +445,43 @@ int tl_tick_world(const TlTownBatch* batch, const TlObsParams* obs, const TlRewa
 
 /* Number of kernels launched by this library since load (the bench reports it). */
 int64_t tl_launch_count(void);
+
+/*
+ * Planned launches (ABI v4).  tl_tick_world validates its arguments, picks the kernel form, grid and shared-memory
+ * carve-up and builds the parameter block on every call; a plan does that ONCE, after which a launch is a single
+ * cudaLaunchKernel — what a rollout loop (the in-loop caller of the reference, core/sim_loop.py:632, called once per
+ * tick) wants.  Every output pointer of obs_out / rew_out is the base of a ring of tick slots spaced by its
+ * *_tick_stride; tl_plan_launch(plan, s, stream) writes the launch's n_ticks ticks to slots s .. s + n_ticks - 1.
+ * The batch, parameter and LUT pointers are captured by value: they must stay valid while the plan lives.
+ * Device pointers; asynchronous on the stream; legal inside CUDA-graph stream capture.  NULL on error.
+ */
+typedef struct TlPlan TlPlan;
+TlPlan* tl_plan_create(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardParams* rew,
+                       const TlDynamicsParams* dyn, const TlObsOut* obs_out, const TlRewardOut* rew_out,
+                       uint32_t phases, int32_t n_ticks);
+void tl_plan_destroy(TlPlan* plan);
+int tl_plan_launch(const TlPlan* plan, int64_t tick_slot, tl_stream_t stream);
+/* n_launches back-to-back launches from one host call: launch i writes to slot ((slot0 / n_ticks + i) mod
+ * (ring_slots / n_ticks)) * n_ticks.  timed != 0 records a CUDA event before the first and after every launch;
+ * after the stream has been synchronised tl_plan_launch_ms returns the n per-launch durations in milliseconds. */
+int tl_plan_launch_many(TlPlan* plan, int64_t slot0, int32_t n_launches, int64_t ring_slots, int32_t timed,
+                        tl_stream_t stream);
+int tl_plan_launch_ms(const TlPlan* plan, float* ms, int32_t n);
+/* grid size, threads per block and dynamic shared memory the plan launches with (any pointer may be NULL) */
+int tl_plan_grid(const TlPlan* plan, int32_t* grid, int32_t* threads, int32_t* smem_bytes);
+
+/*
+ * Kernel-selection switches for parity tests and A/B measurements; process-wide, read when a launch is planned
+ * (never per launch, never from the environment).  Names and values:
+ *   "kernel_form"     -1 by entity count (default), 0 entity-list form with role warps, 1 dense shared-memory grid form
+ *   "pass_agents"     entity form: agents per pass, 1..32 (0 = default)
+ *   "towns_per_cta"   entity form: towns per CTA, 1..16 (0 = chosen from the batch shape)
+ *   "generic_window"  1 = runtime-window kernels instead of the compile-time window specialisations
+ *   "mirror_pass"     1 = bfloat16 mirrors by a cast pass after the launch instead of inside the kernel
+ *   "even_grid"       0 = do not round small grids up to a multiple of the SM count (default 1)
+ */
+int tl_set_option(const char* name, int32_t value);
+void tl_reset_options(void);
 
 /* Generalised advantage estimation over a device rollout (replaces the
  * Python double loop of compute_gae, src/townlet/policy/backends/pytorch/ppo_utils.py:55-67).

@@ -30,3 +30,31 @@ def pytest_collection_modifyitems(config: pytest.Config, items: list[pytest.Item
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+class KernelForm:
+    """Kernel-selection switches of the library (``tl_set_option``) for the parity tests; reset after the test."""
+
+    _NAMES = {
+        "TL_MODE": ("kernel_form", lambda v: {"ent": 0, "grid": 1, "": -1}[v]),
+        "TL_CHUNK": ("pass_agents", int),
+        "TL_TPC": ("towns_per_cta", int),
+        "TL_GENERIC": ("generic_window", lambda v: 1 if v else 0),
+        "TL_NO_MIRROR_FUSE": ("mirror_pass", lambda v: 1 if v else 0),
+        "TL_NO_EVEN_GRID": ("even_grid", lambda v: 0 if v else 1),
+    }
+
+    def setenv(self, name: str, value: str) -> None:
+        """Same call shape as ``monkeypatch.setenv`` for the switches that used to be environment variables."""
+        from townlet_b200 import capi
+
+        option, convert = self._NAMES[name]
+        capi.set_option(option, convert(value))
+
+
+@pytest.fixture
+def kernel_form():
+    from townlet_b200 import capi
+
+    yield KernelForm()
+    capi.reset_options()

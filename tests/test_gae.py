@@ -68,41 +68,62 @@ def test_rollout_capture_matches_tick_by_tick_oracle() -> None:
     dev = DeviceTownBatch(batch, obs, rew)
     torch.manual_seed(0)
     policy = PolicyMLP(obs.n_features, obs.map_shape, action_dim=9)
-    ro = RolloutCapture(dev, policy, autocast_dtype=None).capture(5)
-    ref = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_ALL, 5)
-    assert np.array_equal(ro.map.cpu().numpy(), ref["map"])
-    assert np.array_equal(ro.features.cpu().numpy().view(np.uint32), ref["features"].view(np.uint32))
-    np.testing.assert_allclose(ro.rewards.cpu().numpy(), ref["reward"], rtol=1e-6, atol=1e-9)
-    assert np.array_equal(ro.dones.cpu().numpy(), ref["terminated"].astype(np.float32))
+    cap = RolloutCapture(dev, policy, autocast_dtype=None)
+    ro = cap.capture(5)
+    # step t = observation t, the action chosen on it, and the reward / done of the tick that applied it (tick t + 1;
+    # policy/trajectory_service.py:127-138): six ticks for five steps, the first one only opens the trajectory
+    ref = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_ALL, 6)
+    assert np.array_equal(ro.map.cpu().numpy(), ref["map"][:5])
+    assert np.array_equal(ro.features.cpu().numpy().view(np.uint32), ref["features"][:5].view(np.uint32))
+    np.testing.assert_allclose(ro.rewards.cpu().numpy(), ref["reward"][1:], rtol=1e-6, atol=1e-9)
+    assert np.array_equal(ro.dones.cpu().numpy(), ref["terminated"][1:].astype(np.float32))
+    np.testing.assert_allclose(ro.kpi.cpu().numpy(), ref["kpi"][1:], rtol=1e-5, atol=1e-6)
     assert ro.values.shape == (6, batch.n_agents) and ro.actions.shape == (5, batch.n_agents)
+    # the bootstrap row is the policy's value of the observation after the last tick, not a repeat of the last step
+    last_map = torch.from_numpy(ref["map"][5]).cuda()
+    last_feat = torch.from_numpy(ref["features"][5]).cuda()
+    with torch.no_grad():
+        boot = cap.policy(last_map, last_feat)[1].float()
+    assert torch.allclose(ro.values[5], boot, rtol=1e-5, atol=1e-6) and not torch.equal(ro.values[5], ro.values[4])
     ref_adv, ref_ret = oracle_gae(ro.rewards.cpu().numpy(), ro.values.cpu().numpy(), ro.dones.cpu().numpy(), 0.99, 0.95)
     assert np.array_equal(ro.advantages.cpu().numpy(), ref_adv) and np.array_equal(ro.returns.cpu().numpy(), ref_ret)
+    # a second capture continues the trajectory: its first observation is the last one of the first capture
+    ro2 = cap.capture(3)
+    ref2 = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_ALL, 3)
+    assert np.array_equal(ro2.map[0].cpu().numpy(), ref["map"][5]) and np.array_equal(ro2.map[1:].cpu().numpy(), ref2["map"][:2])
+    np.testing.assert_allclose(ro2.rewards.cpu().numpy(), ref2["reward"], rtol=1e-6, atol=1e-9)
+    assert torch.equal(ro2.values[0], ro.values[5])
 
 
 @pytest.mark.gpu
-def test_graphed_rollout_equals_eager_rollout() -> None:
+@pytest.mark.parametrize("act_on_world", [False, True])
+def test_graphed_rollout_equals_eager_rollout(act_on_world) -> None:
     import torch
 
     from townlet_b200 import capi
     from townlet_b200.engine import DeviceTownBatch
-    from townlet_b200.params import ObsSpec, RewardSpec
+    from townlet_b200.params import DynamicsSpec, ObsSpec, RewardSpec
     from townlet_b200.rollout import PolicyMLP, RolloutCapture
     from townlet_b200.synth import synth_batch
 
-    obs, rew = ObsSpec(variant="compact"), RewardSpec(fuse_faint=True)
+    obs, rew = ObsSpec(variant="hybrid" if act_on_world else "compact"), RewardSpec(fuse_faint=True)
+    dyn = DynamicsSpec() if act_on_world else None
     batch = synth_batch(16, 48, 10, obs)
     policy = PolicyMLP(obs.n_features, obs.map_shape, action_dim=9)
-    eager_dev = DeviceTownBatch(batch.copy(), obs, rew)
-    graph_dev = DeviceTownBatch(batch.copy(), obs, rew)
-    eager = RolloutCapture(eager_dev, policy, autocast_dtype=None)
-    graphed = RolloutCapture(graph_dev, policy, autocast_dtype=None).build_graph(4)
+    eager_dev = DeviceTownBatch(batch.copy(), obs, rew, dyn=dyn)
+    graph_dev = DeviceTownBatch(batch.copy(), obs, rew, dyn=dyn)
+    eager = RolloutCapture(eager_dev, policy, autocast_dtype=None, act_on_world=act_on_world)
+    graph_cap = RolloutCapture(graph_dev, policy, autocast_dtype=None, act_on_world=act_on_world)
+    eager.seed = graph_cap.seed = 5
+    graphed = graph_cap.build_graph(4)  # its warm-up must leave towns, action words and draw counter untouched
+    assert graphed.library_launches >= 4
     for _ in range(2):  # two consecutive rollouts: the graph continues from the device state
         a = eager.capture(4)
         b = graphed.replay()
         torch.cuda.synchronize()
         assert torch.equal(a.map, b.map) and torch.equal(a.features, b.features)
         assert torch.equal(a.rewards, b.rewards) and torch.equal(a.dones, b.dones)
-        assert torch.allclose(a.values, b.values)
+        assert torch.equal(a.actions, b.actions) and torch.allclose(a.values, b.values)
     assert torch.equal(eager_dev.arena, graph_dev.arena)
     assert capi.load_library().tl_launch_count() > 0
 
@@ -165,7 +186,7 @@ def test_rollout_capture_with_the_policy_moving_the_agents() -> None:
     dxs = np.array(RolloutCapture.ACTION_DX + (0,) * 11)[:16]
     dys = np.array(RolloutCapture.ACTION_DY + (0,) * 11)[:16]
     moved = False
-    for t in range(steps):
+    for t in range(steps + 1):  # tick 0 opens the trajectory; tick t applies action t - 1 and yields reward t - 1
         if t == 0:
             words = np.zeros(batch.n_agents, np.uint32)
         else:
@@ -177,9 +198,11 @@ def test_rollout_capture_with_the_policy_moving_the_agents() -> None:
             words = pack_actions(kinds[idx], 0, kinds[idx] == 1, nx, ny, 1)
             moved = moved or bool(np.any((kinds[idx] == 1) & ((nx != x) | (ny != y))))
         ref = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_WORLD, 1, dyn=dyn, actions=words)
-        assert np.array_equal(ro.map[t].cpu().numpy(), ref["map"][0]), t
-        assert np.array_equal(ro.features[t].cpu().numpy().view(np.uint32), ref["features"][0].view(np.uint32)), t
-        np.testing.assert_allclose(ro.rewards[t].cpu().numpy(), ref["reward"][0], rtol=1e-6, atol=1e-9)
+        if t < steps:
+            assert np.array_equal(ro.map[t].cpu().numpy(), ref["map"][0]), t
+            assert np.array_equal(ro.features[t].cpu().numpy().view(np.uint32), ref["features"][0].view(np.uint32)), t
+        if t > 0:
+            np.testing.assert_allclose(ro.rewards[t - 1].cpu().numpy(), ref["reward"][0], rtol=1e-6, atol=1e-9)
     assert moved, "the sampled actions never moved an agent"
     state = dev.download_state()
     assert np.array_equal(state.pos, ref_batch.pos) and np.array_equal(state.ent, ref_batch.ent)
@@ -230,7 +253,7 @@ def test_cast_pad_bf16_and_the_padded_policy_forward() -> None:
     assert (value.float() - exact_value).abs().max().item() < 0.02
 
 
-def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], three_dim: bool, n_ticks: int = 3,
+def _mirror_case(variant: str, world: bool, kernel_form, env: dict[str, str], three_dim: bool, n_ticks: int = 3,
                  combined: bool = False) -> None:
     import torch
 
@@ -240,7 +263,7 @@ def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], th
     from townlet_b200.synth import synth_batch
 
     for key, value in env.items():
-        monkeypatch.setenv(key, value)
+        kernel_form.setenv(key, value)
     obs, rew = ObsSpec(variant=variant), RewardSpec(fuse_faint=True)
     # stacked agents, objects and reserved tiles inside the windows: every patch kind is written
     batch = synth_batch(37, 16, 9, obs)
@@ -293,10 +316,10 @@ def _mirror_case(variant: str, world: bool, monkeypatch, env: dict[str, str], th
         ("compact", False, {}, True),
     ],
 )
-def test_bf16_mirror_of_the_map_equals_the_cast_of_the_float32_map(variant, world, env, three_dim, monkeypatch) -> None:
+def test_bf16_mirror_of_the_map_equals_the_cast_of_the_float32_map(variant, world, env, three_dim, kernel_form) -> None:
     """TlObsOut.map_bf16 (ABI v3): every kernel form leaves the padded bfloat16 rows torch's cast of the float32 map gives."""
-    _mirror_case(variant, world, monkeypatch, env, three_dim)
-    _mirror_case(variant, world, monkeypatch, env, three_dim, combined=True)
+    _mirror_case(variant, world, kernel_form, env, three_dim)
+    _mirror_case(variant, world, kernel_form, env, three_dim, combined=True)
 
 
 @pytest.mark.gpu

@@ -55,8 +55,8 @@ def _check_state(batch, ref):
 
 @pytest.mark.parametrize("mode", ["ent", "grid"])
 @pytest.mark.parametrize("path", FIXTURES, ids=[p.stem for p in FIXTURES])
-def test_device_path_matches_reference_golden(path, mode, monkeypatch) -> None:
-    monkeypatch.setenv("TL_MODE", mode)  # both kernel forms: entity list and dense shared-memory grid
+def test_device_path_matches_reference_golden(path, mode, kernel_form) -> None:
+    kernel_form.setenv("TL_MODE", mode)  # both kernel forms: entity list and dense shared-memory grid
     batch, obs, rew, meta, ref = load_fixture(path)
     got = _device_run(batch, obs, rew, meta["phases"], meta["n_ticks"])
     assert_obs_equal(got, ref, path.stem)
@@ -90,14 +90,14 @@ SYNTH_CASES = [
 
 @pytest.mark.parametrize("mode", ["ent", "grid", "ent-chunk8", "ent-generic"])
 @pytest.mark.parametrize("case", SYNTH_CASES, ids=[c[0] for c in SYNTH_CASES])
-def test_cuda_matches_oracle_on_synthetic_towns(case, mode, monkeypatch) -> None:
+def test_cuda_matches_oracle_on_synthetic_towns(case, mode, kernel_form) -> None:
     from oracle.oracle import oracle_tick
 
-    monkeypatch.setenv("TL_MODE", mode.split("-")[0])
+    kernel_form.setenv("TL_MODE", mode.split("-")[0])
     if mode == "ent-chunk8":
-        monkeypatch.setenv("TL_CHUNK", "8")
+        kernel_form.setenv("TL_CHUNK", "8")
     if mode.endswith("-generic"):
-        monkeypatch.setenv("TL_GENERIC", "1")  # runtime-window kernels instead of the unrolled specialisations
+        kernel_form.setenv("TL_GENERIC", "1")  # runtime-window kernels instead of the unrolled specialisations
 
     _, variant, grid, agents, towns, ticks, extra = case
     obs = ObsSpec(variant=variant, **extra)
@@ -222,12 +222,12 @@ def _ragged_batch(obs, sizes, grid, extra_objects=0):
         ("full", [12, 5, 65], 64, 150),  # more than 128 entities per town: the uncached entity loop
     ],
 )
-def test_ragged_towns_match_oracle(variant, sizes, grid, extra, mode, monkeypatch) -> None:
+def test_ragged_towns_match_oracle(variant, sizes, grid, extra, mode, kernel_form) -> None:
     from oracle.oracle import oracle_tick
 
-    monkeypatch.setenv("TL_MODE", mode.split("-")[0])
+    kernel_form.setenv("TL_MODE", mode.split("-")[0])
     if mode.endswith("-generic"):
-        monkeypatch.setenv("TL_GENERIC", "1")
+        kernel_form.setenv("TL_GENERIC", "1")
     obs = ObsSpec(variant=variant, include_targets=True, object_channels=("stove", "fridge") if variant == "compact" else ())
     rew = RewardSpec(fuse_faint=True)
     batch = _ragged_batch(obs, sizes, grid, extra)
@@ -338,7 +338,7 @@ def test_ctx_reset_request_is_reported_once() -> None:
 
 
 @pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("TL_FUZZ_SEEDS", "24"))))
-def test_kernels_against_oracle_on_random_configurations(seed, monkeypatch) -> None:
+def test_kernels_against_oracle_on_random_configurations(seed, kernel_form) -> None:
     """Fuzz: random variant, window, social layout, object channels, town sizes (ragged), phases and kernel form;
     every output and the whole final state against the oracle."""
     from oracle.oracle import oracle_tick
@@ -372,11 +372,11 @@ def test_kernels_against_oracle_on_random_configurations(seed, monkeypatch) -> N
     phases = capi.TL_PHASE_WORLD if world_phases else capi.TL_PHASE_ALL
     actions = random_actions(base, ticks, seed=seed) if world_phases else None
     mode = ("ent", "grid", "ent")[int(rng.integers(0, 3))]
-    monkeypatch.setenv("TL_MODE", mode)
+    kernel_form.setenv("TL_MODE", mode)
     if rng.random() < 0.3:
-        monkeypatch.setenv("TL_CHUNK", str(int(rng.choice([8, 16, 24]))))
+        kernel_form.setenv("TL_CHUNK", str(int(rng.choice([8, 16, 24]))))
     if rng.random() < 0.3:
-        monkeypatch.setenv("TL_GENERIC", "1")
+        kernel_form.setenv("TL_GENERIC", "1")
 
     import torch
 

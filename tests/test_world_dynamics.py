@@ -124,10 +124,10 @@ def _device_run(batch, obs, rew, dyn, phases, n_ticks, actions, tick_by_tick=Fal
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["ent", "grid", "ent-generic"])
 @pytest.mark.parametrize("path", FIXTURES, ids=[p.stem for p in FIXTURES])
-def test_device_matches_reference_world(path, mode, monkeypatch) -> None:
-    monkeypatch.setenv("TL_MODE", mode.split("-")[0])
+def test_device_matches_reference_world(path, mode, kernel_form) -> None:
+    kernel_form.setenv("TL_MODE", mode.split("-")[0])
     if mode.endswith("generic"):
-        monkeypatch.setenv("TL_GENERIC", "1")
+        kernel_form.setenv("TL_GENERIC", "1")
     batch, obs, rew, meta, ref = load_fixture(path)
     got = _device_run(batch, obs, rew, meta["dyn_spec"], meta["phases"], meta["n_ticks"], meta["actions"])
     assert_obs_equal(got, ref, path.stem)
@@ -164,10 +164,10 @@ WORLD_SYNTH = [
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["ent", "grid", "ent-chunk8"])
 @pytest.mark.parametrize("case", WORLD_SYNTH, ids=[c[0] for c in WORLD_SYNTH])
-def test_device_matches_oracle_world(case, mode, monkeypatch) -> None:
-    monkeypatch.setenv("TL_MODE", mode.split("-")[0])
+def test_device_matches_oracle_world(case, mode, kernel_form) -> None:
+    kernel_form.setenv("TL_MODE", mode.split("-")[0])
     if mode.endswith("chunk8"):
-        monkeypatch.setenv("TL_CHUNK", "8")
+        kernel_form.setenv("TL_CHUNK", "8")
     name, variant, grid, agents, towns, ticks, okw, dkw = case
     obs, rew, dyn = ObsSpec(variant=variant, **okw), RewardSpec(fuse_faint=True), DynamicsSpec(**dkw)
     base = synth_batch(towns, grid, agents, obs)

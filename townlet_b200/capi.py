@@ -18,7 +18,7 @@ CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtownlet_b200.so"
 INCLUDE = ROOT / "include"
 
-TL_ABI_VERSION = 3
+TL_ABI_VERSION = 4
 TL_MAX_ACTIONS = 16
 TL_DTYPE_F32, TL_DTYPE_BF16 = 0, 1
 TL_N_NEEDS = 3
@@ -147,6 +147,8 @@ class TlTownBatch(C.Structure):
         ("riv_count", _p),
         ("riv_embed", _p),
         ("riv_score", _p),
+        ("arena_base", _p),
+        ("arena_bytes", C.c_int64),
     ]
 
 
@@ -261,6 +263,14 @@ EXPORTED_SYMBOLS = (
     "tl_tick",
     "tl_tick_world",
     "tl_launch_count",
+    "tl_plan_create",
+    "tl_plan_destroy",
+    "tl_plan_launch",
+    "tl_plan_launch_many",
+    "tl_plan_launch_ms",
+    "tl_plan_grid",
+    "tl_set_option",
+    "tl_reset_options",
     "tl_gae",
     "tl_cast_pad_bf16",
     "tl_cast_pad_bf16_strided",
@@ -370,6 +380,31 @@ def load_library() -> C.CDLL:
         C.c_int32,
         _p,
     ]
+    lib.tl_plan_create.restype = _p
+    lib.tl_plan_create.argtypes = [
+        C.POINTER(TlTownBatch),
+        C.POINTER(TlObsParams),
+        C.POINTER(TlRewardParams),
+        C.POINTER(TlDynamicsParams),
+        C.POINTER(TlObsOut),
+        C.POINTER(TlRewardOut),
+        C.c_uint32,
+        C.c_int32,
+    ]
+    lib.tl_plan_destroy.restype = None
+    lib.tl_plan_destroy.argtypes = [_p]
+    lib.tl_plan_launch.restype = C.c_int
+    lib.tl_plan_launch.argtypes = [_p, C.c_int64, _p]
+    lib.tl_plan_launch_many.restype = C.c_int
+    lib.tl_plan_launch_many.argtypes = [_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, _p]
+    lib.tl_plan_launch_ms.restype = C.c_int
+    lib.tl_plan_launch_ms.argtypes = [_p, C.POINTER(C.c_float), C.c_int32]
+    lib.tl_plan_grid.restype = C.c_int
+    lib.tl_plan_grid.argtypes = [_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.tl_set_option.restype = C.c_int
+    lib.tl_set_option.argtypes = [C.c_char_p, C.c_int32]
+    lib.tl_reset_options.restype = None
+    lib.tl_reset_options.argtypes = []
     lib.tl_gae.restype = C.c_int
     lib.tl_gae.argtypes = [_p, _p, _p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, _p]
     lib.tl_cast_pad_bf16.restype = C.c_int
@@ -418,6 +453,15 @@ def load_library() -> C.CDLL:
             )
     _lib = lib
     return lib
+
+
+def set_option(name: str, value: int) -> None:
+    """``tl_set_option``: kernel-selection switches for parity tests and A/B runs (see the header)."""
+    check(load_library().tl_set_option(name.encode(), int(value)))
+
+
+def reset_options() -> None:
+    load_library().tl_reset_options()
 
 
 def check(status: int) -> None:

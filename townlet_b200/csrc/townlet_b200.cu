@@ -476,17 +476,65 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
     return TL_OK;
 }
 
-int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlDynamicsParams* dyn,
-           const TlObsOut* oo, const TlRewardOut* ro, uint32_t phases, int n_ticks, cudaStream_t stream,
-           int towns_per_cta_override) {
+// Kernel-selection switches (tl_set_option): process-wide, read when a launch is PLANNED, never per launch and never
+// from the environment.  Defaults are the product configuration; the parity tests flip them to reach every kernel form.
+struct Options {
+    std::atomic<int> kernel_form{-1};   // -1 by entity count, 0 entity-list form with role warps, 1 dense shared-memory grid form
+    std::atomic<int> pass_agents{0};    // entity form: agents per pass (0 = 32, shrunk to what a CTA owns)
+    std::atomic<int> towns_per_cta{0};  // entity form: 0 = chosen from the batch shape
+    std::atomic<int> generic_window{0}; // 1 = runtime-window kernels instead of the unrolled specialisations
+    std::atomic<int> mirror_pass{0};    // 1 = bfloat16 mirrors by a cast pass after the launch instead of inside the kernel
+    std::atomic<int> even_grid{1};      // round small grids up to a multiple of the SM count
+};
+Options g_opt;
+
+struct DeviceInfo {
+    int max_smem;  // opt-in dynamic shared memory per block, minus room for the kernels' static shared memory
+    int sms;
+    bool ok;
+};
+
+// attributes of a device, queried once
+const DeviceInfo* device_info(int device) {
+    static DeviceInfo info[64];
+    static std::once_flag once[64];
+    if (device < 0 || device >= 64) return nullptr;
+    std::call_once(once[device], [device]() {
+        DeviceInfo& d = info[device];
+        d.ok = cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess &&
+               cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+        d.max_smem -= 1024;  // the opt-in limit covers static + dynamic
+    });
+    return info[device].ok ? &info[device] : nullptr;
+}
+
+using TickKernel = void (*)(const KParams);
+
+// Everything a launch needs, resolved once: the kernel instantiation, its grid and shared-memory carve-up, and the
+// parameter block.  Issuing it is one kernel launch (plus the cast passes of the forms without an in-kernel mirror).
+struct LaunchPlan {
+    KParams kp;
+    TickKernel kernel;
+    int grid, threads;
+    int device;
+    int map_elems;
+    bool cast_after;  // bfloat16 mirrors come from cast passes after the launch
+    bool empty;       // nothing to do (empty batch or zero ticks)
+};
+
+int prepare(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlDynamicsParams* dyn,
+            const TlObsOut* oo, const TlRewardOut* ro, uint32_t phases, int n_ticks, int towns_per_cta_override,
+            LaunchPlan& lp) {
+    memset(&lp, 0, sizeof(lp));
+    lp.empty = true;
     // an empty batch is a valid no-op (its zero-length arrays may well be NULL pointers)
     if (b && b->n_towns == 0 && b->n_agents == 0 && n_ticks >= 0) return TL_OK;
     int rc = validate(b, obs, rew, dyn, oo, ro, phases, n_ticks);
     if (rc != TL_OK) return rc;
     if (b->n_towns == 0 || n_ticks == 0) return TL_OK;
+    lp.empty = false;
 
-    KParams kp;
-    memset(&kp, 0, sizeof(kp));
+    KParams& kp = lp.kp;
     kp.b = *b;
     if (obs) kp.obs = *obs;
     if (rew) kp.rew = *rew;
@@ -511,44 +559,39 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
 
     int device = 0;
     if (!cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return TL_ERR_CUDA;
-    int max_smem = 0;
-    if (!cuda_ok(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device),
-                 "cudaDeviceGetAttribute"))
-        return TL_ERR_CUDA;
-    max_smem -= 1024;  // room for the kernels' static shared memory (the opt-in limit covers static + dynamic)
+    const DeviceInfo* di = device_info(device);
+    if (!di) return set_error("cudaDeviceGetAttribute failed"), TL_ERR_CUDA;
+    lp.device = device;
+    const int max_smem = di->max_smem, sms = di->sms;
+
+    const int opt_form = g_opt.kernel_form.load(), opt_pass = g_opt.pass_agents.load(), opt_tpc = g_opt.towns_per_cta.load();
+    const bool opt_generic = g_opt.generic_window.load() != 0, opt_mirror_pass = g_opt.mirror_pass.load() != 0;
+    const bool opt_even = g_opt.even_grid.load() != 0;
 
     const int avg_agents = b->n_towns > 0 ? (b->n_agents + b->n_towns - 1) / b->n_towns : 1;
     const int avg_entities = b->n_towns > 0 ? (b->n_entities + b->n_towns - 1) / b->n_towns : 1;
     const int map_elems = do_obs ? kp.obs.n_channels * kp.obs.window * kp.obs.window : 0;
+    lp.map_elems = map_elems;
     kp.feat_stride = kp.obs.n_features;
     kp.map_stride = round_up(map_elems + 4, 4);
     kp.grid_tiles = b->grid_w * b->grid_h;
-    auto env_int = [](const char* name, int dflt) {
-        const char* v = getenv(name);
-        return v && *v ? atoi(v) : dflt;
-    };
     // The entity-list form costs O(entities of the town) per agent, the dense grid form O(window);
     // the former wins until a town holds several hundred entities (DESIGN.md "Kernel forms").
-    const char* mode_env = getenv("TL_MODE");
-    kp.mode = avg_entities > 384 ? 1 : 0;
-    if (mode_env && !strcmp(mode_env, "grid")) kp.mode = 1;
-    if (mode_env && !strcmp(mode_env, "ent")) kp.mode = 0;
+    kp.mode = opt_form >= 0 ? (opt_form ? 1 : 0) : (avg_entities > 384 ? 1 : 0);
 
     int grid = 0, threads = kThreads;
     if (kp.mode != 1) {
         threads = 32 * kRoleWarps;
-        int chunk = env_int("TL_CHUNK", 32);
-        if (chunk < 1) chunk = 1;
+        int chunk = opt_pass > 0 ? opt_pass : 32;
         if (chunk > 32) chunk = 32;
         kp.chunk = chunk;
-        int tpc = towns_per_cta_override > 0 ? towns_per_cta_override : env_int("TL_TPC", chunk / (avg_agents > 0 ? avg_agents : 1));
+        const bool tpc_fixed = towns_per_cta_override > 0 || opt_tpc > 0;
+        int tpc = towns_per_cta_override > 0 ? towns_per_cta_override : (opt_tpc > 0 ? opt_tpc : chunk / (avg_agents > 0 ? avg_agents : 1));
         if (tpc < 1) tpc = 1;
         if (tpc > kMaxTownsPerWarp) tpc = kMaxTownsPerWarp;
-        if (towns_per_cta_override <= 0 && !getenv("TL_TPC")) {
+        if (!tpc_fixed) {
             // small batches: prefer more, emptier CTAs over idle SMs (measured on configs[1]:
             // 2 towns per 4-warp CTA beat 1, 3 and 4)
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
             const int want = 3 * sms;
             const int floor_tpc = 2 * avg_agents <= chunk ? 2 : 1;
             while (tpc > floor_tpc && (b->n_towns + tpc - 1) / tpc < want) --tpc;
@@ -556,7 +599,7 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         {
             // staging only needs to hold the agents one warp owns per pass
             const int need = tpc * avg_agents;
-            if (!getenv("TL_CHUNK") && need < chunk) kp.chunk = chunk = need < 8 ? 8 : (need + 7) / 8 * 8;
+            if (opt_pass <= 0 && need < chunk) kp.chunk = chunk = need < 8 ? 8 : (need + 7) / 8 * 8;
         }
         int off = 0;
         kp.off_grid = 0;
@@ -567,12 +610,13 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         kp.off_map = off;
         kp.tmpl_mask = 0;
         if (do_obs) {
-            // which 16-byte misalignments (in floats) can a tile of the output tensor have?
+            // which 16-byte misalignments (in floats) can a tile of the output tensor have?  (closed under tick
+            // slots: a plan may be issued at any multiple of the tick stride)
             const int base = (int)(((uintptr_t)kp.oo.map >> 2) & 3);
             const int sa = map_elems & 3, st = (int)(kp.oo.map_tick_stride & 3);
             for (int i = 0; i < 4; ++i)
                 for (int j = 0; j < 4; ++j) kp.tmpl_mask |= 1 << ((base + i * sa + j * st) & 3);
-            const bool static_hybrid = kp.obs.variant == TL_VARIANT_HYBRID && kp.obs.window == 11 && !getenv("TL_GENERIC");
+            const bool static_hybrid = kp.obs.variant == TL_VARIANT_HYBRID && kp.obs.window == 11 && !opt_generic;
             if (static_hybrid && kp.tmpl_mask == 1) kp.tmpl_mask = 0;  // aligned zero tiles come from registers
             int toff = 0;
             for (int m = 0; m < 4; ++m) {
@@ -593,13 +637,11 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         kp.towns_per_cta = tpc;
         grid = (b->n_towns + tpc - 1) / tpc;
         kp.n_big_ctas = grid;  // every CTA owns tpc towns (the last one possibly fewer)
-        if (towns_per_cta_override <= 0 && !getenv("TL_TPC") && tpc > 1) {
+        if (!tpc_fixed && tpc > 1) {
             // A grid that is not a multiple of the SM count leaves some SMs one CTA more than others for the whole
             // launch (the CTAs loop over every tick); round it up and hand the towns out one fewer to the last CTAs.
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
             const int even = (grid + sms - 1) / sms * sms;
-            if (even != grid && even <= b->n_towns && even / sms <= 8 && !getenv("TL_NO_EVEN_GRID")) {
+            if (even != grid && even <= b->n_towns && even / sms <= 8 && opt_even) {
                 grid = even;
                 kp.towns_per_cta = b->n_towns / grid + 1;
                 kp.n_big_ctas = b->n_towns % grid;
@@ -635,82 +677,115 @@ int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* r
         grid = (b->n_towns + tpc - 1) / tpc;
         kp.n_big_ctas = grid;
     }
+    lp.grid = grid;
+    lp.threads = threads;
 
-    auto run = [&](auto kernel) -> int {
-        // opt in to the device's full dynamic shared memory once per kernel and device, so that later
-        // launches issue no attribute call (legal inside CUDA-graph stream capture).  Keyed by the
-        // function address: all instantiations share one function-pointer type.
-        {
-            static std::mutex mu;
-            static std::unordered_map<const void*, uint64_t> opted_in;
-            const uint64_t bit = 1ull << (device & 63);
-            std::lock_guard<std::mutex> lock(mu);
-            uint64_t& mask = opted_in[reinterpret_cast<const void*>(kernel)];
-            if (!(mask & bit)) {
-                if (!cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem),
-                             "cudaFuncSetAttribute"))
-                    return TL_ERR_CUDA;
-                mask |= bit;
-            }
+    auto pick_kernel = [&](TickKernel kernel) -> int {
+        // opt in to the device's full dynamic shared memory once per kernel and device, so that launches
+        // issue no attribute call (legal inside CUDA-graph stream capture).  Keyed by the function address.
+        static std::mutex mu;
+        static std::unordered_map<const void*, uint64_t> opted_in;
+        const uint64_t bit = 1ull << (device & 63);
+        std::lock_guard<std::mutex> lock(mu);
+        uint64_t& mask = opted_in[reinterpret_cast<const void*>(kernel)];
+        if (!(mask & bit)) {
+            if (!cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem), "cudaFuncSetAttribute"))
+                return TL_ERR_CUDA;
+            mask |= bit;
         }
-        kernel<<<grid, threads, kp.smem_bytes, stream>>>(kp);
-        if (!cuda_ok(cudaGetLastError(), "kernel launch")) return TL_ERR_CUDA;
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        lp.kernel = kernel;
         return TL_OK;
     };
-    // The bfloat16 mirror of the map: written by the tiles role itself in the static hybrid form (TL_NO_MIRROR_FUSE
-    // keeps it out, for A/B runs), by one cast pass per tick after the launch in every other form.
+    // The bfloat16 mirror of the map: written by the tiles role itself in the static hybrid form (the mirror_pass
+    // option keeps it out, for A/B runs), by one cast pass per tick after the launch in every other form.
     const bool want_mirror = do_obs && (oo->map_bf16 != nullptr || oo->features_bf16 != nullptr);
     bool mirror_in_kernel = false;
     auto dispatch = [&]() -> int {
-    if (kp.mode == 0) {
-        const bool generic = getenv("TL_GENERIC") != nullptr;  // force the runtime-window form (tests)
-        const int win = do_obs ? kp.obs.window : 0;
-        const bool world = phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY);
-        auto pick = [&](auto variant, auto window) -> int {
-            if (world) return run(tick_kernel_roles<decltype(variant)::value, decltype(window)::value, true>);
-            return run(tick_kernel_roles<decltype(variant)::value, decltype(window)::value, false>);
-        };
-        using std::integral_constant;
+        if (kp.mode == 0) {
+            const int win = do_obs ? kp.obs.window : 0;
+            const bool world = phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY);
+            auto pick = [&](auto variant, auto window) -> int {
+                if (world) return pick_kernel(tick_kernel_roles<decltype(variant)::value, decltype(window)::value, true>);
+                return pick_kernel(tick_kernel_roles<decltype(variant)::value, decltype(window)::value, false>);
+            };
+            using std::integral_constant;
+            switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
+                case TL_VARIANT_HYBRID:
+                    if (win == 11 && !opt_generic && want_mirror && !opt_mirror_pass) {
+                        mirror_in_kernel = true;
+                        if (world) return pick_kernel(tick_kernel_roles<TL_VARIANT_HYBRID, 11, true, true>);
+                        return pick_kernel(tick_kernel_roles<TL_VARIANT_HYBRID, 11, false, true>);
+                    }
+                    if (win == 11 && !opt_generic) return pick(integral_constant<int, TL_VARIANT_HYBRID>{}, integral_constant<int, 11>{});
+                    return pick(integral_constant<int, TL_VARIANT_HYBRID>{}, integral_constant<int, 0>{});
+                case TL_VARIANT_FULL:
+                    if (win == 11 && !opt_generic) return pick(integral_constant<int, TL_VARIANT_FULL>{}, integral_constant<int, 11>{});
+                    return pick(integral_constant<int, TL_VARIANT_FULL>{}, integral_constant<int, 0>{});
+                case TL_VARIANT_COMPACT:
+                    if (win == 7 && kp.obs.n_ctypes == 0 && !opt_generic)
+                        return pick(integral_constant<int, TL_VARIANT_COMPACT>{}, integral_constant<int, 7>{});
+                    return pick(integral_constant<int, TL_VARIANT_COMPACT>{}, integral_constant<int, 0>{});
+                default: return set_error("unknown variant"), TL_ERR_ARG;
+            }
+        }
         switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
-            case TL_VARIANT_HYBRID:
-                if (win == 11 && !generic && want_mirror && !getenv("TL_NO_MIRROR_FUSE")) {
-                    mirror_in_kernel = true;
-                    if (world) return run(tick_kernel_roles<TL_VARIANT_HYBRID, 11, true, true>);
-                    return run(tick_kernel_roles<TL_VARIANT_HYBRID, 11, false, true>);
-                }
-                if (win == 11 && !generic) return pick(integral_constant<int, TL_VARIANT_HYBRID>{}, integral_constant<int, 11>{});
-                return pick(integral_constant<int, TL_VARIANT_HYBRID>{}, integral_constant<int, 0>{});
-            case TL_VARIANT_FULL:
-                if (win == 11 && !generic) return pick(integral_constant<int, TL_VARIANT_FULL>{}, integral_constant<int, 11>{});
-                return pick(integral_constant<int, TL_VARIANT_FULL>{}, integral_constant<int, 0>{});
-            case TL_VARIANT_COMPACT:
-                if (win == 7 && kp.obs.n_ctypes == 0 && !generic)
-                    return pick(integral_constant<int, TL_VARIANT_COMPACT>{}, integral_constant<int, 7>{});
-                return pick(integral_constant<int, TL_VARIANT_COMPACT>{}, integral_constant<int, 0>{});
+            case TL_VARIANT_HYBRID: return pick_kernel(tick_kernel<TL_VARIANT_HYBRID>);
+            case TL_VARIANT_FULL: return pick_kernel(tick_kernel<TL_VARIANT_FULL>);
+            case TL_VARIANT_COMPACT: return pick_kernel(tick_kernel<TL_VARIANT_COMPACT>);
             default: return set_error("unknown variant"), TL_ERR_ARG;
         }
-    }
-    switch (do_obs ? kp.obs.variant : TL_VARIANT_HYBRID) {
-        case TL_VARIANT_HYBRID: return run(tick_kernel<TL_VARIANT_HYBRID>);
-        case TL_VARIANT_FULL: return run(tick_kernel<TL_VARIANT_FULL>);
-        case TL_VARIANT_COMPACT: return run(tick_kernel<TL_VARIANT_COMPACT>);
-        default: return set_error("unknown variant"), TL_ERR_ARG;
-    }
     };
     rc = dispatch();
-    if (rc != TL_OK || !want_mirror || mirror_in_kernel) return rc;
-    for (int it = 0; it < n_ticks; ++it) {
-        if (oo->map_bf16)
-            rc = cast_pad_rows(oo->map + (size_t)it * oo->map_tick_stride, oo->map_bf16 + (size_t)it * oo->map_bf16_tick_stride,
-                               b->n_agents, map_elems, kp.oo.map_bf16_width, oo->map_bf16_row, stream);
-        if (rc == TL_OK && oo->features_bf16)
-            rc = cast_pad_rows(oo->features + (size_t)it * oo->features_tick_stride,
-                               oo->features_bf16 + (size_t)it * oo->features_bf16_tick_stride, b->n_agents, kp.obs.n_features,
-                               kp.oo.features_bf16_width, oo->features_bf16_row, stream);
+    if (rc != TL_OK) return rc;
+    lp.cast_after = want_mirror && !mirror_in_kernel;
+    return TL_OK;
+}
+
+// Issue a planned launch with every output moved `slot` tick strides on (slot 0 = the pointers the plan was made with).
+int issue(const LaunchPlan& lp, int64_t slot, cudaStream_t stream) {
+    if (lp.empty) return TL_OK;
+    const KParams* kpp = &lp.kp;
+    KParams moved;
+    if (slot != 0) {
+        moved = lp.kp;
+        TlObsOut& o = moved.oo;
+        TlRewardOut& r = moved.ro;
+        if (o.map) o.map += slot * o.map_tick_stride;
+        if (o.features) o.features += slot * o.features_tick_stride;
+        if (o.summary) o.summary += slot * o.summary_tick_stride;
+        if (o.map_bf16) o.map_bf16 += slot * o.map_bf16_tick_stride;
+        if (o.features_bf16) o.features_bf16 += slot * o.features_bf16_tick_stride;
+        if (r.reward) r.reward += slot * r.reward_tick_stride;
+        if (r.comps) r.comps += slot * r.comps_tick_stride;
+        if (r.terminated) r.terminated += slot * r.terminated_tick_stride;
+        if (r.kpi) r.kpi += slot * r.kpi_tick_stride;
+        kpp = &moved;
+    }
+    const KParams& kp = *kpp;
+    lp.kernel<<<lp.grid, lp.threads, kp.smem_bytes, stream>>>(kp);
+    if (!cuda_ok(cudaGetLastError(), "kernel launch")) return TL_ERR_CUDA;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!lp.cast_after) return TL_OK;
+    int rc = TL_OK;
+    for (int it = 0; it < kp.n_ticks; ++it) {
+        if (kp.oo.map_bf16)
+            rc = cast_pad_rows(kp.oo.map + (size_t)it * kp.oo.map_tick_stride, kp.oo.map_bf16 + (size_t)it * kp.oo.map_bf16_tick_stride,
+                               kp.b.n_agents, lp.map_elems, kp.oo.map_bf16_width, kp.oo.map_bf16_row, stream);
+        if (rc == TL_OK && kp.oo.features_bf16)
+            rc = cast_pad_rows(kp.oo.features + (size_t)it * kp.oo.features_tick_stride,
+                               kp.oo.features_bf16 + (size_t)it * kp.oo.features_bf16_tick_stride, kp.b.n_agents, kp.obs.n_features,
+                               kp.oo.features_bf16_width, kp.oo.features_bf16_row, stream);
         if (rc != TL_OK) return rc;
     }
     return TL_OK;
+}
+
+int launch(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* rew, const TlDynamicsParams* dyn,
+           const TlObsOut* oo, const TlRewardOut* ro, uint32_t phases, int n_ticks, cudaStream_t stream,
+           int towns_per_cta_override) {
+    LaunchPlan lp;
+    const int rc = prepare(b, obs, rew, dyn, oo, ro, phases, n_ticks, towns_per_cta_override, lp);
+    return rc != TL_OK ? rc : issue(lp, 0, stream);
 }
 
 }  // namespace
@@ -816,6 +891,109 @@ int tl_tick_world(const TlTownBatch* batch, const TlObsParams* obs, const TlRewa
                   const TlDynamicsParams* dyn, const TlObsOut* obs_out, const TlRewardOut* rew_out, uint32_t phases,
                   int32_t n_ticks, tl_stream_t stream) {
     return launch(batch, obs, rew, dyn, obs_out, rew_out, phases, n_ticks, (cudaStream_t)stream, 0);
+}
+
+// ---- kernel-selection switches --------------------------------------------------
+int tl_set_option(const char* name, int32_t value) {
+    if (!name) return set_error("tl_set_option: NULL name"), TL_ERR_ARG;
+    std::atomic<int>* slot = nullptr;
+    if (!strcmp(name, "kernel_form")) slot = &g_opt.kernel_form;
+    else if (!strcmp(name, "pass_agents")) slot = &g_opt.pass_agents;
+    else if (!strcmp(name, "towns_per_cta")) slot = &g_opt.towns_per_cta;
+    else if (!strcmp(name, "generic_window")) slot = &g_opt.generic_window;
+    else if (!strcmp(name, "mirror_pass")) slot = &g_opt.mirror_pass;
+    else if (!strcmp(name, "even_grid")) slot = &g_opt.even_grid;
+    if (!slot) return set_error("tl_set_option: unknown option '%s'", name), TL_ERR_ARG;
+    if (slot == &g_opt.kernel_form && (value < -1 || value > 1)) return set_error("kernel_form is -1, 0 or 1"), TL_ERR_ARG;
+    if (slot == &g_opt.pass_agents && (value < 0 || value > 32)) return set_error("pass_agents is 0..32"), TL_ERR_ARG;
+    if (slot == &g_opt.towns_per_cta && (value < 0 || value > kMaxTownsPerWarp)) return set_error("towns_per_cta is 0..16"), TL_ERR_ARG;
+    slot->store(value);
+    return TL_OK;
+}
+
+void tl_reset_options(void) {
+    g_opt.kernel_form.store(-1);
+    g_opt.pass_agents.store(0);
+    g_opt.towns_per_cta.store(0);
+    g_opt.generic_window.store(0);
+    g_opt.mirror_pass.store(0);
+    g_opt.even_grid.store(1);
+}
+
+// ---- planned launches -----------------------------------------------------------
+struct TlPlan {
+    LaunchPlan lp;
+    cudaEvent_t* events;  // n_events timing events of the last tl_plan_launch_many(..., timed)
+    int n_events, cap_events;
+};
+
+TlPlan* tl_plan_create(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardParams* rew, const TlDynamicsParams* dyn,
+                       const TlObsOut* obs_out, const TlRewardOut* rew_out, uint32_t phases, int32_t n_ticks) {
+    TlPlan* plan = new TlPlan();
+    plan->events = nullptr;
+    plan->n_events = plan->cap_events = 0;
+    if (prepare(batch, obs, rew, dyn, obs_out, rew_out, phases, n_ticks, 0, plan->lp) != TL_OK) {
+        delete plan;
+        return nullptr;
+    }
+    return plan;
+}
+
+void tl_plan_destroy(TlPlan* plan) {
+    if (!plan) return;
+    for (int i = 0; i < plan->cap_events; ++i) cudaEventDestroy(plan->events[i]);
+    free(plan->events);
+    delete plan;
+}
+
+int tl_plan_launch(const TlPlan* plan, int64_t tick_slot, tl_stream_t stream) {
+    if (!plan) return set_error("plan is NULL"), TL_ERR_ARG;
+    if (tick_slot < 0) return set_error("tick_slot < 0"), TL_ERR_ARG;
+    return issue(plan->lp, tick_slot, (cudaStream_t)stream);
+}
+
+int tl_plan_launch_many(TlPlan* plan, int64_t slot0, int32_t n_launches, int64_t ring_slots, int32_t timed, tl_stream_t stream) {
+    if (!plan) return set_error("plan is NULL"), TL_ERR_ARG;
+    const int64_t per = plan->lp.empty ? 1 : plan->lp.kp.n_ticks;
+    if (slot0 < 0 || n_launches < 0 || ring_slots < per) return set_error("tl_plan_launch_many: slot0 >= 0, ring_slots >= n_ticks"), TL_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int want = timed ? n_launches + 1 : 0;
+    if (want > plan->cap_events) {
+        cudaEvent_t* grown = (cudaEvent_t*)realloc(plan->events, sizeof(cudaEvent_t) * want);
+        if (!grown) return set_error("out of memory"), TL_ERR_ARG;
+        plan->events = grown;
+        for (int i = plan->cap_events; i < want; ++i) {
+            if (!cuda_ok(cudaEventCreate(&plan->events[i]), "cudaEventCreate")) return TL_ERR_CUDA;
+            plan->cap_events = i + 1;
+        }
+    }
+    plan->n_events = want;
+    const int64_t n_pos = ring_slots / per;  // launches that fit the ring before it wraps
+    int64_t pos = (slot0 / per) % n_pos;
+    if (timed && !cuda_ok(cudaEventRecord(plan->events[0], s), "cudaEventRecord")) return TL_ERR_CUDA;
+    for (int i = 0; i < n_launches; ++i) {
+        const int rc = issue(plan->lp, pos * per, s);
+        if (rc != TL_OK) return rc;
+        if (timed && !cuda_ok(cudaEventRecord(plan->events[i + 1], s), "cudaEventRecord")) return TL_ERR_CUDA;
+        if (++pos == n_pos) pos = 0;
+    }
+    return TL_OK;
+}
+
+int tl_plan_launch_ms(const TlPlan* plan, float* ms, int32_t n) {
+    if (!plan || !ms) return set_error("tl_plan_launch_ms: NULL pointer"), TL_ERR_ARG;
+    if (n < 0 || n + 1 > plan->n_events) return set_error("tl_plan_launch_ms: more launches than the last timed call issued"), TL_ERR_ARG;
+    for (int i = 0; i < n; ++i)
+        if (!cuda_ok(cudaEventElapsedTime(&ms[i], plan->events[i], plan->events[i + 1]), "cudaEventElapsedTime")) return TL_ERR_CUDA;
+    return TL_OK;
+}
+
+int tl_plan_grid(const TlPlan* plan, int32_t* grid, int32_t* threads, int32_t* smem_bytes) {
+    if (!plan) return set_error("plan is NULL"), TL_ERR_ARG;
+    if (grid) *grid = plan->lp.grid;
+    if (threads) *threads = plan->lp.threads;
+    if (smem_bytes) *smem_bytes = plan->lp.empty ? 0 : plan->lp.kp.smem_bytes;
+    return TL_OK;
 }
 
 // ---- host-buffer context ----------------------------------------------------
@@ -961,16 +1139,20 @@ int tl_host_tick_world(TlContext* ctx, const TlTownBatch* hb, const TlObsParams*
         add(obs->embed_lut, (void**)&dobs.embed_lut, 256 * 4, false);
     }
 
-    // If the batch fields sit in one host arena, move them with a single copy.
-    uintptr_t lo = UINTPTR_MAX, hi = 0;
-    size_t sum = 0;
-    for (int i = 0; i < n_batch_spans; ++i) {
-        const uintptr_t p0 = (uintptr_t)spans[i].host;
-        lo = p0 < lo ? p0 : lo;
-        hi = p0 + spans[i].bytes > hi ? p0 + spans[i].bytes : hi;
-        sum += spans[i].bytes;
+    // One copy for the whole batch only when the caller DECLARES that its arrays share one block
+    // (TlTownBatch.arena_base / arena_bytes); otherwise one copy per array and nothing else is touched.
+    uintptr_t lo = 0, hi = 0;
+    bool contiguous = false;
+    if (hb->arena_base && hb->arena_bytes > 0 && n_batch_spans > 0) {
+        lo = (uintptr_t)hb->arena_base;
+        hi = lo + (size_t)hb->arena_bytes;
+        for (int i = 0; i < n_batch_spans; ++i) {
+            const uintptr_t p0 = (uintptr_t)spans[i].host;
+            if (p0 < lo || p0 + spans[i].bytes > hi)
+                return set_error("an array of the batch lies outside [arena_base, arena_base + arena_bytes)"), TL_ERR_ARG;
+        }
+        contiguous = true;
     }
-    const bool contiguous = n_batch_spans > 0 && (hi - lo) <= sum + sum / 4 + 64 * 1024 && (lo % 16) == 0;
     size_t need = 0;
     if (contiguous) need = round_up((int)((hi - lo + 255) / 256), 1) * (size_t)256;
     size_t cursor = need;
@@ -1070,7 +1252,7 @@ int tl_host_tick_world(TlContext* ctx, const TlTownBatch* hb, const TlObsParams*
         whi = p0 + spans[i].bytes > whi ? p0 + spans[i].bytes : whi;
         wsum += spans[i].bytes;
     }
-    if (contiguous && wsum > 0 && (whi - wlo) <= wsum + wsum / 2 + 4096) {
+    if (contiguous && wsum > 0 && (whi - wlo) <= wsum + wsum / 2 + 4096) {  // [wlo, whi) lies inside the declared arena
         if (!cuda_ok(cudaMemcpyAsync((void*)wlo, ctx->d_arena + (wlo - lo), whi - wlo, cudaMemcpyDeviceToHost, ctx->stream),
                      "D2H state"))
             return TL_ERR_CUDA;

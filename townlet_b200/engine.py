@@ -49,6 +49,53 @@ class TickOutputs:
     features_bf16: torch.Tensor | None = None  # the same mirror of ``features``
 
 
+class TickPlan:
+    """A planned launch (``tl_plan_create``): kernel form, grid and parameter block are resolved once, a launch is
+    one ``cudaLaunchKernel``.  ``out`` is a ring of tick slots; ``launch(slot)`` writes ``n_ticks`` ticks from ``slot``."""
+
+    def __init__(self, dev: "DeviceTownBatch", handle: int, out: TickOutputs, n_ticks: int, keep: tuple) -> None:
+        self.dev = dev
+        self.lib = dev.lib
+        self.handle = handle
+        self.out = out
+        self.n_ticks = n_ticks
+        self._keep = keep  # tensors the plan's parameter block points at
+        first = next(t for t in (out.map, out.reward, out.features, out.kpi) if t is not None)
+        self.ring_slots = int(first.shape[0])
+
+    def launch(self, slot: int = 0) -> None:
+        capi.check(self.lib.tl_plan_launch(self.handle, slot, _stream_ptr(self.dev.device)))
+
+    def launch_many(self, n_launches: int, slot0: int = 0, timed: bool = False) -> None:
+        """``n_launches`` back-to-back launches walking the output ring, issued by one C call."""
+        capi.check(
+            self.lib.tl_plan_launch_many(self.handle, slot0, n_launches, self.ring_slots, 1 if timed else 0, _stream_ptr(self.dev.device))
+        )
+
+    def launch_ms(self, n_launches: int) -> np.ndarray:
+        """Per-launch durations (ms) of the last ``launch_many(..., timed=True)``; synchronise the stream first."""
+        ms = np.zeros(n_launches, dtype=np.float32)
+        capi.check(self.lib.tl_plan_launch_ms(self.handle, ms.ctypes.data_as(C.POINTER(C.c_float)), n_launches))
+        return ms
+
+    @property
+    def grid(self) -> tuple[int, int, int]:
+        g, t, s = C.c_int32(), C.c_int32(), C.c_int32()
+        capi.check(self.lib.tl_plan_grid(self.handle, C.byref(g), C.byref(t), C.byref(s)))
+        return g.value, t.value, s.value
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.tl_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self) -> None:  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DeviceTownBatch:
     """A ``TownBatch`` resident in HBM plus the look-up tables of one ``ObsSpec``."""
 
@@ -179,6 +226,42 @@ class DeviceTownBatch:
         return oo, ro
 
     # launches -------------------------------------------------------------
+    def _dyn_pointer(self, phases: int, n_ticks: int, actions: torch.Tensor | None):
+        if not phases & (capi.TL_PHASE_ACTIONS | capi.TL_PHASE_SOCIAL_DECAY):
+            return None
+        if self._dyn_struct is None:
+            raise capi.TownletB200Error("the world-dynamics phases need a DynamicsSpec")
+        self._dyn_struct.actions = None
+        self._dyn_struct.actions_tick_stride = 0
+        if phases & capi.TL_PHASE_ACTIONS:
+            if actions is None or actions.device != self.arena.device or actions.element_size() != 4:
+                raise capi.TownletB200Error("TL_PHASE_ACTIONS needs a 32-bit action tensor on the batch's device")
+            if not actions.is_contiguous() or actions.shape[-1] != self.n_agents:
+                raise capi.TownletB200Error("actions must be contiguous [n_agents] or [n_ticks, n_agents]")
+            if actions.dim() == 2 and actions.shape[0] != n_ticks:
+                raise capi.TownletB200Error("actions has the wrong number of ticks")
+            self._dyn_struct.actions = actions.data_ptr()
+            self._dyn_struct.actions_tick_stride = self.n_agents if actions.dim() == 2 else 0
+        return C.byref(self._dyn_struct)
+
+    def plan(
+        self,
+        out: TickOutputs,
+        phases: int = capi.TL_PHASE_ALL,
+        n_ticks: int = 1,
+        actions: torch.Tensor | None = None,
+    ) -> TickPlan:
+        """Resolve a launch of ``n_ticks`` ticks once (``tl_plan_create``); ``out`` is a ring of tick slots."""
+        oo, ro = self._out_structs(out, 0)
+        obs_p = C.byref(self._obs_struct) if self._obs_struct is not None else None
+        rew_p = C.byref(self._rew_struct) if self._rew_struct is not None else None
+        dyn_p = self._dyn_pointer(phases, n_ticks, actions)
+        with torch.cuda.device(self.device):
+            handle = self.lib.tl_plan_create(C.byref(self._struct), obs_p, rew_p, dyn_p, C.byref(oo), C.byref(ro), phases, n_ticks)
+        if not handle:
+            capi.check(-1)
+        return TickPlan(self, handle, out, n_ticks, (actions, self.arena, tuple(self._luts.values())))
+
     def tick(
         self,
         out: TickOutputs,
@@ -195,22 +278,7 @@ class DeviceTownBatch:
         oo, ro = self._out_structs(out, tick0)
         obs_p = C.byref(self._obs_struct) if self._obs_struct is not None else None
         rew_p = C.byref(self._rew_struct) if self._rew_struct is not None else None
-        dyn_p = None
-        if phases & (capi.TL_PHASE_ACTIONS | capi.TL_PHASE_SOCIAL_DECAY):
-            if self._dyn_struct is None:
-                raise capi.TownletB200Error("the world-dynamics phases need a DynamicsSpec")
-            self._dyn_struct.actions = None
-            self._dyn_struct.actions_tick_stride = 0
-            if phases & capi.TL_PHASE_ACTIONS:
-                if actions is None or actions.device != self.arena.device or actions.element_size() != 4:
-                    raise capi.TownletB200Error("TL_PHASE_ACTIONS needs a 32-bit action tensor on the batch's device")
-                if not actions.is_contiguous() or actions.shape[-1] != self.n_agents:
-                    raise capi.TownletB200Error("actions must be contiguous [n_agents] or [n_ticks, n_agents]")
-                if actions.dim() == 2 and actions.shape[0] != n_ticks:
-                    raise capi.TownletB200Error("actions has the wrong number of ticks")
-                self._dyn_struct.actions = actions.data_ptr()
-                self._dyn_struct.actions_tick_stride = self.n_agents if actions.dim() == 2 else 0
-            dyn_p = C.byref(self._dyn_struct)
+        dyn_p = self._dyn_pointer(phases, n_ticks, actions)
         with torch.cuda.device(self.device):
             status = self.lib.tl_tick_world(
                 C.byref(self._struct), obs_p, rew_p, dyn_p, C.byref(oo), C.byref(ro), phases, n_ticks,

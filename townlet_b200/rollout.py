@@ -7,8 +7,9 @@ computes GAE with a Python double loop (policy/backends/pytorch/ppo_utils.py:55-
 writes straight into ``[T, N, ...]`` rollout tensors, the policy runs once per tick over all agents of all
 towns (plain torch modules -> cuBLAS; the network is not part of the hot path), and GAE is one scan kernel.
 
-Action application (movement, queueing) is upstream of the path and stays with the caller; sampled actions
-are recorded, not applied.
+A step pairs an observation, the action sampled on it, and the reward / done of the tick that applied that action
+(policy/trajectory_service.py:127-138).  With ``act_on_world`` the next tick applies the sampled moves on the
+device; otherwise action application stays with the caller and the actions are only recorded.
 """
 
 from __future__ import annotations
@@ -196,18 +197,24 @@ def sample_actions(heads: torch.Tensor, n_actions: int, seed: int, counter: torc
 
 @dataclass
 class Rollout:
-    """``[T, N, ...]`` tensors of one capture, all on the device."""
+    """``[T, N, ...]`` tensors of one capture, all on the device.
+
+    Row ``t`` pairs the observation the policy saw (``map[t]``, ``features[t]``), the action it chose on it
+    (``actions[t]``, ``log_probs[t]``, ``values[t]``) and the reward / done flag of the tick that APPLIED that action
+    (the tick after the observation) — the pairing of the reference's trajectory frames
+    (policy/trajectory_service.py:127-138).  ``values[T]`` is the policy's value of the final observation.
+    """
 
     map: torch.Tensor
     features: torch.Tensor
     rewards: torch.Tensor
     dones: torch.Tensor
-    values: torch.Tensor  # [T + 1, N], last row = bootstrap value of the final observation
+    values: torch.Tensor  # [T + 1, N], last row = the policy's value of the observation after the last tick
     actions: torch.Tensor
     log_probs: torch.Tensor
     advantages: torch.Tensor
     returns: torch.Tensor
-    kpi: torch.Tensor  # [T, towns, 8]
+    kpi: torch.Tensor  # [T, towns, 8], of the ticks that produced `rewards`
 
     def replay_batch(self, agents: slice | None = None, bootstrap: str = "value") -> dict[str, "np.ndarray"]:
         """The arrays of the reference's ``ReplayBatch`` (policy/replay.py:161-243), one sample per agent.
@@ -249,14 +256,33 @@ class GraphedRollout:
 
     graph: torch.cuda.CUDAGraph
     rollout: Rollout
+    library_launches: int = 0  # kernels of libtownlet_b200 inside one replay (counted while capturing)
 
     def replay(self) -> Rollout:
         self.graph.replay()
         return self.rollout
 
 
+@dataclass
+class _Carry:
+    """What one capture hands to the next: the last observation and the action already chosen on it."""
+
+    map: torch.Tensor
+    features: torch.Tensor
+    action: torch.Tensor
+    log_prob: torch.Tensor
+    value: torch.Tensor
+
+
 class RolloutCapture:
-    """Collect ``n_ticks`` ticks of every agent of a device batch with the policy in the loop."""
+    """Collect ``n_ticks`` steps of every agent of a device batch with the policy in the loop.
+
+    Step ``t``: the policy reads observation ``t`` and samples action ``t``; the NEXT tick applies it (with
+    ``act_on_world``) and produces reward ``t``, done ``t`` and observation ``t + 1``.  A capture of ``n_ticks``
+    steps therefore holds ``n_ticks + 1`` observations (``slots_for``); the last one — and the action already
+    sampled on it — opens the next capture, so consecutive captures form one unbroken trajectory and every tick
+    and every policy step is run exactly once.  The very first capture runs one priming tick to get observation 0.
+    """
 
     # What a sampled action index does when the policy drives the world (``act_on_world=True``): 0 waits, 1-4 move one
     # tile north / south / east / west (clamped to the grid), anything above is a kind the host services would have
@@ -277,10 +303,11 @@ class RolloutCapture:
         self.fuse_map_cast = True  # False: the policy step casts the float32 observation itself (A/B runs, tests)
         self.fuse_sampling = True  # False: log_softmax / Gumbel-max / gather as separate torch kernels (A/B runs)
         self.seed = int(torch.initial_seed())  # Philox key of tl_sample_actions
-        self._draws = torch.zeros(1, dtype=torch.int64, device=dev.device)  # ticks sampled so far (device counter)
+        self._draws = torch.zeros(1, dtype=torch.int64, device=dev.device)  # policy steps sampled so far (device counter)
         self._map_bf16: torch.Tensor | None = None
         self._feat_bf16: torch.Tensor | None = None
         self._inputs_bf16: torch.Tensor | None = None  # the combined rows the two mirrors are views of
+        self._carry: _Carry | None = None
         if act_on_world:
             if dev.dyn is None:
                 raise capi.TownletB200Error("act_on_world needs a device batch built with a DynamicsSpec")
@@ -288,6 +315,21 @@ class RolloutCapture:
             self._kind = table(self.ACTION_KIND, 4)  # TL_ACT_REQUEST for the indices without a device meaning
             self._dx, self._dy = table(self.ACTION_DX, 0), table(self.ACTION_DY, 0)
             self._words = torch.zeros(dev.n_agents, dtype=torch.int32, device=dev.device)
+
+    @staticmethod
+    def slots_for(n_ticks: int) -> int:
+        """Tick slots the output tensors of a capture of ``n_ticks`` steps need (one more observation than steps)."""
+        return n_ticks + 1
+
+    def describe(self) -> dict:
+        """What the policy step is made of (for the bench record)."""
+        fused = isinstance(self.policy, PolicyMLP) and self.autocast_dtype == torch.bfloat16 and self.fuse_map_cast
+        return {
+            "network": "ConflictAwarePolicyNetwork shape (policy/models.py:36-69): map / feature encoders 256, shared 256, 9 logits + value",
+            "arithmetic": "bfloat16 inputs and weights, float32 accumulation" if self.autocast_dtype == torch.bfloat16 else "float32",
+            "inputs": "bfloat16 rows written by the tick kernel" if fused else "float32 observation cast by the policy step",
+            "sampling": "tl_sample_actions (one kernel: log_softmax + Gumbel-max + gather)" if self.fuse_sampling else "torch ops",
+        }
 
     def _action_words(self, act: torch.Tensor) -> torch.Tensor:
         """Action words (include/townlet_b200.h: TL_ACT_PACK) of the sampled indices, from the agents' positions."""
@@ -323,72 +365,135 @@ class RolloutCapture:
             self._map_bf16, self._feat_bf16 = self.policy.input_views(self._inputs_bf16)
         return self._map_bf16
 
+    def _new_rows(self, n_ticks: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        n, device = self.dev.n_agents, self.dev.device
+        return (torch.empty((n_ticks + 1, n), dtype=torch.int64, device=device),
+                torch.empty((n_ticks + 1, n), dtype=torch.float32, device=device),
+                torch.empty((n_ticks + 1, n), dtype=torch.float32, device=device))
+
+    def _tick(self, out: TickOutputs, slot: int) -> None:
+        """One tick into ``slot``; with ``act_on_world`` it first applies the action words chosen on the previous
+        observation (moves), then decays needs and ledgers."""
+        if self.act_on_world:
+            self.dev.tick(out, capi.TL_PHASE_WORLD, 1, tick0=slot, actions=self._words)
+        else:
+            self.dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=slot)
+
+    def _policy_step(self, out: TickOutputs, slot: int, draw: int, rows, mirror) -> None:
+        """The policy on the observation in ``slot`` (just written by a tick): action, log-probability and value go to
+        row ``slot`` of ``rows``; with ``act_on_world`` the action words of the next tick are derived from the action."""
+        actions, log_probs, values = rows
+        # categorical sample by the Gumbel-max trick (argmax of log-probabilities minus log of Exp(1) noise): the
+        # same distribution as Categorical(logits).sample(), and no host sync
+        if self.fuse_sampling and mirror is not None:
+            # bfloat16 PolicyMLP: one kernel reads the fused heads product and writes action, log-prob and value
+            # straight into the rollout rows
+            heads = self.policy._forward_bf16_padded(out.map[slot], out.features[slot], self._inputs_bf16, raw_heads=True)
+            act = sample_actions(heads, self.policy.policy_head.out_features, self.seed, self._draws, draw,
+                                 with_value=True, out=(actions[slot], log_probs[slot], values[slot]))[0]
+        else:
+            logits, value = self._forward(out.map[slot], out.features[slot], mirror)
+            if self.fuse_sampling and logits.shape[1] <= capi.TL_MAX_ACTIONS:
+                act = sample_actions(logits.contiguous(), logits.shape[1], self.seed, self._draws, draw,
+                                     out=(actions[slot], log_probs[slot]))[0]
+            else:
+                logp = torch.log_softmax(logits, dim=-1)
+                act = (logp - torch.empty_like(logp).exponential_().log_()).argmax(dim=-1)
+                actions[slot], log_probs[slot] = act, logp.gather(1, act.unsqueeze(1)).squeeze(1)
+            values[slot] = value
+        if self.act_on_world:
+            self._words.copy_(self._action_words(act))
+
+    def _with_mirrors(self, out: TickOutputs):
+        mirror = self._mirror()
+        saved = (out.map_bf16, out.features_bf16)
+        out.map_bf16 = mirror
+        out.features_bf16 = self._feat_bf16 if mirror is not None else None
+        return mirror, saved
+
+    @torch.no_grad()
+    def prime(self, out: TickOutputs, n_ticks: int, rows=None) -> None:
+        """The opening observation of a trajectory: one tick into slot ``n_ticks`` (where every capture leaves its last
+        observation) and the policy's first action on it.  The reward of this tick belongs to whatever acted before
+        the trajectory and is not recorded."""
+        rows = rows or self._new_rows(n_ticks)
+        mirror, saved = self._with_mirrors(out)
+        try:
+            self._tick(out, n_ticks)
+            self._policy_step(out, n_ticks, 0, rows, mirror)
+        finally:
+            out.map_bf16, out.features_bf16 = saved
+        self._draws += 1
+        self._carry = _Carry(out.map[n_ticks], out.features[n_ticks], rows[0][n_ticks], rows[1][n_ticks], rows[2][n_ticks])
+
     def build_graph(self, n_ticks: int, out: TickOutputs | None = None) -> "GraphedRollout":
         """Capture the whole ``n_ticks`` rollout (tick launches + policy steps + GAE) in ONE CUDA graph.
 
         A tick is a handful of short kernels (the tick kernel, the policy's GEMMs, the sampling kernel); launched
-        eagerly their CPU launch cost dominates the tick.  Replaying the graph keeps the device busy; the state lives in device memory, so every
-        replay continues from where the previous rollout stopped.
+        eagerly their CPU launch cost dominates the tick.  Replaying the graph keeps the device busy; the state —
+        the towns, the last observation, the action chosen on it, the draw counter — lives in device memory, so every
+        replay continues the trajectory where the previous one stopped, and the first replay starts exactly where an
+        eager ``capture`` on the same batch would.
         """
-        out = out or self.dev.alloc_outputs(capi.TL_PHASE_ALL, n_ticks)
+        out = out or self.dev.alloc_outputs(capi.TL_PHASE_ALL, self.slots_for(n_ticks))
+        rows = self._new_rows(n_ticks)
+        lib = capi.load_library()
         stream = torch.cuda.Stream(self.dev.device)
         stream.wait_stream(torch.cuda.current_stream(self.dev.device))
         with torch.cuda.stream(stream):  # warm-up outside the capture: lazy cuBLAS / allocator initialisation
-            self.dev_state = self.dev.arena.clone()
+            arena = self.dev.arena.clone()
+            draws = self._draws.clone()
+            words = self._words.clone() if self.act_on_world else None
+            carry = self._carry
             self.capture(min(2, n_ticks), out)
-            self.dev.arena.copy_(self.dev_state)
+            # everything the warm-up advanced goes back: the graph starts from the caller's state
+            self.dev.arena.copy_(arena)
+            self._draws.copy_(draws)
+            if words is not None:
+                self._words.copy_(words)
+            self._carry = carry
+            if self._carry is None:
+                self.prime(out, n_ticks, rows)  # observation 0 and its action, into the slot / rows the replays carry over
+            else:  # continue an eager trajectory: its last observation moves into the graph's carry slot
+                c = self._carry
+                out.map[n_ticks].copy_(c.map), out.features[n_ticks].copy_(c.features)
+                rows[0][n_ticks].copy_(c.action), rows[1][n_ticks].copy_(c.log_prob), rows[2][n_ticks].copy_(c.value)
+                self._carry = _Carry(out.map[n_ticks], out.features[n_ticks], rows[0][n_ticks], rows[1][n_ticks], rows[2][n_ticks])
         torch.cuda.current_stream(self.dev.device).wait_stream(stream)
         torch.cuda.synchronize(self.dev.device)
         graph = torch.cuda.CUDAGraph()
+        before = lib.tl_launch_count()
         with torch.cuda.graph(graph):
-            rollout = self.capture(n_ticks, out)
-        return GraphedRollout(graph, rollout)
+            rollout = self.capture(n_ticks, out, rows)
+        return GraphedRollout(graph, rollout, int(lib.tl_launch_count() - before))
 
     @torch.no_grad()
-    def capture(self, n_ticks: int, out: TickOutputs | None = None) -> Rollout:
+    def capture(self, n_ticks: int, out: TickOutputs | None = None, rows=None) -> Rollout:
+        """``n_ticks`` steps; ``out`` needs ``slots_for(n_ticks)`` tick slots (slot ``t`` = observation ``t``)."""
         dev = self.dev
-        n = dev.n_agents
-        out = out or dev.alloc_outputs(capi.TL_PHASE_ALL, n_ticks)
-        values = torch.empty((n_ticks + 1, n), dtype=torch.float32, device=dev.device)
-        actions = torch.empty((n_ticks, n), dtype=torch.int64, device=dev.device)
-        log_probs = torch.empty((n_ticks, n), dtype=torch.float32, device=dev.device)
-        mirror = self._mirror()
-        caller_mirror, out.map_bf16 = (out.map_bf16, out.features_bf16), mirror
-        out.features_bf16 = self._feat_bf16 if mirror is not None else None
+        out = out or dev.alloc_outputs(capi.TL_PHASE_ALL, self.slots_for(n_ticks))
+        if out.map is None or out.map.shape[0] < n_ticks + 1:
+            raise capi.TownletB200Error(f"a capture of {n_ticks} steps needs outputs with {n_ticks + 1} tick slots (slots_for)")
+        rows = rows or self._new_rows(n_ticks)
+        actions, log_probs, values = rows
+        if self._carry is None:
+            self.prime(out, n_ticks, rows)
+        c = self._carry
+        if c.map.data_ptr() != out.map[0].data_ptr():  # observation 0 = the last observation of the previous capture
+            out.map[0].copy_(c.map), out.features[0].copy_(c.features)
+        actions[0].copy_(c.action), log_probs[0].copy_(c.log_prob), values[0].copy_(c.value)
+        mirror, saved = self._with_mirrors(out)
         try:
             for t in range(n_ticks):
-                # obs / reward / done of tick t land in slot t; with act_on_world the tick first applies the action words
-                # the policy chose on the previous observation (moves), then decays needs and ledgers
-                if self.act_on_world:
-                    dev.tick(out, capi.TL_PHASE_WORLD, 1, tick0=t, actions=self._words)
-                else:
-                    dev.tick(out, capi.TL_PHASE_ALL, 1, tick0=t)
-                # categorical sample by the Gumbel-max trick (argmax of log-probabilities minus log of Exp(1) noise): the
-                # same distribution as Categorical(logits).sample(), and no host sync
-                if self.fuse_sampling and mirror is not None:
-                    # bfloat16 PolicyMLP: one kernel reads the fused heads product and writes action, log-prob and value
-                    # straight into the rollout rows
-                    heads = self.policy._forward_bf16_padded(out.map[t], out.features[t], self._inputs_bf16, raw_heads=True)
-                    act = sample_actions(heads, self.policy.policy_head.out_features, self.seed, self._draws, t,
-                                         with_value=True, out=(actions[t], log_probs[t], values[t]))[0]
-                else:
-                    logits, value = self._forward(out.map[t], out.features[t], mirror)
-                    if self.fuse_sampling and logits.shape[1] <= capi.TL_MAX_ACTIONS:
-                        act = sample_actions(logits.contiguous(), logits.shape[1], self.seed, self._draws, t,
-                                             out=(actions[t], log_probs[t]))[0]
-                    else:
-                        logp = torch.log_softmax(logits, dim=-1)
-                        act = (logp - torch.empty_like(logp).exponential_().log_()).argmax(dim=-1)
-                        actions[t], log_probs[t] = act, logp.gather(1, act.unsqueeze(1)).squeeze(1)
-                    values[t] = value
-                if self.act_on_world:
-                    self._words.copy_(self._action_words(act))
+                self._tick(out, t + 1)  # applies action t; reward / done of step t and observation t + 1 land in slot t + 1
+                self._policy_step(out, t + 1, t, rows, mirror)
         finally:
-            out.map_bf16, out.features_bf16 = caller_mirror
+            out.map_bf16, out.features_bf16 = saved
         self._draws += n_ticks  # on the device: the next capture (or graph replay) draws fresh numbers
-        # bootstrap value: the policy on the last observation (no further tick is simulated)
-        values[n_ticks] = values[n_ticks - 1] if n_ticks else 0.0
-        dones = out.terminated[:n_ticks].float()
-        advantages, returns = gae(out.reward[:n_ticks], values, dones, self.gamma, self.gae_lambda)
-        return Rollout(out.map[:n_ticks], out.features[:n_ticks], out.reward[:n_ticks], dones, values, actions,
-                       log_probs, advantages, returns, out.kpi[:n_ticks])
+        self._carry = _Carry(out.map[n_ticks], out.features[n_ticks], actions[n_ticks], log_probs[n_ticks], values[n_ticks])
+        rewards = out.reward[1 : n_ticks + 1]
+        dones = out.terminated[1 : n_ticks + 1].float()
+        # values[n_ticks] is the policy's value of the final observation: the bootstrap row of GAE
+        advantages, returns = gae(rewards, values, dones, self.gamma, self.gae_lambda)
+        return Rollout(out.map[:n_ticks], out.features[:n_ticks], rewards, dones, values, actions[:n_ticks],
+                       log_probs[:n_ticks], advantages, returns, out.kpi[1 : n_ticks + 1])

@@ -219,6 +219,9 @@ class TownBatch:
         s.grid_h = self.grid_h
         for name in FIELD_NAMES:
             setattr(s, name, C.c_void_p(base_ptr + lay.offsets[name]))
+        # the arrays share one block: the host-buffer entry points may move it with a single copy
+        s.arena_base = C.c_void_p(base_ptr)
+        s.arena_bytes = lay.total_bytes
         if not self.has_social_in:
             s.social_in = None
         if not self.has_personality:
