@@ -417,7 +417,7 @@ typedef void* tl_stream_t; /* cudaStream_t */
 const char* tl_last_error(void);
 int tl_abi_version(void);
 /* sizeof of the idx-th ABI struct (0 TlTownBatch, 1 TlObsParams, 2 TlRewardParams,
- * 3 TlObsOut, 4 TlRewardOut, 5 TlDynamicsParams) so bindings can verify their layout; -1 otherwise */
+ * 3 TlObsOut, 4 TlRewardOut, 5 TlDynamicsParams, 6 TlHostStep) so bindings can verify their layout; -1 otherwise */
 int tl_abi_struct_size(int idx);
 /* number of SMs of the current device, or a negative error */
 int tl_device_sm_count(void);
@@ -516,12 +516,82 @@ int tl_sample_actions(const void* heads, int32_t heads_dtype, int64_t n_rows, in
                       const int64_t* counter, int64_t offset, int64_t* actions, float* log_probs, float* values,
                       tl_stream_t stream);
 
-/* Host-buffer entry: every pointer (batch, LUTs, outputs) is HOST memory.
- * Copies the batch to the context's device arena, runs tl_tick, copies the
- * requested outputs and the mutated state back, and synchronises. */
+/*
+ * Host-buffer entries: every pointer (batch, LUTs, outputs) is HOST memory — what a binding under
+ * WorldContext.observe (world/core/context.py:163-168) calls when the world state lives in host memory.
+ *
+ * A context owns TL_HOST_SLOTS independent slots (stream, device arena, device outputs, pinned staging).  A step
+ * is SUBMITTED to a slot (host->device copies, kernels and device->host copies are enqueued, nothing waits) and
+ * later WAITED for; steps in different slots overlap — the upload of one rides the bus while the download of
+ * another comes back (PCIe is full duplex) — so a caller that keeps two batches in flight (two halves of its
+ * towns, or two independent vectors of towns) pays max(up, down) per step instead of up + kernel + down.
+ *
+ * The observation map is 84 % of the bytes that come back and every cell of its integer channels is a small
+ * non-negative integer (0 / 1 in hybrid and full, counts in compact).  `wire` selects how the map crosses the bus:
+ *   TL_WIRE_F32   float32 cells as they are (4 bytes per cell);
+ *   TL_WIRE_U8    one byte per cell of the integer channels;
+ *   TL_WIRE_BITS  one bit per cell (0 / 1 channels only; a count above 1 fails the step with TL_ERR_UNSUPPORTED).
+ * The two agent-independent path channels of the full variant (encoders/map.py:115-125) never cross the bus in the
+ * narrow formats: the host writes them from obs->path_lut.  `map_format` selects what obs_out->map receives:
+ *   TL_MAP_F32    the reference's float32 [N][C][W][W] tensor, bit-identical whatever the wire (the narrow formats
+ *                 are expanded by the context's host threads inside tl_host_wait);
+ *   TL_MAP_WIRE   the wire bytes themselves: rows of tl_wire_row_bytes() bytes per agent — uint8 [N][row] cells in
+ *                 channel-major order, or packed bits (cell i = bit i % 32 of little-endian word i / 32), integer
+ *                 channels only.  obs_out->map_tick_stride is then in BYTES.
+ */
+#define TL_HOST_SLOTS 4
+#define TL_WIRE_F32 0
+#define TL_WIRE_U8 1
+#define TL_WIRE_BITS 2
+#define TL_MAP_F32 0
+#define TL_MAP_WIRE 1
+
+/* index of every array of TlTownBatch in TlHostStep.dirty_fields (declaration order) */
+enum {
+    TL_FIELD_TOWN_AGENT_OFF = 0, TL_FIELD_TOWN_ENT_OFF, TL_FIELD_TOWN_TICK, TL_FIELD_ENT, TL_FIELD_POS, TL_FIELD_NEEDS,
+    TL_FIELD_WALLET, TL_FIELD_ATTENDANCE, TL_FIELD_WAGES_WITHHELD, TL_FIELD_WAGES_PAID, TL_FIELD_PUNCTUALITY,
+    TL_FIELD_EPISODE_TOTAL, TL_FIELD_SOCIAL_IN, TL_FIELD_TERM_BLOCK_TICK, TL_FIELD_LATENESS, TL_FIELD_LAST_ACTION_DURATION,
+    TL_FIELD_EPISODE_TICK, TL_FIELD_SLOT, TL_FIELD_FLAGS, TL_FIELD_LAST_ACTION_HASH, TL_FIELD_PERSONALITY, TL_FIELD_TIE_COUNT,
+    TL_FIELD_TIE_EMBED, TL_FIELD_TIE_TRUST, TL_FIELD_TIE_FAM, TL_FIELD_TIE_RIV, TL_FIELD_RIV_COUNT, TL_FIELD_RIV_EMBED,
+    TL_FIELD_RIV_SCORE, TL_N_FIELDS
+};
+#define TL_DIRTY_ALL (~(uint64_t)0)
+
+typedef struct TlHostStep {
+    const TlTownBatch* batch;   /* HOST arrays */
+    const TlObsParams* obs;     /* HOST look-up tables; may be NULL without TL_PHASE_OBS / TL_PHASE_ADVANCE */
+    const TlRewardParams* rew;  /* may be NULL without TL_PHASE_DECAY / TL_PHASE_REWARD */
+    const TlDynamicsParams* dyn;/* may be NULL without the world-dynamics phases; dyn->actions is HOST memory */
+    const TlObsOut* obs_out;    /* HOST buffers (the bfloat16 mirrors are device-only and ignored) */
+    const TlRewardOut* rew_out; /* HOST buffers */
+    uint32_t phases;
+    int32_t n_ticks;
+    /* The slot keeps the batch RESIDENT on the device between steps.  Bit i set = array i (TL_FIELD_*) changed on the
+     * host since this slot's previous step and is uploaded; clear = the device copy (as the previous steps left it,
+     * including the state the ticks advanced) is used.  TL_DIRTY_ALL uploads everything; a slot's first step, or a
+     * step whose sizes differ from the resident batch, always does. */
+    uint64_t dirty_fields;
+    int32_t wire;       /* TL_WIRE_* */
+    int32_t map_format; /* TL_MAP_* */
+    int32_t writeback;  /* 1 = the arrays the phases mutate are copied back into the host batch; 0 = they stay on the device */
+    int32_t reserved0;
+} TlHostStep;
+
 typedef struct TlContext TlContext;
 TlContext* tl_context_create(int device);
 void tl_context_destroy(TlContext* ctx);
+/* host threads that expand narrow wire formats and copy staged outputs inside tl_host_wait (default: up to 8) */
+int tl_context_set_threads(TlContext* ctx, int32_t n_threads);
+/* bytes per agent row of the map on the wire (TL_MAP_WIRE buffers are [n_ticks][N][row]); negative on error */
+int64_t tl_wire_row_bytes(const TlObsParams* obs, int32_t wire);
+/* enqueue one step on slot 0 <= slot < TL_HOST_SLOTS; the slot must not have a step pending.  Every host buffer of
+ * the step must stay valid until tl_host_wait returns.  Pinned (page-locked) buffers are copied directly; pageable
+ * ones go through the context's pinned staging and are filled inside tl_host_wait. */
+int tl_host_submit(TlContext* ctx, int32_t slot, const TlHostStep* step);
+/* wait for the slot's pending step, expand / scatter what was staged; after it returns every output of the step
+ * (and, with writeback, the mutated state arrays) is in the caller's buffers */
+int tl_host_wait(TlContext* ctx, int32_t slot);
+/* one synchronous step on slot 0: float32 wire, everything uploaded, state written back (ABI v1-v3 behaviour) */
 int tl_host_tick(TlContext* ctx, const TlTownBatch* host_batch, const TlObsParams* obs,
                  const TlRewardParams* rew, const TlObsOut* host_obs_out, const TlRewardOut* host_rew_out,
                  uint32_t phases, int32_t n_ticks);
@@ -530,7 +600,7 @@ int tl_host_tick(TlContext* ctx, const TlTownBatch* host_batch, const TlObsParam
 int tl_host_tick_world(TlContext* ctx, const TlTownBatch* host_batch, const TlObsParams* obs,
                        const TlRewardParams* rew, const TlDynamicsParams* dyn, const TlObsOut* host_obs_out,
                        const TlRewardOut* host_rew_out, uint32_t phases, int32_t n_ticks);
-/* bytes moved by the last tl_host_tick / tl_host_tick_world call */
+/* bytes moved over the bus by the last submitted step */
 int64_t tl_context_last_h2d_bytes(const TlContext* ctx);
 int64_t tl_context_last_d2h_bytes(const TlContext* ctx);
 

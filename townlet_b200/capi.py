@@ -253,6 +253,31 @@ class TlDynamicsParams(C.Structure):
     ]
 
 
+class TlHostStep(C.Structure):
+    _fields_ = [
+        ("batch", C.POINTER(TlTownBatch)),
+        ("obs", C.POINTER(TlObsParams)),
+        ("rew", C.POINTER(TlRewardParams)),
+        ("dyn", C.POINTER(TlDynamicsParams)),
+        ("obs_out", C.POINTER(TlObsOut)),
+        ("rew_out", C.POINTER(TlRewardOut)),
+        ("phases", C.c_uint32),
+        ("n_ticks", C.c_int32),
+        ("dirty_fields", C.c_uint64),
+        ("wire", C.c_int32),
+        ("map_format", C.c_int32),
+        ("writeback", C.c_int32),
+        ("reserved0", C.c_int32),
+    ]
+
+
+TL_HOST_SLOTS = 4
+TL_WIRE = {"f32": 0, "u8": 1, "bits": 2}
+TL_MAP_F32, TL_MAP_WIRE = 0, 1
+TL_DIRTY_ALL = 2**64 - 1
+# index of every TlTownBatch array in TlHostStep.dirty_fields (declaration order of the struct)
+FIELD_INDEX = {name: i for i, (name, _) in enumerate(TlTownBatch._fields_[8:37])}
+
 EXPORTED_SYMBOLS = (
     "tl_last_error",
     "tl_abi_version",
@@ -277,6 +302,10 @@ EXPORTED_SYMBOLS = (
     "tl_sample_actions",
     "tl_context_create",
     "tl_context_destroy",
+    "tl_context_set_threads",
+    "tl_wire_row_bytes",
+    "tl_host_submit",
+    "tl_host_wait",
     "tl_host_tick",
     "tl_host_tick_world",
     "tl_context_last_h2d_bytes",
@@ -417,6 +446,14 @@ def load_library() -> C.CDLL:
     lib.tl_context_create.argtypes = [C.c_int]
     lib.tl_context_destroy.restype = None
     lib.tl_context_destroy.argtypes = [_p]
+    lib.tl_context_set_threads.restype = C.c_int
+    lib.tl_context_set_threads.argtypes = [_p, C.c_int32]
+    lib.tl_wire_row_bytes.restype = C.c_int64
+    lib.tl_wire_row_bytes.argtypes = [C.POINTER(TlObsParams), C.c_int32]
+    lib.tl_host_submit.restype = C.c_int
+    lib.tl_host_submit.argtypes = [_p, C.c_int32, C.POINTER(TlHostStep)]
+    lib.tl_host_wait.restype = C.c_int
+    lib.tl_host_wait.argtypes = [_p, C.c_int32]
     lib.tl_host_tick.restype = C.c_int
     lib.tl_host_tick.argtypes = [
         _p,
@@ -446,7 +483,7 @@ def load_library() -> C.CDLL:
     lib.tl_context_last_d2h_bytes.argtypes = [_p]
     if lib.tl_abi_version() != TL_ABI_VERSION:
         raise TownletB200Error("libtownlet_b200.so ABI version mismatch")
-    for idx, struct in enumerate((TlTownBatch, TlObsParams, TlRewardParams, TlObsOut, TlRewardOut, TlDynamicsParams)):
+    for idx, struct in enumerate((TlTownBatch, TlObsParams, TlRewardParams, TlObsOut, TlRewardOut, TlDynamicsParams, TlHostStep)):
         if lib.tl_abi_struct_size(idx) != C.sizeof(struct):
             raise TownletB200Error(
                 f"struct layout mismatch for {struct.__name__}: C {lib.tl_abi_struct_size(idx)} vs ctypes {C.sizeof(struct)}"

@@ -806,6 +806,7 @@ int tl_abi_struct_size(int idx) {
         case 3: return (int)sizeof(TlObsOut);
         case 4: return (int)sizeof(TlRewardOut);
         case 5: return (int)sizeof(TlDynamicsParams);
+        case 6: return (int)sizeof(TlHostStep);
         default: return -1;
     }
 }
@@ -996,279 +997,6 @@ int tl_plan_grid(const TlPlan* plan, int32_t* grid, int32_t* threads, int32_t* s
     return TL_OK;
 }
 
-// ---- host-buffer context ----------------------------------------------------
-struct TlContext {
-    int device;
-    cudaStream_t stream;
-    unsigned char* d_arena;
-    size_t arena_cap;
-    unsigned char* d_out;
-    size_t out_cap;
-    int64_t last_h2d, last_d2h;
-};
-
-TlContext* tl_context_create(int device) {
-    if (!cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return nullptr;
-    TlContext* ctx = new TlContext();
-    memset(ctx, 0, sizeof(*ctx));
-    ctx->device = device;
-    if (!cuda_ok(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
-        delete ctx;
-        return nullptr;
-    }
-    return ctx;
-}
-
-void tl_context_destroy(TlContext* ctx) {
-    if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    if (ctx->d_arena) cudaFree(ctx->d_arena);
-    if (ctx->d_out) cudaFree(ctx->d_out);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
-}
-
-int64_t tl_context_last_h2d_bytes(const TlContext* ctx) { return ctx ? ctx->last_h2d : 0; }
-int64_t tl_context_last_d2h_bytes(const TlContext* ctx) { return ctx ? ctx->last_d2h : 0; }
-
-namespace {
-
-struct Span {
-    const void* host;
-    void** slot;   // pointer field inside the device copy of the struct
-    size_t bytes;
-    bool writeback;
-};
-
-bool ensure(unsigned char** buf, size_t* cap, size_t need) {
-    if (need <= *cap) return true;
-    if (*buf) cudaFree(*buf);
-    *buf = nullptr;
-    *cap = 0;
-    size_t want = need + need / 4 + 4096;
-    if (!cuda_ok(cudaMalloc(reinterpret_cast<void**>(buf), want), "cudaMalloc")) return false;
-    *cap = want;
-    return true;
-}
-
-}  // namespace
-
-int tl_host_tick(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, const TlRewardParams* rew,
-                 const TlObsOut* hoo, const TlRewardOut* hro, uint32_t phases, int32_t n_ticks) {
-    if (phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY))
-        return set_error("the world-dynamics phases need TlDynamicsParams (tl_host_tick_world)"), TL_ERR_ARG;
-    return tl_host_tick_world(ctx, hb, obs, rew, nullptr, hoo, hro, phases, n_ticks);
-}
-
-int tl_host_tick_world(TlContext* ctx, const TlTownBatch* hb, const TlObsParams* obs, const TlRewardParams* rew,
-                       const TlDynamicsParams* dyn, const TlObsOut* hoo, const TlRewardOut* hro, uint32_t phases,
-                       int32_t n_ticks) {
-    if (!ctx) return set_error("context is NULL"), TL_ERR_ARG;
-    int rc = validate(hb, obs, rew, dyn, hoo, hro, phases, n_ticks);
-    if (rc != TL_OK) return rc;
-    if (!cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return TL_ERR_CUDA;
-    ctx->last_h2d = ctx->last_d2h = 0;
-    if (hb->n_towns == 0 || n_ticks == 0) return TL_OK;
-
-    const size_t T = hb->n_towns, N = hb->n_agents, E = hb->n_entities, K = hb->max_edges, EW = hb->embed_words;
-    TlTownBatch db = *hb;
-    TlObsParams dobs;
-    memset(&dobs, 0, sizeof(dobs));
-    if (obs) dobs = *obs;
-    const bool do_obs = phases & TL_PHASE_OBS;
-    const bool do_state = phases & (TL_PHASE_DECAY | TL_PHASE_REWARD);
-    const bool do_adv = phases & TL_PHASE_ADVANCE;
-    const bool do_act = phases & TL_PHASE_ACTIONS;       // rewrites positions, agent entity words, last-action fields
-    const bool do_led = phases & TL_PHASE_SOCIAL_DECAY;  // rewrites the relationship and rivalry ledgers
-    TlDynamicsParams ddyn;
-    memset(&ddyn, 0, sizeof(ddyn));
-    if (dyn) ddyn = *dyn;
-
-    Span spans[48];
-    int ns = 0;
-    auto add = [&](const void* host, void** slot, size_t bytes, bool wb) {
-        if (!host || bytes == 0) {
-            if (slot && !host) *slot = nullptr;
-            return;
-        }
-        spans[ns++] = Span{host, slot, bytes, wb};
-    };
-#define FIELD(name, bytes, wb) add(hb->name, (void**)&db.name, (bytes), (wb))
-    FIELD(town_agent_off, (T + 1) * 4, false);
-    FIELD(town_ent_off, (T + 1) * 4, false);
-    FIELD(town_tick, T * 4, do_adv);
-    FIELD(ent, E * 4, do_act);
-    FIELD(pos, N * 4, do_act);
-    FIELD(needs, 3 * N * 8, (phases & TL_PHASE_DECAY) != 0);
-    FIELD(wallet, N * 8, false);
-    FIELD(attendance, N * 8, false);
-    FIELD(wages_withheld, N * 8, false);
-    FIELD(wages_paid, N * 8, false);
-    FIELD(punctuality, N * 8, false);
-    FIELD(episode_total, N * 8, (phases & TL_PHASE_REWARD) != 0);
-    FIELD(social_in, 3 * N * 8, false);
-    FIELD(term_block_tick, N * 4, (phases & TL_PHASE_REWARD) != 0);
-    FIELD(lateness, N * 4, false);
-    FIELD(last_action_duration, N * 4, do_act);
-    FIELD(episode_tick, N * 4, do_adv);
-    FIELD(slot, N * 4, false);
-    FIELD(flags, N * 4, do_state || do_act || do_obs);  // the observation consumes TL_F_CTX_RESET
-    FIELD(last_action_hash, N * 4, do_act);
-    FIELD(personality, 3 * N * 4, false);
-    FIELD(tie_count, N, do_led);
-    FIELD(tie_embed, N * K * EW * 8, do_led);
-    FIELD(tie_trust, N * K * 8, do_led);
-    FIELD(tie_fam, N * K * 8, do_led);
-    FIELD(tie_riv, N * K * 8, do_led);
-    FIELD(riv_count, N, do_led);
-    FIELD(riv_embed, N * K * EW * 8, do_led);
-    FIELD(riv_score, N * K * 8, do_led);
-#undef FIELD
-    const int n_batch_spans = ns;
-    if (do_act)  // action words of the launch, [n_ticks][N] with the caller's tick stride
-        add(dyn->actions, (void**)&ddyn.actions, ((size_t)(n_ticks - 1) * (size_t)dyn->actions_tick_stride + N) * 4, false);
-    if (do_obs) {
-        const size_t W2 = (size_t)obs->window * obs->window, R = obs->window / 2;
-        add(obs->time_lut, (void**)&dobs.time_lut, (size_t)obs->ticks_per_day * 2 * 4, false);
-        add(obs->progress_lut, (void**)&dobs.progress_lut, ((size_t)obs->ticks_per_day + 1) * 4, false);
-        add(obs->slot_lut, (void**)&dobs.slot_lut, (size_t)obs->max_slots * 4, false);
-        add(obs->agent_ratio_lut, (void**)&dobs.agent_ratio_lut, W2 * 4, false);
-        add(obs->tile_ratio_lut, (void**)&dobs.tile_ratio_lut, (W2 + 1) * 4, false);
-        add(obs->nearest_lut, (void**)&dobs.nearest_lut, (2 * R * R + 1) * 4, false);
-        add(obs->path_lut, (void**)&dobs.path_lut, 2 * W2 * 4, false);
-        add(obs->embed_lut, (void**)&dobs.embed_lut, 256 * 4, false);
-    }
-
-    // One copy for the whole batch only when the caller DECLARES that its arrays share one block
-    // (TlTownBatch.arena_base / arena_bytes); otherwise one copy per array and nothing else is touched.
-    uintptr_t lo = 0, hi = 0;
-    bool contiguous = false;
-    if (hb->arena_base && hb->arena_bytes > 0 && n_batch_spans > 0) {
-        lo = (uintptr_t)hb->arena_base;
-        hi = lo + (size_t)hb->arena_bytes;
-        for (int i = 0; i < n_batch_spans; ++i) {
-            const uintptr_t p0 = (uintptr_t)spans[i].host;
-            if (p0 < lo || p0 + spans[i].bytes > hi)
-                return set_error("an array of the batch lies outside [arena_base, arena_base + arena_bytes)"), TL_ERR_ARG;
-        }
-        contiguous = true;
-    }
-    size_t need = 0;
-    if (contiguous) need = round_up((int)((hi - lo + 255) / 256), 1) * (size_t)256;
-    size_t cursor = need;
-    size_t dev_off[48];
-    for (int i = 0; i < ns; ++i) {
-        if (contiguous && i < n_batch_spans) {
-            dev_off[i] = (uintptr_t)spans[i].host - lo;
-        } else {
-            dev_off[i] = cursor;
-            cursor += (spans[i].bytes + 255) / 256 * 256;
-        }
-    }
-    if (!ensure(&ctx->d_arena, &ctx->arena_cap, cursor)) return TL_ERR_CUDA;
-    if (contiguous) {
-        if (!cuda_ok(cudaMemcpyAsync(ctx->d_arena, (const void*)lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream), "H2D arena"))
-            return TL_ERR_CUDA;
-        ctx->last_h2d += (int64_t)(hi - lo);
-    }
-    for (int i = 0; i < ns; ++i) {
-        *spans[i].slot = ctx->d_arena + dev_off[i];
-        if (contiguous && i < n_batch_spans) continue;
-        if (!cuda_ok(cudaMemcpyAsync(ctx->d_arena + dev_off[i], spans[i].host, spans[i].bytes, cudaMemcpyHostToDevice,
-                                     ctx->stream),
-                     "H2D field"))
-            return TL_ERR_CUDA;
-        ctx->last_h2d += (int64_t)spans[i].bytes;
-    }
-
-    // outputs
-    TlObsOut doo;
-    TlRewardOut dro;
-    memset(&doo, 0, sizeof(doo));
-    memset(&dro, 0, sizeof(dro));
-    struct OutSpan {
-        void* host;
-        size_t off, bytes;
-    } outs[8];
-    int no = 0;
-    size_t ocur = 0;
-    auto add_out = [&](void* host, size_t bytes) -> size_t {
-        const size_t off = ocur;
-        outs[no++] = OutSpan{host, off, bytes};
-        ocur += (bytes + 255) / 256 * 256;
-        return off;
-    };
-    size_t o_map = 0, o_feat = 0, o_sum = 0, o_rew = 0, o_comps = 0, o_term = 0, o_kpi = 0;
-    const size_t nt = (size_t)n_ticks;
-    if (do_obs) {
-        const size_t me = (size_t)obs->n_channels * obs->window * obs->window;
-        doo = *hoo;
-        doo.map_bf16 = nullptr;  // device entry points only
-        doo.features_bf16 = nullptr;
-        auto span_elems = [&](int64_t stride, size_t per_tick) { return (nt - 1) * (size_t)stride + per_tick; };
-        o_map = add_out(hoo->map, span_elems(hoo->map_tick_stride, N * me) * 4);
-        o_feat = add_out(hoo->features, span_elems(hoo->features_tick_stride, N * (size_t)obs->n_features) * 4);
-        if (hoo->summary) o_sum = add_out(hoo->summary, span_elems(hoo->summary_tick_stride, N * TL_N_SUMMARY) * 4);
-    }
-    if (do_state && hro) {
-        dro = *hro;
-        auto span_elems = [&](int64_t stride, size_t per_tick) { return (nt - 1) * (size_t)stride + per_tick; };
-        if (hro->reward) o_rew = add_out(hro->reward, span_elems(hro->reward_tick_stride, N) * 4);
-        if (hro->comps) o_comps = add_out(hro->comps, span_elems(hro->comps_tick_stride, N * TL_N_COMPS) * 8);
-        if (hro->terminated) o_term = add_out(hro->terminated, span_elems(hro->terminated_tick_stride, N));
-        if (hro->kpi) o_kpi = add_out(hro->kpi, span_elems(hro->kpi_tick_stride, T * TL_N_KPI) * 4);
-    }
-    if (!ensure(&ctx->d_out, &ctx->out_cap, ocur ? ocur : 256)) return TL_ERR_CUDA;
-    if (do_obs) {
-        doo.map = (float*)(ctx->d_out + o_map);
-        doo.features = (float*)(ctx->d_out + o_feat);
-        doo.summary = hoo->summary ? (int32_t*)(ctx->d_out + o_sum) : nullptr;
-    }
-    if (do_state && hro) {
-        dro.reward = hro->reward ? (float*)(ctx->d_out + o_rew) : nullptr;
-        dro.comps = hro->comps ? (double*)(ctx->d_out + o_comps) : nullptr;
-        dro.terminated = hro->terminated ? (uint8_t*)(ctx->d_out + o_term) : nullptr;
-        dro.kpi = hro->kpi ? (float*)(ctx->d_out + o_kpi) : nullptr;
-    }
-
-    rc = launch(&db, obs ? &dobs : nullptr, rew, dyn ? &ddyn : nullptr, do_obs ? &doo : nullptr,
-                (do_state && hro) ? &dro : nullptr, phases, n_ticks, ctx->stream, 0);
-    if (rc != TL_OK) return rc;
-
-    for (int i = 0; i < no; ++i) {
-        if (!cuda_ok(cudaMemcpyAsync(outs[i].host, ctx->d_out + outs[i].off, outs[i].bytes, cudaMemcpyDeviceToHost, ctx->stream),
-                     "D2H output"))
-            return TL_ERR_CUDA;
-        ctx->last_d2h += (int64_t)outs[i].bytes;
-    }
-    // Mutated state goes back.  When the batch is one host arena whose mutated fields sit together (the layout of
-    // soa.py puts them first), one copy covers them: the bytes in between are unchanged and equal on both sides.
-    uintptr_t wlo = UINTPTR_MAX, whi = 0;
-    size_t wsum = 0;
-    for (int i = 0; i < n_batch_spans; ++i) {
-        if (!spans[i].writeback) continue;
-        const uintptr_t p0 = (uintptr_t)spans[i].host;
-        wlo = p0 < wlo ? p0 : wlo;
-        whi = p0 + spans[i].bytes > whi ? p0 + spans[i].bytes : whi;
-        wsum += spans[i].bytes;
-    }
-    if (contiguous && wsum > 0 && (whi - wlo) <= wsum + wsum / 2 + 4096) {  // [wlo, whi) lies inside the declared arena
-        if (!cuda_ok(cudaMemcpyAsync((void*)wlo, ctx->d_arena + (wlo - lo), whi - wlo, cudaMemcpyDeviceToHost, ctx->stream),
-                     "D2H state"))
-            return TL_ERR_CUDA;
-        ctx->last_d2h += (int64_t)(whi - wlo);
-    } else {
-        for (int i = 0; i < n_batch_spans; ++i) {
-            if (!spans[i].writeback) continue;
-            if (!cuda_ok(cudaMemcpyAsync(const_cast<void*>(spans[i].host), ctx->d_arena + dev_off[i], spans[i].bytes,
-                                         cudaMemcpyDeviceToHost, ctx->stream),
-                         "D2H state"))
-                return TL_ERR_CUDA;
-            ctx->last_d2h += (int64_t)spans[i].bytes;
-        }
-    }
-    if (!cuda_ok(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize")) return TL_ERR_CUDA;
-    return TL_OK;
-}
-
 }  // extern "C"
+
+#include "host_path.cuh"

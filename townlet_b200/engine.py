@@ -306,24 +306,30 @@ class DeviceTownBatch:
 
 
 class HostEngine:
-    """Host-buffer path: one ``tl_host_tick`` call = H2D + kernels + D2H + sync.
+    """Host-buffer path: every array (batch, look-up tables, outputs) is HOST memory.
 
-    This is what the drop-in services use and what the bench's ``e2e`` times.
-    Buffers may be pinned (``pin=True`` allocates them with torch) so copies
-    run at full PCIe rate.
+    ``tick`` is one synchronous step (``tl_host_tick_world``: H2D + kernels + D2H + sync) — what the drop-in
+    services use.  ``submit`` / ``wait`` are the pipelined form (``tl_host_submit`` / ``tl_host_wait``): up to
+    ``capi.TL_HOST_SLOTS`` steps in flight, each slot keeping its batch resident on the device, the map crossing
+    the bus as float32, uint8 or bits (``wire``) and arriving as the reference's float32 tensor (expanded by the
+    context's host threads) or as the wire bytes themselves (``map_format="wire"``).  Buffers may be pinned
+    (``pin=True`` allocates them with torch) so copies run at full PCIe rate and without staging.
     """
 
-    def __init__(self, obs: ObsSpec | None, rew: RewardSpec | None, device: int = 0) -> None:
+    def __init__(self, obs: ObsSpec | None, rew: RewardSpec | None, device: int = 0, threads: int | None = None) -> None:
         self.lib = capi.load_library()
         self.obs = obs
         self.rew = rew
         self.ctx = self.lib.tl_context_create(device)
         if not self.ctx:
             capi.check(-2)
+        if threads is not None:
+            capi.check(self.lib.tl_context_set_threads(self.ctx, int(threads)))
         self._luts = {k: np.ascontiguousarray(v) for k, v in obs.luts().items()} if obs is not None else {}
         self._obs_struct = obs.struct({k: v.ctypes.data for k, v in self._luts.items()}) if obs is not None else None
         self._rew_struct = rew.struct() if rew is not None else None
         self._pinned: list[torch.Tensor] = []
+        self._inflight: dict[int, tuple] = {}  # slot -> ctypes objects and arrays the pending step points at
 
     def close(self) -> None:
         if self.ctx:
@@ -344,15 +350,35 @@ class HostEngine:
         self._pinned.append(t)
         return t.numpy()[: int(np.prod(shape, dtype=np.int64)) * np_dtype.itemsize].view(np_dtype).reshape(shape)
 
+    def pinned_batch(self, batch: TownBatch) -> TownBatch:
+        """A copy of ``batch`` whose arena is page-locked (crosses the bus as one direct copy)."""
+        arena = self.pinned_array((batch.layout.total_bytes,), np.uint8)
+        arena[:] = batch.arena[: batch.layout.total_bytes]
+        out = TownBatch(batch.layout, batch.grid_w, batch.grid_h, arena)
+        out.has_social_in, out.has_personality = batch.has_social_in, batch.has_personality
+        return out
+
+    def wire_row_bytes(self, wire: str) -> int:
+        """Bytes per agent row of the map on the wire (``map_format="wire"`` buffers are ``[ticks, N, row]`` uint8)."""
+        assert self._obs_struct is not None
+        row = int(self.lib.tl_wire_row_bytes(C.byref(self._obs_struct), capi.TL_WIRE[wire]))
+        capi.check(row)
+        return row
+
     def alloc_outputs(
-        self, batch: TownBatch, phases: int, n_ticks: int = 1, *, summary: bool = True, comps: bool = True, pin: bool = False
+        self, batch: TownBatch, phases: int, n_ticks: int = 1, *, summary: bool = True, comps: bool = True, pin: bool = False,
+        map_wire: str | None = None,
     ) -> dict[str, np.ndarray]:
+        """``map_wire``: allocate ``map`` as the wire bytes ``[ticks, N, row]`` uint8 (``map_format="wire"``) instead of float32."""
         make = self.pinned_array if pin else (lambda shape, dtype: np.zeros(shape, dtype=dtype))
         n, t = batch.n_agents, batch.n_towns
         out: dict[str, np.ndarray] = {}
         if phases & capi.TL_PHASE_OBS:
             assert self.obs is not None
-            out["map"] = make((n_ticks, n, *self.obs.map_shape), np.float32)
+            if map_wire is not None and map_wire != "f32":
+                out["map"] = make((n_ticks, n, self.wire_row_bytes(map_wire)), np.uint8)
+            else:
+                out["map"] = make((n_ticks, n, *self.obs.map_shape), np.float32)
             out["features"] = make((n_ticks, n, self.obs.n_features), np.float32)
             if summary:
                 out["summary"] = make((n_ticks, n, capi.TL_N_SUMMARY), np.int32)
@@ -363,6 +389,35 @@ class HostEngine:
             if comps:
                 out["comps"] = make((n_ticks, n, capi.TL_N_COMPS), np.float64)
         return out
+
+    def _out_structs(self, out: dict[str, np.ndarray], map_bytes: bool) -> tuple[capi.TlObsOut, capi.TlRewardOut]:
+        oo = capi.TlObsOut()
+        ro = capi.TlRewardOut()
+        for struct, names in ((oo, ("map", "features", "summary")), (ro, ("reward", "comps", "terminated", "kpi"))):
+            for name in names:
+                arr = out.get(name)
+                if arr is None:
+                    continue
+                setattr(struct, name, C.c_void_p(arr.ctypes.data))
+                per = 1 if (name == "map" and map_bytes) else arr.itemsize  # wire-format maps state their tick stride in bytes
+                setattr(struct, f"{name}_tick_stride", int(arr.strides[0] // per))
+        return oo, ro
+
+    def _dyn_struct(self, batch: TownBatch, phases: int, n_ticks: int, dyn: DynamicsSpec | None, actions: np.ndarray | None):
+        if not phases & (capi.TL_PHASE_ACTIONS | capi.TL_PHASE_SOCIAL_DECAY):
+            return None, None
+        if dyn is None:
+            raise capi.TownletB200Error("the world-dynamics phases need a DynamicsSpec")
+        ds = dyn.struct()
+        if phases & capi.TL_PHASE_ACTIONS:
+            if actions is None or actions.shape[-1] != batch.n_agents or actions.dtype.itemsize != 4:
+                raise capi.TownletB200Error("TL_PHASE_ACTIONS needs 32-bit action words [n_agents] or [n_ticks, n_agents]")
+            actions = np.ascontiguousarray(actions)
+            if actions.ndim == 2 and actions.shape[0] != n_ticks:
+                raise capi.TownletB200Error("actions has the wrong number of ticks")
+            ds.actions = actions.ctypes.data
+            ds.actions_tick_stride = batch.n_agents if actions.ndim == 2 else 0
+        return ds, actions
 
     def tick(
         self,
@@ -377,42 +432,79 @@ class HostEngine:
 
         The world-dynamics phases take a ``DynamicsSpec`` and (``TL_PHASE_ACTIONS``) host action words
         ``[n_agents]`` or ``[n_ticks, n_agents]`` (uint32 / int32)."""
-        oo = capi.TlObsOut()
-        ro = capi.TlRewardOut()
-        for struct, names in ((oo, ("map", "features", "summary")), (ro, ("reward", "comps", "terminated", "kpi"))):
-            for name in names:
-                arr = out.get(name)
-                if arr is None:
-                    continue
-                setattr(struct, name, C.c_void_p(arr.ctypes.data))
-                setattr(struct, f"{name}_tick_stride", int(arr.strides[0] // arr.itemsize))
+        oo, ro = self._out_structs(out, False)
         bs = batch.struct()
-        dyn_p = None
-        if phases & (capi.TL_PHASE_ACTIONS | capi.TL_PHASE_SOCIAL_DECAY):
-            if dyn is None:
-                raise capi.TownletB200Error("the world-dynamics phases need a DynamicsSpec")
-            ds = dyn.struct()
-            if phases & capi.TL_PHASE_ACTIONS:
-                if actions is None or actions.shape[-1] != batch.n_agents or actions.dtype.itemsize != 4:
-                    raise capi.TownletB200Error("TL_PHASE_ACTIONS needs 32-bit action words [n_agents] or [n_ticks, n_agents]")
-                actions = np.ascontiguousarray(actions)
-                if actions.ndim == 2 and actions.shape[0] != n_ticks:
-                    raise capi.TownletB200Error("actions has the wrong number of ticks")
-                ds.actions = actions.ctypes.data
-                ds.actions_tick_stride = batch.n_agents if actions.ndim == 2 else 0
-            dyn_p = C.byref(ds)
+        ds, actions = self._dyn_struct(batch, phases, n_ticks, dyn, actions)
         status = self.lib.tl_host_tick_world(
             self.ctx,
             C.byref(bs),
             C.byref(self._obs_struct) if self._obs_struct is not None else None,
             C.byref(self._rew_struct) if self._rew_struct is not None else None,
-            dyn_p,
+            C.byref(ds) if ds is not None else None,
             C.byref(oo),
             C.byref(ro),
             phases,
             n_ticks,
         )
         capi.check(status)
+
+    def submit(
+        self,
+        slot: int,
+        batch: TownBatch,
+        out: dict[str, np.ndarray],
+        phases: int = capi.TL_PHASE_ALL,
+        n_ticks: int = 1,
+        *,
+        wire: str = "f32",
+        map_format: str = "f32",
+        dirty: "int | tuple[str, ...] | None" = None,
+        writeback: bool = True,
+        dyn: DynamicsSpec | None = None,
+        actions: np.ndarray | None = None,
+    ) -> None:
+        """Enqueue one step on ``slot`` (``tl_host_submit``) and return; ``wait(slot)`` completes it.
+
+        ``dirty``: ``None`` uploads every array; a tuple of field names (or a bit mask, ``capi.FIELD_INDEX``) uploads
+        only those and uses the slot's resident copy of the rest.  ``map_format="wire"`` expects ``out["map"]`` as the
+        wire bytes (``alloc_outputs(map_wire=wire)``).  The arrays must stay alive until ``wait`` returns (the engine
+        keeps references)."""
+        if map_format not in ("f32", "wire"):
+            raise ValueError("map_format is 'f32' or 'wire'")
+        as_wire = map_format == "wire"
+        oo, ro = self._out_structs(out, as_wire)
+        bs = batch.struct()
+        ds, actions = self._dyn_struct(batch, phases, n_ticks, dyn, actions)
+        if dirty is None:
+            mask = capi.TL_DIRTY_ALL
+        elif isinstance(dirty, int):
+            mask = dirty
+        else:
+            mask = 0
+            for name in dirty:
+                mask |= 1 << capi.FIELD_INDEX[name]
+        st = capi.TlHostStep()
+        st.batch = C.pointer(bs)
+        st.obs = C.pointer(self._obs_struct) if self._obs_struct is not None else None
+        st.rew = C.pointer(self._rew_struct) if self._rew_struct is not None else None
+        st.dyn = C.pointer(ds) if ds is not None else None
+        st.obs_out = C.pointer(oo)
+        st.rew_out = C.pointer(ro)
+        st.phases = phases
+        st.n_ticks = n_ticks
+        st.dirty_fields = mask
+        st.wire = capi.TL_WIRE[wire]
+        st.map_format = capi.TL_MAP_WIRE if as_wire else capi.TL_MAP_F32
+        st.writeback = 1 if writeback else 0
+        capi.check(self.lib.tl_host_submit(self.ctx, slot, C.byref(st)))
+        self._inflight[slot] = (st, bs, ds, oo, ro, batch, out, actions)
+
+    def wait(self, slot: int) -> None:
+        """Complete the step pending on ``slot``: afterwards its outputs (and written-back state) are in the host arrays."""
+        try:
+            capi.check(self.lib.tl_host_wait(self.ctx, slot))
+        finally:
+            self._inflight.pop(slot, None)
 
     @property
     def last_h2d_bytes(self) -> int:
@@ -421,3 +513,22 @@ class HostEngine:
     @property
     def last_d2h_bytes(self) -> int:
         return int(self.lib.tl_context_last_d2h_bytes(self.ctx))
+
+
+def expand_wire_map(wire_map: np.ndarray, obs: ObsSpec, wire: str) -> np.ndarray:
+    """numpy restatement of the host expander (tests, and callers that keep the wire bytes): ``[..., N, row]`` uint8
+    wire rows -> the reference's float32 ``[..., N, C, W, W]`` map (``full``: path channels from the look-up table)."""
+    c, w, _ = obs.map_shape
+    w2 = w * w
+    cells = (4 if obs.variant == "full" else c) * w2
+    lead = wire_map.shape[:-1]
+    if wire == "u8":
+        flat = wire_map[..., :cells].astype(np.float32)
+    elif wire == "bits":
+        flat = np.unpackbits(wire_map, axis=-1, bitorder="little")[..., :cells].astype(np.float32)
+    else:
+        raise ValueError("wire is 'u8' or 'bits'")
+    if obs.variant == "full":
+        path = np.broadcast_to(np.asarray(obs.luts()["path_lut"], dtype=np.float32).reshape(2 * w2), (*lead, 2 * w2))
+        flat = np.concatenate([flat, path], axis=-1)
+    return flat.reshape(*lead, c, w, w)
