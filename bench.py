@@ -466,37 +466,52 @@ def measure_e2e(key: str, res: dict, args, ranks: Ranks, rank: int, local_rank: 
     cores = os.cpu_count() or 1
     threads = max(1, min(int(os.environ.get("TL_E2E_THREADS", "12")), cores // ranks.world - 1))
     depth = max(1, min(int(os.environ.get("TL_E2E_DEPTH", "3")), capi.TL_HOST_SLOTS))
+    if os.environ.get("TL_E2E_NT"):
+        capi.set_option("stream_stores", int(os.environ["TL_E2E_NT"]))
     host = HostEngine(obs, rew, local_rank, threads=threads)
     batches = [host.pinned_batch(make_batch(wl, rank + k * ranks.world)[0]) for k in range(depth)]
     n_agents = batches[0].n_agents
     phases = capi.TL_PHASE_ALL
     steps = args.e2e_steps
 
-    def run(wire: str, deliver: str, pipelined: bool) -> dict:
+    # the relationship / rivalry ledgers (65 % of the batch bytes) change only on chat / conflict events: a caller that
+    # keeps them resident uploads the other arrays every step
+    ledgers = {"tie_count", "tie_embed", "tie_trust", "tie_fam", "tie_riv", "riv_count", "riv_embed", "riv_score"}
+    not_ledgers = tuple(name for name in capi.FIELD_INDEX if name not in ledgers)
+
+    def run(wire: str, deliver: str, pipelined: bool, dirty=None) -> dict:
         outs = [host.alloc_outputs(b, phases, 1, summary=False, comps=False, pin=True, map_wire=wire if deliver == "wire" else None)
                 for b in batches]
         fmt = "wire" if deliver == "wire" else "f32"
+        prepared = [host.make_step(b, o, phases, 1, wire=wire, map_format=fmt, dirty=dirty) for b, o in zip(batches, outs)]
+        spent = {"submit": 0.0, "wait": 0.0}
 
         def loop(n: int) -> None:
             if not pipelined:
                 for i in range(n):
-                    host.submit(0, batches[0], outs[0], phases, 1, wire=wire, map_format=fmt)
+                    host.submit(0, step=prepared[0])
                     host.wait(0)
                 return
             for i in range(n + depth):
                 slot = i % depth
+                ta = time.perf_counter()
                 if i >= depth:
                     host.wait(slot)
+                tb = time.perf_counter()
                 if i < n:
-                    host.submit(slot, batches[slot], outs[slot], phases, 1, wire=wire, map_format=fmt)
+                    host.submit(slot, step=prepared[slot])
+                spent["wait"] += tb - ta
+                spent["submit"] += time.perf_counter() - tb
 
         loop(2 * depth)
+        spent["submit"] = spent["wait"] = 0.0
         ranks.barrier()
         t0 = time.perf_counter()
         loop(steps)
         dt = ranks.reduce_max(time.perf_counter() - t0)
         return {"value": ranks.world * n_agents * steps / dt, "ms_per_step": 1e3 * dt / steps,
-                "h2d_bytes_per_step": host.last_h2d_bytes, "d2h_bytes_per_step": host.last_d2h_bytes}
+                "h2d_bytes_per_step": host.last_h2d_bytes, "d2h_bytes_per_step": host.last_d2h_bytes,
+                "host_ms_per_step": {k: 1e3 * v / steps for k, v in spent.items()} if pipelined else None}
 
     binary = wl["variant"] != "compact"  # compact cells are counts only when normalize_counts is off (default: on -> 0 / 1)
     formats = {
@@ -507,6 +522,10 @@ def measure_e2e(key: str, res: dict, args, ranks: Ranks, rank: int, local_rank: 
     }
     formats["bits wire -> float32 on the host"] = run("bits", "f32", True)
     formats["bits wire, delivered as bits"] = run("bits", "wire", True)
+    resident = {
+        "bits wire -> float32 on the host, ledgers resident": run("bits", "f32", True, not_ledgers),
+        "bits wire, delivered as bits, ledgers resident": run("bits", "wire", True, not_ledgers),
+    }
     del binary
     host.close()
     f32_names = [k for k in formats if "delivered as" not in k]
@@ -520,6 +539,7 @@ def measure_e2e(key: str, res: dict, args, ranks: Ranks, rank: int, local_rank: 
         "api": f"tl_host_submit / tl_host_wait, pinned host buffers, {depth} batches in flight, {threads} host threads; "
         f"headline = the fastest format that delivers the reference's float32 tensors: {best}",
         "formats": formats,
+        "resident_ledgers": resident,
     }
 
 

@@ -108,7 +108,7 @@ def test_resident_batch_uploads_only_the_dirty_arrays() -> None:
 
     eng.submit(2, batch, out, dirty=(), writeback=False)  # nothing changed on the host: the device state advances
     eng.wait(2)
-    assert eng.last_h2d_bytes < full_upload // 50  # look-up tables only
+    assert eng.last_h2d_bytes < full_upload // 4  # look-up tables only (~21 KB)
     ref = oracle_tick(ref_batch, obs, rew, capi.TL_PHASE_ALL, 1)
     assert_obs_equal(out, ref, "step 1 (resident)")
     assert_reward_close(out, ref, "step 1 (resident)")

@@ -9,6 +9,7 @@
 //         else into the slot's pinned staging block, from where tl_host_wait scatters it with the context's threads.
 // Steps of different slots run on different streams, so the upload of one overlaps the download of another.
 
+#include <algorithm>
 #include <condition_variable>
 #include <functional>
 #include <thread>
@@ -68,17 +69,17 @@ __global__ void __launch_bounds__(256) pack_map_bits_kernel(const float* __restr
 }
 
 // ---- host: wire rows -> float32 rows ------------------------------------------------------------------------
-void expand_u8_cells(const uint8_t* src, float* dst, int n) {
+void expand_u8_cells(const uint8_t* src, float* dst, int n, bool stream) {
     int i = 0;
 #if TL_HAVE_SSE2
-    const bool aligned = (((uintptr_t)dst) & 15) == 0;
+    const bool aligned = stream && (((uintptr_t)dst) & 15) == 0;
     const __m128i zero = _mm_setzero_si128();
     for (; i + 16 <= n; i += 16) {
         const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
         const __m128i lo = _mm_unpacklo_epi8(b, zero), hi = _mm_unpackhi_epi8(b, zero);
         const __m128 f0 = _mm_cvtepi32_ps(_mm_unpacklo_epi16(lo, zero)), f1 = _mm_cvtepi32_ps(_mm_unpackhi_epi16(lo, zero));
         const __m128 f2 = _mm_cvtepi32_ps(_mm_unpacklo_epi16(hi, zero)), f3 = _mm_cvtepi32_ps(_mm_unpackhi_epi16(hi, zero));
-        if (aligned) {  // streaming stores: the rows are written once and read by someone else later
+        if (aligned) {  // streaming stores (optional): the rows are written once and read by someone else later
             _mm_stream_ps(dst + i, f0), _mm_stream_ps(dst + i + 4, f1), _mm_stream_ps(dst + i + 8, f2), _mm_stream_ps(dst + i + 12, f3);
         } else {
             _mm_storeu_ps(dst + i, f0), _mm_storeu_ps(dst + i + 4, f1), _mm_storeu_ps(dst + i + 8, f2), _mm_storeu_ps(dst + i + 12, f3);
@@ -100,11 +101,11 @@ const BitTable& bit_table() {
     return t;
 }
 
-void expand_bit_cells(const uint8_t* src, float* dst, int n) {  // cell i = bit i % 8 of byte i / 8 (little-endian words)
+void expand_bit_cells(const uint8_t* src, float* dst, int n, bool stream) {  // cell i = bit i % 8 of byte i / 8 (little-endian words)
     const BitTable& t = bit_table();
     int i = 0;
 #if TL_HAVE_SSE2
-    const bool aligned = (((uintptr_t)dst) & 15) == 0;
+    const bool aligned = stream && (((uintptr_t)dst) & 15) == 0;
     for (; i + 8 <= n; i += 8) {
         const float* e = t.f[src[i >> 3]];
         const __m128 a = _mm_load_ps(e), b = _mm_load_ps(e + 4);
@@ -118,6 +119,9 @@ void expand_bit_cells(const uint8_t* src, float* dst, int n) {  // cell i = bit 
 }
 
 // ---- a small pool: the caller and n - 1 workers share the tasks of one parallel region ------------------------
+// Workers spin on the region counter for about a millisecond after a region before they go to sleep on the condition
+// variable: in a pipelined loop the next region is ~0.1-0.3 ms away and a futex wake-up per worker would cost as much
+// as the region itself; an idle context sleeps.
 class Pool {
 public:
     explicit Pool(int n_threads) : n_(n_threads < 1 ? 1 : n_threads) {
@@ -126,8 +130,8 @@ public:
     ~Pool() {
         {
             std::lock_guard<std::mutex> lock(mu_);
-            stop_ = true;
-            ++epoch_;
+            stop_.store(true);
+            epoch_.fetch_add(1);
         }
         cv_.notify_all();
         for (auto& w : workers_) w.join();
@@ -139,24 +143,32 @@ public:
             for (int i = 0; i < n_tasks; ++i) fn(i);
             return;
         }
-        {
+        fn_ = &fn;
+        n_tasks_ = n_tasks;
+        next_.store(0);
+        left_.store(n_tasks);
+        open_.store(true);
+        epoch_.fetch_add(1, std::memory_order_release);  // publishes fn_ / n_tasks_ / the counters
+        if (sleepers_.load() > 0) {
             std::lock_guard<std::mutex> lock(mu_);
-            fn_ = &fn;
-            n_tasks_ = n_tasks;
-            next_.store(0);
-            left_.store(n_tasks);
-            ++epoch_;
+            cv_.notify_all();
         }
-        cv_.notify_all();
         drain();
-        // the region ends when every task is done AND no worker is still inside drain(): a straggler must not
-        // meet the counters of the next region
-        while (left_.load(std::memory_order_acquire) > 0 || active_.load(std::memory_order_acquire) > 0) std::this_thread::yield();
-        std::lock_guard<std::mutex> lock(mu_);
-        fn_ = nullptr;
+        // the region ends when every task is done AND every worker that joined it has left drain(): a straggler
+        // must not meet the counters of the next region
+        while (left_.load(std::memory_order_acquire) > 0 || active_.load(std::memory_order_acquire) > 0) spin_pause();
+        open_.store(false, std::memory_order_release);
+        while (active_.load(std::memory_order_acquire) > 0) spin_pause();
     }
 
 private:
+    static void spin_pause() {
+#if TL_HAVE_SSE2
+        _mm_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
     void drain() {
         for (;;) {
             const int i = next_.fetch_add(1);
@@ -168,15 +180,23 @@ private:
     void work() {
         uint64_t seen = 0;
         for (;;) {
-            {
+            // wait for a new region: spin first, then sleep
+            int spins = 0;
+            while (epoch_.load(std::memory_order_acquire) == seen) {
+                if (++spins < 200000) {
+                    spin_pause();
+                    continue;
+                }
                 std::unique_lock<std::mutex> lock(mu_);
-                cv_.wait(lock, [&] { return epoch_ != seen; });
-                seen = epoch_;
-                if (stop_) return;
-                if (!fn_) continue;  // woke up after the region ended
-                active_.fetch_add(1);
+                sleepers_.fetch_add(1);
+                cv_.wait(lock, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+                sleepers_.fetch_sub(1);
             }
-            drain();
+            seen = epoch_.load(std::memory_order_acquire);
+            if (stop_.load()) return;
+            // join the region only while it is open: register, then re-check (run() closes before it reuses the counters)
+            active_.fetch_add(1, std::memory_order_acq_rel);
+            if (open_.load(std::memory_order_acquire) && epoch_.load(std::memory_order_acquire) == seen) drain();
             active_.fetch_sub(1, std::memory_order_release);
         }
     }
@@ -186,9 +206,9 @@ private:
     std::condition_variable cv_;
     const std::function<void(int)>* fn_ = nullptr;
     int n_tasks_ = 0;
-    std::atomic<int> next_{0}, left_{0}, active_{0};
-    uint64_t epoch_ = 0;
-    bool stop_ = false;
+    std::atomic<int> next_{0}, left_{0}, active_{0}, sleepers_{0};
+    std::atomic<uint64_t> epoch_{0};
+    std::atomic<bool> stop_{false}, open_{false};
 };
 
 bool ensure_device(unsigned char** buf, size_t* cap, size_t need) {
@@ -499,6 +519,23 @@ int tl_host_submit(TlContext* ctx, int32_t slot_index, const TlHostStep* st) {
     if (arena && all_dirty) {
         if (!cuda_ok(cudaMemcpyAsync(s.d_arena, (const void*)lo, hi - lo, cudaMemcpyHostToDevice, s.stream), "H2D arena")) return TL_ERR_CUDA;
         ctx->last_h2d += (int64_t)(hi - lo);
+    } else if (arena) {
+        // dirty arrays that sit next to each other in the declared arena (only alignment padding between them) go up
+        // as one copy per run
+        int order[TL_N_FIELDS], n_dirty = 0;
+        for (int i = 0; i < TL_N_FIELDS; ++i)
+            if (f[i].bytes && ((dirty >> i) & 1)) order[n_dirty++] = i;
+        std::sort(order, order + n_dirty, [&](int a, int b) { return off[a] < off[b]; });
+        for (int k = 0; k < n_dirty;) {
+            const size_t begin = off[order[k]];
+            size_t end = begin + f[order[k]].bytes;
+            int j = k + 1;
+            while (j < n_dirty && off[order[j]] <= end + 256) end = off[order[j]] + f[order[j]].bytes, ++j;
+            if (!cuda_ok(cudaMemcpyAsync(s.d_arena + begin, (const void*)(lo + begin), end - begin, cudaMemcpyHostToDevice, s.stream), "H2D arrays"))
+                return TL_ERR_CUDA;
+            ctx->last_h2d += (int64_t)(end - begin);
+            k = j;
+        }
     } else {
         for (int i = 0; i < TL_N_FIELDS; ++i) {
             if (!f[i].bytes || !((dirty >> i) & 1)) continue;
@@ -730,14 +767,15 @@ int tl_host_wait(TlContext* ctx, int32_t slot_index) {
         const HostSlot* sp = &s;
         const long long rows = s.map_agents * s.map_ticks;
         const int jobs = (int)(rows < parts ? rows : parts);
-        ctx->pool->run(jobs, [sp, rows, jobs](int job) {
+        const bool stream = g_opt.stream_stores.load() != 0;
+        ctx->pool->run(jobs, [sp, rows, jobs, stream](int job) {
             const long long r0 = rows * job / jobs, r1 = rows * (job + 1) / jobs;
             for (long long r = r0; r < r1; ++r) {
                 const long long t = r / sp->map_agents, a = r - t * sp->map_agents;
                 const unsigned char* src = sp->h_stage + sp->map_stage_off + (size_t)r * sp->map_wire_row;
                 float* dst = reinterpret_cast<float*>(sp->map_host + (size_t)t * sp->map_host_stride) + (size_t)a * sp->map_cells;
-                if (sp->map_job == kMapU8) expand_u8_cells(src, dst, sp->map_wire_cells);
-                else expand_bit_cells(src, dst, sp->map_wire_cells);
+                if (sp->map_job == kMapU8) expand_u8_cells(src, dst, sp->map_wire_cells, stream);
+                else expand_bit_cells(src, dst, sp->map_wire_cells, stream);
                 if (sp->path_cells) memcpy(dst + sp->map_wire_cells, sp->path_lut, (size_t)sp->path_cells * 4);  // map.py:115-125
             }
 #if TL_HAVE_SSE2

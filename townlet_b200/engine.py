@@ -448,9 +448,8 @@ class HostEngine:
         )
         capi.check(status)
 
-    def submit(
+    def make_step(
         self,
-        slot: int,
         batch: TownBatch,
         out: dict[str, np.ndarray],
         phases: int = capi.TL_PHASE_ALL,
@@ -462,13 +461,9 @@ class HostEngine:
         writeback: bool = True,
         dyn: DynamicsSpec | None = None,
         actions: np.ndarray | None = None,
-    ) -> None:
-        """Enqueue one step on ``slot`` (``tl_host_submit``) and return; ``wait(slot)`` completes it.
-
-        ``dirty``: ``None`` uploads every array; a tuple of field names (or a bit mask, ``capi.FIELD_INDEX``) uploads
-        only those and uses the slot's resident copy of the rest.  ``map_format="wire"`` expects ``out["map"]`` as the
-        wire bytes (``alloc_outputs(map_wire=wire)``).  The arrays must stay alive until ``wait`` returns (the engine
-        keeps references)."""
+    ) -> tuple:
+        """Build the ``TlHostStep`` of one step once; ``submit(slot, step=...)`` then costs one C call.  The step keeps
+        references to the arrays it points at."""
         if map_format not in ("f32", "wire"):
             raise ValueError("map_format is 'f32' or 'wire'")
         as_wire = map_format == "wire"
@@ -496,8 +491,21 @@ class HostEngine:
         st.wire = capi.TL_WIRE[wire]
         st.map_format = capi.TL_MAP_WIRE if as_wire else capi.TL_MAP_F32
         st.writeback = 1 if writeback else 0
-        capi.check(self.lib.tl_host_submit(self.ctx, slot, C.byref(st)))
-        self._inflight[slot] = (st, bs, ds, oo, ro, batch, out, actions)
+        return (st, bs, ds, oo, ro, batch, out, actions)
+
+    def submit(self, slot: int, batch: TownBatch | None = None, out: dict[str, np.ndarray] | None = None, *args, step: tuple | None = None,
+               **kwargs) -> None:
+        """Enqueue one step on ``slot`` (``tl_host_submit``) and return; ``wait(slot)`` completes it.
+
+        Either the arguments of ``make_step`` (``batch, out, phases, n_ticks, wire=..., map_format=..., dirty=...,
+        writeback=..., dyn=..., actions=...``) or a prebuilt ``step``.  ``dirty``: ``None`` uploads every array; a tuple
+        of field names (or a bit mask, ``capi.FIELD_INDEX``) uploads only those and uses the slot's resident copy of the
+        rest.  ``map_format="wire"`` expects ``out["map"]`` as the wire bytes (``alloc_outputs(map_wire=wire)``).  The
+        arrays must stay alive until ``wait`` returns (the engine keeps references)."""
+        if step is None:
+            step = self.make_step(batch, out, *args, **kwargs)
+        capi.check(self.lib.tl_host_submit(self.ctx, slot, C.byref(step[0])))
+        self._inflight[slot] = step
 
     def wait(self, slot: int) -> None:
         """Complete the step pending on ``slot``: afterwards its outputs (and written-back state) are in the host arrays."""
