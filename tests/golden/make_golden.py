@@ -33,6 +33,8 @@ sys.path.insert(0, str(REPO))
 sys.path.insert(0, str(REPO / "tests" / "golden"))
 
 REF_SRC = Path(os.environ.get("TOWNLET_REFERENCE", "/root/reference"))
+if not (REF_SRC / "src" / "townlet").is_dir():  # the GPU box: the copy made by oracle/make_ref.sh
+    REF_SRC = REPO / "oracle" / "_ref"
 WORK = Path(tempfile.mkdtemp(prefix="townlet_ref_"))
 shutil.copytree(REF_SRC, WORK / "ref", symlinks=True)
 os.system(f"chmod -R u+w {WORK / 'ref'}")
@@ -367,6 +369,41 @@ def patch_employment(world, town: TownDescription):
         ctx["on_time_ticks"] = int(round(float(town.punctuality[i]) * 1000))
 
 
+def reference_kpi_row(world, rewards: dict, terminated: dict, config) -> tuple[np.ndarray, float, float]:
+    """The per-town KPI row computed by the REFERENCE's own code on one world after a tick:
+    mean lateness by ``TelemetryPublisher._update_kpi_history`` (telemetry/publisher.py:2671-2694), reward mean and
+    population variance by ``RewardVarianceAnalyzer.analyze`` (stability/analyzers/reward_variance.py:104-108), the
+    starving count by ``StarvationDetector.analyze``'s predicate (stability/analyzers/starvation.py:132-139), hunger
+    levels as ``SimulationLoop.step`` collects them (core/sim_loop.py:740-743), the reward sum as
+    ``compute_sample_metrics`` takes it (policy/metrics.py:13-25)."""
+    from types import SimpleNamespace
+
+    from townlet.stability.analyzers.reward_variance import RewardVarianceAnalyzer
+    from townlet.stability.analyzers.starvation import StarvationDetector
+    from townlet.telemetry.publisher import TelemetryPublisher
+
+    stub = SimpleNamespace(_latest_conflict_snapshot={}, _latest_relationship_metrics={}, _kpi_history={})
+    TelemetryPublisher._update_kpi_history(stub, world)
+    lateness_mean = stub._kpi_history["employment_lateness"][-1]
+    variance = RewardVarianceAnalyzer(window_ticks=1).analyze(tick=world.tick, rewards=dict(rewards))
+    threshold = float(config.stability.starvation.hunger_threshold)
+    hunger_levels = {aid: float(snap.needs.get("hunger", 1.0)) for aid, snap in world.agents.items()}
+    starving = StarvationDetector(hunger_threshold=threshold, min_duration_ticks=1, window_ticks=10).analyze(
+        tick=world.tick, hunger_levels=hunger_levels, terminated={}
+    )["starvation_incidents"]
+    totals = np.asarray([rewards[aid] for aid in world.agents], dtype=np.float32)
+    row = np.zeros(capi.TL_N_KPI, dtype=np.float64)
+    row[capi.KPI_NAMES.index("reward_sum")] = float(np.sum(totals))  # policy/metrics.py:18
+    row[capi.KPI_NAMES.index("reward_sumsq")] = float(np.sum(totals.astype(np.float64) ** 2))
+    row[capi.KPI_NAMES.index("hunger_min")] = min(hunger_levels.values())
+    row[capi.KPI_NAMES.index("hunger_mean")] = sum(hunger_levels.values()) / len(hunger_levels)
+    row[capi.KPI_NAMES.index("starving")] = starving
+    row[capi.KPI_NAMES.index("terminated")] = sum(1 for flag in terminated.values() if flag)
+    row[capi.KPI_NAMES.index("lateness_mean")] = lateness_mean
+    row[capi.KPI_NAMES.index("wallet_mean")] = sum(float(snap.wallet) for snap in world.agents.values()) / len(world.agents)
+    return row, float(variance["reward_mean"]), float(variance["reward_variance"])
+
+
 def synth_cases():
     cases = (
         ("synth_hybrid_48x8", "hybrid", 48, 8, 4, {}),
@@ -444,6 +481,10 @@ def synth_cases():
             "terminated": np.zeros((n_ticks, N), np.uint8),
             "needs": np.zeros((n_ticks, 3, N)),
             "episode_total": np.zeros((n_ticks, N)),
+            # row K: the reference's own telemetry / stability code on every town after every tick
+            "kpi": np.zeros((n_ticks, len(towns), capi.TL_N_KPI)),
+            "kpi_reward_mean": np.zeros((n_ticks, len(towns))),
+            "kpi_reward_variance": np.zeros((n_ticks, len(towns))),
         }
         for it in range(n_ticks):
             a = 0
@@ -466,6 +507,8 @@ def synth_cases():
                 for snap in w.agents.values():  # world/core/context.py:283-289
                     snap.episode_tick = (int(snap.episode_tick) + 1) % max(1, int(tpd))
                 breakdowns = eng.compute(w, terminated, reasons)
+                row, r_mean, r_var = reference_kpi_row(w, {aid: bd.total for aid, bd in breakdowns.items()}, terminated, config)
+                ref["kpi"][it, ti], ref["kpi_reward_mean"][it, ti], ref["kpi_reward_variance"][it, ti] = row, r_mean, r_var
                 ids, maps, feats, summ, _ = reference_obs(w, svc, terminated)
                 assert ids == t.agent_ids
                 ref["map"][it, a : a + n] = maps
@@ -774,6 +817,8 @@ def world_dynamics_cases():
                 for snap in w.agents.values():
                     snap.episode_tick = (int(snap.episode_tick) + 1) % max(1, int(tpd))
                 breakdowns = eng.compute(w, terminated, reasons)
+                row, r_mean, r_var = reference_kpi_row(w, {aid: bd.total for aid, bd in breakdowns.items()}, terminated, config)
+                ref["kpi"][it, ti], ref["kpi_reward_mean"][it, ti], ref["kpi_reward_variance"][it, ti] = row, r_mean, r_var
                 ids, maps, feats, summ, _ = reference_obs(w, svc, terminated)
                 assert ids == t.agent_ids
                 ref["map"][it, a : a + n] = maps
@@ -1093,8 +1138,9 @@ def fuzz_dropin(n_worlds: int = int(os.environ.get("TL_FUZZ_WORLDS", 150)), seed
     import townlet_b200.reward_engine as rew_mod
     from oracle_engine import OracleHostEngine
 
-    obs_mod.HostEngine = OracleHostEngine
-    rew_mod.HostEngine = OracleHostEngine
+    if os.environ.get("TL_DROPIN_ENGINE", "oracle") != "cuda":  # "cuda": the real HostEngine (GPU box, composed test)
+        obs_mod.HostEngine = OracleHostEngine
+        rew_mod.HostEngine = OracleHostEngine
     rng = np.random.default_rng(seed)
     compared = 0
     for w_index in range(n_worlds):
@@ -1223,7 +1269,7 @@ def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
     only = os.environ.get("TL_GOLDEN_ONLY")
     if only:
-        {"gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world, "fuzz-dropin": fuzz_dropin, "fuzz-gae": fuzz_gae}[only]()
+        {"synth": synth_cases, "gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world, "fuzz-dropin": fuzz_dropin, "fuzz-gae": fuzz_gae}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()

@@ -42,3 +42,21 @@ def assert_reward_close(got: dict, ref: dict, what: str) -> None:
         )
     if "terminated" in ref and "terminated" in got:
         assert np.array_equal(np.asarray(got["terminated"]), np.asarray(ref["terminated"])), f"{what}: terminated flags"
+
+
+def assert_kpi_close(got: dict, ref: dict, batch, what: str) -> None:
+    """Per-town KPI rows against the rows the reference's own telemetry / stability code produced (SURVEY.md §8a row K;
+    tests/golden/make_golden.py: reference_kpi_row).  The rows are float32 of float64 accumulations: 1e-5 relative.  The
+    reward mean and POPULATION variance the reference's RewardVarianceAnalyzer reports follow from the sum, the sum of
+    squares and the town's agent count."""
+    if "kpi" not in ref or "kpi" not in got:
+        return
+    g, r = np.asarray(got["kpi"], dtype=np.float64), np.asarray(ref["kpi"], dtype=np.float64)
+    assert g.shape == r.shape, (what, g.shape, r.shape)
+    for k, name in enumerate(capi.KPI_NAMES):
+        np.testing.assert_allclose(g[..., k], r[..., k], rtol=1e-5, atol=1e-7, err_msg=f"{what}: KPI {name}")
+    count = np.diff(np.asarray(batch.town_agent_off)).astype(np.float64)
+    mean = g[..., capi.KPI_NAMES.index("reward_sum")] / count
+    variance = g[..., capi.KPI_NAMES.index("reward_sumsq")] / count - mean**2
+    np.testing.assert_allclose(mean, ref["kpi_reward_mean"], rtol=1e-5, atol=1e-7, err_msg=f"{what}: reward mean")
+    np.testing.assert_allclose(variance, ref["kpi_reward_variance"], rtol=1e-4, atol=1e-7, err_msg=f"{what}: reward variance")

@@ -61,6 +61,7 @@ def test_device_path_matches_reference_golden(path, mode, kernel_form) -> None:
     got = _device_run(batch, obs, rew, meta["phases"], meta["n_ticks"])
     assert_obs_equal(got, ref, path.stem)
     assert_reward_close(got, ref, path.stem)
+    assert_kpi_close(got, ref, batch, path.stem)
     _check_state(batch, ref)
 
 
@@ -70,6 +71,7 @@ def test_host_path_matches_reference_golden(path) -> None:
     got = _host_run(batch, obs, rew, meta["phases"], meta["n_ticks"])
     assert_obs_equal(got, ref, path.stem)
     assert_reward_close(got, ref, path.stem)
+    assert_kpi_close(got, ref, batch, path.stem)
     _check_state(batch, ref)
 
 

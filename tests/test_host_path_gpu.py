@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 import pytest
 from fixture_io import fixture_paths, load_fixture
-from helpers import assert_obs_equal, assert_reward_close
+from helpers import assert_kpi_close, assert_obs_equal, assert_reward_close
 
 from townlet_b200 import capi
 from townlet_b200.params import ObsSpec, RewardSpec
@@ -45,6 +45,7 @@ def test_narrow_wire_formats_deliver_the_reference_tensors(path, wire) -> None:
     eng.wait(0)
     assert_obs_equal(out, ref, f"{path.stem}/{wire}")
     assert_reward_close(out, ref, f"{path.stem}/{wire}")
+    assert_kpi_close(out, ref, batch, f"{path.stem}/{wire}")
     # the same step delivering the wire bytes themselves; the numpy expander restates the host threads' work
     raw = eng.alloc_outputs(load_fixture(path)[0], meta["phases"], meta["n_ticks"], map_wire=wire)
     fresh = load_fixture(path)[0]

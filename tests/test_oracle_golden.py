@@ -11,12 +11,20 @@ from __future__ import annotations
 import numpy as np
 import pytest
 from fixture_io import fixture_paths, load_fixture
-from helpers import assert_obs_equal, assert_reward_close
+from helpers import assert_kpi_close, assert_obs_equal, assert_reward_close
 
 from oracle.oracle import oracle_tick
 from townlet_b200 import capi
 
 FIXTURES = fixture_paths()
+
+
+def test_kpi_rows_are_pinned_to_the_reference() -> None:
+    """Row K: the synthetic-town fixtures carry KPI rows produced by the reference's telemetry / stability classes."""
+    pinned = [p for p in FIXTURES if "kpi" in load_fixture(p)[4]]
+    assert len(pinned) >= 5
+    _, _, _, _, ref = load_fixture(pinned[0])
+    assert ref["kpi"].shape[-1] == capi.TL_N_KPI and ref["kpi"][..., capi.KPI_NAMES.index("starving")].max() >= 1
 
 
 def test_fixtures_present() -> None:
@@ -32,6 +40,7 @@ def test_oracle_matches_reference(path) -> None:
     out = oracle_tick(batch, obs, rew, meta["phases"], meta["n_ticks"])
     assert_obs_equal(out, ref, path.stem)
     assert_reward_close(out, ref, path.stem)
+    assert_kpi_close(out, ref, batch, path.stem)
     if "needs" in ref:  # state after the last tick
         np.testing.assert_allclose(batch.needs, ref["needs"][-1], rtol=1e-6, atol=1e-15)
     if "episode_total" in ref:

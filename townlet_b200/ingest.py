@@ -26,6 +26,10 @@ from .soa import BatchLayout, TownBatch, pack_entity, pack_pos
 
 
 def _as_float(value: object, default: float = 0.0) -> float:
+    """A float64 SoA cell from whatever the snapshot holds (same coercion rules as the reference's context builder,
+    world/observations/context.py:12-31: numbers and numeric strings convert, anything else yields the default)."""
+    if isinstance(value, (int, float)):  # bool included
+        return float(value)
     try:
         return float(value)  # type: ignore[arg-type]
     except (TypeError, ValueError):
@@ -33,19 +37,15 @@ def _as_float(value: object, default: float = 0.0) -> float:
 
 
 def _as_int(value: object, default: int = 0) -> int:
-    # world/observations/context.py:19-31
-    if isinstance(value, bool):
+    """An int32 SoA cell: ints as they are, bools as 0 / 1, floats truncated, integer strings parsed; otherwise the default."""
+    if isinstance(value, (bool, int, float)):
         return int(value)
-    if isinstance(value, int):
-        return value
-    if isinstance(value, float):
+    if not isinstance(value, str):
+        return default
+    try:
         return int(value)
-    if isinstance(value, str):
-        try:
-            return int(value)
-        except ValueError:
-            return default
-    return default
+    except ValueError:
+        return default
 
 
 def resolve_adapter(world: Any) -> Any:

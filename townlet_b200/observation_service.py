@@ -94,8 +94,14 @@ class B200ObservationService:
         pending_resets = set(adapter.consume_ctx_reset_requests())  # destructive, once (service.py:210)
         tick = adapter.tick
         slots: dict[str, int] = {}
-        for agent_id in snapshots:  # allocation order = agent order (service.py:219)
-            slots[agent_id] = adapter.embedding_allocator.allocate(agent_id, tick)
+        allocator = adapter.embedding_allocator
+        for agent_id in snapshots:
+            # one loop in agent order, as the reference interleaves them (service.py:216-229): allocate, and release
+            # at once when the agent is terminated — so a later agent without a slot can take the one just freed
+            # (forced reuse when the pool is full).  The slot value is already captured for the kernel.
+            slots[agent_id] = allocator.allocate(agent_id, tick)
+            if terminated.get(agent_id, False):
+                allocator.release(agent_id, tick)
         observations: dict[str, dict[str, Any]] = {}
         if snapshots:
             rows = ingest_town(
@@ -117,9 +123,6 @@ class B200ObservationService:
                     "features": np.array(out["features"][0, i], dtype=np.float32),
                     "metadata": self._build_metadata(slots[agent_id], out["summary"][0, i], snapshot),
                 }
-        for agent_id in snapshots:
-            if terminated.get(agent_id, False):  # service.py:227-229
-                adapter.embedding_allocator.release(agent_id, tick)
         return observations
 
     def build_single(self, world: Any, agent_id: str, *, slot: int | None = None) -> Mapping[str, Any]:
