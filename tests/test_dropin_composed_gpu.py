@@ -41,6 +41,8 @@ def ref(tmp_path_factory):
     yield work
     os.chdir(cwd)
     sys.path.remove(str(work / "ref" / "src"))
+    for name in [m for m in sys.modules if m == "townlet" or m.startswith("townlet.")]:
+        del sys.modules[name]  # later test modules run without the reference, as on a box that has none
 
 
 # the comparisons themselves are the CPU suite's, collected here against the fixture above

@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 import pytest
 from fixture_io import fixture_paths, load_fixture
-from helpers import REL_TOL, assert_obs_equal, assert_reward_close
+from helpers import REL_TOL, assert_kpi_close, assert_obs_equal, assert_reward_close
 
 from townlet_b200 import capi
 from townlet_b200.params import ObsSpec, RewardSpec

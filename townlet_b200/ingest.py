@@ -57,8 +57,11 @@ def resolve_adapter(world: Any) -> Any:
     try:
         from townlet.world.core.runtime_adapter import ensure_world_adapter  # type: ignore
 
-        return ensure_world_adapter(world)
     except ImportError:
+        return world
+    try:
+        return ensure_world_adapter(world)
+    except TypeError:  # neither a WorldState nor a context: a duck-typed stand-in with the accessors the ingest reads
         return world
 
 
