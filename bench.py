@@ -598,6 +598,7 @@ def main() -> None:
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the other configurations (`workloads`)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (kernel A/B runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
 
@@ -638,8 +639,8 @@ def main() -> None:
     res = measure(args.workload)
 
     # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H per step) ----
-    if wl.get("world") and wl.get("policy"):
-        e2e = None  # the rollout never leaves the device; see c5 for the host-buffer figure of the same batch
+    if args.no_e2e or (wl.get("world") and wl.get("policy")):
+        e2e = None  # (world + policy: the rollout never leaves the device; see c5 for the host-buffer figure of the same batch)
     elif wl.get("world"):
         e2e = measure_e2e_world(res, args, ranks)
     else:

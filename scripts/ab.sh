@@ -7,7 +7,7 @@ for W in "$@"; do
   for R in 1 2 3; do
     for L in A B; do
       LIB=$A; [ $L = B ] && LIB=$B
-      V=$(TOWNLET_B200_LIB=$LIB python bench.py --workload $W --no-cpu --e2e-steps 1 2>/dev/null | tail -1 | python -c "import sys,json; print(json.loads(sys.stdin.read())['value'])")
+      V=$(TOWNLET_B200_LIB=$LIB python bench.py --workload $W --no-cpu --no-e2e --no-extra 2>/dev/null | tail -1 | python -c "import sys,json; print(json.loads(sys.stdin.read())['value'])")
       eval "SUM_$L=\$(python -c \"print(\$SUM_$L + $V)\")"
     done
   done

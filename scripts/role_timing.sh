@@ -9,6 +9,6 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -lineinfo -std=c++1
   -Iinclude -o $LIB townlet_b200/csrc/townlet_b200.cu || exit 1
 for W in "$@"; do
   echo "== $W"
-  TOWNLET_B200_LIB=$LIB python bench.py --workload $W --no-cpu --e2e-steps 1 --steps 64 --warmup 32 2>&1 | grep TL_ROLE_TIMING | tail -8 | sort
+  TOWNLET_B200_LIB=$LIB python bench.py --workload $W --no-cpu --no-e2e --steps 64 --warmup 32 --no-extra --min-launches 4 --min-seconds 0.001 2>&1 | grep TL_ROLE_TIMING | tail -9
 done | tee gpurun_out/role_timing.txt
 rm -f $LIB

@@ -2,6 +2,24 @@
 // (tick_roles.cuh) and the dense grid kernel (townlet_b200.cu).  Included inside the anonymous namespace
 // of townlet_b200.cu; uses KParams, RewardIn / reward_agent, pos_x / pos_y.
 
+// -DTL_ROLE_TIMING: two CTAs print the cycles each role spends per tick in its role body and at the pass
+// barrier + sweep, and CTA 0 the parts of its state role (scripts/role_timing.sh; never part of the shipped library)
+#ifdef TL_ROLE_TIMING
+#define TL_TIMING(...) __VA_ARGS__
+__device__ long long g_state_parts[8];
+#define TL_MARK_BEGIN() long long tl_mark_t = clock64()
+#define TL_MARK(k)                                                         \
+    do {                                                                   \
+        const long long tl_now = clock64();                                \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_state_parts[k] += tl_now - tl_mark_t; \
+        tl_mark_t = tl_now;                                                \
+    } while (0)
+#else
+#define TL_TIMING(...)
+#define TL_MARK_BEGIN()
+#define TL_MARK(k)
+#endif
+
 struct StateRoleOut {
     double need0 = 0.0;         // hunger after decay (KPI)
     double reward_total = 0.0;  // reward of the tick (KPI)
@@ -150,6 +168,59 @@ __device__ __forceinline__ StateIn staged_state_in(const KParams& p, const unsig
     return in;
 }
 
+// slot / max_slots for a slot outside the host table (never with the reference's allocator): kept out of line so the
+// float64 division does not sit in the hot instruction stream
+__device__ __noinline__ float slot_norm_out_of_table(int slot_idx, int max_slots) {
+    return (float)((double)slot_idx / (double)max_slots);
+}
+
+// Nearest object of every landmark type (world/observe.py:109-147) and the landmark features
+// (_encode_landmarks, features.py:333-356) for configurations with include_targets; out of line, the default
+// configuration never runs it.  Returns the path-hint type's squared distance (or -1) and offsets.
+struct NearestHint {
+    int d2, dx, dy;
+};
+template <bool MUT>
+__device__ __noinline__ NearestHint landmarks_all_types(const uint32_t* ent, int e_obj, int e_end, int cx, int cy, int hint_ltype,
+                                                        float* dst0) {
+    int best_d2[5] = {-1, -1, -1, -1, -1};
+    int best_dx[5] = {0, 0, 0, 0, 0}, best_dy[5] = {0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int e = e_obj; e < e_end; ++e) {
+        const uint32_t w = ld_state<MUT>(ent + e);
+        if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w)) continue;
+        const int lt = (int)TL_ENT_LTYPE(w);
+        if (lt == 0) continue;
+        const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
+        const int d2 = dx * dx + dy * dy;
+#pragma unroll
+        for (int l = 1; l <= 4; ++l) {
+            if (l == lt && (best_d2[l] < 0 || d2 < best_d2[l])) {
+                best_d2[l] = d2;
+                best_dx[l] = dx;
+                best_dy[l] = dy;
+            }
+        }
+    }
+    NearestHint hint{-1, 0, 0};
+#pragma unroll
+    for (int l = 1; l <= 4; ++l) {
+        if (l == hint_ltype) hint = NearestHint{best_d2[l], best_dx[l], best_dy[l]};
+        float* dst = dst0 + 3 * (l - 1);
+        if (best_d2[l] < 0) {
+            dst[0] = dst[1] = dst[2] = 0.0f;
+        } else {
+            // sqrt of an exact integer: equals np.hypot after the float32 store
+            const double distance = sqrt((double)best_d2[l]);
+            const double norm = distance > 0.0 ? distance : 1.0;
+            dst[0] = (float)((double)best_dx[l] / norm);
+            dst[1] = (float)((double)best_dy[l] / norm);
+            dst[2] = (float)distance;
+        }
+    }
+    return hint;
+}
+
 // Role "state" for ONE agent: float64 need decay (world/grid.py:1439-1455), faint predicate
 // (lifecycle/manager.py:39-45), episode tick (world/core/context.py:283-289), reward with guardrails
 // (rewards/engine.py:71-172) and, when `f` is not null, the scalar features, path hint, landmarks and
@@ -162,6 +233,7 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
                                                  float* f, StateRoleOut& out) {
     const TlObsParams& o = p.obs;
     const int N = p.b.n_agents;
+    TL_MARK_BEGIN();
     const bool do_decay = p.phases & TL_PHASE_DECAY;
     const bool do_reward = p.phases & TL_PHASE_REWARD;
     const bool do_obs = (p.phases & TL_PHASE_OBS) && f != nullptr;
@@ -222,6 +294,7 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
         }
         p.b.episode_tick[a] = episode_tick;
     }
+    TL_MARK(1);
     if (do_reward) {
         RewardResult rr;
         reward_agent(p.rew, rin, tick, need, fl, terminated, reason, rr);
@@ -239,6 +312,7 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
     if (do_state && p.ro.terminated)
         p.ro.terminated[(size_t)it * p.ro.terminated_tick_stride + a] = terminated ? 1 : 0;
     need0 = need[0];
+    TL_MARK(2);
 
     if (do_obs) {  // encoders/features.py:43-404
         f[TL_FEAT_NEED_HUNGER] = (float)need[0];
@@ -258,9 +332,8 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
         if (st > 4) st = 0;
 #pragma unroll
         for (unsigned k = 0; k < 5; ++k) f[TL_FEAT_SHIFT_PRE + k] = (k == st) ? 1.0f : 0.0f;
-        f[TL_FEAT_SLOT_NORM] = (slot_idx >= 0 && slot_idx < o.max_slots)
-                                   ? __ldg(o.slot_lut + slot_idx)
-                                   : (float)((double)slot_idx / (double)o.max_slots);
+        f[TL_FEAT_SLOT_NORM] = (slot_idx >= 0 && slot_idx < o.max_slots) ? __ldg(o.slot_lut + slot_idx)
+                                                                         : slot_norm_out_of_table(slot_idx, o.max_slots);
         f[TL_FEAT_CTX_RESET] = ((fl & TL_F_CTX_RESET) || terminated) ? 1.0f : 0.0f;  // service.py:224-229
         if (fl & TL_F_CTX_RESET) {  // a pending request is reported once (consume_ctx_reset_requests, grid.py:932-936)
             fl &= ~TL_F_CTX_RESET;
@@ -275,6 +348,7 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
         f[TL_FEAT_IN_QUEUE] = (fl & TL_F_IN_QUEUE) ? 1.0f : 0.0f;
         // nearest object per landmark type: first minimum of the squared
         // distance in insertion order (world/observe.py:109-147)
+        TL_MARK(3);
         const int cx = pos_x(pw), cy = pos_y(pw);
         const bool all_types = o.landmark_base >= 0;
         const int e_obj = town_ebeg + (town_aend - town_abeg);
@@ -295,67 +369,37 @@ __device__ __forceinline__ void state_role_agent(const KParams& p, int it, int a
                 hdy = better ? dy : hdy;
             }
         } else {
-            int best_d2[5] = {-1, -1, -1, -1, -1};
-            int best_dx[5] = {0, 0, 0, 0, 0}, best_dy[5] = {0, 0, 0, 0, 0};
-#pragma unroll 1
-            for (int e = e_obj; e < town_eend; ++e) {
-                const uint32_t w = ld_state<MUT>(p.b.ent + e);
-                if (TL_ENT_KIND(w) != TL_KIND_OBJECT || !TL_ENT_LM(w)) continue;
-                const int lt = (int)TL_ENT_LTYPE(w);
-                if (lt == 0) continue;
-                const int dx = TL_ENT_X(w) - cx, dy = TL_ENT_Y(w) - cy;
-                const int d2 = dx * dx + dy * dy;
-#pragma unroll
-                for (int l = 1; l <= 4; ++l) {
-                    if (l == lt && (best_d2[l] < 0 || d2 < best_d2[l])) {
-                        best_d2[l] = d2;
-                        best_dx[l] = dx;
-                        best_dy[l] = dy;
-                    }
-                }
-            }
-#pragma unroll
-            for (int l = 1; l <= 4; ++l) {  // _encode_landmarks, features.py:333-356
-                if (l == o.path_hint_ltype) {
-                    hd2 = best_d2[l];
-                    hdx = best_dx[l];
-                    hdy = best_dy[l];
-                }
-                float* dst = f + o.landmark_base + 3 * (l - 1);
-                if (best_d2[l] < 0) {
-                    dst[0] = dst[1] = dst[2] = 0.0f;
-                } else {
-                    // sqrt of an exact integer: equals np.hypot after the float32 store
-                    const double distance = sqrt((double)best_d2[l]);
-                    const double norm = distance > 0.0 ? distance : 1.0;
-                    dst[0] = (float)((double)best_dx[l] / norm);
-                    dst[1] = (float)((double)best_dy[l] / norm);
-                    dst[2] = (float)distance;
-                }
-            }
+            const NearestHint hint = landmarks_all_types<MUT>(p.b.ent, e_obj, town_eend, cx, cy, o.path_hint_ltype, f + o.landmark_base);
+            hd2 = hint.d2, hdx = hint.dx, hdy = hint.dy;
         }
+        TL_MARK(4);
         {  // _encode_path_hint, features.py:251-286
-            double north = 0.0, south = 0.0, east = 0.0, west = 0.0;
+            // The reference divides in float64 and stores float32: float32(round64(a / b)).  For integers
+            // 0 <= a <= b < 2^24 that equals the correctly rounded float32 quotient: a float32 rounding boundary
+            // m (25 significant bits) other than a / b itself is at least (a / b) * 2^-25 / b away from a / b,
+            // round64 moves a / b by at most (a / b) * 2^-53, so both sit on the same side of every boundary.
+            // One float32 division instead of two float64 ones (checked against the oracle's float64 form).
+            float north = 0.0f, south = 0.0f, east = 0.0f, west = 0.0f;
             if (hd2 > 0) {
-                const double dn = (double)(abs(hdx) + abs(hdy));
-                // max(0, -dy)/norm etc.: one of each opposite pair is exactly 0.0, so two
-                // IEEE divisions give the four values
-                const double ns = (double)abs(hdy) / dn, ew = (double)abs(hdx) / dn;
-                north = hdy < 0 ? ns : 0.0;
-                south = hdy > 0 ? ns : 0.0;
-                east = hdx > 0 ? ew : 0.0;
-                west = hdx < 0 ? ew : 0.0;
+                const float dn = (float)(abs(hdx) + abs(hdy));
+                // max(0, -dy)/norm etc.: one of each opposite pair is exactly 0.0
+                const float ns = __fdiv_rn((float)abs(hdy), dn), ew = __fdiv_rn((float)abs(hdx), dn);
+                north = hdy < 0 ? ns : 0.0f;
+                south = hdy > 0 ? ns : 0.0f;
+                east = hdx > 0 ? ew : 0.0f;
+                west = hdx < 0 ? ew : 0.0f;
             }
-            f[TL_FEAT_PATH_NORTH + 0] = (float)north;
-            f[TL_FEAT_PATH_NORTH + 1] = (float)south;
-            f[TL_FEAT_PATH_NORTH + 2] = (float)east;
-            f[TL_FEAT_PATH_NORTH + 3] = (float)west;
+            f[TL_FEAT_PATH_NORTH + 0] = north;
+            f[TL_FEAT_PATH_NORTH + 1] = south;
+            f[TL_FEAT_PATH_NORTH + 2] = east;
+            f[TL_FEAT_PATH_NORTH + 3] = west;
         }
         if (o.personality_base >= 0) {  // features.py:359-380
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 f[o.personality_base + k] = p.b.personality ? __ldg(p.b.personality + (size_t)k * N + a) : 0.0f;
         }
+        TL_MARK(5);
     }
 }
 

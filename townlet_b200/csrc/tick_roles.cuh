@@ -33,13 +33,6 @@
 // template row and one 2-byte store beside every patch; static hybrid window only,
 // every other form takes the cast pass after the launch).
 
-// -DTL_ROLE_TIMING: two CTAs print the cycles each role spends per tick in its role body and at the pass
-// barrier + sweep (scripts/role_timing.sh; never part of the shipped library)
-#ifdef TL_ROLE_TIMING
-#define TL_TIMING(...) __VA_ARGS__
-#else
-#define TL_TIMING(...)
-#endif
 
 #ifndef TL_TILE_WARPS
 #define TL_TILE_WARPS 2
@@ -53,6 +46,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);  // [2][chunk * F + 4]
     float* s_tmpl = reinterpret_cast<float*>(smem + p.off_map);
     KpiAcc* s_kpi_all = reinterpret_cast<KpiAcc*>(smem + p.off_meta);  // [2][towns_per_cta], by tick parity
+    KpiRaw* s_kpi_raw = reinterpret_cast<KpiRaw*>(smem + p.off_kpi_raw);  // [2][32], by tick parity (KPI hand-off)
 
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
@@ -122,7 +116,12 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     if (lane < n_towns) my_tick = p.b.town_tick[t0 + lane];
     const int a_begin = __shfl_sync(FULL, my_aoff, 0);
     const int a_end = __shfl_sync(FULL, my_aoff, n_towns);
+    const int my_aoff_next = __shfl_down_sync(FULL, my_aoff, 1);  // lane s < n_towns: end of town t0 + s
     const int n_chunks = (a_end - a_begin + chunk_cap - 1) / chunk_cap;
+    // Small single-pass CTAs leave the tile warps waiting for the state role: there the state role only deposits each
+    // agent's KPI terms in shared memory and the KPI-output warp sums them per town after the pass barrier
+    // (one sequential float64 sum per town instead of a segmented shuffle reduction on the critical path).
+    const bool kpi_handoff = p.kpi_out_warp != 0 && n_chunks == 1;
 
     // tiles role: entity words of the town being served (lane l holds entities cached_eb + l + 32 k)
     int cached_eb = -1;
@@ -148,7 +147,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 my_tick += 1;
                 p.b.town_tick[t0 + lane] = my_tick;
             }
-            if (do_kpi && lane < n_towns) {
+            if (do_kpi && !kpi_handoff && lane < n_towns) {
                 KpiAcc z;
                 z.rsum = z.rsq = z.hsum = z.late = z.wallet = 0.0;
                 z.hmin = 1e300;
@@ -190,18 +189,28 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 const int tick = __shfl_sync(FULL, my_tick, slot);
                 // the inputs of this pass were requested at the end of the previous one (same lane = same column)
                 unsigned char* s_state = smem + p.off_state;
+                TL_MARK_BEGIN();
                 if (!state_in_flight && active) prefetch_state_in(p, s_state, a, lane);
                 cp_async_wait_all();
+                TL_MARK(0);
                 StateRoleOut so;
                 if (active)
                     state_role_agent<WORLD>(p, it, a, tick, town_abeg, town_aend, town_ebeg, town_eend,
                                             do_actions ? __ldg(act + a) : 0u, staged_state_in(p, s_state, lane),
                                             do_obs ? feat_s0 + lane * F : nullptr, so);
+                TL_TIMING(tl_mark_t = clock64();)
                 const double need0 = so.need0, reward_total = so.reward_total, kpi_wallet = so.kpi_wallet;
                 const bool terminated = so.terminated;
                 const int kpi_late = so.kpi_late;
-                // ---- per-town KPIs: segmented warp-shuffle reduction ----------------
-                if (do_kpi) {
+                // ---- per-town KPIs: hand-off, or segmented warp-shuffle reduction ----
+                if (do_kpi && kpi_handoff) {
+                    if (active) {
+                        KpiRaw r;
+                        r.reward = reward_total, r.hunger = need0, r.wallet = kpi_wallet, r.late = kpi_late;
+                        r.flags = (need0 <= p.rew.starvation_threshold ? 1 : 0) | (terminated ? 2 : 0);
+                        s_kpi_raw[(it & 1) * 32 + lane] = r;
+                    }
+                } else if (do_kpi) {
                     const int seg = active ? slot : -1 - lane;  // inactive lanes are their own segment
                     double v_r = reward_total, v_q = reward_total * reward_total, v_h = active ? need0 : 0.0;
                     double v_m = active ? need0 : 1e300, v_w = kpi_wallet;
@@ -239,6 +248,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                         k.count += v_c >> 20;
                     }
                 }
+                TL_MARK(6);
                 // The inputs of the NEXT pass start their trip now, after this pass's stores to the same
                 // arrays; they are re-read from global memory every pass, only earlier.
                 state_in_flight = false;
@@ -576,7 +586,29 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
         if (do_kpi && warp == (do_obs ? p.kpi_out_warp : 0)) {
             __syncwarp();
             if (lane < n_towns) {
-                const KpiAcc k = s_kpi[lane];
+                KpiAcc k;
+                if (kpi_handoff) {  // this lane's town: sum its agents' terms (they all sit in the tick's single pass)
+                    k.rsum = k.rsq = k.hsum = k.late = k.wallet = 0.0;
+                    k.hmin = 1e300;
+                    k.starving = k.term = k.count = 0;
+                    const KpiRaw* raw = s_kpi_raw + (it & 1) * 32;
+                    const int i0 = my_aoff - a_begin, i1 = my_aoff_next - a_begin;
+#pragma unroll 1
+                    for (int i = i0; i < i1; ++i) {
+                        const KpiRaw r = raw[i];
+                        k.rsum += r.reward;
+                        k.rsq += r.reward * r.reward;
+                        k.hsum += r.hunger;
+                        k.hmin = fmin(k.hmin, r.hunger);
+                        k.wallet += r.wallet;
+                        k.late += (double)r.late;
+                        k.starving += r.flags & 1;
+                        k.term += (r.flags >> 1) & 1;
+                        k.count += 1;
+                    }
+                } else {
+                    k = s_kpi[lane];
+                }
                 float* dst = p.ro.kpi + (size_t)it * p.ro.kpi_tick_stride + (size_t)(t0 + lane) * TL_N_KPI;
                 const double inv = k.count ? 1.0 / (double)k.count : 0.0;  // one division for the three means
                 dst[TL_KPI_REWARD_SUM] = (float)k.rsum;
@@ -591,6 +623,12 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
             __syncwarp();
         }
     }
+    TL_TIMING(if (blockIdx.x == 0 && tid == 0 && p.n_ticks > 1) {
+        printf("TL_ROLE_TIMING state parts per tick: wait-inputs %lld decay+faint+tick %lld reward %lld scalar-features %lld landmark-scan %lld "
+               "path-hint %lld kpi %lld\n", g_state_parts[0] / p.n_ticks, g_state_parts[1] / p.n_ticks, g_state_parts[2] / p.n_ticks,
+               g_state_parts[3] / p.n_ticks, g_state_parts[4] / p.n_ticks, g_state_parts[5] / p.n_ticks, g_state_parts[6] / p.n_ticks);
+        for (int k = 0; k < 8; ++k) g_state_parts[k] = 0;
+    })
     TL_TIMING(if ((blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && lane == 0 && p.n_ticks > 1)
                   printf("TL_ROLE_TIMING cta %d warp %d (%s) role %lld barrier+sweep %lld total %lld cycles per tick\n", blockIdx.x, warp,
                          warp == 0 ? "state" : (warp == 1 ? "social" : "tiles"), t_role / p.n_ticks, t_rest / p.n_ticks,

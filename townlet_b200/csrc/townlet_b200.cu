@@ -77,6 +77,7 @@ struct KParams {
     int32_t off_social;    // role form: staged relation rows of a pass (4 x double + 2 x embed words per edge)
     int32_t kpi_out_warp;  // role form: warp that writes the per-town KPI rows of a tick (0 state warp, 2 a tile warp)
     int32_t off_state;     // role form: staged per-agent inputs of the state role (kStateStageBytes)
+    int32_t off_kpi_raw;   // role form: per-agent KPI terms of a tick, two parities x 32 lanes (KpiRaw), summed by the KPI-output warp
     int32_t tmpl_mask;     // entity form: bit m set = a tile template for 16-byte misalignment m floats exists
     int32_t tmpl_off[4];   // entity form: float offset of template m inside the template area
 };
@@ -146,6 +147,36 @@ __device__ __forceinline__ RewardIn load_reward_in(const KParams& p, int a) {
     return in;
 }
 
+// RewardEngine._apply_reward_biases (rewards/engine.py:220-255): personality factors on the social, employment and
+// survival components; `delta` accumulates adjusted - base in the reference's order.  Out of line: only worlds with the
+// reward_multipliers flag and a profile run it, and its five float64 divisions are a fifth of the kernel's code.
+struct RewardBias {
+    double sb, sp, sa, wage, punct, survival, delta;
+};
+__device__ __noinline__ RewardBias apply_reward_biases(RewardBias v, double f0, double f1, double f2) {
+    double delta = 0.0;
+    if (f0 != 1.0) {
+        double adj = scale_bias(v.sb, f0);
+        delta += adj - v.sb, v.sb = adj;
+        adj = scale_bias(v.sp, f0);
+        delta += adj - v.sp, v.sp = adj;
+        adj = scale_bias(v.sa, f0);
+        delta += adj - v.sa, v.sa = adj;
+    }
+    if (f1 != 1.0) {
+        double adj = scale_bias(v.wage, f1);
+        delta += adj - v.wage, v.wage = adj;
+        adj = scale_bias(v.punct, f1);
+        delta += adj - v.punct, v.punct = adj;
+    }
+    if (f2 != 1.0) {
+        const double adj = scale_bias(v.survival, f2);
+        delta += adj - v.survival, v.survival = adj;
+    }
+    v.delta = delta;
+    return v;
+}
+
 __device__ __forceinline__ void reward_agent(const TlRewardParams& r, const RewardIn& in, int tick,
                                              const double (&need)[3], uint32_t fl, bool terminated, unsigned reason,
                                              RewardResult& out) {
@@ -178,32 +209,13 @@ __device__ __forceinline__ void reward_agent(const TlRewardParams& r, const Rewa
     c[TL_COMP_PUNCTUALITY] = punct;
     unsigned profile = (fl & TL_F_PROFILE_MASK) >> TL_F_PROFILE_SHIFT;
     if (r.reward_personality && profile != 0) {  // engine.py:104-106, 220-255
-        double delta = 0.0;
-        double f0 = r.reward_bias[profile][0], f1 = r.reward_bias[profile][1], f2 = r.reward_bias[profile][2];
-        if (f0 != 1.0) {
-#pragma unroll
-            for (int idx = TL_COMP_SOCIAL_BONUS; idx <= TL_COMP_SOCIAL_AVOIDANCE; ++idx) {
-                double base = c[idx], adj = scale_bias(base, f0);
-                c[idx] = adj;
-                delta += adj - base;
-            }
-            c[TL_COMP_SOCIAL] = c[TL_COMP_SOCIAL_BONUS] + c[TL_COMP_SOCIAL_PENALTY] + c[TL_COMP_SOCIAL_AVOIDANCE];
-        }
-        if (f1 != 1.0) {
-            double base = c[TL_COMP_WAGE], adj = scale_bias(base, f1);
-            c[TL_COMP_WAGE] = adj;
-            delta += adj - base;
-            base = c[TL_COMP_PUNCTUALITY];
-            adj = scale_bias(base, f1);
-            c[TL_COMP_PUNCTUALITY] = adj;
-            delta += adj - base;
-        }
-        if (f2 != 1.0) {
-            double base = c[TL_COMP_SURVIVAL], adj = scale_bias(base, f2);
-            c[TL_COMP_SURVIVAL] = adj;
-            delta += adj - base;
-        }
-        total += delta;
+        const RewardBias b = apply_reward_biases(RewardBias{c[TL_COMP_SOCIAL_BONUS], c[TL_COMP_SOCIAL_PENALTY], c[TL_COMP_SOCIAL_AVOIDANCE],
+                                                            c[TL_COMP_WAGE], c[TL_COMP_PUNCTUALITY], c[TL_COMP_SURVIVAL], 0.0},
+                                                 r.reward_bias[profile][0], r.reward_bias[profile][1], r.reward_bias[profile][2]);
+        c[TL_COMP_SOCIAL_BONUS] = b.sb, c[TL_COMP_SOCIAL_PENALTY] = b.sp, c[TL_COMP_SOCIAL_AVOIDANCE] = b.sa;
+        c[TL_COMP_SOCIAL] = b.sb + b.sp + b.sa;  // unchanged values add up to the same sum
+        c[TL_COMP_WAGE] = b.wage, c[TL_COMP_PUNCTUALITY] = b.punct, c[TL_COMP_SURVIVAL] = b.survival;
+        total += b.delta;
     }
     double penalty = 0.0;  // engine.py:400-413
     if (terminated) {
@@ -262,6 +274,12 @@ __device__ __forceinline__ T seg_reduce(T v, int seg, int lane, Op op) {
 struct KpiAcc {
     double rsum, rsq, hmin, hsum, late, wallet;
     int starving, term, count;
+};
+
+// KPI terms of ONE agent and tick, handed from the state role to the warp that writes the KPI rows
+struct KpiRaw {
+    double reward, hunger, wallet;
+    int late, flags;  // flags: bit 0 starving, bit 1 terminated
 };
 
 #include "agent_roles.cuh"
@@ -629,6 +647,8 @@ int prepare(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* 
         kp.off_meta = off;
         off += round_up(2 * (int)sizeof(KpiAcc) * tpc, 16);  // two tick parities
         kp.kpi_out_warp = (do_obs && kp.chunk <= 16) ? 2 : 0;  // measured: +5 % on configs[1], -3 % on 30-agent passes
+        kp.off_kpi_raw = off;
+        off += kp.kpi_out_warp ? 2 * 32 * (int)sizeof(KpiRaw) : 0;
         kp.off_state = off;
         off += kStateStageBytes;
         kp.off_social = off;
