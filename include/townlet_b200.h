@@ -74,6 +74,10 @@ extern "C" {
 #define TL_PHASE_ACTIONS 16u      /* apply the tick's action words: moves + outcome bookkeeping
                                      (world/actions.py:44-105, world/systems/affordances.py:105-229) */
 #define TL_PHASE_SOCIAL_DECAY 32u /* RelationshipService.decay (world/agents/relationships_service.py:165-191) */
+#define TL_PHASE_RESERVATIONS 64u /* refresh_reservations (world/systems/queues.py:14-31,55-86; world/spatial.py:106-119):
+                                     the reserved-tile entity words and the agents' TL_F_RESERVATION flag are re-derived
+                                     every tick from TlTownBatch.ent_holder (who holds which object, as the host's queue
+                                     manager granted it) instead of being ingested */
 
 /*
  * Action word (uint32), one per agent and tick; what process_actions leaves on the agent snapshot.
@@ -114,13 +118,16 @@ extern "C" {
  *   bits 20-21  kind   0 agent occupancy (cache.py:28-31)
  *                      1 object (cache.py:33-38 / observe.py:109-147)
  *                      2 reserved tile (world/spatial.py:117-120)
+ *                      3 empty slot: ignored by every reader (a reservation slot whose object is free)
  *   bits 22-24  ltype  landmark code, exact match on object_type:
  *                      0 other, 1 fridge, 2 stove, 3 bed, 4 shower
  *   bits 25-28  ctype  1 + index into compact.object_channels, 0 = none
  *   bit  29     lm     object is a nearest-of-type candidate
  *   bit  30     tile   object is present in the position lookup
  * Per town, entities are stored agents first (one per agent, agent order),
- * then objects in insertion order, then reserved tiles.
+ * then objects in insertion order, then reserved tiles.  With TL_PHASE_RESERVATIONS the reserved tiles are
+ * reservation SLOTS, one per object that has a position, in object order (kind 2 while reserved, 3 while free,
+ * x / y = the object's position), followed by any reserved tile no object accounts for; ent_holder tells them apart.
  */
 #define TL_ENT_X(e) ((int)((e) & 1023u))
 #define TL_ENT_Y(e) ((int)(((e) >> 10) & 1023u))
@@ -136,6 +143,7 @@ extern "C" {
 #define TL_KIND_AGENT 0u
 #define TL_KIND_OBJECT 1u
 #define TL_KIND_RESERVED 2u
+#define TL_KIND_EMPTY 3u
 #define TL_MAX_GRID 1024
 
 /* per-agent flag word */
@@ -291,6 +299,11 @@ typedef struct TlTownBatch {
     uint64_t* riv_embed; /* [N][K][EW] */
     double* riv_score;   /* [N][K] */
 
+    /* ABI v4, TL_PHASE_RESERVATIONS: per entity, for a reservation slot the town-local index of the agent the queue
+     * manager has granted the slot's object to (QueueManager.active_agent, world/queue/manager.py) or -1 while the
+     * object is free; -2 for every other entity.  May be NULL when the phase is not requested. */
+    const int32_t* ent_holder; /* [E] */
+
     /* ABI v4, host-buffer entry points only: when every array above lies inside ONE caller-owned block
      * [arena_base, arena_base + arena_bytes) the batch crosses the bus as a single copy (the layout of soa.py).
      * NULL / 0 = the arrays are separate allocations: one copy per array, and nothing outside an array is
@@ -436,9 +449,9 @@ int tl_tick(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardPara
             const TlObsOut* obs_out, const TlRewardOut* rew_out, uint32_t phases, int32_t n_ticks,
             tl_stream_t stream);
 
-/* tl_tick plus the world-dynamics phases (TL_PHASE_ACTIONS, TL_PHASE_SOCIAL_DECAY); per tick:
- * actions -> need decay -> ledger decay -> faint -> reward -> episode_tick -> observe.
- * dyn may be NULL when neither phase is requested. */
+/* tl_tick plus the world-dynamics phases (TL_PHASE_ACTIONS, TL_PHASE_SOCIAL_DECAY, TL_PHASE_RESERVATIONS); per tick:
+ * actions -> reservation refresh -> need decay -> ledger decay -> faint -> reward -> episode_tick -> observe.
+ * dyn may be NULL when neither TL_PHASE_ACTIONS nor TL_PHASE_SOCIAL_DECAY is requested. */
 int tl_tick_world(const TlTownBatch* batch, const TlObsParams* obs, const TlRewardParams* rew,
                   const TlDynamicsParams* dyn, const TlObsOut* obs_out, const TlRewardOut* rew_out,
                   uint32_t phases, int32_t n_ticks, tl_stream_t stream);
@@ -555,7 +568,7 @@ enum {
     TL_FIELD_EPISODE_TOTAL, TL_FIELD_SOCIAL_IN, TL_FIELD_TERM_BLOCK_TICK, TL_FIELD_LATENESS, TL_FIELD_LAST_ACTION_DURATION,
     TL_FIELD_EPISODE_TICK, TL_FIELD_SLOT, TL_FIELD_FLAGS, TL_FIELD_LAST_ACTION_HASH, TL_FIELD_PERSONALITY, TL_FIELD_TIE_COUNT,
     TL_FIELD_TIE_EMBED, TL_FIELD_TIE_TRUST, TL_FIELD_TIE_FAM, TL_FIELD_TIE_RIV, TL_FIELD_RIV_COUNT, TL_FIELD_RIV_EMBED,
-    TL_FIELD_RIV_SCORE, TL_N_FIELDS
+    TL_FIELD_RIV_SCORE, TL_FIELD_ENT_HOLDER, TL_N_FIELDS
 };
 #define TL_DIRTY_ALL (~(uint64_t)0)
 

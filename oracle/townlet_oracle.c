@@ -686,6 +686,46 @@ static void social_decay(const TlTownBatch* b, const TlDynamicsParams* d, int a)
     }
 }
 
+/* refresh_reservations, world/systems/queues.py:55-86 (run every tick by queues.step, :14-31): the objects are
+ * walked in order; an object with an active agent adds its tile to the reservation set and records the holder, a free
+ * object discards the tile (world/spatial.py:106-119).  The set is replayed on a scratch list of tiles, then written
+ * back as the slot words: a tile that is in the set is carried by the last slot standing on it.  Holders get
+ * TL_F_RESERVATION (encoders/features.py:215-219). */
+static void refresh_reservations(const TlTownBatch* b, int t) {
+    int a0 = b->town_agent_off[t], a1 = b->town_agent_off[t + 1];
+    int e0 = b->town_ent_off[t] + (a1 - a0), e1 = b->town_ent_off[t + 1];
+    for (int a = a0; a < a1; ++a) b->flags[a] &= ~TL_F_RESERVATION;
+    int n = e1 - e0;
+    if (n <= 0) return;
+    uint32_t* tiles = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n); /* the reservation set, as a list of tiles */
+    int n_tiles = 0;
+    for (int e = e0; e < e1; ++e) {
+        int holder = b->ent_holder[e];
+        if (holder < -1) continue; /* not a reservation slot */
+        uint32_t tile = b->ent[e] & 0xfffffu;
+        int at = -1;
+        for (int i = 0; i < n_tiles; ++i)
+            if (tiles[i] == tile) at = i;
+        if (holder >= 0) { /* _reservation_tiles.add(position); active_reservations[object] = agent */
+            if (at < 0) tiles[n_tiles++] = tile;
+            if (holder < a1 - a0) b->flags[a0 + holder] |= TL_F_RESERVATION;
+        } else if (at >= 0) { /* _reservation_tiles.discard(position) */
+            tiles[at] = tiles[--n_tiles];
+        }
+    }
+    for (int e = e0; e < e1; ++e) {
+        if (b->ent_holder[e] < -1) continue;
+        uint32_t tile = b->ent[e] & 0xfffffu;
+        int reserved = 0, last = 1;
+        for (int i = 0; i < n_tiles; ++i) reserved |= tiles[i] == tile;
+        for (int l = e + 1; l < e1; ++l)
+            if (b->ent_holder[l] >= -1 && (b->ent[l] & 0xfffffu) == tile) last = 0;
+        uint32_t kind = (reserved && last) ? TL_KIND_RESERVED : TL_KIND_EMPTY;
+        b->ent[e] = (b->ent[e] & ~(3u << 20)) | (kind << 20);
+    }
+    free(tiles);
+}
+
 /* One town, one tick, in SimulationLoop.step order (core/sim_loop.py:632-958). */
 static void town_tick(const TlTownBatch* b, const TlObsParams* p, const TlRewardParams* r, const TlDynamicsParams* d,
                       const TlObsOut* oo, const TlRewardOut* ro, uint32_t phases, int t, int it, TownCache* cache,
@@ -695,6 +735,7 @@ static void town_tick(const TlTownBatch* b, const TlObsParams* p, const TlReward
     if (phases & TL_PHASE_ADVANCE) b->town_tick[t] += 1; /* sim_loop.py:635,659 */
     if ((phases & TL_PHASE_ACTIONS) && d->actions) /* world/core/context.py:253-257 */
         for (int a = a0; a < a1; ++a) apply_action(b, d, t, a, d->actions[(size_t)it * d->actions_tick_stride + a]);
+    if ((phases & TL_PHASE_RESERVATIONS) && b->ent_holder) refresh_reservations(b, t); /* queues.step, first of the systems */
     double k_rsum = 0, k_rsq = 0, k_hmin = INFINITY, k_hsum = 0, k_late = 0, k_wallet = 0;
     int k_starving = 0, k_term = 0;
     for (int a = a0; a < a1; ++a) {

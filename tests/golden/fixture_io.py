@@ -60,7 +60,13 @@ def load_fixture(path: Path):
     data = np.load(path, allow_pickle=False)
     meta = json.loads(str(data["meta"]))
     layout = BatchLayout.make(meta["n_towns"], meta["n_agents"], meta["n_entities"], meta["max_edges"], meta["embed_words"])
-    batch = TownBatch(layout, meta["grid_w"], meta["grid_h"], np.array(data["arena"], dtype=np.uint8))
+    arena = np.array(data["arena"], dtype=np.uint8)
+    legacy = arena.size < layout.total_bytes  # stored before TlTownBatch.ent_holder (the last array of the arena) existed
+    if legacy:
+        arena = np.concatenate([arena, np.zeros(layout.total_bytes - arena.size, dtype=np.uint8)])
+    batch = TownBatch(layout, meta["grid_w"], meta["grid_h"], arena)
+    if legacy:
+        batch.ent_holder[...] = -2  # no reservation slots
     batch.has_social_in = meta["has_social_in"]
     batch.has_personality = meta["has_personality"]
     obs_kwargs = dict(meta["obs"])

@@ -309,6 +309,71 @@ def crowded_cases():
         obs_fixture(f"crowded_{tag}", world, config, terminated={"c": True}, note="SURVEY Appendix A1/A3/A5/A6 behaviours")
 
 
+def reservation_cases():
+    """TL_PHASE_RESERVATIONS: the reference's ``refresh_reservations``
+    (world/systems/queues.py:55-86, driven by ``queues.step`` :14-31) against the device phase.  Each world is ingested
+    in a STALE state — grants made and withdrawn through the queue manager without a refresh, as between two ticks
+    (Appendix A6) — then the reference refreshes and observes; the fixture stores the stale batch, the post-refresh
+    observation and the post-refresh entity words / flags of a second ingest."""
+    for variant in ("hybrid", "compact"):
+        config = make_config(variant)
+        spec = ObsSpec.from_config(config)
+        world = WorldState.from_config(config)
+        world.tick = 4321
+        for oid, otype, pos in (
+            ("stove_a", "stove", (2, 1)),
+            ("fridge_a", "fridge", (2, 1)),   # shares the stove's tile: the later object decides the tile
+            ("bed_a", "bed", (-3, 2)),
+            ("bed_b", "bed", (-3, 2)),        # shares bed_a's tile
+            ("shower_a", "shower", (0, -4)),
+            ("stove_far", "stove", (6, 6)),
+        ):
+            world.register_object(object_id=oid, object_type=otype, position=pos)
+        spots = {"a": (0, 0), "b": (1, 0), "c": (2, 0), "d": (2, 1), "e": (-3, 1), "f": (0, -3)}
+        for k, (aid, pos) in enumerate(spots.items()):
+            world.agents[aid] = AgentSnapshot(agent_id=aid, position=pos, needs={"hunger": 0.3 + 0.1 * k, "hygiene": 0.6, "energy": 0.7},
+                                              wallet=float(k), episode_tick=10 * k)
+        world.rebuild_spatial_index()
+        qm = world.queue_manager
+        # state of the previous tick, refreshed: stove_a held by d, shower_a held by f with a waiting queue
+        qm.request_access("stove_a", "d", world.tick)
+        qm.request_access("shower_a", "f", world.tick)
+        qm.request_access("shower_a", "a", world.tick)  # a waits (in_queue, not a holder)
+        world.refresh_reservations()
+        world._spatial_index.set_reservation((4, 4), True)  # a reserved tile no object accounts for: untouched by the refresh
+        # between the ticks, through the queue manager only (no sync): d lets go of the stove, b is granted the fridge on
+        # the same tile, e is granted bed_a while bed_b (later, same tile) stays free, c is granted the far stove
+        qm.release("stove_a", "d", world.tick, success=True)
+        qm.request_access("fridge_a", "b", world.tick)
+        qm.request_access("bed_a", "e", world.tick)
+        qm.request_access("stove_far", "c", world.tick)
+        world.tick += 1
+        pending = set(world._ctx_reset_requests)
+        slots = {aid: world.embedding_allocator.allocate(aid, world.tick) for aid in world.agents}
+        rows = ingest_town(world, spec, terminated={}, reasons={}, pending_resets=pending, slots=slots, device_reservations=True)
+        batch = rows_to_batch([rows], spec)
+        batch.validate(len(spec.object_channels))
+        stale_kinds = (batch.ent >> 20) & 3
+        world.refresh_reservations()  # what queues.step does at the start of the tick
+        service = WorldObservationService(config=config)
+        ids, maps, feats, summ, _ = reference_obs(world, service, {})
+        assert ids == rows.agent_ids
+        after = ingest_town(world, spec, terminated={}, reasons={}, pending_resets=set(), slots=slots, device_reservations=True,
+                            origin=rows.origin)
+        after_batch = rows_to_batch([after], spec, grid=(batch.grid_w, batch.grid_h))
+        assert np.array_equal(after_batch.ent_holder, batch.ent_holder)
+        assert not np.array_equal((after_batch.ent >> 20) & 3, stale_kinds), "the refresh must change some slot"
+        assert world.reservation_tiles() == frozenset({(2, 1), (0, -4), (6, 6), (4, 4)}), world.reservation_tiles()
+        save_fixture(
+            GOLDEN_DIR / f"reservations_{variant}.npz", batch, spec, RewardSpec.from_config(config),
+            capi.TL_PHASE_RESERVATIONS | capi.TL_PHASE_OBS, 1,
+            {"map": maps[None], "features": feats[None], "summary": summ[None], "ent_after": after_batch.ent[None],
+             "flags_after": after_batch.flags[None]},
+            note="stale reservation slots + holders; the reference's refresh_reservations and observation",
+        )
+        print(f"  reservations_{variant}: {len(ids)} agents, {int((batch.ent_holder >= -1).sum())} slots, tiles {sorted(world.reservation_tiles())}")
+
+
 # ---------------------------------------------------------------------------
 # 3. synthetic towns of the benchmark generator, materialised in the reference
 # ---------------------------------------------------------------------------
@@ -1269,13 +1334,14 @@ def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
     only = os.environ.get("TL_GOLDEN_ONLY")
     if only:
-        {"synth": synth_cases, "gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world, "fuzz-dropin": fuzz_dropin, "fuzz-gae": fuzz_gae}[only]()
+        {"synth": synth_cases, "reservations": reservation_cases, "gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world, "fuzz-dropin": fuzz_dropin, "fuzz-gae": fuzz_gae}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()
     social_snippet()
     builder_cases()
     crowded_cases()
+    reservation_cases()
     synth_cases()
     reward_cases()
     snapshot_cases()

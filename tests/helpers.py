@@ -60,3 +60,13 @@ def assert_kpi_close(got: dict, ref: dict, batch, what: str) -> None:
     variance = g[..., capi.KPI_NAMES.index("reward_sumsq")] / count - mean**2
     np.testing.assert_allclose(mean, ref["kpi_reward_mean"], rtol=1e-5, atol=1e-7, err_msg=f"{what}: reward mean")
     np.testing.assert_allclose(variance, ref["kpi_reward_variance"], rtol=1e-4, atol=1e-7, err_msg=f"{what}: reward variance")
+
+
+def assert_refreshed_state(batch, ref: dict, what: str) -> None:
+    """TL_PHASE_RESERVATIONS fixtures: the entity words and the holders' flag after the launch equal a second ingest of the
+    reference world after its own refresh_reservations."""
+    if "ent_after" not in ref:
+        return
+    assert np.array_equal(np.asarray(batch.ent), ref["ent_after"][-1]), f"{what}: entity words after the refresh"
+    bit = capi.TL_F_RESERVATION
+    assert np.array_equal(np.asarray(batch.flags) & bit, ref["flags_after"][-1] & bit), f"{what}: TL_F_RESERVATION after the refresh"

@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 import pytest
 from fixture_io import fixture_paths, load_fixture
-from helpers import REL_TOL, assert_kpi_close, assert_obs_equal, assert_reward_close
+from helpers import REL_TOL, assert_kpi_close, assert_obs_equal, assert_refreshed_state, assert_reward_close
 
 from townlet_b200 import capi
 from townlet_b200.params import ObsSpec, RewardSpec
@@ -32,7 +32,7 @@ def _device_run(batch, obs, rew, phases, n_ticks, tick_by_tick=False):
     else:
         dev.tick(out, phases, n_ticks)
     torch.cuda.synchronize()
-    dev.download_state()
+    dev.download_state(full=bool(phases & capi.TL_PHASE_RESERVATIONS))
     return {k: v.cpu().numpy() for k, v in vars(out).items() if v is not None}
 
 
@@ -47,6 +47,7 @@ def _host_run(batch, obs, rew, phases, n_ticks):
 
 
 def _check_state(batch, ref):
+    assert_refreshed_state(batch, ref, "state")
     if "needs" in ref:
         np.testing.assert_allclose(batch.needs, ref["needs"][-1], rtol=REL_TOL, atol=1e-15)
     if "episode_total" in ref:

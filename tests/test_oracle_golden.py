@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 import pytest
 from fixture_io import fixture_paths, load_fixture
-from helpers import assert_kpi_close, assert_obs_equal, assert_reward_close
+from helpers import assert_kpi_close, assert_obs_equal, assert_refreshed_state, assert_reward_close
 
 from oracle.oracle import oracle_tick
 from townlet_b200 import capi
@@ -41,6 +41,7 @@ def test_oracle_matches_reference(path) -> None:
     assert_obs_equal(out, ref, path.stem)
     assert_reward_close(out, ref, path.stem)
     assert_kpi_close(out, ref, batch, path.stem)
+    assert_refreshed_state(batch, ref, path.stem)
     if "needs" in ref:  # state after the last tick
         np.testing.assert_allclose(batch.needs, ref["needs"][-1], rtol=1e-6, atol=1e-15)
     if "episode_total" in ref:

@@ -42,6 +42,7 @@ TL_PHASE_ADVANCE = 8
 TL_PHASE_ALL = 15
 TL_PHASE_ACTIONS = 16  # needs TlDynamicsParams (tl_tick_world)
 TL_PHASE_SOCIAL_DECAY = 32
+TL_PHASE_RESERVATIONS = 64  # reservation slots and TL_F_RESERVATION re-derived from TlTownBatch.ent_holder every tick
 TL_PHASE_WORLD = TL_PHASE_ALL | TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY
 
 # action kinds of the action word (include/townlet_b200.h: TL_ACT_*)
@@ -51,6 +52,7 @@ ACT_KINDS = ("", "move", "noop", "wait", "request", "start", "release", "chat", 
 TL_KIND_AGENT = 0
 TL_KIND_OBJECT = 1
 TL_KIND_RESERVED = 2
+TL_KIND_EMPTY = 3
 
 TL_F_ON_SHIFT = 1 << 0
 TL_F_SHIFT_SHIFT = 1
@@ -147,6 +149,7 @@ class TlTownBatch(C.Structure):
         ("riv_count", _p),
         ("riv_embed", _p),
         ("riv_score", _p),
+        ("ent_holder", _p),
         ("arena_base", _p),
         ("arena_bytes", C.c_int64),
     ]
@@ -276,7 +279,7 @@ TL_WIRE = {"f32": 0, "u8": 1, "bits": 2}
 TL_MAP_F32, TL_MAP_WIRE = 0, 1
 TL_DIRTY_ALL = 2**64 - 1
 # index of every TlTownBatch array in TlHostStep.dirty_fields (declaration order of the struct)
-FIELD_INDEX = {name: i for i, (name, _) in enumerate(TlTownBatch._fields_[8:37])}
+FIELD_INDEX = {name: i for i, (name, _) in enumerate(TlTownBatch._fields_[8:38])}
 
 EXPORTED_SYMBOLS = (
     "tl_last_error",

@@ -68,6 +68,50 @@ __device__ __forceinline__ uint32_t moved_ent(uint32_t ew, uint32_t act_w) {
     return ew;
 }
 
+// refresh_reservations for ONE town by one warp (world/systems/queues.py:55-86 driven per tick by queues.step, :14-31):
+// the reference walks the objects in order and, for each, adds the object's tile to the reservation set when the queue
+// manager has an active agent for it and discards the tile otherwise (world/spatial.py:106-119) — so a tile ends up
+// reserved exactly when the LAST object standing on it is held.  Here every object with a position owns a reservation
+// slot in the town's entity list (ent_holder >= -1, in object order); the slot becomes a reserved-tile word when its
+// object is the last slot on the tile and is held, an empty word otherwise.  Agents that hold any object get
+// TL_F_RESERVATION (features.py:215-219), all others lose it.  Entities with ent_holder == -2 are left alone.
+__device__ __forceinline__ void refresh_reservations_town(const KParams& p, int abeg, int aend, int ebeg, int eend, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    for (int a = abeg + lane; a < aend; a += 32) p.b.flags[a] &= ~TL_F_RESERVATION;
+    __syncwarp();
+    const int n_agents = aend - abeg;
+    const int e0 = ebeg + n_agents;  // the agents' own words lead the list
+#pragma unroll 1
+    for (int base = e0; base < eend; base += 32) {
+        const int e = base + lane;
+        const bool in = e < eend;
+        const uint32_t w = in ? p.b.ent[e] : 0u;
+        const int holder = in ? __ldg(p.b.ent_holder + e) : -2;
+        const bool slot = holder >= -1;
+        const uint32_t tile = w & 0xfffffu;
+        // a later slot on the same tile decides instead of this one: first within the 32 entities of this step ...
+        const unsigned peers = __match_any_sync(FULL, slot ? tile : (0x100000u | (unsigned)lane));
+        bool later = slot && (peers >> lane) > 1u;
+        // ... then in the rest of the list (towns with more than 32 objects)
+#pragma unroll 1
+        for (int nb = base + 32; nb < eend; nb += 32) {
+            const int ne = nb + lane;
+            const bool nin = ne < eend;
+            const uint32_t nw = nin ? p.b.ent[ne] : 0u;
+            const bool nslot = nin && __ldg(p.b.ent_holder + ne) >= -1;
+            const uint32_t ntile = nslot ? (nw & 0xfffffu) : 0xffffffffu;
+#pragma unroll 1
+            for (int i = 0; i < 32; ++i) later = later || (slot && __shfl_sync(FULL, ntile, i) == tile);
+        }
+        if (slot) {
+            const uint32_t kind = (holder >= 0 && !later) ? TL_KIND_RESERVED : TL_KIND_EMPTY;
+            const uint32_t nw = (w & ~(3u << 20)) | (kind << 20);
+            if (nw != w) p.b.ent[e] = nw;
+            if (holder >= 0 && holder < n_agents) atomicOr(p.b.flags + abeg + holder, TL_F_RESERVATION);
+        }
+    }
+}
+
 // The scalar inputs of ONE agent for one tick (AgentSnapshot fields, world/agents/snapshot.py:19-44, the
 // employment context and the reward engine's per-agent state).
 struct StateIn {

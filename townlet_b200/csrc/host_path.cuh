@@ -398,6 +398,7 @@ int tl_host_submit(TlContext* ctx, int32_t slot_index, const TlHostStep* st) {
     const bool do_adv = phases & TL_PHASE_ADVANCE;
     const bool do_act = phases & TL_PHASE_ACTIONS;       // rewrites positions, agent entity words, last-action fields
     const bool do_led = phases & TL_PHASE_SOCIAL_DECAY;  // rewrites the relationship and rivalry ledgers
+    const bool do_res = phases & TL_PHASE_RESERVATIONS;  // rewrites the reservation slots and TL_F_RESERVATION
     const bool do_decay = phases & TL_PHASE_DECAY, do_reward = phases & TL_PHASE_REWARD;
 
     // ---- the batch arrays: host pointer, bytes, whether the phases mutate them -------------------------------
@@ -414,7 +415,7 @@ int tl_host_submit(TlContext* ctx, int32_t slot_index, const TlHostStep* st) {
     FIELD(TL_FIELD_TOWN_AGENT_OFF, town_agent_off, (T + 1) * 4, false);
     FIELD(TL_FIELD_TOWN_ENT_OFF, town_ent_off, (T + 1) * 4, false);
     FIELD(TL_FIELD_TOWN_TICK, town_tick, T * 4, do_adv);
-    FIELD(TL_FIELD_ENT, ent, E * 4, do_act);
+    FIELD(TL_FIELD_ENT, ent, E * 4, do_act || do_res);
     FIELD(TL_FIELD_POS, pos, N * 4, do_act);
     FIELD(TL_FIELD_NEEDS, needs, 3 * N * 8, do_decay);
     FIELD(TL_FIELD_WALLET, wallet, N * 8, false);
@@ -429,7 +430,7 @@ int tl_host_submit(TlContext* ctx, int32_t slot_index, const TlHostStep* st) {
     FIELD(TL_FIELD_LAST_ACTION_DURATION, last_action_duration, N * 4, do_act);
     FIELD(TL_FIELD_EPISODE_TICK, episode_tick, N * 4, do_adv);
     FIELD(TL_FIELD_SLOT, slot, N * 4, false);
-    FIELD(TL_FIELD_FLAGS, flags, N * 4, do_state || do_act || do_obs);  // the observation consumes TL_F_CTX_RESET
+    FIELD(TL_FIELD_FLAGS, flags, N * 4, do_state || do_act || do_obs || do_res);  // the observation consumes TL_F_CTX_RESET
     FIELD(TL_FIELD_LAST_ACTION_HASH, last_action_hash, N * 4, do_act);
     FIELD(TL_FIELD_PERSONALITY, personality, 3 * N * 4, false);
     FIELD(TL_FIELD_TIE_COUNT, tie_count, N, do_led);
@@ -440,6 +441,7 @@ int tl_host_submit(TlContext* ctx, int32_t slot_index, const TlHostStep* st) {
     FIELD(TL_FIELD_RIV_COUNT, riv_count, N, do_led);
     FIELD(TL_FIELD_RIV_EMBED, riv_embed, N * K * EW * 8, do_led);
     FIELD(TL_FIELD_RIV_SCORE, riv_score, N * K * 8, do_led);
+    FIELD(TL_FIELD_ENT_HOLDER, ent_holder, E * 4, false);
 #undef FIELD
 
     // One copy for the whole batch only when the caller DECLARES that its arrays share one block

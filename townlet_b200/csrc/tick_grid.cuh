@@ -101,6 +101,11 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(const __grid_constant__ 
         }
         // world/core/context.py:253-257: actions land before any system or observer runs
         if (do_actions) apply_actions_cta(p, it, t0, n_towns, tid, kThreads);
+        if (p.phases & TL_PHASE_RESERVATIONS) {  // queues.step: one warp per town refreshes the reservation slots
+            if (do_actions) __syncthreads();  // both rewrite the agents' flag words
+            for (int s = warp; s < n_towns; s += kWarps)
+                refresh_reservations_town(p, s_town[s].agent_begin, s_town[s].agent_end, s_town[s].ent_begin, s_town[s].ent_end, lane);
+        }
         // ---- stage the town grids (cache.py:16-41) ---------------------------
         if (do_obs) {
             const int words = (n_towns * p.grid_tiles + 1) >> 1;

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
     // WORLD: the launch runs world-dynamics phases (they rewrite pos / ent / ledger rows: plain loads)
     const bool do_actions = WORLD && (p.phases & TL_PHASE_ACTIONS);
     const bool do_social_decay = WORLD && (p.phases & TL_PHASE_SOCIAL_DECAY);
+    const bool do_reservations = WORLD && (p.phases & TL_PHASE_RESERVATIONS);
 
     const TlObsParams& o = p.obs;
     constexpr bool kStatic = WT > 0;
@@ -140,6 +141,17 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
         // world/core/context.py:253-257: actions land before any system or observer runs.  No barrier: the state
         // role writes its agent's move back, and every reader of pos / ent re-derives it from the action words.
         const uint32_t* act = do_actions ? p.dyn.actions + (size_t)it * p.dyn.actions_tick_stride : nullptr;
+        if (do_reservations) {
+            // queues.step runs before any observer (world/systems/__init__.py order): the state warp rewrites the
+            // reservation slots and the holders' flags of the CTA's towns, one barrier hands them to every role
+            if (warp == 0) {
+#pragma unroll 1
+                for (int s = 0; s < n_towns; ++s)
+                    refresh_reservations_town(p, __shfl_sync(FULL, my_aoff, s), __shfl_sync(FULL, my_aoff, s + 1),
+                                              __shfl_sync(FULL, my_eoff, s), __shfl_sync(FULL, my_eoff, s + 1), lane);
+            }
+            __syncthreads();
+        }
         // KPI partials of this tick; the other parity is being written out by a tile warp (see below)
         KpiAcc* s_kpi = s_kpi_all + (it & 1) * p.towns_per_cta;
         if (warp == 0) {
@@ -194,10 +206,12 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 cp_async_wait_all();
                 TL_MARK(0);
                 StateRoleOut so;
-                if (active)
+                if (active) {
+                    StateIn sin = staged_state_in(p, s_state, lane);
+                    if (do_reservations) sin.fl = p.b.flags[a];  // the staged word predates this tick's refresh
                     state_role_agent<WORLD>(p, it, a, tick, town_abeg, town_aend, town_ebeg, town_eend,
-                                            do_actions ? __ldg(act + a) : 0u, staged_state_in(p, s_state, lane),
-                                            do_obs ? feat_s0 + lane * F : nullptr, so);
+                                            do_actions ? __ldg(act + a) : 0u, sin, do_obs ? feat_s0 + lane * F : nullptr, so);
+                }
                 TL_TIMING(tl_mark_t = clock64();)
                 const double need0 = so.need0, reward_total = so.reward_total, kpi_wallet = so.kpi_wallet;
                 const bool terminated = so.terminated;

@@ -448,13 +448,14 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
     if (b->grid_w < 1 || b->grid_h < 1 || b->grid_w > TL_MAX_GRID || b->grid_h > TL_MAX_GRID)
         return set_error("grid size out of range"), TL_ERR_ARG;
     const uint32_t known = TL_PHASE_DECAY | TL_PHASE_REWARD | TL_PHASE_OBS | TL_PHASE_ADVANCE | TL_PHASE_ACTIONS |
-                           TL_PHASE_SOCIAL_DECAY;
+                           TL_PHASE_SOCIAL_DECAY | TL_PHASE_RESERVATIONS;
     if (!(phases & known)) return set_error("empty phase mask"), TL_ERR_ARG;
     if (phases & ~known) return set_error("unknown phase bit"), TL_ERR_ARG;
     if (phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY)) {
         if (!dyn) return set_error("dynamics params are NULL (use tl_tick_world)"), TL_ERR_ARG;
         if ((phases & TL_PHASE_ACTIONS) && !dyn->actions) return set_error("action words are NULL"), TL_ERR_ARG;
     }
+    if ((phases & TL_PHASE_RESERVATIONS) && !b->ent_holder) return set_error("ent_holder is NULL (TL_PHASE_RESERVATIONS)"), TL_ERR_ARG;
     if (phases & (TL_PHASE_DECAY | TL_PHASE_REWARD)) {
         if (!rew) return set_error("reward params are NULL"), TL_ERR_ARG;
     }
@@ -724,7 +725,7 @@ int prepare(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* 
     auto dispatch = [&]() -> int {
         if (kp.mode == 0) {
             const int win = do_obs ? kp.obs.window : 0;
-            const bool world = phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY);
+            const bool world = phases & (TL_PHASE_ACTIONS | TL_PHASE_SOCIAL_DECAY | TL_PHASE_RESERVATIONS);
             auto pick = [&](auto variant, auto window) -> int {
                 if (world) return pick_kernel(tick_kernel_roles<decltype(variant)::value, decltype(window)::value, true>);
                 return pick_kernel(tick_kernel_roles<decltype(variant)::value, decltype(window)::value, false>);

@@ -151,13 +151,15 @@ class DeviceTownBatch:
         src = batch or self.host
         self.arena.copy_(torch.from_numpy(src.arena[: self.layout.total_bytes]), non_blocking=True)
 
-    def download_state(self) -> TownBatch:
+    def download_state(self, full: bool | None = None) -> TownBatch:
         """Device → host copy of the mutable fields into ``self.host`` (one copy).
 
-        With a ``DynamicsSpec`` the world-dynamics phases may have rewritten positions, entity words and
-        ledger rows as well, so the whole arena comes back.
+        With a ``DynamicsSpec`` (or ``full=True``) the world-dynamics phases may have rewritten positions, entity
+        words and ledger rows as well, so the whole arena comes back.
         """
-        n = self.layout.mutable_bytes if self.dyn is None else self.layout.total_bytes
+        if full is None:
+            full = self.dyn is not None
+        n = self.layout.total_bytes if full else self.layout.mutable_bytes
         self.host.arena[:n] = self.arena[:n].cpu().numpy()
         return self.host
 

@@ -75,6 +75,7 @@ class TownRows:
     tick: int
     ent: np.ndarray
     fields: dict[str, np.ndarray] = field(default_factory=dict)
+    ent_holder: np.ndarray | None = None  # per entity: holder of a reservation slot, -1 free, -2 not a slot
 
 
 def ingest_town(
@@ -91,6 +92,7 @@ def ingest_town(
     max_edges: int = 6,
     observe: bool = True,
     origin: tuple[int, int] | None = None,
+    device_reservations: bool = False,
 ) -> TownRows:
     """Read one reference world into SoA rows.
 
@@ -98,6 +100,12 @@ def ingest_town(
     queues) for callers that only run decay / reward.  ``origin`` pins the
     town origin (e.g. ``(0, 0)`` for a declared grid); by default it is the
     minimum corner of everything that occupies a tile.
+
+    ``device_reservations=True`` lays the reserved tiles out as reservation SLOTS for ``TL_PHASE_RESERVATIONS``
+    (world/systems/queues.py:55-86 on the device): one slot per object that has a position, in object order, holding
+    the tile's current state, plus ``ent_holder`` — the town-local index of the agent the queue manager has granted the
+    object to (``QueueManager.active_agent``), -1 while it is free.  Reserved tiles no object accounts for stay plain
+    reserved words.
     """
     adapter = resolve_adapter(world)
     terminated = terminated or {}
@@ -238,6 +246,7 @@ def ingest_town(
     ctype_of = {name: k + 1 for k, name in enumerate(spec.object_channels)} if spec.variant == "compact" else {}
     obj_rows: list[tuple[int, int, int, int, int, int]] = []  # x, y, ltype, ctype, lm, tile
     reserved: list[tuple[int, int]] = []
+    slots: list[tuple[int, int, int, int]] = []  # x, y, kind, holder (device_reservations)
     if observe:
         tile_of: dict[str, tuple[int, int]] = {}
         for position, ids in adapter.objects_by_position_view().items():  # cache.py:33-38
@@ -262,6 +271,23 @@ def ingest_town(
                     obj_rows.append((tile_pos[0], tile_pos[1], ltype, ctype, 0, 1))
         # a set in the reference (spatial.py:117-120): canonical (y, x) order here
         reserved = sorted({(int(p[0]), int(p[1])) for p in adapter.reservation_tiles()}, key=lambda p: (p[1], p[0]))
+        if device_reservations:
+            queue_manager = getattr(adapter, "queue_manager", None)
+            index_of = {aid: k for k, aid in enumerate(agent_ids)}
+            reserved_now = set(reserved)
+            positions: list[tuple[int, int]] = []
+            for object_id, payload in objects_view.items():  # refresh_reservations walks the objects in this order
+                position = payload.get("position")
+                if not (isinstance(position, tuple) and len(position) == 2):
+                    continue  # sync_reservation skips objects without a position (queues.py:69-71, 82-83)
+                active = queue_manager.active_agent(object_id) if queue_manager is not None else None
+                holder = -1 if active is None else index_of.get(str(active), n)  # a holder outside the town: held, nobody flagged
+                positions.append((int(position[0]), int(position[1])))
+                slots.append((int(position[0]), int(position[1]), capi.TL_KIND_EMPTY, holder))
+            for k, pos_k in enumerate(positions):  # the tile's current state sits on the last slot of the tile
+                if pos_k in reserved_now and pos_k not in positions[k + 1 :]:
+                    slots[k] = (pos_k[0], pos_k[1], capi.TL_KIND_RESERVED, slots[k][3])
+            reserved = [p for p in reserved if p not in set(positions)]
 
     xs = [occ[:, 0]] if n else []
     ys = [occ[:, 1]] if n else []
@@ -273,6 +299,10 @@ def ingest_town(
         rarr = np.array(reserved, dtype=np.int64)
         xs.append(rarr[:, 0])
         ys.append(rarr[:, 1])
+    if slots:
+        sarr = np.array(slots, dtype=np.int64)
+        xs.append(sarr[:, 0])
+        ys.append(sarr[:, 1])
     if xs:
         allx = np.concatenate(xs)
         ally = np.concatenate(ys)
@@ -290,9 +320,15 @@ def ingest_town(
         ent_parts.append(
             pack_entity(arr[:, 0] - ox, arr[:, 1] - oy, capi.TL_KIND_OBJECT, arr[:, 2], arr[:, 3], arr[:, 4], arr[:, 5])
         )
+    holder_parts = [np.full(part.size, -2, dtype=np.int32) for part in ent_parts]
+    if slots:
+        ent_parts.append(pack_entity(sarr[:, 0] - ox, sarr[:, 1] - oy, sarr[:, 2]))
+        holder_parts.append(sarr[:, 3].astype(np.int32))
     if reserved:
         ent_parts.append(pack_entity(rarr[:, 0] - ox, rarr[:, 1] - oy, capi.TL_KIND_RESERVED))
+        holder_parts.append(np.full(len(reserved), -2, dtype=np.int32))
     ent = np.concatenate(ent_parts) if ent_parts else np.zeros(0, dtype=np.uint32)
+    ent_holder = np.concatenate(holder_parts) if holder_parts else np.zeros(0, dtype=np.int32)
     f["pos"] = pack_pos(centre[:, 0] - ox, centre[:, 1] - oy) if n else np.zeros(0, dtype=np.int32)
     return TownRows(
         agent_ids=agent_ids,
@@ -301,6 +337,7 @@ def ingest_town(
         tick=int(adapter.tick),
         ent=ent,
         fields=f,
+        ent_holder=ent_holder,
     )
 
 
@@ -332,6 +369,7 @@ def rows_to_batch(towns: list[TownRows], spec: ObsSpec, max_edges: int = 6, grid
             else:
                 dst[a : a + n] = values
         b.ent[e : e + t.ent.size] = t.ent
+        b.ent_holder[e : e + t.ent.size] = t.ent_holder if t.ent_holder is not None else -2
         a += n
         e += int(t.ent.size)
         b.town_agent_off[ti + 1] = a

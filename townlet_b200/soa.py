@@ -58,6 +58,8 @@ _FIELDS: tuple[tuple[str, str, Callable[[int, int, int, int, int], tuple[int, ..
     ("riv_count", "u1", lambda T, N, E, K, EW: (N,), False),
     ("riv_embed", "u8", lambda T, N, E, K, EW: (N, K, EW), False),
     ("riv_score", "f8", lambda T, N, E, K, EW: (N, K), False),
+    # reservation slots (TL_PHASE_RESERVATIONS): holder of the slot's object, -1 free, -2 not a slot
+    ("ent_holder", "i4", lambda T, N, E, K, EW: (E,), False),
 )
 
 FIELD_NAMES = tuple(f[0] for f in _FIELDS)
@@ -168,6 +170,7 @@ class TownBatch:
             self._views[name] = arena[off : off + nbytes].view(dtype).reshape(shape)
         if fresh:
             self._views["term_block_tick"][...] = capi.TL_TERM_BLOCK_NONE
+            self._views["ent_holder"][...] = -2
         self.has_social_in = True
         self.has_personality = True
 
@@ -291,7 +294,7 @@ class TownBatch:
                 dst[...] = self.town_ent_off[t0 : t1 + 1] - e0
             elif name == "town_tick":
                 dst[...] = src[t0:t1]
-            elif name == "ent":
+            elif name in ("ent", "ent_holder"):
                 dst[...] = src[e0:e1]
             elif src.ndim >= 1 and src.shape[0] == 3 and name in ("needs", "social_in", "personality"):
                 dst[...] = src[:, a0:a1]

@@ -162,12 +162,16 @@ def _flags(town: TownDescription, holders: set[str]) -> np.ndarray:
     return flags
 
 
-def assemble(towns: list[TownDescription], spec: ObsSpec | None = None, max_edges: int = 6) -> TownBatch:
-    """Pack town descriptions into one ``TownBatch`` (what the ingest produces from reference worlds)."""
+def assemble(towns: list[TownDescription], spec: ObsSpec | None = None, max_edges: int = 6,
+             device_reservations: bool = False) -> TownBatch:
+    """Pack town descriptions into one ``TownBatch`` (what the ingest produces from reference worlds).
+
+    ``device_reservations``: one reservation slot per object with its holder in ``ent_holder`` (the layout of
+    ``ingest_town(..., device_reservations=True)``, for ``TL_PHASE_RESERVATIONS``) instead of plain reserved tiles."""
     spec = spec or ObsSpec()
     ew = spec.embed_words
     n_agents = sum(len(t.agent_ids) for t in towns)
-    n_ent = sum(len(t.agent_ids) + len(t.object_ids) + len(t.reservations) for t in towns)
+    n_ent = sum(len(t.agent_ids) + len(t.object_ids) + (len(t.object_ids) if device_reservations else len(t.reservations)) for t in towns)
     grid = max(t.grid for t in towns)
     layout = BatchLayout.make(len(towns), n_agents, n_ent, max_edges, ew)
     b = TownBatch(layout, grid, grid)
@@ -221,7 +225,14 @@ def assemble(towns: list[TownDescription], spec: ObsSpec | None = None, max_edge
                 t.object_positions[:, 0], t.object_positions[:, 1], capi.TL_KIND_OBJECT, ltype, ctype, 1, 1
             )
             e += no
-        if t.reservations:
+        if device_reservations and no:
+            held = np.array([oid in t.reservations for oid in t.object_ids])
+            agent_index = {aid: i for i, aid in enumerate(t.agent_ids)}
+            b.ent[e : e + no] = pack_entity(t.object_positions[:, 0], t.object_positions[:, 1],
+                                            np.where(held, capi.TL_KIND_RESERVED, capi.TL_KIND_EMPTY))
+            b.ent_holder[e : e + no] = [agent_index[t.reservations[oid]] if oid in t.reservations else -1 for oid in t.object_ids]
+            e += no
+        elif t.reservations:
             obj_index = {oid: i for i, oid in enumerate(t.object_ids)}
             idx = np.array([obj_index[oid] for oid in t.reservations])
             idx = idx[np.lexsort((t.object_positions[idx, 0], t.object_positions[idx, 1]))]  # (y, x) order
@@ -244,10 +255,11 @@ def synth_batch(
     seed: int = 1234,
     first_town: int = 0,
     terminated_frac: float = 0.02,
+    device_reservations: bool = False,
 ) -> TownBatch:
     """Synthetic batch of ``n_towns`` towns (town indices ``first_town`` ...)."""
     towns = [synth_town(first_town + t, grid, n_agents, seed, terminated_frac) for t in range(n_towns)]
-    return assemble(towns, spec)
+    return assemble(towns, spec, device_reservations=device_reservations)
 
 
 def tile_batch(base: TownBatch, repeats: int) -> TownBatch:
