@@ -25,6 +25,11 @@ def pytest_collection_modifyitems(config: pytest.Config, items: list[pytest.Item
     except Exception:
         has_gpu = False
     if has_gpu:
+        # a kernel that never returns must end the run, not hang it: the watchdog thread exits the process (a signal
+        # would wait for the blocked CUDA call to come back)
+        for item in items:
+            if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(600, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

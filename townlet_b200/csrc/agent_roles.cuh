@@ -101,7 +101,10 @@ __device__ __forceinline__ void refresh_reservations_town(const KParams& p, int 
             const bool nslot = nin && __ldg(p.b.ent_holder + ne) >= -1;
             const uint32_t ntile = nslot ? (nw & 0xfffffu) : 0xffffffffu;
 #pragma unroll 1
-            for (int i = 0; i < 32; ++i) later = later || (slot && __shfl_sync(FULL, ntile, i) == tile);
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t other = __shfl_sync(FULL, ntile, i);  // every lane takes part, whatever its own state
+                later = later || (slot && other == tile);
+            }
         }
         if (slot) {
             const uint32_t kind = (holder >= 0 && !later) ? TL_KIND_RESERVED : TL_KIND_EMPTY;
