@@ -430,7 +430,7 @@ typedef void* tl_stream_t; /* cudaStream_t */
 const char* tl_last_error(void);
 int tl_abi_version(void);
 /* sizeof of the idx-th ABI struct (0 TlTownBatch, 1 TlObsParams, 2 TlRewardParams,
- * 3 TlObsOut, 4 TlRewardOut, 5 TlDynamicsParams, 6 TlHostStep) so bindings can verify their layout; -1 otherwise */
+ * 3 TlObsOut, 4 TlRewardOut, 5 TlDynamicsParams, 6 TlHostStep, 7 TlPolicyWeights) so bindings can verify their layout; -1 otherwise */
 int tl_abi_struct_size(int idx);
 /* number of SMs of the current device, or a negative error */
 int tl_device_sm_count(void);
@@ -530,6 +530,35 @@ int tl_cast_pad_bf16_strided(const float* src, void* dst, int64_t n_rows, int32_
 int tl_sample_actions(const void* heads, int32_t heads_dtype, int64_t n_rows, int32_t row, int32_t n_actions, uint64_t seed,
                       const int64_t* counter, int64_t offset, int64_t* actions, float* log_probs, float* values,
                       tl_stream_t stream);
+
+/*
+ * The whole batched policy step in ONE kernel on the tensor cores (ABI v4).  The reference evaluates
+ * ConflictAwarePolicyNetwork (policy/models.py:36-69) per agent at batch size 1 and samples with torch
+ * (policy/runner.py:444-488).  tl_policy_step takes the padded bfloat16 input rows the tick kernel writes
+ * (TlObsOut.map_bf16 / features_bf16 side by side: 512 map columns, then 128 feature columns, rows `input_row` elements
+ * apart) and per 128-agent tile chains map / feature encoders -> shared layer -> policy + value heads with tcgen05.mma
+ * (operands staged by TMA, accumulators in tensor memory, hidden activations kept in shared memory), then takes the
+ * float32 log_softmax and samples exactly as tl_sample_actions does.  Weights are bfloat16 in torch.nn.Linear layout
+ * [out][in], the input dimension zero-padded (484 -> 512, 81 -> 128), heads = policy rows then the value row, zero rows up
+ * to 16; biases float32.  heads_out (optional, [n_rows][16] float32) receives the logits / value row for tests.
+ * Returns TL_ERR_UNSUPPORTED for other layer sizes (callers fall back to their own network code).
+ */
+typedef struct TlPolicyWeights {
+    const uint16_t* w_map;    /* [256][512] */
+    const uint16_t* w_feat;   /* [256][128] */
+    const uint16_t* w_shared; /* [256][512]: columns 0-255 read the map encoder's output, 256-511 the feature encoder's */
+    const uint16_t* w_heads;  /* [16][256] */
+    const float* b_enc;       /* [512] map encoder bias, then feature encoder bias */
+    const float* b_shared;    /* [256] */
+    const float* b_heads;     /* [16] */
+    int32_t hidden;           /* 256 */
+    int32_t map_in;           /* 512 */
+    int32_t feat_in;          /* 128 */
+    int32_t n_actions;        /* policy logits; the value is row n_actions of w_heads */
+} TlPolicyWeights;
+int tl_policy_step(const void* inputs, int64_t n_rows, int64_t input_row, const TlPolicyWeights* weights, uint64_t seed,
+                   const int64_t* counter, int64_t offset, int64_t* actions, float* log_probs, float* values, float* heads_out,
+                   tl_stream_t stream);
 
 /*
  * Host-buffer entries: every pointer (batch, LUTs, outputs) is HOST memory — what a binding under

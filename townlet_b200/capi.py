@@ -274,6 +274,22 @@ class TlHostStep(C.Structure):
     ]
 
 
+class TlPolicyWeights(C.Structure):
+    _fields_ = [
+        ("w_map", _p),
+        ("w_feat", _p),
+        ("w_shared", _p),
+        ("w_heads", _p),
+        ("b_enc", _p),
+        ("b_shared", _p),
+        ("b_heads", _p),
+        ("hidden", C.c_int32),
+        ("map_in", C.c_int32),
+        ("feat_in", C.c_int32),
+        ("n_actions", C.c_int32),
+    ]
+
+
 TL_HOST_SLOTS = 4
 TL_WIRE = {"f32": 0, "u8": 1, "bits": 2}
 TL_MAP_F32, TL_MAP_WIRE = 0, 1
@@ -303,6 +319,7 @@ EXPORTED_SYMBOLS = (
     "tl_cast_pad_bf16",
     "tl_cast_pad_bf16_strided",
     "tl_sample_actions",
+    "tl_policy_step",
     "tl_context_create",
     "tl_context_destroy",
     "tl_context_set_threads",
@@ -445,6 +462,8 @@ def load_library() -> C.CDLL:
     lib.tl_cast_pad_bf16_strided.argtypes = [_p, _p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, _p]
     lib.tl_sample_actions.restype = C.c_int
     lib.tl_sample_actions.argtypes = [_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _p, C.c_int64, _p, _p, _p, _p]
+    lib.tl_policy_step.restype = C.c_int
+    lib.tl_policy_step.argtypes = [_p, C.c_int64, C.c_int64, C.POINTER(TlPolicyWeights), C.c_uint64, _p, C.c_int64, _p, _p, _p, _p, _p]
     lib.tl_context_create.restype = _p
     lib.tl_context_create.argtypes = [C.c_int]
     lib.tl_context_destroy.restype = None
@@ -486,7 +505,7 @@ def load_library() -> C.CDLL:
     lib.tl_context_last_d2h_bytes.argtypes = [_p]
     if lib.tl_abi_version() != TL_ABI_VERSION:
         raise TownletB200Error("libtownlet_b200.so ABI version mismatch")
-    for idx, struct in enumerate((TlTownBatch, TlObsParams, TlRewardParams, TlObsOut, TlRewardOut, TlDynamicsParams, TlHostStep)):
+    for idx, struct in enumerate((TlTownBatch, TlObsParams, TlRewardParams, TlObsOut, TlRewardOut, TlDynamicsParams, TlHostStep, TlPolicyWeights)):
         if lib.tl_abi_struct_size(idx) != C.sizeof(struct):
             raise TownletB200Error(
                 f"struct layout mismatch for {struct.__name__}: C {lib.tl_abi_struct_size(idx)} vs ctypes {C.sizeof(struct)}"

@@ -1,0 +1,391 @@
+// policy_mlp.cuh — the batched policy step of the rollout as ONE sm_100a kernel
+// (included at the end of townlet_b200.cu; uses cuda_ok, set_error, g_launches, philox4x32_10).
+//
+// The reference runs ConflictAwarePolicyNetwork (src/townlet/policy/models.py:36-69) per agent at batch size 1
+// (policy/runner.py:444-488): map encoder Linear(C*W*W, 256) + ReLU, feature encoder Linear(F, 256) + ReLU, shared
+// Linear(512, 256) + ReLU, policy head Linear(256, A) and value head Linear(256, 1), then log_softmax and a categorical
+// sample.  Here one CTA owns a tile of 128 agents and chains the four products on the 5th-generation tensor cores:
+//
+//   X[128 x 640] bf16 (the padded rows the tick kernel writes: 512 map columns | 128 feature columns)
+//     --TMA-->  shared memory (128-byte swizzle)  --tcgen05.mma-->  TMEM  D1[128 x 512] fp32   (two encoders)
+//     --tcgen05.ld, + bias, ReLU, bf16-->  shared memory H1[128 x 512] (written in the operand's swizzled layout)
+//     --tcgen05.mma (weights by TMA)-->  TMEM  D2[128 x 256]  --+ bias, ReLU, bf16-->  H2[128 x 256]
+//     --tcgen05.mma-->  TMEM  D3[128 x 16]  --+ bias-->  log_softmax, Gumbel-max sample (Philox), action / log-prob / value
+//
+// The activations never leave the SM (the three-GEMM library path moves ~130 MB of them through HBM per tick at 65 536
+// agents) and the two encoders are two accumulations instead of one block-diagonal product with half its FLOPs wasted.
+// Warp roles: warp 0 issues the TMA loads, warp 1 the MMAs (one elected lane), warps 2-5 are the epilogue (TMEM lane
+// quarter = warp index mod 4).  Arithmetic: bfloat16 operands, float32 accumulation, bias / ReLU in float32, hidden
+// activations rounded to bfloat16 — the arithmetic of the bfloat16 autocast path it replaces.
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int kPolRows = 128;        // agents per CTA (UMMA M)
+constexpr int kPolHidden = 256;      // hidden width (UMMA N of the encoder / shared products)
+constexpr int kPolMapK = 512;        // padded map columns
+constexpr int kPolFeatK = 128;       // padded feature columns
+constexpr int kPolHeads = 16;        // policy logits + value, padded (UMMA N of the heads product)
+constexpr int kPolKChunk = 64;       // K elements per pipeline step: one 128-byte swizzle row of bf16
+constexpr int kPolStages = 3;
+constexpr int kPolABytes = kPolRows * kPolKChunk * 2;      // 16 KB: an activation chunk [128 x 64]
+constexpr int kPolBBytes = kPolHidden * kPolKChunk * 2;    // 32 KB: a weight chunk [256 x 64]
+constexpr int kPolHBytes = kPolRows * 512 * 2;             // 128 KB: H1 [128 x 512] as 8 chunks (H2 reuses the first 4)
+constexpr int kPolSmemB = 0;
+constexpr int kPolSmemH = kPolStages * kPolBBytes;         // the A stages alias the start of H (X is dead before H1 is written)
+constexpr int kPolSmemBar = kPolSmemH + kPolHBytes;
+constexpr int kPolSmemBytes = kPolSmemBar + 256 + 1024;    // + barriers + slack for the 1024-byte alignment
+constexpr int kPolThreads = 192;
+// pipeline steps: 8 map chunks, 2 feature chunks, 8 shared-layer chunks, 4 heads chunks
+constexpr int kStepsMap = kPolMapK / kPolKChunk, kStepsFeat = kPolFeatK / kPolKChunk;
+constexpr int kStepsShared = 512 / kPolKChunk, kStepsHeads = kPolHidden / kPolKChunk;
+constexpr int kStepEnc = kStepsMap + kStepsFeat, kStepSh = kStepEnc + kStepsShared, kStepAll = kStepSh + kStepsHeads;
+
+struct PolicyParams {
+    const float* b_enc;     // [512]
+    const float* b_shared;  // [256]
+    const float* b_heads;   // [16]
+    long long n_rows;
+    int n_actions;
+    unsigned long long seed;
+    const long long* counter;
+    long long offset;
+    long long* actions;
+    float* log_probs;
+    float* values;
+    float* heads_out;  // optional [n_rows][16] float32 (tests)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// K-major operand tile in shared memory written with the 128-byte swizzle (rows of 64 bf16 = 128 bytes, groups of 8
+// rows 1024 bytes apart): UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, 16-byte units
+    d |= (uint64_t)0 << 16;                        // leading byte offset: unused for a swizzled K-major tile one atom wide
+    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset: 8 rows x 128 bytes
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major (InstrDescriptor in the same header)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on the barrier when every MMA issued so far is done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, "
+        "%28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 32 accumulator columns of one row -> + bias, ReLU, bf16 -> four 16-byte units of the row in the swizzled K-major
+// operand layout (unit c of row r sits at unit position c ^ (r & 7) of the row's 128 bytes)
+__device__ __forceinline__ void hidden_store32(unsigned char* h, int row, int n0, const uint32_t (&acc)[32], const float* __restrict__ bias) {
+    unsigned char* chunk = h + (n0 >> 6) * kPolABytes + row * 128;
+    const int unit0 = (n0 & 63) >> 3;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = 8 * u + 2 * k;
+            const float a = fmaxf(__uint_as_float(acc[j]) + __ldg(bias + n0 + j), 0.0f);
+            const float b = fmaxf(__uint_as_float(acc[j + 1]) + __ldg(bias + n0 + j + 1), 0.0f);
+            const __nv_bfloat162 pair = __floats2bfloat162_rn(a, b);
+            w[k] = *reinterpret_cast<const uint32_t*>(&pair);
+        }
+        *reinterpret_cast<uint4*>(chunk + (((unit0 + u) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+__global__ void __launch_bounds__(kPolThreads, 1)
+policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wm, const __grid_constant__ CUtensorMap map_wf,
+                  const __grid_constant__ CUtensorMap map_ws, const __grid_constant__ CUtensorMap map_wh, const PolicyParams p) {
+    extern __shared__ unsigned char pol_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pol_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* s_b = smem + kPolSmemB;
+    unsigned char* s_h = smem + kPolSmemH;  // also the A stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPolSmemBar);
+    uint64_t* full = bars;                  // [stages] TMA landed
+    uint64_t* empty = bars + kPolStages;    // [stages] MMAs that read the stage are done
+    uint64_t* mma_done = bars + 2 * kPolStages;      // accumulator of a layer is complete (used three times)
+    uint64_t* h_ready = bars + 2 * kPolStages + 1;   // the epilogue has written the next A operand (used twice)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPolStages + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kPolRows;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kPolStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
+        mbar_init(mma_done, 1);
+        mbar_init(h_ready, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wm) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ws) : "memory");
+    }
+    if (warp == 1) {  // the whole tensor memory: D1 needs all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (one lane) =================
+        if (lane == 0) {
+            for (int step = 0; step < kStepAll; ++step) {
+                const int s = step % kPolStages;
+                if (step >= kPolStages) mbar_wait(empty + s, ((step / kPolStages) - 1) & 1);
+                unsigned char* b_dst = s_b + s * kPolBBytes;
+                unsigned char* a_dst = s_h + s * kPolABytes;
+                if (step < kStepsMap) {
+                    mbar_expect_tx(full + s, kPolABytes + kPolBBytes);
+                    tma_load_2d(a_dst, &map_x, full + s, step * kPolKChunk, row0);
+                    tma_load_2d(b_dst, &map_wm, full + s, step * kPolKChunk, 0);
+                } else if (step < kStepEnc) {
+                    const int j = step - kStepsMap;
+                    mbar_expect_tx(full + s, kPolABytes + kPolBBytes);
+                    tma_load_2d(a_dst, &map_x, full + s, kPolMapK + j * kPolKChunk, row0);
+                    tma_load_2d(b_dst, &map_wf, full + s, j * kPolKChunk, 0);
+                } else if (step < kStepSh) {
+                    mbar_expect_tx(full + s, kPolBBytes);
+                    tma_load_2d(b_dst, &map_ws, full + s, (step - kStepEnc) * kPolKChunk, 0);
+                } else {
+                    mbar_expect_tx(full + s, kPolHeads * kPolKChunk * 2);
+                    tma_load_2d(b_dst, &map_wh, full + s, (step - kStepSh) * kPolKChunk, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one lane) =================
+        if (lane == 0) {
+            const uint32_t idesc_n256 = umma_idesc_bf16(kPolRows, kPolHidden), idesc_n16 = umma_idesc_bf16(kPolRows, kPolHeads);
+            for (int step = 0; step < kStepAll; ++step) {
+                const int s = step % kPolStages;
+                if (step == kStepEnc || step == kStepSh) {  // the A operand of this layer comes from the epilogue
+                    mbar_wait(h_ready, step == kStepEnc ? 0 : 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(full + s, (step / kPolStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t a_addr, d_col, idesc = idesc_n256;
+                bool first;
+                if (step < kStepsMap) a_addr = smem_u32(s_h + s * kPolABytes), d_col = 0, first = step == 0;
+                else if (step < kStepEnc) a_addr = smem_u32(s_h + s * kPolABytes), d_col = kPolHidden, first = step == kStepsMap;
+                else if (step < kStepSh) a_addr = smem_u32(s_h + (step - kStepEnc) * kPolABytes), d_col = 0, first = step == kStepEnc;
+                else a_addr = smem_u32(s_h + (step - kStepSh) * kPolABytes), d_col = kPolHidden, first = step == kStepSh, idesc = idesc_n16;
+                const uint32_t b_addr = smem_u32(s_b + s * kPolBBytes);
+#pragma unroll
+                for (int k = 0; k < kPolKChunk / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes along the swizzled row
+                    umma_bf16(tmem + d_col, umma_desc_k128(a_addr + 32 * k), umma_desc_k128(b_addr + 32 * k), idesc, !(first && k == 0));
+                umma_commit(empty + s);
+                if (step == kStepEnc - 1 || step == kStepSh - 1 || step == kStepAll - 1) umma_commit(mma_done);
+            }
+        }
+    } else {
+        // ================= epilogue: warps 2-5, one thread per row =================
+        const int quarter = warp & 3;  // the TMEM lanes this warp may read
+        const int row = 32 * quarter + lane;
+        const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16);
+        uint32_t acc[32];
+        // layer 1: D1[:, 0:512] -> H1
+        mbar_wait(mma_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int n0 = 0; n0 < 512; n0 += 32) {
+            tmem_ld32(trow + n0, acc);
+            hidden_store32(s_h, row, n0, acc, p.b_enc);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(h_ready);
+        // layer 2: D2[:, 0:256] -> H2 (the first four chunks of the same buffer; GEMM2 has finished reading H1)
+        mbar_wait(mma_done, 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int n0 = 0; n0 < kPolHidden; n0 += 32) {
+            tmem_ld32(trow + n0, acc);
+            hidden_store32(s_h, row, n0, acc, p.b_shared);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(h_ready);
+        // layer 3: D3[:, 256:272] -> logits and value of this row, then the sampling step of sample_actions_kernel
+        mbar_wait(mma_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t hv[16];
+        tmem_ld16(trow + kPolHidden, hv);
+        const long long r = (long long)row0 + row;
+        if (r < p.n_rows) {
+            float x[TL_MAX_ACTIONS];
+            float top = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < kPolHeads; ++j) {
+                const float v = __uint_as_float(hv[j]) + __ldg(p.b_heads + j);
+                if (p.heads_out) p.heads_out[r * kPolHeads + j] = v;
+                x[j] = j < p.n_actions ? v : -INFINITY;
+                top = fmaxf(top, x[j]);
+                if (j == p.n_actions && p.values) p.values[r] = v;
+            }
+            float sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kPolHeads; ++j) sum += j < p.n_actions ? expf(x[j] - top) : 0.0f;
+            const float lse = top + logf(sum);
+            const unsigned long long base = 4ull * (unsigned long long)((p.counter ? *p.counter : 0ll) + p.offset);
+            int best = 0;
+            float best_score = -INFINITY, best_logp = 0.0f;
+#pragma unroll
+            for (int d = 0; d < kPolHeads / 4; ++d) {
+                if (4 * d >= p.n_actions) break;
+                const unsigned long long c = base + d;
+                const uint4 bits = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)r, (uint32_t)((unsigned long long)r >> 32),
+                                                 (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+                const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const int j = 4 * d + l;
+                    if (j >= p.n_actions) break;
+                    const float u = ((float)(w[l] >> 9) + 0.5f) * 1.1920928955078125e-07f;
+                    const float logp = x[j] - lse;
+                    const float score = logp - logf(-logf(u));
+                    if (score > best_score) best_score = score, best = j, best_logp = logp;
+                }
+            }
+            p.actions[r] = best;
+            p.log_probs[r] = best_logp;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }();
+    return fn;
+}
+
+// bf16 row-major matrix [rows][cols] (row pitch in elements) as a 2-D tensor map with boxes of 64 columns x box_rows rows
+bool make_bf16_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
+    auto encode = tensor_map_encoder();
+    if (!encode) return set_error("cuTensorMapEncodeTiled is not available"), false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {pitch * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kPolKChunk, box_rows};
+    const cuuint32_t elem[2] = {1, 1};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed"), false;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tl_policy_step(const void* inputs, int64_t n_rows, int64_t input_row, const TlPolicyWeights* w, uint64_t seed, const int64_t* counter,
+                   int64_t offset, int64_t* actions, float* log_probs, float* values, float* heads_out, tl_stream_t stream) {
+    if (!inputs || !w || !actions || !log_probs) return set_error("tl_policy_step: NULL pointer"), TL_ERR_ARG;
+    if (!w->w_map || !w->w_feat || !w->w_shared || !w->w_heads || !w->b_enc || !w->b_shared || !w->b_heads)
+        return set_error("tl_policy_step: NULL weight pointer"), TL_ERR_ARG;
+    if (w->hidden != kPolHidden || w->map_in != kPolMapK || w->feat_in != kPolFeatK)
+        return set_error("tl_policy_step: built for hidden 256, 512 map columns, 128 feature columns"), TL_ERR_UNSUPPORTED;
+    if (w->n_actions < 1 || w->n_actions + (values ? 1 : 0) > kPolHeads) return set_error("tl_policy_step: 1 <= n_actions <= 15"), TL_ERR_ARG;
+    if (input_row < kPolMapK + kPolFeatK || (input_row & 7) || ((uintptr_t)inputs & 15))
+        return set_error("tl_policy_step: input rows are >= 640 bf16, a multiple of 8, 16-byte aligned"), TL_ERR_ARG;
+    if (n_rows < 0 || offset < 0) return set_error("tl_policy_step: negative size"), TL_ERR_ARG;
+    if (n_rows == 0) return TL_OK;
+    CUtensorMap mx, mwm, mwf, mws, mwh;
+    if (!make_bf16_map(&mx, inputs, (uint64_t)n_rows, kPolMapK + kPolFeatK, (uint64_t)input_row, kPolRows) ||
+        !make_bf16_map(&mwm, w->w_map, kPolHidden, kPolMapK, kPolMapK, kPolHidden) ||
+        !make_bf16_map(&mwf, w->w_feat, kPolHidden, kPolFeatK, kPolFeatK, kPolHidden) ||
+        !make_bf16_map(&mws, w->w_shared, kPolHidden, 512, 512, kPolHidden) ||
+        !make_bf16_map(&mwh, w->w_heads, kPolHeads, kPolHidden, kPolHidden, kPolHeads))
+        return TL_ERR_CUDA;
+    static std::once_flag once;
+    static cudaError_t attr_rc = cudaSuccess;
+    std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPolSmemBytes); });
+    if (!cuda_ok(attr_rc, "cudaFuncSetAttribute(policy_mlp_kernel)")) return TL_ERR_CUDA;
+    PolicyParams p;
+    p.b_enc = w->b_enc, p.b_shared = w->b_shared, p.b_heads = w->b_heads;
+    p.n_rows = n_rows, p.n_actions = w->n_actions, p.seed = seed, p.counter = (const long long*)counter, p.offset = offset;
+    p.actions = (long long*)actions, p.log_probs = log_probs, p.values = values, p.heads_out = heads_out;
+    const unsigned grid = (unsigned)((n_rows + kPolRows - 1) / kPolRows);
+    policy_mlp_kernel<<<grid, kPolThreads, kPolSmemBytes, (cudaStream_t)stream>>>(mx, mwm, mwf, mws, mwh, p);
+    if (!cuda_ok(cudaGetLastError(), "policy_mlp launch")) return TL_ERR_CUDA;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return TL_OK;
+}
+
+}  // extern "C"

@@ -829,6 +829,7 @@ int tl_abi_struct_size(int idx) {
         case 4: return (int)sizeof(TlRewardOut);
         case 5: return (int)sizeof(TlDynamicsParams);
         case 6: return (int)sizeof(TlHostStep);
+        case 7: return (int)sizeof(TlPolicyWeights);
         default: return -1;
     }
 }
@@ -1024,3 +1025,4 @@ int tl_plan_grid(const TlPlan* plan, int32_t* grid, int32_t* threads, int32_t* s
 }  // extern "C"
 
 #include "host_path.cuh"
+#include "policy_mlp.cuh"

@@ -135,6 +135,67 @@ class PolicyMLP(nn.Module):
         return out[:, :actions], out[:, actions]
 
 
+class FusedPolicyWeights:
+    """The weights of a ``PolicyMLP`` in the layout ``tl_policy_step`` reads: bfloat16 ``[out, in]`` matrices with the input
+    dimension zero-padded (map 484 -> 512, features 81 -> 128), the policy and value heads stacked and padded to 16 rows,
+    float32 biases.  Raises ``TownletB200Error`` when the network is not the 256-wide reference shape."""
+
+    def __init__(self, policy: "PolicyMLP", device: torch.device) -> None:
+        hidden = policy.map_encoder[1].out_features
+        flat, feat = policy.map_encoder[1].in_features, policy.feature_encoder[0].in_features
+        actions = policy.policy_head.out_features
+        pm, pf = policy._pad_widths()
+        if hidden != 256 or pm != 512 or pf != 128 or actions + 1 > 16 or policy.shared[0].in_features != 512:
+            raise capi.TownletB200Error("tl_policy_step is built for the reference shape: hidden 256, <= 512 map inputs, <= 128 features")
+        bf16 = torch.bfloat16
+
+        def padded(weight: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+            w = torch.zeros((rows, cols), dtype=bf16, device=device)
+            w[: weight.shape[0], : weight.shape[1]] = weight.detach().to(device=device, dtype=bf16)
+            return w.contiguous()
+
+        self.n_actions = actions
+        self.w_map = padded(policy.map_encoder[1].weight, hidden, pm)
+        self.w_feat = padded(policy.feature_encoder[0].weight, hidden, pf)
+        self.w_shared = padded(policy.shared[0].weight, hidden, 2 * hidden)
+        self.w_heads = padded(torch.cat([policy.policy_head.weight.detach(), policy.value_head.weight.detach()], dim=0), 16, hidden)
+        # the biases are rounded to bfloat16 first, as the autocast path holds them, then kept in float32
+        rounded = lambda b: b.detach().to(device=device, dtype=bf16).float()
+        self.b_enc = torch.cat([rounded(policy.map_encoder[1].bias), rounded(policy.feature_encoder[0].bias)]).contiguous()
+        self.b_shared = rounded(policy.shared[0].bias).contiguous()
+        self.b_heads = torch.zeros(16, dtype=torch.float32, device=device)
+        self.b_heads[: actions + 1] = torch.cat([rounded(policy.policy_head.bias), rounded(policy.value_head.bias)])
+        self.struct = capi.TlPolicyWeights()
+        for name in ("w_map", "w_feat", "w_shared", "w_heads", "b_enc", "b_shared", "b_heads"):
+            setattr(self.struct, name, getattr(self, name).data_ptr())
+        self.struct.hidden, self.struct.map_in, self.struct.feat_in, self.struct.n_actions = hidden, pm, pf, actions
+        self.versions = tuple(p._version for p in policy.parameters())
+
+
+def policy_step(inputs_bf16: torch.Tensor, weights: FusedPolicyWeights, seed: int, counter: torch.Tensor | None = None, offset: int = 0,
+                out: tuple[torch.Tensor, torch.Tensor, torch.Tensor] | None = None, heads_out: torch.Tensor | None = None):
+    """``tl_policy_step``: encoders -> shared layer -> heads -> log_softmax -> categorical sample for every row of the padded
+    bfloat16 input buffer, in one tcgen05 kernel.  Returns ``(actions int64, log_probs float32, values float32)``."""
+    if not inputs_bf16.is_cuda or inputs_bf16.dtype != torch.bfloat16 or inputs_bf16.dim() != 2 or inputs_bf16.stride(1) != 1:
+        raise capi.TownletB200Error("policy_step needs a CUDA bfloat16 [rows, >= 640] buffer with unit column stride (no CPU fallback)")
+    n = inputs_bf16.shape[0]
+    if out is None:
+        out = (torch.empty(n, dtype=torch.int64, device=inputs_bf16.device), torch.empty(n, dtype=torch.float32, device=inputs_bf16.device),
+               torch.empty(n, dtype=torch.float32, device=inputs_bf16.device))
+    actions, log_probs, values = out
+    if heads_out is not None and (heads_out.dtype != torch.float32 or heads_out.shape != (n, 16) or not heads_out.is_contiguous()):
+        raise ValueError("heads_out must be contiguous float32 [rows, 16]")
+    lib = capi.load_library()
+    with torch.cuda.device(inputs_bf16.device):
+        status = lib.tl_policy_step(
+            inputs_bf16.data_ptr(), n, int(inputs_bf16.stride(0)), C.byref(weights.struct), seed & (2**64 - 1),
+            counter.data_ptr() if counter is not None else None, offset, actions.data_ptr(), log_probs.data_ptr(), values.data_ptr(),
+            heads_out.data_ptr() if heads_out is not None else None, _stream_ptr(inputs_bf16.device),
+        )
+    capi.check(status)
+    return actions, log_probs, values
+
+
 def gae(rewards: torch.Tensor, values: torch.Tensor, dones: torch.Tensor, gamma: float, gae_lambda: float):
     """``compute_gae`` on time-major CUDA tensors ``[T, N]`` (``values`` ``[T, N]`` or ``[T + 1, N]``)."""
     if rewards.ndim != 2 or dones.ndim != 2:
