@@ -372,6 +372,7 @@ def test_rollout_with_the_kernel_written_bf16_map_equals_the_cast_pass(act_on_wo
     for fuse in (False, True):
         dev = DeviceTownBatch(synth_batch(20, 24, 8, obs), obs, rew, dyn=DynamicsSpec() if act_on_world else None)
         cap = RolloutCapture(dev, policy, act_on_world=act_on_world)
+        cap.fuse_policy = False  # both arms on the library products: what differs is who writes the bfloat16 rows
         cap.fuse_map_cast = fuse
         cap.seed = 23  # Philox key of the sampling kernel (otherwise torch.initial_seed() at construction)
         torch.manual_seed(23)

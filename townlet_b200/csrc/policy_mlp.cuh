@@ -14,9 +14,11 @@
 //
 // The activations never leave the SM (the three-GEMM library path moves ~130 MB of them through HBM per tick at 65 536
 // agents) and the two encoders are two accumulations instead of one block-diagonal product with half its FLOPs wasted.
-// Warp roles: warp 0 issues the TMA loads, warp 1 the MMAs (one elected lane), warps 2-5 are the epilogue (TMEM lane
-// quarter = warp index mod 4).  Arithmetic: bfloat16 operands, float32 accumulation, bias / ReLU in float32, hidden
-// activations rounded to bfloat16 — the arithmetic of the bfloat16 autocast path it replaces.
+// Warp roles: warp 0 issues the TMA loads, warp 1 the MMAs (one elected lane), warps 2-9 are the epilogue (TMEM lane
+// quarter = warp index mod 4, two warps per quarter splitting a layer's columns).  CTAs are persistent: each walks the
+// tiles blockIdx.x, blockIdx.x + gridDim.x, ... so that tensor-memory allocation, barrier set-up and descriptor fetches
+// are paid once and the weight loads of the next tile run under the sampling epilogue of the previous one.  Arithmetic:
+// bfloat16 operands, float32 accumulation, bias / ReLU in float32, hidden activations rounded to bfloat16 — the arithmetic of the bfloat16 autocast path it replaces.
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -37,7 +39,8 @@ constexpr int kPolSmemB = 0;
 constexpr int kPolSmemH = kPolStages * kPolBBytes;         // the A stages alias the start of H (X is dead before H1 is written)
 constexpr int kPolSmemBar = kPolSmemH + kPolHBytes;
 constexpr int kPolSmemBytes = kPolSmemBar + 256 + 1024;    // + barriers + slack for the 1024-byte alignment
-constexpr int kPolThreads = 192;
+constexpr int kPolEpiWarps = 8;                            // two per TMEM lane quarter, each taking half of a layer's columns
+constexpr int kPolThreads = 64 + 32 * kPolEpiWarps;
 // pipeline steps: 8 map chunks, 2 feature chunks, 8 shared-layer chunks, 4 heads chunks
 constexpr int kStepsMap = kPolMapK / kPolKChunk, kStepsFeat = kPolFeatK / kPolKChunk;
 constexpr int kStepsShared = 512 / kPolKChunk, kStepsHeads = kPolHidden / kPolKChunk;
@@ -170,21 +173,25 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPolSmemBar);
     uint64_t* full = bars;                  // [stages] TMA landed
     uint64_t* empty = bars + kPolStages;    // [stages] MMAs that read the stage are done
-    uint64_t* mma_done = bars + 2 * kPolStages;      // accumulator of a layer is complete (used three times)
-    uint64_t* h_ready = bars + 2 * kPolStages + 1;   // the epilogue has written the next A operand (used twice)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPolStages + 2);
+    uint64_t* mma_done = bars + 2 * kPolStages;      // accumulator of a layer is complete (three times per tile)
+    uint64_t* h_ready = bars + 2 * kPolStages + 1;   // the epilogue has written the next A operand (twice per tile)
+    uint64_t* d3_read = bars + 2 * kPolStages + 2;   // the epilogue has read the heads accumulator (once per tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPolStages + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * kPolRows;
+    const int n_tiles = (int)((p.n_rows + kPolRows - 1) / kPolRows);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kPolStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
         mbar_init(mma_done, 1);
-        mbar_init(h_ready, 128);
+        mbar_init(h_ready, 32 * kPolEpiWarps);
+        mbar_init(d3_read, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wm) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wf) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ws) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
     }
     if (warp == 1) {  // the whole tensor memory: D1 needs all 512 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -198,26 +205,29 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer (one lane) =================
         if (lane == 0) {
-            for (int step = 0; step < kStepAll; ++step) {
-                const int s = step % kPolStages;
-                if (step >= kPolStages) mbar_wait(empty + s, ((step / kPolStages) - 1) & 1);
-                unsigned char* b_dst = s_b + s * kPolBBytes;
-                unsigned char* a_dst = s_h + s * kPolABytes;
-                if (step < kStepsMap) {
-                    mbar_expect_tx(full + s, kPolABytes + kPolBBytes);
-                    tma_load_2d(a_dst, &map_x, full + s, step * kPolKChunk, row0);
-                    tma_load_2d(b_dst, &map_wm, full + s, step * kPolKChunk, 0);
-                } else if (step < kStepEnc) {
-                    const int j = step - kStepsMap;
-                    mbar_expect_tx(full + s, kPolABytes + kPolBBytes);
-                    tma_load_2d(a_dst, &map_x, full + s, kPolMapK + j * kPolKChunk, row0);
-                    tma_load_2d(b_dst, &map_wf, full + s, j * kPolKChunk, 0);
-                } else if (step < kStepSh) {
-                    mbar_expect_tx(full + s, kPolBBytes);
-                    tma_load_2d(b_dst, &map_ws, full + s, (step - kStepEnc) * kPolKChunk, 0);
-                } else {
-                    mbar_expect_tx(full + s, kPolHeads * kPolKChunk * 2);
-                    tma_load_2d(b_dst, &map_wh, full + s, (step - kStepSh) * kPolKChunk, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int row0 = tile * kPolRows;
+                for (int step = 0; step < kStepAll; ++step) {
+                    const int g = it * kStepAll + step, s = g % kPolStages;
+                    if (g >= kPolStages) mbar_wait(empty + s, ((g / kPolStages) - 1) & 1);
+                    unsigned char* b_dst = s_b + s * kPolBBytes;
+                    unsigned char* a_dst = s_h + s * kPolABytes;
+                    if (step < kStepEnc) {
+                        const bool is_map = step < kStepsMap;
+                        const int j = is_map ? step : step - kStepsMap;
+                        mbar_expect_tx(full + s, kPolABytes + kPolBBytes);
+                        tma_load_2d(b_dst, is_map ? &map_wm : &map_wf, full + s, j * kPolKChunk, 0);
+                        // the A stages alias the hidden buffer: the previous tile's heads product must be done reading it
+                        if (step == 0 && it > 0) mbar_wait(mma_done, (3 * (it - 1) + 2) & 1);
+                        tma_load_2d(a_dst, &map_x, full + s, (is_map ? 0 : kPolMapK) + j * kPolKChunk, row0);
+                    } else if (step < kStepSh) {
+                        mbar_expect_tx(full + s, kPolBBytes);
+                        tma_load_2d(b_dst, &map_ws, full + s, (step - kStepEnc) * kPolKChunk, 0);
+                    } else {
+                        mbar_expect_tx(full + s, kPolHeads * kPolKChunk * 2);
+                        tma_load_2d(b_dst, &map_wh, full + s, (step - kStepSh) * kPolKChunk, 0);
+                    }
                 }
             }
         }
@@ -225,99 +235,114 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         // ================= MMA issuer (one lane) =================
         if (lane == 0) {
             const uint32_t idesc_n256 = umma_idesc_bf16(kPolRows, kPolHidden), idesc_n16 = umma_idesc_bf16(kPolRows, kPolHeads);
-            for (int step = 0; step < kStepAll; ++step) {
-                const int s = step % kPolStages;
-                if (step == kStepEnc || step == kStepSh) {  // the A operand of this layer comes from the epilogue
-                    mbar_wait(h_ready, step == kStepEnc ? 0 : 1);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                if (it > 0) {  // the encoders' accumulator covers the columns of the previous tile's heads accumulator
+                    mbar_wait(d3_read, (it - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                mbar_wait(full + s, (step / kPolStages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t a_addr, d_col, idesc = idesc_n256;
-                bool first;
-                if (step < kStepsMap) a_addr = smem_u32(s_h + s * kPolABytes), d_col = 0, first = step == 0;
-                else if (step < kStepEnc) a_addr = smem_u32(s_h + s * kPolABytes), d_col = kPolHidden, first = step == kStepsMap;
-                else if (step < kStepSh) a_addr = smem_u32(s_h + (step - kStepEnc) * kPolABytes), d_col = 0, first = step == kStepEnc;
-                else a_addr = smem_u32(s_h + (step - kStepSh) * kPolABytes), d_col = kPolHidden, first = step == kStepSh, idesc = idesc_n16;
-                const uint32_t b_addr = smem_u32(s_b + s * kPolBBytes);
+                for (int step = 0; step < kStepAll; ++step) {
+                    const int g = it * kStepAll + step, s = g % kPolStages;
+                    if (step == kStepEnc || step == kStepSh) {  // the A operand of this layer comes from the epilogue
+                        mbar_wait(h_ready, (2 * it + (step == kStepEnc ? 0 : 1)) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    mbar_wait(full + s, (g / kPolStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t a_addr, d_col, idesc = idesc_n256;
+                    bool first;
+                    if (step < kStepsMap) a_addr = smem_u32(s_h + s * kPolABytes), d_col = 0, first = step == 0;
+                    else if (step < kStepEnc) a_addr = smem_u32(s_h + s * kPolABytes), d_col = kPolHidden, first = step == kStepsMap;
+                    else if (step < kStepSh) a_addr = smem_u32(s_h + (step - kStepEnc) * kPolABytes), d_col = 0, first = step == kStepEnc;
+                    else a_addr = smem_u32(s_h + (step - kStepSh) * kPolABytes), d_col = kPolHidden, first = step == kStepSh, idesc = idesc_n16;
+                    const uint32_t b_addr = smem_u32(s_b + s * kPolBBytes);
 #pragma unroll
-                for (int k = 0; k < kPolKChunk / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes along the swizzled row
-                    umma_bf16(tmem + d_col, umma_desc_k128(a_addr + 32 * k), umma_desc_k128(b_addr + 32 * k), idesc, !(first && k == 0));
-                umma_commit(empty + s);
-                if (step == kStepEnc - 1 || step == kStepSh - 1 || step == kStepAll - 1) umma_commit(mma_done);
+                    for (int k = 0; k < kPolKChunk / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes along the swizzled row
+                        umma_bf16(tmem + d_col, umma_desc_k128(a_addr + 32 * k), umma_desc_k128(b_addr + 32 * k), idesc, !(first && k == 0));
+                    umma_commit(empty + s);
+                    if (step == kStepEnc - 1 || step == kStepSh - 1 || step == kStepAll - 1) umma_commit(mma_done);
+                }
             }
         }
     } else {
-        // ================= epilogue: warps 2-5, one thread per row =================
-        const int quarter = warp & 3;  // the TMEM lanes this warp may read
+        // ================= epilogue: warps 2-9, one thread per row and column half =================
+        const int quarter = warp & 3;          // the TMEM lanes this warp may read
+        const int half = (warp - 2) >> 2;      // which half of a layer's columns
         const int row = 32 * quarter + lane;
         const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16);
         uint32_t acc[32];
-        // layer 1: D1[:, 0:512] -> H1
-        mbar_wait(mma_done, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const long long r = (long long)tile * kPolRows + row;
+            // layer 1: D1[:, 0:512] -> H1
+            mbar_wait(mma_done, (3 * it) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int n0 = 0; n0 < 512; n0 += 32) {
-            tmem_ld32(trow + n0, acc);
-            hidden_store32(s_h, row, n0, acc, p.b_enc);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(h_ready);
-        // layer 2: D2[:, 0:256] -> H2 (the first four chunks of the same buffer; GEMM2 has finished reading H1)
-        mbar_wait(mma_done, 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int n0 = 0; n0 < kPolHidden; n0 += 32) {
-            tmem_ld32(trow + n0, acc);
-            hidden_store32(s_h, row, n0, acc, p.b_shared);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(h_ready);
-        // layer 3: D3[:, 256:272] -> logits and value of this row, then the sampling step of sample_actions_kernel
-        mbar_wait(mma_done, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t hv[16];
-        tmem_ld16(trow + kPolHidden, hv);
-        const long long r = (long long)row0 + row;
-        if (r < p.n_rows) {
-            float x[TL_MAX_ACTIONS];
-            float top = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < kPolHeads; ++j) {
-                const float v = __uint_as_float(hv[j]) + __ldg(p.b_heads + j);
-                if (p.heads_out) p.heads_out[r * kPolHeads + j] = v;
-                x[j] = j < p.n_actions ? v : -INFINITY;
-                top = fmaxf(top, x[j]);
-                if (j == p.n_actions && p.values) p.values[r] = v;
+            for (int n0 = 256 * half; n0 < 256 * half + 256; n0 += 32) {
+                tmem_ld32(trow + n0, acc);
+                hidden_store32(s_h, row, n0, acc, p.b_enc);
             }
-            float sum = 0.0f;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(h_ready);
+            // layer 2: D2[:, 0:256] -> H2 (the first four chunks of the same buffer; GEMM2 has finished reading H1)
+            mbar_wait(mma_done, (3 * it + 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int n0 = 128 * half; n0 < 128 * half + 128; n0 += 32) {
+                tmem_ld32(trow + n0, acc);
+                hidden_store32(s_h, row, n0, acc, p.b_shared);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(h_ready);
+            // layer 3: D3[:, 256:272] -> logits and value of this row, then the sampling step of sample_actions_kernel
+            // (every epilogue thread follows every phase of the barrier: a parity wait must never fall two phases behind)
+            mbar_wait(mma_done, (3 * it + 2) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (half != 0) continue;  // one warp per quarter samples
+            uint32_t hv[16];
+            tmem_ld16(trow + kPolHidden, hv);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(d3_read);  // the next tile's encoders may overwrite the columns now
+            if (r < p.n_rows) {
+                float x[TL_MAX_ACTIONS];
+                float top = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < kPolHeads; ++j) sum += j < p.n_actions ? expf(x[j] - top) : 0.0f;
-            const float lse = top + logf(sum);
-            const unsigned long long base = 4ull * (unsigned long long)((p.counter ? *p.counter : 0ll) + p.offset);
-            int best = 0;
-            float best_score = -INFINITY, best_logp = 0.0f;
-#pragma unroll
-            for (int d = 0; d < kPolHeads / 4; ++d) {
-                if (4 * d >= p.n_actions) break;
-                const unsigned long long c = base + d;
-                const uint4 bits = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)r, (uint32_t)((unsigned long long)r >> 32),
-                                                 (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-                const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
-#pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    const int j = 4 * d + l;
-                    if (j >= p.n_actions) break;
-                    const float u = ((float)(w[l] >> 9) + 0.5f) * 1.1920928955078125e-07f;
-                    const float logp = x[j] - lse;
-                    const float score = logp - logf(-logf(u));
-                    if (score > best_score) best_score = score, best = j, best_logp = logp;
+                for (int j = 0; j < kPolHeads; ++j) {
+                    const float v = __uint_as_float(hv[j]) + __ldg(p.b_heads + j);
+                    if (p.heads_out) p.heads_out[r * kPolHeads + j] = v;
+                    x[j] = j < p.n_actions ? v : -INFINITY;
+                    top = fmaxf(top, x[j]);
+                    if (j == p.n_actions && p.values) p.values[r] = v;
                 }
+                float sum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < kPolHeads; ++j) sum += j < p.n_actions ? expf(x[j] - top) : 0.0f;
+                const float lse = top + logf(sum);
+                const unsigned long long base = 4ull * (unsigned long long)((p.counter ? *p.counter : 0ll) + p.offset);
+                int best = 0;
+                float best_score = -INFINITY, best_logp = 0.0f;
+#pragma unroll
+                for (int d = 0; d < kPolHeads / 4; ++d) {
+                    if (4 * d >= p.n_actions) break;
+                    const unsigned long long c = base + d;
+                    const uint4 bits = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)r, (uint32_t)((unsigned long long)r >> 32),
+                                                     (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+                    const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) {
+                        const int j = 4 * d + l;
+                        if (j >= p.n_actions) break;
+                        const float u = ((float)(w[l] >> 9) + 0.5f) * 1.1920928955078125e-07f;
+                        const float logp = x[j] - lse;
+                        const float score = logp - logf(-logf(u));
+                        if (score > best_score) best_score = score, best = j, best_logp = logp;
+                    }
+                }
+                p.actions[r] = best;
+                p.log_probs[r] = best_logp;
             }
-            p.actions[r] = best;
-            p.log_probs[r] = best_logp;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -381,7 +406,13 @@ int tl_policy_step(const void* inputs, int64_t n_rows, int64_t input_row, const 
     p.b_enc = w->b_enc, p.b_shared = w->b_shared, p.b_heads = w->b_heads;
     p.n_rows = n_rows, p.n_actions = w->n_actions, p.seed = seed, p.counter = (const long long*)counter, p.offset = offset;
     p.actions = (long long*)actions, p.log_probs = log_probs, p.values = values, p.heads_out = heads_out;
-    const unsigned grid = (unsigned)((n_rows + kPolRows - 1) / kPolRows);
+    // persistent CTAs, one per SM (a CTA takes the whole shared memory and tensor memory of its SM)
+    int device = 0;
+    if (!cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return TL_ERR_CUDA;
+    const DeviceInfo* di = device_info(device);
+    if (!di) return set_error("cudaDeviceGetAttribute failed"), TL_ERR_CUDA;
+    const long long n_tiles = (n_rows + kPolRows - 1) / kPolRows;
+    const unsigned grid = (unsigned)(n_tiles < di->sms ? n_tiles : di->sms);
     policy_mlp_kernel<<<grid, kPolThreads, kPolSmemBytes, (cudaStream_t)stream>>>(mx, mwm, mwf, mws, mwh, p);
     if (!cuda_ok(cudaGetLastError(), "policy_mlp launch")) return TL_ERR_CUDA;
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -363,6 +363,8 @@ class RolloutCapture:
         self.act_on_world = act_on_world
         self.fuse_map_cast = True  # False: the policy step casts the float32 observation itself (A/B runs, tests)
         self.fuse_sampling = True  # False: log_softmax / Gumbel-max / gather as separate torch kernels (A/B runs)
+        self.fuse_policy = True  # False: three cuBLASLt products + tl_sample_actions instead of tl_policy_step (A/B runs)
+        self._fused_weights: FusedPolicyWeights | None = None
         self.seed = int(torch.initial_seed())  # Philox key of tl_sample_actions
         self._draws = torch.zeros(1, dtype=torch.int64, device=dev.device)  # policy steps sampled so far (device counter)
         self._map_bf16: torch.Tensor | None = None
@@ -390,6 +392,8 @@ class RolloutCapture:
             "arithmetic": "bfloat16 inputs and weights, float32 accumulation" if self.autocast_dtype == torch.bfloat16 else "float32",
             "inputs": "bfloat16 rows written by the tick kernel" if fused else "float32 observation cast by the policy step",
             "sampling": "tl_sample_actions (one kernel: log_softmax + Gumbel-max + gather)" if self.fuse_sampling else "torch ops",
+            "kernel": "tl_policy_step: one tcgen05 kernel per tick (TMA operands, TMEM accumulators, activations in shared memory, "
+            "sampling in the epilogue)" if (fused and self._fused_policy() is not None) else "three cuBLASLt products",
         }
 
     def _action_words(self, act: torch.Tensor) -> torch.Tensor:
@@ -446,7 +450,12 @@ class RolloutCapture:
         actions, log_probs, values = rows
         # categorical sample by the Gumbel-max trick (argmax of log-probabilities minus log of Exp(1) noise): the
         # same distribution as Categorical(logits).sample(), and no host sync
-        if self.fuse_sampling and mirror is not None:
+        fused = self._fused_policy() if (self.fuse_sampling and mirror is not None) else None
+        if fused is not None:
+            # the whole step — encoders, shared layer, heads, log_softmax, sample — in one tcgen05 kernel reading the rows the
+            # tick kernel just wrote
+            act = policy_step(self._inputs_bf16, fused, self.seed, self._draws, draw, out=(actions[slot], log_probs[slot], values[slot]))[0]
+        elif self.fuse_sampling and mirror is not None:
             # bfloat16 PolicyMLP: one kernel reads the fused heads product and writes action, log-prob and value
             # straight into the rollout rows
             heads = self.policy._forward_bf16_padded(out.map[slot], out.features[slot], self._inputs_bf16, raw_heads=True)
@@ -464,6 +473,19 @@ class RolloutCapture:
             values[slot] = value
         if self.act_on_world:
             self._words.copy_(self._action_words(act))
+
+    def _fused_policy(self) -> "FusedPolicyWeights | None":
+        """The weights for ``tl_policy_step`` when the policy is the 256-wide bfloat16 ``PolicyMLP`` (rebuilt when a parameter changes)."""
+        if not (self.fuse_policy and isinstance(self.policy, PolicyMLP) and self.autocast_dtype == torch.bfloat16):
+            return None
+        versions = tuple(p._version for p in self.policy.parameters())
+        if self._fused_weights is None or self._fused_weights.versions != versions:
+            try:
+                self._fused_weights = FusedPolicyWeights(self.policy, self.dev.device)
+            except capi.TownletB200Error:
+                self.fuse_policy = False  # another layer shape: the library products
+                return None
+        return self._fused_weights
 
     def _with_mirrors(self, out: TickOutputs):
         mirror = self._mirror()
