@@ -430,7 +430,7 @@ typedef void* tl_stream_t; /* cudaStream_t */
 const char* tl_last_error(void);
 int tl_abi_version(void);
 /* sizeof of the idx-th ABI struct (0 TlTownBatch, 1 TlObsParams, 2 TlRewardParams,
- * 3 TlObsOut, 4 TlRewardOut, 5 TlDynamicsParams, 6 TlHostStep, 7 TlPolicyWeights) so bindings can verify their layout; -1 otherwise */
+ * 3 TlObsOut, 4 TlRewardOut, 5 TlDynamicsParams, 6 TlHostStep, 7 TlPolicyWeights, 8 TlEmploymentParams, 9 TlEmploymentState) so bindings can verify their layout; -1 otherwise */
 int tl_abi_struct_size(int idx);
 /* number of SMs of the current device, or a negative error */
 int tl_device_sm_count(void);
@@ -530,6 +530,97 @@ int tl_cast_pad_bf16_strided(const float* src, void* dst, int64_t n_rows, int32_
 int tl_sample_actions(const void* heads, int32_t heads_dtype, int64_t n_rows, int32_t row, int32_t n_actions, uint64_t seed,
                       const int64_t* counter, int64_t offset, int64_t* actions, float* log_probs, float* values,
                       tl_stream_t stream);
+
+/*
+ * Employment shift state machine on the device (ABI v4): EmploymentEngine.apply_job_state
+ * (world/employment.py:63-142 with its helpers :229-455), the `employment` step of the world systems
+ * (world/systems/__init__.py:9-19; between need decay and the ledger decay).  One thread walks the agents of one town in
+ * order — the walk is sequential by construction: an agent's coworker look-up (:466-480) sees the states already
+ * updated this tick for earlier agents and last tick's for later ones.  Per agent it keeps the reference's employment
+ * context (TlEmploymentState, one array per key of context_defaults, :167-193) and rewrites the snapshot fields the hot
+ * path reads: wallet, wages_withheld, lateness, attendance, flags (on_shift, shift state), wages_paid, punctuality.
+ * What stays on the host: the two coworker ledger updates (world.update_relationship for "employment_help" /
+ * "employment_shift_taken", with capacity pruning) and event emission — the kernel reports them as per-agent event bits
+ * (TL_EMP_EV_*) and the host applies them; job assignment (assign_jobs_to_agents) and the exit queue.
+ * `tick_offset` is added to town_tick: 1 when the step runs before the tl_tick launch that advances the tick.
+ */
+#define TL_MAX_JOBS 16
+#define TL_MAX_ATTENDANCE_WINDOW 14 /* employment.attendance_window <= 14 (config/world_config.py:38) */
+#define TL_MAX_ABSENCE_EVENTS 16
+/* ctx["state"] codes */
+#define TL_EMP_PRE_SHIFT 0
+#define TL_EMP_IDLE 1
+#define TL_EMP_AWAIT_START 2
+#define TL_EMP_ON_TIME 3
+#define TL_EMP_LATE 4
+#define TL_EMP_ABSENT 5
+#define TL_EMP_POST_SHIFT 6
+/* boolean context keys, bits of TlEmploymentState.ctx_flags */
+#define TL_EMP_F_LATE_PENALTY (1u << 0)
+#define TL_EMP_F_ABSENCE_PENALTY (1u << 1)
+#define TL_EMP_F_LATE_EVENT (1u << 2)
+#define TL_EMP_F_ABSENCE_EVENT (1u << 3)
+#define TL_EMP_F_DEPARTURE_EVENT (1u << 4)
+#define TL_EMP_F_LATE_HELP_EVENT (1u << 5)
+#define TL_EMP_F_TOOK_SHIFT_EVENT (1u << 6)
+#define TL_EMP_F_LATE_COUNTER (1u << 7)
+#define TL_EMP_F_EVER_ON_TIME (1u << 8)
+#define TL_EMP_F_OUTCOME_RECORDED (1u << 9)
+#define TL_EMP_F_SHIFT_STARTED (1u << 10) /* shift_started_tick is not None */
+#define TL_EMP_F_LAST_PRESENT (1u << 11)  /* last_present_tick is not None */
+/* events of a tick, bits of events_out[tick][agent] (the reference emits them through _emit_event) */
+#define TL_EMP_EV_LATE_START 1u       /* shift_late_start */
+#define TL_EMP_EV_ABSENT 2u           /* shift_absent */
+#define TL_EMP_EV_DEPARTED_EARLY 4u   /* shift_departed_early */
+#define TL_EMP_EV_HELPED_WHEN_LATE 8u /* employment_helped_when_late: the host applies the coworker ledger update */
+#define TL_EMP_EV_TOOK_MY_SHIFT 16u   /* employment_took_my_shift: likewise */
+
+typedef struct TlEmploymentParams {
+    int32_t n_jobs;               /* config.jobs in order; job 0 is the default for an agent without one (:83-89) */
+    int32_t arrival_buffer;       /* behavior.job_arrival_buffer */
+    int32_t ticks_per_day;        /* max(1, employment.exit_review_window) */
+    int32_t grace_ticks;
+    int32_t absent_cutoff;
+    int32_t absence_slack;
+    int32_t attendance_window;    /* max(1, employment.attendance_window) <= TL_MAX_ATTENDANCE_WINDOW */
+    int32_t reserved0;
+    double late_tick_penalty;
+    double absence_penalty;
+    int32_t job_start[TL_MAX_JOBS];
+    int32_t job_end[TL_MAX_JOBS];          /* end_tick or start_tick, never before the start (:92-96) */
+    int32_t job_has_location[TL_MAX_JOBS];
+    int32_t job_x[TL_MAX_JOBS];            /* world coordinates (town_origin is subtracted on the device) */
+    int32_t job_y[TL_MAX_JOBS];
+    double job_wage[TL_MAX_JOBS];          /* spec.wage_rate or economy["wage_income"] (:97) */
+    double job_lateness_penalty[TL_MAX_JOBS];
+} TlEmploymentParams;
+
+typedef struct TlEmploymentState {
+    int32_t* job;               /* [N] index into the job table, -1 = none */
+    int32_t* state;             /* [N] TL_EMP_* */
+    int32_t* current_day;       /* [N] */
+    int32_t* late_ticks;        /* [N] */
+    uint32_t* ctx_flags;        /* [N] TL_EMP_F_* */
+    int32_t* shift_started_tick;/* [N] valid with TL_EMP_F_SHIFT_STARTED */
+    int32_t* shift_end_tick;    /* [N] */
+    int32_t* last_present_tick; /* [N] valid with TL_EMP_F_LAST_PRESENT */
+    int32_t* scheduled_ticks;   /* [N] */
+    int32_t* on_time_ticks;     /* [N] */
+    double* attendance_samples; /* [N][TL_MAX_ATTENDANCE_WINDOW] oldest first (deque(maxlen=window)) */
+    int32_t* attendance_count;  /* [N] */
+    int32_t* absence_events;    /* [N][TL_MAX_ABSENCE_EVENTS] ticks, oldest first */
+    int32_t* absence_count;     /* [N] */
+    int32_t* late_ticks_today;  /* [N] snapshot.late_ticks_today */
+    int32_t* absent_shifts_7d;  /* [N] snapshot.absent_shifts_7d */
+    int32_t* wages_earned;      /* [N] snapshot.inventory["wages_earned"] */
+    const int32_t* town_origin; /* [T][2] world coordinates of the town-relative tile (0, 0) */
+} TlEmploymentState;
+
+/* n_ticks steps of apply_job_state for every town of the batch (tick = town_tick + tick_offset + step).  The batch arrays
+ * wallet, wages_withheld, lateness, attendance, wages_paid, punctuality and flags are rewritten.  events_out may be NULL;
+ * otherwise [n_ticks][N] words of TL_EMP_EV_* bits.  Device pointers, asynchronous on the stream. */
+int tl_employment_step(const TlTownBatch* batch, const TlEmploymentParams* params, const TlEmploymentState* state,
+                       uint32_t* events_out, int32_t n_ticks, int32_t tick_offset, tl_stream_t stream);
 
 /*
  * The whole batched policy step in ONE kernel on the tensor cores (ABI v4).  The reference evaluates

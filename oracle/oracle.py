@@ -189,3 +189,21 @@ def oracle_sample_actions(heads: np.ndarray, n_actions: int, seed: int, counter:
     score = logp - np.log(-np.log(u, dtype=np.float32), dtype=np.float32)
     actions = score.argmax(axis=1)
     return actions.astype(np.int64), logp[np.arange(n), actions], logp, u
+
+
+def oracle_employment_step(batch: TownBatch, spec, arrays, n_ticks: int = 1, tick_offset: int = 0, town_origin: np.ndarray | None = None) -> np.ndarray:
+    """``tlo_employment_step``: ``apply_job_state`` restated in C on the host arrays (``batch`` and ``arrays`` are updated in
+    place); returns the event words ``[n_ticks, n_agents]``."""
+    lib = load()
+    lib.tlo_employment_step.restype = C.c_int
+    lib.tlo_employment_step.argtypes = [C.POINTER(capi.TlTownBatch), C.POINTER(capi.TlEmploymentParams), C.POINTER(capi.TlEmploymentState),
+                                        C.c_void_p, C.c_int32, C.c_int32]
+    origin = np.zeros((batch.n_towns, 2), dtype=np.int32) if town_origin is None else np.ascontiguousarray(town_origin, dtype=np.int32)
+    bs = batch.struct()
+    params = spec.struct()
+    state = arrays.struct({name: arrays.arrays[name].ctypes.data for name, _, _ in capi.EMPLOYMENT_STATE_FIELDS}, origin.ctypes.data)
+    events = np.zeros((n_ticks, batch.n_agents), dtype=np.uint32)
+    status = lib.tlo_employment_step(C.byref(bs), C.byref(params), C.byref(state), events.ctypes.data, n_ticks, tick_offset)
+    if status != 0:
+        raise RuntimeError(f"oracle tlo_employment_step failed with {status}")
+    return events

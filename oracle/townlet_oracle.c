@@ -880,3 +880,233 @@ int tlo_gae(const float* rewards, const float* values, const float* dones, float
 }
 
 int tlo_abi_version(void) { return TL_ABI_VERSION; }
+
+/* ---------------------------------------------------------------------------
+ * Employment shift state machine: EmploymentEngine.apply_job_state,
+ * src/townlet/world/employment.py:63-142, restated helper by helper (the ctx
+ * dictionary of context_defaults, :167-193, is one array per key in
+ * TlEmploymentState).  TEST INFRASTRUCTURE like the rest of this file.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    const TlTownBatch* b;
+    const TlEmploymentParams* p;
+    const TlEmploymentState* s;
+    uint32_t events;
+} EmpCtx;
+
+static void emp_set_shift_state(const TlTownBatch* b, int a, int state, int on_shift) {
+    /* snapshot.shift_state / snapshot.on_shift -> the flag word the features read (features.py:133, 151-169) */
+    unsigned code = state == TL_EMP_ON_TIME ? 1u : state == TL_EMP_LATE ? 2u : state == TL_EMP_ABSENT ? 3u : state == TL_EMP_POST_SHIFT ? 4u : 0u;
+    b->flags[a] = (b->flags[a] & ~(TL_F_ON_SHIFT | TL_F_SHIFT_MASK)) | (on_shift ? TL_F_ON_SHIFT : 0u) | (code << TL_F_SHIFT_SHIFT);
+}
+
+static void emp_finalize_shift(EmpCtx* e, int a) { /* :420-455 */
+    const TlEmploymentState* s = e->s;
+    if (!(s->ctx_flags[a] & TL_EMP_F_SHIFT_STARTED) || (s->ctx_flags[a] & TL_EMP_F_OUTCOME_RECORDED)) {
+        emp_set_shift_state(e->b, a, TL_EMP_POST_SHIFT, 0);
+        return;
+    }
+    int scheduled = s->scheduled_ticks[a] > 1 ? s->scheduled_ticks[a] : 1;
+    double attendance_value = (double)s->on_time_ticks[a] / (double)scheduled;
+    int window = e->p->attendance_window > 1 ? e->p->attendance_window : 1;
+    double* samples = s->attendance_samples + (size_t)a * TL_MAX_ATTENDANCE_WINDOW;
+    int n = s->attendance_count[a];
+    if (n == window) { /* deque(maxlen=window).append */
+        memmove(samples, samples + 1, sizeof(double) * (size_t)(n - 1));
+        n -= 1;
+    }
+    samples[n++] = attendance_value;
+    s->attendance_count[a] = n;
+    double total = 0.0;
+    for (int i = 0; i < n; ++i) total += samples[i];
+    ((double*)e->b->attendance)[a] = total / (double)n;
+    s->ctx_flags[a] |= TL_EMP_F_OUTCOME_RECORDED;
+    s->state[a] = TL_EMP_POST_SHIFT;
+    emp_set_shift_state(e->b, a, TL_EMP_POST_SHIFT, 0);
+    s->ctx_flags[a] &= ~(TL_EMP_F_SHIFT_STARTED | TL_EMP_F_LAST_PRESENT); /* shift_started_tick = shift_end_tick = last_present_tick = None */
+    s->ctx_flags[a] &= ~(TL_EMP_F_LATE_PENALTY | TL_EMP_F_ABSENCE_PENALTY | TL_EMP_F_LATE_EVENT | TL_EMP_F_ABSENCE_EVENT |
+                         TL_EMP_F_DEPARTURE_EVENT | TL_EMP_F_LATE_COUNTER);
+    s->late_ticks_today[a] = s->late_ticks[a];
+    s->late_ticks[a] = 0;
+}
+
+static void emp_idle_state(EmpCtx* e, int a) { /* :229-243 */
+    if (e->s->state[a] != TL_EMP_PRE_SHIFT && e->s->state[a] != TL_EMP_IDLE) emp_finalize_shift(e, a);
+    e->s->state[a] = TL_EMP_IDLE;
+    emp_set_shift_state(e->b, a, TL_EMP_IDLE, 0);
+}
+
+static int emp_coworkers_on_shift(EmpCtx* e, int a0, int a1, int a) { /* :466-480: the list is only tested for emptiness here */
+    int count = 0;
+    for (int o = a0; o < a1; ++o) {
+        if (o == a || e->s->job[o] != e->s->job[a]) continue;
+        if (e->s->state[o] == TL_EMP_ON_TIME || e->s->state[o] == TL_EMP_LATE) ++count;
+    }
+    return count;
+}
+
+static void emp_apply_agent(EmpCtx* e, int t, int a0, int a1, int a, int tick) {
+    const TlTownBatch* b = e->b;
+    const TlEmploymentParams* p = e->p;
+    const TlEmploymentState* s = e->s;
+    double* wallet = (double*)b->wallet;
+    double* wages_withheld = (double*)b->wages_withheld;
+    double* wages_paid = (double*)b->wages_paid;
+    int tpd = p->ticks_per_day > 1 ? p->ticks_per_day : 1;
+    int current_day = tick / tpd;
+    if (tick % tpd != 0 && tick < 0) --current_day; /* Python floor division */
+    if (s->current_day[a] != current_day) { /* :73-78 */
+        s->current_day[a] = current_day;
+        s->late_ticks[a] = 0;
+        wages_paid[a] = 0.0;
+        s->late_ticks_today[a] = 0;
+    }
+    if (s->job[a] < 0 || s->job[a] >= p->n_jobs) { /* :80-86 */
+        if (p->n_jobs <= 0) {
+            emp_idle_state(e, a);
+            return;
+        }
+        s->job[a] = 0;
+    }
+    int job = s->job[a];
+    int start = p->job_start[job], end = p->job_end[job];
+    double wage_rate = p->job_wage[job], lateness_penalty = p->job_lateness_penalty[job];
+    int ox = s->town_origin ? s->town_origin[2 * t] : 0, oy = s->town_origin ? s->town_origin[2 * t + 1] : 0;
+    int at_required_location = !p->job_has_location[job] || (pos_x(b->pos[a]) + ox == p->job_x[job] && pos_y(b->pos[a]) + oy == p->job_y[job]);
+    int32_t* absence = s->absence_events + (size_t)a * TL_MAX_ABSENCE_EVENTS;
+    while (s->absence_count[a] > 0 && (long long)tick - absence[0] > 7ll * tpd) { /* :103-107 popleft */
+        memmove(absence, absence + 1, sizeof(int32_t) * (size_t)(s->absence_count[a] - 1));
+        s->absence_count[a] -= 1;
+    }
+    s->absent_shifts_7d[a] = s->absence_count[a];
+    if (tick < start - p->arrival_buffer) {
+        emp_idle_state(e, a);
+        return;
+    }
+    if (tick < start) { /* _employment_prepare_state :245-248 */
+        s->state[a] = TL_EMP_AWAIT_START;
+        emp_set_shift_state(b, a, TL_EMP_AWAIT_START, 0);
+        return;
+    }
+    if (tick > end) {
+        emp_finalize_shift(e, a);
+        return;
+    }
+    /* _employment_begin_shift :250-268 */
+    if (!(s->ctx_flags[a] & TL_EMP_F_SHIFT_STARTED) || s->shift_started_tick[a] != start) {
+        s->shift_started_tick[a] = start;
+        s->shift_end_tick[a] = end;
+        s->scheduled_ticks[a] = end - start + 1 > 1 ? end - start + 1 : 1;
+        s->on_time_ticks[a] = 0;
+        s->late_ticks[a] = 0;
+        wages_paid[a] = 0.0;
+        s->ctx_flags[a] = TL_EMP_F_SHIFT_STARTED;
+    }
+    /* _employment_determine_state :270-301 */
+    int ticks_since_start = tick - start;
+    int state = s->state[a];
+    if (at_required_location) {
+        s->last_present_tick[a] = tick;
+        s->ctx_flags[a] |= TL_EMP_F_LAST_PRESENT;
+        if ((s->ctx_flags[a] & TL_EMP_F_EVER_ON_TIME) || ticks_since_start <= p->grace_ticks) {
+            state = TL_EMP_ON_TIME;
+            s->ctx_flags[a] |= TL_EMP_F_EVER_ON_TIME;
+        } else {
+            state = TL_EMP_LATE;
+        }
+    } else {
+        if (ticks_since_start <= p->grace_ticks) state = TL_EMP_LATE;
+        else if (ticks_since_start > p->absent_cutoff) state = TL_EMP_ABSENT;
+        else if ((s->ctx_flags[a] & TL_EMP_F_LAST_PRESENT) && tick - s->last_present_tick[a] > p->absence_slack) state = TL_EMP_ABSENT;
+        else state = TL_EMP_LATE;
+    }
+    /* _employment_apply_state_effects :303-418 */
+    int previous_state = s->state[a];
+    s->state[a] = state;
+    int eligible_for_wage = (state == TL_EMP_ON_TIME || state == TL_EMP_LATE) && at_required_location;
+    int coworkers = emp_coworkers_on_shift(e, a0, a1, a);
+    int previous_working = previous_state == TL_EMP_ON_TIME || previous_state == TL_EMP_LATE;
+    if (state == TL_EMP_ON_TIME) s->on_time_ticks[a] += 1;
+    if (state == TL_EMP_LATE) {
+        s->late_ticks[a] += 1;
+        s->late_ticks_today[a] += 1;
+        if (!(s->ctx_flags[a] & TL_EMP_F_LATE_PENALTY) && !previous_working) {
+            wallet[a] = fmax(0.0, wallet[a] - lateness_penalty);
+            s->ctx_flags[a] |= TL_EMP_F_LATE_PENALTY;
+            if (!(s->ctx_flags[a] & TL_EMP_F_LATE_COUNTER)) {
+                ((int32_t*)b->lateness)[a] += 1;
+                s->ctx_flags[a] |= TL_EMP_F_LATE_COUNTER;
+            }
+        }
+        if (!(s->ctx_flags[a] & TL_EMP_F_LATE_EVENT)) {
+            e->events |= TL_EMP_EV_LATE_START;
+            s->ctx_flags[a] |= TL_EMP_F_LATE_EVENT;
+        }
+        if (!at_required_location) {
+            if (p->late_tick_penalty != 0.0) wallet[a] = fmax(0.0, wallet[a] - p->late_tick_penalty);
+            wages_withheld[a] += wage_rate;
+        }
+        if (coworkers && !(s->ctx_flags[a] & TL_EMP_F_LATE_HELP_EVENT)) {
+            e->events |= TL_EMP_EV_HELPED_WHEN_LATE;
+            s->ctx_flags[a] |= TL_EMP_F_LATE_HELP_EVENT;
+        }
+    }
+    if (state == TL_EMP_ABSENT) {
+        if (!(s->ctx_flags[a] & TL_EMP_F_ABSENCE_PENALTY)) {
+            wallet[a] = fmax(0.0, wallet[a] - p->absence_penalty);
+            s->ctx_flags[a] |= TL_EMP_F_ABSENCE_PENALTY;
+        }
+        wages_withheld[a] += wage_rate;
+        if (!(s->ctx_flags[a] & TL_EMP_F_ABSENCE_EVENT)) {
+            e->events |= TL_EMP_EV_ABSENT;
+            s->ctx_flags[a] |= TL_EMP_F_ABSENCE_EVENT;
+            if (s->absence_count[a] == TL_MAX_ABSENCE_EVENTS) {
+                memmove(absence, absence + 1, sizeof(int32_t) * (TL_MAX_ABSENCE_EVENTS - 1));
+                s->absence_count[a] -= 1;
+            }
+            absence[s->absence_count[a]++] = tick;
+            s->absent_shifts_7d[a] = s->absence_count[a];
+        }
+        if (coworkers && !(s->ctx_flags[a] & TL_EMP_F_TOOK_SHIFT_EVENT)) {
+            e->events |= TL_EMP_EV_TOOK_MY_SHIFT;
+            s->ctx_flags[a] |= TL_EMP_F_TOOK_SHIFT_EVENT;
+        }
+    } else if (state == TL_EMP_ON_TIME || state == TL_EMP_LATE) {
+        s->ctx_flags[a] &= ~TL_EMP_F_ABSENCE_PENALTY;
+    }
+    if (eligible_for_wage && state != TL_EMP_ABSENT) {
+        emp_set_shift_state(b, a, state, 1);
+        wallet[a] += wage_rate;
+        s->wages_earned[a] += 1;
+        wages_paid[a] += wage_rate;
+    } else {
+        emp_set_shift_state(b, a, state, 0);
+        if (previous_working && state != TL_EMP_ON_TIME && state != TL_EMP_LATE) {
+            if (!(s->ctx_flags[a] & TL_EMP_F_DEPARTURE_EVENT) && previous_state != TL_EMP_ABSENT) {
+                e->events |= TL_EMP_EV_DEPARTED_EARLY;
+                s->ctx_flags[a] |= TL_EMP_F_DEPARTURE_EVENT;
+            }
+        }
+    }
+}
+
+int tlo_employment_step(const TlTownBatch* b, const TlEmploymentParams* p, const TlEmploymentState* s, uint32_t* events_out,
+                        int32_t n_ticks, int32_t tick_offset) {
+    if (!b || !p || !s || n_ticks < 0) return TL_ERR_ARG;
+    for (int it = 0; it < n_ticks; ++it) {
+        for (int t = 0; t < b->n_towns; ++t) {
+            int a0 = b->town_agent_off[t], a1 = b->town_agent_off[t + 1];
+            int tick = b->town_tick[t] + tick_offset + it;
+            for (int a = a0; a < a1; ++a) {
+                EmpCtx e = {b, p, s, 0u};
+                emp_apply_agent(&e, t, a0, a1, a, tick);
+                /* employment_context_punctuality :215-222 */
+                int scheduled = s->scheduled_ticks[a] > 1 ? s->scheduled_ticks[a] : 1;
+                double value = (double)s->on_time_ticks[a] / (double)scheduled;
+                ((double*)b->punctuality)[a] = fmax(0.0, fmin(1.0, value));
+                if (events_out) events_out[(size_t)it * b->n_agents + a] = e.events;
+            }
+        }
+    }
+    return TL_OK;
+}

@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parents[1]
 OUT = ROOT / "gpurun_out"
 PROF = ROOT / "profiles"
 PROF.mkdir(exist_ok=True)
-UNITS = {"c2": 32 * 8192, "c3-compact": 4 * 163840, "c3-full": 4 * 163840, "c4": 4 * 262144}
+UNITS = {"c2": 20 * 8192, "c3-compact": 4 * 163840, "c3-full": 4 * 163840, "c4": 4 * 262144}
 ALGO = {"c2": 2712, "c3-compact": 1756, "c3-full": 3680, "c4": 2712}
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0}
 

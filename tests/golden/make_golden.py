@@ -374,6 +374,102 @@ def reservation_cases():
         print(f"  reservations_{variant}: {len(ids)} agents, {int((batch.ent_holder >= -1).sum())} slots, tiles {sorted(world.reservation_tiles())}")
 
 
+def employment_case():
+    """``EmploymentEngine.apply_job_state`` (world/employment.py:63-142) run by the reference for two
+    and a half days on a scripted town — punctual, late, absent, early-leaving and jobless agents, coworkers on the same
+    shift, an attendance window that rolls — with every context key, the snapshot fields the hot path reads and the events
+    the reference emits recorded after every tick."""
+    from townlet_b200.employment import EVENT_BITS, SHIFT_FLAG_CODE, EmploymentArrays, EmploymentSpec
+
+    config = make_config(
+        "hybrid",
+        employment__exit_review_window=100, employment__grace_ticks=3, employment__absent_cutoff=12, employment__absence_slack=6,
+        employment__attendance_window=2, employment__enforce_job_loop=True, behavior__job_arrival_buffer=5,
+        jobs={"grocer": {"start_tick": 20, "end_tick": 60, "wage_rate": 0.02, "lateness_penalty": 0.1, "location": [0, 0]},
+              "barista": {"start_tick": 30, "end_tick": 50, "wage_rate": 0.025, "lateness_penalty": 0.12, "location": [1, 0]},
+              "courier": {"start_tick": 70, "end_tick": 0, "wage_rate": 0.0, "lateness_penalty": 0.0, "location": None}},
+    )
+    spec = EmploymentSpec.from_config(config)
+    world = WorldState.from_config(config)
+    jobs_of = {"a": "grocer", "b": "grocer", "c": "grocer", "d": "barista", "e": None, "f": "barista", "g": "courier"}
+    for k, (aid, job) in enumerate(jobs_of.items()):
+        world.agents[aid] = AgentSnapshot(agent_id=aid, position=(5, 5), needs={"hunger": 0.9, "hygiene": 0.9, "energy": 0.9},
+                                          wallet=0.15 + 0.05 * k, job_id=job)
+    agent_ids = list(world.agents)
+    home, grocer, barista = (5, 5), (0, 0), (1, 0)
+
+    def position(aid: str, tick: int) -> tuple[int, int]:
+        day, t = divmod(tick, 100)
+        if aid == "a":  # punctual every day
+            return grocer if 15 <= t <= 65 else home
+        if aid == "b":  # day 0: arrives after the grace period; day 1: on time; day 2: leaves early for good
+            if day == 0:
+                return grocer if 30 <= t <= 65 else home
+            if day == 1:
+                return grocer if 18 <= t <= 65 else home
+            return grocer if 20 <= t <= 35 else home
+        if aid == "c":  # never shows up on day 0 and 2 (absent, "took my shift"); late within grace then present on day 1
+            if day == 1:
+                return grocer if 22 <= t <= 65 else home
+            return home
+        if aid == "d":  # barista: on time, steps out for longer than the absence slack, comes back
+            return barista if (30 <= t <= 36 or 46 <= t <= 50) else home
+        if aid == "e":  # no job: takes the default one (grocer) and arrives late
+            return grocer if 27 <= t <= 65 else home
+        if aid == "f":  # barista: steps out briefly (shorter than the slack)
+            return barista if (29 <= t <= 38 or 42 <= t <= 50) else home
+        return home  # g: a job without a location is always "at the required location"
+
+    emitted: list[tuple[str, dict]] = []
+    engine = world.employment.engine  # the coordinator is a façade (world/employment_service.py:15-40)
+    original_emit = engine._emit_event
+    engine._emit_event = lambda name, payload: (emitted.append((name, dict(payload))), original_emit(name, payload))[1]
+    n_ticks = 250
+    N = len(agent_ids)
+    names = [name for name, _, _ in capi.EMPLOYMENT_STATE_FIELDS]
+    ref: dict[str, np.ndarray] = {f"emp_{name}": [] for name in names}
+    extra = {k: [] for k in ("wallet", "wages_withheld", "lateness", "attendance", "wages_paid", "punctuality", "on_shift", "shift_code", "events", "pos")}
+    for tick in range(n_ticks):
+        world.tick = tick
+        for aid in agent_ids:
+            world.agents[aid].position = position(aid, tick)
+        emitted.clear()
+        engine.apply_job_state(world)
+        arrays = EmploymentArrays(N)
+        for row, aid in enumerate(agent_ids):
+            arrays.load_context(row, engine._state[aid], world.agents[aid], spec)
+        for name in names:
+            ref[f"emp_{name}"].append(arrays.arrays[name].copy())
+        snaps = [world.agents[aid] for aid in agent_ids]
+        extra["wallet"].append([float(s.wallet) for s in snaps])
+        extra["wages_withheld"].append([float(s.wages_withheld) for s in snaps])
+        extra["lateness"].append([int(s.lateness_counter) for s in snaps])
+        extra["attendance"].append([float(s.attendance_ratio) for s in snaps])
+        extra["wages_paid"].append([float(engine.employment_context_wages(aid)) for aid in agent_ids])
+        extra["punctuality"].append([float(engine.employment_context_punctuality(aid)) for aid in agent_ids])
+        extra["on_shift"].append([int(bool(s.on_shift)) for s in snaps])
+        extra["shift_code"].append([SHIFT_FLAG_CODE.get(s.shift_state, 0) for s in snaps])
+        words = [0] * N
+        for name, payload in emitted:
+            if name in EVENT_BITS:
+                words[agent_ids.index(payload["agent_id"])] |= EVENT_BITS[name]
+        extra["events"].append(words)
+        extra["pos"].append([list(position(aid, tick)) for aid in agent_ids])
+    out = {k: np.asarray(v) for k, v in ref.items()}
+    out.update({k: np.asarray(v) for k, v in extra.items()})
+    out["initial_wallet"] = np.asarray([0.15 + 0.05 * k for k in range(N)])
+    out["initial_job"] = np.asarray([spec.job_ids.index(j) if j else -1 for j in jobs_of.values()], dtype=np.int32)
+    import json as _json
+    from dataclasses import asdict
+
+    out["spec"] = np.array(_json.dumps(asdict(spec)))
+    (GOLDEN_DIR / "employment").mkdir(exist_ok=True)
+    np.savez_compressed(GOLDEN_DIR / "employment" / "ref_employment.npz", **out)
+    seen = sorted({name for words in extra["events"] for name, bit in EVENT_BITS.items() if any(w & bit for w in words)})
+    states = sorted({int(v) for v in np.unique(out["emp_state"])})
+    print(f"  ref_employment: {N} agents x {n_ticks} ticks, events {seen}, states {states}, attendance {np.unique(out['attendance']).round(3)}")
+
+
 # ---------------------------------------------------------------------------
 # 3. synthetic towns of the benchmark generator, materialised in the reference
 # ---------------------------------------------------------------------------
@@ -1334,7 +1430,7 @@ def main():
     print(f"reference: {REF_SRC} (copy at {WORK})")
     only = os.environ.get("TL_GOLDEN_ONLY")
     if only:
-        {"synth": synth_cases, "reservations": reservation_cases, "gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world, "fuzz-dropin": fuzz_dropin, "fuzz-gae": fuzz_gae}[only]()
+        {"synth": synth_cases, "reservations": reservation_cases, "employment": employment_case, "gae": gae_case, "snapshots": snapshot_cases, "world": world_dynamics_cases, "replay": replay_case, "fuzz": fuzz_oracle, "fuzz-world": fuzz_world, "fuzz-dropin": fuzz_dropin, "fuzz-gae": fuzz_gae}[only]()
         shutil.rmtree(WORK, ignore_errors=True)
         return
     baselines()
@@ -1342,6 +1438,7 @@ def main():
     builder_cases()
     crowded_cases()
     reservation_cases()
+    employment_case()
     synth_cases()
     reward_cases()
     snapshot_cases()

@@ -290,6 +290,58 @@ class TlPolicyWeights(C.Structure):
     ]
 
 
+TL_MAX_JOBS = 16
+TL_MAX_ATTENDANCE_WINDOW = 14
+TL_MAX_ABSENCE_EVENTS = 16
+
+
+class TlEmploymentParams(C.Structure):
+    _fields_ = [
+        ("n_jobs", C.c_int32),
+        ("arrival_buffer", C.c_int32),
+        ("ticks_per_day", C.c_int32),
+        ("grace_ticks", C.c_int32),
+        ("absent_cutoff", C.c_int32),
+        ("absence_slack", C.c_int32),
+        ("attendance_window", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("late_tick_penalty", C.c_double),
+        ("absence_penalty", C.c_double),
+        ("job_start", C.c_int32 * TL_MAX_JOBS),
+        ("job_end", C.c_int32 * TL_MAX_JOBS),
+        ("job_has_location", C.c_int32 * TL_MAX_JOBS),
+        ("job_x", C.c_int32 * TL_MAX_JOBS),
+        ("job_y", C.c_int32 * TL_MAX_JOBS),
+        ("job_wage", C.c_double * TL_MAX_JOBS),
+        ("job_lateness_penalty", C.c_double * TL_MAX_JOBS),
+    ]
+
+
+EMPLOYMENT_STATE_FIELDS = (
+    ("job", 'i4', ()),
+    ("state", 'i4', ()),
+    ("current_day", 'i4', ()),
+    ("late_ticks", 'i4', ()),
+    ("ctx_flags", 'u4', ()),
+    ("shift_started_tick", 'i4', ()),
+    ("shift_end_tick", 'i4', ()),
+    ("last_present_tick", 'i4', ()),
+    ("scheduled_ticks", 'i4', ()),
+    ("on_time_ticks", 'i4', ()),
+    ("attendance_samples", 'f8', (TL_MAX_ATTENDANCE_WINDOW,)),
+    ("attendance_count", 'i4', ()),
+    ("absence_events", 'i4', (TL_MAX_ABSENCE_EVENTS,)),
+    ("absence_count", 'i4', ()),
+    ("late_ticks_today", 'i4', ()),
+    ("absent_shifts_7d", 'i4', ()),
+    ("wages_earned", 'i4', ()),
+)
+
+
+class TlEmploymentState(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _, _ in EMPLOYMENT_STATE_FIELDS] + [("town_origin", C.c_void_p)]
+
+
 TL_HOST_SLOTS = 4
 TL_WIRE = {"f32": 0, "u8": 1, "bits": 2}
 TL_MAP_F32, TL_MAP_WIRE = 0, 1
@@ -320,6 +372,7 @@ EXPORTED_SYMBOLS = (
     "tl_cast_pad_bf16_strided",
     "tl_sample_actions",
     "tl_policy_step",
+    "tl_employment_step",
     "tl_context_create",
     "tl_context_destroy",
     "tl_context_set_threads",
@@ -464,6 +517,8 @@ def load_library() -> C.CDLL:
     lib.tl_sample_actions.argtypes = [_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _p, C.c_int64, _p, _p, _p, _p]
     lib.tl_policy_step.restype = C.c_int
     lib.tl_policy_step.argtypes = [_p, C.c_int64, C.c_int64, C.POINTER(TlPolicyWeights), C.c_uint64, _p, C.c_int64, _p, _p, _p, _p, _p]
+    lib.tl_employment_step.restype = C.c_int
+    lib.tl_employment_step.argtypes = [C.POINTER(TlTownBatch), C.POINTER(TlEmploymentParams), C.POINTER(TlEmploymentState), _p, C.c_int32, C.c_int32, _p]
     lib.tl_context_create.restype = _p
     lib.tl_context_create.argtypes = [C.c_int]
     lib.tl_context_destroy.restype = None
@@ -505,7 +560,7 @@ def load_library() -> C.CDLL:
     lib.tl_context_last_d2h_bytes.argtypes = [_p]
     if lib.tl_abi_version() != TL_ABI_VERSION:
         raise TownletB200Error("libtownlet_b200.so ABI version mismatch")
-    for idx, struct in enumerate((TlTownBatch, TlObsParams, TlRewardParams, TlObsOut, TlRewardOut, TlDynamicsParams, TlHostStep, TlPolicyWeights)):
+    for idx, struct in enumerate((TlTownBatch, TlObsParams, TlRewardParams, TlObsOut, TlRewardOut, TlDynamicsParams, TlHostStep, TlPolicyWeights, TlEmploymentParams, TlEmploymentState)):
         if lib.tl_abi_struct_size(idx) != C.sizeof(struct):
             raise TownletB200Error(
                 f"struct layout mismatch for {struct.__name__}: C {lib.tl_abi_struct_size(idx)} vs ctypes {C.sizeof(struct)}"

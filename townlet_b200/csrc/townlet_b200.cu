@@ -830,6 +830,8 @@ int tl_abi_struct_size(int idx) {
         case 5: return (int)sizeof(TlDynamicsParams);
         case 6: return (int)sizeof(TlHostStep);
         case 7: return (int)sizeof(TlPolicyWeights);
+        case 8: return (int)sizeof(TlEmploymentParams);
+        case 9: return (int)sizeof(TlEmploymentState);
         default: return -1;
     }
 }
@@ -1026,3 +1028,4 @@ int tl_plan_grid(const TlPlan* plan, int32_t* grid, int32_t* threads, int32_t* s
 
 #include "host_path.cuh"
 #include "policy_mlp.cuh"
+#include "employment.cuh"
