@@ -129,6 +129,7 @@ def test_kernel_equals_oracle_on_random_towns_and_multi_tick_launches() -> None:
     ref_batch, ref_arrays = batch.copy(), arrays.copy()
     dev = DeviceTownBatch(batch, None, None)
     emp = DeviceEmployment(dev, spec, arrays)
+    seen_states, seen_events = set(), 0
     for step in range(40):  # positions change between launches; a launch steps 1-5 ticks
         n_ticks = int(rng.integers(1, 6))
         x, y = rng.choice([3, 7, 1], batch.n_agents), rng.choice([3, 2, 5], batch.n_agents)
@@ -139,9 +140,11 @@ def test_kernel_equals_oracle_on_random_towns_and_multi_tick_launches() -> None:
         ref_batch.town_tick[:] += n_ticks  # the tick kernel would advance it
         dev.field("town_tick").copy_(torch.from_numpy(ref_batch.town_tick))
         assert np.array_equal(events.cpu().numpy().view(np.uint32), want), step
+        seen_states |= set(np.unique(ref_arrays.state).tolist())
+        seen_events |= int(np.bitwise_or.reduce(want, axis=None))
     state, got = dev.download_state(full=True), emp.download()
     for name in ("wallet", "wages_withheld", "wages_paid", "punctuality", "attendance", "lateness", "flags"):
         assert np.array_equal(getattr(state, name), getattr(ref_batch, name)), name
     for name, _, _ in capi.EMPLOYMENT_STATE_FIELDS:
         assert np.array_equal(got.arrays[name], ref_arrays.arrays[name]), name
-    assert len(np.unique(got.state)) >= 5 and (got.attendance_count > 0).any() and (got.absence_count > 0).any()
+    assert len(seen_states) >= 5 and seen_events == 31 and (got.attendance_count > 0).any() and (got.absence_count > 0).any()
