@@ -1,0 +1,23 @@
+import torch, time, sys
+sys.path.insert(0, '.')
+from townlet_b200 import capi
+from townlet_b200.params import ObsSpec
+from townlet_b200.rollout import FusedPolicyWeights, PolicyMLP, policy_step
+obs = ObsSpec()
+torch.manual_seed(0)
+policy = PolicyMLP(obs.n_features, obs.map_shape, action_dim=9).cuda()
+w = FusedPolicyWeights(policy, torch.device("cuda"))
+n = 65536
+x = torch.zeros((n, 640), dtype=torch.bfloat16, device="cuda")
+x[:, :484] = (torch.rand((n, 484), device="cuda") < 0.05).to(torch.bfloat16)
+x[:, 512:593] = torch.randn((n, 81), device="cuda").to(torch.bfloat16)
+out = (torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, device="cuda"))
+for pair in (0, 1, 0, 1):
+    capi.set_option("policy_pair", pair)
+    for _ in range(5): policy_step(x, w, seed=1, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200): policy_step(x, w, seed=1, out=out)
+    e1.record(); torch.cuda.synchronize()
+    print("pair", pair, "us per step", e0.elapsed_time(e1) * 1e3 / 200)

@@ -22,9 +22,14 @@ def _reference_heads(x: "np.ndarray", w) -> "np.ndarray":
     return (h2 @ w.w_heads.double().t() + w.b_heads.double()).float()
 
 
+@pytest.mark.parametrize("pair", [False, True], ids=["cta", "cta-pair"])
 @pytest.mark.parametrize("n_rows", [128, 1000, 65536 + 77])
-def test_fused_policy_step_matches_the_network(n_rows) -> None:
+def test_fused_policy_step_matches_the_network(n_rows, pair, kernel_form) -> None:
     import torch
+
+    from townlet_b200 import capi
+
+    capi.set_option("policy_pair", 1 if pair else 0)  # tcgen05 cta_group::2 over a cluster of two CTAs (reset by the fixture)
 
     from oracle.oracle import oracle_sample_actions
     from townlet_b200.params import ObsSpec

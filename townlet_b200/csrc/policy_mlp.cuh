@@ -163,6 +163,47 @@ __device__ __forceinline__ void hidden_store32(unsigned char* h, int row, int n0
     }
 }
 
+// The heads accumulator of one row -> logits and value (+ bias), float32 log_softmax and the Gumbel-max sample of
+// sample_actions_kernel (same Philox draws), written to the rollout rows.
+__device__ __forceinline__ void policy_sample_row(const PolicyParams& p, long long r, const uint32_t (&hv)[16]) {
+    float x[TL_MAX_ACTIONS];
+    float top = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kPolHeads; ++j) {
+        const float v = __uint_as_float(hv[j]) + __ldg(p.b_heads + j);
+        if (p.heads_out) p.heads_out[r * kPolHeads + j] = v;
+        x[j] = j < p.n_actions ? v : -INFINITY;
+        top = fmaxf(top, x[j]);
+        if (j == p.n_actions && p.values) p.values[r] = v;
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kPolHeads; ++j) sum += j < p.n_actions ? expf(x[j] - top) : 0.0f;
+    const float lse = top + logf(sum);
+    const unsigned long long base = 4ull * (unsigned long long)((p.counter ? *p.counter : 0ll) + p.offset);
+    int best = 0;
+    float best_score = -INFINITY, best_logp = 0.0f;
+#pragma unroll
+    for (int d = 0; d < kPolHeads / 4; ++d) {
+        if (4 * d >= p.n_actions) break;
+        const unsigned long long c = base + d;
+        const uint4 bits = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)r, (uint32_t)((unsigned long long)r >> 32),
+                                         (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int j = 4 * d + l;
+            if (j >= p.n_actions) break;
+            const float u = ((float)(w[l] >> 9) + 0.5f) * 1.1920928955078125e-07f;
+            const float logp = x[j] - lse;
+            const float score = logp - logf(-logf(u));
+            if (score > best_score) best_score = score, best = j, best_logp = logp;
+        }
+    }
+    p.actions[r] = best;
+    p.log_probs[r] = best_logp;
+}
+
 __global__ void __launch_bounds__(kPolThreads, 1)
 policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wm, const __grid_constant__ CUtensorMap map_wf,
                   const __grid_constant__ CUtensorMap map_ws, const __grid_constant__ CUtensorMap map_wh, const PolicyParams p) {
@@ -305,49 +346,226 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             tmem_ld16(trow + kPolHidden, hv);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(d3_read);  // the next tile's encoders may overwrite the columns now
-            if (r < p.n_rows) {
-                float x[TL_MAX_ACTIONS];
-                float top = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < kPolHeads; ++j) {
-                    const float v = __uint_as_float(hv[j]) + __ldg(p.b_heads + j);
-                    if (p.heads_out) p.heads_out[r * kPolHeads + j] = v;
-                    x[j] = j < p.n_actions ? v : -INFINITY;
-                    top = fmaxf(top, x[j]);
-                    if (j == p.n_actions && p.values) p.values[r] = v;
-                }
-                float sum = 0.0f;
-#pragma unroll
-                for (int j = 0; j < kPolHeads; ++j) sum += j < p.n_actions ? expf(x[j] - top) : 0.0f;
-                const float lse = top + logf(sum);
-                const unsigned long long base = 4ull * (unsigned long long)((p.counter ? *p.counter : 0ll) + p.offset);
-                int best = 0;
-                float best_score = -INFINITY, best_logp = 0.0f;
-#pragma unroll
-                for (int d = 0; d < kPolHeads / 4; ++d) {
-                    if (4 * d >= p.n_actions) break;
-                    const unsigned long long c = base + d;
-                    const uint4 bits = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)r, (uint32_t)((unsigned long long)r >> 32),
-                                                     (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-                    const uint32_t w[4] = {bits.x, bits.y, bits.z, bits.w};
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) {
-                        const int j = 4 * d + l;
-                        if (j >= p.n_actions) break;
-                        const float u = ((float)(w[l] >> 9) + 0.5f) * 1.1920928955078125e-07f;
-                        const float logp = x[j] - lse;
-                        const float score = logp - logf(-logf(u));
-                        if (score > best_score) best_score = score, best = j, best_logp = logp;
-                    }
-                }
-                p.actions[r] = best;
-                p.log_probs[r] = best_logp;
-            }
+            if (r < p.n_rows) policy_sample_row(p, r, hv);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same step for a PAIR of CTAs (a cluster of two, tcgen05 cta_group::2): one MMA covers 256 agents — each CTA stages its
+// own 128 input rows and HALF of every weight chunk (128 of the 256 output rows), the tensor cores of both SMs read both
+// halves — so the weight bytes that cross from L2 per agent are halved (the single-CTA kernel waits on exactly those loads).
+// Each CTA keeps its own accumulators (its 128 rows) in its own tensor memory and its own H1 / H2 in its own shared memory;
+// the leader CTA (cluster rank 0) issues every MMA and commits to the barriers of both CTAs; both CTAs' TMA loads report to
+// the leader's `full` barrier; the peer's epilogue threads arrive on the leader's barriers across the cluster.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kPairStages = 6;
+constexpr int kPairBBytes = (kPolHidden / 2) * kPolKChunk * 2;  // 16 KB: this CTA's half of a weight chunk
+constexpr int kPairSmemH = kPairStages * kPairBBytes;           // the A stages alias the first six chunks of H
+constexpr int kPairSmemBar = kPairSmemH + kPolHBytes;
+constexpr int kPairSmemBytes = kPairSmemBar + 256 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t leader_addr(const void* local) {  // the same variable in the cluster's CTA 0
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(local)));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+    const uint32_t zero = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate), "r"(zero)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPolThreads, 1)
+policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wm,
+                       const __grid_constant__ CUtensorMap map_wf, const __grid_constant__ CUtensorMap map_ws,
+                       const __grid_constant__ CUtensorMap map_wh, const PolicyParams p) {
+    extern __shared__ unsigned char pol_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pol_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* s_b = smem;
+    unsigned char* s_h = smem + kPairSmemH;  // also the A stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairSmemBar);
+    uint64_t* full = bars;                        // [stages] leader: both CTAs' loads of the stage have landed
+    uint64_t* empty = bars + kPairStages;         // [stages] each CTA: the MMAs that read the stage are done
+    uint64_t* mma_done = bars + 2 * kPairStages;  // each CTA: a layer's accumulator is complete
+    uint64_t* h_ready = mma_done + 1;             // leader: both CTAs' epilogues have written the next A operand
+    uint64_t* d3_read = mma_done + 2;             // leader: both CTAs' epilogues have read the heads accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int n_pair_tiles = (int)((p.n_rows + 2 * kPolRows - 1) / (2 * kPolRows));
+    const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kPairStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
+        mbar_init(mma_done, 1);
+        mbar_init(h_ready, 2 * 32 * kPolEpiWarps);
+        mbar_init(d3_read, 2 * 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wm) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wf) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ws) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
+    }
+    if (warp == 1) {  // both CTAs, the same warp: the pair's tensor memory (all 512 columns of each SM)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // barriers of both CTAs are initialised before anything arrives on them across the cluster
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (one lane, both CTAs) =================
+        if (lane == 0) {
+            int it = 0;
+            for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride, ++it) {
+                const int row0 = pt * 2 * kPolRows + (int)rank * kPolRows;
+                for (int step = 0; step < kStepAll; ++step) {
+                    const int g = it * kStepAll + step, s = g % kPairStages;
+                    if (g >= kPairStages) mbar_wait(empty + s, ((g / kPairStages) - 1) & 1);
+                    unsigned char* b_dst = s_b + s * kPairBBytes;
+                    unsigned char* a_dst = s_h + s * kPolABytes;
+                    const uint32_t bar = leader_addr(full + s);
+                    const int half_row = (int)rank * (kPolHidden / 2);
+                    if (step < kStepEnc) {
+                        const bool is_map = step < kStepsMap;
+                        const int j = is_map ? step : step - kStepsMap;
+                        if (leader) mbar_expect_tx(full + s, 2 * (kPolABytes + kPairBBytes));
+                        tma_load_2d_pair(b_dst, is_map ? &map_wm : &map_wf, bar, j * kPolKChunk, half_row);
+                        if (step == 0 && it > 0) {
+                            // The A stages alias the hidden buffer: the previous tile's shared-layer and heads products must be
+                            // done reading it.  With six stages this lane can be ahead of the shared layer's completion, and a
+                            // parity wait must follow the barrier phase by phase, so both completions are waited for in order.
+                            mbar_wait(mma_done, (3 * (it - 1) + 1) & 1);
+                            mbar_wait(mma_done, (3 * (it - 1) + 2) & 1);
+                        }
+                        tma_load_2d_pair(a_dst, &map_x, bar, (is_map ? 0 : kPolMapK) + j * kPolKChunk, row0);
+                    } else if (step < kStepSh) {
+                        if (leader) mbar_expect_tx(full + s, 2 * kPairBBytes);
+                        tma_load_2d_pair(b_dst, &map_ws, bar, (step - kStepEnc) * kPolKChunk, half_row);
+                    } else {
+                        if (leader) mbar_expect_tx(full + s, 2 * (kPolHeads / 2) * kPolKChunk * 2);
+                        tma_load_2d_pair(b_dst, &map_wh, bar, (step - kStepSh) * kPolKChunk, (int)rank * (kPolHeads / 2));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one lane of the leader CTA) =================
+        if (leader && lane == 0) {
+            const uint32_t idesc_n256 = umma_idesc_bf16(2 * kPolRows, kPolHidden), idesc_n16 = umma_idesc_bf16(2 * kPolRows, kPolHeads);
+            int it = 0;
+            for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride, ++it) {
+                if (it > 0) {
+                    mbar_wait(d3_read, (it - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int step = 0; step < kStepAll; ++step) {
+                    const int g = it * kStepAll + step, s = g % kPairStages;
+                    if (step == kStepEnc || step == kStepSh) {
+                        mbar_wait(h_ready, (2 * it + (step == kStepEnc ? 0 : 1)) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    mbar_wait(full + s, (g / kPairStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t a_addr, d_col, idesc = idesc_n256;
+                    bool first;
+                    if (step < kStepsMap) a_addr = smem_u32(s_h + s * kPolABytes), d_col = 0, first = step == 0;
+                    else if (step < kStepEnc) a_addr = smem_u32(s_h + s * kPolABytes), d_col = kPolHidden, first = step == kStepsMap;
+                    else if (step < kStepSh) a_addr = smem_u32(s_h + (step - kStepEnc) * kPolABytes), d_col = 0, first = step == kStepEnc;
+                    else a_addr = smem_u32(s_h + (step - kStepSh) * kPolABytes), d_col = kPolHidden, first = step == kStepSh, idesc = idesc_n16;
+                    const uint32_t b_addr = smem_u32(s_b + s * kPairBBytes);
+#pragma unroll
+                    for (int k = 0; k < kPolKChunk / 16; ++k)
+                        umma_bf16_pair(tmem + d_col, umma_desc_k128(a_addr + 32 * k), umma_desc_k128(b_addr + 32 * k), idesc, !(first && k == 0));
+                    umma_commit_pair(empty + s);
+                    if (step == kStepEnc - 1 || step == kStepSh - 1 || step == kStepAll - 1) umma_commit_pair(mma_done);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue: warps 2-9 of both CTAs, one thread per row and column half =================
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = 32 * quarter + lane;
+        const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16);
+        const uint32_t h_ready_leader = leader_addr(h_ready), d3_read_leader = leader_addr(d3_read);
+        uint32_t acc[32];
+        int it = 0;
+        for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride, ++it) {
+            const long long r = (long long)pt * 2 * kPolRows + (long long)rank * kPolRows + row;
+            mbar_wait(mma_done, (3 * it) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int n0 = 256 * half; n0 < 256 * half + 256; n0 += 32) {
+                tmem_ld32(trow + n0, acc);
+                hidden_store32(s_h, row, n0, acc, p.b_enc);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> visible to the pair's MMA (async proxy)
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_cluster(h_ready_leader);
+            mbar_wait(mma_done, (3 * it + 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int n0 = 128 * half; n0 < 128 * half + 128; n0 += 32) {
+                tmem_ld32(trow + n0, acc);
+                hidden_store32(s_h, row, n0, acc, p.b_shared);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_cluster(h_ready_leader);
+            mbar_wait(mma_done, (3 * it + 2) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (half != 0) continue;
+            uint32_t hv[16];
+            tmem_ld16(trow + kPolHidden, hv);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive_cluster(d3_read_leader);
+            if (r < p.n_rows) policy_sample_row(p, r, hv);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs or remote arrivals may touch it
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
@@ -391,29 +609,41 @@ int tl_policy_step(const void* inputs, int64_t n_rows, int64_t input_row, const 
         return set_error("tl_policy_step: input rows are >= 640 bf16, a multiple of 8, 16-byte aligned"), TL_ERR_ARG;
     if (n_rows < 0 || offset < 0) return set_error("tl_policy_step: negative size"), TL_ERR_ARG;
     if (n_rows == 0) return TL_OK;
+    int device = 0;
+    if (!cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return TL_ERR_CUDA;
+    const DeviceInfo* di = device_info(device);
+    if (!di) return set_error("cudaDeviceGetAttribute failed"), TL_ERR_CUDA;
+    const bool pair = g_opt.policy_pair.load() != 0;  // CTA pairs (cta_group::2): half the weight bytes per agent
+    const uint32_t w_rows = pair ? kPolHidden / 2 : kPolHidden, h_rows = pair ? kPolHeads / 2 : kPolHeads;
     CUtensorMap mx, mwm, mwf, mws, mwh;
     if (!make_bf16_map(&mx, inputs, (uint64_t)n_rows, kPolMapK + kPolFeatK, (uint64_t)input_row, kPolRows) ||
-        !make_bf16_map(&mwm, w->w_map, kPolHidden, kPolMapK, kPolMapK, kPolHidden) ||
-        !make_bf16_map(&mwf, w->w_feat, kPolHidden, kPolFeatK, kPolFeatK, kPolHidden) ||
-        !make_bf16_map(&mws, w->w_shared, kPolHidden, 512, 512, kPolHidden) ||
-        !make_bf16_map(&mwh, w->w_heads, kPolHeads, kPolHidden, kPolHidden, kPolHeads))
+        !make_bf16_map(&mwm, w->w_map, kPolHidden, kPolMapK, kPolMapK, w_rows) ||
+        !make_bf16_map(&mwf, w->w_feat, kPolHidden, kPolFeatK, kPolFeatK, w_rows) ||
+        !make_bf16_map(&mws, w->w_shared, kPolHidden, 512, 512, w_rows) ||
+        !make_bf16_map(&mwh, w->w_heads, kPolHeads, kPolHidden, kPolHidden, h_rows))
         return TL_ERR_CUDA;
     static std::once_flag once;
     static cudaError_t attr_rc = cudaSuccess;
-    std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPolSmemBytes); });
+    std::call_once(once, [] {
+        attr_rc = cudaFuncSetAttribute(policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPolSmemBytes);
+        if (attr_rc == cudaSuccess) attr_rc = cudaFuncSetAttribute(policy_mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes);
+    });
     if (!cuda_ok(attr_rc, "cudaFuncSetAttribute(policy_mlp_kernel)")) return TL_ERR_CUDA;
     PolicyParams p;
     p.b_enc = w->b_enc, p.b_shared = w->b_shared, p.b_heads = w->b_heads;
     p.n_rows = n_rows, p.n_actions = w->n_actions, p.seed = seed, p.counter = (const long long*)counter, p.offset = offset;
     p.actions = (long long*)actions, p.log_probs = log_probs, p.values = values, p.heads_out = heads_out;
     // persistent CTAs, one per SM (a CTA takes the whole shared memory and tensor memory of its SM)
-    int device = 0;
-    if (!cuda_ok(cudaGetDevice(&device), "cudaGetDevice")) return TL_ERR_CUDA;
-    const DeviceInfo* di = device_info(device);
-    if (!di) return set_error("cudaDeviceGetAttribute failed"), TL_ERR_CUDA;
-    const long long n_tiles = (n_rows + kPolRows - 1) / kPolRows;
-    const unsigned grid = (unsigned)(n_tiles < di->sms ? n_tiles : di->sms);
-    policy_mlp_kernel<<<grid, kPolThreads, kPolSmemBytes, (cudaStream_t)stream>>>(mx, mwm, mwf, mws, mwh, p);
+    if (pair) {
+        const long long n_pairs = (n_rows + 2 * kPolRows - 1) / (2 * kPolRows);
+        const long long max_pairs = di->sms / 2;
+        const unsigned grid = 2u * (unsigned)(n_pairs < max_pairs ? n_pairs : max_pairs);
+        policy_mlp_pair_kernel<<<grid, kPolThreads, kPairSmemBytes, (cudaStream_t)stream>>>(mx, mwm, mwf, mws, mwh, p);
+    } else {
+        const long long n_tiles = (n_rows + kPolRows - 1) / kPolRows;
+        const unsigned grid = (unsigned)(n_tiles < di->sms ? n_tiles : di->sms);
+        policy_mlp_kernel<<<grid, kPolThreads, kPolSmemBytes, (cudaStream_t)stream>>>(mx, mwm, mwf, mws, mwh, p);
+    }
     if (!cuda_ok(cudaGetLastError(), "policy_mlp launch")) return TL_ERR_CUDA;
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return TL_OK;
