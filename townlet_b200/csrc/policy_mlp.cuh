@@ -25,6 +25,14 @@
 
 namespace {
 
+// -DTL_POLICY_TIMING: CTA 0 prints the cycles its first epilogue warp spends per tile waiting for each accumulator and
+// converting it (scripts/policy_step_bench.py with an instrumented build; never part of the shipped library)
+#ifdef TL_POLICY_TIMING
+#define POL_TIMING(...) __VA_ARGS__
+#else
+#define POL_TIMING(...)
+#endif
+
 constexpr int kPolRows = 128;        // agents per CTA (UMMA M)
 constexpr int kPolHidden = 256;      // hidden width (UMMA N of the encoder / shared products)
 constexpr int kPolMapK = 512;        // padded map columns
@@ -122,7 +130,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {  // arrives on the barrier when every MMA issued so far is done
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// issue only: the registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, "
@@ -132,7 +142,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
           "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -148,18 +157,38 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __device__ __forceinline__ void hidden_store32(unsigned char* h, int row, int n0, const uint32_t (&acc)[32], const float* __restrict__ bias) {
     unsigned char* chunk = h + (n0 >> 6) * kPolABytes + row * 128;
     const int unit0 = (n0 & 63) >> 3;
+    const float4* b4 = reinterpret_cast<const float4*>(bias + n0);  // every thread reads the same 32 floats: eight broadcast loads
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+        const float4 lo = __ldg(b4 + 2 * u), hi = __ldg(b4 + 2 * u + 1);
+        const float bv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int j = 8 * u + 2 * k;
-            const float a = fmaxf(__uint_as_float(acc[j]) + __ldg(bias + n0 + j), 0.0f);
-            const float b = fmaxf(__uint_as_float(acc[j + 1]) + __ldg(bias + n0 + j + 1), 0.0f);
+            const float a = fmaxf(__uint_as_float(acc[j]) + bv[2 * k], 0.0f);
+            const float b = fmaxf(__uint_as_float(acc[j + 1]) + bv[2 * k + 1], 0.0f);
             const __nv_bfloat162 pair = __floats2bfloat162_rn(a, b);
             w[k] = *reinterpret_cast<const uint32_t*>(&pair);
         }
         *reinterpret_cast<uint4*>(chunk + (((unit0 + u) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// A layer's accumulator columns [n_begin, n_end) of this thread's row -> hidden activations in shared memory, 32 columns at a
+// time, the tensor-memory load of the next 32 in flight while the current 32 are converted
+__device__ __forceinline__ void hidden_epilogue(unsigned char* h, int row, uint32_t trow, int n_begin, int n_end, const float* __restrict__ bias) {
+    uint32_t a0[32], a1[32];
+    tmem_ld32_issue(trow + n_begin, a0);
+    tmem_ld_wait();
+#pragma unroll 1
+    for (int n0 = n_begin; n0 < n_end; n0 += 64) {
+        tmem_ld32_issue(trow + n0 + 32, a1);  // (n_end - n_begin is a multiple of 64)
+        hidden_store32(h, row, n0, a0, bias);
+        tmem_ld_wait();
+        if (n0 + 64 < n_end) tmem_ld32_issue(trow + n0 + 64, a0);
+        hidden_store32(h, row, n0 + 32, a1, bias);
+        tmem_ld_wait();
     }
 }
 
@@ -311,35 +340,32 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int half = (warp - 2) >> 2;      // which half of a layer's columns
         const int row = 32 * quarter + lane;
         const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16);
-        uint32_t acc[32];
         int it = 0;
+        POL_TIMING(long long tw1 = 0, te1 = 0, tw2 = 0, te2 = 0, tw3 = 0, te3 = 0, tc = clock64(), tn;)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const long long r = (long long)tile * kPolRows + row;
             // layer 1: D1[:, 0:512] -> H1
             mbar_wait(mma_done, (3 * it) & 1);
+            POL_TIMING(tn = clock64(); tw1 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int n0 = 256 * half; n0 < 256 * half + 256; n0 += 32) {
-                tmem_ld32(trow + n0, acc);
-                hidden_store32(s_h, row, n0, acc, p.b_enc);
-            }
+            hidden_epilogue(s_h, row, trow, 256 * half, 256 * half + 256, p.b_enc);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(h_ready);
+            POL_TIMING(tn = clock64(); te1 += tn - tc; tc = tn;)
             // layer 2: D2[:, 0:256] -> H2 (the first four chunks of the same buffer; GEMM2 has finished reading H1)
             mbar_wait(mma_done, (3 * it + 1) & 1);
+            POL_TIMING(tn = clock64(); tw2 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int n0 = 128 * half; n0 < 128 * half + 128; n0 += 32) {
-                tmem_ld32(trow + n0, acc);
-                hidden_store32(s_h, row, n0, acc, p.b_shared);
-            }
+            hidden_epilogue(s_h, row, trow, 128 * half, 128 * half + 128, p.b_shared);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(h_ready);
+            POL_TIMING(tn = clock64(); te2 += tn - tc; tc = tn;)
             // layer 3: D3[:, 256:272] -> logits and value of this row, then the sampling step of sample_actions_kernel
             // (every epilogue thread follows every phase of the barrier: a parity wait must never fall two phases behind)
             mbar_wait(mma_done, (3 * it + 2) & 1);
+            POL_TIMING(tn = clock64(); tw3 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (half != 0) continue;  // one warp per quarter samples
             uint32_t hv[16];
@@ -347,7 +373,11 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(d3_read);  // the next tile's encoders may overwrite the columns now
             if (r < p.n_rows) policy_sample_row(p, r, hv);
+            POL_TIMING(tn = clock64(); te3 += tn - tc; tc = tn;)
         }
+        POL_TIMING(if (blockIdx.x == 0 && warp == 2 && lane == 0 && it > 0)
+                       printf("TL_POLICY_TIMING cycles per tile: wait-enc %lld epi-enc %lld wait-shared %lld epi-shared %lld wait-heads %lld sample %lld (%d tiles)\n",
+                              tw1 / it, te1 / it, tw2 / it, te2 / it, tw3 / it, te3 / it, it);)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -528,27 +558,18 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const int row = 32 * quarter + lane;
         const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16);
         const uint32_t h_ready_leader = leader_addr(h_ready), d3_read_leader = leader_addr(d3_read);
-        uint32_t acc[32];
         int it = 0;
         for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride, ++it) {
             const long long r = (long long)pt * 2 * kPolRows + (long long)rank * kPolRows + row;
             mbar_wait(mma_done, (3 * it) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int n0 = 256 * half; n0 < 256 * half + 256; n0 += 32) {
-                tmem_ld32(trow + n0, acc);
-                hidden_store32(s_h, row, n0, acc, p.b_enc);
-            }
+            hidden_epilogue(s_h, row, trow, 256 * half, 256 * half + 256, p.b_enc);
             asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> visible to the pair's MMA (async proxy)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive_cluster(h_ready_leader);
             mbar_wait(mma_done, (3 * it + 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int n0 = 128 * half; n0 < 128 * half + 128; n0 += 32) {
-                tmem_ld32(trow + n0, acc);
-                hidden_store32(s_h, row, n0, acc, p.b_shared);
-            }
+            hidden_epilogue(s_h, row, trow, 128 * half, 128 * half + 128, p.b_shared);
             asm volatile("fence.proxy.async;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive_cluster(h_ready_leader);
