@@ -244,7 +244,7 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint64_t* full = bars;                  // [stages] TMA landed
     uint64_t* empty = bars + kPolStages;    // [stages] MMAs that read the stage are done
     uint64_t* mma_done = bars + 2 * kPolStages;      // accumulator of a layer is complete (three times per tile)
-    uint64_t* h_ready = bars + 2 * kPolStages + 1;   // the epilogue has written the next A operand (twice per tile)
+    uint64_t* h_ready = bars + 2 * kPolStages + 1;   // the epilogue has written (half of) the next A operand (three times per tile)
     uint64_t* d3_read = bars + 2 * kPolStages + 2;   // the epilogue has read the heads accumulator (once per tile)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPolStages + 3);
 
@@ -313,8 +313,12 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 }
                 for (int step = 0; step < kStepAll; ++step) {
                     const int g = it * kStepAll + step, s = g % kPolStages;
-                    if (step == kStepEnc || step == kStepSh) {  // the A operand of this layer comes from the epilogue
-                        mbar_wait(h_ready, (2 * it + (step == kStepEnc ? 0 : 1)) & 1);
+                    if (step == kStepEnc || step == kStepEnc + kStepsShared / 2 || step == kStepSh) {
+                        // The A operand of this layer comes from the epilogue.  The shared layer starts on the map encoder's half
+                        // of H1 (its first four K chunks) while the epilogue still converts the feature encoder's half: the
+                        // accumulator D2 takes the columns of the half that has already been read.
+                        const int k = step == kStepEnc ? 0 : (step == kStepSh ? 2 : 1);
+                        mbar_wait(h_ready, (3 * it + k) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     mbar_wait(full + s, (g / kPolStages) & 1);
@@ -348,8 +352,12 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             mbar_wait(mma_done, (3 * it) & 1);
             POL_TIMING(tn = clock64(); tw1 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            hidden_epilogue(s_h, row, trow, 256 * half, 256 * half + 256, p.b_enc);
+            hidden_epilogue(s_h, row, trow, 128 * half, 128 * half + 128, p.b_enc);  // the map encoder's half first
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(h_ready);
+            hidden_epilogue(s_h, row, trow, 256 + 128 * half, 256 + 128 * half + 128, p.b_enc);  // under the shared layer's first MMAs
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(h_ready);
             POL_TIMING(tn = clock64(); te1 += tn - tc; tc = tn;)
