@@ -175,18 +175,19 @@ __device__ __forceinline__ void hidden_store32(unsigned char* h, int row, int n0
     }
 }
 
-// A layer's accumulator columns [n_begin, n_end) of this thread's row -> hidden activations in shared memory, 32 columns at a
-// time, the tensor-memory load of the next 32 in flight while the current 32 are converted
-__device__ __forceinline__ void hidden_epilogue(unsigned char* h, int row, uint32_t trow, int n_begin, int n_end, const float* __restrict__ bias) {
+// Hidden units [n_begin, n_end) of this thread's row: accumulator columns tcol .. (tcol = the tensor-memory address of unit
+// n_begin) -> hidden activations in shared memory, 32 at a time, the tensor-memory load of the next 32 in flight while the
+// current 32 are converted
+__device__ __forceinline__ void hidden_epilogue(unsigned char* h, int row, uint32_t tcol, int n_begin, int n_end, const float* __restrict__ bias) {
     uint32_t a0[32], a1[32];
-    tmem_ld32_issue(trow + n_begin, a0);
+    tmem_ld32_issue(tcol, a0);
     tmem_ld_wait();
 #pragma unroll 1
     for (int n0 = n_begin; n0 < n_end; n0 += 64) {
-        tmem_ld32_issue(trow + n0 + 32, a1);  // (n_end - n_begin is a multiple of 64)
+        tmem_ld32_issue(tcol + (n0 - n_begin) + 32, a1);  // (n_end - n_begin is a multiple of 64)
         hidden_store32(h, row, n0, a0, bias);
         tmem_ld_wait();
-        if (n0 + 64 < n_end) tmem_ld32_issue(trow + n0 + 64, a0);
+        if (n0 + 64 < n_end) tmem_ld32_issue(tcol + (n0 - n_begin) + 64, a0);
         hidden_store32(h, row, n0 + 32, a1, bias);
         tmem_ld_wait();
     }
@@ -250,6 +251,8 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (int)((p.n_rows + kPolRows - 1) / kPolRows);
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int n_local = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kPolStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
@@ -263,7 +266,7 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ws) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
     }
-    if (warp == 1) {  // the whole tensor memory: D1 needs all 512 columns
+    if (warp == 1) {  // the whole tensor memory: the two encoders' accumulators need all 512 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -272,70 +275,93 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
+    // The schedule both the TMA producer and the MMA issuer walk (one ring step each, in this order), software-pipelined over
+    // the tiles of the CTA so that the tensor pipe works on tile i + 1 while the epilogue warps convert and sample tile i:
+    //   ENC_A(0) ENC_B(0)   then per tile i:   SHARED(i)   ENC_A(i+1)   HEADS(i)   ENC_B(i+1)
+    // ENC_A = map encoder (8 K chunks), ENC_B = feature encoder (2), SHARED = shared layer (8), HEADS = policy + value heads (4).
+    // Accumulator columns ping-pong with the tile's parity: with P = 256 * (i & 1) and S = 256 - P,
+    //   ENC_A(i) -> [P, P+256)   ENC_B(i) -> [S, S+256)   SHARED(i) -> [P, P+256) (ENC_A's columns, already converted)
+    //   HEADS(i) -> [P, P+16) (SHARED's columns, already converted);   ENC_A(i+1) takes S as soon as ENC_B(i) is converted.
+    // The A stages of the encoders alias chunks 4-6 of the hidden buffer: free once SHARED(i) has read H1.
+    enum Seg { ENC_A, ENC_B, SHARED, HEADS };
+    auto a_stage = [&](int s) { return s_h + (4 + s) * kPolABytes; };
+
     if (warp == 0) {
         // ================= TMA producer (one lane) =================
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int row0 = tile * kPolRows;
-                for (int step = 0; step < kStepAll; ++step) {
-                    const int g = it * kStepAll + step, s = g % kPolStages;
+        if (lane == 0 && n_local > 0) {
+            int g = 0;  // ring step
+            auto segment = [&](Seg seg, int it) {
+                const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * kPolRows;
+                const int n_steps = seg == ENC_A ? kStepsMap : seg == ENC_B ? kStepsFeat : seg == SHARED ? kStepsShared : kStepsHeads;
+                for (int j = 0; j < n_steps; ++j, ++g) {
+                    const int s = g % kPolStages;
                     if (g >= kPolStages) mbar_wait(empty + s, ((g / kPolStages) - 1) & 1);
                     unsigned char* b_dst = s_b + s * kPolBBytes;
-                    unsigned char* a_dst = s_h + s * kPolABytes;
-                    if (step < kStepEnc) {
-                        const bool is_map = step < kStepsMap;
-                        const int j = is_map ? step : step - kStepsMap;
+                    if (seg == ENC_A || seg == ENC_B) {
                         mbar_expect_tx(full + s, kPolABytes + kPolBBytes);
-                        tma_load_2d(b_dst, is_map ? &map_wm : &map_wf, full + s, j * kPolKChunk, 0);
-                        // the A stages alias the hidden buffer: the previous tile's heads product must be done reading it
-                        if (step == 0 && it > 0) mbar_wait(mma_done, (3 * (it - 1) + 2) & 1);
-                        tma_load_2d(a_dst, &map_x, full + s, (is_map ? 0 : kPolMapK) + j * kPolKChunk, row0);
-                    } else if (step < kStepSh) {
+                        tma_load_2d(b_dst, seg == ENC_A ? &map_wm : &map_wf, full + s, j * kPolKChunk, 0);
+                        // the A stages alias the hidden buffer: the previous tile's shared layer must be done reading H1
+                        if (seg == ENC_A && j == 0 && it > 0) mbar_wait(mma_done, (3 * (it - 1) + 1) & 1);
+                        tma_load_2d(a_stage(s), &map_x, full + s, (seg == ENC_A ? 0 : kPolMapK) + j * kPolKChunk, row0);
+                    } else if (seg == SHARED) {
                         mbar_expect_tx(full + s, kPolBBytes);
-                        tma_load_2d(b_dst, &map_ws, full + s, (step - kStepEnc) * kPolKChunk, 0);
+                        tma_load_2d(b_dst, &map_ws, full + s, j * kPolKChunk, 0);
                     } else {
                         mbar_expect_tx(full + s, kPolHeads * kPolKChunk * 2);
-                        tma_load_2d(b_dst, &map_wh, full + s, (step - kStepSh) * kPolKChunk, 0);
+                        tma_load_2d(b_dst, &map_wh, full + s, j * kPolKChunk, 0);
                     }
                 }
+            };
+            segment(ENC_A, 0);
+            segment(ENC_B, 0);
+            for (int it = 0; it < n_local; ++it) {
+                segment(SHARED, it);
+                if (it + 1 < n_local) segment(ENC_A, it + 1);
+                segment(HEADS, it);
+                if (it + 1 < n_local) segment(ENC_B, it + 1);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one lane) =================
-        if (lane == 0) {
+        if (lane == 0 && n_local > 0) {
             const uint32_t idesc_n256 = umma_idesc_bf16(kPolRows, kPolHidden), idesc_n16 = umma_idesc_bf16(kPolRows, kPolHeads);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                if (it > 0) {  // the encoders' accumulator covers the columns of the previous tile's heads accumulator
+            int g = 0;
+            auto segment = [&](Seg seg, int it) {
+                const uint32_t P = 256u * (uint32_t)(it & 1), S = 256u - P;
+                const int n_steps = seg == ENC_A ? kStepsMap : seg == ENC_B ? kStepsFeat : seg == SHARED ? kStepsShared : kStepsHeads;
+                const uint32_t d_col = seg == ENC_B ? S : P;
+                const uint32_t idesc = seg == HEADS ? idesc_n16 : idesc_n256;
+                if (seg == ENC_B && it > 0) {  // these columns hold the previous tile's heads accumulator until it has been read
                     mbar_wait(d3_read, (it - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                for (int step = 0; step < kStepAll; ++step) {
-                    const int g = it * kStepAll + step, s = g % kPolStages;
-                    if (step == kStepEnc || step == kStepEnc + kStepsShared / 2 || step == kStepSh) {
-                        // The A operand of this layer comes from the epilogue.  The shared layer starts on the map encoder's half
-                        // of H1 (its first four K chunks) while the epilogue still converts the feature encoder's half: the
-                        // accumulator D2 takes the columns of the half that has already been read.
-                        const int k = step == kStepEnc ? 0 : (step == kStepSh ? 2 : 1);
+                for (int j = 0; j < n_steps; ++j, ++g) {
+                    const int s = g % kPolStages;
+                    // operands written by the epilogue: H1's map half before SHARED step 0, its feature half before step 4 (the
+                    // epilogue converts it under the first four steps), H2 before HEADS
+                    if ((seg == SHARED && (j == 0 || j == kStepsShared / 2)) || (seg == HEADS && j == 0)) {
+                        const int k = seg == HEADS ? 2 : (j == 0 ? 0 : 1);
                         mbar_wait(h_ready, (3 * it + k) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     mbar_wait(full + s, (g / kPolStages) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    uint32_t a_addr, d_col, idesc = idesc_n256;
-                    bool first;
-                    if (step < kStepsMap) a_addr = smem_u32(s_h + s * kPolABytes), d_col = 0, first = step == 0;
-                    else if (step < kStepEnc) a_addr = smem_u32(s_h + s * kPolABytes), d_col = kPolHidden, first = step == kStepsMap;
-                    else if (step < kStepSh) a_addr = smem_u32(s_h + (step - kStepEnc) * kPolABytes), d_col = 0, first = step == kStepEnc;
-                    else a_addr = smem_u32(s_h + (step - kStepSh) * kPolABytes), d_col = kPolHidden, first = step == kStepSh, idesc = idesc_n16;
+                    const uint32_t a_addr = (seg == ENC_A || seg == ENC_B) ? smem_u32(a_stage(s)) : smem_u32(s_h + j * kPolABytes);
                     const uint32_t b_addr = smem_u32(s_b + s * kPolBBytes);
 #pragma unroll
                     for (int k = 0; k < kPolKChunk / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes along the swizzled row
-                        umma_bf16(tmem + d_col, umma_desc_k128(a_addr + 32 * k), umma_desc_k128(b_addr + 32 * k), idesc, !(first && k == 0));
+                        umma_bf16(tmem + d_col, umma_desc_k128(a_addr + 32 * k), umma_desc_k128(b_addr + 32 * k), idesc, !(j == 0 && k == 0));
                     umma_commit(empty + s);
-                    if (step == kStepEnc - 1 || step == kStepSh - 1 || step == kStepAll - 1) umma_commit(mma_done);
                 }
+                if (seg != ENC_A) umma_commit(mma_done);  // completions per tile, in this order: encoders, shared layer, heads
+            };
+            segment(ENC_A, 0);
+            segment(ENC_B, 0);
+            for (int it = 0; it < n_local; ++it) {
+                segment(SHARED, it);
+                if (it + 1 < n_local) segment(ENC_A, it + 1);
+                segment(HEADS, it);
+                if (it + 1 < n_local) segment(ENC_B, it + 1);
             }
         }
     } else {
@@ -344,48 +370,55 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int half = (warp - 2) >> 2;      // which half of a layer's columns
         const int row = 32 * quarter + lane;
         const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16);
-        int it = 0;
+        uint32_t hv[16];           // the heads accumulator of the previous tile's row, sampled under the next tile's shared layer
+        long long pending_r = -1;  // (-1: nothing pending)
         POL_TIMING(long long tw1 = 0, te1 = 0, tw2 = 0, te2 = 0, tw3 = 0, te3 = 0, tc = clock64(), tn;)
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const long long r = (long long)tile * kPolRows + row;
-            // layer 1: D1[:, 0:512] -> H1
+        for (int it = 0; it < n_local; ++it) {
+            const uint32_t P = 256u * (uint32_t)(it & 1), S = 256u - P;
+            const long long r = (long long)((int)blockIdx.x + it * (int)gridDim.x) * kPolRows + row;
+            // encoders: map half [P, P+256) -> H1 chunks 0-3 first, then the feature half [S, S+256) -> chunks 4-7 (the shared
+            // layer's first MMAs run under the second conversion)
             mbar_wait(mma_done, (3 * it) & 1);
             POL_TIMING(tn = clock64(); tw1 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            hidden_epilogue(s_h, row, trow, 128 * half, 128 * half + 128, p.b_enc);  // the map encoder's half first
+            hidden_epilogue(s_h, row, trow + P + 128 * half, 128 * half, 128 * half + 128, p.b_enc);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(h_ready);
-            hidden_epilogue(s_h, row, trow, 256 + 128 * half, 256 + 128 * half + 128, p.b_enc);  // under the shared layer's first MMAs
+            hidden_epilogue(s_h, row, trow + S + 128 * half, 256 + 128 * half, 256 + 128 * half + 128, p.b_enc);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(h_ready);
             POL_TIMING(tn = clock64(); te1 += tn - tc; tc = tn;)
-            // layer 2: D2[:, 0:256] -> H2 (the first four chunks of the same buffer; GEMM2 has finished reading H1)
+            if (pending_r >= 0) {  // the previous tile's sample: its arithmetic hides under this tile's shared layer
+                if (pending_r < p.n_rows) policy_sample_row(p, pending_r, hv);
+                pending_r = -1;
+            }
+            POL_TIMING(tn = clock64(); te3 += tn - tc; tc = tn;)
+            // shared layer: [P, P+256) -> H2 (chunks 0-3 of the same buffer; the shared layer has finished reading H1)
             mbar_wait(mma_done, (3 * it + 1) & 1);
             POL_TIMING(tn = clock64(); tw2 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            hidden_epilogue(s_h, row, trow, 128 * half, 128 * half + 128, p.b_shared);
+            hidden_epilogue(s_h, row, trow + P + 128 * half, 128 * half, 128 * half + 128, p.b_shared);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(h_ready);
             POL_TIMING(tn = clock64(); te2 += tn - tc; tc = tn;)
-            // layer 3: D3[:, 256:272] -> logits and value of this row, then the sampling step of sample_actions_kernel
+            // heads: [P, P+16) -> registers; the next tile's feature encoder may overwrite the columns at once
             // (every epilogue thread follows every phase of the barrier: a parity wait must never fall two phases behind)
             mbar_wait(mma_done, (3 * it + 2) & 1);
             POL_TIMING(tn = clock64(); tw3 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (half != 0) continue;  // one warp per quarter samples
-            uint32_t hv[16];
-            tmem_ld16(trow + kPolHidden, hv);
+            tmem_ld16(trow + P, hv);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(d3_read);  // the next tile's encoders may overwrite the columns now
-            if (r < p.n_rows) policy_sample_row(p, r, hv);
-            POL_TIMING(tn = clock64(); te3 += tn - tc; tc = tn;)
+            mbar_arrive(d3_read);
+            pending_r = r;
         }
-        POL_TIMING(if (blockIdx.x == 0 && warp == 2 && lane == 0 && it > 0)
+        if (pending_r >= 0 && pending_r < p.n_rows) policy_sample_row(p, pending_r, hv);
+        POL_TIMING(if (blockIdx.x == 0 && warp == 2 && lane == 0 && n_local > 0)
                        printf("TL_POLICY_TIMING cycles per tile: wait-enc %lld epi-enc %lld wait-shared %lld epi-shared %lld wait-heads %lld sample %lld (%d tiles)\n",
-                              tw1 / it, te1 / it, tw2 / it, te2 / it, tw3 / it, te3 / it, it);)
+                              tw1 / n_local, te1 / n_local, tw2 / n_local, te2 / n_local, tw3 / n_local, te3 / n_local, n_local);)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -571,13 +604,13 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             const long long r = (long long)pt * 2 * kPolRows + (long long)rank * kPolRows + row;
             mbar_wait(mma_done, (3 * it) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            hidden_epilogue(s_h, row, trow, 256 * half, 256 * half + 256, p.b_enc);
+            hidden_epilogue(s_h, row, trow + 256 * half, 256 * half, 256 * half + 256, p.b_enc);
             asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> visible to the pair's MMA (async proxy)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive_cluster(h_ready_leader);
             mbar_wait(mma_done, (3 * it + 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            hidden_epilogue(s_h, row, trow, 128 * half, 128 * half + 128, p.b_shared);
+            hidden_epilogue(s_h, row, trow + 128 * half, 128 * half, 128 * half + 128, p.b_shared);
             asm volatile("fence.proxy.async;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive_cluster(h_ready_leader);
