@@ -166,10 +166,11 @@ __device__ __forceinline__ void hidden_store32(unsigned char* h, int row, int n0
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int j = 8 * u + 2 * k;
-            const float a = fmaxf(__uint_as_float(acc[j]) + bv[2 * k], 0.0f);
-            const float b = fmaxf(__uint_as_float(acc[j + 1]) + bv[2 * k + 1], 0.0f);
-            const __nv_bfloat162 pair = __floats2bfloat162_rn(a, b);
-            w[k] = *reinterpret_cast<const uint32_t*>(&pair);
+            // bias in float32, round the pair to bfloat16, ReLU on the packed pair: rounding is monotonic and keeps the sign,
+            // so max(round(x), 0) == round(max(x, 0)) — three instructions per pair instead of five
+            const __nv_bfloat162 pair = __floats2bfloat162_rn(__uint_as_float(acc[j]) + bv[2 * k], __uint_as_float(acc[j + 1]) + bv[2 * k + 1]);
+            const __nv_bfloat162 relu = __hmax2(pair, __float2bfloat162_rn(0.0f));
+            w[k] = *reinterpret_cast<const uint32_t*>(&relu);
         }
         *reinterpret_cast<uint4*>(chunk + (((unit0 + u) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
