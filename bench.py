@@ -5,11 +5,11 @@
     python bench.py --impl reference ...      # the CPU arm (oracle port, all host threads)
 
 A "step" is ONE TICK of the whole synthetic batch: need decay -> faint predicate -> reward -> observation build
-for every agent.  One launch advances K = ``--steps`` ticks (the kernel re-reads state and recomputes every output
-every tick; a multi-tick launch only amortises launch overhead).  The launch is PLANNED once (``tl_plan_create``)
-and then repeated back to back from one C call — ``reps`` launches, at least ``--min-launches`` (200) and at least
-``--min-seconds`` (0.1 s) of device time — so the timed region holds nothing but kernels: no Python, no ctypes
-struct building, no attribute queries between the two CUDA events.  Every tick writes its observation tensors to
+for every agent.  One launch advances a rollout segment of ticks (128 for configs[1]; the kernel re-reads state and
+recomputes every output every tick; a multi-tick launch only amortises launch overhead).  The launch is PLANNED once
+(``tl_plan_create``) and then repeated back to back from one C call — ``reps`` launches, at least ``--min-launches``
+(200), at least ``--min-seconds`` (0.1 s) of device time and at least the ``--steps K`` ticks asked for — so the timed
+region holds nothing but kernels: no Python, no ctypes struct building, no attribute queries between the two CUDA events.  Every tick writes its observation tensors to
 its own slot of an output ring of at least 1 GiB (8x the 126 MiB L2), so every output byte drains to HBM.
 
 Rank 0 prints ONE JSON line (README / DESIGN.md §5): the headline workload plus, under ``workloads``, the other
@@ -271,13 +271,17 @@ class Ranks:
 
 
 def ticks_per_launch_for(wl: dict, steps: int, override: int | None) -> int:
+    """Ticks one launch advances.  A launch is a rollout segment: 128 ticks for the configs[1]-sized batches (the rollout
+    length of configs[4]; configs[1] moves only ~22 MB per tick, so SURVEY's caveat asks for a multi-tick
+    launch), 8 for the large batches (0.3-0.6 GB of output per tick), 32-tick captured rollouts with the policy in the
+    loop.  `--steps K` is the number of ticks the caller asks to have timed: the timed region is at least that long (it
+    is in fact `reps` launches, >= 200 launches / >= 0.1 s); `--ticks-per-launch` overrides the segment length."""
+    del steps
     if override:
         return max(1, override)
-    # the larger batches write 0.3-0.6 GB per tick: keep their launches (and output rings) short
-    cap = 8 if wl["towns"] * wl["agents"] > 65536 else steps
     if wl.get("policy"):
-        cap = min(steps, 32)  # a rollout segment
-    return max(1, min(steps, cap))
+        return 32
+    return 8 if wl["towns"] * wl["agents"] > 65536 else 128
 
 
 def measure_tick_workload(key: str, args, ranks: Ranks, rank: int, sampler: ClockSampler | None, tpl: int, warm_ticks: int) -> dict:
@@ -317,7 +321,7 @@ def measure_tick_workload(key: str, args, ranks: Ranks, rank: int, sampler: Cloc
     e1.record()
     torch.cuda.synchronize()
     est_s = max(e0.elapsed_time(e1) * 1e-3 / 8, 1e-6)
-    reps = int(ranks.reduce_max(max(args.min_launches, math.ceil(1.1 * args.min_seconds / est_s))))
+    reps = int(ranks.reduce_max(max(args.min_launches, math.ceil(1.1 * args.min_seconds / est_s), -(-args.steps // tpl))))
 
     ranks.barrier()
     launches0 = lib.tl_launch_count()
@@ -417,7 +421,7 @@ def measure_policy_workload(key: str, args, ranks: Ranks, rank: int, sampler: Cl
     e1.record()
     torch.cuda.synchronize()
     est_s = max(e0.elapsed_time(e1) * 1e-3 / 2, 1e-6)
-    reps = int(ranks.reduce_max(max(8, math.ceil(1.1 * args.min_seconds / est_s))))
+    reps = int(ranks.reduce_max(max(8, math.ceil(1.1 * args.min_seconds / est_s), -(-args.steps // tpl))))
     ranks.barrier()
     t0 = time.perf_counter()
     e0.record()
@@ -587,11 +591,11 @@ def measure_e2e_world(res: dict, args, ranks: Ranks) -> dict:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20, help="K: ticks advanced by one launch (the timed region repeats the launch)")
+    ap.add_argument("--steps", type=int, default=20, help="K: ticks to time at least (the timed region is `reps` launches of a rollout segment, never shorter)")
     ap.add_argument("--warmup", type=int, default=5, help="W: untimed warm-up ticks (at least 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--ticks-per-launch", type=int, default=None, help="override: ticks per launch (default K, 8 for the large batches)")
+    ap.add_argument("--ticks-per-launch", type=int, default=None, help="override: ticks per launch (default 128; 8 for the large batches; 32-tick rollouts with the policy)")
     ap.add_argument("--min-launches", type=int, default=200, help="the timed region repeats the K-tick launch at least this often")
     ap.add_argument("--min-seconds", type=float, default=0.1, help="... and for at least this much device time")
     ap.add_argument("--e2e-steps", type=int, default=100)
@@ -696,7 +700,7 @@ def main() -> None:
             "value": res["value"],
             "unit": "agent-steps/s",
             "n_gpus": world,
-            "steps": res["tpl"],
+            "steps": args.steps,
             "warmup": warm,
             "ms_per_step": res["elapsed_ms"] / res["ticks"],
             "higher_is_better": True,
@@ -710,8 +714,9 @@ def main() -> None:
                 "reps": res["reps"],
                 "timed_ticks": res["ticks"],
                 "timed_region_s": res["elapsed_ms"] * 1e-3,
-                "how": "one planned launch of K ticks repeated `reps` times back to back by one C call between two CUDA events "
-                "on the launching stream; barrier + synchronize on both sides; max over ranks",
+                "how": "one planned launch of `ticks_per_launch` ticks repeated `reps` times back to back by one C call between two "
+                "CUDA events on the launching stream (timed_ticks >= the K steps asked for); barrier + synchronize on both sides; "
+                "max over ranks",
                 "output_ring_ticks": res["ring"],
                 "output_ring_mib": res["ring_bytes"] / 2**20,
                 "soa_state_mib": res["batch"].layout.total_bytes / 2**20,
