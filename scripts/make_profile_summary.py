@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parents[1]
 OUT = ROOT / "gpurun_out"
 PROF = ROOT / "profiles"
 PROF.mkdir(exist_ok=True)
-UNITS = {"c2": 20 * 8192, "c3-compact": 4 * 163840, "c3-full": 4 * 163840, "c4": 4 * 262144}
+UNITS = {"c2": 32 * 8192, "c3-compact": 4 * 163840, "c3-full": 4 * 163840, "c4": 4 * 262144}
 ALGO = {"c2": 2712, "c3-compact": 1756, "c3-full": 3680, "c4": 2712}
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0}
 
@@ -60,22 +60,22 @@ lines.append("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for row in table:
     lines.append("| %s | `%s` | %d | %.1f | %.1f | %.1f | %.0f | %d | %.0f | %.0f | %.1f | %.1f | %d | %.1f |" % row)
 lines.append("")
-lines.append("## Bench lines (default `python bench.py --workload W`, 8 192 ticks, 32 ticks per launch)")
+lines.append("## Bench lines (`python bench.py --gpus 1 --steps 20 --warmup 5`: the headline workload and, under `workloads`, the others)")
 lines.append("")
 lines.append("| workload | agent-steps/s | roofline frac | ms per tick | e2e agent-steps/s (host buffers) | CPU oracle agent-steps/s (cores) | SM MHz |")
 lines.append("|---|---|---|---|---|---|---|")
-for w in UNITS:
-    src = OUT / f"{TAG}_bench_{w}.json"
-    if not src.exists():
-        continue
+src = OUT / f"{TAG}_bench_c2.json"
+if src.exists():
     shutil.copy(src, PROF / src.name)
-    d = json.loads(src.read_text())
+    d = json.loads(src.read_text().strip().splitlines()[-1])
     cpu = d.get("cpu_baseline") or {}
     lines.append(
-        "| %s | %.4g | %.3f | %.5f | %.4g | %s | %s |"
-        % (w, d["value"], d["roofline"]["frac"], d["ms_per_step"], d["e2e"]["value"],
+        "| c2 (headline) | %.4g | %.3f | %.5f | %.4g | %s | %s |"
+        % (d["value"], d["roofline"]["frac"], d["ms_per_step"], d["e2e"]["value"],
            ("%.4g (%d)" % (cpu["value"], cpu["cores"])) if cpu else "-", d["clocks"]["sm_mhz"])
     )
+    for w, v in (d.get("workloads") or {}).items():
+        lines.append("| %s | %.4g | %.3f | %.5f | - | - | %s |" % (w, v["value"], v["roofline_frac"], v["ms_per_tick"], v.get("sm_mhz")))
 ref = OUT / f"{TAG}_bench_reference_c2.json"
 if ref.exists():
     shutil.copy(ref, PROF / ref.name)
