@@ -39,9 +39,10 @@
 #endif
 constexpr int kTileWarps = TL_TILE_WARPS;  // warps in the tiles role
 constexpr int kRoleWarps = 2 + kTileWarps;
+constexpr int kRoleCtas = 512 / (32 * kRoleWarps);  // resident CTAs per SM the register budget is set for (128 registers)
 
 template <int VARIANT, int WT, bool WORLD, bool MIRROR = false>
-__global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick_kernel_roles(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(32 * kRoleWarps, kRoleCtas) tick_kernel_roles(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);  // [2][chunk * F + 4]
     float* s_tmpl = reinterpret_cast<float*>(smem + p.off_map);
@@ -391,6 +392,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                 uint16_t* brow_g = (MIRROR && p.oo.map_bf16)
                                        ? p.oo.map_bf16 + (size_t)it * p.oo.map_bf16_tick_stride + (size_t)(c_begin + parity) * brow
                                        : nullptr;
+                constexpr bool kAlignedRows = kStatic && (kMapElems & 3) == 0;
+                const int map_mis0 = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
 #pragma unroll 1
                 for (int i = parity; i < c_n; i += kTileWarps, mrow_g += kTileWarps * map_elems, brow_g += (MIRROR && brow_g) ? kTileWarps * brow : 0) {
                     const int32_t pwi = __shfl_sync(FULL, pw, i);
@@ -411,7 +414,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                         for (int k = 0; k < kEntCache; ++k) wc[k] = ent_word(eb + 32 * k + lane);
                     }
                     // ---- template tile: 16-byte vectorised coalesced stores -------------
-                    const int map_mis = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
+                    // rows of a multiple of four floats all sit at the misalignment of the first one
+                    const int map_mis = kAlignedRows ? map_mis0 : (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
                     const int head = (4 - map_mis) & 3;
                     const int nvec = (map_elems - head) >> 2;
                     float4* g4 = reinterpret_cast<float4*>(mrow_g + head);
@@ -469,15 +473,13 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                         const bool is_agent = inwin && kind == TL_KIND_AGENT;
                         const bool is_obj = inwin && kind == TL_KIND_OBJECT && TL_ENT_TILE(w);
                         const bool is_res = inwin && kind == TL_KIND_RESERVED;
-                        // LocalSummary (map.py:88-103)
-                        n_ag += is_agent ? 1 : 0;
-                        n_obj += is_obj ? 1 : 0;
-                        n_res += is_res ? 1 : 0;
+                        // LocalSummary (map.py:88-103): one vote per count, so every lane holds the warp's totals
+                        n_ag += __popc(__ballot_sync(FULL, is_agent));
+                        n_obj += __popc(__ballot_sync(FULL, is_obj));
+                        n_res += __popc(__ballot_sync(FULL, is_res));
                         const int d2 = dx * dx + dy * dy;
-                        if (is_agent) {
-                            if (d2 == 0) centre_has = 1;
-                            else nearest = min(nearest, (unsigned)d2);
-                        }
+                        centre_has |= __ballot_sync(FULL, is_agent && d2 == 0) != 0u;
+                        if (is_agent && d2 != 0) nearest = min(nearest, (unsigned)d2);
                         if (VARIANT == TL_VARIANT_COMPACT) {
                             const bool is_other = is_agent && e != self_e;  // map.py:198
                             const bool norm = o.normalize_counts != 0;
@@ -522,20 +524,8 @@ __global__ void __launch_bounds__(32 * kRoleWarps, 512 / (32 * kRoleWarps)) tick
                             }
                         }
                     }
-                    // three warp reductions: packed counts (agents | objects << 10 | reserved << 20, each
-                    // below 1024 because a window holds fewer than 1024 entities), centre flag, nearest
-                    int counts, centre;
-                    if (ee - eb < 1024) {
-                        counts = __reduce_add_sync(FULL, n_ag | (n_obj << 10) | (n_res << 20));
-                        n_ag = counts & 1023;
-                        n_obj = (counts >> 10) & 1023;
-                        n_res = (counts >> 20) & 1023;
-                    } else {
-                        n_ag = __reduce_add_sync(FULL, n_ag);
-                        n_obj = __reduce_add_sync(FULL, n_obj);
-                        n_res = __reduce_add_sync(FULL, n_res);
-                    }
-                    centre = __reduce_or_sync(FULL, (unsigned)centre_has);
+                    // the counts are warp totals already (votes); the nearest distance needs one reduction
+                    const int centre = centre_has;
                     nearest = __reduce_min_sync(FULL, nearest);
                     if (lane == i) {
                         my_others = n_ag - centre;  // self excluded on the centre tile only
