@@ -154,13 +154,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 
 // 32 accumulator columns of one row -> + bias, ReLU, bf16 -> four 16-byte units of the row in the swizzled K-major
 // operand layout (unit c of row r sits at unit position c ^ (r & 7) of the row's 128 bytes)
+// (SMEM_BIAS: the bias vector is a shared-memory copy — the pair kernel's cluster-scope arrivals invalidate L1 all the time)
+template <bool SMEM_BIAS = false>
 __device__ __forceinline__ void hidden_store32(unsigned char* h, int row, int n0, const uint32_t (&acc)[32], const float* __restrict__ bias) {
     unsigned char* chunk = h + (n0 >> 6) * kPolABytes + row * 128;
     const int unit0 = (n0 & 63) >> 3;
     const float4* b4 = reinterpret_cast<const float4*>(bias + n0);  // every thread reads the same 32 floats: eight broadcast loads
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const float4 lo = __ldg(b4 + 2 * u), hi = __ldg(b4 + 2 * u + 1);
+        const float4 lo = SMEM_BIAS ? b4[2 * u] : __ldg(b4 + 2 * u), hi = SMEM_BIAS ? b4[2 * u + 1] : __ldg(b4 + 2 * u + 1);
         const float bv[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
         uint32_t w[4];
 #pragma unroll
@@ -179,6 +181,7 @@ __device__ __forceinline__ void hidden_store32(unsigned char* h, int row, int n0
 // Hidden units [n_begin, n_end) of this thread's row: accumulator columns tcol .. (tcol = the tensor-memory address of unit
 // n_begin) -> hidden activations in shared memory, 32 at a time, the tensor-memory load of the next 32 in flight while the
 // current 32 are converted
+template <bool SMEM_BIAS = false>
 __device__ __forceinline__ void hidden_epilogue(unsigned char* h, int row, uint32_t tcol, int n_begin, int n_end, const float* __restrict__ bias) {
     uint32_t a0[32], a1[32];
     tmem_ld32_issue(tcol, a0);
@@ -186,10 +189,10 @@ __device__ __forceinline__ void hidden_epilogue(unsigned char* h, int row, uint3
 #pragma unroll 1
     for (int n0 = n_begin; n0 < n_end; n0 += 64) {
         tmem_ld32_issue(tcol + (n0 - n_begin) + 32, a1);  // (n_end - n_begin is a multiple of 64)
-        hidden_store32(h, row, n0, a0, bias);
+        hidden_store32<SMEM_BIAS>(h, row, n0, a0, bias);
         tmem_ld_wait();
         if (n0 + 64 < n_end) tmem_ld32_issue(tcol + (n0 - n_begin) + 64, a0);
-        hidden_store32(h, row, n0 + 32, a1, bias);
+        hidden_store32<SMEM_BIAS>(h, row, n0 + 32, a1, bias);
         tmem_ld_wait();
     }
 }
@@ -327,13 +330,16 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (lane == 0 && n_local > 0) {
             const uint32_t idesc_n256 = umma_idesc_bf16(kPolRows, kPolHidden), idesc_n16 = umma_idesc_bf16(kPolRows, kPolHeads);
             int g = 0;
+            POL_TIMING(long long m_full = 0, m_h = 0, m_d3 = 0, m_t0 = clock64(), m_c;)
             auto segment = [&](Seg seg, int it) {
                 const uint32_t P = 256u * (uint32_t)(it & 1), S = 256u - P;
                 const int n_steps = seg == ENC_A ? kStepsMap : seg == ENC_B ? kStepsFeat : seg == SHARED ? kStepsShared : kStepsHeads;
                 const uint32_t d_col = seg == ENC_B ? S : P;
                 const uint32_t idesc = seg == HEADS ? idesc_n16 : idesc_n256;
                 if (seg == ENC_B && it > 0) {  // these columns hold the previous tile's heads accumulator until it has been read
+                    POL_TIMING(m_c = clock64();)
                     mbar_wait(d3_read, (it - 1) & 1);
+                    POL_TIMING(m_d3 += clock64() - m_c;)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 for (int j = 0; j < n_steps; ++j, ++g) {
@@ -342,10 +348,14 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     // epilogue converts it under the first four steps), H2 before HEADS
                     if ((seg == SHARED && (j == 0 || j == kStepsShared / 2)) || (seg == HEADS && j == 0)) {
                         const int k = seg == HEADS ? 2 : (j == 0 ? 0 : 1);
+                        POL_TIMING(m_c = clock64();)
                         mbar_wait(h_ready, (3 * it + k) & 1);
+                        POL_TIMING(m_h += clock64() - m_c;)
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
+                    POL_TIMING(m_c = clock64();)
                     mbar_wait(full + s, (g / kPolStages) & 1);
+                    POL_TIMING(m_full += clock64() - m_c;)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = (seg == ENC_A || seg == ENC_B) ? smem_u32(a_stage(s)) : smem_u32(s_h + j * kPolABytes);
                     const uint32_t b_addr = smem_u32(s_b + s * kPolBBytes);
@@ -364,6 +374,8 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 segment(HEADS, it);
                 if (it + 1 < n_local) segment(ENC_B, it + 1);
             }
+            POL_TIMING(if (blockIdx.x == 0) printf("TL_POLICY_TIMING MMA issuer cycles per tile: total %lld, waiting for TMA %lld, for the epilogue's operands %lld, for the heads read %lld\n",
+                                                   (clock64() - m_t0) / n_local, m_full / n_local, m_h / n_local, m_d3 / n_local);)
         }
     } else {
         // ================= epilogue: warps 2-9, one thread per row and column half =================
@@ -429,17 +441,22 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 // ---------------------------------------------------------------------------------------------------------------------
 // The same step for a PAIR of CTAs (a cluster of two, tcgen05 cta_group::2): one MMA covers 256 agents — each CTA stages its
 // own 128 input rows and HALF of every weight chunk (128 of the 256 output rows), the tensor cores of both SMs read both
-// halves — so the weight bytes that cross from L2 per agent are halved (the single-CTA kernel waits on exactly those loads).
+// halves — so the weight bytes that cross from L2 per agent are halved.  That is what bounds the single-CTA kernel: 744 KB
+// per tile per SM at the ~43 bytes per cycle per SM the L2 slices deliver chip-wide is the 17 k cycles per tile it
+// measures; a pair moves 452 KB per CTA and tile.  Same schedule, software-pipelined over the pair's tiles:
+//   ENC_A(0) ENC_B(0)   then per tile i:   SHARED(i)   ENC_A(i+1)   HEADS(i)   ENC_B(i+1)
 // Each CTA keeps its own accumulators (its 128 rows) in its own tensor memory and its own H1 / H2 in its own shared memory;
 // the leader CTA (cluster rank 0) issues every MMA and commits to the barriers of both CTAs; both CTAs' TMA loads report to
 // the leader's `full` barrier; the peer's epilogue threads arrive on the leader's barriers across the cluster.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kPairStages = 6;
+constexpr int kPairStages = 4;
 constexpr int kPairBBytes = (kPolHidden / 2) * kPolKChunk * 2;  // 16 KB: this CTA's half of a weight chunk
-constexpr int kPairSmemH = kPairStages * kPairBBytes;           // the A stages alias the first six chunks of H
+constexpr int kPairSmemH = kPairStages * kPairBBytes;           // the A stages alias chunks 4-7 of H
 constexpr int kPairSmemBar = kPairSmemH + kPolHBytes;
-constexpr int kPairSmemBytes = kPairSmemBar + 256 + 1024;
+constexpr int kPairSmemBias = kPairSmemBar + 256;               // encoder (512) and shared-layer (256) biases, float32
+constexpr int kPairSmemBytes = kPairSmemBias + (512 + kPolHidden) * 4 + 1024;
 
+#define PAIR_PROXY_FENCE() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -492,22 +509,24 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairSmemBar);
     uint64_t* full = bars;                        // [stages] leader: both CTAs' loads of the stage have landed
     uint64_t* empty = bars + kPairStages;         // [stages] each CTA: the MMAs that read the stage are done
-    uint64_t* mma_done = bars + 2 * kPairStages;  // each CTA: a layer's accumulator is complete
-    uint64_t* h_ready = mma_done + 1;             // leader: both CTAs' epilogues have written the next A operand
+    uint64_t* mma_done = bars + 2 * kPairStages;  // each CTA: a layer's accumulator is complete (three times per tile)
+    uint64_t* h_ready = mma_done + 1;             // leader: both CTAs' epilogues have written (half of) the next A operand
     uint64_t* d3_read = mma_done + 2;             // leader: both CTAs' epilogues have read the heads accumulator
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 3);
+    float* s_bias = reinterpret_cast<float*>(smem + kPairSmemBias);  // [0, 512) encoders, [512, 768) shared layer
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const bool leader = rank == 0;
     const int n_pair_tiles = (int)((p.n_rows + 2 * kPolRows - 1) / (2 * kPolRows));
     const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+    const int n_local = pair0 < n_pair_tiles ? (n_pair_tiles - 1 - pair0) / pair_stride + 1 : 0;  // tiles of this pair
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kPairStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
         mbar_init(mma_done, 1);
-        mbar_init(h_ready, 2 * 32 * kPolEpiWarps);
-        mbar_init(d3_read, 2 * 128);
+        mbar_init(h_ready, 2 * kPolEpiWarps);  // one elected lane per epilogue warp of either CTA
+        mbar_init(d3_read, 2 * 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wm) : "memory");
@@ -515,6 +534,7 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ws) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wh) : "memory");
     }
+    for (int i = threadIdx.x; i < 512 + kPolHidden; i += kPolThreads) s_bias[i] = i < 512 ? __ldg(p.b_enc + i) : __ldg(p.b_shared + i - 512);
     if (warp == 1) {  // both CTAs, the same warp: the pair's tensor memory (all 512 columns of each SM)
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -524,73 +544,88 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
+    // the schedule and the accumulator columns of policy_mlp_kernel (P = 256 * (i & 1), S = 256 - P)
+    enum Seg { ENC_A, ENC_B, SHARED, HEADS };
+    auto a_stage = [&](int s) { return s_h + (4 + s) * kPolABytes; };
+
     if (warp == 0) {
         // ================= TMA producer (one lane, both CTAs) =================
-        if (lane == 0) {
-            int it = 0;
-            for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride, ++it) {
-                const int row0 = pt * 2 * kPolRows + (int)rank * kPolRows;
-                for (int step = 0; step < kStepAll; ++step) {
-                    const int g = it * kStepAll + step, s = g % kPairStages;
+        if (lane == 0 && n_local > 0) {
+            int g = 0;  // ring step
+            const int half_row = (int)rank * (kPolHidden / 2);
+            auto segment = [&](Seg seg, int it) {
+                const int row0 = (pair0 + it * pair_stride) * 2 * kPolRows + (int)rank * kPolRows;
+                const int n_steps = seg == ENC_A ? kStepsMap : seg == ENC_B ? kStepsFeat : seg == SHARED ? kStepsShared : kStepsHeads;
+                for (int j = 0; j < n_steps; ++j, ++g) {
+                    const int s = g % kPairStages;
                     if (g >= kPairStages) mbar_wait(empty + s, ((g / kPairStages) - 1) & 1);
                     unsigned char* b_dst = s_b + s * kPairBBytes;
-                    unsigned char* a_dst = s_h + s * kPolABytes;
                     const uint32_t bar = leader_addr(full + s);
-                    const int half_row = (int)rank * (kPolHidden / 2);
-                    if (step < kStepEnc) {
-                        const bool is_map = step < kStepsMap;
-                        const int j = is_map ? step : step - kStepsMap;
+                    if (seg == ENC_A || seg == ENC_B) {
                         if (leader) mbar_expect_tx(full + s, 2 * (kPolABytes + kPairBBytes));
-                        tma_load_2d_pair(b_dst, is_map ? &map_wm : &map_wf, bar, j * kPolKChunk, half_row);
-                        if (step == 0 && it > 0) {
-                            // The A stages alias the hidden buffer: the previous tile's shared-layer and heads products must be
-                            // done reading it.  With six stages this lane can be ahead of the shared layer's completion, and a
-                            // parity wait must follow the barrier phase by phase, so both completions are waited for in order.
-                            mbar_wait(mma_done, (3 * (it - 1) + 1) & 1);
-                            mbar_wait(mma_done, (3 * (it - 1) + 2) & 1);
-                        }
-                        tma_load_2d_pair(a_dst, &map_x, bar, (is_map ? 0 : kPolMapK) + j * kPolKChunk, row0);
-                    } else if (step < kStepSh) {
+                        tma_load_2d_pair(b_dst, seg == ENC_A ? &map_wm : &map_wf, bar, j * kPolKChunk, half_row);
+                        // the A stages alias the hidden buffer: the previous tile's shared layer must be done reading H1 (four
+                        // stages keep this lane within one phase of that completion: its ring slot was freed by the shared
+                        // layer's fifth step)
+                        if (seg == ENC_A && j == 0 && it > 0) mbar_wait(mma_done, (3 * (it - 1) + 1) & 1);
+                        tma_load_2d_pair(a_stage(s), &map_x, bar, (seg == ENC_A ? 0 : kPolMapK) + j * kPolKChunk, row0);
+                    } else if (seg == SHARED) {
                         if (leader) mbar_expect_tx(full + s, 2 * kPairBBytes);
-                        tma_load_2d_pair(b_dst, &map_ws, bar, (step - kStepEnc) * kPolKChunk, half_row);
+                        tma_load_2d_pair(b_dst, &map_ws, bar, j * kPolKChunk, half_row);
                     } else {
                         if (leader) mbar_expect_tx(full + s, 2 * (kPolHeads / 2) * kPolKChunk * 2);
-                        tma_load_2d_pair(b_dst, &map_wh, bar, (step - kStepSh) * kPolKChunk, (int)rank * (kPolHeads / 2));
+                        tma_load_2d_pair(b_dst, &map_wh, bar, j * kPolKChunk, (int)rank * (kPolHeads / 2));
                     }
                 }
+            };
+            segment(ENC_A, 0);
+            segment(ENC_B, 0);
+            for (int it = 0; it < n_local; ++it) {
+                segment(SHARED, it);
+                if (it + 1 < n_local) segment(ENC_A, it + 1);
+                segment(HEADS, it);
+                if (it + 1 < n_local) segment(ENC_B, it + 1);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one lane of the leader CTA) =================
-        if (leader && lane == 0) {
+        if (leader && lane == 0 && n_local > 0) {
             const uint32_t idesc_n256 = umma_idesc_bf16(2 * kPolRows, kPolHidden), idesc_n16 = umma_idesc_bf16(2 * kPolRows, kPolHeads);
-            int it = 0;
-            for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride, ++it) {
-                if (it > 0) {
+            int g = 0;
+            auto segment = [&](Seg seg, int it) {
+                const uint32_t P = 256u * (uint32_t)(it & 1), S = 256u - P;
+                const int n_steps = seg == ENC_A ? kStepsMap : seg == ENC_B ? kStepsFeat : seg == SHARED ? kStepsShared : kStepsHeads;
+                const uint32_t d_col = seg == ENC_B ? S : P;
+                const uint32_t idesc = seg == HEADS ? idesc_n16 : idesc_n256;
+                if (seg == ENC_B && it > 0) {  // these columns hold the previous tile's heads accumulator until both CTAs have read it
                     mbar_wait(d3_read, (it - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                for (int step = 0; step < kStepAll; ++step) {
-                    const int g = it * kStepAll + step, s = g % kPairStages;
-                    if (step == kStepEnc || step == kStepSh) {
-                        mbar_wait(h_ready, (2 * it + (step == kStepEnc ? 0 : 1)) & 1);
+                for (int j = 0; j < n_steps; ++j, ++g) {
+                    const int s = g % kPairStages;
+                    if ((seg == SHARED && (j == 0 || j == kStepsShared / 2)) || (seg == HEADS && j == 0)) {
+                        const int k = seg == HEADS ? 2 : (j == 0 ? 0 : 1);
+                        mbar_wait(h_ready, (3 * it + k) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     mbar_wait(full + s, (g / kPairStages) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    uint32_t a_addr, d_col, idesc = idesc_n256;
-                    bool first;
-                    if (step < kStepsMap) a_addr = smem_u32(s_h + s * kPolABytes), d_col = 0, first = step == 0;
-                    else if (step < kStepEnc) a_addr = smem_u32(s_h + s * kPolABytes), d_col = kPolHidden, first = step == kStepsMap;
-                    else if (step < kStepSh) a_addr = smem_u32(s_h + (step - kStepEnc) * kPolABytes), d_col = 0, first = step == kStepEnc;
-                    else a_addr = smem_u32(s_h + (step - kStepSh) * kPolABytes), d_col = kPolHidden, first = step == kStepSh, idesc = idesc_n16;
+                    const uint32_t a_addr = (seg == ENC_A || seg == ENC_B) ? smem_u32(a_stage(s)) : smem_u32(s_h + j * kPolABytes);
                     const uint32_t b_addr = smem_u32(s_b + s * kPairBBytes);
 #pragma unroll
                     for (int k = 0; k < kPolKChunk / 16; ++k)
-                        umma_bf16_pair(tmem + d_col, umma_desc_k128(a_addr + 32 * k), umma_desc_k128(b_addr + 32 * k), idesc, !(first && k == 0));
+                        umma_bf16_pair(tmem + d_col, umma_desc_k128(a_addr + 32 * k), umma_desc_k128(b_addr + 32 * k), idesc, !(j == 0 && k == 0));
                     umma_commit_pair(empty + s);
-                    if (step == kStepEnc - 1 || step == kStepSh - 1 || step == kStepAll - 1) umma_commit_pair(mma_done);
                 }
+                if (seg != ENC_A) umma_commit_pair(mma_done);  // completions per tile, in this order: encoders, shared layer, heads
+            };
+            segment(ENC_A, 0);
+            segment(ENC_B, 0);
+            for (int it = 0; it < n_local; ++it) {
+                segment(SHARED, it);
+                if (it + 1 < n_local) segment(ENC_A, it + 1);
+                segment(HEADS, it);
+                if (it + 1 < n_local) segment(ENC_B, it + 1);
             }
         }
     } else {
@@ -600,30 +635,55 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const int row = 32 * quarter + lane;
         const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16);
         const uint32_t h_ready_leader = leader_addr(h_ready), d3_read_leader = leader_addr(d3_read);
-        int it = 0;
-        for (int pt = pair0; pt < n_pair_tiles; pt += pair_stride, ++it) {
-            const long long r = (long long)pt * 2 * kPolRows + (long long)rank * kPolRows + row;
+        uint32_t hv[16];           // the heads accumulator of the previous tile's row, sampled under the next tile's shared layer
+        long long pending_r = -1;  // (-1: nothing pending)
+        // This warp's part of an operand is written: every lane fences its generic-proxy stores towards the async proxy (the
+        // pair's MMA), the warp synchronises, ONE lane arrives on the leader's barrier.  A cluster-scope release invalidates
+        // L1; 512 of them per phase (one per thread) made every later global load of the epilogue miss.
+        auto arrive_warp = [&](uint32_t bar) {
+            PAIR_PROXY_FENCE();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar);
+        };
+        POL_TIMING(long long tw1 = 0, te1 = 0, tw2 = 0, te2 = 0, tw3 = 0, te3 = 0, tc = clock64(), tn;)
+        for (int it = 0; it < n_local; ++it) {
+            const uint32_t P = 256u * (uint32_t)(it & 1), S = 256u - P;
+            const long long r = (long long)(pair0 + it * pair_stride) * 2 * kPolRows + (long long)rank * kPolRows + row;
             mbar_wait(mma_done, (3 * it) & 1);
+            POL_TIMING(tn = clock64(); tw1 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            hidden_epilogue(s_h, row, trow + 256 * half, 256 * half, 256 * half + 256, p.b_enc);
-            asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores -> visible to the pair's MMA (async proxy)
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive_cluster(h_ready_leader);
+            hidden_epilogue<true>(s_h, row, trow + P + 128 * half, 128 * half, 128 * half + 128, s_bias);
+            arrive_warp(h_ready_leader);
+            hidden_epilogue<true>(s_h, row, trow + S + 128 * half, 256 + 128 * half, 256 + 128 * half + 128, s_bias);
+            arrive_warp(h_ready_leader);
+            POL_TIMING(tn = clock64(); te1 += tn - tc; tc = tn;)
+            if (pending_r >= 0) {  // the previous tile's sample: its arithmetic hides under this tile's shared layer
+                if (pending_r < p.n_rows) policy_sample_row(p, pending_r, hv);
+                pending_r = -1;
+            }
+            POL_TIMING(tn = clock64(); te3 += tn - tc; tc = tn;)
             mbar_wait(mma_done, (3 * it + 1) & 1);
+            POL_TIMING(tn = clock64(); tw2 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            hidden_epilogue(s_h, row, trow + 128 * half, 128 * half, 128 * half + 128, p.b_shared);
-            asm volatile("fence.proxy.async;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive_cluster(h_ready_leader);
+            hidden_epilogue<true>(s_h, row, trow + P + 128 * half, 128 * half, 128 * half + 128, s_bias + 512);
+            arrive_warp(h_ready_leader);
+            POL_TIMING(tn = clock64(); te2 += tn - tc; tc = tn;)
+            // (every epilogue thread follows every phase of the barrier: a parity wait must never fall two phases behind)
             mbar_wait(mma_done, (3 * it + 2) & 1);
+            POL_TIMING(tn = clock64(); tw3 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (half != 0) continue;
-            uint32_t hv[16];
-            tmem_ld16(trow + kPolHidden, hv);
+            if (half != 0) continue;  // one warp per quarter samples
+            tmem_ld16(trow + P, hv);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive_cluster(d3_read_leader);
-            if (r < p.n_rows) policy_sample_row(p, r, hv);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(d3_read_leader);
+            pending_r = r;
         }
+        if (pending_r >= 0 && pending_r < p.n_rows) policy_sample_row(p, pending_r, hv);
+        POL_TIMING(if (blockIdx.x < 2 && warp == 2 && lane == 0 && n_local > 0)
+                       printf("TL_POLICY_TIMING pair rank %u cycles per tile: wait-enc %lld epi-enc %lld wait-shared %lld epi-shared %lld wait-heads %lld sample %lld (%d tiles)\n",
+                              rank, tw1 / n_local, te1 / n_local, tw2 / n_local, te2 / n_local, tw3 / n_local, te3 / n_local, n_local);)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the pair's MMAs or remote arrivals may touch it
