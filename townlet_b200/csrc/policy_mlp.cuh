@@ -52,7 +52,10 @@ constexpr int kPolThreads = 64 + 32 * kPolEpiWarps;
 // pipeline steps: 8 map chunks, 2 feature chunks, 8 shared-layer chunks, 4 heads chunks
 constexpr int kStepsMap = kPolMapK / kPolKChunk, kStepsFeat = kPolFeatK / kPolKChunk;
 constexpr int kStepsShared = 512 / kPolKChunk, kStepsHeads = kPolHidden / kPolKChunk;
-constexpr int kStepEnc = kStepsMap + kStepsFeat, kStepSh = kStepEnc + kStepsShared, kStepAll = kStepSh + kStepsHeads;
+// Operand hand-offs from the epilogue to the MMA issuer per tile: H1's map half, H1's feature half, H2.  (Finer hand-offs do
+// not help: the shared layer accumulates into the map encoder's tensor-memory columns and cannot start before the epilogue
+// has read all 256 of them — tried, and it read stale accumulators.)
+constexpr int kHandoffs = 3;
 
 struct PolicyParams {
     const float* b_enc;     // [512]
@@ -249,9 +252,11 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     uint64_t* full = bars;                  // [stages] TMA landed
     uint64_t* empty = bars + kPolStages;    // [stages] MMAs that read the stage are done
     uint64_t* mma_done = bars + 2 * kPolStages;      // accumulator of a layer is complete (three times per tile)
-    uint64_t* h_ready = bars + 2 * kPolStages + 1;   // the epilogue has written (half of) the next A operand (three times per tile)
-    uint64_t* d3_read = bars + 2 * kPolStages + 2;   // the epilogue has read the heads accumulator (once per tile)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPolStages + 3);
+    // [kHandoffs] the epilogue has written a part of the next A operand.  One barrier per hand-off of a tile (each completes
+    // once per tile): with a single barrier a warp that ran one hand-off ahead would complete the phase of a slower warp.
+    uint64_t* h_ready = bars + 2 * kPolStages + 1;
+    uint64_t* d3_read = h_ready + kHandoffs;         // the epilogue has read the heads accumulator (once per tile)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d3_read + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (int)((p.n_rows + kPolRows - 1) / kPolRows);
@@ -261,7 +266,7 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kPolStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
         mbar_init(mma_done, 1);
-        mbar_init(h_ready, 32 * kPolEpiWarps);
+        for (int k = 0; k < kHandoffs; ++k) mbar_init(h_ready + k, 32 * kPolEpiWarps);
         mbar_init(d3_read, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -349,7 +354,7 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     if ((seg == SHARED && (j == 0 || j == kStepsShared / 2)) || (seg == HEADS && j == 0)) {
                         const int k = seg == HEADS ? 2 : (j == 0 ? 0 : 1);
                         POL_TIMING(m_c = clock64();)
-                        mbar_wait(h_ready, (3 * it + k) & 1);
+                        mbar_wait(h_ready + k, it & 1);
                         POL_TIMING(m_h += clock64() - m_c;)
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
@@ -394,14 +399,13 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             mbar_wait(mma_done, (3 * it) & 1);
             POL_TIMING(tn = clock64(); tw1 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            hidden_epilogue(s_h, row, trow + P + 128 * half, 128 * half, 128 * half + 128, p.b_enc);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(h_ready);
-            hidden_epilogue(s_h, row, trow + S + 128 * half, 256 + 128 * half, 256 + 128 * half + 128, p.b_enc);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(h_ready);
+            for (int q = 0; q < 2; ++q) {  // the map half, then the feature half: 128 columns per column half of the warps
+                const int n0 = 256 * q + 128 * half;
+                hidden_epilogue(s_h, row, trow + (q == 0 ? P : S) + 128 * half, n0, n0 + 128, p.b_enc);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(h_ready + q);
+            }
             POL_TIMING(tn = clock64(); te1 += tn - tc; tc = tn;)
             if (pending_r >= 0) {  // the previous tile's sample: its arithmetic hides under this tile's shared layer
                 if (pending_r < p.n_rows) policy_sample_row(p, pending_r, hv);
@@ -415,7 +419,7 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             hidden_epilogue(s_h, row, trow + P + 128 * half, 128 * half, 128 * half + 128, p.b_shared);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(h_ready);
+            mbar_arrive(h_ready + kHandoffs - 1);
             POL_TIMING(tn = clock64(); te2 += tn - tc; tc = tn;)
             // heads: [P, P+16) -> registers; the next tile's feature encoder may overwrite the columns at once
             // (every epilogue thread follows every phase of the barrier: a parity wait must never fall two phases behind)
@@ -454,7 +458,11 @@ constexpr int kPairBBytes = (kPolHidden / 2) * kPolKChunk * 2;  // 16 KB: this C
 constexpr int kPairSmemH = kPairStages * kPairBBytes;           // the A stages alias chunks 4-7 of H
 constexpr int kPairSmemBar = kPairSmemH + kPolHBytes;
 constexpr int kPairSmemBias = kPairSmemBar + 256;               // encoder (512) and shared-layer (256) biases, float32
-constexpr int kPairSmemBytes = kPairSmemBias + (512 + kPolHidden) * 4 + 1024;
+constexpr int kPairEarlyA = 1;                                  // the map encoder's first input chunk gets a buffer of its own
+constexpr int kPairSmemA = kPairSmemBias + (512 + kPolHidden) * 4 + 768;  // (1024-byte aligned)
+constexpr int kPairSmemBytes = kPairSmemA + kPairEarlyA * kPolABytes + 1024;
+static_assert(kPairSmemBytes <= 227 * 1024, "shared memory of one SM");
+static_assert(kPairSmemA % 1024 == 0, "swizzled operand tiles are 1024-byte aligned");
 
 #define PAIR_PROXY_FENCE() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -510,9 +518,11 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     uint64_t* full = bars;                        // [stages] leader: both CTAs' loads of the stage have landed
     uint64_t* empty = bars + kPairStages;         // [stages] each CTA: the MMAs that read the stage are done
     uint64_t* mma_done = bars + 2 * kPairStages;  // each CTA: a layer's accumulator is complete (three times per tile)
-    uint64_t* h_ready = mma_done + 1;             // leader: both CTAs' epilogues have written (half of) the next A operand
-    uint64_t* d3_read = mma_done + 2;             // leader: both CTAs' epilogues have read the heads accumulator
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 3);
+    uint64_t* h_local = mma_done + 1;             // [kHandoffs] each CTA: its own epilogue has written a part of the next A operand
+    uint64_t* d3_local = h_local + kHandoffs;     // each CTA: its own epilogue has read the heads accumulator
+    uint64_t* peer_h = d3_local + 1;              // [kHandoffs] leader: the peer's h_local phases, forwarded by the peer's relay lane
+    uint64_t* peer_d3 = peer_h + kHandoffs;       // leader: the peer's d3_local phase, forwarded likewise
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_d3 + 1);
     float* s_bias = reinterpret_cast<float*>(smem + kPairSmemBias);  // [0, 512) encoders, [512, 768) shared layer
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -525,8 +535,9 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kPairStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
         mbar_init(mma_done, 1);
-        mbar_init(h_ready, 2 * kPolEpiWarps);  // one elected lane per epilogue warp of either CTA
-        mbar_init(d3_read, 2 * 4);
+        for (int k = 0; k < kHandoffs; ++k) mbar_init(h_local + k, kPolEpiWarps), mbar_init(peer_h + k, 1);  // one elected lane per epilogue warp
+        mbar_init(d3_local, 4);
+        mbar_init(peer_d3, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wm) : "memory");
@@ -546,7 +557,11 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
 
     // the schedule and the accumulator columns of policy_mlp_kernel (P = 256 * (i & 1), S = 256 - P)
     enum Seg { ENC_A, ENC_B, SHARED, HEADS };
-    auto a_stage = [&](int s) { return s_h + (4 + s) * kPolABytes; };
+    // A stage of ring slot s: chunk 4 + s of the hidden buffer (free once the previous tile's shared layer has read H1) — except
+    // the first chunks of the map encoder, which have buffers of their own so that their loads run under that shared layer
+    // and the tensor pipe does not wait a load latency at every tile boundary
+    unsigned char* s_a_early = smem + kPairSmemA;
+    auto a_stage = [&](Seg seg, int j, int s) { return (seg == ENC_A && j < kPairEarlyA) ? s_a_early + j * kPolABytes : s_h + (4 + s) * kPolABytes; };
 
     if (warp == 0) {
         // ================= TMA producer (one lane, both CTAs) =================
@@ -564,11 +579,10 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                     if (seg == ENC_A || seg == ENC_B) {
                         if (leader) mbar_expect_tx(full + s, 2 * (kPolABytes + kPairBBytes));
                         tma_load_2d_pair(b_dst, seg == ENC_A ? &map_wm : &map_wf, bar, j * kPolKChunk, half_row);
-                        // the A stages alias the hidden buffer: the previous tile's shared layer must be done reading H1 (four
-                        // stages keep this lane within one phase of that completion: its ring slot was freed by the shared
-                        // layer's fifth step)
-                        if (seg == ENC_A && j == 0 && it > 0) mbar_wait(mma_done, (3 * (it - 1) + 1) & 1);
-                        tma_load_2d_pair(a_stage(s), &map_x, bar, (seg == ENC_A ? 0 : kPolMapK) + j * kPolKChunk, row0);
+                        // the aliased A stages: the previous tile's shared layer must be done reading H1 (four stages keep this
+                        // lane within one phase of that completion: its ring slot was freed by one of the shared layer's last steps)
+                        if (seg == ENC_A && j == kPairEarlyA && it > 0) mbar_wait(mma_done, (3 * (it - 1) + 1) & 1);
+                        tma_load_2d_pair(a_stage(seg, j, s), &map_x, bar, (seg == ENC_A ? 0 : kPolMapK) + j * kPolKChunk, row0);
                     } else if (seg == SHARED) {
                         if (leader) mbar_expect_tx(full + s, 2 * kPairBBytes);
                         tma_load_2d_pair(b_dst, &map_ws, bar, j * kPolKChunk, half_row);
@@ -592,25 +606,36 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         if (leader && lane == 0 && n_local > 0) {
             const uint32_t idesc_n256 = umma_idesc_bf16(2 * kPolRows, kPolHidden), idesc_n16 = umma_idesc_bf16(2 * kPolRows, kPolHeads);
             int g = 0;
+            POL_TIMING(long long m_full = 0, m_h = 0, m_d3 = 0, m_t0 = clock64(), m_c;)
             auto segment = [&](Seg seg, int it) {
                 const uint32_t P = 256u * (uint32_t)(it & 1), S = 256u - P;
                 const int n_steps = seg == ENC_A ? kStepsMap : seg == ENC_B ? kStepsFeat : seg == SHARED ? kStepsShared : kStepsHeads;
                 const uint32_t d_col = seg == ENC_B ? S : P;
                 const uint32_t idesc = seg == HEADS ? idesc_n16 : idesc_n256;
                 if (seg == ENC_B && it > 0) {  // these columns hold the previous tile's heads accumulator until both CTAs have read it
-                    mbar_wait(d3_read, (it - 1) & 1);
+                    POL_TIMING(m_c = clock64();)
+                    mbar_wait(d3_local, (it - 1) & 1);
+                    mbar_wait(peer_d3, (it - 1) & 1);
+                    POL_TIMING(m_d3 += clock64() - m_c;)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 for (int j = 0; j < n_steps; ++j, ++g) {
                     const int s = g % kPairStages;
+                    // operands written by the epilogue: H1's map half before SHARED step 0, its feature half before step 4 (the
+                    // epilogue converts it under the first four steps), H2 before HEADS
                     if ((seg == SHARED && (j == 0 || j == kStepsShared / 2)) || (seg == HEADS && j == 0)) {
                         const int k = seg == HEADS ? 2 : (j == 0 ? 0 : 1);
-                        mbar_wait(h_ready, (3 * it + k) & 1);
+                        POL_TIMING(m_c = clock64();)
+                        mbar_wait(h_local + k, it & 1);
+                        mbar_wait(peer_h + k, it & 1);
+                        POL_TIMING(m_h += clock64() - m_c;)
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
+                    POL_TIMING(m_c = clock64();)
                     mbar_wait(full + s, (g / kPairStages) & 1);
+                    POL_TIMING(m_full += clock64() - m_c;)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = (seg == ENC_A || seg == ENC_B) ? smem_u32(a_stage(s)) : smem_u32(s_h + j * kPolABytes);
+                    const uint32_t a_addr = (seg == ENC_A || seg == ENC_B) ? smem_u32(a_stage(seg, j, s)) : smem_u32(s_h + j * kPolABytes);
                     const uint32_t b_addr = smem_u32(s_b + s * kPairBBytes);
 #pragma unroll
                     for (int k = 0; k < kPolKChunk / 16; ++k)
@@ -627,6 +652,23 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 segment(HEADS, it);
                 if (it + 1 < n_local) segment(ENC_B, it + 1);
             }
+            POL_TIMING(if (blockIdx.x == 0) printf("TL_POLICY_TIMING pair MMA issuer cycles per tile: total %lld, waiting for TMA %lld, for the epilogues' operands %lld, for the heads reads %lld\n",
+                                                   (clock64() - m_t0) / n_local, m_full / n_local, m_h / n_local, m_d3 / n_local);)
+        } else if (!leader && lane == 0) {
+            // ================= relay (the same lane of the peer CTA, otherwise idle) =================
+            // The peer's epilogue warps arrive on their OWN CTA's barriers (CTA-scope release, cheap); this lane follows those
+            // phases and forwards each with one cluster-scope arrival on the leader's barrier.  A cluster-scope release is a
+            // membar that waits for the thread's outstanding global stores as well: executed by the epilogue warps (with the
+            // sampled actions still in flight) it cost them ~3 k cycles per tile.
+            const uint32_t peer_d3_leader = leader_addr(peer_d3);
+            for (int it = 0; it < n_local; ++it) {
+                for (int k = 0; k < kHandoffs; ++k) {
+                    mbar_wait(h_local + k, it & 1);
+                    mbar_arrive_cluster(leader_addr(peer_h + k));
+                }
+                mbar_wait(d3_local, it & 1);
+                mbar_arrive_cluster(peer_d3_leader);
+            }
         }
     } else {
         // ================= epilogue: warps 2-9 of both CTAs, one thread per row and column half =================
@@ -634,17 +676,15 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const int half = (warp - 2) >> 2;
         const int row = 32 * quarter + lane;
         const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16);
-        const uint32_t h_ready_leader = leader_addr(h_ready), d3_read_leader = leader_addr(d3_read);
         uint32_t hv[16];           // the heads accumulator of the previous tile's row, sampled under the next tile's shared layer
         long long pending_r = -1;  // (-1: nothing pending)
         // This warp's part of an operand is written: every lane fences its generic-proxy stores towards the async proxy (the
-        // pair's MMA), the warp synchronises, ONE lane arrives on the leader's barrier.  A cluster-scope release invalidates
-        // L1; 512 of them per phase (one per thread) made every later global load of the epilogue miss.
-        auto arrive_warp = [&](uint32_t bar) {
+        // pair's MMA), the warp synchronises, ONE lane arrives on this CTA's barrier.
+        auto arrive_warp = [&](uint64_t* bar) {
             PAIR_PROXY_FENCE();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(bar);
+            if (lane == 0) mbar_arrive(bar);
         };
         POL_TIMING(long long tw1 = 0, te1 = 0, tw2 = 0, te2 = 0, tw3 = 0, te3 = 0, tc = clock64(), tn;)
         for (int it = 0; it < n_local; ++it) {
@@ -653,10 +693,11 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             mbar_wait(mma_done, (3 * it) & 1);
             POL_TIMING(tn = clock64(); tw1 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            hidden_epilogue<true>(s_h, row, trow + P + 128 * half, 128 * half, 128 * half + 128, s_bias);
-            arrive_warp(h_ready_leader);
-            hidden_epilogue<true>(s_h, row, trow + S + 128 * half, 256 + 128 * half, 256 + 128 * half + 128, s_bias);
-            arrive_warp(h_ready_leader);
+            for (int q = 0; q < 2; ++q) {  // the map half, then the feature half: 128 columns per column half of the warps
+                const int n0 = 256 * q + 128 * half;
+                hidden_epilogue<true>(s_h, row, trow + (q == 0 ? P : S) + 128 * half, n0, n0 + 128, s_bias);
+                arrive_warp(h_local + q);
+            }
             POL_TIMING(tn = clock64(); te1 += tn - tc; tc = tn;)
             if (pending_r >= 0) {  // the previous tile's sample: its arithmetic hides under this tile's shared layer
                 if (pending_r < p.n_rows) policy_sample_row(p, pending_r, hv);
@@ -667,7 +708,7 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             POL_TIMING(tn = clock64(); tw2 += tn - tc; tc = tn;)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             hidden_epilogue<true>(s_h, row, trow + P + 128 * half, 128 * half, 128 * half + 128, s_bias + 512);
-            arrive_warp(h_ready_leader);
+            arrive_warp(h_local + kHandoffs - 1);
             POL_TIMING(tn = clock64(); te2 += tn - tc; tc = tn;)
             // (every epilogue thread follows every phase of the barrier: a parity wait must never fall two phases behind)
             mbar_wait(mma_done, (3 * it + 2) & 1);
@@ -677,7 +718,7 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             tmem_ld16(trow + P, hv);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(d3_read_leader);
+            if (lane == 0) mbar_arrive(d3_local);
             pending_r = r;
         }
         if (pending_r >= 0 && pending_r < p.n_rows) policy_sample_row(p, pending_r, hv);
