@@ -273,14 +273,14 @@ class Ranks:
 def ticks_per_launch_for(wl: dict, steps: int, override: int | None) -> int:
     """Ticks one launch advances.  A launch is a rollout segment: 128 ticks for the configs[1]-sized batches (the rollout
     length of configs[4]; configs[1] moves only ~22 MB per tick, so SURVEY's caveat asks for a multi-tick
-    launch), 8 for the large batches (0.3-0.6 GB of output per tick), 32-tick captured rollouts with the policy in the
-    loop.  `--steps K` is the number of ticks the caller asks to have timed: the timed region is at least that long (it
+    launch), 8 for the large batches (0.3-0.6 GB of output per tick), 128-tick captured rollouts with the policy in the
+    loop (configs[4]: one KPI exchange per 128-tick rollout).  `--steps K` is the number of ticks the caller asks to have timed: the timed region is at least that long (it
     is in fact `reps` launches, >= 200 launches / >= 0.1 s); `--ticks-per-launch` overrides the segment length."""
     del steps
     if override:
         return max(1, override)
     if wl.get("policy"):
-        return 32
+        return 128
     return 8 if wl["towns"] * wl["agents"] > 65536 else 128
 
 
@@ -595,7 +595,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5, help="W: untimed warm-up ticks (at least 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--ticks-per-launch", type=int, default=None, help="override: ticks per launch (default 128; 8 for the large batches; 32-tick rollouts with the policy)")
+    ap.add_argument("--ticks-per-launch", type=int, default=None, help="override: ticks per launch (default 128; 8 for the large batches)")
     ap.add_argument("--min-launches", type=int, default=200, help="the timed region repeats the K-tick launch at least this often")
     ap.add_argument("--min-seconds", type=float, default=0.1, help="... and for at least this much device time")
     ap.add_argument("--e2e-steps", type=int, default=100)
