@@ -603,12 +603,20 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the other configurations (`workloads`)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (kernel A/B runs)")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="a library switch for an A/B run (tl_set_option; defaults are the product configuration)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
 
     if args.impl == "reference":
         run_reference_arm(args, wl)
         return
+    if args.option:
+        from townlet_b200 import capi
+
+        for item in args.option:
+            name, _, value = item.partition("=")
+            capi.set_option(name, int(value))
 
     import torch
     import torch.distributed as dist
