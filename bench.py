@@ -48,11 +48,15 @@ WORKLOADS = {
     # configs[4] per GPU: 65,536 towns over 8 GPUs = 8,192 towns per rank, policy forward in the loop
     "c5": dict(variant="hybrid", towns=8192, grid=48, agents=8, bytes_per_agent_step=2712, policy=True,
                name="configs[4]: PPO rollout capture, 8,192 towns per GPU x 48x48 x 8 agents, policy forward in-loop"),
+    # configs[4] with the map kept ONCE, as the bfloat16 rows the policy reads (exact: its cells are 0 or 1) instead of a float32
+    # tensor plus those rows: 2 712 - 1 936 (float32 map) + 1 280 (the padded bfloat16 row of map and features) bytes per agent-step
+    "c5-bf16": dict(variant="hybrid", towns=8192, grid=48, agents=8, bytes_per_agent_step=2712 - 1936 + 1280, policy=True, map_bf16=True,
+                    name="configs[4], map observation stored as bfloat16 rows only: 8,192 towns per GPU x 48x48 x 8 agents, policy forward in-loop"),
     # configs[4] with the sampled actions applied by the next tick (moves) and ledger decay: the policy drives the world
     "c5-world": dict(variant="hybrid", towns=8192, grid=48, agents=8, bytes_per_agent_step=2712 + 24, policy=True, world=True,
                      name="configs[4] + the policy's actions applied on the device: 8,192 towns per GPU x 48x48 x 8 agents"),
 }
-EXTRA_WORKLOADS = ("c3-compact", "c3-full", "c4", "c5")  # measured beside the headline workload in the default run
+EXTRA_WORKLOADS = ("c3-compact", "c3-full", "c4", "c5", "c5-bf16")  # measured beside the headline workload in the default run
 L2_BYTES = 126 * 1024 * 1024
 RING_BYTES = 8 * L2_BYTES  # output ring: >= 8 x L2 (>= 1 GiB)
 DISTINCT_TOWNS = 256  # towns generated on the host; larger batches tile them
@@ -401,8 +405,9 @@ def measure_policy_workload(key: str, args, ranks: Ranks, rank: int, sampler: Cl
     dev = DeviceTownBatch(batch, obs, rew, ranks.device, dyn=dyn)
     n_agents = batch.n_agents
     torch.manual_seed(1234 + rank)
-    capture = RolloutCapture(dev, PolicyMLP(obs.n_features, obs.map_shape, action_dim=9), act_on_world=bool(wl.get("world")))
-    out = dev.alloc_outputs(capi.TL_PHASE_ALL, capture.slots_for(tpl), summary=False, comps=False, kpi=True)
+    capture = RolloutCapture(dev, PolicyMLP(obs.n_features, obs.map_shape, action_dim=9), act_on_world=bool(wl.get("world")),
+                             map_dtype="bf16" if wl.get("map_bf16") else "f32")
+    out = capture.alloc_outputs(tpl, summary=False, comps=False, kpi=True)
     before = lib.tl_launch_count()
     graphed = capture.build_graph(tpl, out)
     graph_launches = graphed.library_launches  # kernels of this library inside one replay (counted while capturing)

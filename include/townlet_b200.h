@@ -368,7 +368,10 @@ typedef struct TlRewardParams {
 
 /* Observation outputs.  Row strides are in elements; per-tick strides apply in tl_tick. */
 typedef struct TlObsOut {
-    float* map;        /* [N][C][W][W] */
+    float* map;        /* [N][C][W][W]; may be NULL when map_bf16 is given and the kernel writes that row itself (entity
+                          form, hybrid variant, window 11): the map is then delivered once, as bfloat16 — exact, its cells
+                          are 0 or 1 — which takes 1 936 of the 3 992 bytes per agent-step off a rollout with the policy in
+                          the loop; any other form answers TL_ERR_UNSUPPORTED */
     float* features;   /* [N][F] */
     int32_t* summary;  /* [N][TL_N_SUMMARY]; may be NULL */
     int64_t map_tick_stride;      /* elements between consecutive ticks (0 = overwrite) */

@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(32 * kRoleWarps, kRoleCtas) tick_kernel_roles(
                                        ? p.oo.map_bf16 + (size_t)it * p.oo.map_bf16_tick_stride + (size_t)(c_begin + parity) * brow
                                        : nullptr;
                 constexpr bool kAlignedRows = kStatic && (kMapElems & 3) == 0;
+                const bool f32_map = !MIRROR || p.oo.map != nullptr;  // (MIRROR: the float32 tile is optional)
                 const int map_mis0 = (int)((reinterpret_cast<uintptr_t>(mrow_g) >> 2) & 3);
 #pragma unroll 1
                 for (int i = parity; i < c_n; i += kTileWarps, mrow_g += kTileWarps * map_elems, brow_g += (MIRROR && brow_g) ? kTileWarps * brow : 0) {
@@ -419,7 +420,9 @@ __global__ void __launch_bounds__(32 * kRoleWarps, kRoleCtas) tick_kernel_roles(
                     const int head = (4 - map_mis) & 3;
                     const int nvec = (map_elems - head) >> 2;
                     float4* g4 = reinterpret_cast<float4*>(mrow_g + head);
-                    if (kStatic && VARIANT == TL_VARIANT_HYBRID && map_mis == 0) {
+                    if (MIRROR && !f32_map) {
+                        // the map is delivered as its bfloat16 row only (TlObsOut.map == NULL)
+                    } else if (kStatic && VARIANT == TL_VARIANT_HYBRID && map_mis == 0) {
                         // all zeros except the self cell: flat float centre_tile (60 for W = 11) sits in
                         // float4 number 15, component 0, which lane 15 writes in its first store
                         static_assert(!kStatic || VARIANT != TL_VARIANT_HYBRID || (((WT / 2) * WT + WT / 2) & 3) == 0, "self cell component");
@@ -499,9 +502,11 @@ __global__ void __launch_bounds__(32 * kRoleWarps, kRoleCtas) tick_kernel_roles(
                             if (is_res) mrow_g[3 * W2 + tile] = 1.0f;
                             if (is_other || is_obj || is_res) mrow_g[walk_off + tile] = 0.0f;
                         } else {
-                            if (is_agent) mrow_g[W2 + tile] = 1.0f;  // includes the observer (map.py:109-110)
-                            if (is_obj) mrow_g[2 * W2 + tile] = 1.0f;
-                            if (is_res) mrow_g[3 * W2 + tile] = 1.0f;
+                            if (!MIRROR || f32_map) {
+                                if (is_agent) mrow_g[W2 + tile] = 1.0f;  // includes the observer (map.py:109-110)
+                                if (is_obj) mrow_g[2 * W2 + tile] = 1.0f;
+                                if (is_res) mrow_g[3 * W2 + tile] = 1.0f;
+                            }
                             if (MIRROR && brow_g) {
                                 if (is_agent) brow_g[W2 + tile] = 0x3f80;
                                 if (is_obj) brow_g[2 * W2 + tile] = 0x3f80;

@@ -463,7 +463,8 @@ int validate(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams*
         if (!obs) return set_error("observation params are NULL"), TL_ERR_ARG;
     }
     if (phases & TL_PHASE_OBS) {
-        if (!oo || !oo->map || !oo->features) return set_error("observation outputs are NULL"), TL_ERR_ARG;
+        // (map may be NULL when map_bf16 is given and the kernel writes the mirror itself: checked once the form is known)
+        if (!oo || !oo->features || (!oo->map && !oo->map_bf16)) return set_error("observation outputs are NULL"), TL_ERR_ARG;
         if (obs->variant < 0 || obs->variant > 2) return set_error("unknown variant"), TL_ERR_ARG;
         if (obs->window < 3 || obs->window > TL_MAX_WINDOW || !(obs->window & 1))
             return set_error("window must be odd and in 3..21"), TL_ERR_ARG;
@@ -760,6 +761,8 @@ int prepare(const TlTownBatch* b, const TlObsParams* obs, const TlRewardParams* 
     };
     rc = dispatch();
     if (rc != TL_OK) return rc;
+    if (do_obs && !oo->map && !mirror_in_kernel)
+        return set_error("map may be NULL only where the kernel writes map_bf16 itself (entity form, hybrid, window 11)"), TL_ERR_UNSUPPORTED;
     lp.cast_after = want_mirror && !mirror_in_kernel;
     return TL_OK;
 }

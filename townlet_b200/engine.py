@@ -174,12 +174,16 @@ class DeviceTownBatch:
         kpi: bool = True,
         reward: bool = True,
         terminated: bool = True,
+        map_f32: bool = True,
     ) -> TickOutputs:
+        """``map_f32=False`` leaves ``out.map`` unset: the caller supplies ``map_bf16`` rows and the map is delivered as
+        bfloat16 only (``TlObsOut.map == NULL``)."""
         out = TickOutputs()
         n, t, dev = self.n_agents, self.n_towns, self.device
         if phases & capi.TL_PHASE_OBS:
             assert self.obs is not None
-            out.map = torch.empty((n_ticks, n, *self.obs.map_shape), dtype=torch.float32, device=dev)
+            if map_f32:
+                out.map = torch.empty((n_ticks, n, *self.obs.map_shape), dtype=torch.float32, device=dev)
             out.features = torch.empty((n_ticks, n, self.obs.n_features), dtype=torch.float32, device=dev)
             if summary:
                 out.summary = torch.empty((n_ticks, n, capi.TL_N_SUMMARY), dtype=torch.int32, device=dev)

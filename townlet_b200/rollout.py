@@ -15,6 +15,7 @@ device; otherwise action application stays with the caller and the actions are o
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass
 
 import torch
@@ -301,6 +302,7 @@ class Rollout:
         elif bootstrap != "value":
             raise ValueError("bootstrap must be 'value' or 'repeat'")
         return {
+            # (a bfloat16 map — RolloutCapture(map_dtype="bf16") — is flat [T, N, C*W*W]; callers reshape with the spec's map_shape)
             "maps": agent_major(self.map.float()),
             "features": agent_major(self.features.float()),
             "actions": agent_major(self.actions.long()).astype(np.int64),
@@ -354,8 +356,16 @@ class RolloutCapture:
     ACTION_DY = (0, -1, 1, 0, 0)
 
     def __init__(self, dev: DeviceTownBatch, policy: nn.Module, gamma: float = 0.99, gae_lambda: float = 0.95,
-                 autocast_dtype: torch.dtype | None = torch.bfloat16, act_on_world: bool = False) -> None:
+                 autocast_dtype: torch.dtype | None = torch.bfloat16, act_on_world: bool = False, map_dtype: str = "f32") -> None:
+        """``map_dtype="bf16"``: the rollout keeps the map observation ONCE, as the bfloat16 rows the policy reads (exact: the
+        hybrid map's cells are 0 or 1), instead of a float32 tensor plus that mirror — 2 056 instead of 3 992 bytes written
+        per agent-step.  Needs the fused policy step (bfloat16 ``PolicyMLP``); ``alloc_outputs`` then allocates no ``map``
+        and ``Rollout.map`` is a bfloat16 ``[T, N, C·W·W]`` view (``replay_batch`` casts it back, exactly)."""
         assert dev.obs is not None and dev.rew is not None
+        if map_dtype not in ("f32", "bf16"):
+            raise ValueError("map_dtype must be 'f32' or 'bf16'")
+        self.map_dtype = map_dtype
+        self._ring: torch.Tensor | None = None  # map_dtype="bf16": [slots, N, padded row] bfloat16, one row set per tick slot
         self.dev = dev
         self.policy = policy.to(dev.device).eval()
         self.gamma, self.gae_lambda = gamma, gae_lambda
@@ -384,6 +394,18 @@ class RolloutCapture:
         """Tick slots the output tensors of a capture of ``n_ticks`` steps need (one more observation than steps)."""
         return n_ticks + 1
 
+    def alloc_outputs(self, n_ticks: int, **kwargs) -> TickOutputs:
+        """Output tensors for captures of ``n_ticks`` steps (without a float32 map when ``map_dtype="bf16"``)."""
+        return self.dev.alloc_outputs(capi.TL_PHASE_ALL, self.slots_for(n_ticks), map_f32=self.map_dtype == "f32", **kwargs)
+
+    def _rows_ring(self, slots: int) -> torch.Tensor:
+        """``map_dtype="bf16"``: the combined bfloat16 input rows of every tick slot (the rollout's map observation)."""
+        if self._mirror() is None or self._fused_policy() is None:
+            raise capi.TownletB200Error("map_dtype='bf16' needs the bfloat16 PolicyMLP and the fused policy step")
+        if self._ring is None or self._ring.shape[0] < slots:
+            self._ring = torch.zeros((slots, *self._inputs_bf16.shape), dtype=torch.bfloat16, device=self.dev.device)
+        return self._ring
+
     def describe(self) -> dict:
         """What the policy step is made of (for the bench record)."""
         fused = isinstance(self.policy, PolicyMLP) and self.autocast_dtype == torch.bfloat16 and self.fuse_map_cast
@@ -391,6 +413,8 @@ class RolloutCapture:
             "network": "ConflictAwarePolicyNetwork shape (policy/models.py:36-69): map / feature encoders 256, shared 256, 9 logits + value",
             "arithmetic": "bfloat16 inputs and weights, float32 accumulation" if self.autocast_dtype == torch.bfloat16 else "float32",
             "inputs": "bfloat16 rows written by the tick kernel" if fused else "float32 observation cast by the policy step",
+            "map_delivery": "bfloat16 rows only (exact for the 0/1 map), features float32 + bfloat16" if self.map_dtype == "bf16"
+            else "float32 tensor + bfloat16 rows for the policy",
             "sampling": "tl_sample_actions (one kernel: log_softmax + Gumbel-max + gather)" if self.fuse_sampling else "torch ops",
             "kernel": "tl_policy_step: one tcgen05 kernel per tick (TMA operands, TMEM accumulators, activations in shared memory, "
             "sampling in the epilogue)" if (fused and self._fused_policy() is not None) else "three cuBLASLt products",
@@ -454,7 +478,8 @@ class RolloutCapture:
         if fused is not None:
             # the whole step — encoders, shared layer, heads, log_softmax, sample — in one tcgen05 kernel reading the rows the
             # tick kernel just wrote
-            act = policy_step(self._inputs_bf16, fused, self.seed, self._draws, draw, out=(actions[slot], log_probs[slot], values[slot]))[0]
+            rows_in = self._ring[slot] if self.map_dtype == "bf16" else self._inputs_bf16
+            act = policy_step(rows_in, fused, self.seed, self._draws, draw, out=(actions[slot], log_probs[slot], values[slot]))[0]
         elif self.fuse_sampling and mirror is not None:
             # bfloat16 PolicyMLP: one kernel reads the fused heads product and writes action, log-prob and value
             # straight into the rollout rows
@@ -490,9 +515,18 @@ class RolloutCapture:
     def _with_mirrors(self, out: TickOutputs):
         mirror = self._mirror()
         saved = (out.map_bf16, out.features_bf16)
+        if self.map_dtype == "bf16":  # one set of rows per tick slot: they ARE the stored map observation
+            ring = self._rows_ring(out.features.shape[0])
+            pm = self._map_bf16.shape[1]
+            out.map_bf16, out.features_bf16 = ring[:, :, :pm], ring[:, :, pm:]
+            return mirror, saved
         out.map_bf16 = mirror
         out.features_bf16 = self._feat_bf16 if mirror is not None else None
         return mirror, saved
+
+    def _obs_slot(self, out: TickOutputs, slot: int) -> torch.Tensor:
+        """The stored map observation of a tick slot (float32 tensor, or the bfloat16 rows with ``map_dtype="bf16"``)."""
+        return self._ring[slot] if self.map_dtype == "bf16" else out.map[slot]
 
     @torch.no_grad()
     def prime(self, out: TickOutputs, n_ticks: int, rows=None) -> None:
@@ -507,7 +541,7 @@ class RolloutCapture:
         finally:
             out.map_bf16, out.features_bf16 = saved
         self._draws += 1
-        self._carry = _Carry(out.map[n_ticks], out.features[n_ticks], rows[0][n_ticks], rows[1][n_ticks], rows[2][n_ticks])
+        self._carry = _Carry(self._obs_slot(out, n_ticks), out.features[n_ticks], rows[0][n_ticks], rows[1][n_ticks], rows[2][n_ticks])
 
     def build_graph(self, n_ticks: int, out: TickOutputs | None = None) -> "GraphedRollout":
         """Capture the whole ``n_ticks`` rollout (tick launches + policy steps + GAE) in ONE CUDA graph.
@@ -518,7 +552,7 @@ class RolloutCapture:
         replay continues the trajectory where the previous one stopped, and the first replay starts exactly where an
         eager ``capture`` on the same batch would.
         """
-        out = out or self.dev.alloc_outputs(capi.TL_PHASE_ALL, self.slots_for(n_ticks))
+        out = out or self.alloc_outputs(n_ticks)
         rows = self._new_rows(n_ticks)
         lib = capi.load_library()
         stream = torch.cuda.Stream(self.dev.device)
@@ -539,9 +573,11 @@ class RolloutCapture:
                 self.prime(out, n_ticks, rows)  # observation 0 and its action, into the slot / rows the replays carry over
             else:  # continue an eager trajectory: its last observation moves into the graph's carry slot
                 c = self._carry
-                out.map[n_ticks].copy_(c.map), out.features[n_ticks].copy_(c.features)
+                if self.map_dtype == "bf16":
+                    self._rows_ring(out.features.shape[0])
+                self._obs_slot(out, n_ticks).copy_(c.map), out.features[n_ticks].copy_(c.features)
                 rows[0][n_ticks].copy_(c.action), rows[1][n_ticks].copy_(c.log_prob), rows[2][n_ticks].copy_(c.value)
-                self._carry = _Carry(out.map[n_ticks], out.features[n_ticks], rows[0][n_ticks], rows[1][n_ticks], rows[2][n_ticks])
+                self._carry = _Carry(self._obs_slot(out, n_ticks), out.features[n_ticks], rows[0][n_ticks], rows[1][n_ticks], rows[2][n_ticks])
         torch.cuda.current_stream(self.dev.device).wait_stream(stream)
         torch.cuda.synchronize(self.dev.device)
         graph = torch.cuda.CUDAGraph()
@@ -554,16 +590,18 @@ class RolloutCapture:
     def capture(self, n_ticks: int, out: TickOutputs | None = None, rows=None) -> Rollout:
         """``n_ticks`` steps; ``out`` needs ``slots_for(n_ticks)`` tick slots (slot ``t`` = observation ``t``)."""
         dev = self.dev
-        out = out or dev.alloc_outputs(capi.TL_PHASE_ALL, self.slots_for(n_ticks))
-        if out.map is None or out.map.shape[0] < n_ticks + 1:
+        out = out or self.alloc_outputs(n_ticks)
+        if out.features is None or out.features.shape[0] < n_ticks + 1 or (self.map_dtype == "f32" and out.map is None):
             raise capi.TownletB200Error(f"a capture of {n_ticks} steps needs outputs with {n_ticks + 1} tick slots (slots_for)")
+        if self.map_dtype == "bf16":
+            self._rows_ring(out.features.shape[0])
         rows = rows or self._new_rows(n_ticks)
         actions, log_probs, values = rows
         if self._carry is None:
             self.prime(out, n_ticks, rows)
         c = self._carry
-        if c.map.data_ptr() != out.map[0].data_ptr():  # observation 0 = the last observation of the previous capture
-            out.map[0].copy_(c.map), out.features[0].copy_(c.features)
+        if c.map.data_ptr() != self._obs_slot(out, 0).data_ptr():  # observation 0 = the last observation of the previous capture
+            self._obs_slot(out, 0).copy_(c.map), out.features[0].copy_(c.features)
         actions[0].copy_(c.action), log_probs[0].copy_(c.log_prob), values[0].copy_(c.value)
         mirror, saved = self._with_mirrors(out)
         try:
@@ -573,10 +611,14 @@ class RolloutCapture:
         finally:
             out.map_bf16, out.features_bf16 = saved
         self._draws += n_ticks  # on the device: the next capture (or graph replay) draws fresh numbers
-        self._carry = _Carry(out.map[n_ticks], out.features[n_ticks], actions[n_ticks], log_probs[n_ticks], values[n_ticks])
+        self._carry = _Carry(self._obs_slot(out, n_ticks), out.features[n_ticks], actions[n_ticks], log_probs[n_ticks], values[n_ticks])
         rewards = out.reward[1 : n_ticks + 1]
         dones = out.terminated[1 : n_ticks + 1].float()
         # values[n_ticks] is the policy's value of the final observation: the bootstrap row of GAE
         advantages, returns = gae(rewards, values, dones, self.gamma, self.gae_lambda)
-        return Rollout(out.map[:n_ticks], out.features[:n_ticks], rewards, dones, values, actions[:n_ticks],
+        if self.map_dtype == "bf16":  # [T, N, C*W*W] bfloat16: the map columns of the stored rows
+            maps = self._ring[:n_ticks, :, : math.prod(dev.obs.map_shape)]
+        else:
+            maps = out.map[:n_ticks]
+        return Rollout(maps, out.features[:n_ticks], rewards, dones, values, actions[:n_ticks],
                        log_probs[:n_ticks], advantages, returns, out.kpi[1 : n_ticks + 1])
