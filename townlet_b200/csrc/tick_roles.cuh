@@ -430,7 +430,11 @@ __global__ void __launch_bounds__(32 * kRoleWarps, kRoleCtas) tick_kernel_roles(
 #pragma unroll
                         for (int k = 0; k < (kMapElems / 4 + 31) / 32; ++k) {
                             const int v = lane + 32 * k;
-                            if (v < kMapElems / 4) g4[v] = make_float4(k == 0 ? self0 : 0.0f, 0.0f, 0.0f, 0.0f);
+                            if (v < kMapElems / 4) {
+                                const float4 z = make_float4(k == 0 ? self0 : 0.0f, 0.0f, 0.0f, 0.0f);
+                                if (MIRROR) __stcs(g4 + v, z);  // streamed: the bfloat16 rows should be what stays in L2 for the policy step
+                                else g4[v] = z;
+                            }
                         }
                     } else {
                         const float* t = s_tmpl + p.tmpl_off[map_mis] + map_mis;
@@ -563,7 +567,10 @@ __global__ void __launch_bounds__(32 * kRoleWarps, kRoleCtas) tick_kernel_roles(
                 float4* g4 = reinterpret_cast<float4*>(feat_g0 + head);
                 const float4* s4 = reinterpret_cast<const float4*>(feat_s0 + head);
 #pragma unroll 4
-                for (int v = tid; v < nvec; v += 32 * kRoleWarps) g4[v] = s4[v];
+                for (int v = tid; v < nvec; v += 32 * kRoleWarps) {
+                    if (MIRROR) __stcs(g4 + v, s4[v]);
+                    else g4[v] = s4[v];
+                }
                 const int tail0 = head + (nvec << 2);
                 if (tid < total - tail0) feat_g0[tail0 + tid] = feat_s0[tail0 + tid];
             }
