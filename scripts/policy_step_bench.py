@@ -15,12 +15,14 @@ out = (torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, device="
 # "warm": the same 84 MB of input rows every launch (they stay in the 126 MB L2); "cold": four inputs in turn (336 MB), the
 # case of the rollout, where the tick kernel has just streamed 260 MB of observations through L2
 xs = [x] + [x.clone() for _ in range(3)]
-for pair, cold in ((0, 0), (0, 1), (1, 0), (1, 1), (0, 0), (0, 1)):
-    capi.set_option("policy_pair", pair)
+# forms: 0 single CTAs, 1 CTA pairs (cta_group::2), 2 clusters of two single-CTA pipelines sharing the weight stream (multicast)
+for pair, cold in ((0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1), (0, 0), (2, 0)):
+    capi.set_option("policy_pair", 1 if pair == 1 else 0)
+    capi.set_option("policy_multicast", 1 if pair == 2 else 0)
     for k in range(5): policy_step(xs[k % 4 if cold else 0], w, seed=1, out=out)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(200): policy_step(xs[k % 4 if cold else 0], w, seed=1, out=out)
     e1.record(); torch.cuda.synchronize()
-    print("pair", pair, "cold" if cold else "warm", "us per step", e0.elapsed_time(e1) * 1e3 / 200)
+    print("form", pair, "cold" if cold else "warm", "us per step", e0.elapsed_time(e1) * 1e3 / 200)

@@ -22,14 +22,18 @@ def _reference_heads(x: "np.ndarray", w) -> "np.ndarray":
     return (h2 @ w.w_heads.double().t() + w.b_heads.double()).float()
 
 
-@pytest.mark.parametrize("pair", [False, True], ids=["cta", "cta-pair"])
-@pytest.mark.parametrize("n_rows", [128, 1000, 65536 + 77])
-def test_fused_policy_step_matches_the_network(n_rows, pair, kernel_form) -> None:
+@pytest.mark.parametrize("form", ["cta", "cta-pair", "cta-multicast"])
+@pytest.mark.parametrize("n_rows", [128, 1000, 65536 + 77, 65536 + 200])
+def test_fused_policy_step_matches_the_network(n_rows, form, kernel_form) -> None:
     import torch
 
     from townlet_b200 import capi
 
-    capi.set_option("policy_pair", 1 if pair else 0)  # tcgen05 cta_group::2 over a cluster of two CTAs (reset by the fixture)
+    # cta-pair: tcgen05 cta_group::2 over a cluster of two CTAs; cta-multicast: two single-CTA pipelines sharing the weight
+    # stream by TMA multicast (65 736 rows = 514 tiles = an even count, 65 613 rows = 513: one CTA of the last pair runs a tile
+    # past the end).  Both options are reset by the fixture.
+    capi.set_option("policy_pair", 1 if form == "cta-pair" else 0)
+    capi.set_option("policy_multicast", 1 if form == "cta-multicast" else 0)
 
     from oracle.oracle import oracle_sample_actions
     from townlet_b200.params import ObsSpec

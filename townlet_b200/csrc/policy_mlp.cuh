@@ -241,9 +241,38 @@ __device__ __forceinline__ void policy_sample_row(const PolicyParams& p, long lo
     p.log_probs[r] = best_logp;
 }
 
-__global__ void __launch_bounds__(kPolThreads, 1)
-policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wm, const __grid_constant__ CUtensorMap map_wf,
-                  const __grid_constant__ CUtensorMap map_ws, const __grid_constant__ CUtensorMap map_wh, const PolicyParams p) {
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one box into the same shared-memory offset of both CTAs of a pair; each CTA's barrier (same offset) counts the bytes
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    const uint16_t mask = 3;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs of the pair
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
+// MC (policy_mlp_mc_kernel): the CTAs of a cluster of two run the same schedule on their own tiles and SHARE the weight stream:
+// each loads half of every weight chunk and multicasts it into both CTAs' rings, so a weight byte leaves L2 once per pair
+// (452 instead of 744 KB per tile and SM — the loads are what the single-CTA form waits for).  A stage is refilled when the
+// MMAs of BOTH CTAs have read it (every commit on `empty` goes to both CTAs); everything else stays per CTA.
+template <bool MC>
+__device__ __forceinline__ void policy_mlp_body(const CUtensorMap& map_x, const CUtensorMap& map_wm, const CUtensorMap& map_wf,
+                                                const CUtensorMap& map_ws, const CUtensorMap& map_wh, const PolicyParams& p) {
     extern __shared__ unsigned char pol_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pol_smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* s_b = smem + kPolSmemB;
@@ -260,11 +289,14 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (int)((p.n_rows + kPolRows - 1) / kPolRows);
-    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const int n_local = (int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...  (MC: both CTAs of a pair walk the same number of tiles — the
+    // shared weight ring keeps them in step — so the count is the pair's; a tile past the end loads zeros and writes nothing)
+    const uint32_t mc_rank = MC ? cluster_rank() : 0u;
+    const int n_local = MC ? ((int)blockIdx.x / 2 < (n_tiles + 1) / 2 ? ((n_tiles + 1) / 2 - 1 - (int)blockIdx.x / 2) / ((int)gridDim.x / 2) + 1 : 0)
+                           : ((int)blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0);
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kPolStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
+        for (int s = 0; s < kPolStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, MC ? 2 : 1);
         mbar_init(mma_done, 1);
         for (int k = 0; k < kHandoffs; ++k) mbar_init(h_ready + k, 32 * kPolEpiWarps);
         mbar_init(d3_read, 128);
@@ -280,7 +312,8 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (MC) cluster_sync_all();  // the peer multicasts into this CTA's ring and arrives on its barriers: initialised first
+    else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
@@ -306,7 +339,20 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     const int s = g % kPolStages;
                     if (g >= kPolStages) mbar_wait(empty + s, ((g / kPolStages) - 1) & 1);
                     unsigned char* b_dst = s_b + s * kPolBBytes;
-                    if (seg == ENC_A || seg == ENC_B) {
+                    if (MC) {
+                        // this CTA's half of the weight chunk (rows 128 r .. of 256; 8 r .. of the 16 head rows) into both rings;
+                        // the full barrier of each CTA counts the whole chunk: its own half and the peer's
+                        const bool heads = seg == HEADS, enc = seg == ENC_A || seg == ENC_B;
+                        const int half_rows = heads ? kPolHeads / 2 : kPolHidden / 2;
+                        mbar_expect_tx(full + s, (enc ? kPolABytes : 0) + 2 * half_rows * kPolKChunk * 2);
+                        tma_load_2d_mc(b_dst + mc_rank * half_rows * kPolKChunk * 2,
+                                       seg == ENC_A ? &map_wm : seg == ENC_B ? &map_wf : seg == SHARED ? &map_ws : &map_wh, full + s,
+                                       j * kPolKChunk, (int)mc_rank * half_rows);
+                        if (enc) {
+                            if (seg == ENC_A && j == 0 && it > 0) mbar_wait(mma_done, (3 * (it - 1) + 1) & 1);
+                            tma_load_2d(a_stage(s), &map_x, full + s, (seg == ENC_A ? 0 : kPolMapK) + j * kPolKChunk, row0);
+                        }
+                    } else if (seg == ENC_A || seg == ENC_B) {
                         mbar_expect_tx(full + s, kPolABytes + kPolBBytes);
                         tma_load_2d(b_dst, seg == ENC_A ? &map_wm : &map_wf, full + s, j * kPolKChunk, 0);
                         // the A stages alias the hidden buffer: the previous tile's shared layer must be done reading H1
@@ -367,7 +413,8 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < kPolKChunk / 16; ++k)  // UMMA K = 16 bf16 = 32 bytes along the swizzled row
                         umma_bf16(tmem + d_col, umma_desc_k128(a_addr + 32 * k), umma_desc_k128(b_addr + 32 * k), idesc, !(j == 0 && k == 0));
-                    umma_commit(empty + s);
+                    if (MC) umma_commit_mc(empty + s);  // the stage is free when both CTAs' MMAs have read it
+                    else umma_commit(empty + s);
                 }
                 if (seg != ENC_A) umma_commit(mma_done);  // completions per tile, in this order: encoders, shared layer, heads
             };
@@ -438,8 +485,21 @@ policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                               tw1 / n_local, te1 / n_local, tw2 / n_local, te2 / n_local, tw3 / n_local, te3 / n_local, n_local);)
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (MC) cluster_sync_all();  // the peer's multicast loads and commits may still target this CTA
+    else __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+__global__ void __launch_bounds__(kPolThreads, 1)
+policy_mlp_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wm, const __grid_constant__ CUtensorMap map_wf,
+                  const __grid_constant__ CUtensorMap map_ws, const __grid_constant__ CUtensorMap map_wh, const PolicyParams p) {
+    policy_mlp_body<false>(map_x, map_wm, map_wf, map_ws, map_wh, p);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPolThreads, 1)
+policy_mlp_mc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_wm, const __grid_constant__ CUtensorMap map_wf,
+                     const __grid_constant__ CUtensorMap map_ws, const __grid_constant__ CUtensorMap map_wh, const PolicyParams p) {
+    policy_mlp_body<true>(map_x, map_wm, map_wf, map_ws, map_wh, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -465,19 +525,10 @@ static_assert(kPairSmemBytes <= 227 * 1024, "shared memory of one SM");
 static_assert(kPairSmemA % 1024 == 0, "swizzled operand tiles are 1024-byte aligned");
 
 #define PAIR_PROXY_FENCE() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
 __device__ __forceinline__ uint32_t leader_addr(const void* local) {  // the same variable in the cluster's CTA 0
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(local)));
     return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -778,7 +829,8 @@ int tl_policy_step(const void* inputs, int64_t n_rows, int64_t input_row, const 
     const DeviceInfo* di = device_info(device);
     if (!di) return set_error("cudaDeviceGetAttribute failed"), TL_ERR_CUDA;
     const bool pair = g_opt.policy_pair.load() != 0;  // CTA pairs (cta_group::2): half the weight bytes per agent
-    const uint32_t w_rows = pair ? kPolHidden / 2 : kPolHidden, h_rows = pair ? kPolHeads / 2 : kPolHeads;
+    const bool mc = !pair && g_opt.policy_multicast.load() != 0;  // clusters of two sharing the weight stream by TMA multicast
+    const uint32_t w_rows = (pair || mc) ? kPolHidden / 2 : kPolHidden, h_rows = (pair || mc) ? kPolHeads / 2 : kPolHeads;
     CUtensorMap mx, mwm, mwf, mws, mwh;
     if (!make_bf16_map(&mx, inputs, (uint64_t)n_rows, kPolMapK + kPolFeatK, (uint64_t)input_row, kPolRows) ||
         !make_bf16_map(&mwm, w->w_map, kPolHidden, kPolMapK, kPolMapK, w_rows) ||
@@ -791,6 +843,7 @@ int tl_policy_step(const void* inputs, int64_t n_rows, int64_t input_row, const 
     std::call_once(once, [] {
         attr_rc = cudaFuncSetAttribute(policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPolSmemBytes);
         if (attr_rc == cudaSuccess) attr_rc = cudaFuncSetAttribute(policy_mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes);
+        if (attr_rc == cudaSuccess) attr_rc = cudaFuncSetAttribute(policy_mlp_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPolSmemBytes);
     });
     if (!cuda_ok(attr_rc, "cudaFuncSetAttribute(policy_mlp_kernel)")) return TL_ERR_CUDA;
     PolicyParams p;
@@ -803,6 +856,11 @@ int tl_policy_step(const void* inputs, int64_t n_rows, int64_t input_row, const 
         const long long max_pairs = di->sms / 2;
         const unsigned grid = 2u * (unsigned)(n_pairs < max_pairs ? n_pairs : max_pairs);
         policy_mlp_pair_kernel<<<grid, kPolThreads, kPairSmemBytes, (cudaStream_t)stream>>>(mx, mwm, mwf, mws, mwh, p);
+    } else if (mc) {
+        const long long n_pairs = ((n_rows + kPolRows - 1) / kPolRows + 1) / 2;
+        const long long max_pairs = di->sms / 2;
+        const unsigned grid = 2u * (unsigned)(n_pairs < max_pairs ? n_pairs : max_pairs);
+        policy_mlp_mc_kernel<<<grid, kPolThreads, kPolSmemBytes, (cudaStream_t)stream>>>(mx, mwm, mwf, mws, mwh, p);
     } else {
         const long long n_tiles = (n_rows + kPolRows - 1) / kPolRows;
         const unsigned grid = (unsigned)(n_tiles < di->sms ? n_tiles : di->sms);

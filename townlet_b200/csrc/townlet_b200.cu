@@ -507,6 +507,7 @@ struct Options {
     std::atomic<int> even_grid{1};      // round small grids up to a multiple of the SM count
     std::atomic<int> stream_stores{0};  // host expander: non-temporal stores into the caller's float32 map
     std::atomic<int> policy_pair{0};    // tl_policy_step: CTA pairs (tcgen05 cta_group::2) instead of single CTAs
+    std::atomic<int> policy_multicast{0};  // tl_policy_step: clusters of two single-CTA pipelines sharing the weight stream (TMA multicast)
 };
 Options g_opt;
 
@@ -935,6 +936,8 @@ int tl_set_option(const char* name, int32_t value) {
     else if (!strcmp(name, "even_grid")) slot = &g_opt.even_grid;
     else if (!strcmp(name, "stream_stores")) slot = &g_opt.stream_stores;
     else if (!strcmp(name, "policy_pair")) slot = &g_opt.policy_pair;
+    else if (!strcmp(name, "policy_multicast")) slot = &g_opt.policy_multicast;
+    else if (!strcmp(name, "policy_multicast")) slot = &g_opt.policy_multicast;
     if (!slot) return set_error("tl_set_option: unknown option '%s'", name), TL_ERR_ARG;
     if (slot == &g_opt.kernel_form && (value < -1 || value > 1)) return set_error("kernel_form is -1, 0 or 1"), TL_ERR_ARG;
     if (slot == &g_opt.pass_agents && (value < 0 || value > 32)) return set_error("pass_agents is 0..32"), TL_ERR_ARG;
@@ -952,6 +955,7 @@ void tl_reset_options(void) {
     g_opt.even_grid.store(1);
     g_opt.stream_stores.store(0);
     g_opt.policy_pair.store(0);
+    g_opt.policy_multicast.store(0);
 }
 
 // ---- planned launches -----------------------------------------------------------
