@@ -41,8 +41,11 @@ constexpr int kTileWarps = TL_TILE_WARPS;  // warps in the tiles role
 constexpr int kRoleWarps = 2 + kTileWarps;
 constexpr int kRoleCtas = 512 / (32 * kRoleWarps);  // resident CTAs per SM the register budget is set for (128 registers)
 
+// (the instances that also write the policy's bfloat16 rows take 96 registers and a fifth resident CTA per SM: their batches are
+// rollout-sized, several waves of CTAs per tick: +1.7 % on configs[4], +3.6 % with bfloat16-only map rows; on configs[1], whose grid
+// is one wave of four CTAs per SM, the same trade measured -9 %)
 template <int VARIANT, int WT, bool WORLD, bool MIRROR = false>
-__global__ void __launch_bounds__(32 * kRoleWarps, kRoleCtas) tick_kernel_roles(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(32 * kRoleWarps, MIRROR ? kRoleCtas + 1 : kRoleCtas) tick_kernel_roles(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     float* s_feat = reinterpret_cast<float*>(smem + p.off_feat);  // [2][chunk * F + 4]
     float* s_tmpl = reinterpret_cast<float*>(smem + p.off_map);
