@@ -17,8 +17,12 @@
 // Warp roles: warp 0 issues the TMA loads, warp 1 the MMAs (one elected lane), warps 2-9 are the epilogue (TMEM lane
 // quarter = warp index mod 4, two warps per quarter splitting a layer's columns).  CTAs are persistent: each walks the
 // tiles blockIdx.x, blockIdx.x + gridDim.x, ... so that tensor-memory allocation, barrier set-up and descriptor fetches
-// are paid once and the weight loads of the next tile run under the sampling epilogue of the previous one.  Arithmetic:
-// bfloat16 operands, float32 accumulation, bias / ReLU in float32, hidden activations rounded to bfloat16 — the arithmetic of the bfloat16 autocast path it replaces.
+// are paid once, and the schedule is software-pipelined over the CTA's tiles (the tensor pipe works on tile i + 1 while the
+// epilogue converts and samples tile i; accumulator columns ping-pong with the tile's parity).  Arithmetic: bfloat16
+// operands, float32 accumulation, bias in float32, ReLU on the rounded bfloat16 pair (same result), hidden activations
+// rounded to bfloat16 — the arithmetic of the bfloat16 autocast path it replaces.
+// Three forms (tl_set_option): policy_mlp_kernel (default), policy_mlp_mc_kernel (clusters of two sharing the weight stream
+// by TMA multicast), policy_mlp_pair_kernel (CTA pairs, tcgen05 cta_group::2).  DESIGN.md 5b has what each measures and why.
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -26,7 +30,8 @@
 namespace {
 
 // -DTL_POLICY_TIMING: CTA 0 prints the cycles its first epilogue warp spends per tile waiting for each accumulator and
-// converting it (scripts/policy_step_bench.py with an instrumented build; never part of the shipped library)
+// converting it, and the MMA-issuing lane what it waits for (scripts/policy_phase_timing.py with an instrumented build; never
+// part of the shipped library)
 #ifdef TL_POLICY_TIMING
 #define POL_TIMING(...) __VA_ARGS__
 #else
