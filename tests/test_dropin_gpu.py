@@ -160,3 +160,53 @@ def test_parallel_env_applies_action_words_on_the_device() -> None:
         np.testing.assert_allclose(rewards.cpu().numpy(), ref["reward"][0], rtol=1e-6, atol=1e-9)
     state = env.state().download_state()
     assert np.array_equal(state.pos, ref_batch.pos) and np.array_equal(state.riv_score, ref_batch.riv_score)
+
+
+def test_env_step_loop_with_employment_and_reservation_refresh() -> None:
+    """The env's tick = shift state machine (tl_employment_step) for the coming tick, then actions, reservation refresh, ledger decay,
+    need decay, reward and observation in one launch — against the oracle doing the same on the host, tick by tick."""
+    import torch
+
+    from oracle.oracle import oracle_employment_step, oracle_tick
+    from townlet_b200.employment import EmploymentArrays, EmploymentSpec
+    from townlet_b200.env import TownletParallelEnv
+    from townlet_b200.params import DynamicsSpec
+    from townlet_b200.synth import random_actions, synth_batch
+
+    obs, rew, dyn = ObsSpec(), RewardSpec(fuse_faint=True), DynamicsSpec()
+    rng = np.random.default_rng(4)
+    batch = synth_batch(30, 16, 7, obs, device_reservations=True)
+    batch.town_tick[:] = rng.integers(0, 50, batch.n_towns)
+    spec = EmploymentSpec(
+        job_ids=("a", "b", "c"), job_start=(10, 25, 40), job_end=(30, 45, 40), job_wage=(0.02, 0.03, 0.01), job_lateness_penalty=(0.1, 0.2, 0.0),
+        job_location=((3, 3), None, (7, 2)), arrival_buffer=4, ticks_per_day=60, grace_ticks=2, absent_cutoff=9, absence_slack=4,
+        attendance_window=3, late_tick_penalty=0.005, absence_penalty=0.2,
+    )
+    arrays = EmploymentArrays(batch.n_agents)
+    arrays.job[:] = rng.integers(-1, 3, batch.n_agents)
+    env = TownletParallelEnv(batch, obs, rew, dyn=dyn, employment=(spec, arrays))
+    ref_batch, ref_arrays = batch.copy(), arrays.copy()
+    env.reset()
+    phases = capi.TL_PHASE_WORLD | capi.TL_PHASE_RESERVATIONS
+    seen_events = 0
+    for t in range(40):
+        words = random_actions(ref_batch, 1, seed=100 + t)
+        observations, reward, terminations, _, infos = env.step(torch.from_numpy(words[0].view(np.int32)).cuda())
+        torch.cuda.synchronize()
+        want_events = oracle_employment_step(ref_batch, spec, ref_arrays, 1, 1)
+        ref = oracle_tick(ref_batch, obs, rew, phases, 1, dyn=dyn, actions=words)
+        assert np.array_equal(infos["employment_events"].cpu().numpy().view(np.uint32), want_events[0]), t
+        assert np.array_equal(observations["map"].cpu().numpy(), ref["map"][0]), t
+        assert np.array_equal(observations["features"].cpu().numpy().view(np.uint32), ref["features"][0].view(np.uint32)), t
+        np.testing.assert_allclose(reward.cpu().numpy(), ref["reward"][0], rtol=1e-6, atol=1e-9)
+        assert np.array_equal(terminations.cpu().numpy(), ref["terminated"][0].astype(bool)), t
+        seen_events |= int(np.bitwise_or.reduce(want_events, axis=None))
+    state = env.state().download_state(full=True)
+    assert np.array_equal(state.arena, ref_batch.arena)
+    got = env.employment_state().download()
+    for name, _, _ in capi.EMPLOYMENT_STATE_FIELDS:
+        assert np.array_equal(got.arrays[name], ref_arrays.arrays[name]), name
+    assert seen_events != 0  # shifts started, ran late or were missed along the way
+    # reset restores towns and employment context
+    env.reset()
+    assert np.array_equal(env.employment_state().download().arrays["state"], arrays.arrays["state"])
