@@ -535,8 +535,9 @@ __device__ __forceinline__ uint32_t leader_addr(const void* local) {  // the sam
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(local)));
     return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// remote arrival with the default (CTA-scope) release: no cluster-scope membar (the data it publishes sits in shared memory)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -574,10 +575,10 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     uint64_t* full = bars;                        // [stages] leader: both CTAs' loads of the stage have landed
     uint64_t* empty = bars + kPairStages;         // [stages] each CTA: the MMAs that read the stage are done
     uint64_t* mma_done = bars + 2 * kPairStages;  // each CTA: a layer's accumulator is complete (three times per tile)
-    uint64_t* h_local = mma_done + 1;             // [kHandoffs] each CTA: its own epilogue has written a part of the next A operand
-    uint64_t* d3_local = h_local + kHandoffs;     // each CTA: its own epilogue has read the heads accumulator
-    uint64_t* peer_h = d3_local + 1;              // [kHandoffs] leader: the peer's h_local phases, forwarded by the peer's relay lane
-    uint64_t* peer_d3 = peer_h + kHandoffs;       // leader: the peer's d3_local phase, forwarded likewise
+    uint64_t* h_local = mma_done + 1;             // [kHandoffs] leader: its own epilogue has written a part of the next A operand
+    uint64_t* d3_local = h_local + kHandoffs;     // leader: its own epilogue has read the heads accumulator
+    uint64_t* peer_h = d3_local + 1;              // [kHandoffs] leader: the same from the peer's epilogue warps (remote arrivals)
+    uint64_t* peer_d3 = peer_h + kHandoffs;       // leader: the peer's heads read
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_d3 + 1);
     float* s_bias = reinterpret_cast<float*>(smem + kPairSmemBias);  // [0, 512) encoders, [512, 768) shared layer
 
@@ -591,9 +592,9 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kPairStages; ++s) mbar_init(full + s, 1), mbar_init(empty + s, 1);
         mbar_init(mma_done, 1);
-        for (int k = 0; k < kHandoffs; ++k) mbar_init(h_local + k, kPolEpiWarps), mbar_init(peer_h + k, 1);  // one elected lane per epilogue warp
+        for (int k = 0; k < kHandoffs; ++k) mbar_init(h_local + k, kPolEpiWarps), mbar_init(peer_h + k, kPolEpiWarps);  // one elected lane per epilogue warp
         mbar_init(d3_local, 4);
-        mbar_init(peer_d3, 1);
+        mbar_init(peer_d3, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wm) : "memory");
@@ -710,21 +711,6 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             }
             POL_TIMING(if (blockIdx.x == 0) printf("TL_POLICY_TIMING pair MMA issuer cycles per tile: total %lld, waiting for TMA %lld, for the epilogues' operands %lld, for the heads reads %lld\n",
                                                    (clock64() - m_t0) / n_local, m_full / n_local, m_h / n_local, m_d3 / n_local);)
-        } else if (!leader && lane == 0) {
-            // ================= relay (the same lane of the peer CTA, otherwise idle) =================
-            // The peer's epilogue warps arrive on their OWN CTA's barriers (CTA-scope release, cheap); this lane follows those
-            // phases and forwards each with one cluster-scope arrival on the leader's barrier.  A cluster-scope release is a
-            // membar that waits for the thread's outstanding global stores as well: executed by the epilogue warps (with the
-            // sampled actions still in flight) it cost them ~3 k cycles per tile.
-            const uint32_t peer_d3_leader = leader_addr(peer_d3);
-            for (int it = 0; it < n_local; ++it) {
-                for (int k = 0; k < kHandoffs; ++k) {
-                    mbar_wait(h_local + k, it & 1);
-                    mbar_arrive_cluster(leader_addr(peer_h + k));
-                }
-                mbar_wait(d3_local, it & 1);
-                mbar_arrive_cluster(peer_d3_leader);
-            }
         }
     } else {
         // ================= epilogue: warps 2-9 of both CTAs, one thread per row and column half =================
@@ -735,12 +721,18 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         uint32_t hv[16];           // the heads accumulator of the previous tile's row, sampled under the next tile's shared layer
         long long pending_r = -1;  // (-1: nothing pending)
         // This warp's part of an operand is written: every lane fences its generic-proxy stores towards the async proxy (the
-        // pair's MMA), the warp synchronises, ONE lane arrives on this CTA's barrier.
+        // pair's MMA), the warp synchronises, ONE lane arrives on the leader's barrier — the peer's across the cluster, with the
+        // default CTA-scope release (the 2-SM kernels of CUTLASS signal operand hand-offs the same way): a cluster-scope release
+        // is a membar that also waits for the thread's outstanding global stores (the sampled actions) and cost the epilogue
+        // warps ~3 k cycles per tile; the data published here sits in shared memory, written before the arrival is sent.
         auto arrive_warp = [&](uint64_t* bar) {
             PAIR_PROXY_FENCE();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar);
+            if (lane == 0) {
+                if (leader) mbar_arrive(bar);
+                else mbar_arrive_remote(leader_addr(peer_h + (bar - h_local)));
+            }
         };
         POL_TIMING(long long tw1 = 0, te1 = 0, tw2 = 0, te2 = 0, tw3 = 0, te3 = 0, tc = clock64(), tn;)
         for (int it = 0; it < n_local; ++it) {
@@ -774,7 +766,10 @@ policy_mlp_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             tmem_ld16(trow + P, hv);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(d3_local);
+            if (lane == 0) {
+                if (leader) mbar_arrive(d3_local);
+                else mbar_arrive_remote(leader_addr(peer_d3));
+            }
             pending_r = r;
         }
         if (pending_r >= 0 && pending_r < p.n_rows) policy_sample_row(p, pending_r, hv);
