@@ -495,10 +495,10 @@ int tl_plan_grid(const TlPlan* plan, int32_t* grid, int32_t* threads, int32_t* s
  *   "generic_window"  1 = runtime-window kernels instead of the compile-time window specialisations
  *   "mirror_pass"     1 = bfloat16 mirrors by a cast pass after the launch instead of inside the kernel
  *   "even_grid"       0 = do not round small grids up to a multiple of the SM count (default 1)
- *   "policy_pair"     1 = tl_policy_step runs CTA pairs (a cluster of two, tcgen05 cta_group::2: each CTA stages half of every
- *                     weight chunk); 0 = single CTAs
+ *   "policy_pair"     1 (default) = tl_policy_step runs CTA pairs (a cluster of two, tcgen05 cta_group::2: each CTA stages half
+ *                     of every weight chunk); 0 = single CTAs
  *   "policy_multicast" 1 = tl_policy_step runs clusters of two single-CTA pipelines that share the weight stream: each CTA
- *                     loads half of every weight chunk and TMA-multicasts it into both rings (ignored with policy_pair)
+ *                     loads half of every weight chunk and TMA-multicasts it into both rings (with policy_pair = 0 only)
  *   "stream_stores"   1 = the host expander of the narrow wire formats writes the float32 map with non-temporal
  *                     stores (default 0: ordinary stores, the rows stay in the last-level cache for the consumer)
  */

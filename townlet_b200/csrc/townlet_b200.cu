@@ -506,7 +506,7 @@ struct Options {
     std::atomic<int> mirror_pass{0};    // 1 = bfloat16 mirrors by a cast pass after the launch instead of inside the kernel
     std::atomic<int> even_grid{1};      // round small grids up to a multiple of the SM count
     std::atomic<int> stream_stores{0};  // host expander: non-temporal stores into the caller's float32 map
-    std::atomic<int> policy_pair{0};    // tl_policy_step: CTA pairs (tcgen05 cta_group::2) instead of single CTAs
+    std::atomic<int> policy_pair{1};    // tl_policy_step: CTA pairs (tcgen05 cta_group::2, the fastest form); 0 = single CTAs
     std::atomic<int> policy_multicast{0};  // tl_policy_step: clusters of two single-CTA pipelines sharing the weight stream (TMA multicast)
 };
 Options g_opt;
@@ -954,7 +954,7 @@ void tl_reset_options(void) {
     g_opt.mirror_pass.store(0);
     g_opt.even_grid.store(1);
     g_opt.stream_stores.store(0);
-    g_opt.policy_pair.store(0);
+    g_opt.policy_pair.store(1);
     g_opt.policy_multicast.store(0);
 }
 
